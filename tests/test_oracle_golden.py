@@ -1,0 +1,265 @@
+"""Pins oracle/spaa_oracle.py against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+produced by tests/golden/make_golden.py in the build container).  CPU only."""
+import io
+import contextlib
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import spaa_oracle as O
+
+torch.set_num_threads(4)
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, atol, rtol=0.0, what=""):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    nan_a, nan_b = torch.isnan(a), torch.isnan(b)
+    assert torch.equal(nan_a, nan_b), what + " NaN pattern differs"
+    err = ((a - b).abs() - rtol * b.abs())[~nan_a]
+    assert err.numel() == 0 or err.max().item() <= atol, f"{what}: max err {((a - b).abs())[~nan_a].max().item():.3e}"
+
+
+@pytest.mark.parametrize("tag", ["rand", "edge"])
+def test_colour_forward_backward(golden, tag):
+    g = golden("colour")
+    x = T(g[tag + "_x"]).requires_grad_(True)
+    y = T(g[tag + "_y"]).requires_grad_(True)
+    lx, ly = O.srgb_to_lab(x), O.srgb_to_lab(y)
+    close(lx, g[tag + "_labx"], 1e-4, 1e-6, "labx")   # a=500(fx-fy): 1 ulp of f is 6e-5
+    close(ly, g[tag + "_laby"], 1e-4, 1e-6, "laby")
+    de = O.de2000_variant(lx, ly)
+    close(de, g[tag + "_de"], 2e-5, 1e-5, "de")
+    gx, gy = torch.autograd.grad((de * T(g[tag + "_cot"])).sum(), (x, y))
+    # The hue of a near-neutral colour (chroma ~1e-3, e.g. gray 0.5 -> a=0.0011,b=-0.0022) is ill-conditioned
+    # in fp32: the reference's own gradient there carries O(10%) rounding noise.  Such pixels get a loose
+    # bound, all others a tight one.
+    chroma = torch.minimum(lx[:, 1:].detach().norm(dim=1), ly[:, 1:].detach().norm(dim=1))
+    ok = (chroma > 0.5).unsqueeze(1).expand_as(gx)
+    for got, ref, nm in ((gx, T(g[tag + "_gx"]), "gx"), (gy, T(g[tag + "_gy"]), "gy")):
+        close(got[ok], ref[ok], 1e-3, 1e-4, nm)
+        close(got[~ok], ref[~ok], 1e-3, 0.5, nm + " near-neutral")
+
+
+def test_colour_known_answers(golden):
+    g = golden("colour")
+    lab = lambda *v: torch.tensor(v, dtype=torch.float32).view(1, 3, 1, 1)
+    close(O.de2000_variant(lab(50, 2.5, 0), lab(73, 25, -18)), g["kat_27"], 1e-5)
+    assert abs(float(g["kat_27"].ravel()[0]) - 27.1470) < 1e-3           # SURVEY 8c probe
+    close(O.de2000_variant(lab(50, 0, 0), lab(50, -1, 2)), g["kat_neutral"], 0)
+    assert float(g["kat_neutral"].ravel()[0]) == 0.0
+    px = lambda *v: torch.tensor(v, dtype=torch.float32).view(1, 3, 1, 1)
+    w = O.srgb_to_lab(px(1, 1, 1)).flatten()
+    assert abs(w[0] - 100) < 1e-3 and abs(w[1] - 0.00197) < 2e-4 and abs(w[2] + 0.00367) < 2e-4
+    assert torch.allclose(O.srgb_to_lab(px(0, 0, 0)).flatten(), torch.tensor([-16., 0., 0.]))
+    a = synth.rand(11, "col.a", (2, 3, 10, 12))
+    b = (a + synth.randn(12, "col.b", (2, 3, 10, 12), 0.08)).clamp(0, 1)
+    assert abs(O.mean_delta_e(a, b) - float(g["mean_de"])) < 1e-4
+    x = a.clone().requires_grad_(True)
+    de = O.de2000_variant(O.srgb_to_lab(x), O.srgb_to_lab(a))
+    assert float(de.abs().max()) == 0.0
+    gx, = torch.autograd.grad(de.sum(), x)
+    assert torch.isfinite(gx).all() and float(gx.abs().max()) == 0.0
+
+
+def test_tps_and_warp(golden):
+    g = golden("warp")
+    P = synth.warping_params(21)
+    close(O.uniform_ctrl((6, 6)), g["uniform_grid"], 0)
+    close(O.tps_sampling_grid(P["warping_net.theta"], P["warping_net.ctrl_pts"], 12, 16), g["tps_grid"], 1e-6)
+    Pg = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "ctrl" not in k) for k, v in P.items()}
+    x = synth.textured(22, "warp.x", (2, 3, 20, 20)).requires_grad_(True)
+    y = O.warp(Pg, x, (12, 16))
+    close(y, g["y"], 1e-6)
+    cot = synth.randn(23, "warp.cot", y.shape)
+    names = [k for k in Pg if Pg[k].requires_grad]
+    grads = torch.autograd.grad((y * cot).sum(), [x] + [Pg[k] for k in names])
+    close(grads[0], g["gx"], 1e-5, 1e-5)
+    for n, gr in zip(names, grads[1:]):
+        close(gr, g["g_" + n[len("warping_net."):]], 2e-4, 1e-4, n)
+    with torch.no_grad():
+        close(O.warping_fine_grid(P, (20, 20), (12, 16)), g["fine_grid"], 1e-6)
+        close(O.warp(P, x, (12, 16), with_refine=False), g["y_norefine"], 1e-6)
+        # explicit bilinear restatement == ATen grid_sample
+        grid = O.warping_fine_grid(P, (20, 20), (12, 16)).expand(2, -1, -1, -1) * 1.3
+        close(O.bilinear_sample(x, grid), torch.nn.functional.grid_sample(x, grid, align_corners=True), 1e-6)
+        th = P["warping_net.affine_mat"]
+        close(O.affine_base_grid(th, 20, 20), torch.nn.functional.affine_grid(th, (1, 3, 20, 20), align_corners=True), 1e-6)
+
+
+def test_models(golden):
+    g = golden("models")
+    cam_hw, prj_hw = (24, 32), (32, 32)
+    P = synth.pcnet_params(31, cam_hw)
+    Pg = {k: v.clone().requires_grad_(k not in ("mask", "warping_net.ctrl_pts")) for k, v in P.items()}
+    prj = synth.textured(32, "pc.prj", (2, 3, *prj_hw)).requires_grad_(True)
+    scene = synth.textured(33, "pc.s", (1, 3, *cam_hw)).expand(2, -1, -1, -1)
+    y = O.pcnet(Pg, prj, scene, cam_hw)
+    close(y, g["pcnet_y"], 1e-6)
+    cot = synth.randn(34, "pc.cot", y.shape)
+    names = [k for k in Pg if Pg[k].requires_grad]
+    grads = torch.autograd.grad((y * cot).sum(), [prj] + [Pg[k] for k in names])
+    close(grads[0], g["pcnet_gprj"], 1e-5, 1e-4)
+    for n, gr in zip(names, grads[1:]):
+        if "pcnet_g_" + n in g:
+            close(gr, g["pcnet_g_" + n], 1e-3, 1e-3, n)
+        else:
+            ref_abs = float(g["pcnet_gabs_" + n][0])
+            assert abs(float(gr.double().sum()) - float(g["pcnet_gsum_" + n][0])) <= 1e-4 * ref_abs + 1e-4, n
+            assert abs(float(gr.double().abs().sum()) - ref_abs) <= 1e-4 * ref_abs + 1e-4, n
+    with torch.no_grad():
+        x = synth.textured(35, "sn.x", (2, 3, *cam_hw))
+        close(O.shading_net(P, x, scene, x * scene), g["shading_y"], 1e-6)
+        Pn = synth.pcnet_params(36, cam_hw, use_rough=False)
+        close(O.pcnet(Pn, prj, scene, cam_hw, use_rough=False), g["pcnet_norough_y"], 1e-6)
+        close(O.pcnet(P, prj, scene, cam_hw), g["pcnet_simplified_warp_y"], 1e-6)
+    C = synth.compennet_pp_params(37)
+    cam = synth.textured(38, "cpp.cam", (2, 3, *cam_hw)).requires_grad_(True)
+    yc = O.compennet_pp(C, cam, scene, prj_hw)
+    close(yc, g["cpp_y"], 1e-6)
+    gc, = torch.autograd.grad((yc * synth.randn(39, "cpp.cot", yc.shape)).sum(), cam)
+    close(gc, g["cpp_gcam"], 1e-5, 1e-4)
+
+
+def test_losses(golden):
+    g = golden("loss")
+    a = synth.textured(41, "loss.a", (2, 3, 24, 32)).requires_grad_(True)
+    b = (a.detach() + synth.randn(42, "loss.b", a.shape, 0.1)).clamp(0, 1)
+    for opt in ("l1", "l1+ssim", "l1+l2+ssim", "l2+huber", "ssim"):
+        loss, l2 = O.training_loss(a, b, opt)
+        gr, = torch.autograd.grad(loss, a)
+        key = opt.replace("+", "_")
+        close(loss, g[key + "_loss"], 1e-6, 0, opt)
+        close(l2, g[key + "_l2"], 1e-7, 0, opt)
+        close(gr, g[key + "_g"], 1e-7, 1e-4, opt)
+    with torch.no_grad():
+        close(O.ssim_index(a, b), g["ssim_fn"], 1e-6)
+        close(O.ssim_index(a, b, size_average=False), g["ssim_per_sample"], 1e-6)
+        w = O.gauss_window()
+        close((w[:, None] @ w[None, :]).view(1, 1, 11, 11), g["window"], 1e-9)
+    with pytest.raises(TypeError):
+        O.training_loss(a, b, "")
+
+
+def test_classifier_preprocess(golden):
+    g = golden("classifier")
+    im = synth.textured(51, "clf.im", (2, 3, 24, 32))
+    for sz in (20, 30, 24):
+        close(O.classifier_preprocess(im, (24, 24), (sz, sz)), g[f"pre_{sz}"], 1e-6)
+    logits, p, idx = O.classify(synth.TinyClassifier(0), im, (24, 24), (20, 20))
+    close(logits, g["tiny_logits"], 1e-4)
+    close(p, g["tiny_p"], 1e-6)
+    assert np.array_equal(idx[:, :5].numpy(), g["tiny_idx"][:, :5])
+    assert O.crop_center(torch.zeros(1, 3, 240, 320), (240, 240)).shape[-2:] == (240, 240)
+    assert O.to_4d(torch.zeros(5, 6)).shape == (1, 1, 5, 6)
+
+
+def _tiny_clf(seed):
+    m = synth.TinyClassifier(seed)
+    return lambda im: O.classify(m, im, (24, 24), (20, 20))
+
+
+def test_spaa_loop(golden):
+    g = golden("spaa")
+    cam_hw = (24, 32)
+    P = synth.pcnet_params(61, cam_hw)
+    scene = synth.textured(62, "spaa.scene", (1, 3, *cam_hw))
+    pc = lambda x, s: O.pcnet(P, x, s, cam_hw)
+    clf = _tiny_clf(1)
+    targets = list(synth.SPAA_TARGETS10[:8])
+    for tag, iters, loss, d_thr in (("t12", 12, "camdE_caml2", 2.0), ("t50", 50, "camdE", 3.0)):
+        trace = []
+        cam_best, prj_best = O.spaa_attack(pc, clf, targets, True, scene, d_thr, loss, (32, 32), 0.5, iters, trace=trace)
+        samp = torch.stack([trace[i]["prj_in"][:2].clamp(0, 1) for i in (1, iters // 2, iters - 1)])
+        tol = 1e-4 if iters <= 12 else 2e-3      # free-running fp32 drift grows with the iteration count
+        close(samp, g[tag + "_prj_in_sample"], tol, 0, tag + " trajectory")
+        close(trace[-1]["prj_in"].clamp(0, 1), g[tag + "_prj_last"], tol, 0, tag + " last prj")
+        close(trace[-1]["cam"], g[tag + "_cam_last"], tol, 0, tag + " last cam")
+        close(cam_best, g[tag + "_cam_best"], tol, 0, tag + " cam_best")
+        close(prj_best, g[tag + "_prj_best"], tol, 0, tag + " prj_best")
+    true_idx = int(g["u10_true_idx"])
+    assert int(clf(scene)[2][0, 0]) == true_idx
+    cam_best, prj_best = O.spaa_attack(pc, clf, [true_idx], False, scene, 1.0, "prjl2_caml2_camdE", (32, 32), 0.5, 10)
+    close(cam_best, g["u10_cam_best"], 1e-4)
+    close(prj_best, g["u10_prj_best"], 1e-4)
+
+
+def test_percal_loop(golden):
+    g = golden("percal")
+    cam_hw, prj_hw = (24, 32), (32, 32)
+    scene = synth.textured(71, "pa.scene", (1, 3, *cam_hw))
+    clf = _tiny_clf(2)
+    targets = torch.tensor(list(synth.SPAA_TARGETS10[:8]))
+    xb = O.perc_al_attack(clf, scene.expand(8, -1, -1, -1), targets, 2.0, True, max_iterations=15)
+    close(xb, g["t15_best"], 1e-6)
+    true_idx = int(g["u15_true_idx"])
+    xu = O.perc_al_attack(clf, scene, torch.tensor([true_idx]), 2.0, False, max_iterations=15, confidence=40)
+    close(xu, g["u15_best"], 1e-6)
+    C = synth.compennet_pp_params(72)
+    cam_best, prj_best = O.perc_al_compennet_pp_attack(lambda x, s: O.compennet_pp(C, x, s, prj_hw), clf, [true_idx],
+                                                       False, scene, 2.0)
+    close(cam_best, g["full_cam_best"], 1e-6)
+    close(prj_best, g["full_prj_best"], 1e-5)
+    with pytest.raises(ValueError):
+        O.perc_al_attack(clf, scene + 1, torch.tensor([0]), 2.0, False)
+
+
+def _train(P, fwd, data_in, data_gt, scene, groups, n_steps, batch, N, seed, loss_name_fn, lr_fn):
+    params = {k: v.clone().requires_grad_(True) for k, v in P.items() if k not in ("mask", "warping_net.ctrl_pts")}
+    const = {k: v for k, v in P.items() if k not in params}
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in params.items()}
+    random.seed(seed)
+    losses = []
+    for it in range(n_steps):
+        idx = random.sample(range(N), batch)
+        full = dict(const, **params)
+        pred = fwd(full, data_in[idx], scene.expand(batch, -1, -1, -1))
+        loss, _ = O.training_loss(pred, data_gt[idx], loss_name_fn(it))
+        names = list(params)
+        grads = torch.autograd.grad(loss, [params[n] for n in names])
+        losses.append(float(loss))
+        with torch.no_grad():
+            for n, gr in zip(names, grads):
+                lr, wd = lr_fn(n, it)
+                O.adam_step(params[n], gr, state[n][0], state[n][1], it + 1, lr, wd)
+    return losses, {k: v.detach() for k, v in params.items()}
+
+
+def test_training_steps(golden):
+    g = golden("train")
+    cam_hw, prj_hw, N = (24, 32), (32, 32), 6
+    prj_train = synth.textured(82, "tr.prj", (N, 3, *prj_hw))
+    scene = synth.textured(83, "tr.scene", (1, 3, *cam_hw))
+    cam_train = synth.textured(84, "tr.cam", (N, 3, *cam_hw))
+    P = synth.pcnet_params(81, cam_hw)
+    g1, g2, g3 = O.pcnet_param_groups([k for k in P if k not in ("mask", "warping_net.ctrl_pts")])
+
+    def lr_fn(n, it):
+        if n in g1:
+            return O.multistep_lr(1e-2, it, [100], 0.2), 0.0
+        if n in g2:
+            return O.multistep_lr(5e-3, it, [1200], 0.2), 0.0
+        return O.multistep_lr(1e-3, it, [1800], 0.2), 1e-4
+    losses, after = _train(P, lambda p, x, s: O.pcnet(p, x, s, cam_hw), prj_train, cam_train, scene, None, 3, 4, N, 5,
+                           O.pcnet_loss_name, lr_fn)
+    assert np.allclose(losses, g["pcnet_losses"], atol=2e-4), (losses, g["pcnet_losses"])
+    for k, v in after.items():
+        if "pcnet_after_" + k in g:
+            close(v, g["pcnet_after_" + k], 2e-4, 0, k)
+        else:
+            d = float((v - P[k]).double().abs().sum())
+            assert abs(d - float(g["pcnet_afterdelta_" + k][0])) <= 0.02 * d + 1e-6, k
+    C = synth.compennet_pp_params(85)
+    losses, after = _train(C, lambda p, x, s: O.compennet_pp(p, x, s, prj_hw), cam_train, prj_train, scene, None, 3, 4, N,
+                           6, lambda it: "l1+ssim", lambda n, it: (1e-3, 1e-4))
+    assert np.allclose(losses, g["cpp_losses"], atol=2e-4), (losses, g["cpp_losses"])
+    for k, v in after.items():
+        if "cpp_after_" + k in g:
+            close(v, g["cpp_after_" + k], 2e-4, 0, k)
