@@ -1,0 +1,225 @@
+/* spaa_b200 -- C ABI of the B200-native SPAA hot path (libspaa_b200.so, sm_100a).
+ *
+ * The reference (BingyaoHuang/SPAA) is pure Python on stock PyTorch ops: it has no FFI of its own.  Each entry
+ * point below replaces the PyTorch library calls the reference makes at the cited place
+ * (paths relative to /root/reference/src/python/).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error (never throws); spaa_last_error() gives a thread-local text
+ *  - all pointers are DEVICE pointers unless named host_*; nothing is allocated or synchronised inside
+ *  - `stream` is a cudaStream_t; calls are asynchronous and CUDA-graph capturable
+ *  - images are fp32 NCHW planar ("plane" = H*W floats); conv activations are described by explicit strides
+ */
+#ifndef SPAA_B200_H
+#define SPAA_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spaa_stream_t; /* cudaStream_t */
+
+const char* spaa_last_error(void);
+int spaa_abi_version(void);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Colour: sRGB->Lab and the reference's CIEDE2000 variant
+ * replaces perc_al/differential_color_functions.py:12-64 (rgb2xyz, xyz_lab, rgb2lab_diff) and :67-180
+ * (hpf_diff, dhpf_diff, ahpf_diff, ciede2000_diff) and their autograd graphs.
+ * Tensors are [B,3,HW] planar fp32.  *_bstride = elements between consecutive batch items (0 = broadcast).
+ * -------------------------------------------------------------------------------------------------------- */
+int spaa_rgb2lab_fwd(const float* rgb, float* lab, int64_t B, int64_t HW, spaa_stream_t stream);
+int spaa_rgb2lab_bwd(const float* rgb, const float* dlab, float* drgb, int64_t B, int64_t HW, spaa_stream_t stream);
+int spaa_de2000_fwd(const float* lab1, int64_t lab1_bstride, const float* lab2, int64_t lab2_bstride, float* de,
+                    int64_t B, int64_t HW, spaa_stream_t stream);
+/* dlab1 / dlab2 may be NULL; cot is the [B,HW] cotangent of the dE map */
+int spaa_de2000_bwd(const float* lab1, int64_t lab1_bstride, const float* lab2, int64_t lab2_bstride, const float* cot,
+                    float* dlab1, float* dlab2, int64_t B, int64_t HW, spaa_stream_t stream);
+
+/* Fused stealth-loss kernel of the attack loops: replaces projector_based_attack.py:279-283 (caml2, camdE) and
+ * perc_al/__init__.py:197-199, plus the backward of those terms to the camera image.
+ *   cam        [B,3,HW]  camera image (PCNet output / inputs+delta)
+ *   ref_rgb    [*,3,HW]  un-attacked scene, ref_lab its precomputed Lab (spaa_rgb2lab_fwd)
+ *   cam_is_lab2: 0 -> dE(lab(cam), ref_lab) (SPAA argument order), 1 -> dE(ref_lab, lab(cam)) (PerC-AL order)
+ *   stats      [B,4] out: sum_p dE, sum_p ||cam-ref||_2, sum_p dE^2, 0        (sums over pixels, not means)
+ *   grad       [B,3,HW] out or NULL: c_de * d(sum_p w_p dE_p)/dcam + c_l2 * d(sum_p ||.||_2)/dcam,
+ *              with w_p = 1 (de_weighting 0) or w_p = dE_p (de_weighting 1: gradient of 0.5*sum dE^2)
+ *   ws         workspace of spaa_color_loss_ws_bytes(B,HW) bytes, zero-initialised once by the caller
+ */
+int64_t spaa_color_loss_ws_bytes(int64_t B, int64_t HW);
+int spaa_color_loss_fwd_bwd(const float* cam, const float* ref_rgb, const float* ref_lab, int64_t ref_bstride,
+                            int64_t B, int64_t HW, int cam_is_lab2, int de_weighting, float c_de, float c_l2,
+                            float* stats, float* grad, void* ws, spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Warping: affine o thin-plate-spline sampling grid and bilinear grid_sample
+ * replaces models.py:163-185 (WarpingNet.forward: F.affine_grid, pytorch_tps.tps_grid, 2x F.grid_sample),
+ * pytorch_tps.py:29-106 (tps, tps_grid).  Grids are channel-planar [2,H,W] (x plane then y plane), in [-1,1].
+ * -------------------------------------------------------------------------------------------------------- */
+/* plain TPS grid (pytorch_tps.tps_grid); theta [(T+2),2] reduced form, ctrl [T,2] */
+int spaa_tps_grid_fwd(const float* theta, const float* ctrl, int T, int H, int W, float* grid, spaa_stream_t stream);
+/* coarse grid = grid_sample(affine_grid(affine; Hin x Win), tps_grid(theta; H x W)) */
+int spaa_coarse_grid_fwd(const float* affine, const float* theta, const float* ctrl, int T, int Hin, int Win, int H,
+                         int W, float* grid, spaa_stream_t stream);
+/* gradients of the coarse grid wrt affine [2,3] and theta [(T+2),2]; ws: spaa_coarse_grid_ws_bytes(T,H,W), zeroed once.
+ * affine may be NULL (then Hin/Win are ignored and this is the backward of spaa_tps_grid_fwd). */
+int64_t spaa_coarse_grid_ws_bytes(int T, int H, int W);
+int spaa_coarse_grid_bwd(const float* affine, const float* theta, const float* ctrl, int T, int Hin, int Win, int H,
+                         int W, const float* dgrid, float* daffine, float* dtheta, void* ws, spaa_stream_t stream);
+/* fine = clamp(coarse + refine, -1, 1) and its backward (models.py:176-178) */
+int spaa_grid_finish_fwd(const float* coarse, const float* refine /*nullable*/, float* fine, int64_t n,
+                         spaa_stream_t stream);
+int spaa_grid_finish_bwd(const float* coarse, const float* refine /*nullable*/, const float* dfine, float* dsum,
+                         int64_t n, spaa_stream_t stream);
+
+/* out[b,c,y,x] = bilinear(img[b,c], grid[:,y,x]) (zeros padding, align_corners=True) [* mask[y,x]]
+ *   clamp01: sample clamp(img,0,1) instead of img   (projector_based_attack.py:265)
+ *   mask   : [H*W] or NULL                          (models.py:340)
+ *   rough  : if non-NULL, out2[b,c] = out[b,c] * rough[b?,c] (models.py:342, "x*s"); out2/rough have their own
+ *            batch strides so out2 can be the tail channels of a wider tensor
+ *   grid_bstride: 0 when one grid serves the whole batch                                                    */
+int spaa_grid_sample_fwd(const float* img, int64_t B, int C, int Hi, int Wi, const float* grid, int64_t grid_bstride,
+                         int H, int W, int clamp01, const float* mask, float* out, const float* rough,
+                         int64_t rough_bstride, float* out2, int64_t out2_bstride, spaa_stream_t stream);
+/* dimg (+)= scatter of (dout + dout2*rough) * mask ; dimg must be zero-filled by the caller (atomic accumulate);
+ * clamp01: zero the gradient where img is outside [0,1] is NOT applied here (applied by the consumer). */
+int spaa_grid_sample_bwd_input(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,
+                               int64_t rough_bstride, const float* mask, const float* grid, int64_t grid_bstride,
+                               int64_t B, int C, int Hi, int Wi, int H, int W, float* dimg, spaa_stream_t stream);
+/* dgrid[2,H,W] (grid_bstride==0: summed over the batch; else [B,2,H,W]) */
+int spaa_grid_sample_bwd_grid(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,
+                              int64_t rough_bstride, const float* mask, const float* img, int clamp01, const float* grid,
+                              int64_t grid_bstride, int64_t B, int C, int Hi, int Wi, int H, int W, float* dgrid,
+                              spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Convolution / transposed convolution as one strided "gather conv":
+ *   out[b,oy,ox,co] = epi( sum_{r,s,ci} in[b,(oy*stride+r-pad)/up,(ox*stride+s-pad)/up,ci] * w[r,s,ci,co] )
+ * (terms whose division is inexact or whose coordinates are out of range are skipped).
+ * up==1: nn.Conv2d (models.py:18-46,223-252 via F.conv2d); up>1: nn.ConvTranspose2d with the kernel flipped and
+ * pad = k-1-padding; the backward-data passes of both are the same operation with swapped roles (see
+ * spaa_b200/conv_plan.py).  Replaces cudnnConvolutionForward/BackwardData/BackwardFilter for those modules.
+ * dtype: 0 = fp32 storage, 1 = bf16 storage (fp32 accumulate).  Addressing is by explicit element strides so NCHW
+ * and NHWC tensors (and channel slices of wider tensors) can be read/written without repacking.
+ * -------------------------------------------------------------------------------------------------------- */
+enum {
+    SPAA_EPI_RELU = 1,        /* v = max(v,0) */
+    SPAA_EPI_LEAKY01 = 2,     /* v = v>0 ? v : 0.1 v                    (models.py:138) */
+    SPAA_EPI_CLAMP_MAX1 = 4,  /* v = min(v,1) after the activation      (models.py:301) */
+    SPAA_EPI_ADD_AFTER_ACT = 8 /* add `add` after the activation instead of before */
+};
+enum {
+    SPAA_MASK_NONE = 0,
+    SPAA_MASK_POS = 1,    /* v *= (m > 0)              backward of ReLU expressed on its output */
+    SPAA_MASK_LEAKY01 = 2,/* v *= (m > 0 ? 1 : 0.1)    backward of LeakyReLU(0.1) */
+    SPAA_MASK_OPEN01 = 3  /* v *= (m > 0 && m < 1)     backward of clamp(relu(.),max=1) */
+};
+typedef struct spaa_conv_desc {
+    int32_t in_dtype, out_dtype;         /* 0 fp32, 1 bf16; add / mask / mask2 / out2 share out_dtype */
+    int32_t B, Cin, Hin, Win, Cout, Hout, Wout;
+    int32_t KH, KW, stride, up, pad_h, pad_w;
+    int32_t flip;                        /* 1: tap (r,s) reads weight tap (KH-1-r, KW-1-s) */
+    int64_t in_bs, in_ps, in_cs;         /* element strides: batch, pixel (iy*Win+ix), channel */
+    int64_t w_ts, w_cis, w_cos;          /* fp32 weight strides: tap (r*KW+s), input channel, output channel */
+    int64_t out_bs, out_ps, out_cs;      /* out and out2 */
+    int64_t add_bs, add_ps, add_cs;      /* strides of `add` (add_bs = 0 broadcasts over the batch) */
+    int64_t mask_bs, mask_ps, mask_cs;   /* mask and mask2 (mask_bs = 0 broadcasts) */
+    int32_t epi_flags, mask_mode;
+} spaa_conv_desc;
+/* v = sum + bias; [v += add]; activation; [clamp]; [v += add if ADD_AFTER_ACT]; v *= mask(mask_mode); out = v;
+ * out2 (nullable) = v * (mask2 > 0).
+ * w: fp32, addressed by (w_ts, w_cis, w_cos) so nn.Conv2d [Cout,Cin,KH,KW] and nn.ConvTranspose2d
+ * [Cin,Cout,KH,KW] parameters are read in place; bias: fp32 [Cout] or NULL; add / mask / mask2 / out2 nullable.
+ * CUDA-core fp32 path (any shape).  */
+int spaa_conv_fwd(const spaa_conv_desc* d, const void* in, const float* w, const float* bias, const void* add,
+                  const void* mask, const void* mask2, void* out, void* out2, spaa_stream_t stream);
+/* dw (fp32, += into a caller-zeroed buffer, addressed by d->w_* strides) = sum_pixels in(gathered) x dout ;
+ * dbias[Cout] (fp32, +=, nullable) = sum_pixels dout.  `d` describes the FORWARD gather conv with up == 1 and
+ * flip == 0; `dout` has the forward output's strides (d->out_*) and dtype d->out_dtype. */
+int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* dout, float* dw, float* dbias,
+                         spaa_stream_t stream);
+/* out[c] += sum_{b,p} x[b,p,c]  (bias gradient; x addressed by element strides, dtype 0 fp32 / 1 bf16) */
+int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int64_t bs, int64_t ps, int64_t cs, float* out,
+                     spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Training loss: replaces train_network.py:367-392 (compute_loss: F.l1_loss, F.mse_loss, 1-SSIM) and
+ * pytorch_ssim/__init__.py:24-61 (_ssim: 2 replicate pads + 5 depthwise 11x11 Gaussian convs) fwd+bwd.
+ *   pred,target [N,H,W] planes (N = B*C); sums[4] out = sum|d|, sum d^2, sum ssim_map, 0
+ *   grad (nullable) = w_l1*sign(d)/numel + w_l2*2d/numel - w_ssim * d(mean ssim)/dpred
+ *   cot_map (nullable, [N,H,W]): per-pixel cotangent of the SSIM map used INSTEAD of the uniform -w_ssim/numel
+ *                                (the mask / weights / size_average=False branches of pytorch_ssim :54-67)
+ *   ssim_map (nullable, [N,H,W]): the SSIM map itself
+ *   ws: spaa_ssim_l1_ws_bytes(N,H,W) bytes, zeroed once by the caller
+ * -------------------------------------------------------------------------------------------------------- */
+int64_t spaa_ssim_l1_ws_bytes(int64_t N, int H, int W);
+int spaa_ssim_l1_fwd_bwd(const float* pred, const float* target, int64_t N, int H, int W, float w_l1, float w_l2,
+                         float w_ssim, const float* cot_map, float* sums, float* ssim_map, float* grad, void* ws,
+                         spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Attack-loop updates: replaces projector_based_attack.py:275,290-328 and perc_al/__init__.py:193-245
+ * (per-sample gradient norms, masked normalised steps, clamp/quantise, best-so-far bookkeeping, decision masks).
+ * Rows are samples: tensors are [B,n] fp32 with n = C*H*W.  Row selectors are uint8 [B] on the device.
+ * -------------------------------------------------------------------------------------------------------- */
+/* sq[b] = sum_n g[b,n]^2, counting g as zero where x_for_clamp (nullable) is outside [lo,hi] (torch.clamp backward).
+ * ws: spaa_rownorm_ws_bytes(B,n) bytes, zeroed once by the caller. */
+int64_t spaa_rownorm_ws_bytes(int64_t B, int64_t n);
+int spaa_row_sqnorm(const float* g, const float* x_for_clamp /*nullable*/, float lo, float hi, int64_t B, int64_t n,
+                    float* sq, void* ws, spaa_stream_t stream);
+/* x[b] += step * g[b] / sqrt(sq[b]) with step = step2[sel[b] != 0] (step2: DEVICE float[2]; sel NULL -> step2[0]);
+ * rows whose step is exactly 0 are not touched.  No epsilon: a zero gradient gives NaN as in the reference (:307,315).
+ * use_clamp_mask: gradient entries where x (before the step) is outside [lo,hi] count as zero.
+ * sum_out (nullable): sum_out[b] = base[b] + x[b] (after the step) for every row   (perc_al/__init__.py:197 input)
+ * copy_dst/copy_sel (nullable): copy_dst[b] = x[b] (after the step) where copy_sel[b] != 0   (:323) */
+int spaa_row_normalized_step(float* x, const float* g, const float* sq, const uint8_t* sel, const float* step2,
+                             int use_clamp_mask, float lo, float hi, const float* base, int64_t base_bstride,
+                             float* sum_out, float* copy_dst, const uint8_t* copy_sel, int64_t B, int64_t n,
+                             spaa_stream_t stream);
+/* dst[b] = src[b] where sel[b] != 0 */
+int spaa_masked_copy_rows(float* dst, const float* src, const uint8_t* sel, int64_t B, int64_t n, spaa_stream_t stream);
+/* out[b] = mask(act[b]; mask_mode) * (sel[b] ? g1[b] : g0[b])  -- picks each sample's cotangent (adversarial or
+ * stealth) and applies the backward of the network's output activation in the same pass. act/sel nullable. */
+int spaa_select_cotangent(const float* g0, const float* g1, const uint8_t* sel, const float* act, int mask_mode,
+                          float* out, int64_t B, int64_t n, spaa_stream_t stream);
+/* PerC-AL projection: delta = clamp(base+delta,0,1)-base ; xsum (nullable) = base+delta ;
+ * xq = round((base+delta)*255)/255 ; l2sum[b] = sum_p ||delta[b,:,p]||_2   (perc_al/__init__.py:211-215, :15-18).
+ * Tensors [B,3,HW]; base_bstride may be 0. */
+int64_t spaa_percal_project_ws_bytes(int64_t B, int64_t HW);
+int spaa_percal_project(const float* base, int64_t base_bstride, float* delta, float* xq, float* xsum, float* l2sum,
+                        int64_t B, int64_t HW, void* ws, spaa_stream_t stream);
+/* sums[b] = sum_p ||x[b,:,p] - ref[b,:,p]||_2 (projector_based_attack.py:275).  grad (nullable, in/out):
+ * entries where x is outside [0,1] are zeroed first when apply_clamp_mask, then c*(x-ref)/||x-ref|| is added on
+ * rows with sel[b] != 0 (sel NULL = all rows). */
+int64_t spaa_chan_l2_ws_bytes(int64_t B, int64_t HW);
+int spaa_chan_l2_fwd_bwd(const float* x, const float* ref, int64_t ref_bstride, int64_t B, int64_t HW, float c,
+                         const uint8_t* sel, int apply_clamp_mask, float* sums, float* grad, void* ws,
+                         spaa_stream_t stream);
+/* SPAA decision logic on the device (projector_based_attack.py:290-299, 318-320):
+ *   logits [B,ncls]; target [B]; stats from spaa_color_loss_fwd_bwd; prjl2sum [B] (nullable)
+ *   outputs (uint8 [B]): use_col (=mask_best_adv), succ (=mask_succ_adv), better (=mask_best);
+ *   col_loss [B] = w_prjl2*prjl2 + w_caml2*caml2 + w_camde*camde ; best_col [B] updated in place */
+int spaa_attack_masks(const float* logits, int ncls, const int64_t* target, int targeted, const float* stats,
+                      const float* prjl2sum, int64_t HW_cam, int64_t HW_prj, float w_prjl2, float w_caml2, float w_camde,
+                      float d_thr, float p_thresh, int64_t B, uint8_t* use_col, uint8_t* succ, uint8_t* better,
+                      float* col_loss, float* best_col, spaa_stream_t stream);
+/* PerC-AL decision logic (perc_al/__init__.py:215-242).  mode 0: untargeted argmax != label; 1: targeted
+ * (argmax == label, p_top1 > p_thresh); 2: untargeted with logit margin (real - best other <= -margin).
+ * dis[b] = sqrt(stats[b,2]) (the L2 norm of the dE map); best_dis updated in place. */
+int spaa_percal_masks(const float* logits, int ncls, const int64_t* labels, int mode, float margin, const float* l2sum,
+                      int64_t HW, float d_thr, float p_thresh, const float* stats, int64_t B, uint8_t* isadv,
+                      uint8_t* use_col, uint8_t* better, float* dis, float* best_dis, spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
+ * Optimiser: replaces optim.Adam.step over the parameter groups of train_network.py:253-255,145 with one
+ * launch over a flat fp32 buffer split into segments with their own lr / weight decay.
+ *   seg_end[nseg] (int64, device): exclusive end offsets; seg_lr / seg_wd [nseg] (float, device)
+ * -------------------------------------------------------------------------------------------------------- */
+int spaa_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, const int64_t* seg_end,
+                   const float* seg_lr, const float* seg_wd, int nseg, float beta1, float beta2, float eps, int step,
+                   float grad_scale, spaa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPAA_B200_H */

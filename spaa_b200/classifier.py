@@ -1,0 +1,92 @@
+"""Classifier wrapper with the reference's call convention (/root/reference/src/python/classifier.py:12-75).
+
+The torchvision networks stay cuDNN modules (external operands, BASELINE.json north_star).  `classify` keeps the
+reference's return convention `(raw_score, p_sorted numpy, idx numpy)`; the fused attack loops in
+`projector_based_attack` / `perc_al` use `logits()` instead, which never leaves the device.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn.functional as F
+
+from .img_proc import center_crop as cc, expand_4d, resize
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+_URLS = {"vgg16": "vgg16-397923af.pth", "resnet18": "resnet18-5c106cde.pth", "inception_v3": "inception_v3_google-0cc3c7bd.pth"}
+
+
+def preprocess(im, crop_sz, input_sz):
+    """classifier.py:55-59: uint8 -> float/255, centre crop, area resize, ImageNet normalise (one broadcasted op
+    instead of the reference's per-sample python loop)."""
+    if im.dtype == torch.uint8:
+        im = im.type(torch.float32) / 255
+    x = resize(cc(expand_4d(im), crop_sz), input_sz)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+class Classifier(object):
+    def __init__(self, model_name, device, device_ids, fix_params=True, sort_results=True, weights_dir=None, seed=0):
+        from torchvision import models
+        self.name = model_name
+        self.fix_params = fix_params
+        self.device = torch.device(device)
+        self.sort_results = sort_results
+        if self.name in ("vgg16", "resnet18"):
+            self.input_sz = (224, 224)
+            ctor = lambda: getattr(models, self.name)(weights=None)
+        elif self.name == "inception_v3":
+            self.input_sz = (299, 299)
+            ctor = lambda: models.inception_v3(weights=None, init_weights=False, transform_input=True, aux_logits=True)
+        else:
+            raise ValueError(f"unknown classifier {model_name}")
+        # The reference downloads ImageNet weights (classifier.py:36).  Offline: load them from `weights_dir` (or
+        # $SPAA_WEIGHTS_DIR / torch hub cache) when present, otherwise use a seeded random initialisation.
+        rng = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        self.model = ctor()
+        torch.random.set_rng_state(rng)
+        self.pretrained = False
+        for d in (weights_dir, os.environ.get("SPAA_WEIGHTS_DIR"), os.path.join(torch.hub.get_dir(), "checkpoints")):
+            if d and os.path.exists(os.path.join(d, _URLS[self.name])):
+                self.model.load_state_dict(torch.load(os.path.join(d, _URLS[self.name]), map_location="cpu"))
+                self.pretrained = True
+                break
+        self.model = self.model.to(self.device)
+        if len(device_ids) > 1:
+            self.model = torch.nn.DataParallel(self.model, device_ids=device_ids)
+        if self.fix_params:
+            self.model.eval()
+            for param in self.model.parameters():
+                param.requires_grad = False
+
+    def logits(self, im, crop_sz=(240, 240)):
+        """Device-only forward: pre-processing + network, no softmax / host copy."""
+        out = self.model(preprocess(im, crop_sz, self.input_sz).to(self.device))
+        return out.logits if hasattr(out, "logits") else out
+
+    def classify(self, im, crop_sz=(240, 240)):
+        raw_score = self.logits(im, crop_sz)
+        p = F.softmax(raw_score, dim=1).detach().cpu()
+        if self.sort_results:
+            p_sorted, idx = p.sort(descending=True)
+        else:
+            p_sorted, idx = p, torch.arange(p.shape[1]).repeat(p.shape[0], 1)
+        return raw_score, p_sorted.numpy(), idx.numpy()
+
+    def __call__(self, im, crop_sz):
+        return self.classify(im, crop_sz)
+
+
+def device_logits(classifier, im, crop_sz):
+    """Logits of `im` through any classifier object: ours or the reference's `Classifier` (uses .model/.input_sz on
+    the device), or an opaque callable with the reference convention (falls back to its own __call__)."""
+    model, input_sz = getattr(classifier, "model", None), getattr(classifier, "input_sz", None)
+    if model is not None and input_sz is not None:
+        out = model(preprocess(im, crop_sz, input_sz))
+        return out.logits if hasattr(out, "logits") else out
+    return classifier(im, crop_sz)[0]

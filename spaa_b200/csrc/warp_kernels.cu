@@ -1,0 +1,347 @@
+// WarpingNet kernels: fused affine o TPS sampling-grid generation (fwd/bwd) and bilinear grid_sample
+// (fwd, bwd-input scatter, bwd-grid).  All HBM/L2-bound gather/scatter work; see DESIGN.md section 4.
+#include "common.cuh"
+#include "warp_math.cuh"
+#include "../../include/spaa_b200.h"
+
+using namespace spaa;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxT = 64;          // control points held in shared memory (reference uses 6x6 = 36)
+
+struct GridParams {
+    int T, Hin, Win, H, W;
+};
+
+// Backward: every thread owns pixels, accumulates the 6 + 2(T+2) parameter gradients privately in a
+// round-robin over shared-memory reductions, block partials go to the workspace and the last block sums them.
+__global__ void __launch_bounds__(kThreads) coarse_grid_bwd_kernel(const float* __restrict__ aff, GridParams gp, const float* __restrict__ theta, const float* __restrict__ ctrl,
+                                                                    const float* __restrict__ dgrid, float* __restrict__ daff,
+                                                                    float* __restrict__ dtheta, float* __restrict__ partial,
+                                                                    unsigned* __restrict__ counter) {
+    __shared__ float s_theta[(kMaxT + 2) * 2];
+    __shared__ float s_ctrl[kMaxT * 2];
+    __shared__ float s_acc[6 + (kMaxT + 2) * 2];
+    __shared__ float s_aff[6];
+    __shared__ bool is_last;
+    const int nout = 6 + (gp.T + 2) * 2;
+    const bool has_aff = aff != nullptr;
+    if (threadIdx.x < 6) s_aff[threadIdx.x] = has_aff ? aff[threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < (gp.T + 2) * 2; i += blockDim.x) s_theta[i] = theta[i];
+    for (int i = threadIdx.x; i < gp.T * 2; i += blockDim.x) s_ctrl[i] = ctrl[i];
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+    const int HW = gp.H * gp.W;
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together so the shuffles below are convergent
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int base = warp_id * 32; base < HW; base += warps_total * 32) {
+        const int p = base + lane;
+        float da[6] = {0, 0, 0, 0, 0, 0}, dzx = 0.f, dzy = 0.f, px = 0.f, py = 0.f;
+        if (p < HW) {
+            const int y = p / gp.W, x = p - y * gp.W;
+            const float gox = __ldg(dgrid + p), goy = __ldg(dgrid + HW + p);
+            px = warp::linspace_at<float>(0.f, 1.f, gp.W, x);
+            py = warp::linspace_at<float>(0.f, 1.f, gp.H, y);
+            if (has_aff) {
+                warp::coarse_grid_point_bwd_local<float>(s_aff, s_theta, s_ctrl, gp.T, gp.Hin, gp.Win, gp.H, gp.W, y, x, gox, goy, da, dzx, dzy);
+            } else {  // grid = (p + z)*2 - 1
+                dzx = 2.f * gox; dzy = 2.f * goy;
+            }
+        }
+        if (has_aff) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const float v = warp_sum(da[i]);
+                if (lane == 0) atomicAdd(&s_acc[i], v);
+            }
+        }
+        float* acc_t = s_acc + 6;
+        {   // affine part of theta: rows T-1..T+1
+            const float v0 = warp_sum(dzx), v1 = warp_sum(dzy), v2 = warp_sum(dzx * px), v3 = warp_sum(dzy * px);
+            const float v4 = warp_sum(dzx * py), v5 = warp_sum(dzy * py);
+            if (lane == 0) {
+                float* a = acc_t + (gp.T - 1) * 2;
+                atomicAdd(a + 0, v0); atomicAdd(a + 1, v1); atomicAdd(a + 2, v2);
+                atomicAdd(a + 3, v3); atomicAdd(a + 4, v4); atomicAdd(a + 5, v5);
+            }
+        }
+        const float u0 = warp::tps_u<float>(px - s_ctrl[0], py - s_ctrl[1]);
+        for (int t = 1; t < gp.T; ++t) {
+            const float u = warp::tps_u<float>(px - s_ctrl[2 * t], py - s_ctrl[2 * t + 1]) - u0;
+            const float vx = warp_sum(u * dzx), vy = warp_sum(u * dzy);
+            if (lane == 0) { atomicAdd(acc_t + 2 * (t - 1), vx); atomicAdd(acc_t + 2 * (t - 1) + 1, vy); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) partial[(int64_t)blockIdx.x * nout + i] = s_acc[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const volatile float* q = partial;
+        for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+            float s = 0.f;
+            for (unsigned k = 0; k < gridDim.x; ++k) s += q[(int64_t)k * nout + i];
+            if (i < 6) { if (daff) daff[i] = s; }
+            else dtheta[i - 6] = s;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+constexpr int kGridBwdBlocks = 148;
+
+__global__ void __launch_bounds__(kThreads) grid_finish_fwd_kernel(const float* __restrict__ coarse, const float* __restrict__ refine,
+                                                                    float* __restrict__ fine, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = __ldg(coarse + i);
+        if (refine) v = __ldg(refine + i) + v;
+        fine[i] = fminf(fmaxf(v, -1.f), 1.f);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) grid_finish_bwd_kernel(const float* __restrict__ coarse, const float* __restrict__ refine,
+                                                                    const float* __restrict__ dfine, float* __restrict__ dsum, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = __ldg(coarse + i);
+        if (refine) v = __ldg(refine + i) + v;
+        dsum[i] = (v >= -1.f && v <= 1.f) ? __ldg(dfine + i) : 0.f;   // torch.clamp backward: inclusive bounds
+    }
+}
+
+SPAA_D float clamp01_if(float v, int on) { return on ? fminf(fmaxf(v, 0.f), 1.f) : v; }
+
+// one thread per output pixel, loops over channels (C is 2 or 3 here)
+__global__ void __launch_bounds__(kThreads) grid_sample_fwd_kernel(const float* __restrict__ img, int C, int Hi, int Wi,
+                                                                    const float* __restrict__ grid, int64_t grid_bs, int H, int W, int clamp01,
+                                                                    const float* __restrict__ mask, float* __restrict__ out,
+                                                                    const float* __restrict__ rough, int64_t rough_bs, float* __restrict__ out2,
+                                                                    int64_t out2_bs) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int64_t HWi = (int64_t)Hi * Wi;
+    const float* g = grid + (int64_t)b * grid_bs;
+    const float* ib = img + (int64_t)b * C * HWi;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const warp::Taps<float> t = warp::make_taps<float>(__ldg(g + p), __ldg(g + HW + p), Hi, Wi);
+        const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
+        const float w00 = wx0 * wy0, w01 = t.wx1 * wy0, w10 = wx0 * t.wy1, w11 = t.wx1 * t.wy1;
+        const float m = mask ? __ldg(mask + p) : 1.f;
+        const int64_t o00 = (int64_t)t.y0 * Wi + t.x0;
+        for (int c = 0; c < C; ++c) {
+            const float* ic = ib + c * HWi;
+            float v = 0.f;
+            if (t.vy0 && t.vx0) v += clamp01_if(__ldg(ic + o00), clamp01) * w00;
+            if (t.vy0 && t.vx1) v += clamp01_if(__ldg(ic + o00 + 1), clamp01) * w01;
+            if (t.vy1 && t.vx0) v += clamp01_if(__ldg(ic + o00 + Wi), clamp01) * w10;
+            if (t.vy1 && t.vx1) v += clamp01_if(__ldg(ic + o00 + Wi + 1), clamp01) * w11;
+            if (mask) v *= m;
+            out[((int64_t)b * C + c) * HW + p] = v;
+            if (out2) out2[(int64_t)b * out2_bs + (int64_t)c * HW + p] = v * __ldg(rough + (int64_t)b * rough_bs + (int64_t)c * HW + p);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) grid_sample_bwd_input_kernel(const float* __restrict__ dout, const float* __restrict__ dout2,
+                                                                          int64_t dout2_bs, const float* __restrict__ rough, int64_t rough_bs,
+                                                                          const float* __restrict__ mask, const float* __restrict__ grid,
+                                                                          int64_t grid_bs, int C, int Hi, int Wi, int H, int W,
+                                                                          float* __restrict__ dimg) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int64_t HWi = (int64_t)Hi * Wi;
+    const float* g = grid + (int64_t)b * grid_bs;
+    float* db = dimg + (int64_t)b * C * HWi;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const float m = mask ? __ldg(mask + p) : 1.f;
+        if (mask && m == 0.f) continue;
+        const warp::Taps<float> t = warp::make_taps<float>(__ldg(g + p), __ldg(g + HW + p), Hi, Wi);
+        const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
+        const float w00 = wx0 * wy0, w01 = t.wx1 * wy0, w10 = wx0 * t.wy1, w11 = t.wx1 * t.wy1;
+        const int64_t o00 = (int64_t)t.y0 * Wi + t.x0;
+        for (int c = 0; c < C; ++c) {
+            float d = __ldg(dout + ((int64_t)b * C + c) * HW + p);
+            if (dout2) d += __ldg(dout2 + (int64_t)b * dout2_bs + (int64_t)c * HW + p) * __ldg(rough + (int64_t)b * rough_bs + (int64_t)c * HW + p);
+            d *= m;
+            float* dc = db + c * HWi;
+            if (t.vy0 && t.vx0) atomicAdd(dc + o00, d * w00);
+            if (t.vy0 && t.vx1) atomicAdd(dc + o00 + 1, d * w01);
+            if (t.vy1 && t.vx0) atomicAdd(dc + o00 + Wi, d * w10);
+            if (t.vy1 && t.vx1) atomicAdd(dc + o00 + Wi + 1, d * w11);
+        }
+    }
+}
+
+// dgrid for a grid shared by the whole batch (grid_bs == 0 -> sum over b) or per-sample grids.
+__global__ void __launch_bounds__(kThreads) grid_sample_bwd_grid_kernel(const float* __restrict__ dout, const float* __restrict__ dout2,
+                                                                         int64_t dout2_bs, const float* __restrict__ rough, int64_t rough_bs,
+                                                                         const float* __restrict__ mask, const float* __restrict__ img, int clamp01,
+                                                                         const float* __restrict__ grid, int64_t grid_bs, int B, int C, int Hi,
+                                                                         int Wi, int H, int W, float* __restrict__ dgrid) {
+    const int HW = H * W;
+    const int64_t HWi = (int64_t)Hi * Wi;
+    const int nb_outer = grid_bs == 0 ? 1 : B;        // blockIdx.y indexes independent grids
+    const int bo = blockIdx.y;
+    (void)nb_outer;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const float* g = grid + (int64_t)bo * grid_bs;
+        const warp::Taps<float> t = warp::make_taps<float>(__ldg(g + p), __ldg(g + HW + p), Hi, Wi);
+        const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
+        const float m = mask ? __ldg(mask + p) : 1.f;
+        const int64_t o00 = (int64_t)t.y0 * Wi + t.x0;
+        float gix = 0.f, giy = 0.f;
+        const int b_lo = grid_bs == 0 ? 0 : bo, b_hi = grid_bs == 0 ? B : bo + 1;
+        for (int b = b_lo; b < b_hi; ++b) {
+            const float* ib = img + (int64_t)b * C * HWi;
+            for (int c = 0; c < C; ++c) {
+                float d = __ldg(dout + ((int64_t)b * C + c) * HW + p);
+                if (dout2) d += __ldg(dout2 + (int64_t)b * dout2_bs + (int64_t)c * HW + p) * __ldg(rough + (int64_t)b * rough_bs + (int64_t)c * HW + p);
+                d *= m;
+                const float* ic = ib + c * HWi;
+                const float v00 = (t.vy0 && t.vx0) ? clamp01_if(__ldg(ic + o00), clamp01) : 0.f;
+                const float v01 = (t.vy0 && t.vx1) ? clamp01_if(__ldg(ic + o00 + 1), clamp01) : 0.f;
+                const float v10 = (t.vy1 && t.vx0) ? clamp01_if(__ldg(ic + o00 + Wi), clamp01) : 0.f;
+                const float v11 = (t.vy1 && t.vx1) ? clamp01_if(__ldg(ic + o00 + Wi + 1), clamp01) : 0.f;
+                gix += d * ((v01 - v00) * wy0 + (v11 - v10) * t.wy1);
+                giy += d * ((v10 - v00) * wx0 + (v11 - v01) * t.wx1);
+            }
+        }
+        float* dg = dgrid + (int64_t)bo * 2 * HW;
+        dg[p] = gix * 0.5f * (float)(Wi - 1);
+        dg[HW + p] = giy * 0.5f * (float)(Hi - 1);
+    }
+}
+
+inline int blocks_for(int64_t n, int cap_mult = 8) {
+    int64_t g = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)kNumSMs * cap_mult;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int spaa_tps_grid_fwd(const float* theta, const float* ctrl, int T, int H, int W, float* grid, spaa_stream_t stream) {
+    return spaa_coarse_grid_fwd(nullptr, theta, ctrl, T, 0, 0, H, W, grid, stream);
+}
+
+int64_t spaa_coarse_grid_ws_bytes(int T, int H, int W) {
+    (void)H; (void)W;
+    return (int64_t)kGridBwdBlocks * (6 + (T + 2) * 2) * sizeof(float) + 16;
+}
+
+}  // extern "C"
+
+namespace {
+
+__global__ void __launch_bounds__(kThreads) coarse_grid_fwd_dev(const float* __restrict__ aff, GridParams gp, const float* __restrict__ theta,
+                                                                 const float* __restrict__ ctrl, float* __restrict__ grid) {
+    __shared__ float s_theta[(kMaxT + 2) * 2];
+    __shared__ float s_ctrl[kMaxT * 2];
+    __shared__ float s_aff[6];
+    for (int i = threadIdx.x; i < (gp.T + 2) * 2; i += blockDim.x) s_theta[i] = theta[i];
+    for (int i = threadIdx.x; i < gp.T * 2; i += blockDim.x) s_ctrl[i] = ctrl[i];
+    if (threadIdx.x < 6) s_aff[threadIdx.x] = aff ? aff[threadIdx.x] : 0.f;
+    __syncthreads();
+    const int HW = gp.H * gp.W;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const int y = p / gp.W, x = p - y * gp.W;
+        float gx, gy;
+        if (aff) warp::coarse_grid_point<float>(s_aff, s_theta, s_ctrl, gp.T, gp.Hin, gp.Win, gp.H, gp.W, y, x, gx, gy);
+        else warp::tps_point<float>(s_theta, s_ctrl, gp.T, gp.H, gp.W, y, x, gx, gy);
+        grid[p] = gx;
+        grid[HW + p] = gy;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int spaa_coarse_grid_fwd(const float* affine, const float* theta, const float* ctrl, int T, int Hin, int Win, int H, int W, float* grid,
+                         spaa_stream_t stream) {
+    SPAA_CHECK_ARG(theta && ctrl && grid && T >= 2 && T <= kMaxT && H > 0 && W > 0, "spaa_coarse_grid_fwd: bad arguments (T<=%d)", kMaxT);
+    SPAA_CHECK_ARG(!affine || (Hin > 1 && Win > 1), "spaa_coarse_grid_fwd: affine needs Hin,Win > 1");
+    GridParams gp{T, Hin, Win, H, W};
+    coarse_grid_fwd_dev<<<blocks_for((int64_t)H * W, 4), kThreads, 0, (cudaStream_t)stream>>>(affine, gp, theta, ctrl, grid);
+    SPAA_CHECK_LAUNCH("spaa_coarse_grid_fwd");
+    return SPAA_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int spaa_coarse_grid_bwd(const float* affine, const float* theta, const float* ctrl, int T, int Hin, int Win, int H, int W,
+                         const float* dgrid, float* daffine, float* dtheta, void* ws, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(theta && ctrl && dgrid && dtheta && ws && T >= 2 && T <= kMaxT && H > 0 && W > 0, "spaa_coarse_grid_bwd: bad arguments");
+    SPAA_CHECK_ARG(!affine || (Hin > 1 && Win > 1 && daffine), "spaa_coarse_grid_bwd: affine needs Hin,Win > 1 and daffine");
+    GridParams gp{T, Hin, Win, H, W};
+    float* partial = (float*)ws;
+    unsigned* counter = (unsigned*)(partial + (int64_t)kGridBwdBlocks * (6 + (T + 2) * 2));
+    coarse_grid_bwd_kernel<<<kGridBwdBlocks, kThreads, 0, (cudaStream_t)stream>>>(affine, gp, theta, ctrl, dgrid, daffine, dtheta, partial, counter);
+    SPAA_CHECK_LAUNCH("spaa_coarse_grid_bwd");
+    return SPAA_OK;
+}
+
+int spaa_grid_finish_fwd(const float* coarse, const float* refine, float* fine, int64_t n, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(coarse && fine && n > 0, "spaa_grid_finish_fwd: bad arguments");
+    grid_finish_fwd_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(coarse, refine, fine, n);
+    SPAA_CHECK_LAUNCH("spaa_grid_finish_fwd");
+    return SPAA_OK;
+}
+
+int spaa_grid_finish_bwd(const float* coarse, const float* refine, const float* dfine, float* dsum, int64_t n, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(coarse && dfine && dsum && n > 0, "spaa_grid_finish_bwd: bad arguments");
+    grid_finish_bwd_kernel<<<blocks_for(n), kThreads, 0, (cudaStream_t)stream>>>(coarse, refine, dfine, dsum, n);
+    SPAA_CHECK_LAUNCH("spaa_grid_finish_bwd");
+    return SPAA_OK;
+}
+
+int spaa_grid_sample_fwd(const float* img, int64_t B, int C, int Hi, int Wi, const float* grid, int64_t grid_bstride, int H, int W,
+                         int clamp01, const float* mask, float* out, const float* rough, int64_t rough_bstride, float* out2,
+                         int64_t out2_bstride, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(img && grid && out && B > 0 && B < 65536 && C > 0 && Hi > 1 && Wi > 1 && H > 0 && W > 0, "spaa_grid_sample_fwd: bad arguments");
+    SPAA_CHECK_ARG((out2 == nullptr) == (rough == nullptr), "spaa_grid_sample_fwd: out2 and rough go together");
+    dim3 g(blocks_for((int64_t)H * W, 4), (unsigned)B);
+    grid_sample_fwd_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(img, C, Hi, Wi, grid, grid_bstride, H, W, clamp01, mask, out, rough,
+                                                                   rough_bstride, out2, out2_bstride);
+    SPAA_CHECK_LAUNCH("spaa_grid_sample_fwd");
+    return SPAA_OK;
+}
+
+int spaa_grid_sample_bwd_input(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough, int64_t rough_bstride,
+                               const float* mask, const float* grid, int64_t grid_bstride, int64_t B, int C, int Hi, int Wi, int H, int W,
+                               float* dimg, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(dout && grid && dimg && B > 0 && B < 65536 && C > 0 && Hi > 1 && Wi > 1, "spaa_grid_sample_bwd_input: bad arguments");
+    SPAA_CHECK_ARG((dout2 == nullptr) || rough, "spaa_grid_sample_bwd_input: dout2 needs rough");
+    dim3 g(blocks_for((int64_t)H * W, 4), (unsigned)B);
+    grid_sample_bwd_input_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(dout, dout2, dout2_bstride, rough, rough_bstride, mask, grid,
+                                                                         grid_bstride, C, Hi, Wi, H, W, dimg);
+    SPAA_CHECK_LAUNCH("spaa_grid_sample_bwd_input");
+    return SPAA_OK;
+}
+
+int spaa_grid_sample_bwd_grid(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough, int64_t rough_bstride,
+                              const float* mask, const float* img, int clamp01, const float* grid, int64_t grid_bstride, int64_t B, int C,
+                              int Hi, int Wi, int H, int W, float* dgrid, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(dout && img && grid && dgrid && B > 0 && B < 65536 && C > 0 && Hi > 1 && Wi > 1, "spaa_grid_sample_bwd_grid: bad arguments");
+    SPAA_CHECK_ARG((dout2 == nullptr) || rough, "spaa_grid_sample_bwd_grid: dout2 needs rough");
+    dim3 g(blocks_for((int64_t)H * W, 4), grid_bstride == 0 ? 1u : (unsigned)B);
+    grid_sample_bwd_grid_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(dout, dout2, dout2_bstride, rough, rough_bstride, mask, img, clamp01,
+                                                                        grid, grid_bstride, (int)B, C, Hi, Wi, H, W, dgrid);
+    SPAA_CHECK_LAUNCH("spaa_grid_sample_bwd_grid");
+    return SPAA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,519 @@
+"""PCNet / WarpingNet / ShadingNetSPAA / CompenNet / CompenNet++ with the reference's module API
+(/root/reference/src/python/models.py:11-346) and state-dict layout, executed by the sm_100a kernels of
+libspaa_b200.so.
+
+Each network is ONE autograd node: its forward runs a hand-scheduled chain of fused conv kernels (bias, residual add,
+ReLU / clamp in the epilogue) and keeps the activations; its backward runs the matching chain of backward-data
+kernels with the ReLU masks and skip-connection sums fused into their epilogues, plus the backward-weight kernels
+when parameters need gradients.  The nn.Conv2d / nn.ConvTranspose2d sub-modules only hold parameters (so reference
+checkpoints load unchanged); their own forward is never called.
+
+CUDA only -- calling a module with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import pytorch_tps
+from .ops import ConvSpec, EPI_RELU, EPI_LEAKY01, EPI_CLAMP_MAX1, EPI_ADD_AFTER_ACT, MASK_POS, MASK_LEAKY01, MASK_OPEN01
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------------------------
+# shared conv-stack engine for ShadingNetSPAA and CompenNet (same topology, models.py:74-94 and :280-303)
+# --------------------------------------------------------------------------------------------------------------
+
+def _stack_specs(variant: str, surf_ch: int) -> Dict[str, ConvSpec]:
+    shading = variant == "shading"
+    return {
+        "conv1": ConvSpec("conv", 3, 32, 3, 2, 1), "conv2": ConvSpec("conv", 32, 64, 3, 2, 1),
+        "conv3": ConvSpec("conv", 64, 128, 3, 1, 1), "conv4": ConvSpec("conv", 128, 256, 3, 1, 1),
+        "conv5": ConvSpec("conv", 256, 128, 3, 1, 1),
+        "conv1_s": ConvSpec("conv", surf_ch, 32, 3, 2, 1), "conv2_s": ConvSpec("conv", 32, 64, 3, 2, 1),
+        "conv3_s": ConvSpec("conv", 64, 128, 3, 1, 1), "conv4_s": ConvSpec("conv", 128, 256, 3, 1, 1),
+        "transConv1": ConvSpec("convT", 128, 64, 3, 2, 1, 1) if shading else ConvSpec("convT", 128, 64, 2, 2, 0),
+        "transConv2": ConvSpec("convT", 64, 32, 2, 2, 0), "conv6": ConvSpec("conv", 32, 3, 3, 1, 1),
+        "skipConv1.0": ConvSpec("conv", 3, 3, 1, 1, 0) if shading else ConvSpec("conv", 3, 3, 3, 1, 1),
+        "skipConv1.2": ConvSpec("conv", 3, 3, 3, 1, 1), "skipConv1.4": ConvSpec("conv", 3, 3, 3, 1, 1),
+        "skipConv2": ConvSpec("conv", 32, 64, 1, 1, 0),
+        "skipConv3": ConvSpec("conv", 64, 128, 3, 1, 1) if shading else ConvSpec("conv", 64, 128, 1, 1, 0),
+    }
+
+
+def _get(net: nn.Module, name: str) -> nn.Module:
+    m = net
+    for part in name.split("."):
+        m = m[int(part)] if part.isdigit() else getattr(m, part)
+    return m
+
+
+class _Stack:
+    """Forward / backward schedules of the 17-conv stack.  `net` supplies parameters and specs."""
+
+    @staticmethod
+    def surface_branch(net, surf: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        sp = net._specs
+        W = lambda n: (_get(net, n).weight, _get(net, n).bias)
+        r1s = ops.conv_forward(sp["conv1_s"], surf, *W("conv1_s"), epi=EPI_RELU)
+        r2s = ops.conv_forward(sp["conv2_s"], r1s, *W("conv2_s"), epi=EPI_RELU)
+        r3s = ops.conv_forward(sp["conv3_s"], r2s, *W("conv3_s"), epi=EPI_RELU)
+        r4s = ops.conv_forward(sp["conv4_s"], r3s, *W("conv4_s"), epi=EPI_RELU)
+        return r1s, r2s, r3s, r4s
+
+    @staticmethod
+    def skip1(net, skip_in: Tensor):
+        sp = net._specs
+        W = lambda n: (_get(net, n).weight, _get(net, n).bias)
+        t1 = ops.conv_forward(sp["skipConv1.0"], skip_in, *W("skipConv1.0"), epi=EPI_RELU)
+        t2 = ops.conv_forward(sp["skipConv1.2"], t1, *W("skipConv1.2"), epi=EPI_RELU)
+        res1 = ops.conv_forward(sp["skipConv1.4"], t2, *W("skipConv1.4"), epi=EPI_RELU)
+        return t1, t2, res1
+
+    @staticmethod
+    def forward(net, x: Tensor, surf: Optional[Tensor], skip_in: Optional[Tensor], *, surf_acts=None, skip_acts=None) -> Tuple[Tensor, dict]:
+        """x [B,3,H,W]; surf [B or 1,Cs,H,W] (ignored when surf_acts given); skip_in [B or 1,3,H,W] (ignored when
+        skip_acts given).  Returns (out, saved activations)."""
+        sp = net._specs
+        W = lambda n: (_get(net, n).weight, _get(net, n).bias)
+        S: dict = {"x": x, "surf": surf, "skip_in": skip_in}
+        if surf_acts is None:
+            surf_acts = _Stack.surface_branch(net, surf)
+            S["surf_own"] = True
+        r1s, r2s, r3s, r4s = surf_acts
+        if skip_acts is None:
+            skip_acts = _Stack.skip1(net, skip_in)
+            S["skip_own"] = True
+        t1, t2, res1 = skip_acts
+        x1 = ops.conv_forward(sp["conv1"], x, *W("conv1"), add=r1s, epi=EPI_RELU)
+        res2 = ops.conv_forward(sp["skipConv2"], x1, *W("skipConv2"))
+        x2 = ops.conv_forward(sp["conv2"], x1, *W("conv2"), add=r2s, epi=EPI_RELU)
+        res3 = ops.conv_forward(sp["skipConv3"], x2, *W("skipConv3"))
+        x3 = ops.conv_forward(sp["conv3"], x2, *W("conv3"), add=r3s, epi=EPI_RELU)
+        x4 = ops.conv_forward(sp["conv4"], x3, *W("conv4"), add=r4s, epi=EPI_RELU)
+        x5 = ops.conv_forward(sp["conv5"], x4, *W("conv5"), add=res3, epi=EPI_RELU)
+        x6 = ops.conv_forward(sp["transConv1"], x5, *W("transConv1"), add=res2, epi=EPI_RELU)
+        x7 = ops.conv_forward(sp["transConv2"], x6, *W("transConv2"), epi=EPI_RELU)
+        out = ops.conv_forward(sp["conv6"], x7, *W("conv6"), add=res1, epi=EPI_RELU | EPI_CLAMP_MAX1)
+        S.update(r1s=r1s, r2s=r2s, r3s=r3s, r4s=r4s, t1=t1, t2=t2, res1=res1, x1=x1, x2=x2, x3=x3, x4=x4, x5=x5, x6=x6, x7=x7, out=out)
+        return out, S
+
+    @staticmethod
+    def backward(net, S: dict, d_pre6: Tensor, *, need_dx: bool = True, surf_grad_channels: Optional[Tuple[int, int]] = None,
+                 need_dskip: bool = False, param_grads: Optional[Dict[str, Tensor]] = None):
+        """d_pre6 = d(loss)/d(conv6 pre-activation) = dout * [0 < out < 1].
+        Returns (dx, dsurf[:, lo:hi] or None, dskip_in or None); accumulates parameter gradients into `param_grads`
+        ({"conv1.weight": fp32 tensor, ...}, zero-filled by the caller) when given."""
+        sp = net._specs
+        Wt = lambda n: _get(net, n).weight
+        pg = param_grads
+        hw = lambda t: (t.shape[2], t.shape[3])
+        B = d_pre6.shape[0]
+
+        def wgrad(name, inp, dy):
+            if pg is not None and (name + ".weight") in pg:
+                if inp.shape[0] == 1 and B > 1:
+                    inp = inp.expand(B, -1, -1, -1)
+                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"))
+
+        surf_live = S.get("surf_own", False) and (surf_grad_channels is not None or pg is not None)
+        if surf_live and S["r1s"].shape[0] != B:
+            raise RuntimeError("gradients through a batch-broadcast surface branch are not supported; expand `s` to the batch")
+        x7, x6, x5, x4, x3, x2, x1 = S["x7"], S["x6"], S["x5"], S["x4"], S["x3"], S["x2"], S["x1"]
+        d7 = ops.conv_backward_data(sp["conv6"], d_pre6, Wt("conv6"), hw(x7), mask=x7, mask_mode=MASK_POS)
+        wgrad("conv6", x7, d_pre6)
+        d6 = ops.conv_backward_data(sp["transConv2"], d7, Wt("transConv2"), hw(x6), mask=x6, mask_mode=MASK_POS)
+        wgrad("transConv2", x6, d7)
+        d5 = ops.conv_backward_data(sp["transConv1"], d6, Wt("transConv1"), hw(x5), mask=x5, mask_mode=MASK_POS)
+        wgrad("transConv1", x5, d6)
+        d4s = torch.empty_like(x4) if surf_live else None
+        d4 = ops.conv_backward_data(sp["conv5"], d5, Wt("conv5"), hw(x4), mask=x4, mask_mode=MASK_POS,
+                                    mask2=S["r4s"] if surf_live else None, out2=d4s)
+        wgrad("conv5", x4, d5)
+        d3 = ops.conv_backward_data(sp["conv4"], d4, Wt("conv4"), hw(x3), mask=x3, mask_mode=MASK_POS)
+        wgrad("conv4", x3, d4)
+        t2_ = ops.conv_backward_data(sp["conv3"], d3, Wt("conv3"), hw(x2))
+        wgrad("conv3", x2, d3)
+        d2 = ops.conv_backward_data(sp["skipConv3"], d5, Wt("skipConv3"), hw(x2), add=t2_, mask=x2, mask_mode=MASK_POS)
+        wgrad("skipConv3", x2, d5)
+        t1_ = ops.conv_backward_data(sp["conv2"], d2, Wt("conv2"), hw(x1))
+        wgrad("conv2", x1, d2)
+        d1 = ops.conv_backward_data(sp["skipConv2"], d6, Wt("skipConv2"), hw(x1), add=t1_, mask=x1, mask_mode=MASK_POS)
+        wgrad("skipConv2", x1, d6)
+        dx = None
+        if need_dx:
+            dx = ops.conv_backward_data(sp["conv1"], d1, Wt("conv1"), hw(S["x"]))
+        wgrad("conv1", S["x"], d1)
+        dsurf = None
+        if surf_live:
+            r3s, r2s, r1s = S["r3s"], S["r2s"], S["r1s"]
+            d3s = ops.conv_backward_data(sp["conv4_s"], d4s, Wt("conv4_s"), hw(r3s), add=d3, mask=r3s, mask_mode=MASK_POS)
+            wgrad("conv4_s", r3s, d4s)
+            d2s = ops.conv_backward_data(sp["conv3_s"], d3s, Wt("conv3_s"), hw(r2s), add=d2, mask=r2s, mask_mode=MASK_POS)
+            wgrad("conv3_s", r2s, d3s)
+            d1s = ops.conv_backward_data(sp["conv2_s"], d2s, Wt("conv2_s"), hw(r1s), add=d1, mask=r1s, mask_mode=MASK_POS)
+            wgrad("conv2_s", r1s, d2s)
+            if surf_grad_channels is not None:
+                lo, hi = surf_grad_channels
+                dsurf = ops.conv_backward_data(sp["conv1_s"], d1s, Wt("conv1_s")[:, lo:hi], hw(S["surf"]))
+            wgrad("conv1_s", S["surf"], d1s)
+        dskip = None
+        skip_params = pg is not None and "skipConv1.4.weight" in pg
+        if S.get("skip_own", False) and (need_dskip or skip_params):
+            t1, t2, res1 = S["t1"], S["t2"], S["res1"]
+            if res1.shape[0] != B:
+                raise RuntimeError("gradients through a batch-broadcast skipConv1 branch are not supported; expand its input")
+            dr = ops.select_cotangent(d_pre6, None, None, res1, MASK_POS, torch.empty_like(d_pre6))
+            dt2 = ops.conv_backward_data(sp["skipConv1.4"], dr, Wt("skipConv1.4"), hw(t2), mask=t2, mask_mode=MASK_POS)
+            wgrad("skipConv1.4", t2, dr)
+            dt1 = ops.conv_backward_data(sp["skipConv1.2"], dt2, Wt("skipConv1.2"), hw(t1), mask=t1, mask_mode=MASK_POS)
+            wgrad("skipConv1.2", t1, dt2)
+            if need_dskip:
+                dskip = ops.conv_backward_data(sp["skipConv1.0"], dt1, Wt("skipConv1.0"), hw(S["skip_in"]))
+            wgrad("skipConv1.0", S["skip_in"], dt1)
+        return dx, dsurf, dskip
+
+
+_STACK_PARAM_ORDER = ["conv1", "conv2", "conv3", "conv4", "conv5", "conv1_s", "conv2_s", "conv3_s", "conv4_s", "transConv1",
+                      "transConv2", "conv6", "skipConv1.0", "skipConv1.2", "skipConv1.4", "skipConv2", "skipConv3"]
+
+
+class _StackFn(torch.autograd.Function):
+    """out = stack(x, surf, skip_in; params).  One autograd node for the whole 17-conv network."""
+
+    @staticmethod
+    def forward(ctx, net, x, surf, skip_in, use_cached_surf, *params):
+        x = ops._f32c(x)
+        surf_acts = skip_acts = None
+        if use_cached_surf:
+            surf_acts = tuple(t if t.dim() == 4 else t.unsqueeze(0) for t in (net.res1_s, net.res2_s, net.res3_s, net.res4_s))
+        else:
+            surf = ops._f32c(surf)
+        skip_in = ops._f32c(skip_in)
+        with torch.no_grad():
+            out, S = _Stack.forward(net, x, surf, skip_in, surf_acts=surf_acts, skip_acts=skip_acts)
+        ctx.net, ctx.S = net, S
+        ctx.n_params = len(params)
+        ctx.surf_given = not use_cached_surf
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net, S = ctx.net, ctx.S
+        need_x, need_surf, need_skip = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        names = [n for n, _ in net.named_parameters()]
+        pneed = ctx.needs_input_grad[5:]
+        pg = None
+        if any(pneed):
+            pg = {n: torch.zeros_like(p, dtype=torch.float32) for (n, p), need in zip(net.named_parameters(), pneed) if need}
+        d_pre6 = ops.select_cotangent(ops._f32c(dout), None, None, S["out"], MASK_OPEN01, torch.empty_like(S["out"]))
+        cs = S["surf"].shape[1] if (S["surf"] is not None and ctx.surf_given) else 0
+        with torch.no_grad():
+            dx, dsurf, dskip = _Stack.backward(net, S, d_pre6, need_dx=need_x, surf_grad_channels=(0, cs) if (need_surf and cs) else None,
+                                               need_dskip=need_skip, param_grads=pg)
+        ctx.S = None
+        pgr = tuple((pg.get(n) if pg is not None else None) for n in names)
+        return (None, dx, dsurf, dskip, None) + pgr
+
+
+class _ConvStackNet(nn.Module):
+    """Common parameter container + engine access for ShadingNetSPAA and CompenNet."""
+
+    def _build(self, variant: str, surf_ch: int):
+        self._variant = variant
+        self._specs = _stack_specs(variant, surf_ch)
+        sp = self._specs
+        mk = lambda s: (nn.Conv2d(s.cin, s.cout, s.k, s.stride, s.pad) if s.kind == "conv"
+                        else nn.ConvTranspose2d(s.cin, s.cout, s.k, s.stride, s.pad, s.outpad))
+        self.relu = nn.ReLU()
+        for n in ("conv1", "conv2", "conv3", "conv4", "conv5", "conv1_s", "conv2_s", "conv3_s", "conv4_s", "transConv1", "transConv2", "conv6"):
+            setattr(self, n, mk(sp[n]))
+        self.skipConv1 = nn.Sequential(mk(sp["skipConv1.0"]), self.relu, mk(sp["skipConv1.2"]), self.relu, mk(sp["skipConv1.4"]), self.relu)
+        self.skipConv2 = mk(sp["skipConv2"])
+        self.skipConv3 = mk(sp["skipConv3"])
+        for n in ("res1_s", "res2_s", "res3_s", "res4_s"):     # surface-branch activations after simplify() (models.py:49-52)
+            self.register_buffer(n, None)
+
+        def _init(m):                                          # models.py:55-59: Conv2d only; ConvTranspose2d keeps the default init
+            if type(m) == nn.Conv2d:
+                nn.init.kaiming_normal_(m.weight)
+        self.apply(_init)
+
+    def simplify(self, s: Tensor):
+        """models.py:62-71 / :268-277: cache the surface branch for a constant surface image."""
+        with torch.no_grad():
+            r = _Stack.surface_branch(self, ops._f32c(s))
+        self.res1_s, self.res2_s, self.res3_s, self.res4_s = (t.squeeze() for t in r)
+
+    def _run(self, x: Tensor, surf: Optional[Tensor], skip_in: Tensor) -> Tensor:
+        cached = self.res1_s is not None
+        params = [p for _, p in self.named_parameters()]
+        return _StackFn.apply(self, x, None if cached else surf, skip_in, cached, *params)
+
+
+class CompenNet(_ConvStackNet):
+    """models.py:11-94."""
+
+    def __init__(self):
+        super().__init__()
+        self.name = "CompenNet"
+        self._build("compen", 3)
+
+    def forward(self, x: Tensor, s: Tensor) -> Tensor:
+        ops._need_cuda(x, s)
+        return self._run(x, s, x)
+
+
+class ShadingNetSPAA(_ConvStackNet):
+    """models.py:214-303."""
+
+    def __init__(self, use_rough: bool = True):
+        super().__init__()
+        self.use_rough = use_rough
+        self.name = self.__class__.__name__ if use_rough else self.__class__.__name__ + "_no_rough"
+        self._build("shading", 6 if use_rough else 3)
+
+    def forward(self, x: Tensor, *argv: Tensor) -> Tensor:
+        ops._need_cuda(x, *argv)
+        surf = argv[0] if len(argv) == 1 else torch.cat(argv, 1)
+        return self._run(x, surf, argv[0])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# WarpingNet (models.py:98-185)
+# --------------------------------------------------------------------------------------------------------------
+
+_REFINE_SPECS = [ConvSpec("conv", 2, 32, 3, 2, 1), ConvSpec("conv", 32, 64, 3, 2, 1), ConvSpec("convT", 64, 32, 2, 2, 0),
+                 ConvSpec("convT", 32, 2, 2, 2, 0)]
+_REFINE_IDX = [0, 2, 4, 6]
+
+
+class _CoarseGridFn(torch.autograd.Function):
+    """grid_sample(affine_grid(affine; input size), tps_grid(theta; out size)) fused analytically -> planar [2,H,W]."""
+
+    @staticmethod
+    def forward(ctx, affine, theta, ctrl, in_hw, out_hw):
+        ctx.save_for_backward(affine, theta, ctrl)
+        ctx.in_hw, ctx.out_hw = in_hw, out_hw
+        return ops.coarse_grid(affine, theta, ctrl, in_hw, out_hw)
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        affine, theta, ctrl = ctx.saved_tensors
+        daff, dtheta = ops.coarse_grid_bwd(affine, theta, ctrl, ctx.in_hw, ctx.out_hw, dgrid)
+        return daff.view_as(affine), dtheta.view_as(theta), None, None, None
+
+
+class _RefineFn(torch.autograd.Function):
+    """fine = clamp(refine_net(coarse) + coarse, -1, 1) on ONE copy of the grid (the reference runs the refinement net
+    on B identical copies, models.py:172-176; the result and, by linearity, the gradients are the same)."""
+
+    @staticmethod
+    def forward(ctx, net, coarse, *params):
+        g = coarse.unsqueeze(0)
+        w = [net.grid_refine_net[i] for i in _REFINE_IDX]
+        a1 = ops.conv_forward(_REFINE_SPECS[0], g, w[0].weight, w[0].bias, epi=EPI_RELU)
+        a2 = ops.conv_forward(_REFINE_SPECS[1], a1, w[1].weight, w[1].bias, epi=EPI_RELU)
+        a3 = ops.conv_forward(_REFINE_SPECS[2], a2, w[2].weight, w[2].bias, epi=EPI_RELU)
+        # last layer: LeakyReLU(0.1) then + coarse (residual added after the activation)
+        s = ops.conv_forward(_REFINE_SPECS[3], a3, w[3].weight, w[3].bias, add=g, epi=EPI_LEAKY01 | EPI_ADD_AFTER_ACT)
+        pre4 = None
+        if any(p.requires_grad for p in params) or coarse.requires_grad:
+            pre4 = s - g            # leaky(pre): sign(pre) == sign(leaky(pre)) so it serves as the LeakyReLU mask
+        fine = ops.grid_finish(s[0], None)
+        ctx.net = net
+        ctx.saved = (g, a1, a2, a3, s, pre4)
+        return fine
+
+    @staticmethod
+    def backward(ctx, dfine):
+        net = ctx.net
+        g, a1, a2, a3, s, pre4 = ctx.saved
+        w = [net.grid_refine_net[i] for i in _REFINE_IDX]
+        ds = ops.grid_finish_bwd(s[0], None, dfine).unsqueeze(0)                 # clamp backward
+        d4 = ops.select_cotangent(ds, None, None, pre4, MASK_LEAKY01, torch.empty_like(ds))
+        grads = [torch.zeros_like(p) for m in w for p in (m.weight, m.bias)]
+        ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7])
+        d3 = ops.conv_backward_data(_REFINE_SPECS[3], d4, w[3].weight, a3.shape[2:], mask=a3, mask_mode=MASK_POS)
+        ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5])
+        d2 = ops.conv_backward_data(_REFINE_SPECS[2], d3, w[2].weight, a2.shape[2:], mask=a2, mask_mode=MASK_POS)
+        ops.conv_backward_weight(_REFINE_SPECS[1], a1, d2, grads[2], grads[3])
+        d1 = ops.conv_backward_data(_REFINE_SPECS[1], d2, w[1].weight, a1.shape[2:], mask=a1, mask_mode=MASK_POS)
+        ops.conv_backward_weight(_REFINE_SPECS[0], g, d1, grads[0], grads[1])
+        dg = ops.conv_backward_data(_REFINE_SPECS[0], d1, w[0].weight, g.shape[2:], add=ds)      # + identity path
+        ctx.saved = None
+        return (None, dg[0]) + tuple(grads)
+
+
+class _ClampGridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coarse):
+        ctx.save_for_backward(coarse)
+        return ops.grid_finish(coarse, None)
+
+    @staticmethod
+    def backward(ctx, dfine):
+        coarse, = ctx.saved_tensors
+        return ops.grid_finish_bwd(coarse, None, dfine)
+
+
+class _WarpFn(torch.autograd.Function):
+    """out = grid_sample(x, grid) [* mask]; optionally sfeat = cat(s, out * s) written in the same pass."""
+
+    @staticmethod
+    def forward(ctx, x, grid, mask, s):
+        x = ops._f32c(x)
+        B, C = x.shape[:2]
+        H, W = grid.shape[-2:]
+        sfeat = None
+        if s is not None:
+            s = ops._f32c(s)
+            sfeat = torch.empty((B, 2 * C, H, W), dtype=torch.float32, device=x.device)
+            sfeat[:, :C] = s
+            out = ops.grid_sample(x, grid, mask=mask, rough=s, out2=sfeat[:, C:])
+        else:
+            out = ops.grid_sample(x, grid, mask=mask)
+        ctx.save_for_backward(x, grid, mask, s)
+        if sfeat is None:
+            return out
+        return out, sfeat
+
+    @staticmethod
+    def backward(ctx, dout, dsfeat=None):
+        x, grid, mask, s = ctx.saved_tensors
+        C = x.shape[1]
+        dout = ops._f32c(dout)
+        d2 = None
+        if dsfeat is not None and s is not None:
+            dsfeat = ops._f32c(dsfeat)
+            d2 = dsfeat[:, C:]
+        dx = dgrid = ds = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.grid_sample_bwd_input(dout, grid, x.shape[2:], mask=mask, dout2=d2, rough=s)
+        if ctx.needs_input_grad[1]:
+            dgrid = ops.grid_sample_bwd_grid(dout, x, grid, mask=mask, dout2=d2, rough=s)
+            if grid.dim() == 4 and dgrid.dim() == 3:
+                dgrid = dgrid.unsqueeze(0)
+        if ctx.needs_input_grad[3] and dsfeat is not None:
+            # sfeat = cat(s, out*s): d s = dsfeat[:, :C] + dsfeat[:, C:] * out   (rarely needed: s is data)
+            out = ops.grid_sample(x, grid, mask=mask)
+            ds = dsfeat[:, :C] + d2 * out
+        return dx, dgrid, None, ds
+
+
+class WarpingNet(nn.Module):
+    def __init__(self, grid_shape=(6, 6), out_size=(256, 256), with_refine=True):
+        super().__init__()
+        self.grid_shape = grid_shape
+        self.out_size = tuple(out_size)
+        self.with_refine = with_refine
+        self.name = self.__class__.__name__ if with_refine else self.__class__.__name__ + "_without_refine"
+        self.relu = nn.ReLU()
+        self.leakyRelu = nn.LeakyReLU(0.1)
+        self.register_buffer("fine_grid", None)
+        self.affine_mat = nn.Parameter(torch.Tensor([1, 0, 0, 0, 1, 0]).view(-1, 2, 3))
+        self.nctrl = self.grid_shape[0] * self.grid_shape[1]
+        self.nparam = self.nctrl + 2
+        self.register_buffer("ctrl_pts", pytorch_tps.uniform_grid(grid_shape).view(-1, 2))
+        self.theta = nn.Parameter(torch.ones((1, self.nparam * 2), dtype=torch.float32).view(-1, self.nparam, 2) * 1e-3)
+
+        def init_normal(m):                                    # models.py:124-126 (Conv2d only)
+            if type(m) == nn.Conv2d:
+                nn.init.normal_(m.weight, 0, 1e-4)
+
+        if self.with_refine:
+            self.grid_refine_net = nn.Sequential(
+                nn.Conv2d(2, 32, 3, 2, 1), self.relu, nn.Conv2d(32, 64, 3, 2, 1), self.relu,
+                nn.ConvTranspose2d(64, 32, 2, 2, 0), self.relu, nn.ConvTranspose2d(32, 2, 2, 2, 0), self.leakyRelu)
+            self.grid_refine_net.apply(init_normal)
+        else:
+            self.grid_refine_net = None
+
+    def set_affine(self, affine_vec):
+        self.affine_mat.data = torch.Tensor(affine_vec).view(-1, 2, 3).to(self.affine_mat.device)
+
+    def planar_grid(self, in_hw) -> Tensor:
+        """The fine sampling grid as a planar [2,H,W] tensor shared by the whole batch (with autograd to the parameters)."""
+        if self.fine_grid is not None:
+            return self.fine_grid[0].permute(2, 0, 1).contiguous()
+        coarse = _CoarseGridFn.apply(self.affine_mat, self.theta, self.ctrl_pts, tuple(in_hw), self.out_size)
+        if self.with_refine:
+            params = [p for m in (self.grid_refine_net[i] for i in _REFINE_IDX) for p in (m.weight, m.bias)]
+            return _RefineFn.apply(self, coarse, *params)
+        return _ClampGridFn.apply(coarse)
+
+    def simplify(self, x: Tensor):
+        """models.py:149-161: freeze the sampling grid (stored as 1xHxWx2 like the reference)."""
+        with torch.no_grad():
+            g = self.planar_grid(x.shape[2:])
+        self.fine_grid = g.permute(1, 2, 0).unsqueeze(0).contiguous()
+
+    def forward(self, x: Tensor) -> Tensor:
+        ops._need_cuda(x)
+        return _WarpFn.apply(x, self.planar_grid(x.shape[2:]), None, None)
+
+
+class CompenNetPlusplus(nn.Module):
+    """models.py:188-212."""
+
+    def __init__(self, warping_net=None, compen_net=None):
+        super().__init__()
+        self.name = "CompenNet++"
+        self.warping_net = copy.deepcopy(warping_net.module) if warping_net is not None else WarpingNet()
+        self.compen_net = copy.deepcopy(compen_net.module) if compen_net is not None else CompenNet()
+
+    def simplify(self, s):
+        self.warping_net.simplify(s)
+        self.compen_net.simplify(self.warping_net(s))
+
+    def forward(self, x, s):
+        ops._need_cuda(x, s)
+        grid = self.warping_net.planar_grid(x.shape[2:])
+        x = _WarpFn.apply(x, grid, None, None)
+        s = _WarpFn.apply(s, grid, None, None)
+        return self.compen_net(x, s)
+
+
+class PCNet(nn.Module):
+    """models.py:305-346."""
+
+    def __init__(self, mask, warping_net=None, shading_net=None, fix_shading_net=False, use_mask=True, use_rough=True):
+        super().__init__()
+        self.name = self.__class__.__name__
+        self.use_mask = use_mask
+        self.use_rough = use_rough
+        if not self.use_mask:
+            self.name += "_no_mask"
+        if not self.use_rough:
+            self.name += "_no_rough"
+        self.warping_net = copy.deepcopy(warping_net.module) if warping_net is not None else WarpingNet()
+        self.shading_net = copy.deepcopy(shading_net.module) if shading_net is not None else ShadingNetSPAA()
+        if self.use_mask:
+            self.register_buffer("mask", mask.clone())
+        for param in self.shading_net.parameters():
+            param.requires_grad = not fix_shading_net
+
+    def simplify(self, s):
+        self.warping_net.simplify(s)
+        self.shading_net.simplify(self.warping_net(s))
+
+    def flat_mask(self) -> Optional[Tensor]:
+        if not self.use_mask:
+            return None
+        return self.mask.to(torch.float32).reshape(-1).contiguous()
+
+    def forward(self, x, s):
+        ops._need_cuda(x, s)
+        grid = self.warping_net.planar_grid(x.shape[2:])
+        if s.shape[0] != x.shape[0]:
+            s = s.expand(x.shape[0], -1, -1, -1)
+        if self.use_rough:
+            xw, sfeat = _WarpFn.apply(x, grid, self.flat_mask(), s)
+            return self.shading_net._run(xw, sfeat, s)
+        xw = _WarpFn.apply(x, grid, self.flat_mask(), None)
+        return self.shading_net._run(xw, s, s)

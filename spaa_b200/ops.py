@@ -1,0 +1,487 @@
+"""Thin tensor-level wrappers over the C ABI (include/spaa_b200.h).
+
+PyTorch is used for device memory, streams and autograd plumbing only; every function here launches hand-written
+sm_100a kernels from libspaa_b200.so on torch's current CUDA stream.  There is no CPU path: inputs must be CUDA
+tensors and the library must be built (spaa_b200.build) -- otherwise an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import ConvDesc, lib
+
+Tensor = torch.Tensor
+
+EPI_RELU, EPI_LEAKY01, EPI_CLAMP_MAX1, EPI_ADD_AFTER_ACT = 1, 2, 4, 8
+MASK_NONE, MASK_POS, MASK_LEAKY01, MASK_OPEN01 = 0, 1, 2, 3
+
+_launches = 0      # number of kernels launched through this module (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("spaa_b200 kernels need CUDA tensors (there is no CPU fallback); got a "
+                               f"{t.device} tensor of shape {tuple(t.shape)}")
+
+
+def _f32c(t: Tensor) -> Tensor:
+    _need_cuda(t)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_ws_cache: Dict[Tuple[str, int, int], Tensor] = {}
+
+
+def workspace(tag: str, nbytes: int, device) -> Tensor:
+    """Zero-initialised scratch owned by this module; kernels leave it zeroed (self-resetting counters), so it is
+    reused across launches on the same stream.  Distinct `tag`s never alias."""
+    dev = torch.device(device)
+    key = (tag, dev.index if dev.index is not None else torch.cuda.current_device(), int(nbytes))
+    t = _ws_cache.get(key)
+    if t is None:
+        t = torch.zeros((int(nbytes) + 3) // 4, dtype=torch.int32, device=dev)
+        _ws_cache[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------
+# colour
+# ------------------------------------------------------------------------------------------------------------
+
+def rgb2lab(rgb: Tensor) -> Tensor:
+    rgb = _f32c(rgb)
+    B, C, H, W = rgb.shape
+    assert C == 3
+    lab = torch.empty_like(rgb)
+    lib().spaa_rgb2lab_fwd(_p(rgb), _p(lab), B, H * W, _stream()); _count()
+    return lab
+
+
+def rgb2lab_bwd(rgb: Tensor, dlab: Tensor) -> Tensor:
+    rgb, dlab = _f32c(rgb), _f32c(dlab)
+    B, _, H, W = rgb.shape
+    out = torch.empty_like(rgb)
+    lib().spaa_rgb2lab_bwd(_p(rgb), _p(dlab), _p(out), B, H * W, _stream()); _count()
+    return out
+
+
+def _bstride(t: Tensor, B: int) -> int:
+    if t.shape[0] == B:
+        return t.stride(0)
+    if t.shape[0] == 1:
+        return 0
+    raise ValueError(f"batch {t.shape[0]} does not broadcast to {B}")
+
+
+def de2000(lab1: Tensor, lab2: Tensor) -> Tensor:
+    lab1, lab2 = _f32c(lab1), _f32c(lab2)
+    B = max(lab1.shape[0], lab2.shape[0])
+    H, W = lab1.shape[-2:]
+    de = torch.empty((B, H, W), dtype=torch.float32, device=lab1.device)
+    lib().spaa_de2000_fwd(_p(lab1), _bstride(lab1, B), _p(lab2), _bstride(lab2, B), _p(de), B, H * W, _stream()); _count()
+    return de
+
+
+def de2000_bwd(lab1: Tensor, lab2: Tensor, cot: Tensor, need1: bool = True, need2: bool = True):
+    lab1, lab2, cot = _f32c(lab1), _f32c(lab2), _f32c(cot)
+    B = max(lab1.shape[0], lab2.shape[0])
+    H, W = lab1.shape[-2:]
+    d1 = torch.empty((B, 3, H, W), dtype=torch.float32, device=lab1.device) if need1 else None
+    d2 = torch.empty((B, 3, H, W), dtype=torch.float32, device=lab1.device) if need2 else None
+    lib().spaa_de2000_bwd(_p(lab1), _bstride(lab1, B), _p(lab2), _bstride(lab2, B), _p(cot), _p(d1), _p(d2), B, H * W,
+                          _stream()); _count()
+    if d1 is not None and lab1.shape[0] == 1 and B > 1:
+        d1 = d1.sum(0, keepdim=True)
+    if d2 is not None and lab2.shape[0] == 1 and B > 1:
+        d2 = d2.sum(0, keepdim=True)
+    return d1, d2
+
+
+def color_loss(cam: Tensor, ref_rgb: Tensor, ref_lab: Tensor, *, cam_is_lab2: bool, de_weighting: bool, c_de: float,
+               c_l2: float, stats: Optional[Tensor] = None, grad: Optional[Tensor] = None, want_grad: bool = True):
+    """Fused Lab + dE2000 + channel-L2 statistics and gradient (spaa_color_loss_fwd_bwd).
+    Returns (stats [B,4] = sum dE, sum ||.||_2, sum dE^2, 0 ; grad [B,3,H,W] or None)."""
+    cam, ref_rgb, ref_lab = _f32c(cam), _f32c(ref_rgb), _f32c(ref_lab)
+    B, _, H, W = cam.shape
+    assert ref_rgb.shape == ref_lab.shape
+    if stats is None:
+        stats = torch.empty((B, 4), dtype=torch.float32, device=cam.device)
+    if grad is None and want_grad:
+        grad = torch.empty_like(cam)
+    L = lib()
+    ws = workspace("color_loss", L.spaa_color_loss_ws_bytes(B, H * W), cam.device)
+    L.spaa_color_loss_fwd_bwd(_p(cam), _p(ref_rgb), _p(ref_lab), _bstride(ref_rgb, B), B, H * W, int(cam_is_lab2),
+                              int(de_weighting), float(c_de), float(c_l2), _p(stats), _p(grad), _p(ws), _stream()); _count()
+    return stats, grad
+
+
+# ------------------------------------------------------------------------------------------------------------
+# warping
+# ------------------------------------------------------------------------------------------------------------
+
+def tps_grid(theta: Tensor, ctrl: Tensor, H: int, W: int) -> Tensor:
+    """pytorch_tps.tps_grid as a planar [2,H,W] grid (x plane, y plane)."""
+    theta, ctrl = _f32c(theta), _f32c(ctrl)
+    T = ctrl.shape[0]
+    assert theta.numel() == (T + 2) * 2, "only the reduced TPS form (T+2 rows) is implemented, as used by WarpingNet"
+    g = torch.empty((2, H, W), dtype=torch.float32, device=theta.device)
+    lib().spaa_tps_grid_fwd(_p(theta), _p(ctrl), T, H, W, _p(g), _stream()); _count()
+    return g
+
+
+def coarse_grid(affine: Tensor, theta: Tensor, ctrl: Tensor, in_hw, out_hw) -> Tensor:
+    affine, theta, ctrl = _f32c(affine), _f32c(theta), _f32c(ctrl)
+    T = ctrl.shape[0]
+    g = torch.empty((2, out_hw[0], out_hw[1]), dtype=torch.float32, device=theta.device)
+    lib().spaa_coarse_grid_fwd(_p(affine), _p(theta), _p(ctrl), T, in_hw[0], in_hw[1], out_hw[0], out_hw[1], _p(g), _stream()); _count()
+    return g
+
+
+def coarse_grid_bwd(affine: Optional[Tensor], theta: Tensor, ctrl: Tensor, in_hw, out_hw, dgrid: Tensor):
+    theta, ctrl, dgrid = _f32c(theta), _f32c(ctrl), _f32c(dgrid)
+    T = ctrl.shape[0]
+    L = lib()
+    daff = torch.empty((1, 2, 3), dtype=torch.float32, device=theta.device) if affine is not None else None
+    dtheta = torch.empty_like(theta)
+    ws = workspace("coarse_grid", L.spaa_coarse_grid_ws_bytes(T, out_hw[0], out_hw[1]), theta.device)
+    L.spaa_coarse_grid_bwd(_p(_f32c(affine)) if affine is not None else None, _p(theta), _p(ctrl), T, in_hw[0], in_hw[1], out_hw[0],
+                           out_hw[1], _p(dgrid), _p(daff), _p(dtheta), _p(ws), _stream()); _count()
+    return daff, dtheta
+
+
+def grid_finish(coarse: Tensor, refine: Optional[Tensor]) -> Tensor:
+    coarse = _f32c(coarse)
+    refine = _f32c(refine) if refine is not None else None
+    fine = torch.empty_like(coarse)
+    lib().spaa_grid_finish_fwd(_p(coarse), _p(refine), _p(fine), coarse.numel(), _stream()); _count()
+    return fine
+
+
+def grid_finish_bwd(coarse: Tensor, refine: Optional[Tensor], dfine: Tensor) -> Tensor:
+    coarse, dfine = _f32c(coarse), _f32c(dfine)
+    refine = _f32c(refine) if refine is not None else None
+    d = torch.empty_like(coarse)
+    lib().spaa_grid_finish_bwd(_p(coarse), _p(refine), _p(dfine), _p(d), coarse.numel(), _stream()); _count()
+    return d
+
+
+def _grid_bs(grid: Tensor, B: int) -> int:
+    if grid.dim() == 3:
+        return 0
+    return _bstride(grid, B)
+
+
+def grid_sample(img: Tensor, grid: Tensor, *, clamp01: bool = False, mask: Optional[Tensor] = None,
+                out: Optional[Tensor] = None, rough: Optional[Tensor] = None, out2: Optional[Tensor] = None) -> Tensor:
+    """img [B,C,Hi,Wi]; grid planar [2,H,W] (shared) or [B,2,H,W]; mask [H*W] floats; out [B,C,H,W].
+    rough/out2: out2 = out * rough written in the same pass (out2 may be a channel slice of a wider tensor)."""
+    img, grid = _f32c(img), _f32c(grid)
+    B, C, Hi, Wi = img.shape
+    H, W = grid.shape[-2:]
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=img.device)
+    assert out.is_contiguous()
+    rb = ob = 0
+    if out2 is not None:
+        assert rough is not None and rough.dtype == torch.float32 and out2.dtype == torch.float32
+        assert rough.stride(1) == H * W and rough.stride(3) == 1 and out2.stride(1) == H * W and out2.stride(3) == 1
+        rb, ob = _bstride(rough, B), out2.stride(0)
+    lib().spaa_grid_sample_fwd(_p(img), B, C, Hi, Wi, _p(grid), _grid_bs(grid, B), H, W, int(clamp01), _p(mask), _p(out),
+                               _p(rough) if out2 is not None else None, rb, _p(out2), ob, _stream()); _count()
+    return out
+
+
+def grid_sample_bwd_input(dout: Tensor, grid: Tensor, in_hw, *, mask: Optional[Tensor] = None, dout2: Optional[Tensor] = None,
+                          rough: Optional[Tensor] = None, dimg: Optional[Tensor] = None) -> Tensor:
+    dout, grid = _f32c(dout), _f32c(grid)
+    B, C, H, W = dout.shape
+    if dimg is None:
+        dimg = torch.zeros((B, C, in_hw[0], in_hw[1]), dtype=torch.float32, device=dout.device)
+    else:
+        dimg.zero_()
+    db = rb = 0
+    if dout2 is not None:
+        assert dout2.stride(1) == H * W and dout2.stride(3) == 1 and rough.stride(1) == H * W
+        db, rb = dout2.stride(0), _bstride(rough, B)
+    lib().spaa_grid_sample_bwd_input(_p(dout), _p(dout2), db, _p(rough) if dout2 is not None else None, rb, _p(mask), _p(grid),
+                                     _grid_bs(grid, B), B, C, in_hw[0], in_hw[1], H, W, _p(dimg), _stream()); _count()
+    return dimg
+
+
+def grid_sample_bwd_grid(dout: Tensor, img: Tensor, grid: Tensor, *, clamp01: bool = False, mask: Optional[Tensor] = None,
+                         dout2: Optional[Tensor] = None, rough: Optional[Tensor] = None) -> Tensor:
+    dout, img, grid = _f32c(dout), _f32c(img), _f32c(grid)
+    B, C, H, W = dout.shape
+    Hi, Wi = img.shape[-2:]
+    shared = grid.dim() == 3 or grid.shape[0] == 1
+    dgrid = torch.empty((2, H, W) if shared else (B, 2, H, W), dtype=torch.float32, device=dout.device)
+    db = rb = 0
+    if dout2 is not None:
+        db, rb = dout2.stride(0), _bstride(rough, B)
+    lib().spaa_grid_sample_bwd_grid(_p(dout), _p(dout2), db, _p(rough) if dout2 is not None else None, rb, _p(mask), _p(img),
+                                    int(clamp01), _p(grid), 0 if shared else grid.stride(0), B, C, Hi, Wi, H, W, _p(dgrid),
+                                    _stream()); _count()
+    return dgrid
+
+
+# ------------------------------------------------------------------------------------------------------------
+# convolution (gather conv, see include/spaa_b200.h)
+# ------------------------------------------------------------------------------------------------------------
+
+class ConvSpec:
+    """Static description of an nn.Conv2d (kind 'conv') or nn.ConvTranspose2d (kind 'convT') layer."""
+
+    def __init__(self, kind: str, cin: int, cout: int, k: int, stride: int = 1, pad: int = 0, outpad: int = 0):
+        assert kind in ("conv", "convT")
+        self.kind, self.cin, self.cout, self.k, self.stride, self.pad, self.outpad = kind, cin, cout, k, stride, pad, outpad
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        if self.kind == "conv":
+            f = lambda n: (n + 2 * self.pad - self.k) // self.stride + 1
+        else:
+            f = lambda n: (n - 1) * self.stride - 2 * self.pad + self.k + self.outpad
+        return f(h), f(w)
+
+    def weight_shape(self):
+        return (self.cout, self.cin, self.k, self.k) if self.kind == "conv" else (self.cin, self.cout, self.k, self.k)
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _act_strides(t: Tensor) -> Tuple[int, int, int]:
+    """(batch, pixel, channel) element strides of a logical [B,C,H,W] tensor (NCHW or channels-last, or a channel slice)."""
+    sb, sc, sh, sw = t.stride()
+    if t.shape[2] > 1 and sh != t.shape[3] * sw:
+        raise ValueError("activation rows must be densely packed (stride_h == W * stride_w)")
+    return (0 if t.shape[0] == 1 else sb), sw, sc
+
+
+def _fill_desc(d: ConvDesc, x: Tensor, out: Tensor, add: Optional[Tensor], mask: Optional[Tensor]) -> None:
+    d.in_dtype, d.out_dtype = _dt(x), _dt(out)
+    d.B = out.shape[0]
+    d.Hin, d.Win = x.shape[2], x.shape[3]
+    d.Hout, d.Wout = out.shape[2], out.shape[3]
+    d.in_bs, d.in_ps, d.in_cs = _act_strides(x)
+    d.out_bs, d.out_ps, d.out_cs = _act_strides(out)
+    if add is not None:
+        assert add.dtype == out.dtype and add.shape[1:] == out.shape[1:]
+        d.add_bs, d.add_ps, d.add_cs = _act_strides(add)
+    if mask is not None:
+        assert mask.dtype == out.dtype and mask.shape[1:] == out.shape[1:]
+        d.mask_bs, d.mask_ps, d.mask_cs = _act_strides(mask)
+
+
+def _w_strides(w: Tensor, k: int):
+    assert w.dtype == torch.float32 and w.stride(3) == 1 and (k == 1 or w.stride(2) == k), "weights must be fp32 with dense taps"
+    return w.stride(0), w.stride(1)
+
+
+def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, out: Optional[Tensor] = None,
+                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None) -> Tensor:
+    """Forward of nn.Conv2d / nn.ConvTranspose2d with the fused epilogue `epi` (bias, residual add, activation, clamp)."""
+    _need_cuda(x, w)
+    B, _, H, W = x.shape
+    Ho, Wo = spec.out_hw(H, W)
+    if out is None:
+        out = torch.empty((B, spec.cout, Ho, Wo), dtype=out_dtype or x.dtype, device=x.device)
+    d = ConvDesc()
+    d.Cin, d.Cout, d.KH, d.KW = spec.cin, spec.cout, spec.k, spec.k
+    s0, s1 = _w_strides(w, spec.k)
+    d.w_ts = 1
+    if spec.kind == "conv":
+        d.stride, d.up, d.pad_h, d.pad_w, d.flip = spec.stride, 1, spec.pad, spec.pad, 0
+        d.w_cos, d.w_cis = s0, s1
+    else:
+        d.stride, d.up, d.flip = 1, spec.stride, 1
+        d.pad_h = d.pad_w = spec.k - 1 - spec.pad
+        d.w_cis, d.w_cos = s0, s1
+    d.epi_flags, d.mask_mode = epi, MASK_NONE
+    _fill_desc(d, x, out, add, None)
+    lib().spaa_conv_fwd(ctypes.byref(d), _p(x), _p(w), _p(b), _p(add), None, None, _p(out), None, _stream()); _count()
+    return out
+
+
+def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Optional[Tensor] = None, add: Optional[Tensor] = None,
+                       mask: Optional[Tensor] = None, mask_mode: int = MASK_NONE, mask2: Optional[Tensor] = None,
+                       out2: Optional[Tensor] = None, out_dtype=None) -> Tensor:
+    """Gradient wrt the layer input: out = mask(mask_mode) * (bwd_data(dy) + add); out2 = out * (mask2 > 0).
+    `w` may be a channel-sliced view of the parameter (to produce only some input channels' gradients)."""
+    _need_cuda(dy, w)
+    B = dy.shape[0]
+    cin = w.shape[1] if spec.kind == "conv" else w.shape[0]      # possibly sliced
+    if out is None:
+        out = torch.empty((B, cin, in_hw[0], in_hw[1]), dtype=out_dtype or dy.dtype, device=dy.device)
+    d = ConvDesc()
+    d.Cin, d.Cout, d.KH, d.KW = spec.cout, cin, spec.k, spec.k
+    s0, s1 = _w_strides(w, spec.k)
+    d.w_ts = 1
+    if spec.kind == "conv":       # dX = gather conv of dY with flipped taps, up = stride
+        d.stride, d.up, d.flip = 1, spec.stride, 1
+        d.pad_h = d.pad_w = spec.k - 1 - spec.pad
+        d.w_cis, d.w_cos = s0, s1
+    else:                         # ConvTranspose backward-data is a plain strided conv
+        d.stride, d.up, d.pad_h, d.pad_w, d.flip = spec.stride, 1, spec.pad, spec.pad, 0
+        d.w_cos, d.w_cis = s0, s1
+    d.epi_flags, d.mask_mode = 0, (mask_mode if mask is not None else MASK_NONE)
+    _fill_desc(d, dy, out, add, mask if mask is not None else mask2)
+    if mask2 is not None:
+        assert out2 is not None and out2.stride() == out.stride()
+        if mask is not None:
+            assert mask2.stride()[1:] == mask.stride()[1:]
+    lib().spaa_conv_fwd(ctypes.byref(d), _p(dy), _p(w), None, _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream()); _count()
+    return out
+
+
+def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor]) -> None:
+    """dw += d(loss)/d(weight), db += d(loss)/d(bias); dw/db are fp32 accumulators in the parameter's own layout."""
+    _need_cuda(x, dy, dw)
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    d = ConvDesc()
+    d.KH = d.KW = spec.k
+    d.stride, d.up, d.pad_h, d.pad_w, d.flip = spec.stride, 1, spec.pad, spec.pad, 0
+    d.w_ts = 1
+    L = lib()
+    if spec.kind == "conv":
+        d.Cin, d.Cout = spec.cin, spec.cout
+        d.w_cos, d.w_cis = dw.stride(0), dw.stride(1)
+        _fill_desc(d, x, dy, None, None)
+        L.spaa_conv_bwd_weight(ctypes.byref(d), _p(x), _p(dy), _p(dw), _p(db), _stream()); _count(2 if db is not None else 1)
+    else:
+        # dWt[ci,co,r,s] = sum in[iy,ci] * dOut[iy*s-p+r, co]: the gathered operand is dOut, the pointwise one is `x`
+        d.Cin, d.Cout = spec.cout, spec.cin
+        d.w_cis, d.w_cos = dw.stride(1), dw.stride(0)
+        _fill_desc(d, dy, x, None, None)
+        L.spaa_conv_bwd_weight(ctypes.byref(d), _p(dy), _p(x), _p(dw), None, _stream()); _count()
+        if db is not None:
+            channel_sum(dy, db)
+
+
+def channel_sum(x: Tensor, out: Tensor) -> None:
+    """out[c] += sum over batch and pixels of x[:, c]."""
+    bs, ps, cs = _act_strides(x)
+    lib().spaa_channel_sum(_p(x), _dt(x), x.shape[0], x.shape[1], x.shape[2] * x.shape[3], bs, ps, cs, _p(out), _stream()); _count()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# training loss / optimiser
+# ------------------------------------------------------------------------------------------------------------
+
+def ssim_l1(pred: Tensor, target: Tensor, w_l1: float, w_l2: float, w_ssim: float, *, want_grad: bool = True,
+            want_map: bool = False, cot_map: Optional[Tensor] = None):
+    """Returns (sums[4] = sum|d|, sum d^2, sum ssim, 0 ; grad or None ; ssim_map or None)."""
+    pred, target = _f32c(pred), _f32c(target)
+    assert pred.shape == target.shape
+    B, C, H, W = pred.shape
+    L = lib()
+    sums = torch.empty(4, dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    smap = torch.empty_like(pred) if want_map else None
+    ws = workspace("ssim", L.spaa_ssim_l1_ws_bytes(B * C, H, W), pred.device)
+    L.spaa_ssim_l1_fwd_bwd(_p(pred), _p(target), B * C, H, W, float(w_l1), float(w_l2), float(w_ssim),
+                           _p(_f32c(cot_map)) if cot_map is not None else None, _p(sums), _p(smap), _p(grad), _p(ws), _stream()); _count()
+    return sums, grad, smap
+
+
+def adam_step(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor, seg_wd: Tensor, step: int,
+              beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    for t in (param, grad, m, v):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    lib().spaa_adam_step(_p(param), _p(grad), _p(m), _p(v), param.numel(), _p(seg_end), _p(seg_lr), _p(seg_wd), seg_end.numel(),
+                         beta1, beta2, eps, int(step), float(grad_scale), _stream()); _count()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# attack-loop updates
+# ------------------------------------------------------------------------------------------------------------
+
+def row_sqnorm(g: Tensor, sq: Tensor, x_for_clamp: Optional[Tensor] = None, lo: float = 0.0, hi: float = 1.0) -> Tensor:
+    B = g.shape[0]
+    n = g.numel() // B
+    L = lib()
+    ws = workspace("rownorm", L.spaa_rownorm_ws_bytes(B, n), g.device)
+    L.spaa_row_sqnorm(_p(g), _p(x_for_clamp), lo, hi, B, n, _p(sq), _p(ws), _stream()); _count()
+    return sq
+
+
+def row_normalized_step(x: Tensor, g: Tensor, sq: Tensor, step2: Tensor, sel: Optional[Tensor] = None, *, use_clamp_mask: bool = False,
+                        lo: float = 0.0, hi: float = 1.0, base: Optional[Tensor] = None, sum_out: Optional[Tensor] = None,
+                        copy_dst: Optional[Tensor] = None, copy_sel: Optional[Tensor] = None) -> None:
+    B = x.shape[0]
+    n = x.numel() // B
+    lib().spaa_row_normalized_step(_p(x), _p(g), _p(sq), _p(sel), _p(step2), int(use_clamp_mask), lo, hi, _p(base),
+                                   _bstride(base, B) if base is not None else 0, _p(sum_out), _p(copy_dst), _p(copy_sel), B, n,
+                                   _stream()); _count()
+
+
+def masked_copy_rows(dst: Tensor, src: Tensor, sel: Tensor) -> None:
+    B = dst.shape[0]
+    lib().spaa_masked_copy_rows(_p(dst), _p(src), _p(sel), B, dst.numel() // B, _stream()); _count()
+
+
+def select_cotangent(g0: Tensor, g1: Optional[Tensor], sel: Optional[Tensor], act: Optional[Tensor], mask_mode: int, out: Tensor) -> Tensor:
+    B = g0.shape[0]
+    lib().spaa_select_cotangent(_p(g0), _p(g1), _p(sel), _p(act), mask_mode, _p(out), B, g0.numel() // B, _stream()); _count()
+    return out
+
+
+def percal_project(base: Tensor, delta: Tensor, xq: Tensor, xsum: Optional[Tensor], l2sum: Tensor) -> None:
+    B, _, H, W = delta.shape
+    L = lib()
+    ws = workspace("percal_project", L.spaa_percal_project_ws_bytes(B, H * W), delta.device)
+    L.spaa_percal_project(_p(base), _bstride(base, B), _p(delta), _p(xq), _p(xsum), _p(l2sum), B, H * W, _p(ws), _stream()); _count()
+
+
+def chan_l2(x: Tensor, ref: Tensor, sums: Tensor, *, c: float = 0.0, sel: Optional[Tensor] = None, apply_clamp_mask: bool = False,
+            grad: Optional[Tensor] = None) -> None:
+    B, _, H, W = x.shape
+    L = lib()
+    ws = workspace("chan_l2", L.spaa_chan_l2_ws_bytes(B, H * W), x.device)
+    L.spaa_chan_l2_fwd_bwd(_p(x), _p(ref), _bstride(ref, B), B, H * W, float(c), _p(sel), int(apply_clamp_mask), _p(sums), _p(grad), _p(ws),
+                           _stream()); _count()
+
+
+def attack_masks(logits: Tensor, target: Tensor, targeted: bool, stats: Tensor, prjl2sum: Optional[Tensor], hw_cam: int, hw_prj: int,
+                 w_prjl2: float, w_caml2: float, w_camde: float, d_thr: float, p_thresh: float, use_col: Tensor, succ: Tensor,
+                 better: Tensor, col_loss: Tensor, best_col: Tensor) -> None:
+    logits = _f32c(logits)
+    B, ncls = logits.shape
+    lib().spaa_attack_masks(_p(logits), ncls, _p(target), int(targeted), _p(stats), _p(prjl2sum), hw_cam, hw_prj, float(w_prjl2),
+                            float(w_caml2), float(w_camde), float(d_thr), float(p_thresh), B, _p(use_col), _p(succ), _p(better),
+                            _p(col_loss), _p(best_col), _stream()); _count()
+
+
+def percal_masks(logits: Tensor, labels: Tensor, mode: int, margin: float, l2sum: Tensor, hw: int, d_thr: float, p_thresh: float,
+                 stats: Tensor, isadv: Tensor, use_col: Tensor, better: Tensor, dis: Tensor, best_dis: Tensor) -> None:
+    logits = _f32c(logits)
+    B, ncls = logits.shape
+    lib().spaa_percal_masks(_p(logits), ncls, _p(labels), mode, float(margin), _p(l2sum), hw, float(d_thr), float(p_thresh), _p(stats), B,
+                            _p(isadv), _p(use_col), _p(better), _p(dis), _p(best_dis), _stream()); _count()

@@ -1,0 +1,110 @@
+"""PerC-AL attacker -- API of /root/reference/src/python/perc_al/__init__.py:15-256 on the sm_100a kernels.
+
+Per iteration: classifier forward+backward (cuDNN, external) -> per-sample norm + masked step -> fused Lab + dE2000
+gradient of ||dE map||_2 -> norm + masked step -> fused clamp / quantise / L2 projection -> classifier forward on
+the quantised image -> device-side decision masks and best-so-far copy.  No host synchronisation inside the loop.
+"""
+from __future__ import annotations
+
+from math import cos, pi
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..classifier import device_logits
+from .differential_color_functions import ciede2000_diff, deltaE, rgb2lab_diff  # noqa: F401  (re-exported like the reference)
+
+
+def quantization(x):
+    """:15-18."""
+    return torch.round(x * 255) / 255
+
+
+class PerC_AL:
+    def __init__(self, max_iterations: int = 1000, alpha_l_init: float = 1., alpha_c_init: float = 0.5, confidence: float = 0,
+                 device: torch.device = torch.device("cuda")) -> None:
+        self.max_iterations = max_iterations
+        self.alpha_l_init = alpha_l_init
+        self.alpha_c_init = alpha_c_init
+        self.confidence = confidence
+        self.device = torch.device(device)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _run(self, logits_fn, inputs, labels, targeted, d_thr, p_thresh, projector_rules, trace):
+        if inputs.min() < 0 or inputs.max() > 1:
+            raise ValueError("Input values should be in the [0, 1] range.")
+        ops._need_cuda(inputs)
+        if targeted and self.confidence != 0:
+            print("Only support setting confidence in untargeted case!")
+            return None
+        dev = inputs.device
+        inputs = ops._f32c(inputs)
+        labels = labels.to(dev).long()
+        B, _, H, W = inputs.shape
+        hw = H * W
+        a_l_min, a_c_min = self.alpha_l_init / 100, self.alpha_c_init / 10
+        n_it = self.max_iterations
+        # cosine-annealed step sizes (:184-185) as a device table: row i = (step for ~mask rows, step for mask rows)
+        cosf = [1 + cos(i / n_it * pi) for i in range(n_it)]
+        a_l = [a_l_min + 0.5 * (self.alpha_l_init - a_l_min) * c for c in cosf]
+        a_c = [a_c_min + 0.5 * (self.alpha_c_init - a_c_min) * c for c in cosf]
+        sign = -1.0 if targeted else 1.0
+        # delta += a_l * g/||g|| on ~mask rows with g = grad of (sign * CE): table holds +a_l ; colour: -a_c on mask rows
+        tab_l = torch.tensor([[a, 0.0] for a in a_l], device=dev)
+        tab_c = torch.tensor([[0.0, -a] for a in a_c], device=dev)
+
+        best = inputs.clone()
+        ref_lab = ops.rgb2lab(inputs)
+        delta = torch.zeros_like(inputs)
+        xs = inputs.clone()                       # inputs + delta
+        xs2 = torch.empty_like(inputs)
+        xq = torch.empty_like(inputs)
+        g_c = torch.empty_like(inputs)
+        use_col, isadv, better = (torch.zeros(B, dtype=torch.uint8, device=dev) for _ in range(3))
+        best_dis = torch.ones(B, device=dev) * 100000
+        dis, l2sum, sq = (torch.empty(B, device=dev) for _ in range(3))
+        stats = torch.empty(B, 4, device=dev)
+        if not targeted and self.confidence != 0:
+            mode = 2
+        elif targeted:
+            mode = 1
+        else:
+            mode = 0
+        if not projector_rules:                   # original `adversary`: no perturbation-size / confidence gates
+            d_thr, p_thresh = -1.0, -1.0
+        for i in range(n_it):
+            leaf = xs.detach().requires_grad_(True)
+            with torch.enable_grad():
+                logits = logits_fn(leaf)
+                loss = sign * nn.functional.cross_entropy(logits, labels, reduction="sum")
+                g_a, = torch.autograd.grad(loss, leaf)
+            ops.row_sqnorm(g_a, sq)
+            ops.row_normalized_step(delta, g_a, sq, tab_l[i], use_col, base=inputs, sum_out=xs2)
+            ops.color_loss(xs2, inputs, ref_lab, cam_is_lab2=True, de_weighting=True, c_de=1.0, c_l2=0.0, stats=stats, grad=g_c)
+            ops.row_sqnorm(g_c, sq)
+            ops.row_normalized_step(delta, g_c, sq, tab_c[i], use_col)
+            ops.percal_project(inputs, delta, xq, xs, l2sum)
+            with torch.no_grad():
+                logits2 = logits_fn(xq)
+            ops.percal_masks(logits2, labels, mode, 40.0, l2sum, hw, d_thr, p_thresh, stats, isadv, use_col, better, dis, best_dis)
+            ops.masked_copy_rows(best, xq, isadv if projector_rules else better)      # :244-245 vs :128
+            if trace is not None:
+                trace.append(dict(g_a=g_a.clone(), g_c=g_c.clone(), delta=delta.clone(), dis=dis.clone(), x_round=xq.clone(),
+                                  use_col=use_col.bool().clone(), isadv=isadv.bool().clone(), best=best.clone()))
+        return best
+
+    # ---------------------------------------------------------------------------------------------------------
+    def adversary(self, model: nn.Module, inputs: torch.Tensor, labels: torch.Tensor, targeted: bool = True) -> torch.Tensor:
+        """:53-131: the original digital PerC-AL against a bare model fed (x - 0.5) / 0.5."""
+        def fn(x):
+            return model((x - 0.5) / 0.5)
+        return self._run(fn, inputs, labels, targeted, 0.0, 0.0, False, None)
+
+    def adversary_projector(self, classifier, inputs: torch.Tensor, labels: torch.Tensor, imagenet_labels, d_thr, targeted: bool = True,
+                            cp_sz=(240, 240), trace: Optional[List[dict]] = None) -> torch.Tensor:
+        """:133-256."""
+        def fn(x):
+            return device_logits(classifier, x, cp_sz)
+        return self._run(fn, inputs, labels, targeted, float(d_thr), 0.9, True, trace)

@@ -1,0 +1,289 @@
+"""PCNet / CompenNet++ training -- API of /root/reference/src/python/train_network.py:130-473 on the sm_100a kernels.
+
+One training step = batch gather -> PCNet forward (warp + 17 fused convs) -> ONE fused L1+MSE+SSIM loss/gradient kernel
+-> backward (data + weight kernels) accumulating into a FLAT gradient buffer -> [NCCL all-reduce of that one bucket
+when torch.distributed is initialised, one process per GPU] -> ONE fused Adam launch over the flat parameter buffer with
+per-group learning rates read from a device-side schedule table.  No host synchronisation inside a step.
+"""
+from __future__ import annotations
+
+import math
+import random
+import time
+from os.path import join
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from . import utils as ut
+
+
+class AttrDict(dict):
+    """Minimal stand-in for omegaconf.DictConfig (attribute + item access), which this image does not ship."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+    def copy(self):
+        return AttrDict(dict.copy(self))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------------------------
+
+class _FusedLossFn(torch.autograd.Function):
+    """(w_l1 * L1 + w_l2 * MSE + w_ssim * (1 - SSIM), MSE) with the gradient produced by the same launch."""
+
+    @staticmethod
+    def forward(ctx, pred, target, w_l1, w_l2, w_ssim):
+        need = pred.requires_grad
+        sums, grad, _ = ops.ssim_l1(pred, target, w_l1, w_l2, w_ssim, want_grad=need)
+        n = pred.numel()
+        ctx.grad = grad
+        l2 = sums[1] / n
+        loss = w_l1 * sums[0] / n + w_l2 * l2 + (w_ssim * (1 - sums[2] / n) if w_ssim else 0.0)
+        ctx.mark_non_differentiable(l2)
+        return loss, l2
+
+    @staticmethod
+    def backward(ctx, dloss, _dl2):
+        return ctx.grad * dloss, None, None, None, None
+
+
+def huber(x, y, delta=0.1):
+    """train_network.py:29-36 (pseudo-Huber)."""
+    return ((1 + ((x - y) / delta) ** 2).clamp(1e-4).sqrt() - 1) * delta
+
+
+def compute_loss(prj_infer, prj_train, loss_option):
+    """train_network.py:367-392: substring-selected terms; the MSE is always returned second."""
+    if loss_option == "":
+        raise TypeError("Loss type not specified")
+    ops._need_cuda(prj_infer, prj_train)
+    w_l1 = 1.0 if "l1" in loss_option else 0.0
+    w_l2 = 1.0 if "l2" in loss_option else 0.0
+    w_ssim = 1.0 if "ssim" in loss_option else 0.0
+    train_loss, l2_loss = _FusedLossFn.apply(ops._f32c(prj_infer), ops._f32c(prj_train.detach()), w_l1, w_l2, w_ssim)
+    if "huber" in loss_option:
+        train_loss = train_loss + huber(prj_infer, prj_train).abs().mean()
+    return train_loss, l2_loss
+
+
+# ------------------------------------------------------------------------------------------------------------
+# flat-buffer Adam with per-group schedules
+# ------------------------------------------------------------------------------------------------------------
+
+class FlatAdam:
+    """All trainable parameters live in one flat fp32 buffer (the modules' .data and .grad become views of it), so
+    zero_grad is one memset, the data-parallel all-reduce is one NCCL call on one bucket and the update is one kernel.
+    groups: list of (params, lr, weight_decay, milestones, gamma) -- MultiStepLR / StepLR semantics evaluated per step
+    into a device table so no host value is read while training."""
+
+    def __init__(self, groups: Sequence[Tuple[List[torch.nn.Parameter], float, float, Sequence[int], float]], max_steps: int,
+                 step_lr: Optional[int] = None):
+        groups = [g for g in groups if len(g[0])]
+        dev = groups[0][0][0].device
+        n = sum(p.numel() for g in groups for p in g[0])
+        self.param = torch.empty(n, device=dev)
+        self.grad = torch.zeros(n, device=dev)
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        off, ends = 0, []
+        self.params = []
+        for plist, *_ in groups:
+            for p in plist:
+                k = p.numel()
+                self.param[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.param[off:off + k].view_as(p.data)
+                p.grad = self.grad[off:off + k].view_as(p.data)
+                self.params.append(p)
+                off += k
+            ends.append(off)
+        self.seg_end = torch.tensor(ends, dtype=torch.int64, device=dev)
+        self.seg_wd = torch.tensor([g[2] for g in groups], device=dev)
+        table = []
+        for s in range(max_steps + 1):
+            row = []
+            for _, lr, _, milestones, gamma in groups:
+                if step_lr is not None:
+                    row.append(lr * gamma ** (s // step_lr))
+                else:
+                    row.append(lr * gamma ** sum(1 for m in milestones if s >= m))
+            table.append(row)
+        self.lr_table_host = table
+        self.lr_table = torch.tensor(table, device=dev)
+        self.t = 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p in self.params:                      # autograd may have replaced a .grad view; re-attach
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
+                raise RuntimeError("a parameter's .grad was detached from the flat gradient buffer")
+
+    def step(self, grad_scale: float = 1.0):
+        """One Adam update with the learning rates of scheduler step `self.t` (then advances the schedule)."""
+        self.t += 1
+        row = self.lr_table[min(self.t - 1, self.lr_table.shape[0] - 1)]
+        ops.adam_step(self.param, self.grad, self.m, self.v, self.seg_end, row, self.seg_wd, self.t, grad_scale=grad_scale)
+
+    def lr(self, group: int = 0) -> float:
+        return self.lr_table_host[min(self.t, len(self.lr_table_host) - 1)][group]
+
+
+def _strip(name: str) -> str:
+    return name[len("module."):] if name.startswith("module.") else name
+
+
+def pcnet_param_groups(model, l2_reg: float, lr_drop_ratio: float):
+    """train_network.py:248-265: (affine+theta | refine net | everything else) with their Adam / MultiStepLR settings."""
+    named = [(_strip(n), p) for n, p in model.named_parameters() if p.requires_grad]
+    g1 = [p for n, p in named if n in ("warping_net.affine_mat", "warping_net.theta")]
+    g2 = [p for n, p in named if "warping_net.grid_refine_net" in n]
+    g3 = [p for n, p in named if "warping_net" not in n]
+    return [(g1, 1e-2, 0.0, [100], lr_drop_ratio), (g2, 5e-3, 0.0, [1200], lr_drop_ratio), (g3, 1e-3, l2_reg, [1800], lr_drop_ratio)]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# data parallelism: one process per GPU, one NCCL all-reduce of the flat gradient bucket per step
+# ------------------------------------------------------------------------------------------------------------
+
+def _world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(idx: Sequence[int], rank: int, world: int) -> List[int]:
+    """Global-batch semantics: every rank draws the SAME seeded sample (train_network.py:295) and takes a strided share."""
+    return list(idx[rank::world])
+
+
+def allreduce_grads(opt: FlatAdam, world: int) -> float:
+    """Sum the flat gradient bucket over ranks; returns the scale that turns the sum into the global-batch mean."""
+    if world > 1:
+        dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM)
+        return 1.0 / world
+    return 1.0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# training loops
+# ------------------------------------------------------------------------------------------------------------
+
+def _resident(t: torch.Tensor, device) -> torch.Tensor:
+    return t if t.device == device else t.to(device)
+
+
+def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter, valid_data, title, verbose):
+    device = torch.device(cfg["device"])
+    rank, world = _world()
+    dp_mode = cfg.get("dp_mode", "global")            # 'global': shard one global batch; 'weak': batch_size per rank
+    B = cfg["batch_size"]
+    local_B = B if dp_mode == "weak" else len(shard_indices(list(range(B)), rank, world))
+    scene_batch = scene.expand(local_B, -1, -1, -1)
+    start = time.time()
+    history = torch.zeros(cfg["max_iters"], 2, device=device)        # (loss, mse) per step, read only when printing
+    valid_psnr = valid_rmse = valid_ssim = 0.0
+    print_rate = cfg.get("print_rate", 1 if verbose else 0)
+    iters = 0
+    while iters < cfg["max_iters"]:
+        idx = random.sample(range(cfg["num_train"]), B)             # :295 (python RNG, same draw on every rank)
+        if dp_mode != "weak":
+            idx = shard_indices(idx, rank, world)
+        it = torch.as_tensor(idx, device=device)
+        x_batch, y_batch = inputs.index_select(0, it), targets.index_select(0, it)
+        cfg["loss"] = loss_of_iter(iters)
+        model.train()
+        infer = model(x_batch, scene_batch)
+        loss, l2 = compute_loss(infer, y_batch, cfg["loss"])
+        opt.zero_grad()
+        loss.backward()
+        scale = allreduce_grads(opt, world)
+        opt.step(grad_scale=scale)
+        history[iters, 0], history[iters, 1] = loss.detach(), l2
+        if valid_data is not None and (iters % cfg["valid_rate"] == 0 or iters == cfg["max_iters"] - 1):
+            valid_psnr, valid_rmse, valid_ssim, _ = evaluate_model(model, valid_data)
+        if print_rate and (iters % print_rate == 0 or iters == cfg["max_iters"] - 1) and rank == 0:
+            lv, mv = history[iters].tolist()
+            lapse = time.strftime("%H:%M:%S", time.gmtime(time.time() - start))
+            print(f"Iter:{iters:5d} | Time: {lapse} | Train Loss: {lv:.4f} | Train RMSE: {math.sqrt(mv * 3):.4f} "
+                  f"| Valid PSNR: {f'{valid_psnr:>2.4f}' if valid_psnr else '':7s}  | Valid RMSE: {f'{valid_rmse:.4f}' if valid_rmse else '':6s}  "
+                  f"| Valid SSIM: {f'{valid_ssim:.4f}' if valid_ssim else '':6s}  | Learn Rate: {opt.lr(0):.5f} |")
+        iters += 1
+    cfg["loss_history"] = history
+    if cfg.get("data_root") and rank == 0 and cfg.get("save_checkpoint", True):
+        ut.save_checkpoint(join(cfg["data_root"], "../checkpoint"), model, title)
+    return model, valid_psnr, valid_rmse, valid_ssim
+
+
+def train_pcnet(model, train_data, valid_data, cfg, verbose: bool = True):
+    """train_network.py:235-363.  `model` may be the bare PCNet or wrapped (DataParallel with one device / DDP-style
+    wrappers are unwrapped for parameter naming only)."""
+    device = torch.device(cfg["device"])
+    scene = _resident(train_data["cam_scene"], device)
+    cam_train = _resident(train_data["cam_train"], device)         # kept resident in HBM (855 MB for 500 pairs)
+    prj_train = _resident(train_data["prj_train"], device)
+    if "model_name" not in cfg:
+        cfg["model_name"] = model.name if hasattr(model, "name") else model.module.name
+    opt = FlatAdam(pcnet_param_groups(model, cfg["l2_reg"], cfg["lr_drop_ratio"]), cfg["max_iters"])
+    cfg["loss"] = "l1+ssim"
+    title = ut.opt_to_string(cfg) if "setup_name" in cfg else "pcnet"
+    loss_of_iter = lambda it: "l1" if it <= 400 else "l1+ssim"     # :300-303
+    return _train_loop(model, prj_train, cam_train, scene, cfg, opt, loss_of_iter, valid_data, title, verbose)
+
+
+def train_compennet_pp(model, train_data, valid_data, cfg, verbose: bool = True):
+    """train_network.py:130-232: one Adam (lr, l2_reg), StepLR(lr_drop_rate, lr_drop_ratio), fixed cfg.loss,
+    input = camera image, target = projector image."""
+    device = torch.device(cfg["device"])
+    scene = _resident(train_data["cam_scene"], device)
+    cam_train = _resident(train_data["cam_train"], device)
+    prj_train = _resident(train_data["prj_train"], device)
+    if "model_name" not in cfg:
+        cfg["model_name"] = model.name if hasattr(model, "name") else model.module.name
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = FlatAdam([(params, cfg["lr"], cfg["l2_reg"], [], cfg["lr_drop_ratio"])], cfg["max_iters"], step_lr=cfg["lr_drop_rate"])
+    fixed = cfg["loss"]
+    title = ut.opt_to_string(cfg) if "setup_name" in cfg else "compennet_pp"
+    return _train_loop(model, cam_train, prj_train, scene, cfg, opt, lambda it: fixed, valid_data, title, verbose)
+
+
+def evaluate_model(model, valid_data, chunk_sz=10):
+    """train_network.py:395-441."""
+    cam_scene, cam_valid, prj_valid = valid_data["cam_scene"], valid_data["cam_valid"], valid_data["prj_valid"]
+    device = next(model.parameters()).device
+    name = model.name if hasattr(model, "name") else model.module.name
+    with torch.no_grad():
+        model.eval()
+        valid_psnr = valid_rmse = valid_ssim = 0.0
+        model_infer = torch.zeros(cam_valid.shape if "PCNet" in name else prj_valid.shape)
+        num_valid = cam_valid.shape[0]
+        for idx in torch.chunk(torch.arange(num_valid), chunk_sz):
+            bs = len(idx)
+            scene_b = cam_scene[idx].to(device) if cam_scene.shape[0] == num_valid else cam_scene.to(device).expand(bs, -1, -1, -1)
+            cam_b, prj_b = cam_valid[idx].to(device), prj_valid[idx].to(device)
+            inp, gt = (prj_b, cam_b) if "PCNet" in name else (cam_b, prj_b)
+            out = model(inp, scene_b)
+            model_infer[idx] = out.detach().cpu()
+            m = ut.calc_img_dists(out, gt)
+            valid_psnr += m[0] * bs / num_valid
+            valid_rmse += m[1] * bs / num_valid
+            valid_ssim += m[2] * bs / num_valid
+    return valid_psnr, valid_rmse, valid_ssim, model_infer
+
+
+def get_model_train_cfg(model_list, data_root=None, setup_list=None, device_ids=[0], center_crop=False, load_pretrained=False, plot_on=True,
+                        single=False):
+    """train_network.py:444-473."""
+    cfg = AttrDict()
+    cfg.data_root, cfg.setup_list, cfg.device, cfg.device_ids = data_root, setup_list, "cuda", device_ids
+    cfg.load_pretrained, cfg.max_iters, cfg.batch_size, cfg.lr = load_pretrained, 2000, 24, 1e-3
+    cfg.lr_drop_ratio, cfg.lr_drop_rate, cfg.l2_reg = 0.2, 800, 1e-4
+    cfg.train_plot_rate, cfg.valid_rate, cfg.plot_on, cfg.center_crop = 50, 200, plot_on, center_crop
+    if single:
+        cfg.model_name, cfg.num_train, cfg.loss = model_list[0], 500, "l1+ssim"
+    else:
+        cfg.model_list, cfg.num_train_list, cfg.loss_list = model_list, [500], ["l1+ssim"]
+    return cfg

