@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native SPAA hot path (contract: see README / DESIGN.md section 7).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+
+Workload (BASELINE.json configs[1]): SPAA attack, resnet18 classifier, batch of 32 target images, synthetic 256x256
+projector / 240x320 camera data, random-init PCNet.  One "step" = one iteration of the attack loop for the whole batch
+(PCNet forward, classifier forward+backward, fused Lab+dE2000+L2 loss, one PCNet backward, normalised masked update).
+Prints ONE JSON line (rank 0).  With N > 1 (torchrun) every rank runs an independent batch of 32 targets (attack jobs
+shard with no collective: weak scaling); the time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+CAM_HW, PRJ_HW, CROP = (240, 320), (256, 256), (240, 240)
+BATCH = 32
+SETUP = {"classifier_crop_sz": CROP, "prj_brightness": 0.5, "prj_im_sz": PRJ_HW}
+STEALTH, D_THR = "camdE_caml2", 5.0
+# algorithmic work of the dominant layer family (conv4 / conv4_s / conv5 and their backward-data passes):
+# 2 * Hout * Wout * Cout * Cin * k^2 FLOP per sample
+HEAVY_FLOP_PER_SAMPLE = 2 * 60 * 80 * 256 * 128 * 9
+
+
+def synthetic_inputs(seed: int):
+    import synth
+    scene = synth.textured(seed, "bench.scene", (1, 3, *CAM_HW))
+    P = synth.pcnet_params(100 + seed, CAM_HW)
+    targets = [synth.SPAA_TARGETS10[i % 10] for i in range(BATCH)]
+    return scene, P, targets
+
+
+def make_classifier(device, name="resnet18"):
+    from torchvision import models
+    torch.manual_seed(0)
+    net = getattr(models, name)(weights=None).to(device).eval()
+    for p in net.parameters():
+        p.requires_grad = False
+
+    class C:                                   # reference convention: .model / .input_sz (classifier.py:15-33)
+        model, input_sz = net, (224, 224)
+    return C()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0])); mx.append(int(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference algorithm on the host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------------------------
+
+def cpu_reference_run(sample_B: int, warmup: int, steps: int, device="cpu"):
+    """Times oracle.spaa_attack (the CPU restatement of projector_based_attack.py:212-339 on stock PyTorch ops -- the
+    same ops the reference dispatches) for `sample_B` targets.  Returns seconds per iteration of that sample."""
+    from oracle import spaa_oracle as O
+    scene, P, targets = synthetic_inputs(0)
+    dev = torch.device(device)
+    P = {k: v.to(dev) for k, v in P.items()}
+    scene = scene.to(dev)
+    clf = make_classifier(dev)
+    times = []
+
+    def classify(im):
+        return O.classify(clf.model, im, CROP, clf.input_sz)
+
+    def pc(x, s):
+        return O.pcnet(P, x, s, CAM_HW)
+
+    class Timer(list):                          # spaa_attack appends one dict per iteration: timestamp them
+        def append(self, item):
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            times.append(time.perf_counter())
+
+    t0 = time.perf_counter()
+    O.spaa_attack(pc, classify, targets[:sample_B], True, scene, D_THR, STEALTH, prj_hw=PRJ_HW, iters=warmup + steps, trace=Timer())
+    stamps = [t0] + times
+    per_it = [(stamps[i + 1] - stamps[i]) for i in range(warmup, warmup + steps)]
+    return sum(per_it) / len(per_it)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_B = 4
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    sec = cpu_reference_run(sample_B, warmup, steps)
+    its = 1.0 / (sec * BATCH / sample_B)            # iterations/s of the full 32-target batch (CPU time scales linearly in B)
+    sample = f"{sample_B} of {BATCH} targets x {steps} timed iterations (+{warmup} warm-up), scaled x{BATCH // sample_B} to the full batch"
+    line = {"impl": "reference", "metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(1, "fp32"),
+            "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(n_gpus: int, precision: str):
+    return {"workload": "spaa_attack resnet18 B=32 targets/GPU, prj 256x256, cam 240x320, camdE_caml2 d_thr=5 (BASELINE configs[1])",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "precision": precision, "classifier": "torchvision resnet18 (cuDNN, external operand)",
+            "l2": "per-iteration working set (~3 GB of activations at B=32) is far larger than the 126 MB L2; no explicit flush",
+            "parallelism": f"{n_gpus} independent attack jobs, no collective"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import spaa_b200
+    from spaa_b200 import models, ops
+    from spaa_b200.projector_based_attack import SpaaAttack, spaa
+
+    scene, P, targets = synthetic_inputs(rank)
+    wn = models.WarpingNet(out_size=CAM_HW)
+    sn = models.ShadingNetSPAA(use_rough=True)
+    pcnet = models.PCNet(P["mask"], torch.nn.DataParallel(wn), torch.nn.DataParallel(sn))
+    pcnet.load_state_dict(P, strict=True)
+    pcnet = pcnet.to(dev).eval()
+    for p in pcnet.parameters():
+        p.requires_grad = False
+    clf = make_classifier(dev)
+
+    A = SpaaAttack(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP)
+    for _ in range(args.warmup):
+        A.step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: exactly K iterations, CUDA events on the launching stream -----------------------------------
+    probe = ops.set_probe(lambda kind, spec: spec.k == 3 and {spec.cin, spec.cout} == {128, 256})
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = ops.launch_count()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        A.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - n0
+    clk = clocks.stop()
+    ops.set_probe(None)
+    kern_ms = [a.elapsed_time(b) for a, b in probe["events"]]
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    its = args.steps / (ms / 1e3) * world                   # whole-job iterations/s (each rank runs its own 32-target batch)
+
+    # ---- classifier share (external operand, reported separately) --------------------------------------------------
+    from spaa_b200.projector_based_attack import _adv_grad
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        _adv_grad(clf, A.cam, CROP, A.target, True)
+    c1.record()
+    torch.cuda.synchronize()
+    clf_ms = c0.elapsed_time(c1) / 5
+
+    # ---- e2e: the public spaa() call with HOST buffers, copies inside the timed region -----------------------------
+    scene_host = scene.clone().pin_memory()
+    out_cam = torch.empty(BATCH, 3, *CAM_HW).pin_memory()
+    out_prj = torch.empty(BATCH, 3, *PRJ_HW).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    cam_best, prj_best = spaa(pcnet, clf, None, targets, True, scene_host.to(dev, non_blocking=True), D_THR, STEALTH, dev, SETUP, iters=args.steps)
+    out_cam.copy_(cam_best, non_blocking=True)
+    out_prj.copy_(prj_best, non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_its = args.steps / t.item() * world
+    h2d = scene_host.numel() * 4 + len(targets) * 8
+    d2h = (out_cam.numel() + out_prj.numel()) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    k_ms = sum(kern_ms) / max(1, len(kern_ms))
+    flop = HEAVY_FLOP_PER_SAMPLE * BATCH
+    achieved = flop / (k_ms * 1e-3) / 1e12 if k_ms else 0.0
+    line = {"metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config_dict(world, args.precision),
+            "sample_iters_per_sec": its * BATCH, "classifier_ms_per_step": clf_ms,
+            "clocks": clk, "gpu_launches": launches,
+            "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+                    "note": "one spaa() call of `steps` iterations: scene H2D from pinned memory + results D2H inside the timed region; bytes are per call / steps"},
+            "roofline": {"bound": "tensor", "kernel": "conv_gather_kernel<128,64,8,4> on the 128<->256-channel 3x3 layers (fp32 CUDA-core path)",
+                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                         "traffic": None, "launches_timed": len(kern_ms), "avg_launch_ms": k_ms, "peak_source": pk["source"] + " bf16 sustained"}}
+    if world == 1 and not args.skip_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sample_B = 4
+        sec = cpu_reference_run(sample_B, 1, 3)
+        line["cpu_baseline"] = {"value": 1.0 / (sec * BATCH / sample_B), "unit": "it/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample_B} of {BATCH} targets x 3 timed iterations (+1 warm-up) of the oracle port, scaled x{BATCH // sample_B}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

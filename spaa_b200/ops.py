@@ -25,6 +25,31 @@ def launch_count() -> int:
     return _launches
 
 
+_probe = None      # optional per-launch timing of one kernel family: {"match": fn(kind, spec), "events": [(start, end), ...]}
+
+
+def set_probe(match=None):
+    """bench.py: time every launch for which match(kind, spec) is true with a CUDA-event pair on the launching stream."""
+    global _probe
+    _probe = None if match is None else {"match": match, "events": []}
+    return _probe
+
+
+class _Probe:
+    def __init__(self, kind, spec):
+        self.on = _probe is not None and _probe["match"](kind, spec)
+
+    def __enter__(self):
+        if self.on:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            _probe["events"].append((self.e0, self.e1))
+
+
 def _count(n: int = 1) -> None:
     global _launches
     _launches += n
@@ -326,7 +351,8 @@ def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, o
         d.w_cis, d.w_cos = s0, s1
     d.epi_flags, d.mask_mode = epi, MASK_NONE
     _fill_desc(d, x, out, add, None)
-    lib().spaa_conv_fwd(ctypes.byref(d), _p(x), _p(w), _p(b), _p(add), None, None, _p(out), None, _stream()); _count()
+    with _Probe("fwd", spec):
+        lib().spaa_conv_fwd(ctypes.byref(d), _p(x), _p(w), _p(b), _p(add), None, None, _p(out), None, _stream()); _count()
     return out
 
 
@@ -357,7 +383,8 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
         assert out2 is not None and out2.stride() == out.stride()
         if mask is not None:
             assert mask2.stride()[1:] == mask.stride()[1:]
-    lib().spaa_conv_fwd(ctypes.byref(d), _p(dy), _p(w), None, _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream()); _count()
+    with _Probe("bwd_data", spec):
+        lib().spaa_conv_fwd(ctypes.byref(d), _p(dy), _p(w), None, _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream()); _count()
     return out
 
 

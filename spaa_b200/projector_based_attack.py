@@ -37,122 +37,141 @@ def _adv_grad(classifier, cam, cp_sz, target, targeted):
     return logits.detach(), g
 
 
+class SpaaAttack:
+    """State + one-iteration stepper of the SPAA loop (projector_based_attack.py:212-339).  `spaa()` below is
+    `SpaaAttack(...)`, `iters` x `step()`, `result()`; bench.py drives `step()` directly to time exactly K iterations."""
+
+    def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("spaa_b200.spaa runs on CUDA devices only (no CPU fallback)")
+        self.device, self.classifier, self.targeted, self.d_thr = device, classifier, bool(targeted), float(d_thr)
+        self.B = B = len(target_idx)
+        self.cp_sz = setup_info["classifier_crop_sz"]
+        self.prj_hw = prj_hw = tuple(setup_info["prj_im_sz"])
+        self.scene = scene = ops._f32c(expand_4d(cam_scene).to(device))
+        if scene.shape[0] != 1:
+            raise ValueError("cam_scene must be a single image (3xHxW or 1x3xHxW)")
+        H, W = scene.shape[2:]
+        self.hw_cam, self.hw_prj = H * W, prj_hw[0] * prj_hw[1]
+        self.target = torch.as_tensor(list(target_idx), dtype=torch.int64, device=device)
+        self.gray = setup_info["prj_brightness"] * torch.ones(B, 3, *prj_hw, device=device)
+        self.prj_adv = self.gray.clone()
+        self.adv_lr, self.col_lr = 2.0, 1.0                                    # :243-244
+        self.w_prjl2 = 0.1 if "prjl2" in stealth_loss else 0.0                 # :249-251
+        self.w_caml2 = 1.0 if "caml2" in stealth_loss else 0.0
+        self.w_camde = 1.0 if "camdE" in stealth_loss else 0.0
+        self.p_thresh = 0.9                                                    # :255
+        self.prj_best = self.prj_adv.clone()
+        self.cam_best = scene.repeat(B, 1, 1, 1)
+        self.best_col = 1e6 * torch.ones(B, device=device)
+        self.use_col, self.succ, self.better = (torch.zeros(B, dtype=torch.uint8, device=device) for _ in range(3))
+        self.col_loss = torch.empty(B, device=device)
+        self.stats = torch.empty(B, 4, device=device)
+        self.sq = torch.empty(B, device=device)
+        self.prjl2sum = torch.empty(B, device=device) if self.w_prjl2 else None
+        self.step2 = torch.tensor([-self.adv_lr, -self.col_lr], device=device)
+        self.ref_lab = ops.rgb2lab(scene)
+        self.g_col = torch.empty(B, 3, H, W, device=device)
+        self.d_pre6 = torch.empty(B, 3, H, W, device=device)
+        self.dprj = torch.empty(B, 3, *prj_hw, device=device)
+        self.pcnet = pcnet
+        self.net = net = _unwrap(pcnet)
+        self.fused = isinstance(net, PCNet)
+        if self.fused:
+            with torch.no_grad():
+                self.sh = sh = net.shading_net
+                self.grid = net.warping_net.planar_grid(prj_hw).detach()
+                self.mask = net.flat_mask()
+                self.skip_acts = _Stack.skip1(sh, scene)                      # skipConv1(cam_scene): loop constant
+                self.xw = torch.empty(B, 3, H, W, device=device)
+                if net.use_rough:
+                    self.sfeat = torch.empty(B, 6, H, W, device=device)
+                    self.sfeat[:, :3] = scene
+                    self.surf_acts = None
+                else:
+                    self.sfeat = None
+                    self.surf_acts = _Stack.surface_branch(sh, scene) if sh.res1_s is None else tuple(
+                        t if t.dim() == 4 else t.unsqueeze(0) for t in (sh.res1_s, sh.res2_s, sh.res3_s, sh.res4_s))
+        self.scene_b = scene.expand(B, -1, -1, -1)
+        self.cam = self.logits = None
+
+    def step(self):
+        """One iteration of the loop body (:265-328)."""
+        net, scene = self.net, self.scene
+        # ---- forward ---------------------------------------------------------------------------------
+        if self.fused:
+            with torch.no_grad():
+                if net.use_rough:
+                    ops.grid_sample(self.prj_adv, self.grid, clamp01=True, mask=self.mask, out=self.xw, rough=scene, out2=self.sfeat[:, 3:])
+                    cam, S = _Stack.forward(self.sh, self.xw, self.sfeat, None, skip_acts=self.skip_acts)
+                    S["surf_own"] = True
+                else:
+                    ops.grid_sample(self.prj_adv, self.grid, clamp01=True, mask=self.mask, out=self.xw)
+                    cam, S = _Stack.forward(self.sh, self.xw, None, None, surf_acts=self.surf_acts, skip_acts=self.skip_acts)
+        else:
+            prj_leaf = self.prj_adv.detach().requires_grad_(True)
+            with torch.enable_grad():
+                cam_g = self.pcnet(torch.clamp(prj_leaf, 0, 1), self.scene_b)
+            cam = cam_g.detach()
+        # ---- losses, masks ---------------------------------------------------------------------------
+        logits, g_adv = _adv_grad(self.classifier, cam, self.cp_sz, self.target, self.targeted)
+        ops.color_loss(cam, scene, self.ref_lab, cam_is_lab2=False, de_weighting=False, c_de=self.w_camde / self.hw_cam,
+                       c_l2=self.w_caml2 / self.hw_cam, stats=self.stats, grad=self.g_col)
+        if self.w_prjl2:
+            ops.chan_l2(self.prj_adv, self.gray, self.prjl2sum)
+        ops.attack_masks(logits, self.target, self.targeted, self.stats, self.prjl2sum, self.hw_cam, self.hw_prj, self.w_prjl2, self.w_caml2,
+                         self.w_camde, self.d_thr, self.p_thresh, self.use_col, self.succ, self.better, self.col_loss, self.best_col)
+        # ---- one backward with the per-sample selected cotangent ---------------------------------------
+        if self.fused:
+            ops.select_cotangent(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6)
+            with torch.no_grad():
+                if net.use_rough:
+                    dxw, dsf, _ = _Stack.backward(self.sh, S, self.d_pre6, need_dx=True, surf_grad_channels=(3, 6))
+                else:
+                    dxw, dsf, _ = _Stack.backward(self.sh, S, self.d_pre6, need_dx=True)
+                ops.grid_sample_bwd_input(dxw, self.grid, self.prj_hw, mask=self.mask, dout2=dsf, rough=scene if dsf is not None else None,
+                                          dimg=self.dprj)
+            S = None
+        else:
+            ops.select_cotangent(g_adv, self.g_col, self.use_col, None, 0, self.d_pre6)
+            g, = torch.autograd.grad(cam_g, prj_leaf, grad_outputs=self.d_pre6)      # clamp backward already applied by autograd
+            self.dprj.copy_(g)
+        # ---- normalised masked step + best-so-far ------------------------------------------------------
+        clamp_in_kernel = self.fused
+        if self.w_prjl2:
+            ops.chan_l2(self.prj_adv, self.gray, self.sq, c=self.w_prjl2 / self.hw_prj, sel=self.use_col, apply_clamp_mask=clamp_in_kernel,
+                        grad=self.dprj)
+            clamp_in_kernel = False
+        ops.row_sqnorm(self.dprj, self.sq, self.prj_adv if clamp_in_kernel else None)
+        ops.row_normalized_step(self.prj_adv, self.dprj, self.sq, self.step2, self.use_col, use_clamp_mask=clamp_in_kernel,
+                                copy_dst=self.prj_best, copy_sel=self.succ)
+        ops.masked_copy_rows(self.cam_best, cam, self.succ)
+        self.cam, self.logits = cam, logits
+
+    def result(self):
+        return self.cam_best, torch.clamp(self.prj_best, 0, 1)                 # :337-339
+
+
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,
          iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None):
     """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1))."""
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise RuntimeError("spaa_b200.spaa runs on CUDA devices only (no CPU fallback)")
-    B = len(target_idx)
-    cp_sz = setup_info["classifier_crop_sz"]
-    prj_hw = tuple(setup_info["prj_im_sz"])
-    scene = ops._f32c(expand_4d(cam_scene).to(device))
-    if scene.shape[0] != 1:
-        raise ValueError("cam_scene must be a single image (3xHxW or 1x3xHxW)")
-    H, W = scene.shape[2:]
-    hw_cam, hw_prj = H * W, prj_hw[0] * prj_hw[1]
-    target = torch.as_tensor(list(target_idx), dtype=torch.int64, device=device)
-
-    gray = setup_info["prj_brightness"] * torch.ones(B, 3, *prj_hw, device=device)
-    prj_adv = gray.clone()
-    adv_lr, col_lr = 2.0, 1.0                                              # :243-244
-    w_prjl2 = 0.1 if "prjl2" in stealth_loss else 0.0                      # :249-251
-    w_caml2 = 1.0 if "caml2" in stealth_loss else 0.0
-    w_camde = 1.0 if "camdE" in stealth_loss else 0.0
-    p_thresh = 0.9                                                         # :255
-
-    prj_best = prj_adv.clone()
-    cam_best = scene.repeat(B, 1, 1, 1)
-    best_col = 1e6 * torch.ones(B, device=device)
-    use_col, succ, better = (torch.zeros(B, dtype=torch.uint8, device=device) for _ in range(3))
-    col_loss = torch.empty(B, device=device)
-    stats = torch.empty(B, 4, device=device)
-    sq = torch.empty(B, device=device)
-    prjl2sum = torch.empty(B, device=device) if w_prjl2 else None
-    step2 = torch.tensor([-adv_lr, -col_lr], device=device)
-    ref_lab = ops.rgb2lab(scene)
-    g_col = torch.empty(B, 3, H, W, device=device)
-    d_pre6 = torch.empty(B, 3, H, W, device=device)
-    dprj = torch.empty(B, 3, *prj_hw, device=device)
-
-    net = _unwrap(pcnet)
-    fused = isinstance(net, PCNet)
-    if fused:
-        with torch.no_grad():
-            sh = net.shading_net
-            grid = net.warping_net.planar_grid(prj_hw).detach()
-            mask = net.flat_mask()
-            skip_acts = _Stack.skip1(sh, scene)                           # skipConv1(cam_scene): loop constant
-            xw = torch.empty(B, 3, H, W, device=device)
-            if net.use_rough:
-                sfeat = torch.empty(B, 6, H, W, device=device)
-                sfeat[:, :3] = scene
-                surf_acts = None
-            else:
-                sfeat = None
-                surf_acts = _Stack.surface_branch(sh, scene) if sh.res1_s is None else tuple(
-                    t if t.dim() == 4 else t.unsqueeze(0) for t in (sh.res1_s, sh.res2_s, sh.res3_s, sh.res4_s))
-    scene_b = scene.expand(B, -1, -1, -1)
-
+    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info)
     for it in range(iters):
         if forced_prj is not None:
-            prj_adv.copy_(forced_prj[it])
-        prj_in = prj_adv.clone() if trace is not None else None
-        # ---- forward ---------------------------------------------------------------------------------
-        if fused:
-            with torch.no_grad():
-                if net.use_rough:
-                    ops.grid_sample(prj_adv, grid, clamp01=True, mask=mask, out=xw, rough=scene, out2=sfeat[:, 3:])
-                    cam, S = _Stack.forward(sh, xw, sfeat, None, skip_acts=skip_acts)
-                    S["surf_own"] = True
-                else:
-                    ops.grid_sample(prj_adv, grid, clamp01=True, mask=mask, out=xw)
-                    cam, S = _Stack.forward(sh, xw, None, None, surf_acts=surf_acts, skip_acts=skip_acts)
-        else:
-            prj_leaf = prj_adv.detach().requires_grad_(True)
-            with torch.enable_grad():
-                cam_g = pcnet(torch.clamp(prj_leaf, 0, 1), scene_b)
-            cam = cam_g.detach()
-        # ---- losses, masks ---------------------------------------------------------------------------
-        logits, g_adv = _adv_grad(classifier, cam, cp_sz, target, targeted)
-        ops.color_loss(cam, scene, ref_lab, cam_is_lab2=False, de_weighting=False, c_de=w_camde / hw_cam, c_l2=w_caml2 / hw_cam,
-                       stats=stats, grad=g_col)
-        if w_prjl2:
-            ops.chan_l2(prj_adv, gray, prjl2sum)
-        ops.attack_masks(logits, target, targeted, stats, prjl2sum, hw_cam, hw_prj, w_prjl2, w_caml2, w_camde, d_thr, p_thresh,
-                         use_col, succ, better, col_loss, best_col)
-        # ---- one backward with the per-sample selected cotangent ---------------------------------------
-        if fused:
-            ops.select_cotangent(g_adv, g_col, use_col, cam, MASK_OPEN01, d_pre6)
-            with torch.no_grad():
-                if net.use_rough:
-                    dxw, dsf, _ = _Stack.backward(sh, S, d_pre6, need_dx=True, surf_grad_channels=(3, 6))
-                else:
-                    dxw, dsf, _ = _Stack.backward(sh, S, d_pre6, need_dx=True)
-                ops.grid_sample_bwd_input(dxw, grid, prj_hw, mask=mask, dout2=dsf, rough=scene if dsf is not None else None, dimg=dprj)
-            S = None
-        else:
-            ops.select_cotangent(g_adv, g_col, use_col, None, 0, d_pre6)
-            g, = torch.autograd.grad(cam_g, prj_leaf, grad_outputs=d_pre6)      # clamp backward already applied by autograd
-            dprj.copy_(g)
-        # ---- normalised masked step + best-so-far ------------------------------------------------------
-        clamp_in_kernel = fused
-        if w_prjl2:
-            ops.chan_l2(prj_adv, gray, sq, c=w_prjl2 / hw_prj, sel=use_col, apply_clamp_mask=clamp_in_kernel, grad=dprj)
-            clamp_in_kernel = False
-        ops.row_sqnorm(dprj, sq, prj_adv if clamp_in_kernel else None)
-        ops.row_normalized_step(prj_adv, dprj, sq, step2, use_col, use_clamp_mask=clamp_in_kernel, copy_dst=prj_best, copy_sel=succ)
-        ops.masked_copy_rows(cam_best, cam, succ)
+            A.prj_adv.copy_(forced_prj[it])
+        prj_in = A.prj_adv.clone() if trace is not None else None
+        A.step()
         if trace is not None:
-            trace.append(dict(prj_in=prj_in, cam=cam.clone(), logits=logits.clone(), stats=stats.clone(), col_b=col_loss.clone(),
-                              use_col=use_col.bool().clone(), succ=succ.bool().clone(), better=better.bool().clone(),
-                              g=dprj.clone(), prj_out=prj_adv.clone(), best_col=best_col.clone(), best_prj=prj_best.clone(),
-                              best_cam=cam_best.clone()))
+            trace.append(dict(prj_in=prj_in, cam=A.cam.clone(), logits=A.logits.clone(), stats=A.stats.clone(), col_b=A.col_loss.clone(),
+                              use_col=A.use_col.bool().clone(), succ=A.succ.bool().clone(), better=A.better.bool().clone(),
+                              g=A.dprj.clone(), prj_out=A.prj_adv.clone(), best_col=A.best_col.clone(), best_prj=A.prj_best.clone(),
+                              best_cam=A.cam_best.clone()))
         if verbose and (it % 30 == 0 or it == iters - 1):
-            v = min(7 if targeted else 0, B - 1)                           # :240 (guarded: the reference indexes v=7 blindly)
-            print(f"adv_loss_sel_logit = {logits[v, target[v]].item():<9.4f} | col_loss = {col_loss[v].item():.4f} | "
-                  f"succ = {bool(succ[v].item())}")
-    return cam_best, torch.clamp(prj_best, 0, 1)
+            v = min(7 if targeted else 0, A.B - 1)                             # :240 (guarded: the reference indexes v=7 blindly)
+            print(f"adv_loss_sel_logit = {A.logits[v, A.target[v]].item():<9.4f} | col_loss = {A.col_loss[v].item():.4f} | "
+                  f"succ = {bool(A.succ[v].item())}")
+    return A.result()
 
 
 def perc_al_compennet_pp(compennet_pp, classifier, imgnet_labels, target_idx, targeted, cam_scene, d_thr, device, setup_info, *,
