@@ -138,6 +138,18 @@ int spaa_conv_fwd(const spaa_conv_desc* d, const void* in, const float* w, const
  * flip == 0; `dout` has the forward output's strides (d->out_*) and dtype d->out_dtype. */
 int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* dout, float* dw, float* dbias,
                          spaa_stream_t stream);
+/* Tensor-core path of the same operation: tcgen05.mma (M=128 x N=Cout x K=16, fp32 accumulators in TMEM) fed by 4-D TMA
+ * box loads of the NHWC input (one shifted box per filter tap; zero padding = TMA out-of-bound fill).  Requirements
+ * (spaa_conv_tc_supported tells): bf16 in/out, dense NHWC (in_cs = out_cs = 1, *_ps = C), Cin and Cout multiples of 32
+ * (Cin > 64: of 64; Cout <= 256), square kernels <= 3x3, (stride, up) in {(1,1), (2,1), (1,2)}.  Epilogue: bias,
+ * residual add, ReLU (SPAA_EPI_RELU only), mask / mask2 / out2 as in spaa_conv_fwd.
+ * Weights are packed once per layer and direction into bf16 [tap][Cout][Cin] by spaa_conv_tc_pack_weights (which reads
+ * the fp32 parameter through d->w_* / d->flip). */
+int spaa_conv_tc_supported(const spaa_conv_desc* d);
+int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d);
+int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, void* packed, spaa_stream_t stream);
+int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add,
+                     const void* mask, const void* mask2, void* out, void* out2, spaa_stream_t stream);
 /* out[c] += sum_{b,p} x[b,p,c]  (bias gradient; x addressed by element strides, dtype 0 fp32 / 1 bf16) */
 int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int64_t bs, int64_t ps, int64_t cs, float* out,
                      spaa_stream_t stream);

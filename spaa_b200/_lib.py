@@ -56,7 +56,7 @@ class SpaaError(RuntimeError):
 class _Lib:
     def __init__(self):
         if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m spaa_b200.build` "
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python spaa_b200/build.py` "
                               "(or __graft_entry__.build()); spaa_b200 has no CPU / PyTorch fallback")
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()
@@ -64,8 +64,8 @@ class _Lib:
             fn = getattr(self.cdll, name)          # AttributeError if the library does not export a declared symbol
             fn.argtypes = [_ctype(a) for a in args]
             fn.restype = ctypes.c_char_p if "char" in ret else (ctypes.c_int64 if ret == "int64_t" else ctypes.c_int)
-            if ret == "int":
-                setattr(self, name, self._checked(name, fn))
+            if ret == "int" and name != "spaa_abi_version" and not name.endswith("_supported"):
+                setattr(self, name, self._checked(name, fn))     # status-returning entry point: raise on non-zero
             else:
                 setattr(self, name, fn)
 
@@ -74,7 +74,7 @@ class _Lib:
 
         def call(*a):
             rc = fn(*a)
-            if rc != 0 and name != "spaa_abi_version":
+            if rc != 0:
                 raise SpaaError(f"{name} failed ({rc}): {last_error().decode()}")
             return rc
         return call

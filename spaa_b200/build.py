@@ -1,7 +1,8 @@
 """Builds spaa_b200/libspaa_b200.so (the C-ABI library of include/spaa_b200.h) with nvcc for sm_100a.
 
 In-tree build: the .so sits next to this file so it travels to the GPU box with the repo snapshot.
-`python -m spaa_b200.build [--force]` or `__graft_entry__.build()`.
+`python spaa_b200/build.py [--force] [-v]` or `__graft_entry__.build()` (run it as a script: importing the package
+requires the library to exist already).
 """
 from __future__ import annotations
 

@@ -1,0 +1,532 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 NHWC activations, fp32 accumulation in TMEM).
+//
+// One kernel family serves nn.Conv2d (stride 1 or 2), nn.ConvTranspose2d (stride 2) and the backward-data pass of each
+// (the same "gather conv" of include/spaa_b200.h, spaa_conv_desc) for the layers whose channel counts are multiples
+// of 32 -- conv2..conv5, conv*_s, skipConv2/3, transConv1/2 of /root/reference/src/python/models.py:18-46,223-252 --
+// i.e. the work cuDNN does for those modules in the reference.
+//
+// Formulation.  Output pixels are tiled in 8 x 16 rectangles (M = 128 rows of the MMA).  For one filter tap the A
+// operand of such a tile is a shifted 8 x 16 x BK box of the NHWC input: ONE 4-D TMA load (cp.async.bulk.tensor) lands
+// it in shared memory already in the K-major 128B/64B-swizzled layout tcgen05.mma reads; convolution padding and ragged
+// edge tiles are TMA out-of-bound zero fill; stride-2 convolutions use the TMA traversal stride; transposed /
+// backward-of-strided convolutions are split into their 4 output-parity phases, each a stride-1 problem over a subset
+// of the taps.  The B operand is the pre-packed bf16 weight slice [tap][Cout][Cin] (2-D TMA).  K loop = taps x Cin/BK.
+//
+// Kernel: persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+// lane issues tcgen05.mma, M=128, N=Cout, K=16) + TMEM owner, warps 2..5 = epilogue (tcgen05.ld of their 32-lane
+// quadrant -> bias / residual add / ReLU / ReLU-mask of the backward pass -> bf16 -> global).  smem ring of NSTAGES
+// {A,B} stages with full/empty mbarriers; TWO accumulators in TMEM (2 x Cout columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "../../include/spaa_b200.h"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+
+using namespace spaa;
+
+namespace {
+
+constexpr int TH = 8, TW = 16, BM = TH * TW;      // output tile = 128 MMA rows
+constexpr int kThreads = 192;                      // 6 warps
+constexpr int kMaxTaps = 9, kMaxPhases = 4;
+
+struct Tap { int8_t dy, dx, slot, pad; };
+struct Phase {
+    int32_t ntaps, py, px, Hph, Wph, tiles_y, tiles_x, tile_base;   // tile_base: first global tile index of this phase
+    Tap taps[kMaxTaps];
+};
+struct TcParams {
+    int32_t B, Cin, Hin, Win, Cout, Hout, Wout;
+    int32_t in_step;            // TMA traversal stride of the input (conv stride), 1 for up-sampling phases
+    int32_t out_step;           // output pixel step (2 for the parity phases of up == 2)
+    int32_t nphases, total_tiles, kchunks;
+    int32_t epi_flags, mask_mode;
+    int64_t add_bs;             // 0: `add` is broadcast over the batch
+    int64_t mask_bs;
+    Phase ph[kMaxPhases];
+    const float* bias;
+    const __nv_bfloat16* add;
+    const __nv_bfloat16* mask;
+    const __nv_bfloat16* mask2;
+    __nv_bfloat16* out;
+    __nv_bfloat16* out2;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+SPAA_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+SPAA_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+SPAA_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SPAA_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+SPAA_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+SPAA_D void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+SPAA_D void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+                 "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+SPAA_D void prefetch_tmap(const CUtensorMap* map) { asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory"); }
+
+SPAA_D void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+SPAA_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+SPAA_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+SPAA_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+SPAA_D void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, M = 128, N from idesc, K = 16
+SPAA_D void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+SPAA_D void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, rows of ROW_BYTES (= swizzle width), 8-row groups ROW_BYTES*8 apart.
+// Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64): 2 = 128B swizzle, 4 = 64B, 6 = 32B.
+template <int ROW_BYTES> SPAA_D uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = ROW_BYTES == 128 ? 2 : (ROW_BYTES == 64 ? 4 : 6);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(((ROW_BYTES * 8) >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+// kind::f16 instruction descriptor (InstrDescriptor): C fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1, both K-major,
+// N>>3 at [17,23), M>>4 at [24,29)
+SPAA_D uint32_t make_idesc(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+SPAA_D float apply_mask_tc(float v, float m, int mode) {
+    switch (mode) {
+        case SPAA_MASK_POS: return m > 0.f ? v : 0.f;
+        case SPAA_MASK_LEAKY01: return m > 0.f ? v : 0.1f * v;
+        case SPAA_MASK_OPEN01: return (m > 0.f && m < 1.f) ? v : 0.f;
+        default: return v;
+    }
+}
+
+template <int BN, int BK> struct SmemLayout {
+    static constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+    static constexpr int kBarOff = kStages * kStageBytes;                 // full[kStages], empty[kStages], tfull[2], tempty[2]
+    static constexpr int kBiasOff = kBarOff + (2 * kStages + 4) * 8 + 16;
+    static constexpr int kTotal = kBiasOff + BN * 4 + 1024;               // + slack for the 1024 B alignment of the ring
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                              const __grid_constant__ TcParams P) {
+    using L = SmemLayout<BN, BK>;
+    constexpr int kStages = L::kStages;
+    constexpr uint32_t kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;           // power of two >= 32 (BN in {32,64,128,256})
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + L::kBarOff);
+    uint64_t* empty = full + kStages;
+    uint64_t* tfull = empty + kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    float* s_bias = (float*)(smem + L::kBiasOff);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    for (int i = threadIdx.x; i < BN; i += kThreads) s_bias[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int tile, int& ph, int& b, int& ty, int& tx) {
+        ph = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxPhases; ++i)
+            if (i < P.nphases && tile >= P.ph[i].tile_base) ph = i;
+        const Phase& F = P.ph[ph];
+        int t = tile - F.tile_base;
+        const int per_img = F.tiles_y * F.tiles_x;
+        b = t / per_img;
+        t -= b * per_img;
+        ty = t / F.tiles_x;
+        tx = t - ty * F.tiles_x;
+    };
+
+    if (warp == 0) {
+        // ===================================== TMA producer ========================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                int ph, b, ty, tx;
+                decode(tile, ph, b, ty, tx);
+                const Phase& F = P.ph[ph];
+                const int y0 = ty * TH * P.in_step, x0 = tx * TW * P.in_step;
+                for (int t = 0; t < F.ntaps; ++t) {
+                    const Tap tp = F.taps[t];
+                    for (int kc = 0; kc < P.kchunks; ++kc) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        uint8_t* sa = smem + stage * L::kStageBytes;
+                        uint8_t* sb = sa + L::kABytes;
+                        mbar_expect_tx(full + stage, L::kStageBytes);
+                        tma_load_4d(sa, &map_a, full + stage, kc * BK, x0 + tp.dx, y0 + tp.dy, b);
+                        tma_load_2d(sb, &map_b, full + stage, kc * BK, tp.slot * BN);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ==========================================
+        const uint32_t idesc = make_idesc(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
+            int ph, b, ty, tx;
+            decode(tile, ph, b, ty, tx);
+            const int nk = P.ph[ph].ntaps * P.kchunks;
+            const int acc = local & 1;
+            mbar_wait(tempty + acc, ((local >> 1) & 1) ^ 1);           // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(full + stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+                    const uint64_t adesc = make_kmajor_desc<BK * 2>(a_addr);
+                    const uint64_t bdesc = make_kmajor_desc<BK * 2>(a_addr + L::kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)                    // +32 B per K=16 step inside the swizzle atom
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    umma_commit(empty + stage);                          // frees the smem stage when these MMAs retire
+                    if (kb == nk - 1) umma_commit(tfull + acc);          // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================== epilogue ============================================
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int j = row / TW, i = row - j * TW;
+        const int ef = P.epi_flags;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
+            int ph, b, ty, tx;
+            decode(tile, ph, b, ty, tx);
+            const Phase& F = P.ph[ph];
+            const int acc = local & 1;
+            const int oy = (ty * TH + j) * P.out_step + F.py, ox = (tx * TW + i) * P.out_step + F.px;
+            const bool valid = (ty * TH + j) < F.Hph && (tx * TW + i) < F.Wph && oy < P.Hout && ox < P.Wout;
+            const int64_t pix = ((int64_t)oy * P.Wout + ox) * P.Cout;
+            const int64_t o_off = (int64_t)b * P.Hout * P.Wout * P.Cout + pix;
+            mbar_wait(tfull + acc, (local >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                if (valid && c0 < P.Cout) {
+                    float v[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) + s_bias[c0 + k];
+                    if (P.add) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(P.add + (int64_t)b * P.add_bs + pix + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 u = __ldg(ap + g);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(h[e]);
+                                v[g * 8 + e * 2] += f.x; v[g * 8 + e * 2 + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (ef & SPAA_EPI_RELU) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+                    }
+                    if (P.mask) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask + (int64_t)b * P.mask_bs + pix + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 u = __ldg(mp + g);
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(h[e]);
+                                v[g * 8 + e * 2] = apply_mask_tc(v[g * 8 + e * 2], f.x, P.mask_mode);
+                                v[g * 8 + e * 2 + 1] = apply_mask_tc(v[g * 8 + e * 2 + 1], f.y, P.mask_mode);
+                            }
+                        }
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(P.out + o_off + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 u;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+                        op[g] = u;
+                    }
+                    if (P.out2) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask2 + (int64_t)b * P.mask_bs + pix + c0);
+                        uint4* op2 = reinterpret_cast<uint4*>(P.out2 + o_off + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint4 m = __ldg(mp + g);
+                            const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m);
+                            uint4 u;
+                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __bfloat1622float2(mh[e]);
+                                h[e] = __floats2bfloat162_rn(f.x > 0.f ? v[g * 8 + e * 2] : 0.f, f.y > 0.f ? v[g * 8 + e * 2 + 1] : 0.f);
+                            }
+                            op2[g] = u;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 parameter (any layout, by strides) -> bf16 [slot = gather tap][BN rows = cout][Cin]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KH, int KW, int Cin, int Cout, int BN, int flip,
+                                    int64_t w_ts, int64_t w_cis, int64_t w_cos) {
+    const int64_t total = (int64_t)KH * KW * BN * Cin;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(e % Cin);
+        const int co = (int)((e / Cin) % BN);
+        const int tap = (int)(e / ((int64_t)Cin * BN));
+        const int r = tap / KW, s = tap - r * KW;
+        const int wtap = flip ? (KH - 1 - r) * KW + (KW - 1 - s) : tap;
+        out[e] = __float2bfloat16_rn(co < Cout ? w[(int64_t)wtap * w_ts + (int64_t)ci * w_cis + (int64_t)co * w_cos] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int bn_for(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <= 128 ? 128 : 256)); }
+
+bool tc_supported(const spaa_conv_desc* d, const char** why) {
+    auto fail = [&](const char* m) { if (why) *why = m; return false; };
+    if (d->in_dtype != 1 || d->out_dtype != 1) return fail("tensor-core path needs bf16 activations");
+    if (d->Cin % 32 != 0 || d->Cin < 32 || d->Cout % 32 != 0 || d->Cout > 256) return fail("channel counts must be multiples of 32 (Cout <= 256)");
+    if (d->Cin > 64 && d->Cin % 64 != 0) return fail("Cin > 64 must be a multiple of 64");
+    if (!((d->up == 1 && (d->stride == 1 || d->stride == 2)) || (d->up == 2 && d->stride == 1))) return fail("unsupported stride / up combination");
+    if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return fail("square kernels up to 3x3 only");
+    if (d->in_cs != 1 || d->in_ps != d->Cin || d->out_cs != 1 || d->out_ps != d->Cout) return fail("activations must be dense NHWC");
+    if (d->in_bs != (int64_t)d->Hin * d->Win * d->Cin || d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout) return fail("activations must be dense NHWC");
+    return true;
+}
+
+template <int BN, int BK>
+int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, cudaStream_t st) {
+    using L = SmemLayout<BN, BK>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+            set_last_error("spaa_conv_tc_fwd: cannot reserve %d bytes of shared memory", L::kTotal);
+            return SPAA_ERR_CUDA;
+        }
+        attr = true;
+    }
+    const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+    conv_tc_kernel<BN, BK><<<grid, kThreads, L::kTotal, st>>>(ma, mb, P);
+    return SPAA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spaa_conv_tc_supported(const spaa_conv_desc* d) { return (d && tc_supported(d, nullptr)) ? 1 : 0; }
+
+int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d) {
+    if (!d) return 0;
+    return (int64_t)d->KH * d->KW * bn_for(d->Cout) * d->Cin;
+}
+
+int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, void* packed, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(d && w && packed, "spaa_conv_tc_pack_weights: null argument");
+    const int BN = bn_for(d->Cout);
+    const int64_t total = spaa_conv_tc_packed_elems(d);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, d->KH, d->KW, d->Cin, d->Cout, BN, d->flip, d->w_ts,
+                                                                           d->w_cis, d->w_cos);
+    SPAA_CHECK_LAUNCH("spaa_conv_tc_pack_weights");
+    return SPAA_OK;
+}
+
+int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add, const void* mask, const void* mask2,
+                     void* out, void* out2, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(d && in && wpacked && out, "spaa_conv_tc_fwd: null argument");
+    const char* why = "";
+    SPAA_CHECK_ARG(tc_supported(d, &why), "spaa_conv_tc_fwd: %s", why);
+    SPAA_CHECK_ARG((out2 == nullptr) == (mask2 == nullptr), "spaa_conv_tc_fwd: out2 and mask2 go together");
+    SPAA_CHECK_ARG(d->mask_mode == SPAA_MASK_NONE || mask, "spaa_conv_tc_fwd: mask_mode needs mask");
+    SPAA_CHECK_ARG(!(d->epi_flags & ~SPAA_EPI_RELU), "spaa_conv_tc_fwd: only the ReLU epilogue flag is implemented on the tensor-core path");
+    SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == d->Cout), "spaa_conv_tc_fwd: add must be dense NHWC");
+    SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == d->Cout), "spaa_conv_tc_fwd: masks must be dense NHWC");
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled is unavailable in this driver"); return SPAA_ERR_CUDA; }
+    const int BN = bn_for(d->Cout);
+    const int BK = d->Cin >= 64 ? 64 : 32;
+
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = d->B; P.Cin = d->Cin; P.Hin = d->Hin; P.Win = d->Win; P.Cout = d->Cout; P.Hout = d->Hout; P.Wout = d->Wout;
+    P.in_step = d->stride; P.out_step = d->up; P.kchunks = d->Cin / BK;
+    P.epi_flags = d->epi_flags; P.mask_mode = mask ? d->mask_mode : SPAA_MASK_NONE;
+    P.add_bs = d->add_bs; P.mask_bs = d->mask_bs;
+    P.bias = bias; P.add = (const __nv_bfloat16*)add; P.mask = (const __nv_bfloat16*)mask; P.mask2 = (const __nv_bfloat16*)mask2;
+    P.out = (__nv_bfloat16*)out; P.out2 = (__nv_bfloat16*)out2;
+    int tile_base = 0;
+    P.nphases = d->up * d->up;
+    for (int py = 0; py < d->up; ++py)
+        for (int px = 0; px < d->up; ++px) {
+            Phase& F = P.ph[py * d->up + px];
+            F.py = py; F.px = px;
+            F.Hph = (d->Hout - py + d->up - 1) / d->up;
+            F.Wph = (d->Wout - px + d->up - 1) / d->up;
+            F.tiles_y = (F.Hph + TH - 1) / TH; F.tiles_x = (F.Wph + TW - 1) / TW;
+            F.tile_base = tile_base;
+            tile_base += d->B * F.tiles_y * F.tiles_x;
+            F.ntaps = 0;
+            for (int r = 0; r < d->KH; ++r)
+                for (int s = 0; s < d->KW; ++s) {
+                    const int vy = py + r - d->pad_h, vx = px + s - d->pad_w;
+                    if (d->up > 1 && ((vy % d->up) != 0 || (vx % d->up) != 0)) continue;
+                    Tap& t = F.taps[F.ntaps++];
+                    t.dy = (int8_t)(d->up > 1 ? vy / d->up : r - d->pad_h);
+                    t.dx = (int8_t)(d->up > 1 ? vx / d->up : s - d->pad_w);
+                    t.slot = (int8_t)(r * d->KW + s);
+                }
+        }
+    P.total_tiles = tile_base;
+    SPAA_CHECK_ARG(P.total_tiles > 0, "spaa_conv_tc_fwd: empty problem");
+
+    CUtensorMap ma, mb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(TW * d->stride), (cuuint32_t)(TH * d->stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(input) failed with %d", (int)r); return SPAA_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->KH * d->KW * BN};
+        cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return SPAA_ERR_CUDA; }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = SPAA_OK;
+    if (BK == 64) {
+        if (BN == 32) rc = launch_tc<32, 64>(ma, mb, P, st);
+        else if (BN == 64) rc = launch_tc<64, 64>(ma, mb, P, st);
+        else if (BN == 128) rc = launch_tc<128, 64>(ma, mb, P, st);
+        else rc = launch_tc<256, 64>(ma, mb, P, st);
+    } else {
+        if (BN == 32) rc = launch_tc<32, 32>(ma, mb, P, st);
+        else if (BN == 64) rc = launch_tc<64, 32>(ma, mb, P, st);
+        else if (BN == 128) rc = launch_tc<128, 32>(ma, mb, P, st);
+        else rc = launch_tc<256, 32>(ma, mb, P, st);
+    }
+    if (rc != SPAA_OK) return rc;
+    SPAA_CHECK_LAUNCH("spaa_conv_tc_fwd");
+    return SPAA_OK;
+}
+
+}  // extern "C"

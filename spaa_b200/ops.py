@@ -330,6 +330,47 @@ def _w_strides(w: Tensor, k: int):
     return w.stride(0), w.stride(1)
 
 
+_packed_cache: Dict[tuple, Tensor] = {}
+TC_ENABLED = True          # tests flip this to compare the tensor-core path against the CUDA-core path
+
+
+def invalidate_packed_weights() -> None:
+    """Drop the bf16 packed-weight cache (call after parameters were updated in place by a raw kernel)."""
+    _packed_cache.clear()
+
+
+def _tc_weights(d: ConvDesc, w: Tensor) -> Tensor:
+    key = (w.data_ptr(), w._version, tuple(w.shape), tuple(w.stride()), d.flip, d.w_cis, d.w_cos, d.KH, d.Cin, d.Cout)
+    t = _packed_cache.get(key)
+    if t is None:
+        L = lib()
+        t = torch.empty(L.spaa_conv_tc_packed_elems(ctypes.byref(d)), dtype=torch.bfloat16, device=w.device)
+        L.spaa_conv_tc_pack_weights(ctypes.byref(d), _p(w), _p(t), _stream()); _count()
+        if len(_packed_cache) > 512:
+            _packed_cache.clear()
+        _packed_cache[key] = t
+    return t
+
+
+def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, out2) -> None:
+    L = lib()
+    use_tc = (TC_ENABLED and d.in_dtype == 1 and d.out_dtype == 1 and (d.epi_flags & ~EPI_RELU) == 0
+              and L.spaa_conv_tc_supported(ctypes.byref(d)) == 1)
+    with _Probe(kind + ("_tc" if use_tc else ""), spec):
+        if use_tc:
+            L.spaa_conv_tc_fwd(ctypes.byref(d), _p(x), _p(_tc_weights(d, w)), _p(b), _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream())
+        else:
+            L.spaa_conv_fwd(ctypes.byref(d), _p(x), _p(w), _p(b), _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream())
+    _count()
+
+
+def _new_act(shape, dtype, device) -> Tensor:
+    """Activation buffer: bf16 tensors are NHWC (channels-last) so the tensor-core kernels can TMA them; fp32 stays NCHW."""
+    if dtype == torch.bfloat16:
+        return torch.empty(shape, dtype=dtype, device=device, memory_format=torch.channels_last)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
 def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, out: Optional[Tensor] = None,
                  add: Optional[Tensor] = None, epi: int = 0, out_dtype=None) -> Tensor:
     """Forward of nn.Conv2d / nn.ConvTranspose2d with the fused epilogue `epi` (bias, residual add, activation, clamp)."""
@@ -337,7 +378,7 @@ def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, o
     B, _, H, W = x.shape
     Ho, Wo = spec.out_hw(H, W)
     if out is None:
-        out = torch.empty((B, spec.cout, Ho, Wo), dtype=out_dtype or x.dtype, device=x.device)
+        out = _new_act((B, spec.cout, Ho, Wo), out_dtype or x.dtype, x.device)
     d = ConvDesc()
     d.Cin, d.Cout, d.KH, d.KW = spec.cin, spec.cout, spec.k, spec.k
     s0, s1 = _w_strides(w, spec.k)
@@ -351,8 +392,7 @@ def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, o
         d.w_cis, d.w_cos = s0, s1
     d.epi_flags, d.mask_mode = epi, MASK_NONE
     _fill_desc(d, x, out, add, None)
-    with _Probe("fwd", spec):
-        lib().spaa_conv_fwd(ctypes.byref(d), _p(x), _p(w), _p(b), _p(add), None, None, _p(out), None, _stream()); _count()
+    _launch_conv("fwd", spec, d, x, w, b, add, None, None, out, None)
     return out
 
 
@@ -365,7 +405,7 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
     B = dy.shape[0]
     cin = w.shape[1] if spec.kind == "conv" else w.shape[0]      # possibly sliced
     if out is None:
-        out = torch.empty((B, cin, in_hw[0], in_hw[1]), dtype=out_dtype or dy.dtype, device=dy.device)
+        out = _new_act((B, cin, in_hw[0], in_hw[1]), out_dtype or dy.dtype, dy.device)
     d = ConvDesc()
     d.Cin, d.Cout, d.KH, d.KW = spec.cout, cin, spec.k, spec.k
     s0, s1 = _w_strides(w, spec.k)
@@ -383,8 +423,7 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
         assert out2 is not None and out2.stride() == out.stride()
         if mask is not None:
             assert mask2.stride()[1:] == mask.stride()[1:]
-    with _Probe("bwd_data", spec):
-        lib().spaa_conv_fwd(ctypes.byref(d), _p(dy), _p(w), None, _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream()); _count()
+    _launch_conv("bwd_data", spec, d, dy, w, None, add, mask, mask2, out, out2)
     return out
 
 
