@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native SPAA hot path (contract: see README / DESIGN.md section 7).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16|bf16|fp32]
 
 Workload (BASELINE.json configs[1]): SPAA attack, resnet18 classifier, batch of 32 target images, synthetic 256x256
 projector / 240x320 camera data, random-init PCNet.  One "step" = one iteration of the attack loop for the whole batch
@@ -113,6 +113,13 @@ def cpu_reference_run(sample_B: int, warmup: int, steps: int, device="cpu"):
     times = []
 
     def classify(im):
+        if dev.type == "cuda":      # stock ops the reference dispatches (img_proc.py:117-123: F.interpolate(mode='area')), no python pool matrix
+            x = torch.nn.functional.interpolate(O.crop_center(im, CROP), clf.input_sz, mode="area")
+            mean = torch.tensor(O.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+            std = torch.tensor(O.IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+            logits = clf.model((x - mean) / std)
+            p_sorted, idx = torch.softmax(logits, 1).detach().sort(descending=True)
+            return logits, p_sorted, idx
         return O.classify(clf.model, im, CROP, clf.input_sz)
 
     def pc(x, s):
@@ -181,6 +188,7 @@ def run_ours(args):
     pcnet = models.PCNet(P["mask"], torch.nn.DataParallel(wn), torch.nn.DataParallel(sn))
     pcnet.load_state_dict(P, strict=True)
     pcnet = pcnet.to(dev).eval()
+    models.set_precision(pcnet, args.precision)
     for p in pcnet.parameters():
         p.requires_grad = False
     clf = make_classifier(dev)
@@ -196,7 +204,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- timed region: exactly K iterations, CUDA events on the launching stream -----------------------------------
-    probe = ops.set_probe(lambda kind, spec: spec.k == 3 and {spec.cin, spec.cout} == {128, 256})
+    probe = ops.set_probe(lambda kind, spec: spec.k == 3 and {spec.cin, spec.cout} == {128, 256})      # conv4 / conv4_s / conv5 fwd + bwd-data
     clocks = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = ops.launch_count()
@@ -255,14 +263,37 @@ def run_ours(args):
     achieved = flop / (k_ms * 1e-3) / 1e12 if k_ms else 0.0
     line = {"metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config_dict(world, args.precision),
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world, args.precision),
             "sample_iters_per_sec": its * BATCH, "classifier_ms_per_step": clf_ms,
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                     "note": "one spaa() call of `steps` iterations: scene H2D from pinned memory + results D2H inside the timed region; bytes are per call / steps"},
-            "roofline": {"bound": "tensor", "kernel": "conv_gather_kernel<128,64,8,4> on the 128<->256-channel 3x3 layers (fp32 CUDA-core path)",
+            "roofline": {"bound": "tensor", "kernel": ("conv_tc_kernel (tcgen05.mma M128 x N{128,256} x K16, TMA-fed) on the 128<->256-channel 3x3 layers" if args.precision != "fp32"
+                                    else "conv_gather_kernel<128,64,8,4> on the 128<->256-channel 3x3 layers (fp32 CUDA-core path)"),
                          "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                          "traffic": None, "launches_timed": len(kern_ms), "avg_launch_ms": k_ms, "peak_source": pk["source"] + " bf16 sustained"}}
+    if world == 1 and not args.skip_side_legs:
+        # side legs (not the headline): the exact fp32 mode of the same engine, and the reference algorithm on stock PyTorch-CUDA ops
+        # (cuDNN TF32 convolutions + ~1.3k ATen kernels per iteration = what the reference executes on a GPU), same batch, same box
+        if args.precision != "fp32":
+            models.set_precision(pcnet, "fp32")
+            A32 = SpaaAttack(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP)
+            n32 = max(3, min(args.steps, 10))
+            for _ in range(3):
+                A32.step()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); f0.record()
+            for _ in range(n32):
+                A32.step()
+            f1.record(); torch.cuda.synchronize()
+            line["fp32_mode"] = {"value": n32 / (f0.elapsed_time(f1) / 1e3), "unit": "it/s", "steps": n32,
+                                 "note": "same engine, exact CUDA-core fp32 convolutions (the 1e-5 parity mode)"}
+            models.set_precision(pcnet, args.precision)
+            del A32
+        sec = cpu_reference_run(BATCH, 2, 5, device=str(dev))
+        line["torch_cuda_reference"] = {"value": 1.0 / sec, "unit": "it/s", "steps": 5,
+                                        "note": "oracle port of projector_based_attack.py:212-339 on stock PyTorch-CUDA ops (cuDNN, allow_tf32 default), "
+                                                "B=32, two backward passes per iteration as in the reference; wall clock with synchronize"}
     if world == 1 and not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -281,7 +312,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16", "fp16"],
+                    help="fp16 (default): tcgen05 convolutions, fp16 activations / bf16 gradients, fp32 accumulation -- the 16-bit mode that meets "
+                         "BASELINE.json's 2e-3 bar; bf16: pure bf16 storage; fp32: exact CUDA-core convolutions (1e-5 parity mode)")
+    ap.add_argument("--skip-side-legs", action="store_true", help="profiling runs only: omit the fp32 and torch-CUDA side measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -81,6 +81,12 @@ int spaa_grid_finish_bwd(const float* coarse, const float* refine /*nullable*/, 
 int spaa_grid_sample_fwd(const float* img, int64_t B, int C, int Hi, int Wi, const float* grid, int64_t grid_bstride,
                          int H, int W, int clamp01, const float* mask, float* out, const float* rough,
                          int64_t rough_bstride, float* out2, int64_t out2_bstride, spaa_stream_t stream);
+/* The same 3-channel warp written as the zero-padded 16-channel 16-bit NHWC tensor [B,H,W,16] the tensor-core
+ * convolutions read: channels 0-2 = bilinear(clamp(img)) * mask (conv1 input), 3-5 = rough (the surface image),
+ * 6-8 = their product (conv1_s input is channels 3-8), 9-15 = 0.  dtype: 1 bf16, 2 fp16.  rough may be NULL. */
+int spaa_grid_sample_fwd_packed(const float* img, int64_t B, int Hi, int Wi, const float* grid, int64_t grid_bstride, int H,
+                                int W, int clamp01, const float* mask, const float* rough, int64_t rough_bstride, void* out16,
+                                int dtype, spaa_stream_t stream);
 /* dimg (+)= scatter of (dout + dout2*rough) * mask ; dimg must be zero-filled by the caller (atomic accumulate);
  * clamp01: zero the gradient where img is outside [0,1] is NOT applied here (applied by the consumer). */
 int spaa_grid_sample_bwd_input(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,
@@ -115,7 +121,7 @@ enum {
     SPAA_MASK_OPEN01 = 3  /* v *= (m > 0 && m < 1)     backward of clamp(relu(.),max=1) */
 };
 typedef struct spaa_conv_desc {
-    int32_t in_dtype, out_dtype;         /* 0 fp32, 1 bf16; add / mask / mask2 / out2 share out_dtype */
+    int32_t in_dtype, out_dtype;         /* 0 fp32, 1 bf16, 2 fp16; add / out2 share out_dtype; masks: see below */
     int32_t B, Cin, Hin, Win, Cout, Hout, Wout;
     int32_t KH, KW, stride, up, pad_h, pad_w;
     int32_t flip;                        /* 1: tap (r,s) reads weight tap (KH-1-r, KW-1-s) */
@@ -140,14 +146,19 @@ int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* do
                          spaa_stream_t stream);
 /* Tensor-core path of the same operation: tcgen05.mma (M=128 x N=Cout x K=16, fp32 accumulators in TMEM) fed by 4-D TMA
  * box loads of the NHWC input (one shifted box per filter tap; zero padding = TMA out-of-bound fill).  Requirements
- * (spaa_conv_tc_supported tells): bf16 in/out, dense NHWC (in_cs = out_cs = 1, *_ps = C), Cin and Cout multiples of 32
- * (Cin > 64: of 64; Cout <= 256), square kernels <= 3x3, (stride, up) in {(1,1), (2,1), (1,2)}.  Epilogue: bias,
- * residual add, ReLU (SPAA_EPI_RELU only), mask / mask2 / out2 as in spaa_conv_fwd.
+ * (spaa_conv_tc_supported tells): bf16 or fp16 dense NHWC input with 16, 32 or 64k channels; output either the same
+ * 16-bit type, dense NHWC, Cout a multiple of 32 (<= 256), or fp32 dense NCHW with Cout <= 32 (conv6 forward, conv1
+ * backward); square kernels <= 3x3, (stride, up) in {(1,1), (2,1), (1,2)}.  Epilogue: bias, residual add, ReLU
+ * (+ clamp for fp32 output), ReLU mask / mask2 / out2 as in spaa_conv_fwd; masks are 16-bit activations of EITHER
+ * type (only their sign is used), so fp16 forward activations can mask bf16 gradients.
  * Weights are packed once per layer and direction into bf16 [tap][Cout][Cin] by spaa_conv_tc_pack_weights (which reads
  * the fp32 parameter through d->w_* / d->flip). */
 int spaa_conv_tc_supported(const spaa_conv_desc* d);
 int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d);
-int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, void* packed, spaa_stream_t stream);
+/* cin_real / cin_offset: the fp32 parameter has cin_real input channels which sit at tensor channels
+ * [cin_offset, cin_offset + cin_real) of a zero-padded d->Cin-channel NHWC activation (3-, 6-channel images padded to 16). */
+int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, int cin_real, int cin_offset, void* packed,
+                              spaa_stream_t stream);
 int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add,
                      const void* mask, const void* mask2, void* out, void* out2, spaa_stream_t stream);
 /* out[c] += sum_{b,p} x[b,p,c]  (bias gradient; x addressed by element strides, dtype 0 fp32 / 1 bf16) */
@@ -194,6 +205,10 @@ int spaa_masked_copy_rows(float* dst, const float* src, const uint8_t* sel, int6
  * stealth) and applies the backward of the network's output activation in the same pass. act/sel nullable. */
 int spaa_select_cotangent(const float* g0, const float* g1, const uint8_t* sel, const float* act, int mask_mode,
                           float* out, int64_t B, int64_t n, spaa_stream_t stream);
+/* The same selection for 3-channel images [B,3,HW], written as zero-padded 16-channel 16-bit NHWC [B,HW,16]
+ * (the operand of the tensor-core backward of the network's last convolution).  dtype: 1 bf16, 2 fp16. */
+int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t* sel, const float* act, int mask_mode,
+                                 void* out16, int dtype, int64_t B, int64_t HW, spaa_stream_t stream);
 /* PerC-AL projection: delta = clamp(base+delta,0,1)-base ; xsum (nullable) = base+delta ;
  * xq = round((base+delta)*255)/255 ; l2sum[b] = sum_p ||delta[b,:,p]||_2   (perc_al/__init__.py:211-215, :15-18).
  * Tensors [B,3,HW]; base_bstride may be 0. */

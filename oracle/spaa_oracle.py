@@ -2,8 +2,10 @@
 
 A plain-torch (CPU, fp32 or fp64) restatement of the reference algorithms on the
 hot path named by BASELINE.json `north_star`.  Only `tests/`,
-`__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs may
-import this module; nothing under `spaa_b200/` does.
+`__graft_entry__.smoke()` and `bench.py`'s baseline legs (`cpu_baseline`, `--impl reference`,
+and the `torch_cuda_reference` side leg, which runs these same stock-PyTorch ops on the
+GPU as the denominator of the north-star's ">= 10x PyTorch-CUDA" target) may import this
+module; nothing under `spaa_b200/` does.  Tensors are created on the device of the inputs.
 
 Pinning: every function here is checked against the UNMODIFIED reference, imported in
 the build container by `tests/golden/make_golden.py`, through the fixtures committed in
@@ -56,7 +58,7 @@ def area_resize(x: Tensor, size: Sequence[int]) -> Tensor:
     oh, ow = int(size[0]), int(size[1])
 
     def pool_matrix(n_in: int, n_out: int) -> Tensor:
-        m = torch.zeros(n_out, n_in, dtype=x4.dtype)
+        m = torch.zeros(n_out, n_in, dtype=x4.dtype, device=x4.device)
         for o in range(n_out):
             lo = (o * n_in) // n_out
             hi = -((-(o + 1) * n_in) // n_out)
@@ -78,8 +80,8 @@ def classifier_preprocess(im: Tensor, crop_sz: Sequence[int], input_sz: Sequence
     if im.dtype == torch.uint8:
         im = im.to(torch.float32) / 255
     x = area_resize(crop_center(to_4d(im), crop_sz), input_sz)
-    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, dtype=x.dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     return (x - mean) / std
 
 
@@ -122,7 +124,7 @@ def _lab_f(t: Tensor) -> Tensor:
 def srgb_to_lab(rgb: Tensor) -> Tensor:
     """differential_color_functions.py:39-64 (rgb2lab_diff).  rgb: Bx3xHxW -> Lab Bx3xHxW."""
     lin = _srgb_linear_x100(rgb)
-    m = torch.tensor(_RGB2XYZ, dtype=rgb.dtype)
+    m = torch.tensor(_RGB2XYZ, dtype=rgb.dtype, device=rgb.device)
     # :22 is a [3,3]x[3,BHW] matmul; einsum over the channel axis is the same contraction
     xyz = torch.einsum("kc,bchw->bkhw", m, lin)
     fx = _lab_f(xyz[:, 0] / _WHITE[0])
@@ -233,14 +235,15 @@ def tps_sampling_grid(theta: Tensor, ctrl: Tensor, H: int, W: int) -> Tensor:
     """pytorch_tps.py:79-106 + 54-74.  theta: 1x(T+2)x2 (reduced form) or 1x(T+3)x2;
     ctrl: Tx2 in [0,1].  Returns 1xHxWx2 sampling grid in [-1,1] (x,y order)."""
     dt = theta.dtype
-    ys, xs = torch.meshgrid(torch.linspace(0, 1, H, dtype=dt), torch.linspace(0, 1, W, dtype=dt), indexing="ij")
+    dv = theta.device
+    ys, xs = torch.meshgrid(torch.linspace(0, 1, H, dtype=dt, device=dv), torch.linspace(0, 1, W, dtype=dt, device=dv), indexing="ij")
     xy = torch.stack((xs, ys), dim=-1)                                    # H W 2
-    d = torch.sqrt(((xy.unsqueeze(-2) - ctrl.to(dt)) ** 2).sum(-1))       # H W T
+    d = torch.sqrt(((xy.unsqueeze(-2) - ctrl.to(dv, dt)) ** 2).sum(-1))       # H W T
     U = d ** 2 * torch.log(d + 1e-6)
     w, a = theta[0, :-3], theta[0, -3:]
     if theta.shape[1] == ctrl.shape[0] + 2:                               # reduced form, :66-69
         w = torch.cat((-w.sum(0, keepdim=True), w), 0)
-    ones = torch.ones(H, W, 1, dtype=dt)
+    ones = torch.ones(H, W, 1, dtype=dt, device=dv)
     z = torch.cat((ones, xy), -1) @ a + U @ w                             # H W 2
     return ((xy + z) * 2 - 1).unsqueeze(0)
 
@@ -248,7 +251,7 @@ def tps_sampling_grid(theta: Tensor, ctrl: Tensor, H: int, W: int) -> Tensor:
 def affine_base_grid(theta: Tensor, H: int, W: int) -> Tensor:
     """F.affine_grid(theta[1,2,3], (1,C,H,W), align_corners=True) (models.py:151,168) -> 1xHxWx2."""
     dt = theta.dtype
-    ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, dtype=dt), torch.linspace(-1, 1, W, dtype=dt), indexing="ij")
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, H, dtype=dt, device=theta.device), torch.linspace(-1, 1, W, dtype=dt, device=theta.device), indexing="ij")
     base = torch.stack((xs, ys, torch.ones_like(xs)), -1)                 # H W 3
     return (base @ theta[0].t()).unsqueeze(0)
 
@@ -465,8 +468,8 @@ def spaa_attack(pcnet_fn, classifier_fn, target_idx: Sequence[int], targeted: bo
     B = len(target_idx)
     scene = to_4d(cam_scene)
     scene_b = scene.expand(B, -1, -1, -1)
-    tgt = torch.as_tensor(list(target_idx), dtype=torch.long)
-    gray = prj_brightness * torch.ones(B, 3, *prj_hw, dtype=scene.dtype)
+    tgt = torch.as_tensor(list(target_idx), dtype=torch.long, device=scene.device)
+    gray = prj_brightness * torch.ones(B, 3, *prj_hw, dtype=scene.dtype, device=scene.device)
     prj = gray.clone().requires_grad_(True)
     adv_lr, col_lr, p_thresh = 2, 1, 0.9                                  # :243-255
     w_prjl2 = 0.1 if "prjl2" in stealth_loss else 0
@@ -474,8 +477,8 @@ def spaa_attack(pcnet_fn, classifier_fn, target_idx: Sequence[int], targeted: bo
     w_camde = 1 if "camdE" in stealth_loss else 0
     best_prj = prj.detach().clone()
     best_cam = scene.repeat(B, 1, 1, 1).clone()
-    best_col = 1e6 * torch.ones(B, dtype=scene.dtype)
-    ar = torch.arange(B)
+    best_col = 1e6 * torch.ones(B, dtype=scene.dtype, device=scene.device)
+    ar = torch.arange(B, device=scene.device)
 
     for it in range(iters):
         if forced_prj is not None:

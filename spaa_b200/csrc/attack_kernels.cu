@@ -104,6 +104,37 @@ __global__ void __launch_bounds__(kThreads) select_cot_kernel(const float* __res
     }
 }
 
+// same selection, written as the zero-padded 16-channel 16-bit NHWC tensor the tensor-core backward of conv6 reads
+template <bool F16>
+__global__ void __launch_bounds__(kThreads) select_cot_packed_kernel(const float* __restrict__ g0, const float* __restrict__ g1, const uint8_t* __restrict__ sel,
+                                                                     const float* __restrict__ act, int mode, uint4* __restrict__ out16, int64_t HW) {
+    const int b = blockIdx.y;
+    const float* src = ((sel && sel[b]) ? g1 : g0) + (int64_t)b * 3 * HW;
+    const float* a = act ? act + (int64_t)b * 3 * HW : nullptr;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            v[c] = __ldg(src + c * HW + p);
+            if (a) {
+                const float m = __ldg(a + c * HW + p);
+                if (mode == SPAA_MASK_POS) v[c] = m > 0.f ? v[c] : 0.f;
+                else if (mode == SPAA_MASK_OPEN01) v[c] = (m > 0.f && m < 1.f) ? v[c] : 0.f;
+            }
+        }
+        uint4 lo = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (F16) {
+            const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], 0.f);
+            lo.x = *reinterpret_cast<const uint32_t*>(&h0); lo.y = *reinterpret_cast<const uint32_t*>(&h1);
+        } else {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], 0.f);
+            lo.x = *reinterpret_cast<const uint32_t*>(&h0); lo.y = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        uint4* o = out16 + ((int64_t)b * HW + p) * 2;
+        o[0] = lo; o[1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // PerC-AL projection (perc_al/__init__.py:211-215, :15-18)
 __global__ void __launch_bounds__(kThreads) percal_project_kernel(const float* __restrict__ base, int64_t base_bs, float* __restrict__ delta,
                                                                   float* __restrict__ xq, float* __restrict__ xsum, float* __restrict__ l2sum, int64_t HW,
@@ -289,6 +320,15 @@ int spaa_select_cotangent(const float* g0, const float* g1, const uint8_t* sel, 
     SPAA_CHECK_ARG(g0 && out && B > 0 && B < 65536 && n > 0 && (!sel || g1), "spaa_select_cotangent: bad arguments");
     select_cot_kernel<<<row_grid(n, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, out, n);
     SPAA_CHECK_LAUNCH("spaa_select_cotangent");
+    return SPAA_OK;
+}
+
+int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t* sel, const float* act, int mask_mode, void* out16, int dtype, int64_t B,
+                                 int64_t HW, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(g0 && out16 && B > 0 && B < 65536 && HW > 0 && (!sel || g1) && (dtype == 1 || dtype == 2), "spaa_select_cotangent_packed: bad arguments");
+    if (dtype == 2) select_cot_packed_kernel<true><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
+    else select_cot_packed_kernel<false><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
+    SPAA_CHECK_LAUNCH("spaa_select_cotangent_packed");
     return SPAA_OK;
 }
 

@@ -6,6 +6,7 @@
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #define SPAA_HD __host__ __device__ __forceinline__
 #define SPAA_D __device__ __forceinline__
 #else
@@ -116,6 +117,8 @@ SPAA_D float ld_f(const float* p) { return __ldg(p); }
 SPAA_D float ld_f(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 SPAA_D void st_f(float* p, float v) { *p = v; }
 SPAA_D void st_f(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+SPAA_D float ld_f(const __half* p) { return __half2float(*p); }
+SPAA_D void st_f(__half* p, float v) { *p = __float2half_rn(v); }
 
 #endif  // __CUDACC__
 

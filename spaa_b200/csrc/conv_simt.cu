@@ -198,10 +198,16 @@ int launch_cfg(const ConvP& p, cudaStream_t st) {
     const spaa_conv_desc& d = p.d;
     const int64_t M = (int64_t)d.B * d.Hout * d.Wout;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((d.Cout + BN - 1) / BN));
-    if (d.in_dtype == 0 && d.out_dtype == 0) conv_gather_kernel<BM, BN, TM, TN, float, float><<<grid, kThreads, 0, st>>>(p);
-    else if (d.in_dtype == 0 && d.out_dtype == 1) conv_gather_kernel<BM, BN, TM, TN, float, __nv_bfloat16><<<grid, kThreads, 0, st>>>(p);
-    else if (d.in_dtype == 1 && d.out_dtype == 0) conv_gather_kernel<BM, BN, TM, TN, __nv_bfloat16, float><<<grid, kThreads, 0, st>>>(p);
-    else conv_gather_kernel<BM, BN, TM, TN, __nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, st>>>(p);
+#define SPAA_CONV_CASE(I, O, IT, OT) \
+    if (d.in_dtype == I && d.out_dtype == O) conv_gather_kernel<BM, BN, TM, TN, IT, OT><<<grid, kThreads, 0, st>>>(p)
+    SPAA_CONV_CASE(0, 0, float, float);
+    SPAA_CONV_CASE(0, 1, float, __nv_bfloat16);
+    SPAA_CONV_CASE(0, 2, float, __half);
+    SPAA_CONV_CASE(1, 0, __nv_bfloat16, float);
+    SPAA_CONV_CASE(1, 1, __nv_bfloat16, __nv_bfloat16);
+    SPAA_CONV_CASE(2, 0, __half, float);
+    SPAA_CONV_CASE(2, 2, __half, __half);
+#undef SPAA_CONV_CASE
     return 0;
 }
 
@@ -339,7 +345,8 @@ int spaa_conv_fwd(const spaa_conv_desc* d, const void* in, const float* w, const
     SPAA_CHECK_ARG(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Hin > 0 && d->Win > 0 && d->Hout > 0 && d->Wout > 0 && d->KH > 0 && d->KW > 0 &&
                        d->stride > 0 && d->up > 0,
                    "spaa_conv_fwd: bad dimensions");
-    SPAA_CHECK_ARG((unsigned)d->in_dtype < 2 && (unsigned)d->out_dtype < 2, "spaa_conv_fwd: bad dtype");
+    SPAA_CHECK_ARG((unsigned)d->in_dtype < 3 && (unsigned)d->out_dtype < 3 && !(d->in_dtype && d->out_dtype && d->in_dtype != d->out_dtype),
+                   "spaa_conv_fwd: dtype must be 0 (fp32), 1 (bf16) or 2 (fp16); mixed bf16/fp16 is not implemented on the CUDA-core path");
     SPAA_CHECK_ARG((out2 == nullptr) == (mask2 == nullptr), "spaa_conv_fwd: out2 and mask2 go together");
     SPAA_CHECK_ARG(d->mask_mode == SPAA_MASK_NONE || mask, "spaa_conv_fwd: mask_mode needs mask");
     ConvP p{*d, in, w, bias, add, mask, mask2, out, out2};
@@ -355,7 +362,7 @@ int spaa_conv_fwd(const spaa_conv_desc* d, const void* in, const float* w, const
 int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* dout, float* dw, float* dbias, spaa_stream_t stream) {
     SPAA_CHECK_ARG(d && in && dout && dw, "spaa_conv_bwd_weight: null argument");
     SPAA_CHECK_ARG(d->up == 1 && d->flip == 0, "spaa_conv_bwd_weight: describe the forward gather conv (up == 1, flip == 0)");
-    SPAA_CHECK_ARG((unsigned)d->in_dtype < 2 && (unsigned)d->out_dtype < 2, "spaa_conv_bwd_weight: bad dtype");
+    SPAA_CHECK_ARG((unsigned)d->in_dtype < 3 && (unsigned)d->out_dtype < 3, "spaa_conv_bwd_weight: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t M = (int64_t)d->B * d->Hout * d->Wout;
     const int ci_tiles = (d->Cin + WB - 1) / WB, co_tiles = (d->Cout + WB - 1) / WB;
@@ -369,10 +376,18 @@ int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* do
     splits = (M + pps - 1) / pps;
     WgP p{*d, in, dout, dw, pps};
     dim3 grid((unsigned)splits, (unsigned)(d->KH * d->KW * ci_tiles), (unsigned)co_tiles);
-    if (d->in_dtype == 0 && d->out_dtype == 0) conv_bwd_weight_kernel<float, float><<<grid, kThreads, 0, st>>>(p);
-    else if (d->in_dtype == 0) conv_bwd_weight_kernel<float, __nv_bfloat16><<<grid, kThreads, 0, st>>>(p);
-    else if (d->out_dtype == 0) conv_bwd_weight_kernel<__nv_bfloat16, float><<<grid, kThreads, 0, st>>>(p);
-    else conv_bwd_weight_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kThreads, 0, st>>>(p);
+#define SPAA_WG_CASE(I, O, IT, OT) \
+    if (d->in_dtype == I && d->out_dtype == O) conv_bwd_weight_kernel<IT, OT><<<grid, kThreads, 0, st>>>(p)
+    SPAA_WG_CASE(0, 0, float, float);
+    SPAA_WG_CASE(0, 1, float, __nv_bfloat16);
+    SPAA_WG_CASE(0, 2, float, __half);
+    SPAA_WG_CASE(1, 0, __nv_bfloat16, float);
+    SPAA_WG_CASE(1, 1, __nv_bfloat16, __nv_bfloat16);
+    SPAA_WG_CASE(1, 2, __nv_bfloat16, __half);
+    SPAA_WG_CASE(2, 0, __half, float);
+    SPAA_WG_CASE(2, 1, __half, __nv_bfloat16);
+    SPAA_WG_CASE(2, 2, __half, __half);
+#undef SPAA_WG_CASE
     SPAA_CHECK_LAUNCH("spaa_conv_bwd_weight");
     if (dbias) {
         int64_t bsplits = M / 4096;
@@ -381,14 +396,15 @@ int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* do
         const int64_t bpps = (M + bsplits - 1) / bsplits;
         bsplits = (M + bpps - 1) / bpps;
         if (d->out_dtype == 0) bias_grad_kernel<float><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const float*)dout, dbias, bpps);
-        else bias_grad_kernel<__nv_bfloat16><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const __nv_bfloat16*)dout, dbias, bpps);
+        else if (d->out_dtype == 1) bias_grad_kernel<__nv_bfloat16><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const __nv_bfloat16*)dout, dbias, bpps);
+        else bias_grad_kernel<__half><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const __half*)dout, dbias, bpps);
         SPAA_CHECK_LAUNCH("spaa_conv_bwd_weight(bias)");
     }
     return SPAA_OK;
 }
 
 int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int64_t bs, int64_t ps, int64_t cs, float* out, spaa_stream_t stream) {
-    SPAA_CHECK_ARG(x && out && B > 0 && C > 0 && HW > 0 && HW < (1ll << 31) && (unsigned)dtype < 2, "spaa_channel_sum: bad arguments");
+    SPAA_CHECK_ARG(x && out && B > 0 && C > 0 && HW > 0 && HW < (1ll << 31) && (unsigned)dtype < 3, "spaa_channel_sum: bad arguments");
     spaa_conv_desc d{};
     d.B = (int)B; d.Cout = C; d.Hout = 1; d.Wout = (int)HW;
     d.out_bs = bs; d.out_ps = ps; d.out_cs = cs;
@@ -399,7 +415,8 @@ int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int
     const int64_t pps = (M + splits - 1) / splits;
     splits = (M + pps - 1) / pps;
     if (dtype == 0) bias_grad_kernel<float><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const float*)x, out, pps);
-    else bias_grad_kernel<__nv_bfloat16><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const __nv_bfloat16*)x, out, pps);
+    else if (dtype == 1) bias_grad_kernel<__nv_bfloat16><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const __nv_bfloat16*)x, out, pps);
+    else bias_grad_kernel<__half><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const __half*)x, out, pps);
     SPAA_CHECK_LAUNCH("spaa_channel_sum");
     return SPAA_OK;
 }

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "../../include/spaa_b200.h"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -47,12 +48,13 @@ struct TcParams {
     int64_t add_bs;             // 0: `add` is broadcast over the batch
     int64_t mask_bs;
     Phase ph[kMaxPhases];
+    int32_t out_planar;         // 1: out / add are fp32 NCHW planes with Cout (real) channels; 0: 16-bit NHWC with Cout channels
     const float* bias;
-    const __nv_bfloat16* add;
-    const __nv_bfloat16* mask;
-    const __nv_bfloat16* mask2;
-    __nv_bfloat16* out;
-    __nv_bfloat16* out2;
+    const void* add;            // 16-bit NHWC (same type as out) or fp32 planar
+    const uint16_t* mask;       // 16-bit NHWC, fp16 or bf16: only the sign / zero test is used
+    const uint16_t* mask2;
+    void* out;
+    void* out2;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -142,16 +144,23 @@ template <int ROW_BYTES> SPAA_D uint64_t make_kmajor_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor (InstrDescriptor): C fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1, both K-major,
 // N>>3 at [17,23), M>>4 at [24,29)
-SPAA_D uint32_t make_idesc(int M, int N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
-
-SPAA_D float apply_mask_tc(float v, float m, int mode) {
-    switch (mode) {
-        case SPAA_MASK_POS: return m > 0.f ? v : 0.f;
-        case SPAA_MASK_LEAKY01: return m > 0.f ? v : 0.1f * v;
-        case SPAA_MASK_OPEN01: return (m > 0.f && m < 1.f) ? v : 0.f;
-        default: return v;
-    }
+SPAA_D uint32_t make_idesc(int M, int N, bool fp16) {
+    const uint32_t fmt = fp16 ? 0u : 1u;          // F32F16Format: 0 = F16, 1 = BF16
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// 16-bit float helpers: T16 = __half or __nv_bfloat16
+template <bool F16> SPAA_D float2 unpack2(uint32_t u) {
+    if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <bool F16> SPAA_D uint32_t pack2(float a, float b) {
+    if constexpr (F16) { const __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+    else { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+}
+// x > 0 for an fp16 or bf16 bit pattern (both: sign bit 15, zero = all other bits clear; NaN counts as positive like `m > 0` never would,
+// but activations are finite)
+SPAA_D bool pos16(uint32_t bits) { return (bits & 0x8000u) == 0u && (bits & 0x7FFFu) != 0u; }
 
 template <int BN, int BK> struct SmemLayout {
     static constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
@@ -161,7 +170,7 @@ template <int BN, int BK> struct SmemLayout {
     static constexpr int kTotal = kBiasOff + BN * 4 + 1024;               // + slack for the 1024 B alignment of the ring
 };
 
-template <int BN, int BK>
+template <int BN, int BK, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                               const __grid_constant__ TcParams P) {
     using L = SmemLayout<BN, BK>;
@@ -231,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer ==========================================
-        const uint32_t idesc = make_idesc(BM, BN);
+        const uint32_t idesc = make_idesc(BM, BN, F16);
         int stage = 0;
         uint32_t phase = 0;
         int local = 0;
@@ -282,66 +291,78 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                if (valid && c0 < P.Cout) {
-                    float v[32];
+                if (!valid || c0 >= P.Cout) continue;
+                float v[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) + s_bias[c0 + k];
-                    if (P.add) {
-                        const uint4* ap = reinterpret_cast<const uint4*>(P.add + (int64_t)b * P.add_bs + pix + c0);
+                for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) + s_bias[c0 + k];
+                if (P.out_planar) {
+                    // fp32 NCHW planes, Cout (<= 32) real channels: conv6 forward, conv1 / conv1_s backward-data
+                    const int64_t hw = (int64_t)P.Hout * P.Wout;
+                    const int64_t p = (int64_t)oy * P.Wout + ox;
+                    float* op = (float*)P.out + (int64_t)b * P.Cout * hw + p;
+                    const float* ap = P.add ? (const float*)P.add + (int64_t)b * P.add_bs + p : nullptr;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 u = __ldg(ap + g);
-                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = __bfloat1622float2(h[e]);
-                                v[g * 8 + e * 2] += f.x; v[g * 8 + e * 2 + 1] += f.y;
-                            }
+                    for (int k = 0; k < 32; ++k) {
+                        if (k < P.Cout) {
+                            float y = v[k];
+                            if (ap) y += __ldg(ap + k * hw);
+                            if (ef & SPAA_EPI_RELU) y = fmaxf(y, 0.f);
+                            if (ef & SPAA_EPI_CLAMP_MAX1) y = fminf(y, 1.f);
+                            op[k * hw] = y;
                         }
                     }
-                    if (ef & SPAA_EPI_RELU) {
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
-                    }
-                    if (P.mask) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask + (int64_t)b * P.mask_bs + pix + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 u = __ldg(mp + g);
-                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = __bfloat1622float2(h[e]);
-                                v[g * 8 + e * 2] = apply_mask_tc(v[g * 8 + e * 2], f.x, P.mask_mode);
-                                v[g * 8 + e * 2 + 1] = apply_mask_tc(v[g * 8 + e * 2 + 1], f.y, P.mask_mode);
-                            }
-                        }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(P.out + o_off + c0);
+                    continue;
+                }
+                if (P.add) {
+                    const uint4* ap = reinterpret_cast<const uint4*>((const uint16_t*)P.add + (int64_t)b * P.add_bs + pix + c0);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        uint4 u;
-                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+                        const uint4 u = __ldg(ap + g);
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-                        op[g] = u;
-                    }
-                    if (P.out2) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask2 + (int64_t)b * P.mask_bs + pix + c0);
-                        uint4* op2 = reinterpret_cast<uint4*>(P.out2 + o_off + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint4 m = __ldg(mp + g);
-                            const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m);
-                            uint4 u;
-                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 f = __bfloat1622float2(mh[e]);
-                                h[e] = __floats2bfloat162_rn(f.x > 0.f ? v[g * 8 + e * 2] : 0.f, f.y > 0.f ? v[g * 8 + e * 2 + 1] : 0.f);
-                            }
-                            op2[g] = u;
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = unpack2<F16>(w4[e]);
+                            v[g * 8 + e * 2] += f.x; v[g * 8 + e * 2 + 1] += f.y;
                         }
+                    }
+                }
+                if (ef & SPAA_EPI_RELU) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+                }
+                if (P.mask) {                                  // backward of ReLU: keep the gradient where the activation was > 0
+                    const uint4* mp = reinterpret_cast<const uint4*>(P.mask + (int64_t)b * P.mask_bs + pix + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint4 u = __ldg(mp + g);
+                        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (!pos16(w4[e] & 0xFFFFu)) v[g * 8 + e * 2] = 0.f;
+                            if (!pos16(w4[e] >> 16)) v[g * 8 + e * 2 + 1] = 0.f;
+                        }
+                    }
+                }
+                uint4* op = reinterpret_cast<uint4*>((uint16_t*)P.out + o_off + c0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u;
+                    u.x = pack2<F16>(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack2<F16>(v[g * 8 + 2], v[g * 8 + 3]);
+                    u.z = pack2<F16>(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack2<F16>(v[g * 8 + 6], v[g * 8 + 7]);
+                    op[g] = u;
+                }
+                if (P.out2) {
+                    const uint4* mp = reinterpret_cast<const uint4*>(P.mask2 + (int64_t)b * P.mask_bs + pix + c0);
+                    uint4* op2 = reinterpret_cast<uint4*>((uint16_t*)P.out2 + o_off + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint4 m = __ldg(mp + g);
+                        const uint32_t w4[4] = {m.x, m.y, m.z, m.w};
+                        uint32_t o4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o4[e] = pack2<F16>(pos16(w4[e] & 0xFFFFu) ? v[g * 8 + e * 2] : 0.f, pos16(w4[e] >> 16) ? v[g * 8 + e * 2 + 1] : 0.f);
+                        op2[g] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
                     }
                 }
             }
@@ -358,16 +379,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameter (any layout, by strides) -> bf16 [slot = gather tap][BN rows = cout][Cin]
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int KH, int KW, int Cin, int Cout, int BN, int flip,
-                                    int64_t w_ts, int64_t w_cis, int64_t w_cos) {
+template <bool F16>
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int KH, int KW, int Cin, int cin_real, int cin_off, int Cout,
+                                    int BN, int flip, int64_t w_ts, int64_t w_cis, int64_t w_cos) {
     const int64_t total = (int64_t)KH * KW * BN * Cin;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int ci = (int)(e % Cin);
+        const int c = (int)(e % Cin);
         const int co = (int)((e / Cin) % BN);
         const int tap = (int)(e / ((int64_t)Cin * BN));
         const int r = tap / KW, s = tap - r * KW;
         const int wtap = flip ? (KH - 1 - r) * KW + (KW - 1 - s) : tap;
-        out[e] = __float2bfloat16_rn(co < Cout ? w[(int64_t)wtap * w_ts + (int64_t)ci * w_cis + (int64_t)co * w_cos] : 0.f);
+        const int ci = c - cin_off;
+        const float v = (co < Cout && ci >= 0 && ci < cin_real) ? w[(int64_t)wtap * w_ts + (int64_t)ci * w_cis + (int64_t)co * w_cos] : 0.f;
+        if constexpr (F16) { const __half h = __float2half_rn(v); out[e] = *reinterpret_cast<const uint16_t*>(&h); }
+        else { const __nv_bfloat16 h = __float2bfloat16_rn(v); out[e] = *reinterpret_cast<const uint16_t*>(&h); }
     }
 }
 
@@ -393,29 +418,39 @@ int bn_for(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <= 128 
 
 bool tc_supported(const spaa_conv_desc* d, const char** why) {
     auto fail = [&](const char* m) { if (why) *why = m; return false; };
-    if (d->in_dtype != 1 || d->out_dtype != 1) return fail("tensor-core path needs bf16 activations");
-    if (d->Cin % 32 != 0 || d->Cin < 32 || d->Cout % 32 != 0 || d->Cout > 256) return fail("channel counts must be multiples of 32 (Cout <= 256)");
-    if (d->Cin > 64 && d->Cin % 64 != 0) return fail("Cin > 64 must be a multiple of 64");
+    if (d->in_dtype != 1 && d->in_dtype != 2) return fail("tensor-core path needs bf16 or fp16 input activations");
+    const bool planar = d->out_dtype == 0;
+    if (!planar && d->out_dtype != d->in_dtype) return fail("16-bit output must have the input's type");
+    if (!(d->Cin == 16 || d->Cin == 32 || (d->Cin >= 64 && d->Cin % 64 == 0))) return fail("Cin must be 16, 32 or a multiple of 64");
+    if (planar) {
+        if (d->Cout < 1 || d->Cout > 32) return fail("fp32 planar output supports up to 32 channels");
+        const int64_t hw = (int64_t)d->Hout * d->Wout;
+        if (d->out_ps != 1 || d->out_cs != hw || d->out_bs != hw * d->Cout) return fail("fp32 output must be dense NCHW");
+    } else {
+        if (d->Cout % 32 != 0 || d->Cout > 256) return fail("Cout must be a multiple of 32 (<= 256)");
+        if (d->out_cs != 1 || d->out_ps != d->Cout || d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout) return fail("16-bit output must be dense NHWC");
+    }
+    if (d->Cin == 16 && bn_for(d->Cout) != 32) return fail("Cin == 16 is implemented for Cout <= 32");
+    if (d->Cin == 32 && bn_for(d->Cout) > 64) return fail("Cin == 32 is implemented for Cout <= 64");
     if (!((d->up == 1 && (d->stride == 1 || d->stride == 2)) || (d->up == 2 && d->stride == 1))) return fail("unsupported stride / up combination");
     if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return fail("square kernels up to 3x3 only");
-    if (d->in_cs != 1 || d->in_ps != d->Cin || d->out_cs != 1 || d->out_ps != d->Cout) return fail("activations must be dense NHWC");
-    if (d->in_bs != (int64_t)d->Hin * d->Win * d->Cin || d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout) return fail("activations must be dense NHWC");
+    if (d->in_cs != 1 || d->in_ps != d->Cin || d->in_bs != (int64_t)d->Hin * d->Win * d->Cin) return fail("input must be dense NHWC");
     return true;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool F16>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, cudaStream_t st) {
     using L = SmemLayout<BN, BK>;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
             set_last_error("spaa_conv_tc_fwd: cannot reserve %d bytes of shared memory", L::kTotal);
             return SPAA_ERR_CUDA;
         }
         attr = true;
     }
     const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-    conv_tc_kernel<BN, BK><<<grid, kThreads, L::kTotal, st>>>(ma, mb, P);
+    conv_tc_kernel<BN, BK, F16><<<grid, kThreads, L::kTotal, st>>>(ma, mb, P);
     return SPAA_OK;
 }
 
@@ -430,14 +465,18 @@ int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d) {
     return (int64_t)d->KH * d->KW * bn_for(d->Cout) * d->Cin;
 }
 
-int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, void* packed, spaa_stream_t stream) {
-    SPAA_CHECK_ARG(d && w && packed, "spaa_conv_tc_pack_weights: null argument");
+int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, int cin_real, int cin_offset, void* packed, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(d && w && packed && cin_real > 0 && cin_offset >= 0 && cin_offset + cin_real <= d->Cin, "spaa_conv_tc_pack_weights: bad arguments");
     const int BN = bn_for(d->Cout);
     const int64_t total = spaa_conv_tc_packed_elems(d);
     int64_t blocks = (total + 255) / 256;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-    pack_weights_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)packed, d->KH, d->KW, d->Cin, d->Cout, BN, d->flip, d->w_ts,
-                                                                           d->w_cis, d->w_cos);
+    if (d->in_dtype == 2)
+        pack_weights_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, d->KH, d->KW, d->Cin, cin_real, cin_offset, d->Cout,
+                                                                                     BN, d->flip, d->w_ts, d->w_cis, d->w_cos);
+    else
+        pack_weights_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, d->KH, d->KW, d->Cin, cin_real, cin_offset, d->Cout,
+                                                                                      BN, d->flip, d->w_ts, d->w_cis, d->w_cos);
     SPAA_CHECK_LAUNCH("spaa_conv_tc_pack_weights");
     return SPAA_OK;
 }
@@ -449,13 +488,22 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
     SPAA_CHECK_ARG(tc_supported(d, &why), "spaa_conv_tc_fwd: %s", why);
     SPAA_CHECK_ARG((out2 == nullptr) == (mask2 == nullptr), "spaa_conv_tc_fwd: out2 and mask2 go together");
     SPAA_CHECK_ARG(d->mask_mode == SPAA_MASK_NONE || mask, "spaa_conv_tc_fwd: mask_mode needs mask");
-    SPAA_CHECK_ARG(!(d->epi_flags & ~SPAA_EPI_RELU), "spaa_conv_tc_fwd: only the ReLU epilogue flag is implemented on the tensor-core path");
-    SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == d->Cout), "spaa_conv_tc_fwd: add must be dense NHWC");
-    SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == d->Cout), "spaa_conv_tc_fwd: masks must be dense NHWC");
+    const bool planar = d->out_dtype == 0;
+    SPAA_CHECK_ARG(!(d->epi_flags & ~(SPAA_EPI_RELU | (planar ? SPAA_EPI_CLAMP_MAX1 : 0))),
+                   "spaa_conv_tc_fwd: epilogue flags: ReLU (and clamp for fp32 planar output) only");
+    SPAA_CHECK_ARG(!mask || d->mask_mode == SPAA_MASK_POS, "spaa_conv_tc_fwd: only the ReLU mask (SPAA_MASK_POS) is implemented on the tensor-core path");
+    if (planar) {
+        SPAA_CHECK_ARG(!mask && !mask2, "spaa_conv_tc_fwd: masks are not implemented for fp32 planar output");
+        SPAA_CHECK_ARG(!add || (d->add_ps == 1 && d->add_cs == (int64_t)d->Hout * d->Wout), "spaa_conv_tc_fwd: add must be fp32 NCHW planes");
+    } else {
+        SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == d->Cout), "spaa_conv_tc_fwd: add must be dense NHWC");
+        SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == d->Cout), "spaa_conv_tc_fwd: masks must be dense NHWC");
+    }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled is unavailable in this driver"); return SPAA_ERR_CUDA; }
     const int BN = bn_for(d->Cout);
-    const int BK = d->Cin >= 64 ? 64 : 32;
+    const int BK = d->Cin >= 64 ? 64 : d->Cin;
+    const bool f16 = d->in_dtype == 2;
 
     TcParams P;
     memset(&P, 0, sizeof(P));
@@ -463,8 +511,9 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
     P.in_step = d->stride; P.out_step = d->up; P.kchunks = d->Cin / BK;
     P.epi_flags = d->epi_flags; P.mask_mode = mask ? d->mask_mode : SPAA_MASK_NONE;
     P.add_bs = d->add_bs; P.mask_bs = d->mask_bs;
-    P.bias = bias; P.add = (const __nv_bfloat16*)add; P.mask = (const __nv_bfloat16*)mask; P.mask2 = (const __nv_bfloat16*)mask2;
-    P.out = (__nv_bfloat16*)out; P.out2 = (__nv_bfloat16*)out2;
+    P.out_planar = planar ? 1 : 0;
+    P.bias = bias; P.add = add; P.mask = (const uint16_t*)mask; P.mask2 = (const uint16_t*)mask2;
+    P.out = out; P.out2 = out2;
     int tile_base = 0;
     P.nphases = d->up * d->up;
     for (int py = 0; py < d->up; ++py)
@@ -496,8 +545,8 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
         cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2};
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(TW * d->stride), (cuuint32_t)(TH * d->stride), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
-        CUresult r = enc(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+        CUresult r = enc(&ma, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(input) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
@@ -506,24 +555,26 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
         cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
         cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
         cuuint32_t es[2] = {1, 1};
-        CUresult r = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CUresult r = enc(&mb, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = SPAA_OK;
+#define SPAA_TC_LAUNCH(BN_, BK_) rc = f16 ? launch_tc<BN_, BK_, true>(ma, mb, P, st) : launch_tc<BN_, BK_, false>(ma, mb, P, st)
     if (BK == 64) {
-        if (BN == 32) rc = launch_tc<32, 64>(ma, mb, P, st);
-        else if (BN == 64) rc = launch_tc<64, 64>(ma, mb, P, st);
-        else if (BN == 128) rc = launch_tc<128, 64>(ma, mb, P, st);
-        else rc = launch_tc<256, 64>(ma, mb, P, st);
+        if (BN == 32) SPAA_TC_LAUNCH(32, 64);
+        else if (BN == 64) SPAA_TC_LAUNCH(64, 64);
+        else if (BN == 128) SPAA_TC_LAUNCH(128, 64);
+        else SPAA_TC_LAUNCH(256, 64);
+    } else if (BK == 32) {
+        if (BN == 32) SPAA_TC_LAUNCH(32, 32);
+        else SPAA_TC_LAUNCH(64, 32);
     } else {
-        if (BN == 32) rc = launch_tc<32, 32>(ma, mb, P, st);
-        else if (BN == 64) rc = launch_tc<64, 32>(ma, mb, P, st);
-        else if (BN == 128) rc = launch_tc<128, 32>(ma, mb, P, st);
-        else rc = launch_tc<256, 32>(ma, mb, P, st);
+        SPAA_TC_LAUNCH(32, 16);
     }
+#undef SPAA_TC_LAUNCH
     if (rc != SPAA_OK) return rc;
     SPAA_CHECK_LAUNCH("spaa_conv_tc_fwd");
     return SPAA_OK;

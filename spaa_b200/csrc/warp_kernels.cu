@@ -221,6 +221,48 @@ __global__ void __launch_bounds__(kThreads) grid_sample_bwd_grid_kernel(const fl
     }
 }
 
+// 3-channel warp that emits the padded 16-channel 16-bit NHWC tensor the tensor-core convolutions read:
+// [x0,x1,x2, s0,s1,s2, x0*s0,x1*s1,x2*s2, 0 x 7] per pixel (x = bilinear(clamp(img)) * mask, s = surface image).
+template <bool F16>
+__global__ void __launch_bounds__(kThreads) grid_sample_fwd_packed_kernel(const float* __restrict__ img, int Hi, int Wi, const float* __restrict__ grid,
+                                                                           int64_t grid_bs, int H, int W, int clamp01, const float* __restrict__ mask,
+                                                                           const float* __restrict__ rough, int64_t rough_bs, uint4* __restrict__ out16) {
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int64_t HWi = (int64_t)Hi * Wi;
+    const float* g = grid + (int64_t)b * grid_bs;
+    const float* ib = img + (int64_t)b * 3 * HWi;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const warp::Taps<float> t = warp::make_taps<float>(__ldg(g + p), __ldg(g + HW + p), Hi, Wi);
+        const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
+        const float w00 = wx0 * wy0, w01 = t.wx1 * wy0, w10 = wx0 * t.wy1, w11 = t.wx1 * t.wy1;
+        const float m = mask ? __ldg(mask + p) : 1.f;
+        const int64_t o00 = (int64_t)t.y0 * Wi + t.x0;
+        float x[3], sv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* ic = ib + c * HWi;
+            float v = 0.f;
+            if (t.vy0 && t.vx0) v += clamp01_if(__ldg(ic + o00), clamp01) * w00;
+            if (t.vy0 && t.vx1) v += clamp01_if(__ldg(ic + o00 + 1), clamp01) * w01;
+            if (t.vy1 && t.vx0) v += clamp01_if(__ldg(ic + o00 + Wi), clamp01) * w10;
+            if (t.vy1 && t.vx1) v += clamp01_if(__ldg(ic + o00 + Wi + 1), clamp01) * w11;
+            if (mask) v *= m;
+            x[c] = v;
+            sv[c] = rough ? __ldg(rough + (int64_t)b * rough_bs + (int64_t)c * HW + p) : 0.f;
+        }
+        auto pk = [](float a, float c) -> uint32_t {
+            if constexpr (F16) { const __half2 h = __floats2half2_rn(a, c); return *reinterpret_cast<const uint32_t*>(&h); }
+            else { const __nv_bfloat162 h = __floats2bfloat162_rn(a, c); return *reinterpret_cast<const uint32_t*>(&h); }
+        };
+        uint4 lo, hi;
+        lo.x = pk(x[0], x[1]); lo.y = pk(x[2], sv[0]); lo.z = pk(sv[1], sv[2]); lo.w = pk(x[0] * sv[0], x[1] * sv[1]);
+        hi.x = pk(x[2] * sv[2], 0.f); hi.y = 0u; hi.z = 0u; hi.w = 0u;
+        uint4* o = out16 + ((int64_t)b * HW + p) * 2;
+        o[0] = lo; o[1] = hi;
+    }
+}
+
 inline int blocks_for(int64_t n, int cap_mult = 8) {
     int64_t g = (n + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)kNumSMs * cap_mult;
@@ -341,6 +383,21 @@ int spaa_grid_sample_bwd_grid(const float* dout, const float* dout2, int64_t dou
     grid_sample_bwd_grid_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(dout, dout2, dout2_bstride, rough, rough_bstride, mask, img, clamp01,
                                                                         grid, grid_bstride, (int)B, C, Hi, Wi, H, W, dgrid);
     SPAA_CHECK_LAUNCH("spaa_grid_sample_bwd_grid");
+    return SPAA_OK;
+}
+
+int spaa_grid_sample_fwd_packed(const float* img, int64_t B, int Hi, int Wi, const float* grid, int64_t grid_bstride, int H, int W, int clamp01,
+                                const float* mask, const float* rough, int64_t rough_bstride, void* out16, int dtype, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(img && grid && out16 && B > 0 && B < 65536 && Hi > 1 && Wi > 1 && H > 0 && W > 0 && (dtype == 1 || dtype == 2),
+                   "spaa_grid_sample_fwd_packed: bad arguments");
+    dim3 g(blocks_for((int64_t)H * W, 4), (unsigned)B);
+    if (dtype == 2)
+        grid_sample_fwd_packed_kernel<true><<<g, kThreads, 0, (cudaStream_t)stream>>>(img, Hi, Wi, grid, grid_bstride, H, W, clamp01, mask, rough, rough_bstride,
+                                                                                    (uint4*)out16);
+    else
+        grid_sample_fwd_packed_kernel<false><<<g, kThreads, 0, (cudaStream_t)stream>>>(img, Hi, Wi, grid, grid_bstride, H, W, clamp01, mask, rough, rough_bstride,
+                                                                                     (uint4*)out16);
+    SPAA_CHECK_LAUNCH("spaa_grid_sample_fwd_packed");
     return SPAA_OK;
 }
 

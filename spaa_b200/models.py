@@ -57,10 +57,24 @@ class _Stack:
     """Forward / backward schedules of the 17-conv stack.  `net` supplies parameters and specs."""
 
     @staticmethod
-    def surface_branch(net, surf: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    def act_dtype(net):
+        """Storage type of the forward activations: fp32 NCHW (exact CUDA-core path) or 16-bit NHWC (tcgen05 path)."""
+        return {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[getattr(net, "precision", "fp32")]
+
+    @staticmethod
+    def grad_dtype(net):
+        """Storage type of the backward activations: bf16 on both tensor-core modes (gradients need the exponent range)."""
+        return torch.float32 if getattr(net, "precision", "fp32") == "fp32" else torch.bfloat16
+
+    @staticmethod
+    def surface_branch(net, surf: Tensor, packed: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         sp = net._specs
+        ad = _Stack.act_dtype(net)
         W = lambda n: (_get(net, n).weight, _get(net, n).bias)
-        r1s = ops.conv_forward(sp["conv1_s"], surf, *W("conv1_s"), epi=EPI_RELU)
+        if packed is not None:          # [x | s | x*s | 0] 16-channel NHWC: the surface features start at channel 3
+            r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=3)
+        else:
+            r1s = ops.conv_forward(sp["conv1_s"], surf, *W("conv1_s"), epi=EPI_RELU, out_dtype=ad)
         r2s = ops.conv_forward(sp["conv2_s"], r1s, *W("conv2_s"), epi=EPI_RELU)
         r3s = ops.conv_forward(sp["conv3_s"], r2s, *W("conv3_s"), epi=EPI_RELU)
         r4s = ops.conv_forward(sp["conv4_s"], r3s, *W("conv4_s"), epi=EPI_RELU)
@@ -76,21 +90,26 @@ class _Stack:
         return t1, t2, res1
 
     @staticmethod
-    def forward(net, x: Tensor, surf: Optional[Tensor], skip_in: Optional[Tensor], *, surf_acts=None, skip_acts=None) -> Tuple[Tensor, dict]:
+    def forward(net, x: Optional[Tensor], surf: Optional[Tensor], skip_in: Optional[Tensor], *, surf_acts=None, skip_acts=None,
+                packed: Optional[Tensor] = None) -> Tuple[Tensor, dict]:
         """x [B,3,H,W]; surf [B or 1,Cs,H,W] (ignored when surf_acts given); skip_in [B or 1,3,H,W] (ignored when
-        skip_acts given).  Returns (out, saved activations)."""
+        skip_acts given).  `packed`: the 16-channel NHWC tensor [x | s | x*s | 0] from ops.grid_sample_packed replaces x and
+        surf on the tensor-core path.  Returns (out, saved activations)."""
         sp = net._specs
         W = lambda n: (_get(net, n).weight, _get(net, n).bias)
-        S: dict = {"x": x, "surf": surf, "skip_in": skip_in}
+        S: dict = {"x": x, "surf": surf, "skip_in": skip_in, "packed": packed}
         if surf_acts is None:
-            surf_acts = _Stack.surface_branch(net, surf)
+            surf_acts = _Stack.surface_branch(net, surf, packed)
             S["surf_own"] = True
         r1s, r2s, r3s, r4s = surf_acts
         if skip_acts is None:
             skip_acts = _Stack.skip1(net, skip_in)
             S["skip_own"] = True
         t1, t2, res1 = skip_acts
-        x1 = ops.conv_forward(sp["conv1"], x, *W("conv1"), add=r1s, epi=EPI_RELU)
+        if packed is not None:
+            x1 = ops.conv_forward(sp["conv1"], packed, *W("conv1"), add=r1s, epi=EPI_RELU, cin_offset=0)
+        else:
+            x1 = ops.conv_forward(sp["conv1"], x, *W("conv1"), add=r1s, epi=EPI_RELU, out_dtype=r1s.dtype)
         res2 = ops.conv_forward(sp["skipConv2"], x1, *W("skipConv2"))
         x2 = ops.conv_forward(sp["conv2"], x1, *W("conv2"), add=r2s, epi=EPI_RELU)
         res3 = ops.conv_forward(sp["skipConv3"], x2, *W("skipConv3"))
@@ -99,21 +118,23 @@ class _Stack:
         x5 = ops.conv_forward(sp["conv5"], x4, *W("conv5"), add=res3, epi=EPI_RELU)
         x6 = ops.conv_forward(sp["transConv1"], x5, *W("transConv1"), add=res2, epi=EPI_RELU)
         x7 = ops.conv_forward(sp["transConv2"], x6, *W("transConv2"), epi=EPI_RELU)
-        out = ops.conv_forward(sp["conv6"], x7, *W("conv6"), add=res1, epi=EPI_RELU | EPI_CLAMP_MAX1)
+        out = ops.conv_forward(sp["conv6"], x7, *W("conv6"), add=res1, epi=EPI_RELU | EPI_CLAMP_MAX1, out_dtype=torch.float32)
         S.update(r1s=r1s, r2s=r2s, r3s=r3s, r4s=r4s, t1=t1, t2=t2, res1=res1, x1=x1, x2=x2, x3=x3, x4=x4, x5=x5, x6=x6, x7=x7, out=out)
         return out, S
 
     @staticmethod
-    def backward(net, S: dict, d_pre6: Tensor, *, need_dx: bool = True, surf_grad_channels: Optional[Tuple[int, int]] = None,
-                 need_dskip: bool = False, param_grads: Optional[Dict[str, Tensor]] = None):
-        """d_pre6 = d(loss)/d(conv6 pre-activation) = dout * [0 < out < 1].
+    def backward(net, S: dict, d_pre6: Optional[Tensor], *, need_dx: bool = True, surf_grad_channels: Optional[Tuple[int, int]] = None,
+                 need_dskip: bool = False, param_grads: Optional[Dict[str, Tensor]] = None, d_pre6_packed: Optional[Tensor] = None):
+        """d_pre6 = d(loss)/d(conv6 pre-activation) = dout * [0 < out < 1]: fp32 [B,3,H,W], or on the tensor-core path the
+        and/or (tensor-core path) `d_pre6_packed`, the same values as a zero-padded 16-channel bf16 NHWC tensor from
+        ops.select_cotangent_packed, which feeds the backward-data chain (the fp32 form is still needed for parameter gradients).
         Returns (dx, dsurf[:, lo:hi] or None, dskip_in or None); accumulates parameter gradients into `param_grads`
         ({"conv1.weight": fp32 tensor, ...}, zero-filled by the caller) when given."""
         sp = net._specs
         Wt = lambda n: _get(net, n).weight
         pg = param_grads
         hw = lambda t: (t.shape[2], t.shape[3])
-        B = d_pre6.shape[0]
+        B = (d_pre6 if d_pre6 is not None else d_pre6_packed).shape[0]
 
         def wgrad(name, inp, dy):
             if pg is not None and (name + ".weight") in pg:
@@ -125,13 +146,17 @@ class _Stack:
         if surf_live and S["r1s"].shape[0] != B:
             raise RuntimeError("gradients through a batch-broadcast surface branch are not supported; expand `s` to the batch")
         x7, x6, x5, x4, x3, x2, x1 = S["x7"], S["x6"], S["x5"], S["x4"], S["x3"], S["x2"], S["x1"]
-        d7 = ops.conv_backward_data(sp["conv6"], d_pre6, Wt("conv6"), hw(x7), mask=x7, mask_mode=MASK_POS)
-        wgrad("conv6", x7, d_pre6)
+        gdt = _Stack.grad_dtype(net)
+        in_hw = hw(S["packed"]) if S.get("packed") is not None else hw(S["x"])
+        d7 = ops.conv_backward_data(sp["conv6"], d_pre6_packed if d_pre6_packed is not None else d_pre6, Wt("conv6"), hw(x7), mask=x7,
+                                    mask_mode=MASK_POS, out_dtype=gdt)
+        if d_pre6 is not None:
+            wgrad("conv6", x7, d_pre6)
         d6 = ops.conv_backward_data(sp["transConv2"], d7, Wt("transConv2"), hw(x6), mask=x6, mask_mode=MASK_POS)
         wgrad("transConv2", x6, d7)
         d5 = ops.conv_backward_data(sp["transConv1"], d6, Wt("transConv1"), hw(x5), mask=x5, mask_mode=MASK_POS)
         wgrad("transConv1", x5, d6)
-        d4s = torch.empty_like(x4) if surf_live else None
+        d4s = torch.empty_like(x4, dtype=gdt) if surf_live else None
         d4 = ops.conv_backward_data(sp["conv5"], d5, Wt("conv5"), hw(x4), mask=x4, mask_mode=MASK_POS,
                                     mask2=S["r4s"] if surf_live else None, out2=d4s)
         wgrad("conv5", x4, d5)
@@ -147,8 +172,9 @@ class _Stack:
         wgrad("skipConv2", x1, d6)
         dx = None
         if need_dx:
-            dx = ops.conv_backward_data(sp["conv1"], d1, Wt("conv1"), hw(S["x"]))
-        wgrad("conv1", S["x"], d1)
+            dx = ops.conv_backward_data(sp["conv1"], d1, Wt("conv1"), in_hw, out_dtype=torch.float32)
+        if S["x"] is not None:
+            wgrad("conv1", S["x"], d1)
         dsurf = None
         if surf_live:
             r3s, r2s, r1s = S["r3s"], S["r2s"], S["r1s"]
@@ -160,8 +186,9 @@ class _Stack:
             wgrad("conv2_s", r1s, d2s)
             if surf_grad_channels is not None:
                 lo, hi = surf_grad_channels
-                dsurf = ops.conv_backward_data(sp["conv1_s"], d1s, Wt("conv1_s")[:, lo:hi], hw(S["surf"]))
-            wgrad("conv1_s", S["surf"], d1s)
+                dsurf = ops.conv_backward_data(sp["conv1_s"], d1s, Wt("conv1_s")[:, lo:hi], in_hw, out_dtype=torch.float32)
+            if S["surf"] is not None:
+                wgrad("conv1_s", S["surf"], d1s)
         dskip = None
         skip_params = pg is not None and "skipConv1.4.weight" in pg
         if S.get("skip_own", False) and (need_dskip or skip_params):
@@ -211,18 +238,37 @@ class _StackFn(torch.autograd.Function):
         pg = None
         if any(pneed):
             pg = {n: torch.zeros_like(p, dtype=torch.float32) for (n, p), need in zip(net.named_parameters(), pneed) if need}
-        d_pre6 = ops.select_cotangent(ops._f32c(dout), None, None, S["out"], MASK_OPEN01, torch.empty_like(S["out"]))
+        dout = ops._f32c(dout)
+        d_pre6 = ops.select_cotangent(dout, None, None, S["out"], MASK_OPEN01, torch.empty_like(S["out"]))
+        packed = None
+        if _Stack.act_dtype(net) != torch.float32:
+            Bq, _, Hq, Wq = dout.shape
+            packed = torch.empty((Bq, 16, Hq, Wq), dtype=_Stack.grad_dtype(net), device=dout.device, memory_format=torch.channels_last)
+            ops.select_cotangent_packed(dout, None, None, S["out"], MASK_OPEN01, packed)
         cs = S["surf"].shape[1] if (S["surf"] is not None and ctx.surf_given) else 0
         with torch.no_grad():
             dx, dsurf, dskip = _Stack.backward(net, S, d_pre6, need_dx=need_x, surf_grad_channels=(0, cs) if (need_surf and cs) else None,
-                                               need_dskip=need_skip, param_grads=pg)
+                                               need_dskip=need_skip, param_grads=pg, d_pre6_packed=packed)
         ctx.S = None
         pgr = tuple((pg.get(n) if pg is not None else None) for n in names)
         return (None, dx, dsurf, dskip, None) + pgr
 
 
+def set_precision(model: nn.Module, precision: str) -> nn.Module:
+    """'fp32': exact CUDA-core convolutions, fp32 NCHW activations (1e-5 parity mode).
+    'bf16': tcgen05 tensor-core convolutions, bf16 NHWC activations and gradients, fp32 accumulation.
+    'fp16': the same kernels with fp16 forward activations (3 more mantissa bits) and bf16 gradients."""
+    if precision not in ("fp32", "bf16", "fp16"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
+    for m in model.modules():
+        if isinstance(m, _ConvStackNet):
+            m.precision = precision
+    return model
+
+
 class _ConvStackNet(nn.Module):
     """Common parameter container + engine access for ShadingNetSPAA and CompenNet."""
+    precision = "fp32"
 
     def _build(self, variant: str, surf_ch: int):
         self._variant = variant

@@ -7,6 +7,7 @@ tensors and the library must be built (spaa_b200.build) -- otherwise an exceptio
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -239,6 +240,29 @@ def grid_sample(img: Tensor, grid: Tensor, *, clamp01: bool = False, mask: Optio
     return out
 
 
+def grid_sample_packed(img: Tensor, grid: Tensor, dtype, *, clamp01: bool = False, mask: Optional[Tensor] = None,
+                       rough: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """3-channel warp emitted as the zero-padded 16-channel NHWC tensor [x | s | x*s | 0] (logical shape [B,16,H,W],
+    channels-last) that the tensor-core conv1 / conv1_s read."""
+    img, grid = _f32c(img), _f32c(grid)
+    B, C, Hi, Wi = img.shape
+    assert C == 3
+    H, W = grid.shape[-2:]
+    if out is None:
+        out = torch.empty((B, 16, H, W), dtype=dtype, device=img.device, memory_format=torch.channels_last)
+    lib().spaa_grid_sample_fwd_packed(_p(img), B, Hi, Wi, _p(grid), _grid_bs(grid, B), H, W, int(clamp01), _p(mask), _p(rough),
+                                      _bstride(rough, B) if rough is not None else 0, _p(out), _dt(out), _stream()); _count()
+    return out
+
+
+def select_cotangent_packed(g0: Tensor, g1: Optional[Tensor], sel: Optional[Tensor], act: Optional[Tensor], mask_mode: int, out: Tensor) -> Tensor:
+    """select_cotangent for 3-channel images, written as zero-padded 16-channel NHWC (`out`: [B,16,H,W] channels-last)."""
+    B, C, H, W = g0.shape
+    assert C == 3 and out.shape == (B, 16, H, W)
+    lib().spaa_select_cotangent_packed(_p(g0), _p(g1), _p(sel), _p(act), mask_mode, _p(out), _dt(out), B, H * W, _stream()); _count()
+    return out
+
+
 def grid_sample_bwd_input(dout: Tensor, grid: Tensor, in_hw, *, mask: Optional[Tensor] = None, dout2: Optional[Tensor] = None,
                           rough: Optional[Tensor] = None, dimg: Optional[Tensor] = None) -> Tensor:
     dout, grid = _f32c(dout), _f32c(grid)
@@ -294,12 +318,14 @@ class ConvSpec:
         return (self.cout, self.cin, self.k, self.k) if self.kind == "conv" else (self.cin, self.cout, self.k, self.k)
 
 
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
 def _dt(t: Tensor) -> int:
-    if t.dtype == torch.float32:
-        return 0
-    if t.dtype == torch.bfloat16:
-        return 1
-    raise TypeError(f"unsupported activation dtype {t.dtype}")
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported activation dtype {t.dtype}") from None
 
 
 def _act_strides(t: Tensor) -> Tuple[int, int, int]:
@@ -321,7 +347,7 @@ def _fill_desc(d: ConvDesc, x: Tensor, out: Tensor, add: Optional[Tensor], mask:
         assert add.dtype == out.dtype and add.shape[1:] == out.shape[1:]
         d.add_bs, d.add_ps, d.add_cs = _act_strides(add)
     if mask is not None:
-        assert mask.dtype == out.dtype and mask.shape[1:] == out.shape[1:]
+        assert mask.shape[1:] == out.shape[1:]      # dtype may differ between 16-bit types (tensor-core path: sign test only)
         d.mask_bs, d.mask_ps, d.mask_cs = _act_strides(mask)
 
 
@@ -339,26 +365,45 @@ def invalidate_packed_weights() -> None:
     _packed_cache.clear()
 
 
-def _tc_weights(d: ConvDesc, w: Tensor) -> Tensor:
-    key = (w.data_ptr(), w._version, tuple(w.shape), tuple(w.stride()), d.flip, d.w_cis, d.w_cos, d.KH, d.Cin, d.Cout)
-    t = _packed_cache.get(key)
-    if t is None:
-        L = lib()
-        t = torch.empty(L.spaa_conv_tc_packed_elems(ctypes.byref(d)), dtype=torch.bfloat16, device=w.device)
-        L.spaa_conv_tc_pack_weights(ctypes.byref(d), _p(w), _p(t), _stream()); _count()
+def _tc_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int) -> Tensor:
+    """Packed 16-bit copy of a layer's weights for the tensor-core kernel, cached per parameter tensor.  The entry holds a
+    weak reference to the parameter (the base of `w` when `w` is a channel slice): a different tensor that happens to be
+    allocated at the same address after the first one was freed can never hit a stale entry, and in-place updates are
+    caught by the version counter."""
+    base = w._base if w._base is not None else w
+    key = (id(base), w.data_ptr(), tuple(w.shape), tuple(w.stride()), d.flip, d.w_cis, d.w_cos, d.KH, d.Cin, d.Cout, d.in_dtype, cin_real, cin_off)
+    hit = _packed_cache.get(key)
+    if hit is not None and hit[0]() is base and hit[1] == base._version:
+        return hit[2]
+    L = lib()
+    t = torch.empty(L.spaa_conv_tc_packed_elems(ctypes.byref(d)), dtype=torch.int16, device=w.device)
+    L.spaa_conv_tc_pack_weights(ctypes.byref(d), _p(w), cin_real, cin_off, _p(t), _stream()); _count()
+    if len(_packed_cache) > 512:
+        for k in [k for k, v in _packed_cache.items() if v[0]() is None]:
+            del _packed_cache[k]
         if len(_packed_cache) > 512:
             _packed_cache.clear()
-        _packed_cache[key] = t
+    _packed_cache[key] = (weakref.ref(base), base._version, t)
     return t
 
 
-def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, out2) -> None:
+def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, out2, cin_real: Optional[int] = None, cin_off: int = 0) -> None:
     L = lib()
-    use_tc = (TC_ENABLED and d.in_dtype == 1 and d.out_dtype == 1 and (d.epi_flags & ~EPI_RELU) == 0
-              and L.spaa_conv_tc_supported(ctypes.byref(d)) == 1)
+    planar = d.out_dtype == 0
+    allowed = EPI_RELU | (EPI_CLAMP_MAX1 if planar else 0)
+    use_tc = (TC_ENABLED and d.in_dtype in (1, 2) and (d.epi_flags & ~allowed) == 0 and (mask is None or d.mask_mode == MASK_POS)
+              and not (planar and (mask is not None or mask2 is not None)) and L.spaa_conv_tc_supported(ctypes.byref(d)) == 1)
+    padded = cin_real is not None and cin_real != d.Cin
+    if not use_tc:
+        if padded:
+            raise RuntimeError("zero-padded channel inputs are only implemented on the tensor-core path")
+        for m in (mask, mask2):
+            if m is not None and m.dtype != out.dtype:
+                raise RuntimeError("the CUDA-core conv path needs masks of the output's dtype")
     with _Probe(kind + ("_tc" if use_tc else ""), spec):
         if use_tc:
-            L.spaa_conv_tc_fwd(ctypes.byref(d), _p(x), _p(_tc_weights(d, w)), _p(b), _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream())
+            wp = _tc_weights(d, w, cin_real if cin_real is not None else d.Cin, cin_off)
+            L.spaa_conv_tc_fwd(ctypes.byref(d), _p(x), _p(wp), _p(b), _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream())
         else:
             L.spaa_conv_fwd(ctypes.byref(d), _p(x), _p(w), _p(b), _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream())
     _count()
@@ -366,21 +411,23 @@ def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, o
 
 def _new_act(shape, dtype, device) -> Tensor:
     """Activation buffer: bf16 tensors are NHWC (channels-last) so the tensor-core kernels can TMA them; fp32 stays NCHW."""
-    if dtype == torch.bfloat16:
+    if dtype in (torch.bfloat16, torch.float16):
         return torch.empty(shape, dtype=dtype, device=device, memory_format=torch.channels_last)
     return torch.empty(shape, dtype=dtype, device=device)
 
 
 def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, out: Optional[Tensor] = None,
-                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None) -> Tensor:
-    """Forward of nn.Conv2d / nn.ConvTranspose2d with the fused epilogue `epi` (bias, residual add, activation, clamp)."""
+                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None, cin_offset: int = 0) -> Tensor:
+    """Forward of nn.Conv2d / nn.ConvTranspose2d with the fused epilogue `epi` (bias, residual add, activation, clamp).
+    `x` may carry more channels than spec.cin (a zero-padded 16-channel NHWC tensor): the layer then reads channels
+    [cin_offset, cin_offset + spec.cin) (tensor-core path only)."""
     _need_cuda(x, w)
     B, _, H, W = x.shape
     Ho, Wo = spec.out_hw(H, W)
     if out is None:
         out = _new_act((B, spec.cout, Ho, Wo), out_dtype or x.dtype, x.device)
     d = ConvDesc()
-    d.Cin, d.Cout, d.KH, d.KW = spec.cin, spec.cout, spec.k, spec.k
+    d.Cin, d.Cout, d.KH, d.KW = x.shape[1], spec.cout, spec.k, spec.k
     s0, s1 = _w_strides(w, spec.k)
     d.w_ts = 1
     if spec.kind == "conv":
@@ -392,7 +439,7 @@ def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, o
         d.w_cis, d.w_cos = s0, s1
     d.epi_flags, d.mask_mode = epi, MASK_NONE
     _fill_desc(d, x, out, add, None)
-    _launch_conv("fwd", spec, d, x, w, b, add, None, None, out, None)
+    _launch_conv("fwd", spec, d, x, w, b, add, None, None, out, None, cin_real=spec.cin, cin_off=cin_offset)
     return out
 
 
@@ -407,7 +454,7 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
     if out is None:
         out = _new_act((B, cin, in_hw[0], in_hw[1]), out_dtype or dy.dtype, dy.device)
     d = ConvDesc()
-    d.Cin, d.Cout, d.KH, d.KW = spec.cout, cin, spec.k, spec.k
+    d.Cin, d.Cout, d.KH, d.KW = dy.shape[1], cin, spec.k, spec.k      # dy may be zero-padded to 16 channels (tensor-core path)
     s0, s1 = _w_strides(w, spec.k)
     d.w_ts = 1
     if spec.kind == "conv":       # dX = gather conv of dY with flipped taps, up = stride
@@ -423,7 +470,7 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
         assert out2 is not None and out2.stride() == out.stride()
         if mask is not None:
             assert mask2.stride()[1:] == mask.stride()[1:]
-    _launch_conv("bwd_data", spec, d, dy, w, None, add, mask, mask2, out, out2)
+    _launch_conv("bwd_data", spec, d, dy, w, None, add, mask, mask2, out, out2, cin_real=spec.cout, cin_off=0)
     return out
 
 

@@ -17,7 +17,7 @@ import torch
 from . import ops
 from .classifier import device_logits
 from .img_proc import expand_4d
-from .models import PCNet, _Stack
+from .models import PCNet, _Stack, set_precision
 from .ops import MASK_OPEN01
 from .perc_al import PerC_AL
 
@@ -41,8 +41,10 @@ class SpaaAttack:
     """State + one-iteration stepper of the SPAA loop (projector_based_attack.py:212-339).  `spaa()` below is
     `SpaaAttack(...)`, `iters` x `step()`, `result()`; bench.py drives `step()` directly to time exactly K iterations."""
 
-    def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info):
+    def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None):
         device = torch.device(device)
+        if precision is not None:
+            set_precision(_unwrap(pcnet), precision)
         if device.type != "cuda":
             raise RuntimeError("spaa_b200.spaa runs on CUDA devices only (no CPU fallback)")
         self.device, self.classifier, self.targeted, self.d_thr = device, classifier, bool(targeted), float(d_thr)
@@ -85,6 +87,10 @@ class SpaaAttack:
                 self.mask = net.flat_mask()
                 self.skip_acts = _Stack.skip1(sh, scene)                      # skipConv1(cam_scene): loop constant
                 self.xw = torch.empty(B, 3, H, W, device=device)
+                self.tc = _Stack.act_dtype(sh) != torch.float32          # tensor-core path: packed 16-channel boundary tensors
+                if self.tc:
+                    self.packed = torch.empty((B, 16, H, W), dtype=_Stack.act_dtype(sh), device=device, memory_format=torch.channels_last)
+                    self.d_pre6_packed = torch.empty((B, 16, H, W), dtype=_Stack.grad_dtype(sh), device=device, memory_format=torch.channels_last)
                 if net.use_rough:
                     self.sfeat = torch.empty(B, 6, H, W, device=device)
                     self.sfeat[:, :3] = scene
@@ -102,7 +108,10 @@ class SpaaAttack:
         # ---- forward ---------------------------------------------------------------------------------
         if self.fused:
             with torch.no_grad():
-                if net.use_rough:
+                if self.tc:
+                    ops.grid_sample_packed(self.prj_adv, self.grid, self.packed.dtype, clamp01=True, mask=self.mask, rough=scene, out=self.packed)
+                    cam, S = _Stack.forward(self.sh, None, None, None, surf_acts=self.surf_acts, skip_acts=self.skip_acts, packed=self.packed)
+                elif net.use_rough:
                     ops.grid_sample(self.prj_adv, self.grid, clamp01=True, mask=self.mask, out=self.xw, rough=scene, out2=self.sfeat[:, 3:])
                     cam, S = _Stack.forward(self.sh, self.xw, self.sfeat, None, skip_acts=self.skip_acts)
                     S["surf_own"] = True
@@ -124,12 +133,16 @@ class SpaaAttack:
                          self.w_camde, self.d_thr, self.p_thresh, self.use_col, self.succ, self.better, self.col_loss, self.best_col)
         # ---- one backward with the per-sample selected cotangent ---------------------------------------
         if self.fused:
-            ops.select_cotangent(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6)
+            d_pre6 = d_pk = None
+            if self.tc:
+                d_pk = ops.select_cotangent_packed(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6_packed)
+            else:
+                d_pre6 = ops.select_cotangent(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6)
             with torch.no_grad():
                 if net.use_rough:
-                    dxw, dsf, _ = _Stack.backward(self.sh, S, self.d_pre6, need_dx=True, surf_grad_channels=(3, 6))
+                    dxw, dsf, _ = _Stack.backward(self.sh, S, d_pre6, need_dx=True, surf_grad_channels=(3, 6), d_pre6_packed=d_pk)
                 else:
-                    dxw, dsf, _ = _Stack.backward(self.sh, S, self.d_pre6, need_dx=True)
+                    dxw, dsf, _ = _Stack.backward(self.sh, S, d_pre6, need_dx=True, d_pre6_packed=d_pk)
                 ops.grid_sample_bwd_input(dxw, self.grid, self.prj_hw, mask=self.mask, dout2=dsf, rough=scene if dsf is not None else None,
                                           dimg=self.dprj)
             S = None
@@ -154,9 +167,11 @@ class SpaaAttack:
 
 
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,
-         iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None):
-    """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1))."""
-    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info)
+         iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None,
+         precision: Optional[str] = None):
+    """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1)).
+    Keyword-only extras (reference defaults): iters=50; precision None (keep the model's), 'fp32' or 'bf16'."""
+    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision)
     for it in range(iters):
         if forced_prj is not None:
             A.prj_adv.copy_(forced_prj[it])

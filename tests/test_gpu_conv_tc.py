@@ -16,8 +16,8 @@ CASES = [
 ]
 
 
-def cl(t):
-    return t.to("cuda:0").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+def cl(t, dtype=torch.bfloat16):
+    return t.to("cuda:0").to(dtype).contiguous(memory_format=torch.channels_last)
 
 
 def close(a, b, atol, rtol, what):
@@ -30,6 +30,7 @@ def close(a, b, atol, rtol, what):
 def test_tc_conv_forward_and_backward_data(case):
     from spaa_b200 import ops
     from spaa_b200._lib import lib
+    ops.invalidate_packed_weights()
     kind, cin, cout, k, stride, pad, outpad, H, W = case
     B = 3
     spec = ops.ConvSpec(kind, cin, cout, k, stride, pad, outpad)
@@ -66,3 +67,72 @@ def test_tc_conv_forward_and_backward_data(case):
     close(dx.float(), refb, 2e-2 * scale, 1e-2, "backward data")
     close(out2.float(), refb * (m2.double() > 0), 2e-2 * scale, 1e-2, "backward data out2")
     assert lib().spaa_conv_tc_supported is not None and ops.launch_count() > n0
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_tc_padded_input_and_planar_output(dtype):
+    """The boundary layers on the tensor-core path: 3/6-channel images zero-padded to 16 NHWC channels (conv1, conv1_s,
+    backward of conv6) and fp32 NCHW outputs with <= 32 channels (conv6 forward, backward of conv1)."""
+    from spaa_b200 import ops
+    B, H, W = 2, 20, 36
+    dev = "cuda:0"
+    # conv1_s-like: 6 input channels living at channels 3..8 of a padded 16-channel tensor, stride 2
+    spec = ops.ConvSpec("conv", 6, 32, 3, 2, 1)
+    x16 = torch.zeros(B, 16, H, W)
+    x16[:, 3:9] = synth.randn(11, "pd.x", (B, 6, H, W))
+    x16 = x16.to(dtype)
+    w = synth.randn(12, "pd.w", spec.weight_shape(), 0.2)
+    b = synth.randn(13, "pd.b", (32,), 0.1)
+    ref = F.relu(F.conv2d(x16[:, 3:9].double(), w.to(dtype).double(), b.double(), 2, 1))
+    got = ops.conv_forward(spec, cl(x16, dtype), w.to(dev), b.to(dev), epi=ops.EPI_RELU, cin_offset=3)
+    assert got.dtype == dtype
+    close(got.float(), ref, 2e-2, 1e-2, "padded-input forward")
+    # conv6-like: 32 -> 3 channels, fp32 NCHW output, residual + ReLU + clamp
+    spec6 = ops.ConvSpec("conv", 32, 3, 3, 1, 1)
+    x7 = synth.randn(14, "pd.x7", (B, 32, H, W)).to(dtype)
+    w6 = synth.randn(15, "pd.w6", spec6.weight_shape(), 0.1)
+    b6 = synth.randn(16, "pd.b6", (3,), 0.1)
+    res = synth.randn(17, "pd.res", (1, 3, H, W), 0.3)
+    ref6 = torch.clamp(F.relu(F.conv2d(x7.double(), w6.to(dtype).double(), b6.double(), 1, 1) + res.double()), max=1)
+    probe = ops.set_probe(lambda kind, sp: kind.endswith("_tc"))
+    got6 = ops.conv_forward(spec6, cl(x7, dtype), w6.to(dev), b6.to(dev), add=res.to(dev), epi=ops.EPI_RELU | ops.EPI_CLAMP_MAX1, out_dtype=torch.float32)
+    assert got6.dtype == torch.float32 and got6.is_contiguous() and len(probe["events"]) == 1
+    close(got6, ref6, 2e-3, 1e-3, "planar forward")
+    # backward of conv6: padded 16-channel cotangent (3 real) -> 32-channel gradient with ReLU mask of an fp16/bf16 activation
+    cot = torch.zeros(B, 16, H, W)
+    cot[:, :3] = synth.randn(18, "pd.cot", (B, 3, H, W))
+    cotq = cot.to(torch.bfloat16)
+    xd = x7.double().requires_grad_(True)
+    pre = F.conv2d(xd, w6.to(torch.bfloat16).double(), None, 1, 1)
+    gx, = torch.autograd.grad((pre * cotq[:, :3].double()).sum(), xd)
+    d7 = ops.conv_backward_data(spec6, cl(cotq), w6.to(dev), (H, W), mask=cl(x7, dtype), mask_mode=ops.MASK_POS, out_dtype=torch.bfloat16)
+    close(d7.float(), gx * (x7.double() > 0), 3e-2, 1e-2, "padded backward of conv6")
+    # backward of conv1: 32-channel bf16 gradient -> 3-channel fp32 NCHW (up = 2 parity phases)
+    spec1 = ops.ConvSpec("conv", 3, 32, 3, 2, 1)
+    w1 = synth.randn(19, "pd.w1", spec1.weight_shape(), 0.2)
+    d1 = synth.randn(20, "pd.d1", (B, 32, H // 2, W // 2)).to(torch.bfloat16)
+    xin = torch.zeros(B, 3, H, W, dtype=torch.double, requires_grad=True)
+    pre1 = F.conv2d(xin, w1.to(torch.bfloat16).double(), None, 2, 1)
+    gx1, = torch.autograd.grad((pre1 * d1.double()).sum(), xin)
+    dx = ops.conv_backward_data(spec1, cl(d1), w1.to(dev), (H, W), out_dtype=torch.float32)
+    ops.set_probe(None)
+    assert dx.dtype == torch.float32 and len(probe["events"]) == 3
+    close(dx, gx1, 2e-3 * max(1.0, gx1.abs().max().item()), 1e-3, "planar backward of conv1")
+    # packed warp output and packed cotangent
+    img = synth.rand(21, "pd.img", (B, 3, 24, 24))
+    grid = (synth.rand(22, "pd.grid", (2, H, W)) * 2.2 - 1.1).to(dev)
+    mask = (synth.rand(23, "pd.mask", (H * W,)) > 0.2).float().to(dev)
+    s = synth.rand(24, "pd.s", (1, 3, H, W)).to(dev)
+    xw = ops.grid_sample(img.to(dev), grid, clamp01=True, mask=mask)
+    pk = ops.grid_sample_packed(img.to(dev), grid, dtype, clamp01=True, mask=mask, rough=s)
+    want = torch.zeros(B, 16, H, W, device=dev)
+    want[:, :3], want[:, 3:6], want[:, 6:9] = xw, s, xw * s
+    close(pk.float(), want.to(dtype).float(), 1e-2, 0, "packed warp")
+    g0, g1 = synth.randn(25, "pd.g0", (B, 3, H, W)).to(dev), synth.randn(26, "pd.g1", (B, 3, H, W)).to(dev)
+    sel = torch.tensor([1, 0], dtype=torch.uint8, device=dev)
+    act = (synth.rand(27, "pd.act", (B, 3, H, W)) * 1.4 - 0.2).clamp(0, 1).to(dev)
+    outp = torch.empty((B, 16, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    ops.select_cotangent_packed(g0, g1, sel, act, ops.MASK_OPEN01, outp)
+    wantc = torch.zeros(B, 16, H, W, device=dev)
+    wantc[:, :3] = ops.select_cotangent(g0, g1, sel, act, ops.MASK_OPEN01, torch.empty_like(g0))
+    close(outp.float(), wantc.to(torch.bfloat16).float(), 0, 0, "packed cotangent")

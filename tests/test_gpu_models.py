@@ -398,3 +398,95 @@ def test_evaluate_model_and_metrics():
     assert abs(rmse - (mse * 3) ** 0.5) < 2e-2 and abs(ssim - O.ssim_index(ref, cam).item()) < 1e-3
     d = ut.calc_img_dists(ref.to(dev()), cam.to(dev()))
     assert abs(d[5] - O.mean_delta_e(ref, cam)) < 1e-3 and abs(d[3] - torch.norm(ref - cam, dim=1).mean().item() * 255) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bf16 tensor-core path (BASELINE.json: within 2e-3 max-abs of the fp32 result, identical classifier top-1)
+# ---------------------------------------------------------------------------------------------------------
+
+# Measured on B200 (this fixture): PCNet output max-abs error 2.9e-3 with pure bf16 storage, 3.4e-4 with fp16 forward
+# activations -- so 'fp16' is the mode that meets BASELINE.json's 2e-3 bar and the one bench.py reports; 'bf16' is kept
+# as the wider-range variant and bounded at 4e-3.
+MODES = [("bf16", 4e-3, 0.12, 0.95), ("fp16", 2e-3, 0.04, 0.98)]      # precision, output tol, gradient rel-F tol, min update cosine
+
+
+@pytest.mark.parametrize("precision,tol,gtol,mincos", MODES)
+def test_pcnet_16bit_tensor_core_path_vs_reference(golden, precision, tol, gtol, mincos):
+    """Tensor-core path vs the fp32 reference fixture (tests/golden/models.npz)."""
+    from spaa_b200 import models, ops
+    g = golden("models")
+    P = synth.pcnet_params(31, CAM_HW)
+    m = models.set_precision(make_pcnet(P, CAM_HW), precision)
+    prj = synth.textured(32, "pc.prj", (2, 3, *PRJ_HW)).to(dev()).requires_grad_(True)
+    scene = synth.textured(33, "pc.s", (1, 3, *CAM_HW)).expand(2, -1, -1, -1).to(dev())
+    probe = ops.set_probe(lambda kind, spec: kind.endswith("_tc"))
+    y = m(prj, scene)
+    cot = synth.randn(34, "pc.cot", y.shape).to(dev())
+    (y * cot).sum().backward()
+    n_tc = len(probe["events"])
+    ops.set_probe(None)
+    assert n_tc >= 20, f"only {n_tc} launches went through the tcgen05 kernel"
+    err = (y.detach().cpu() - T(g["pcnet_y"])).abs()
+    print(f"16bit[{precision}] PCNet output: max abs err {err.max().item():.2e}, mean {err.mean().item():.2e}")
+    assert err.max().item() <= tol, err.max().item()
+    gref = T(g["pcnet_gprj"]).double()
+    got = prj.grad.cpu().double()
+    rel = ((got - gref).norm() / gref.norm()).item()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(1), gref.flatten(1), dim=1)
+    print(f"16bit[{precision}] d/dprj: relative Frobenius error {rel:.3e}, per-sample cosine {cos.tolist()}")
+    assert rel <= gtol and (cos >= mincos).all(), (rel, cos.tolist())
+
+
+@pytest.mark.parametrize("precision,tol,gtol,mincos", MODES)
+def test_spaa_16bit_teacher_forced_outcome(golden, precision, tol, gtol, mincos):
+    """Tensor-core PCNet inside the attack loop: per-iteration camera image close to the fp32 oracle, identical top-1."""
+    from spaa_b200 import models, projector_based_attack as pba
+    P, m, scene = _spaa_setup()
+    targets = [int(v) for v in golden("spaa")["targets"]]
+    tiny_cpu = synth.TinyClassifier(1)
+    otrace, trace = [], []
+    O.spaa_attack(lambda x, s: O.pcnet(P, x, s, CAM_HW), lambda im: O.classify(tiny_cpu, im, (24, 24), (20, 20)), targets, True, scene,
+                  2.0, "camdE_caml2", prj_hw=PRJ_HW, iters=8, trace=otrace)
+    pba.spaa(m, TinyClf(1), LABELS, targets, True, scene, 2.0, "camdE_caml2", dev(), SETUP, iters=8, trace=trace,
+             forced_prj=[t["prj_in"].to(dev()) for t in otrace], precision=precision)
+    models.set_precision(m, "fp32")
+    worst = 1.0
+    for i, (a, o) in enumerate(zip(trace, otrace)):
+        close(a["cam"], o["cam"], tol, 0, f"it{i} cam ({precision})")
+        assert torch.equal(a["logits"].argmax(1).cpu(), o["logits"].argmax(1)), f"it{i} top-1"
+        step_ref = o["prj_out"] - o["prj_in"]
+        same = (a["use_col"].cpu() == o["use_col"])
+        cos = torch.nn.functional.cosine_similarity((a["prj_out"] - a["prj_in"]).cpu().flatten(1), step_ref.flatten(1), dim=1)
+        worst = min(worst, cos[same].min().item())
+        assert (cos[same] > mincos).all(), f"it{i} update direction cos {cos.tolist()}"
+    print(f"16bit[{precision}] teacher-forced: worst update-direction cosine {worst:.4f}")
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_spaa_16bit_free_running_success_rate(precision):
+    """BASELINE.json: the 16-bit path must agree with fp32 on attack success within +-1 image per 100 (free-running, so
+    individual trajectories may fork at a threshold; the COUNT is the invariant) and classify every attacked image
+    (the returned cam_infer_best) to the same top-1 as the fp32 classifier does on the same image."""
+    from spaa_b200 import models, projector_based_attack as pba
+    P, m, scene = _spaa_setup()
+    targets = [(37 * i + 11) % 1000 for i in range(100)]
+    tiny_cpu, clf = synth.TinyClassifier(1), TinyClf(1)
+    iters, d_thr = 40, 2.0
+    ocam, oprj = O.spaa_attack(lambda x, s: O.pcnet(P, x, s, CAM_HW), lambda im: O.classify(tiny_cpu, im, (24, 24), (20, 20)), targets, True,
+                               scene, d_thr, "camdE_caml2", prj_hw=PRJ_HW, iters=iters)
+    cam, prj = pba.spaa(m, clf, LABELS, targets, True, scene, d_thr, "camdE_caml2", dev(), SETUP, iters=iters, precision=precision)
+    models.set_precision(m, "fp32")
+    tgt = torch.tensor(targets)
+
+    def success(cam_best):
+        lg = O.classify(tiny_cpu, cam_best.cpu(), (24, 24), (20, 20))[0].detach()
+        return lg.argmax(1) == tgt, lg
+    s_ref, _ = success(ocam)
+    s_got, lg_cpu = success(cam)
+    print(f"16bit[{precision}] free-running: fp32 oracle {int(s_ref.sum())}/100 successful attacks, tensor-core path {int(s_got.sum())}/100")
+    assert 0 < int(s_ref.sum()) < 100, "fixture must produce a mix of successes and failures"
+    assert abs(int(s_got.sum()) - int(s_ref.sum())) <= 1
+    # top-1 of every attacked image: device classifier on our output == fp32 CPU classifier on the same image
+    from spaa_b200.classifier import device_logits
+    lg_dev = device_logits(clf, cam, (24, 24))
+    assert torch.equal(lg_dev.argmax(1).cpu(), lg_cpu.argmax(1))

@@ -12,7 +12,7 @@ def main():
     which = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = [(r["Kernel Name"], float(r["Metric Value"])) for r in csv.DictReader(lines)]
-    marks = [i for i, (k, _) in enumerate(rows) if "grid_sample_fwd_kernel" in k]
+    marks = [i for i, (k, _) in enumerate(rows) if "grid_sample_fwd_kernel" in k or "grid_sample_fwd_packed_kernel" in k]
     a, b = marks[which], marks[which + 1]
     it = rows[a:b]
     tot = sum(v for _, v in it)
