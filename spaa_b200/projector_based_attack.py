@@ -203,3 +203,38 @@ def perc_al_compennet_pp(compennet_pp, classifier, imgnet_labels, target_idx, ta
     with torch.no_grad():
         prj_adv_best = compennet_pp(cam_infer_best, cam_scene_batch)
     return cam_infer_best, prj_adv_best
+
+
+# ------------------------------------------------------------------------------------------------------------
+# multi-GPU: attack jobs are independent -- shard them over ranks, no data-path collective
+# ------------------------------------------------------------------------------------------------------------
+
+def shard_jobs(jobs, rank: Optional[int] = None, world: Optional[int] = None):
+    """Round-robin share of an attack sweep (the (setup, classifier, stealth_loss, d_thr, targets) tuples that
+    run_projector_based_attack iterates serially, projector_based_attack.py:83-129) for this rank.
+    Returns [(global job index, job), ...]."""
+    import torch.distributed as dist
+    if rank is None or world is None:
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+    return [(i, jobs[i]) for i in range(rank, len(jobs), world)]
+
+
+def gather_job_results(local_results, n_jobs: int):
+    """local_results: [(global job index, picklable result), ...] from this rank's shard.  Every rank gets the list of all
+    n_jobs results in job order (host-side all_gather_object: bookkeeping, not on the data path)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        parts = [local_results]
+    else:
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, local_results)
+    out = [None] * n_jobs
+    for part in parts:
+        for i, r in part:
+            if out[i] is not None:
+                raise RuntimeError(f"attack job {i} was executed by more than one rank")
+            out[i] = r
+    missing = [i for i, r in enumerate(out) if r is None]
+    if missing:
+        raise RuntimeError(f"attack jobs {missing} were not executed by any rank")
+    return out
