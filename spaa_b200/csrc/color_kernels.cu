@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(kThreads) color_loss_kernel(const float* __res
         const float r = __ldg(cb + p), g = __ldg(cb + HW + p), bl = __ldg(cb + 2 * HW + p);
         const float L0 = __ldg(rl + p), A0 = __ldg(rl + HW + p), B0 = __ldg(rl + 2 * HW + p);
         float L, A, Bv;
-        color::rgb_to_lab<float>(r, g, bl, L, A, Bv);
+        color::LabJac<float> J;
+        if (WithGrad) color::rgb_to_lab_jac<float>(r, g, bl, L, A, Bv, J);
+        else color::rgb_to_lab<float>(r, g, bl, L, A, Bv);
         float gc[3], gr[3];
         float de;
         if (cam_is_lab2) de = color::de2000<float, WithGrad>(L0, A0, B0, L, A, Bv, gr, gc);
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kThreads) color_loss_kernel(const float* __res
         if (WithGrad) {
             const float w = c_de * (de_weighting ? de : 1.f);
             float gr_, gg_, gb_;
-            color::rgb_to_lab_bwd<float>(r, g, bl, w * gc[0], w * gc[1], w * gc[2], gr_, gg_, gb_);
+            color::lab_jac_bwd<float>(J, w * gc[0], w * gc[1], w * gc[2], gr_, gg_, gb_);
             const float inv = nrm > 0.f ? c_l2 / nrm : 0.f;   // torch.norm sub-gradient 0 at 0
             gb[p] = gr_ + inv * dr;
             gb[HW + p] = gg_ + inv * dg;

@@ -24,23 +24,57 @@ template <typename R> SPAA_HD R rpow(R x, R p) { return pow(x, p); }
 #if defined(__CUDACC__)
 template <> SPAA_HD float rpow<float>(float x, float p) { return powf(x, p); }
 #endif
+// Integer powers by multiplication (at least as accurate as pow(); the reference's `x ** 7.`, :135-143,163) and the cube
+// root by cbrt (1 ulp): a precise powf costs ~150 instructions, and the fused loss kernel would otherwise issue 17 of them
+// per pixel and be instruction-bound at 3% of its HBM roofline.
+template <typename R> SPAA_HD void pow67(R x, R& x6, R& x7) { const R x2 = x * x, x3 = x2 * x; x6 = x3 * x3; x7 = x6 * x; }
+// Division used in the REVERSE pass only: MUFU.RCP-based (2 ulp) on the device instead of the ~12-instruction IEEE
+// sequence with its slow-path branch -- the fused loss kernel has ~35 of them per pixel.  Forward values keep IEEE
+// division (they are compared with the reference at 1e-5); gradients carry a relative tolerance of 1e-4.
+template <typename R> SPAA_HD R fdiv(R a, R b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(R) == 4) return (R)__fdividef((float)a, (float)b);
+    else return a / b;
+#else
+    return a / b;
+#endif
+}
+template <typename R> SPAA_HD R rcbrt(R x) { return cbrt(x); }               // float argument -> cbrtf on host and device
+template <typename R> SPAA_HD void rsincos(R x, R& sn, R& cs) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(R) == 4) sincosf((float)x, (float*)&sn, (float*)&cs);       // one range reduction for both
+    else sincos((double)x, (double*)&sn, (double*)&cs);
+#else
+    sn = sin(x); cs = cos(x);
+#endif
+}
 
-// ---- sRGB channel -> 100 * linear  (differential_color_functions.py:16-20) ----------------------------
+// ---- sRGB channel -> 100 * linear, value and derivative  (differential_color_functions.py:16-20) -------
+// y^1.4 of the derivative is y^2.4 / y: one powf serves both.
+template <typename R> SPAA_HD void srgb_lin100_vg(R c, R& v, R& g) {
+    if (c > R(0.0405)) {
+        const R y = (c + R(0.055)) / R(1.055);
+        const R p = rpow(y, R(2.4));
+        v = R(100) * p;
+        g = R(100.0 * 2.4 / 1.055) * fdiv(p, y);
+    } else {
+        v = R(100) * (c / R(12.92));
+        g = R(100) / R(12.92);
+    }
+}
 template <typename R> SPAA_HD R srgb_lin100(R c) {
     return c > R(0.0405) ? R(100) * rpow((c + R(0.055)) / R(1.055), R(2.4)) : R(100) * (c / R(12.92));
 }
-template <typename R> SPAA_HD R srgb_lin100_grad(R c) {
-    return c > R(0.0405) ? R(100) * (R(2.4) * rpow((c + R(0.055)) / R(1.055), R(1.4))) / R(1.055) : R(100) / R(12.92);
-}
 
-// ---- Lab f()  (:27-36): exact zero -> 0 with zero slope ----------------------------------------------
+// ---- Lab f()  (:27-36), value and derivative: exact zero -> 0 with zero slope -------------------------
+template <typename R> SPAA_HD void lab_f_vg(R t, R& f, R& g) {
+    if (t == R(0)) { f = R(0); g = R(0); return; }
+    if (t > R(0.008856)) { f = rcbrt(t); g = fdiv(R(1.0 / 3.0), f * f); }      // d t^(1/3) = t^(-2/3) / 3
+    else { f = R(7.787) * t + R(16.0 / 116.0); g = R(7.787); }
+}
 template <typename R> SPAA_HD R lab_f(R t) {
     if (t == R(0)) return R(0);
-    return t > R(0.008856) ? rpow(t, R(1.0 / 3.0)) : R(7.787) * t + R(16.0 / 116.0);
-}
-template <typename R> SPAA_HD R lab_f_grad(R t) {
-    if (t == R(0)) return R(0);
-    return t > R(0.008856) ? R(1.0 / 3.0) * rpow(t, R(1.0 / 3.0 - 1.0)) : R(7.787);
+    return t > R(0.008856) ? rcbrt(t) : R(7.787) * t + R(16.0 / 116.0);
 }
 
 template <typename R> struct White {
@@ -59,21 +93,36 @@ template <typename R> SPAA_HD void rgb_to_lab(R r, R g, R b, R& L, R& A, R& B) {
     B = R(200) * (fy - fz);
 }
 
-// reverse mode of rgb_to_lab: (dL,dA,dB) -> (dr,dg,db)
-template <typename R> SPAA_HD void rgb_to_lab_bwd(R r, R g, R b, R dL, R dA, R dB, R& dr, R& dg, R& db) {
-    const R lr = srgb_lin100(r), lg = srgb_lin100(g), lb = srgb_lin100(b);
+// Forward that keeps the six local derivatives the reverse pass needs (no transcendental is evaluated twice).
+template <typename R> struct LabJac { R gr, gg, gb, jx, jy, jz; };     // d lin/d c per channel; f'(t)/white per axis
+template <typename R> SPAA_HD void rgb_to_lab_jac(R r, R g, R b, R& L, R& A, R& B, LabJac<R>& J) {
+    R lr, lg, lb;
+    srgb_lin100_vg(r, lr, J.gr); srgb_lin100_vg(g, lg, J.gg); srgb_lin100_vg(b, lb, J.gb);
     const R X = R(0.4124) * lr + R(0.3576) * lg + R(0.1805) * lb;
     const R Y = R(0.2126) * lr + R(0.7152) * lg + R(0.0722) * lb;
     const R Z = R(0.0193) * lr + R(0.1192) * lg + R(0.9504) * lb;
-    const R dfx = R(500) * dA;
-    const R dfy = R(116) * dL - R(500) * dA + R(200) * dB;
-    const R dfz = -R(200) * dB;
-    const R dX = dfx * lab_f_grad(X / White<R>::xn) / White<R>::xn;
-    const R dY = dfy * lab_f_grad(Y / White<R>::yn) / White<R>::yn;
-    const R dZ = dfz * lab_f_grad(Z / White<R>::zn) / White<R>::zn;
-    dr = (R(0.4124) * dX + R(0.2126) * dY + R(0.0193) * dZ) * srgb_lin100_grad(r);
-    dg = (R(0.3576) * dX + R(0.7152) * dY + R(0.1192) * dZ) * srgb_lin100_grad(g);
-    db = (R(0.1805) * dX + R(0.0722) * dY + R(0.9504) * dZ) * srgb_lin100_grad(b);
+    R fx, fy, fz;
+    lab_f_vg(X / White<R>::xn, fx, J.jx); lab_f_vg(Y / White<R>::yn, fy, J.jy); lab_f_vg(Z / White<R>::zn, fz, J.jz);
+    J.jx = J.jx * R(1.0 / 95.0489); J.jy = J.jy * R(1.0 / 100.0); J.jz = J.jz * R(1.0 / 108.8840);
+    L = R(116) * fy - R(16);
+    A = R(500) * (fx - fy);
+    B = R(200) * (fy - fz);
+}
+template <typename R> SPAA_HD void lab_jac_bwd(const LabJac<R>& J, R dL, R dA, R dB, R& dr, R& dg, R& db) {
+    const R dX = (R(500) * dA) * J.jx;
+    const R dY = (R(116) * dL - R(500) * dA + R(200) * dB) * J.jy;
+    const R dZ = (-R(200) * dB) * J.jz;
+    dr = (R(0.4124) * dX + R(0.2126) * dY + R(0.0193) * dZ) * J.gr;
+    dg = (R(0.3576) * dX + R(0.7152) * dY + R(0.1192) * dZ) * J.gg;
+    db = (R(0.1805) * dX + R(0.0722) * dY + R(0.9504) * dZ) * J.gb;
+}
+
+// reverse mode of rgb_to_lab: (dL,dA,dB) -> (dr,dg,db)
+template <typename R> SPAA_HD void rgb_to_lab_bwd(R r, R g, R b, R dL, R dA, R dB, R& dr, R& dg, R& db) {
+    R L, A, B;
+    LabJac<R> J;
+    rgb_to_lab_jac(r, g, b, L, A, B, J);
+    lab_jac_bwd(J, dL, dA, dB, dr, dg, db);
 }
 
 // hue in degrees, [0,360)  (:73-81).  After the neutral nudge the arguments are never both zero.
@@ -94,7 +143,8 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     const R C1 = sqrt(A1 * A1 + B1 * B1);
     const R C2 = sqrt(A2 * A2 + B2 * B2);
     const R cbar = (C1 + C2) * R(0.5);
-    const R c7 = rpow(cbar, R(7));
+    R c6, c7;
+    pow67(cbar, c6, c7);
     const R u = c7 / (c7 + P25_7);
     const R su = sqrt(u);
     const R G = R(0.5) * (R(1) - su);
@@ -112,7 +162,8 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     if (nz) dhp = (fabs(dh) <= R(180)) ? dh : (dh > R(180) ? dh - R(360) : dh + R(360));
     const R sq12 = sqrt(c1p * c2p);
     const R half_ang = K<R>::rad * dhp * R(0.5);
-    const R sn = sin(half_ang);
+    R sn, cs_half;
+    rsincos(half_ang, sn, cs_half);
     const R dHp = on ? R(2) * sq12 * sn : R(0);
     const R Lbar = (L1 + L2) * R(0.5);
     const R cpbar = (c1p + c2p) * R(0.5);
@@ -125,11 +176,15 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     }
     const R ang1 = K<R>::rad * (hbar - R(39)), ang2 = K<R>::rad * (R(2) * hbar);
     const R ang3 = K<R>::rad * (R(3) * hbar + R(6)), ang4 = K<R>::rad * (R(4) * hbar - R(63));
-    const R T = R(1) - R(0.17) * cos(ang1) + R(0.24) * cos(ang2) + R(0.32) * cos(ang3) - R(0.2) * cos(ang4);
+    R s1, k1, s2, k2, s3, k3, s4, k4;
+    if (WithGrad) { rsincos(ang1, s1, k1); rsincos(ang2, s2, k2); rsincos(ang3, s3, k3); rsincos(ang4, s4, k4); }
+    else { k1 = cos(ang1); k2 = cos(ang2); k3 = cos(ang3); k4 = cos(ang4); s1 = s2 = s3 = s4 = R(0); }
+    const R T = R(1) - R(0.17) * k1 + R(0.24) * k2 + R(0.32) * k3 - R(0.2) * k4;
     const R hq = (hbar - R(275)) / R(25);
     const R ex = exp(-(hq * hq));
     const R dtheta = R(30) * ex;
-    const R cp7 = rpow(cpbar, R(7));
+    R cp6, cp7;
+    pow67(cpbar, cp6, cp7);
     const R v = cp7 / (cp7 + P25_7);
     const R rC = sqrt(v);
     const R Lm = Lbar - R(50);
@@ -139,7 +194,8 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     const R sC = R(1) + R(0.045) * cpbar;
     const R sH = R(1) + R(0.015) * cpbar * T;
     const R ang5 = K<R>::rad * (R(2) * dtheta);
-    const R s5 = sin(ang5);
+    R s5, k5;
+    if (WithGrad) rsincos(ang5, s5, k5); else { s5 = sin(ang5); k5 = R(0); }
     const R rT = R(-2) * rC * s5;
     const R tl = dLp / sL, tc = dCp / sC, th = dHp / sH;
     const R sq = on ? (tl * tl + tc * tc + th * th + rT * tc * th) : (tl * tl);
@@ -150,7 +206,8 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     // ------------------------------- reverse mode ---------------------------------------------------
     R gL1 = 0, gA1 = 0, gB1 = 0, gL2 = 0, gA2 = 0, gB2 = 0;
     if (pos) {
-        const R dsq = R(0.5) / res;
+        const R dsq = fdiv(R(0.5), res);
+        const R isL = fdiv(R(1), sL), isC = fdiv(R(1), sC), isH = fdiv(R(1), sH);
         // sq = tl^2 + on*(tc^2 + th^2 + rT*tc*th)
         const R d_tl = dsq * R(2) * tl;
         R d_tc = 0, d_th = 0, d_rT = 0;
@@ -160,33 +217,33 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
             d_rT = dsq * tc * th;
         }
         // tl = dLp/sL ; tc = dCp/sC ; th = dHp/sH
-        const R d_dLp = d_tl / sL;
-        R d_sL = -d_tl * tl / sL;
-        const R d_dCp = d_tc / sC;
-        R d_sC = -d_tc * tc / sC;
-        const R d_dHp = d_th / sH;
-        R d_sH = -d_th * th / sH;
+        const R d_dLp = d_tl * isL;
+        R d_sL = -d_tl * tl * isL;
+        const R d_dCp = d_tc * isC;
+        R d_sC = -d_tc * tc * isC;
+        const R d_dHp = d_th * isH;
+        R d_sH = -d_th * th * isH;
         // rT = -2 rC sin(rad*2*dtheta)
         const R d_rC = d_rT * R(-2) * s5;
-        const R d_dtheta = d_rT * R(-2) * rC * cos(ang5) * K<R>::rad * R(2);
+        const R d_dtheta = d_rT * R(-2) * rC * k5 * K<R>::rad * R(2);
         // sH = 1 + 0.015 cpbar T ; sC = 1 + 0.045 cpbar
         R d_cpbar = d_sH * R(0.015) * T + d_sC * R(0.045);
         const R d_T = d_sH * R(0.015) * cpbar;
         // sL = 1 + 0.015 q / sqrt(20+q), q = (Lbar-50)^2
-        const R d_q = d_sL * R(0.015) * (R(1) / sq20 - R(0.5) * q / (sq20 * (R(20) + q)));
+        const R isq20 = fdiv(R(1), sq20);
+        const R d_q = d_sL * R(0.015) * (isq20 - R(0.5) * q * isq20 * isq20 * isq20);      // 1/(sq20*(20+q)) = 1/sq20^3
         const R d_Lbar = d_q * R(2) * Lm;
         // rC = sqrt(v), v = cp7/(cp7+25^7), cp7 = cpbar^7
         {
-            const R d_v = d_rC * R(0.5) / rC;
+            const R d_v = fdiv(d_rC * R(0.5), rC);
             const R den = cp7 + P25_7;
-            const R d_cp7 = d_v * P25_7 / (den * den);
-            d_cpbar += d_cp7 * R(7) * rpow(cpbar, R(6));
+            const R d_cp7 = fdiv(d_v * P25_7, den * den);
+            d_cpbar += d_cp7 * R(7) * cp6;
         }
         // dtheta = 30 exp(-hq^2), hq = (hbar-275)/25
-        R d_hbar = d_dtheta * R(30) * ex * (R(-2) * hq) / R(25);
+        R d_hbar = d_dtheta * R(30) * ex * (R(-2) * hq) * R(1.0 / 25.0);
         // T
-        d_hbar += d_T * K<R>::rad * (R(0.17) * sin(ang1) - R(0.24) * R(2) * sin(ang2) - R(0.32) * R(3) * sin(ang3) +
-                                      R(0.2) * R(4) * sin(ang4));
+        d_hbar += d_T * K<R>::rad * (R(0.17) * s1 - R(0.24) * R(2) * s2 - R(0.32) * R(3) * s3 + R(0.2) * R(4) * s4);
         // hbar = 0.5*(h1p+h2p (+-360)) when nz
         R d_h1p = 0, d_h2p = 0;
         if (nz) { d_h1p += R(0.5) * d_hbar; d_h2p += R(0.5) * d_hbar; }
@@ -196,8 +253,8 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
         // dHp = on * 2 sqrt(c1p c2p) sin(rad*dhp/2)
         if (on) {
             const R d_sq12 = d_dHp * R(2) * sn;
-            const R d_dhp = d_dHp * R(2) * sq12 * cos(half_ang) * K<R>::rad * R(0.5);
-            const R d_prod = d_sq12 * R(0.5) / sq12;
+            const R d_dhp = d_dHp * R(2) * sq12 * cs_half * K<R>::rad * R(0.5);
+            const R d_prod = fdiv(d_sq12 * R(0.5), sq12);
             d_c1p += d_prod * c2p;
             d_c2p += d_prod * c1p;
             if (nz) { d_h2p += d_dhp; d_h1p -= d_dhp; }
@@ -208,31 +265,35 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
         // h1p = hue(B1, a1p) unless neutral: d atan2(y,x): dy = x/(x^2+y^2), dx = -y/(x^2+y^2); degrees
         R d_a1p = 0, d_a2p = 0;
         if (!n1) {
-            const R den = a1p * a1p + B1 * B1;
-            gB1 += d_h1p * K<R>::deg * a1p / den;
-            d_a1p += d_h1p * K<R>::deg * (-B1) / den;
+            const R k = fdiv(d_h1p * K<R>::deg, a1p * a1p + B1 * B1);
+            gB1 += k * a1p;
+            d_a1p += k * (-B1);
         }
         if (!n2) {
-            const R den = a2p * a2p + B2 * B2;
-            gB2 += d_h2p * K<R>::deg * a2p / den;
-            d_a2p += d_h2p * K<R>::deg * (-B2) / den;
+            const R k = fdiv(d_h2p * K<R>::deg, a2p * a2p + B2 * B2);
+            gB2 += k * a2p;
+            d_a2p += k * (-B2);
         }
         // c1p = sqrt(a1p^2 + B1^2)
-        d_a1p += d_c1p * a1p / c1p; gB1 += d_c1p * B1 / c1p;
-        d_a2p += d_c2p * a2p / c2p; gB2 += d_c2p * B2 / c2p;
+        {
+            const R k1 = fdiv(d_c1p, c1p), k2 = fdiv(d_c2p, c2p);
+            d_a1p += k1 * a1p; gB1 += k1 * B1;
+            d_a2p += k2 * a2p; gB2 += k2 * B2;
+        }
         // a1p = (1+G) A1
         gA1 += d_a1p * (R(1) + G); gA2 += d_a2p * (R(1) + G);
         const R d_G = d_a1p * A1 + d_a2p * A2;
         // G = 0.5 (1 - sqrt(u)), u = c7/(c7+25^7), c7 = cbar^7, cbar = (C1+C2)/2
         {
             const R d_su = R(-0.5) * d_G;
-            const R d_u = d_su * R(0.5) / su;
+            const R d_u = fdiv(d_su * R(0.5), su);
             const R den = c7 + P25_7;
-            const R d_c7 = d_u * P25_7 / (den * den);
-            const R d_cbar = d_c7 * R(7) * rpow(cbar, R(6));
+            const R d_c7 = fdiv(d_u * P25_7, den * den);
+            const R d_cbar = d_c7 * R(7) * c6;
             const R d_C = R(0.5) * d_cbar;
-            gA1 += d_C * A1 / C1; gB1 += d_C * B1 / C1;
-            gA2 += d_C * A2 / C2; gB2 += d_C * B2 / C2;
+            const R k1 = fdiv(d_C, C1), k2 = fdiv(d_C, C2);
+            gA1 += k1 * A1; gB1 += k1 * B1;
+            gA2 += k2 * A2; gB2 += k2 * B2;
         }
     }
     g1[0] = gL1; g1[1] = gA1; g1[2] = gB1;

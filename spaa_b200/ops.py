@@ -38,7 +38,7 @@ def set_probe(match=None):
 
 class _Probe:
     def __init__(self, kind, spec):
-        self.on = _probe is not None and _probe["match"](kind, spec)
+        self.on = _probe is not None and _probe["match"](kind, spec) and not torch.cuda.is_current_stream_capturing()
 
     def __enter__(self):
         if self.on:

@@ -10,12 +10,14 @@ Loop constants the reference recomputes every iteration (sampling grid, skipConv
 """
 from __future__ import annotations
 
+import collections
+import weakref
 from typing import List, Optional
 
 import torch
 
 from . import ops
-from .classifier import device_logits
+from .classifier import device_logits, use_channels_last
 from .img_proc import expand_4d
 from .models import PCNet, _Stack, set_precision
 from .ops import MASK_OPEN01
@@ -26,11 +28,11 @@ def _unwrap(m):
     return m.module if isinstance(m, torch.nn.DataParallel) else m
 
 
-def _adv_grad(classifier, cam, cp_sz, target, targeted):
+def _adv_grad(classifier, cam, cp_sz, target, targeted, channels_last: bool = False):
     """logits (detached) and d(-+ sum_b logit[b, target_b]) / d cam through the external classifier."""
     leaf = cam.detach().requires_grad_(True)
     with torch.enable_grad():
-        logits = device_logits(classifier, leaf, cp_sz)
+        logits = device_logits(classifier, leaf, cp_sz, channels_last)
         sel = logits.gather(1, target.view(-1, 1)).sum()
         loss = -sel if targeted else sel
         g, = torch.autograd.grad(loss, leaf)
@@ -41,7 +43,12 @@ class SpaaAttack:
     """State + one-iteration stepper of the SPAA loop (projector_based_attack.py:212-339).  `spaa()` below is
     `SpaaAttack(...)`, `iters` x `step()`, `result()`; bench.py drives `step()` directly to time exactly K iterations."""
 
-    def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None):
+    def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
+                 graph: Optional[bool] = None):
+        """graph: replay one captured CUDA graph per iteration (default: on for the fused PCNet path).  An iteration is a fixed
+        sequence of ~80 of our launches + ~300 cuDNN/ATen launches of the external classifier with no host decision in
+        between, so after two eager iterations (which fill the packed-weight / workspace caches) the third is captured and
+        every later step() is a single cudaGraphLaunch."""
         device = torch.device(device)
         if precision is not None:
             set_precision(_unwrap(pcnet), precision)
@@ -51,7 +58,7 @@ class SpaaAttack:
         self.B = B = len(target_idx)
         self.cp_sz = setup_info["classifier_crop_sz"]
         self.prj_hw = prj_hw = tuple(setup_info["prj_im_sz"])
-        self.scene = scene = ops._f32c(expand_4d(cam_scene).to(device))
+        self.scene = scene = ops._f32c(expand_4d(cam_scene).to(device)).clone()      # own copy: reset() overwrites it in place
         if scene.shape[0] != 1:
             raise ValueError("cam_scene must be a single image (3xHxW or 1x3xHxW)")
         H, W = scene.shape[2:]
@@ -101,9 +108,71 @@ class SpaaAttack:
                         t if t.dim() == 4 else t.unsqueeze(0) for t in (sh.res1_s, sh.res2_s, sh.res3_s, sh.res4_s))
         self.scene_b = scene.expand(B, -1, -1, -1)
         self.cam = self.logits = None
+        self.clf_cl = use_channels_last(classifier) if device.type == "cuda" else False
+        self.use_graph = self.fused if graph is None else (bool(graph) and self.fused)
+        self._graph, self._n_eager = None, 0
 
     def step(self):
         """One iteration of the loop body (:265-328)."""
+        if self._graph is not None:
+            self._graph.replay()
+            ops._count(self._graph_launches)
+            return
+        if self.use_graph and self._n_eager >= 2 and not torch.cuda.is_current_stream_capturing():
+            self._capture()
+            self._graph.replay()
+            return
+        self._step_eager()
+        self._n_eager += 1
+
+    def _capture(self):
+        """Record one iteration into a CUDA graph.  Manual capture_begin/capture_end on a side stream instead of the
+        `torch.cuda.graph` context: that context empties the caching allocator first, which turns every capture into seconds
+        of cudaFree/cudaMalloc of the multi-GB activation cache (measured 47 ms .. 3 s)."""
+        # every tensor whose address is baked into the graph must outlive it: the packed 16-bit weights live in a cache
+        self._keepalive = [v[2] for v in ops._packed_cache.values()]
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        n0 = ops.launch_count()
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            try:
+                self._step_eager()                  # records the launches only; the caller's replay executes this iteration
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph_launches = ops.launch_count() - n0      # our kernels per replay (the counter ran during capture)
+        self._graph = g
+
+    def reset(self, cam_scene, target_idx):
+        """Start a new attack job (new scene / targets, same shapes and configuration) on this engine: every buffer whose
+        address the captured graph holds is refreshed IN PLACE, so the graph is reused (no re-capture)."""
+        scene = ops._f32c(expand_4d(cam_scene).to(self.device))
+        if scene.shape != self.scene.shape or len(target_idx) != self.B:
+            raise ValueError("reset() needs the scene shape and batch size the engine was built for")
+        with torch.no_grad():
+            self.scene.copy_(scene)
+            self.target.copy_(torch.as_tensor(list(target_idx), dtype=torch.int64))
+            self.prj_adv.copy_(self.gray)
+            self.prj_best.copy_(self.gray)
+            self.cam_best.copy_(self.scene.expand(self.B, -1, -1, -1))
+            self.best_col.fill_(1e6)
+            for t in (self.use_col, self.succ, self.better):
+                t.zero_()
+            self.ref_lab.copy_(ops.rgb2lab(self.scene))
+            if self.fused:
+                for dst, src in zip(self.skip_acts, _Stack.skip1(self.sh, self.scene)):
+                    dst.copy_(src)
+                if self.sfeat is not None:
+                    self.sfeat[:, :3] = self.scene
+                elif self.sh.res1_s is None:
+                    for dst, src in zip(self.surf_acts, _Stack.surface_branch(self.sh, self.scene)):
+                        dst.copy_(src)
+        self.cam = self.logits = None
+        return self
+
+    def _step_eager(self):
         net, scene = self.net, self.scene
         # ---- forward ---------------------------------------------------------------------------------
         if self.fused:
@@ -124,7 +193,7 @@ class SpaaAttack:
                 cam_g = self.pcnet(torch.clamp(prj_leaf, 0, 1), self.scene_b)
             cam = cam_g.detach()
         # ---- losses, masks ---------------------------------------------------------------------------
-        logits, g_adv = _adv_grad(self.classifier, cam, self.cp_sz, self.target, self.targeted)
+        logits, g_adv = _adv_grad(self.classifier, cam, self.cp_sz, self.target, self.targeted, self.clf_cl)
         ops.color_loss(cam, scene, self.ref_lab, cam_is_lab2=False, de_weighting=False, c_de=self.w_camde / self.hw_cam,
                        c_l2=self.w_caml2 / self.hw_cam, stats=self.stats, grad=self.g_col)
         if self.w_prjl2:
@@ -166,12 +235,54 @@ class SpaaAttack:
         return self.cam_best, torch.clamp(self.prj_best, 0, 1)                 # :337-339
 
 
+_ENGINES: "collections.OrderedDict" = collections.OrderedDict()
+_MAX_ENGINES = 2
+
+
+def _state_version(module) -> int:
+    return sum(int(t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
+                  graph: Optional[bool] = None) -> SpaaAttack:
+    """A SpaaAttack for this job.  Sweeps call spaa() many times with the same model, classifier, batch size and loss
+    configuration (run_projector_based_attack, projector_based_attack.py:83-129): the engine -- its buffers and its captured
+    CUDA graph -- is kept (LRU of 2) and only reset() for the new scene / targets.  A model whose parameters changed in
+    between (version counters) gets a new engine."""
+    net = _unwrap(pcnet)
+    if not isinstance(net, PCNet) or graph is False:
+        return SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph)
+    if precision is not None:
+        set_precision(net, precision)
+    scene_shape = tuple(expand_4d(cam_scene).shape)
+    key = (id(net), _state_version(net), id(getattr(classifier, "model", classifier)), len(target_idx), bool(targeted), stealth_loss, float(d_thr),
+           tuple(setup_info["classifier_crop_sz"]), tuple(setup_info["prj_im_sz"]), float(setup_info["prj_brightness"]), scene_shape,
+           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32))
+    hit = _ENGINES.get(key)
+    if hit is not None and hit[0]() is net and hit[1]() is getattr(classifier, "model", classifier):
+        _ENGINES.move_to_end(key)
+        return hit[2].reset(cam_scene, target_idx)
+    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, graph=graph)
+    try:
+        _ENGINES[key] = (weakref.ref(net), weakref.ref(getattr(classifier, "model", classifier)), A)
+    except TypeError:               # classifier object without weak-reference support: do not cache
+        return A
+    while len(_ENGINES) > _MAX_ENGINES:
+        _ENGINES.popitem(last=False)
+    return A
+
+
+def clear_engines() -> None:
+    _ENGINES.clear()
+
+
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,
          iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None,
-         precision: Optional[str] = None):
+         precision: Optional[str] = None, graph: Optional[bool] = None):
     """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1)).
-    Keyword-only extras (reference defaults): iters=50; precision None (keep the model's), 'fp32' or 'bf16'."""
-    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision)
+    Keyword-only extras (reference defaults): iters=50; precision None (keep the model's), 'fp32', 'fp16' or 'bf16';
+    graph None (CUDA-graph replay of the iteration when the fused PCNet path is used), True or False."""
+    A = attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph)
     for it in range(iters):
         if forced_prj is not None:
             A.prj_adv.copy_(forced_prj[it])
@@ -186,7 +297,8 @@ def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_
             v = min(7 if targeted else 0, A.B - 1)                             # :240 (guarded: the reference indexes v=7 blindly)
             print(f"adv_loss_sel_logit = {A.logits[v, A.target[v]].item():<9.4f} | col_loss = {A.col_loss[v].item():.4f} | "
                   f"succ = {bool(A.succ[v].item())}")
-    return A.result()
+    cam_best, prj_best = A.result()
+    return cam_best.clone(), prj_best                                          # the engine's buffers are reused by the next job
 
 
 def perc_al_compennet_pp(compennet_pp, classifier, imgnet_labels, target_idx, targeted, cam_scene, d_thr, device, setup_info, *,

@@ -4,7 +4,7 @@
 #include <cmath>
 #include <cstdint>
 using std::sqrt; using std::pow; using std::atan2; using std::fabs; using std::sin; using std::cos; using std::exp;
-using std::log; using std::floor;
+using std::log; using std::floor; using std::cbrt;
 #include "../../spaa_b200/csrc/color_math.cuh"
 #include "../../spaa_b200/csrc/warp_math.cuh"
 
