@@ -25,6 +25,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 
 using namespace spaa;
 
@@ -104,6 +105,11 @@ SPAA_D void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 SPAA_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+SPAA_D bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 SPAA_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 SPAA_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 SPAA_D void umma_commit(uint64_t* bar) {
@@ -129,6 +135,19 @@ SPAA_D void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+SPAA_D void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+SPAA_D void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, rows of ROW_BYTES (= swizzle width), 8-row groups ROW_BYTES*8 apart.
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -376,6 +395,349 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ===============================================================================================================
+// v2: halo-tile kernel.  Measured on B200 (profiles/r1_tc_v1_ncu.md): v1 above is bound by the rate at which TMA delivers
+// smem rows (~3 clk per <=128 B row, ~43 B/clk/SM): it fetches one shifted 8x16 box per filter TAP, so every input pixel is
+// pulled from L2 nine times (conv6: 1.9 GB of L2->SM traffic for 158 MB of HBM reads).  Here the A operand of an output tile
+// is fetched ONCE per 64-channel chunk as a (TH+KH-1) x (TW+KW-1) halo box; the MMA of tap (r,s) reads the same smem through
+// a descriptor whose start address is shifted by (r*halo_w + s) rows.  That needs every 8-row group of the MMA (one core
+// matrix row group) to be 8 CONSECUTIVE x-pixels, hence the 16 x 8 output tile (row m = j*8 + i) and SBO = halo_w rows.
+//   stride-2 convolutions: four input-parity planes (TMA element stride 2), a tap reads plane (r&1, s&1) at shift (r>>1, s>>1);
+//   up-sampling (transposed / backward-of-strided) convolutions: the four output-parity phases share one input halo tile
+//   and accumulate into four TMEM column ranges.
+// Weights: all taps of small layers stay resident in shared memory for the life of the CTA; large layers stream one
+// (tap, 64-channel) slice per stage through a second ring.
+// ===============================================================================================================
+constexpr int HTH = 16, HTW = 8;                   // output tile: 16 rows x 8 columns = 128 MMA rows
+
+struct HTap { int16_t shift; int8_t slot; int8_t plane; };
+struct HPhase { int32_t ntaps, py, px, pad_; HTap taps[kMaxTaps]; };
+struct HaloParams {
+    int32_t B, Cin, Hin, Win, Cout, Hout, Wout;
+    int32_t up, stride;
+    int32_t nphases, nplanes;
+    int32_t halo_w, halo_h;            // pixels per plane box
+    int32_t org_x, org_y;              // plane origin relative to the tile origin, in plane pixels
+    int32_t tiles_x, tiles_y, total_tiles, kchunks;
+    int32_t a_plane_bytes, a_stage_bytes, a_tx_bytes, b_slice_bytes;
+    int32_t sa, sb, resident, nslots, use_base_off, ntap_total;
+    uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
+    int32_t epi_flags, out_planar;
+    int64_t add_bs, mask_bs;
+    HPhase ph[kMaxPhases];
+    const float* bias;
+    const void* add;
+    const uint16_t* mask;
+    const uint16_t* mask2;
+    void* out;
+    void* out2;
+};
+
+template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t use_base_off) {
+    constexpr uint64_t layout = ROW_BYTES == 128 ? 2 : (ROW_BYTES == 64 ? 4 : 6);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    if (use_base_off) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+    d |= layout << 61;
+    return d;
+}
+
+template <int BN, int BK, bool F16>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                                const __grid_constant__ HaloParams P) {
+    constexpr int ROWB = BK * 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int SA = P.sa, SB = P.sb;
+    uint8_t* a_ring = smem;
+    uint8_t* b_base = smem + (size_t)SA * P.a_stage_bytes;
+    const size_t b_bytes = P.resident ? (size_t)P.kchunks * P.nslots * P.b_slice_bytes : (size_t)SB * P.b_slice_bytes;
+    uint64_t* bars = (uint64_t*)(b_base + b_bytes);
+    uint64_t* a_full = bars;                       // [SA]
+    uint64_t* a_empty = a_full + 8;                // [SA]
+    uint64_t* b_full = a_empty + 8;                // [SB] (b_full[0] doubles as the "resident weights loaded" barrier)
+    uint64_t* b_empty = b_full + 8;                // [SB]
+    uint64_t* tfull = b_empty + 8;                 // [2]
+    uint64_t* tempty = tfull + 2;                  // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint32_t* s_tap = tmem_slot + 4;               // [kMaxTaps * kMaxPhases]
+    float* s_bias = (float*)(s_tap + kMaxTaps * kMaxPhases);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NPH = P.nphases;
+    for (int i = threadIdx.x; i < P.ntap_total; i += kThreads) s_tap[i] = P.tap_tab[i];
+    const uint32_t acc_cols = (uint32_t)(NPH * BN);                  // TMEM columns of one accumulator buffer
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a);
+        prefetch_tmap(&map_b);
+        for (int i = 0; i < 8; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = threadIdx.x; i < BN; i += kThreads) s_bias[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_img = P.tiles_x * P.tiles_y;
+
+    if (warp == 0) {
+        // ===================================== TMA producer ========================================
+        if (lane == 0) {
+            if (P.resident) {
+                mbar_expect_tx(b_full, (uint32_t)b_bytes);
+                for (int kc = 0; kc < P.kchunks; ++kc)
+                    for (int sl = 0; sl < P.nslots; ++sl)
+                        tma_load_2d(b_base + (size_t)(kc * P.nslots + sl) * P.b_slice_bytes, &map_b, b_full, kc * BK, sl * BN);
+            }
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                const int b = tile / per_img;
+                const int t = tile - b * per_img;
+                const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+                const int x0 = (tx * HTW + P.org_x) * P.stride, y0 = (ty * HTH + P.org_y) * P.stride;
+                for (int kc = 0; kc < P.kchunks; ++kc) {
+                    mbar_wait(a_empty + sa, pa ^ 1);
+                    uint8_t* dst = a_ring + (size_t)sa * P.a_stage_bytes;
+                    mbar_expect_tx(a_full + sa, (uint32_t)P.a_tx_bytes);
+                    for (int pl = 0; pl < P.nplanes; ++pl)
+                        tma_load_4d(dst + (size_t)pl * P.a_plane_bytes, &map_a, a_full + sa, kc * BK, x0 + (pl & 1), y0 + (pl >> 1), b);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    if (!P.resident) {
+                        for (int ph = 0; ph < NPH; ++ph)
+                            for (int tp = 0; tp < P.ph[ph].ntaps; ++tp) {
+                                mbar_wait(b_empty + sb, pb ^ 1);
+                                mbar_expect_tx(b_full + sb, (uint32_t)P.b_slice_bytes);
+                                tma_load_2d(b_base + (size_t)sb * P.b_slice_bytes, &map_b, b_full + sb, kc * BK, P.ph[ph].taps[tp].slot * BN);
+                                if (++sb == SB) { sb = 0; pb ^= 1; }
+                            }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer ==========================================
+        // ONE elected thread runs the whole loop.  The first version of this loop (every lane evaluating the waits, lane 0
+        // building both 64-bit descriptors per MMA from the tap table in the constant bank) spent ~300 clk of issue overhead
+        // per tcgen05.mma -- more than the 16..128 clk the MMA itself needs -- and was THE bottleneck of every layer
+        // (profiles/r1_tc_issue_bound.md).  Now: descriptor high words are loop constants, low words are a base plus a
+        // per-tap 16-byte-unit offset read from a small shared-memory table.
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(BM, BN, F16);
+            constexpr uint32_t layout = ROWB == 128 ? 2u : (ROWB == 64 ? 4u : 6u);
+            const uint32_t a_hi = (((uint32_t)(P.halo_w * ROWB) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+            const uint32_t b_hi = (((uint32_t)(8 * ROWB) >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+            const uint32_t a_ring_lo = smem_u32(a_ring) >> 4, b_base_lo = smem_u32(b_base) >> 4;
+            const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4, b_slice16 = (uint32_t)P.b_slice_bytes >> 4;
+            const int ntap = P.ntap_total;                   // <= kMaxTaps: each filter tap belongs to exactly one output phase
+            uint32_t taps[kMaxTaps];
+#pragma unroll
+            for (int e = 0; e < kMaxTaps; ++e) taps[e] = e < ntap ? s_tap[e] : 0u;
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int local = 0;
+            if (P.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                mbar_wait(tempty + acc, ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + (uint32_t)acc * acc_cols;
+                for (int kc = 0; kc < P.kchunks; ++kc) {
+                    mbar_wait(a_full + sa, pa);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_ring_lo + (uint32_t)sa * a_stage16;
+                    const uint32_t b_kc_lo = b_base_lo + (uint32_t)(kc * P.nslots) * b_slice16;
+#pragma unroll
+                    for (int e = 0; e < kMaxTaps; ++e) {        // tap table lives in registers (compile-time indices after unrolling)
+                        if (e < ntap) {
+                            const uint32_t te = taps[e];            // [0,16) A offset in 16 B units, [16,20) weight slot, [20,22) phase, bit 22: first tap of its phase
+                            uint32_t b_lo;
+                            if (P.resident) b_lo = b_kc_lo + ((te >> 16) & 15u) * b_slice16;
+                            else {
+                                mbar_wait(b_full + sb, pb);
+                                tc_fence_after();
+                                b_lo = b_base_lo + (uint32_t)sb * b_slice16;
+                            }
+                            const uint32_t d_tmem = d_base + ((te >> 20) & 3u) * (uint32_t)BN;
+                            const uint32_t at = a_lo + (te & 0xFFFFu);
+                            const uint32_t fresh = (kc == 0 && (te & (1u << 22))) ? 1u : 0u;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (uint64_t)(at + 2 * k), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2 * k), idesc,
+                                          (k == 0 && fresh) ? 0u : 1u);
+                            if (!P.resident) {
+                                umma_commit(b_empty + sb);
+                                if (++sb == SB) { sb = 0; pb ^= 1; }
+                            }
+                        }
+                    }
+                    umma_commit(a_empty + sa);
+                    if (kc == P.kchunks - 1) umma_commit(tfull + acc);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================== epilogue ============================================
+        // Operands that do not depend on the accumulator (residual, ReLU masks) are fetched one 32-channel chunk AHEAD of
+        // the TMEM read that needs them -- and for the first chunk of a tile before the wait for its MMAs -- so their
+        // global-memory latency is not paid once per chunk in series.
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int j = row >> 3, i = row & 7;
+        const int ef = P.epi_flags;
+        const bool has_add = P.add != nullptr, has_mask = P.mask != nullptr, has_out2 = P.out2 != nullptr;
+        struct Ops { uint4 a[4], m[4], m2[4]; };
+        int local = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
+            const int b = tile / per_img;
+            const int t = tile - b * per_img;
+            const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+            const int acc = local & 1;
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
+            bool waited = false;
+            for (int ph = 0; ph < NPH; ++ph) {
+                const int oy = (ty * HTH + j) * P.up + P.ph[ph].py, ox = (tx * HTW + i) * P.up + P.ph[ph].px;
+                const bool valid = oy < P.Hout && ox < P.Wout;
+                const int64_t pix = ((int64_t)oy * P.Wout + ox) * P.Cout;
+                const int64_t o_off = (int64_t)b * P.Hout * P.Wout * P.Cout + pix;
+                if (P.out_planar) {
+                    // fp32 NCHW planes, Cout (<= 32) real channels: conv6 forward, conv1 / conv1_s backward-data
+                    const int64_t hw = (int64_t)P.Hout * P.Wout;
+                    const int64_t p = (int64_t)oy * P.Wout + ox;
+                    float* op = (float*)P.out + (int64_t)b * P.Cout * hw + p;
+                    const float* ap = has_add ? (const float*)P.add + (int64_t)b * P.add_bs + p : nullptr;
+                    float av[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid && ap && P.Cout <= 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (k < P.Cout) av[k] = __ldg(ap + k * hw);
+                    }
+                    if (!waited) { mbar_wait(tfull + acc, (local >> 1) & 1); tc_fence_after(); waited = true; }
+                    uint32_t r[32];
+                    tmem_ld32(t_row + (uint32_t)(ph * BN), r);
+                    if (!valid) continue;
+                    if (P.Cout <= 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < P.Cout) {
+                                float y = __uint_as_float(r[k]) + s_bias[k] + av[k];
+                                if (ef & SPAA_EPI_RELU) y = fmaxf(y, 0.f);
+                                if (ef & SPAA_EPI_CLAMP_MAX1) y = fminf(y, 1.f);
+                                op[k * hw] = y;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            if (k < P.Cout) {
+                                float y = __uint_as_float(r[k]) + s_bias[k];
+                                if (ap) y += __ldg(ap + k * hw);
+                                if (ef & SPAA_EPI_RELU) y = fmaxf(y, 0.f);
+                                if (ef & SPAA_EPI_CLAMP_MAX1) y = fminf(y, 1.f);
+                                op[k * hw] = y;
+                            }
+                        }
+                    }
+                    continue;
+                }
+                auto fetch = [&](int c0, Ops& o) {
+                    if (!valid || c0 >= P.Cout) return;
+                    if (has_add) {
+                        const uint4* ap = reinterpret_cast<const uint4*>((const uint16_t*)P.add + (int64_t)b * P.add_bs + pix + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) o.a[g] = __ldg(ap + g);
+                    }
+                    if (has_mask) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask + (int64_t)b * P.mask_bs + pix + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) o.m[g] = __ldg(mp + g);
+                    }
+                    if (has_out2) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask2 + (int64_t)b * P.mask_bs + pix + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) o.m2[g] = __ldg(mp + g);
+                    }
+                };
+                Ops cur, nxt;
+                fetch(0, cur);
+                if (!waited) { mbar_wait(tfull + acc, (local >> 1) & 1); tc_fence_after(); waited = true; }
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32_nowait(t_row + (uint32_t)(ph * BN + c0), r);
+                    if (c0 + 32 < BN) fetch(c0 + 32, nxt);
+                    tmem_wait_ld();
+                    if (valid && c0 < P.Cout) {
+                        float v[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) + s_bias[c0 + k];
+                        if (has_add) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint32_t w4[4] = {cur.a[g].x, cur.a[g].y, cur.a[g].z, cur.a[g].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = unpack2<F16>(w4[e]);
+                                    v[g * 8 + e * 2] += f.x; v[g * 8 + e * 2 + 1] += f.y;
+                                }
+                            }
+                        }
+                        if (ef & SPAA_EPI_RELU) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+                        }
+                        if (has_mask) {                                  // backward of ReLU: keep the gradient where the activation was > 0
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint32_t w4[4] = {cur.m[g].x, cur.m[g].y, cur.m[g].z, cur.m[g].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    if (!pos16(w4[e] & 0xFFFFu)) v[g * 8 + e * 2] = 0.f;
+                                    if (!pos16(w4[e] >> 16)) v[g * 8 + e * 2 + 1] = 0.f;
+                                }
+                            }
+                        }
+                        uint4* op = reinterpret_cast<uint4*>((uint16_t*)P.out + o_off + c0);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 u;
+                            u.x = pack2<F16>(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack2<F16>(v[g * 8 + 2], v[g * 8 + 3]);
+                            u.z = pack2<F16>(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack2<F16>(v[g * 8 + 6], v[g * 8 + 7]);
+                            op[g] = u;
+                        }
+                        if (has_out2) {
+                            uint4* op2 = reinterpret_cast<uint4*>((uint16_t*)P.out2 + o_off + c0);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint32_t w4[4] = {cur.m2[g].x, cur.m2[g].y, cur.m2[g].z, cur.m2[g].w};
+                                uint32_t o4[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    o4[e] = pack2<F16>(pos16(w4[e] & 0xFFFFu) ? v[g * 8 + e * 2] : 0.f, pos16(w4[e] >> 16) ? v[g * 8 + e * 2 + 1] : 0.f);
+                                op2[g] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                            }
+                        }
+                    }
+                    if (c0 + 32 < BN) cur = nxt;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: fp32 parameter (any layout, by strides) -> bf16 [slot = gather tap][BN rows = cout][Cin]
 // ---------------------------------------------------------------------------------------------------------------
@@ -454,6 +816,154 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, c
     return SPAA_OK;
 }
 
+// ---- v2 host side ---------------------------------------------------------------------------------------------
+constexpr int kHaloBarBytes = (8 * 4 + 4) * 8 + 16 + kMaxTaps * kMaxPhases * 4;      // a_full/a_empty/b_full/b_empty [8] + tfull/tempty [2] + tmem slot
+
+template <int BN, int BK, bool F16>
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, size_t smem_bytes, cudaStream_t st) {
+    static size_t reserved = 0;
+    if (smem_bytes > reserved) {
+        if (cudaFuncSetAttribute(conv_halo_kernel<BN, BK, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+            set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
+            return SPAA_ERR_CUDA;
+        }
+        reserved = smem_bytes;
+    }
+    const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+    conv_halo_kernel<BN, BK, F16><<<grid, kThreads, smem_bytes, st>>>(ma, mb, P);
+    return SPAA_OK;
+}
+
+inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+// Returns SPAA_ERR_UNSUPPORTED when the halo kernel does not cover the case (the caller then uses v1).
+int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add, const void* mask, const void* mask2,
+              void* out, void* out2, cudaStream_t st, EncodeTiledFn enc) {
+    const int BN = bn_for(d->Cout);
+    const int BK = d->Cin >= 64 ? 64 : d->Cin;
+    const bool f16 = d->in_dtype == 2;
+    const int nph = d->up * d->up;
+    if (nph * BN > 256) return SPAA_ERR_UNSUPPORTED;
+    HaloParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = d->B; P.Cin = d->Cin; P.Hin = d->Hin; P.Win = d->Win; P.Cout = d->Cout; P.Hout = d->Hout; P.Wout = d->Wout;
+    P.up = d->up; P.stride = d->stride; P.nphases = nph; P.nplanes = d->stride * d->stride; P.kchunks = d->Cin / BK;
+    P.nslots = d->KH * d->KW;
+    P.epi_flags = d->epi_flags; P.out_planar = d->out_dtype == 0 ? 1 : 0;
+    P.add_bs = d->add_bs; P.mask_bs = d->mask_bs;
+    P.bias = bias; P.add = add; P.mask = (const uint16_t*)mask; P.mask2 = (const uint16_t*)mask2; P.out = out; P.out2 = out2;
+    // Measured on B200: the MMA unit applies the 128/64/32-byte swizzle to the ABSOLUTE shared-memory address bits (the same
+    // function TMA used when it wrote the box), so a start address shifted by whole rows needs NO base-offset correction;
+    // setting the descriptor's base_offset field to (addr >> 7) & 7 gives wrong results (tests/test_gpu_conv_tc.py).
+    P.use_base_off = 0;
+    // ---- tap tables: (plane, shift) of every tap; first pass finds the halo extent, second fills the tables ----
+    int qminx = 1 << 20, qmaxx = -(1 << 20), qminy = 1 << 20, qmaxy = -(1 << 20);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            P.org_x = qminx; P.org_y = qminy;
+            P.halo_w = HTW + (qmaxx - qminx); P.halo_h = HTH + (qmaxy - qminy);
+        }
+        for (int py = 0; py < d->up; ++py)
+            for (int px = 0; px < d->up; ++px) {
+                HPhase& F = P.ph[py * d->up + px];
+                if (pass == 1) { F.py = py; F.px = px; F.ntaps = 0; }
+                for (int r = 0; r < d->KH; ++r)
+                    for (int s2 = 0; s2 < d->KW; ++s2) {
+                        int qy, qx, plane = 0;
+                        if (d->up > 1) {
+                            const int vy = py + r - d->pad_h, vx = px + s2 - d->pad_w;
+                            if ((vy & 1) || (vx & 1)) continue;
+                            qy = floordiv2(vy); qx = floordiv2(vx);
+                        } else if (d->stride == 2) {
+                            const int ry = r - d->pad_h, rx = s2 - d->pad_w;
+                            const int ppy = ry & 1, ppx = rx & 1;
+                            qy = floordiv2(ry - ppy); qx = floordiv2(rx - ppx);
+                            plane = ppy * 2 + ppx;
+                        } else {
+                            qy = r - d->pad_h; qx = s2 - d->pad_w;
+                        }
+                        if (pass == 0) {
+                            qminx = qx < qminx ? qx : qminx; qmaxx = qx > qmaxx ? qx : qmaxx;
+                            qminy = qy < qminy ? qy : qminy; qmaxy = qy > qmaxy ? qy : qmaxy;
+                        } else {
+                            HTap& t = F.taps[F.ntaps++];
+                            t.shift = (int16_t)((qy - qminy) * P.halo_w + (qx - qminx));
+                            t.slot = (int8_t)(r * d->KW + s2);
+                            t.plane = (int8_t)plane;
+                        }
+                    }
+            }
+    }
+    const int rowb16 = (BK * 2) >> 4;
+    P.ntap_total = 0;
+    for (int ph = 0; ph < nph; ++ph)
+        for (int t = 0; t < P.ph[ph].ntaps; ++t) {
+            const HTap& T = P.ph[ph].taps[t];
+            const uint32_t plane16 = (uint32_t)T.plane * ((((uint32_t)(P.halo_h * P.halo_w * BK * 2) + 1023u) & ~1023u) >> 4);
+            P.tap_tab[P.ntap_total++] = (plane16 + (uint32_t)T.shift * rowb16) | ((uint32_t)T.slot << 16) | ((uint32_t)ph << 20) | (t == 0 ? (1u << 22) : 0u);
+        }
+    const int Hgrid = (d->Hout + d->up - 1) / d->up, Wgrid = (d->Wout + d->up - 1) / d->up;
+    P.tiles_y = (Hgrid + HTH - 1) / HTH; P.tiles_x = (Wgrid + HTW - 1) / HTW;
+    P.total_tiles = d->B * P.tiles_y * P.tiles_x;
+    if (P.total_tiles <= 0) { set_last_error("spaa_conv_tc_fwd: empty problem"); return SPAA_ERR_ARG; }
+    const int rowb = BK * 2;
+    P.a_tx_bytes = P.nplanes * P.halo_h * P.halo_w * rowb;
+    P.a_plane_bytes = (P.halo_h * P.halo_w * rowb + 1023) & ~1023;
+    P.a_stage_bytes = P.nplanes * P.a_plane_bytes;
+    P.b_slice_bytes = BN * rowb;
+    const int budget = 200 * 1024;
+    const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
+    P.resident = res_bytes <= 80 * 1024 ? 1 : 0;
+    int64_t bbytes;
+    if (P.resident) { bbytes = res_bytes; P.sb = 1; }
+    else {
+        P.sb = P.b_slice_bytes <= 16 * 1024 ? 6 : 4;
+        while (P.sb > 2 && (int64_t)P.sb * P.b_slice_bytes + 2 * (int64_t)P.a_stage_bytes > budget) --P.sb;
+        bbytes = (int64_t)P.sb * P.b_slice_bytes;
+    }
+    int64_t sa = (budget - bbytes) / P.a_stage_bytes;
+    if (sa < 2) return SPAA_ERR_UNSUPPORTED;
+    P.sa = (int)(sa > 6 ? 6 : sa);
+    const size_t smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + kHaloBarBytes + BN * 4 + 1024;
+
+    CUtensorMap ma, mb;
+    const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(P.halo_w * d->stride), (cuuint32_t)(P.halo_h * d->stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        CUresult r = enc(&ma, dt, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(halo input) failed with %d", (int)r); return SPAA_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->KH * d->KW * BN};
+        cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&mb, dt, 2, const_cast<void*>(wpacked), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return SPAA_ERR_CUDA; }
+    }
+    int rc = SPAA_OK;
+#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? launch_halo<BN_, BK_, true>(ma, mb, P, smem_bytes, st) : launch_halo<BN_, BK_, false>(ma, mb, P, smem_bytes, st)
+    if (BK == 64) {
+        if (BN == 32) SPAA_HALO_LAUNCH(32, 64);
+        else if (BN == 64) SPAA_HALO_LAUNCH(64, 64);
+        else if (BN == 128) SPAA_HALO_LAUNCH(128, 64);
+        else SPAA_HALO_LAUNCH(256, 64);
+    } else if (BK == 32) {
+        if (BN == 32) SPAA_HALO_LAUNCH(32, 32);
+        else SPAA_HALO_LAUNCH(64, 32);
+    } else {
+        SPAA_HALO_LAUNCH(32, 16);
+    }
+#undef SPAA_HALO_LAUNCH
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -501,6 +1011,12 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
     }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled is unavailable in this driver"); return SPAA_ERR_CUDA; }
+    static const int force_v1 = [] { const char* e = getenv("SPAA_TC_V1"); return e ? atoi(e) : 0; }();
+    if (!force_v1) {
+        const int rc2 = conv_halo(d, in, wpacked, bias, add, mask, mask2, out, out2, (cudaStream_t)stream, enc);
+        if (rc2 == SPAA_OK) { SPAA_CHECK_LAUNCH("spaa_conv_tc_fwd (halo kernel)"); return SPAA_OK; }
+        if (rc2 != SPAA_ERR_UNSUPPORTED) return rc2;
+    }
     const int BN = bn_for(d->Cout);
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
     const bool f16 = d->in_dtype == 2;
