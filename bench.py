@@ -164,6 +164,86 @@ def config_dict(n_gpus: int, precision: str):
             "parallelism": f"{n_gpus} independent attack jobs, no collective"}
 
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# training leg: PCNet training step (train_network.py:235-363), data-parallel, one NCCL all-reduce of the flat gradient bucket
+# ---------------------------------------------------------------------------------------------------------------
+TRAIN_BATCH, TRAIN_N = 24, 500
+
+
+def train_leg(dev, rank, world, steps, warmup, precision="bf16"):
+    """img/s of `train_pcnet` (batch 24 per GPU, weak scaling; 500 synthetic pairs resident in HBM) in the L1 phase (iterations
+    <= 400) and the L1+SSIM phase (> 400), timed with CUDA events around exactly `steps` optimizer steps (max over ranks)."""
+    import random
+    import torch.distributed as dist
+    import synth
+    from spaa_b200 import models, train_network as tn
+    torch.manual_seed(123 + rank)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    prj = torch.rand(TRAIN_N, 3, *PRJ_HW, device=dev, generator=g)
+    cam = torch.rand(TRAIN_N, 3, *CAM_HW, device=dev, generator=g)
+    scene = synth.textured(rank, "bench.train.scene", (1, 3, *CAM_HW)).to(dev)
+    P = synth.pcnet_params(300, CAM_HW)
+    model = models.PCNet(P["mask"], torch.nn.DataParallel(models.WarpingNet(out_size=CAM_HW)), torch.nn.DataParallel(models.ShadingNetSPAA()))
+    model.load_state_dict(P, strict=True)
+    model = models.set_precision(model.to(dev), precision)
+    out = {}
+    for phase, offset in (("l1", 0), ("l1+ssim", 401)):
+        times = []
+        for n in (max(1, warmup), steps):
+            cfg = tn.AttrDict(device=str(dev), data_root=None, model_name="PCNet", num_train=TRAIN_N, batch_size=TRAIN_BATCH, max_iters=n, lr=1e-3,
+                              lr_drop_ratio=0.2, lr_drop_rate=800, l2_reg=1e-4, plot_on=False, valid_rate=10 ** 9, dp_mode="weak", iter_offset=offset,
+                              save_checkpoint=False)
+            random.seed(123)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tn.train_pcnet(model, dict(cam_scene=scene, cam_train=cam, prj_train=prj, mask=P["mask"]), None, cfg, verbose=False)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        t = torch.tensor([times[1]], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item() / steps
+        out[phase] = {"img_per_s": TRAIN_BATCH * world / (ms / 1e3), "ms_per_step": ms}
+    return {"metric": "pcnet_train_img_per_sec", "value": out["l1+ssim"]["img_per_s"], "unit": "img/s", "phases": out, "steps": steps,
+            "batch_per_gpu": TRAIN_BATCH, "global_batch": TRAIN_BATCH * world, "scaling": "weak", "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[precision],
+            "note": "train_pcnet (3 Adam groups in one flat fp32 bucket, one NCCL all-reduce per step when N>1); " +
+                    ("bf16 activations / gradients on tcgen05 (forward, backward-data, backward-weight), fp32 master weights and accumulation; "
+                     if precision != "fp32" else "exact fp32 CUDA-core convolutions; ") + "value = L1+SSIM phase (1600 of the reference's 2000 steps)"}
+
+
+def torch_cuda_train_step_ms(dev, steps=5):
+    """The reference's training step on stock PyTorch-CUDA ops (oracle port: F.conv2d/grid_sample/SSIM via autograd, torch.optim.Adam)."""
+    import synth
+    from oracle import spaa_oracle as O
+    P = {k: v.to(dev).requires_grad_(v.dtype.is_floating_point and k not in ("mask", "warping_net.ctrl_pts")) for k, v in synth.pcnet_params(300, CAM_HW).items()}
+    params = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-4)
+    g = torch.Generator(device=dev).manual_seed(7)
+    prj = torch.rand(TRAIN_BATCH, 3, *PRJ_HW, device=dev, generator=g)
+    cam = torch.rand(TRAIN_BATCH, 3, *CAM_HW, device=dev, generator=g)
+    scene = synth.textured(0, "bench.train.scene", (1, 3, *CAM_HW)).to(dev).expand(TRAIN_BATCH, -1, -1, -1)
+
+    def step():
+        opt.zero_grad()
+        loss, _ = O.training_loss(O.pcnet(P, prj, scene, CAM_HW), cam, "l1+ssim")
+        loss.backward()
+        opt.step()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
@@ -265,6 +345,16 @@ def run_ours(args):
     h2d = scene_host.numel() * 4 + len(targets) * 8
     d2h = (out_cam.numel() + out_prj.numel()) * 4
 
+    train = None
+    if not args.skip_train:
+        from spaa_b200.projector_based_attack import clear_engines
+        clear_engines()
+        del A
+        torch.cuda.empty_cache()
+        train = train_leg(dev, rank, world, max(3, min(args.steps, 10)), 2, args.train_precision)
+        if world == 1 and not args.skip_side_legs and args.train_precision != "fp32":
+            t32 = train_leg(dev, rank, world, 3, 1, "fp32")
+            train["fp32_mode"] = {"img_per_s": t32["value"], "ms_per_step": t32["phases"]["l1+ssim"]["ms_per_step"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -286,6 +376,8 @@ def run_ours(args):
                          "traffic": None, "launches_timed": len(kern_ms), "avg_launch_ms": k_ms, "peak_source": pk["source"] + " bf16 sustained",
                          "note": "per-launch CUDA events need host-launched kernels: timed over the same K iterations re-run without graph replay"},
             "cuda_graph": not args.no_graph}
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.skip_side_legs:
         # side legs (not the headline): the exact fp32 mode of the same engine, and the reference algorithm on stock PyTorch-CUDA ops
         # (cuDNN TF32 convolutions + ~1.3k ATen kernels per iteration = what the reference executes on a GPU), same batch, same box
@@ -304,6 +396,10 @@ def run_ours(args):
                                  "note": "same engine, exact CUDA-core fp32 convolutions (the 1e-5 parity mode)"}
             models.set_precision(pcnet, args.precision)
             del A32
+        if train is not None:
+            tms = torch_cuda_train_step_ms(dev)
+            train["torch_cuda_reference"] = {"img_per_s": TRAIN_BATCH / (tms / 1e3), "ms_per_step": tms,
+                                             "note": "oracle port of the reference training step on stock PyTorch-CUDA ops (cuDNN TF32 default), batch 24, L1+SSIM"}
         sec = cpu_reference_run(BATCH, 2, 5, device=str(dev))
         line["torch_cuda_reference"] = {"value": 1.0 / sec, "unit": "it/s", "steps": 5,
                                         "note": "oracle port of projector_based_attack.py:212-339 on stock PyTorch-CUDA ops (cuDNN, allow_tf32 default), "
@@ -330,6 +426,8 @@ def main():
                     help="fp16 (default): tcgen05 convolutions, fp16 activations / bf16 gradients, fp32 accumulation -- the 16-bit mode that meets "
                          "BASELINE.json's 2e-3 bar; bf16: pure bf16 storage; fp32: exact CUDA-core convolutions (1e-5 parity mode)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
+    ap.add_argument("--skip-train", action="store_true", help="omit the PCNet training leg")
+    ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--skip-side-legs", action="store_true", help="profiling runs only: omit the fp32 and torch-CUDA side measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     args = ap.parse_args()

@@ -161,6 +161,17 @@ int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, int cin_r
                               spaa_stream_t stream);
 int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add,
                      const void* mask, const void* mask2, void* out, void* out2, spaa_stream_t stream);
+/* Tensor-core backward-weight (training): tcgen05.mma with BOTH operands MN-major (the contraction index is the pixel),
+ * fp32 accumulation in TMEM over all pixel tiles of a CTA, one atomic flush per CTA.  `d` describes the forward gather
+ * conv as for spaa_conv_bwd_weight; x (gathered operand) and dy (pointwise operand) are dense 16-bit NHWC with 16, 32, 64,
+ * 128 or 256 channels, both bf16 or both fp16 (tcgen05 kind::f16 traps on mixed operand formats); cx_real / cx_off / cy_real describe zero-padded operands (real X channels
+ * at [cx_off, cx_off + cx_real), real DY channels [0, cy_real)); dw is addressed by d->w_ts / w_cis (X channel) / w_cos
+ * (DY channel).  Replaces cudnnConvolutionBackwardFilter for models.py:18-46,223-252 under train_network.py:304-320. */
+int spaa_conv_wgrad_tc_supported(const spaa_conv_desc* d);
+int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real,
+                       spaa_stream_t stream);
+/* out[c] += sum over pixels of a dense 16-bit NHWC tensor [npix][C] (C in 8..256, power of two); dtype 1 bf16, 2 fp16 */
+int spaa_channel_sum_nhwc16(const void* x, int dtype, int64_t npix, int C, float* out, spaa_stream_t stream);
 /* out[c] += sum_{b,p} x[b,p,c]  (bias gradient; x addressed by element strides, dtype 0 fp32 / 1 bf16) */
 int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int64_t bs, int64_t ps, int64_t cs, float* out,
                      spaa_stream_t stream);

@@ -401,7 +401,7 @@ def ssim_map(a: Tensor, b: Tensor, size: int = 11) -> Tensor:
     """pytorch_ssim/__init__.py:24-51: replicate-pad, 11x11 Gaussian moments, C1=1e-4, C2=9e-4."""
     ch = a.shape[1]
     g = gauss_window(size, dtype=torch.float32)
-    win = (g[:, None] @ g[None, :]).to(a.dtype).expand(ch, 1, size, size).contiguous()
+    win = (g[:, None] @ g[None, :]).to(a.device, a.dtype).expand(ch, 1, size, size).contiguous()
     p = size // 2
     a = F.pad(a, (p, p, p, p), mode="replicate")
     b = F.pad(b, (p, p, p, p), mode="replicate")

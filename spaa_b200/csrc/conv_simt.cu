@@ -335,6 +335,63 @@ __global__ void __launch_bounds__(kThreads) bias_grad_kernel(const spaa_conv_des
     }
 }
 
+// Backward-weight (+ bias) for the 3 -> 3 channel full-resolution layers (skipConv1.*, models.py:243-247): fp32 NCHW planes, stride 1.
+// The generic kernel above wastes a 64 x 64 tile on a 3 x 3 channel block (9 ms per layer at B=24); here every thread
+// walks pixels and keeps all CO*CI*K*K partial sums (<= 81) in registers; one shuffle/shared reduction and CO*CI*K*K
+// atomics per block.  HBM traffic is the algorithmic read of x and dy (neighbour taps hit L1/L2).
+template <int K>
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const spaa_conv_desc d, const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dw, float* __restrict__ dbias) {
+    constexpr int C = 3, KK = K * K, NACC = C * C * KK + C;
+    __shared__ float red[8][NACC];
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    const int H = d.Hout, W = d.Wout, HW = H * W;
+    const int64_t total = (int64_t)d.B * HW;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(p / HW);
+        const int pix = (int)(p - (int64_t)b * HW);
+        const int oy = pix / W, ox = pix - oy * W;
+        float g[C];
+#pragma unroll
+        for (int co = 0; co < C; ++co) g[co] = co < d.Cout ? __ldg(dy + (int64_t)b * d.out_bs + (int64_t)co * d.out_cs + pix) : 0.f;
+#pragma unroll
+        for (int co = 0; co < C; ++co) acc[C * C * KK + co] += g[co];
+#pragma unroll
+        for (int r = 0; r < K; ++r)
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const int iy = oy + r - d.pad_h, ix = ox + s - d.pad_w;
+                const bool v = iy >= 0 && ix >= 0 && iy < d.Hin && ix < d.Win;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    const float xv = (v && ci < d.Cin) ? __ldg(x + (int64_t)b * d.in_bs + (int64_t)ci * d.in_cs + (int64_t)iy * d.Win + ix) : 0.f;
+#pragma unroll
+                    for (int co = 0; co < C; ++co) acc[(co * C + ci) * KK + r * K + s] = fmaf(xv, g[co], acc[(co * C + ci) * KK + r * K + s]);
+                }
+            }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[wid][i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][i];
+        if (i < C * C * KK) {
+            const int co = i / (C * KK), ci = (i / KK) % C, tap = i % KK;
+            if (co < d.Cout && ci < d.Cin) atomicAdd(dw + (int64_t)tap * d.w_ts + (int64_t)ci * d.w_cis + (int64_t)co * d.w_cos, v);
+        } else if (dbias && i - C * C * KK < d.Cout) {
+            atomicAdd(dbias + (i - C * C * KK), v);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -365,6 +422,15 @@ int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* do
     SPAA_CHECK_ARG((unsigned)d->in_dtype < 3 && (unsigned)d->out_dtype < 3, "spaa_conv_bwd_weight: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t M = (int64_t)d->B * d->Hout * d->Wout;
+    if (d->Cin <= 3 && d->Cout <= 3 && d->in_dtype == 0 && d->out_dtype == 0 && d->stride == 1 && d->in_ps == 1 && d->out_ps == 1 &&
+        d->Hin == d->Hout && d->Win == d->Wout && d->KH == d->KW && (d->KH == 1 || d->KH == 3)) {
+        int64_t blocks = (M + 255) / 256;
+        if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+        if (d->KH == 1) wgrad_small_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*d, (const float*)in, (const float*)dout, dw, dbias);
+        else wgrad_small_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(*d, (const float*)in, (const float*)dout, dw, dbias);
+        SPAA_CHECK_LAUNCH("spaa_conv_bwd_weight(small)");
+        return SPAA_OK;
+    }
     const int ci_tiles = (d->Cin + WB - 1) / WB, co_tiles = (d->Cout + WB - 1) / WB;
     const int64_t base_blocks = (int64_t)d->KH * d->KW * ci_tiles * co_tiles;
     int64_t splits = (4 * kNumSMs + base_blocks - 1) / base_blocks;      // aim for ~4 blocks per SM in total

@@ -1,0 +1,397 @@
+// tcgen05 backward-weight kernel for the convolution stacks (training only).
+//
+//   dW[tap][cx][cy] += sum_{b,oy,ox} X[b, oy*s + r - pad, ox*s + q - pad, cx] * DY[b, oy, ox, cy]
+//
+// (X = the operand the forward pass GATHERS through the filter taps, DY = the pointwise one; for nn.Conv2d X is the layer
+// input and DY the output gradient, for nn.ConvTranspose2d the roles swap -- see ops.conv_backward_weight).  Replaces
+// cudnnConvolutionBackwardFilter as reached from the autograd graph of /root/reference/src/python/models.py:18-46,223-252
+// in train_network.py:304-320.
+//
+// GEMM view: the contraction index K is the PIXEL, which is the slow (row) index of both 16-bit NHWC operands, so both MMA
+// operands are MN-major: a TMA box [pixels][64 channels] lands in shared memory as 128-byte rows = exactly the canonical
+// MN-major SWIZZLE_128B layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) of cute/atom/mma_traits_sm100.hpp (rows = K, 8-row
+// groups SBO apart, 64-channel atoms LBO apart).  D[M = 128 X-channels][N = Cy] accumulates in TMEM over ALL pixel tiles a
+// CTA owns and is added to the fp32 gradient with atomics once, at the end.
+//
+//   * pixel tile = 16 x 8 output pixels = 8 MMA K-steps of 16 pixels; X is fetched once per tile as a halo box (same scheme
+//     as conv_halo_kernel: the view of tap (r,q) is the same smem with the start address shifted by whole rows, SBO =
+//     halo_w rows; stride-2 layers use the four input-parity planes);
+//   * M = 128 rows: Cx >= 128 -> 128 channels of one tap (two 64-channel atoms, LBO = box stride);
+//                   Cx == 64  -> TWO taps per MMA (atom 1 = the other tap's view: LBO = distance of the two start addresses);
+//                   Cx <= 32  -> one tap, the remaining atoms alias shifted rows (computed, ignored);
+//   * one launch accumulates up to 512 / Cy (tap, 128-channel) pairs; ops.py issues one launch per such set.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/spaa_b200.h"
+#include <cstring>
+
+using namespace spaa;
+using namespace spaa::tc;
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int WTH = 16, WTW = 8;
+constexpr int kMaxGroups = 32;     // accumulators (tap x 128-channel chunk, or tap pair) of one layer
+constexpr int kMaxSets = 16;       // a CTA owns one set: accumulators that fit in TMEM together and share one X chunk
+
+struct WgGroup {
+    uint32_t a_off16;          // start of the A view inside a stage, 16 B units (plane offset + row shift)
+    uint32_t a_lbo16;          // distance between the 64/32/16-channel atoms of the 128 M rows, 16 B units
+    int8_t tap[8];             // filter tap of each atom (row block), -1: ignore those rows
+    int32_t cx0;               // first X channel of atom 0 (Cx >= 128: both atoms are consecutive channel blocks of one tap)
+};
+struct WgParams {
+    int32_t B, Cx, Cy, Hy, Wy;
+    int32_t stride, nplanes, halo_w, halo_h, org_x, org_y;
+    int32_t tiles_x, tiles_y, total_tiles;
+    int32_t cxb, cyb;                      // channels per X / DY box (64, 32 or 16)
+    int32_t x_boxes, y_boxes;              // boxes per plane of X loaded per stage; boxes of DY
+    int32_t nsets;
+    int16_t set_first[kMaxSets], set_count[kMaxSets], set_ch0[kMaxSets];      // accumulators / first X channel of every set
+    int32_t x_plane_bytes, x_bytes, y_box_bytes, stage_bytes, tx_bytes, nstages;
+    int32_t max_groups, n_cols;            // most accumulators in a set; TMEM columns per accumulator (= Cy)
+    int32_t atom_rows;                     // rows of D per atom (= cxb, or 64 when Cx >= 128)
+    int32_t cx_real, cx_off, cy_real;      // padded operands: real X channels sit at [cx_off, cx_off + cx_real); real DY channels [0, cy_real)
+    int32_t x_f16, y_f16;
+    int64_t w_ts, w_xs, w_ys;
+    float* dw;
+    WgGroup g[kMaxGroups];
+};
+
+SPAA_D uint64_t make_mn_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
+    return (uint64_t)(addr16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)layout << 61);
+}
+SPAA_HD uint32_t layout_for(int ch) { return ch == 64 ? 2u : (ch == 32 ? 4u : 6u); }
+
+__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                                                                    const __grid_constant__ WgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + (size_t)P.nstages * P.stage_bytes);
+    uint64_t* empty = full + 4;
+    uint64_t* tdone = empty + 4;
+    uint32_t* tmem_slot = (uint32_t*)(tdone + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTA c owns accumulator set c % nsets and every (gridDim.x / nsets)-th pixel tile: each weight receives gridDim.x / nsets
+    // partial sums instead of gridDim.x (the fp32 atomics of the flush were the dominant cost with all CTAs on all sets).
+    const int set = (int)blockIdx.x % P.nsets;
+    const int tile0 = (int)blockIdx.x / P.nsets, tile_step = ((int)gridDim.x + P.nsets - 1 - set) / P.nsets;
+    const int g0 = P.set_first[set], ngroups = P.set_count[set], x_ch0 = P.set_ch0[set];
+    const uint32_t need_cols = (uint32_t)(P.max_groups * P.n_cols);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < need_cols) tmem_cols <<= 1;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_x);
+        prefetch_tmap(&map_y);
+        for (int i = 0; i < 4; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(tdone, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int per_img = P.tiles_x * P.tiles_y;
+    const int S = P.nstages;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
+                const int b = tile / per_img;
+                const int t = tile - b * per_img;
+                const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+                mbar_wait(empty + st, ph ^ 1);
+                uint8_t* dst = smem + (size_t)st * P.stage_bytes;
+                mbar_expect_tx(full + st, (uint32_t)P.tx_bytes);
+                const int x0 = (tx * WTW + P.org_x) * P.stride, y0 = (ty * WTH + P.org_y) * P.stride;
+                for (int pl = 0; pl < P.nplanes; ++pl)
+                    for (int xb = 0; xb < P.x_boxes; ++xb)
+                        tma_load_4d(dst + (size_t)(pl * P.x_boxes + xb) * P.x_plane_bytes, &map_x, full + st, x_ch0 + xb * P.cxb, x0 + (pl & 1), y0 + (pl >> 1), b);
+                for (int yb = 0; yb < P.y_boxes; ++yb)
+                    tma_load_4d(dst + P.x_bytes + (size_t)yb * P.y_box_bytes, &map_y, full + st, yb * P.cyb, tx * WTW, ty * WTH, b);
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // instruction descriptor: fp32 accumulate, A / B formats, BOTH operands MN-major (bits 15, 16), N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | ((P.x_f16 ? 0u : 1u) << 7) | ((P.y_f16 ? 0u : 1u) << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(P.n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t rowx16 = (uint32_t)(P.cxb * 2) >> 4, rowy16 = (uint32_t)(P.cyb * 2) >> 4;
+            const uint32_t a_sbo16 = (uint32_t)P.halo_w * rowx16;             // next 8 pixels of K = next tile row = halo_w rows of the halo box
+            const uint32_t b_sbo16 = 8u * rowy16;
+            const uint32_t b_lbo16 = (uint32_t)P.y_box_bytes >> 4;
+            const uint32_t la = layout_for(P.cxb), lb = layout_for(P.cyb);
+            const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = (uint32_t)P.stage_bytes >> 4, xbytes16 = (uint32_t)P.x_bytes >> 4;
+            int st = 0;
+            uint32_t ph = 0;
+            bool first = true;
+            for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
+                mbar_wait(full + st, ph);
+                tc_fence_after();
+                const uint32_t base16 = smem16 + (uint32_t)st * stage16;
+#pragma unroll 1
+                for (int ks = 0; ks < 8; ++ks) {                             // 16 pixels (two tile rows) per MMA
+                    const uint64_t bdesc = make_mn_desc(base16 + xbytes16 + (uint32_t)ks * 2u * b_sbo16, b_lbo16, b_sbo16, lb);
+                    for (int g = 0; g < ngroups; ++g) {
+                        const uint64_t adesc = make_mn_desc(base16 + P.g[g0 + g].a_off16 + (uint32_t)ks * 2u * a_sbo16, P.g[g0 + g].a_lbo16, a_sbo16, la);
+                        umma_bf16(tmem_base + (uint32_t)(g * P.n_cols), adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
+                    }
+                }
+                umma_commit(empty + st);
+                first = false;
+                if (++st == S) { st = 0; ph ^= 1; }
+            }
+            umma_commit(tdone);
+        }
+        __syncwarp();
+    } else {
+        // epilogue: once per CTA.  Row of D = X channel (and tap), column = DY channel.
+        const bool has_work = tile0 < P.total_tiles;
+        if (has_work) {
+            const int q = warp & 3;
+            const int row = q * 32 + lane;
+            mbar_wait(tdone, 0);
+            tc_fence_after();
+            for (int g = 0; g < ngroups; ++g) {
+                const int blk = row / P.atom_rows;
+                const int tap = P.g[g0 + g].tap[blk];
+                const int cx = P.g[g0 + g].cx0 + (P.Cx >= 128 ? row : row - blk * P.atom_rows) - P.cx_off;
+                const bool ok = tap >= 0 && cx >= 0 && cx < P.cx_real;
+                float* dst = P.dw + (int64_t)tap * P.w_ts + (int64_t)cx * P.w_xs;
+                for (int c0 = 0; c0 < P.n_cols; c0 += 16) {
+                    uint32_t r[16];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * P.n_cols + c0)));
+                    tmem_wait_ld();
+                    if (ok) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if (c0 + k < P.cy_real) atomicAdd(dst + (int64_t)(c0 + k) * P.w_ys, __uint_as_float(r[k]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// dbias[c] += sum over pixels of a dense 16-bit NHWC tensor [P][C]: 256 threads, thread = (8-channel vector, pixel phase).
+template <bool F16>
+__global__ void __launch_bounds__(256) channel_sum_nhwc_kernel(const uint16_t* __restrict__ x, int64_t npix, int C, float* __restrict__ out) {
+    __shared__ float sacc[256 * 8];
+    const int vecs = C >> 3;                       // uint4 vectors per pixel
+    const int v = threadIdx.x % vecs, phase = threadIdx.x / vecs, nphase = 256 / vecs;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (phase < nphase) {
+        for (int64_t p = (int64_t)blockIdx.x * nphase + phase; p < npix; p += (int64_t)gridDim.x * nphase) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * C) + v);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 f;
+                if constexpr (F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                acc[e * 2] += f.x; acc[e * 2 + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc[threadIdx.x * 8 + k] = (phase < nphase) ? acc[k] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < C) {                          // channel c = vector (c >> 3), element (c & 7): sum over the phases
+        const int c = threadIdx.x;
+        float s = 0.f;
+        for (int ph = 0; ph < nphase; ++ph) s += sacc[(ph * vecs + (c >> 3)) * 8 + (c & 7)];
+        atomicAdd(out + c, s);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int spaa_conv_wgrad_tc_supported(const spaa_conv_desc* d) {
+    if (!d) return 0;
+    auto okc = [](int c) { return c == 16 || c == 32 || c == 64 || c == 128 || c == 256; };
+    if (!(d->in_dtype == 1 || d->in_dtype == 2) || d->out_dtype != d->in_dtype) return 0;      // kind::f16 traps on mixed fp16 x bf16 operands (measured)
+    if (!okc(d->Cin) || !okc(d->Cout)) return 0;
+    if (d->up != 1 || d->flip != 0 || !(d->stride == 1 || d->stride == 2)) return 0;
+    if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return 0;
+    if (d->in_cs != 1 || d->in_ps != d->Cin || d->in_bs != (int64_t)d->Hin * d->Win * d->Cin) return 0;
+    if (d->out_cs != 1 || d->out_ps != d->Cout || d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout) return 0;
+    return 1;
+}
+
+static inline int wg_floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+/* d describes the FORWARD gather conv (up == 1, flip == 0): `x` = gathered operand, dense 16-bit NHWC [B,Hin,Win,Cin];
+ * `dy` = pointwise operand, dense 16-bit NHWC [B,Hout,Wout,Cout]; dw fp32 (+=) addressed by d->w_ts / w_cis (X channel) / w_cos (DY channel).
+ * cx_real / cx_off / cy_real: zero-padded operands (3- and 6-channel images padded to 16). */
+int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(d && x && dy && dw, "spaa_conv_wgrad_tc: null argument");
+    SPAA_CHECK_ARG(spaa_conv_wgrad_tc_supported(d), "spaa_conv_wgrad_tc: unsupported shape / layout (see spaa_conv_wgrad_tc_supported)");
+    SPAA_CHECK_ARG(cx_real > 0 && cx_off >= 0 && cx_off + cx_real <= d->Cin && cy_real > 0 && cy_real <= d->Cout, "spaa_conv_wgrad_tc: bad channel ranges");
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_last_error("spaa_conv_wgrad_tc: cuTensorMapEncodeTiled is unavailable in this driver"); return SPAA_ERR_CUDA; }
+    const int Cx = d->Cin, Cy = d->Cout;
+    WgParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = d->B; P.Cx = Cx; P.Cy = Cy; P.Hy = d->Hout; P.Wy = d->Wout;
+    P.stride = d->stride; P.nplanes = d->stride * d->stride;
+    P.cxb = Cx >= 64 ? 64 : Cx; P.cyb = Cy >= 64 ? 64 : Cy;
+    P.y_boxes = Cy / P.cyb;
+    P.n_cols = Cy;
+    P.atom_rows = Cx >= 128 ? 64 : P.cxb;
+    P.cx_real = cx_real; P.cx_off = cx_off; P.cy_real = cy_real;
+    P.x_f16 = d->in_dtype == 2; P.y_f16 = d->out_dtype == 2;
+    P.w_ts = d->w_ts; P.w_xs = d->w_cis; P.w_ys = d->w_cos; P.dw = dw;
+    // ---- taps: (plane, shift) ----
+    struct TapPos { int plane, qy, qx; };
+    TapPos tp[9];
+    int ntaps = 0, qminx = 1 << 20, qmaxx = -(1 << 20), qminy = 1 << 20, qmaxy = -(1 << 20);
+    for (int r = 0; r < d->KH; ++r)
+        for (int s = 0; s < d->KW; ++s) {
+            TapPos t{0, r - d->pad_h, s - d->pad_w};
+            if (d->stride == 2) {
+                const int ry = r - d->pad_h, rx = s - d->pad_w, py = ry & 1, px = rx & 1;
+                t.plane = py * 2 + px; t.qy = wg_floordiv2(ry - py); t.qx = wg_floordiv2(rx - px);
+            }
+            qminx = t.qx < qminx ? t.qx : qminx; qmaxx = t.qx > qmaxx ? t.qx : qmaxx;
+            qminy = t.qy < qminy ? t.qy : qminy; qmaxy = t.qy > qmaxy ? t.qy : qmaxy;
+            tp[ntaps++] = t;
+        }
+    P.org_x = qminx; P.org_y = qminy;
+    P.halo_w = WTW + (qmaxx - qminx); P.halo_h = WTH + (qmaxy - qminy);
+    P.tiles_y = (d->Hout + WTH - 1) / WTH; P.tiles_x = (d->Wout + WTW - 1) / WTW;
+    P.total_tiles = d->B * P.tiles_y * P.tiles_x;
+    SPAA_CHECK_ARG(P.total_tiles > 0, "spaa_conv_wgrad_tc: empty problem");
+    const int rowx = P.cxb * 2, rowy = P.cyb * 2;
+    P.x_boxes = Cx >= 128 ? 2 : 1;                                   // one 128-channel chunk of X per launch
+    P.x_plane_bytes = (P.halo_h * P.halo_w * rowx + 1023) & ~1023;
+    P.x_bytes = P.nplanes * P.x_boxes * P.x_plane_bytes;
+    P.y_box_bytes = 128 * rowy;                                       // 16 x 8 pixels
+    if (P.y_box_bytes & 1023) P.y_box_bytes = (P.y_box_bytes + 1023) & ~1023;
+    P.stage_bytes = P.x_bytes + P.y_boxes * P.y_box_bytes;
+    P.tx_bytes = P.nplanes * P.x_boxes * P.halo_h * P.halo_w * rowx + P.y_boxes * 128 * rowy;
+    P.nstages = (200 * 1024) / P.stage_bytes;
+    if (P.nstages > 4) P.nstages = 4;
+    SPAA_CHECK_ARG(P.nstages >= 1, "spaa_conv_wgrad_tc: stage does not fit in shared memory");
+    auto tap_off16 = [&](int t, int xb) {
+        return (uint32_t)(((tp[t].plane * P.x_boxes + xb) * P.x_plane_bytes + ((tp[t].qy - qminy) * P.halo_w + (tp[t].qx - qminx)) * rowx) >> 4);
+    };
+    // ---- accumulator list: (tap, 128-channel chunk) for Cx >= 128, tap pairs for Cx == 64, single taps below ----
+    struct Acc { WgGroup g; int chunk; };
+    Acc accs[32];
+    int nacc = 0;
+    if (Cx >= 128) {
+        for (int ch = 0; ch < Cx / 128; ++ch)
+            for (int t = 0; t < ntaps; ++t) {
+                Acc& a = accs[nacc++];
+                memset(&a, 0, sizeof(a));
+                a.chunk = ch;
+                a.g.a_off16 = tap_off16(t, 0); a.g.a_lbo16 = (uint32_t)P.x_plane_bytes >> 4;       // channels 64..127 = the next box of the same plane
+                for (int k = 0; k < 8; ++k) a.g.tap[k] = (int8_t)t;
+                a.g.cx0 = ch * 128;
+            }
+    } else if (Cx == 64) {
+        for (int t = 0; t < ntaps; t += 2) {                       // two taps per MMA: atom 0 / atom 1 = the views of tap t0 / t1
+            Acc& a = accs[nacc++];
+            memset(&a, 0, sizeof(a));
+            for (int k = 0; k < 8; ++k) a.g.tap[k] = -1;
+            int t0 = t, t1 = t + 1 < ntaps ? t + 1 : -1;
+            if (t1 >= 0 && tap_off16(t1, 0) < tap_off16(t0, 0)) { const int tmp = t0; t0 = t1; t1 = tmp; }
+            a.g.a_off16 = tap_off16(t0, 0);
+            a.g.tap[0] = (int8_t)t0;
+            if (t1 >= 0) { a.g.a_lbo16 = tap_off16(t1, 0) - tap_off16(t0, 0); a.g.tap[1] = (int8_t)t1; }    // distinct taps: distinct (plane, shift)
+            else a.g.a_lbo16 = (uint32_t)rowx >> 4;
+        }
+    } else {
+        for (int t = 0; t < ntaps; ++t) {
+            Acc& a = accs[nacc++];
+            memset(&a, 0, sizeof(a));
+            for (int k = 0; k < 8; ++k) a.g.tap[k] = -1;
+            a.g.a_off16 = tap_off16(t, 0); a.g.a_lbo16 = (uint32_t)rowx >> 4; a.g.tap[0] = (int8_t)t;
+        }
+    }
+    int max_per_set = 512 / Cy;
+    if (max_per_set > 8) max_per_set = 8;
+    SPAA_CHECK_ARG(nacc <= kMaxGroups, "spaa_conv_wgrad_tc: too many accumulators");
+    for (int i = 0; i < nacc; ++i) P.g[i] = accs[i].g;
+    P.nsets = 0; P.max_groups = 0;
+    for (int i = 0; i < nacc;) {
+        int n = 0;
+        while (i + n < nacc && accs[i + n].chunk == accs[i].chunk) ++n;          // accumulators of this X chunk
+        const int k = (n + max_per_set - 1) / max_per_set;                        // sets for the chunk, evenly filled
+        for (int j = 0, first = i; j < k; ++j) {
+            const int cnt = (n - (first - i) + (k - j) - 1) / (k - j);
+            SPAA_CHECK_ARG(P.nsets < kMaxSets, "spaa_conv_wgrad_tc: too many accumulator sets");
+            P.set_first[P.nsets] = (int16_t)first; P.set_count[P.nsets] = (int16_t)cnt; P.set_ch0[P.nsets] = (int16_t)(accs[i].chunk * 128);
+            if (cnt > P.max_groups) P.max_groups = cnt;
+            ++P.nsets;
+            first += cnt;
+        }
+        i += n;
+    }
+    CUtensorMap mx, my;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cx * 2, (cuuint64_t)d->Win * Cx * 2, (cuuint64_t)d->Hin * d->Win * Cx * 2};
+        cuuint32_t box[4] = {(cuuint32_t)P.cxb, (cuuint32_t)(P.halo_w * d->stride), (cuuint32_t)(P.halo_h * d->stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        const CUtensorMapSwizzle sw = P.cxb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.cxb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUresult r = enc(&mx, P.x_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SPAA_ERR_CUDA; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cy, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cy * 2, (cuuint64_t)d->Wout * Cy * 2, (cuuint64_t)d->Hout * d->Wout * Cy * 2};
+        cuuint32_t box[4] = {(cuuint32_t)P.cyb, (cuuint32_t)WTW, (cuuint32_t)WTH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        const CUtensorMapSwizzle sw = P.cyb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.cyb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        CUresult r = enc(&my, P.y_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r); return SPAA_ERR_CUDA; }
+    }
+    const size_t smem_bytes = (size_t)P.nstages * P.stage_bytes + 128 + 1024;
+    static size_t reserved = 0;
+    if (smem_bytes > reserved) {
+        if (cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
+            set_last_error("spaa_conv_wgrad_tc: cannot reserve shared memory");
+            return SPAA_ERR_CUDA;
+        }
+        reserved = 220 * 1024;
+    }
+    int grid = kNumSMs;
+    if ((int64_t)P.total_tiles * P.nsets < grid) grid = P.total_tiles * P.nsets;
+    conv_wgrad_tc_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(mx, my, P);
+    SPAA_CHECK_LAUNCH("spaa_conv_wgrad_tc");
+    return SPAA_OK;
+}
+
+/* out[c] += sum over pixels of a DENSE 16-bit NHWC tensor [npix][C] (C a multiple of 8, <= 256): bias gradients. dtype 1 bf16, 2 fp16. */
+int spaa_channel_sum_nhwc16(const void* x, int dtype, int64_t npix, int C, float* out, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(x && out && npix > 0 && C >= 8 && C <= 256 && (C & 7) == 0 && (256 % (C >> 3)) == 0 && (dtype == 1 || dtype == 2),
+                   "spaa_channel_sum_nhwc16: bad arguments");
+    const int nphase = 256 / (C >> 3);
+    int64_t blocks = (npix + nphase * 8 - 1) / (nphase * 8);
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    if (dtype == 2) channel_sum_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, npix, C, out);
+    else channel_sum_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, npix, C, out);
+    SPAA_CHECK_LAUNCH("spaa_channel_sum_nhwc16");
+    return SPAA_OK;
+}
+
+}  // extern "C"

@@ -136,11 +136,24 @@ class _Stack:
         hw = lambda t: (t.shape[2], t.shape[3])
         B = (d_pre6 if d_pre6 is not None else d_pre6_packed).shape[0]
 
-        def wgrad(name, inp, dy):
+        def wgrad(name, inp, dy, x_offset=0):
             if pg is not None and (name + ".weight") in pg:
                 if inp.shape[0] == 1 and B > 1:
                     inp = inp.expand(B, -1, -1, -1)
-                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"))
+                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset)
+
+        def packed_input():
+            """[x | surf | 0] as one zero-padded 16-channel NHWC tensor in the gradient dtype: the X operand of the tensor-core
+            backward-weight kernel for conv1 (channels 0-2) and conv1_s (channels 3..3+Cs); built once per backward."""
+            if "packed_bw" not in S:
+                if S.get("packed") is not None and S["packed"].dtype == gdt:
+                    S["packed_bw"] = S["packed"]
+                else:
+                    xs = S["x"] if S["surf"] is None else torch.cat((S["x"], S["surf"].expand(B, -1, -1, -1)), 1)
+                    pk = torch.zeros((B, xs.shape[2], xs.shape[3], 16), dtype=gdt, device=xs.device).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
+                    pk[:, :xs.shape[1]] = xs
+                    S["packed_bw"] = pk
+            return S["packed_bw"]
 
         surf_live = S.get("surf_own", False) and (surf_grad_channels is not None or pg is not None)
         if surf_live and S["r1s"].shape[0] != B:
@@ -150,7 +163,9 @@ class _Stack:
         in_hw = hw(S["packed"]) if S.get("packed") is not None else hw(S["x"])
         d7 = ops.conv_backward_data(sp["conv6"], d_pre6_packed if d_pre6_packed is not None else d_pre6, Wt("conv6"), hw(x7), mask=x7,
                                     mask_mode=MASK_POS, out_dtype=gdt)
-        if d_pre6 is not None:
+        if d_pre6_packed is not None and d_pre6_packed.dtype == x7.dtype:
+            wgrad("conv6", x7, d_pre6_packed)                       # tensor-core backward-weight: padded 16-channel cotangent (3 real)
+        elif d_pre6 is not None:
             wgrad("conv6", x7, d_pre6)
         d6 = ops.conv_backward_data(sp["transConv2"], d7, Wt("transConv2"), hw(x6), mask=x6, mask_mode=MASK_POS)
         wgrad("transConv2", x6, d7)
@@ -173,7 +188,10 @@ class _Stack:
         dx = None
         if need_dx:
             dx = ops.conv_backward_data(sp["conv1"], d1, Wt("conv1"), in_hw, out_dtype=torch.float32)
-        if S["x"] is not None:
+        tc_bw = pg is not None and d1.dtype in (torch.bfloat16, torch.float16) and d1.dtype == gdt and (S["x"] is not None or S.get("packed") is not None)
+        if tc_bw:
+            wgrad("conv1", packed_input(), d1, 0)
+        elif S["x"] is not None:
             wgrad("conv1", S["x"], d1)
         dsurf = None
         if surf_live:
@@ -187,7 +205,9 @@ class _Stack:
             if surf_grad_channels is not None:
                 lo, hi = surf_grad_channels
                 dsurf = ops.conv_backward_data(sp["conv1_s"], d1s, Wt("conv1_s")[:, lo:hi], in_hw, out_dtype=torch.float32)
-            if S["surf"] is not None:
+            if tc_bw:
+                wgrad("conv1_s", packed_input(), d1s, 3)
+            elif S["surf"] is not None:
                 wgrad("conv1_s", S["surf"], d1s)
         dskip = None
         skip_params = pg is not None and "skipConv1.4.weight" in pg

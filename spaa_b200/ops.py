@@ -474,8 +474,14 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
     return out
 
 
-def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor]) -> None:
-    """dw += d(loss)/d(weight), db += d(loss)/d(bias); dw/db are fp32 accumulators in the parameter's own layout."""
+def _dense_nhwc16(t: Tensor) -> bool:
+    return t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(memory_format=torch.channels_last) and t.shape[1] in (16, 32, 64, 128, 256)
+
+
+def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor], *, x_offset: int = 0) -> None:
+    """dw += d(loss)/d(weight), db += d(loss)/d(bias); dw/db are fp32 accumulators in the parameter's own layout.
+    16-bit dense NHWC operands go to the tcgen05 backward-weight kernel; `x` / `dy` may then be zero-padded to 16 channels
+    (the layer's real input channels sit at [x_offset, x_offset + spec.cin) of `x`, the real output channels at [0, spec.cout) of `dy`)."""
     _need_cuda(x, dy, dw)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
     d = ConvDesc()
@@ -483,23 +489,68 @@ def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: 
     d.stride, d.up, d.pad_h, d.pad_w, d.flip = spec.stride, 1, spec.pad, spec.pad, 0
     d.w_ts = 1
     L = lib()
+    use_tc = TC_ENABLED and _dense_nhwc16(x) and _dense_nhwc16(dy) and x.dtype == dy.dtype      # tcgen05 kind::f16: both operands one format
+    if not use_tc and (x.shape[1] != spec.cin or dy.shape[1] != spec.cout):
+        raise RuntimeError("zero-padded channel operands are only implemented on the tensor-core backward-weight path")
     if spec.kind == "conv":
-        d.Cin, d.Cout = spec.cin, spec.cout
+        d.Cin, d.Cout = x.shape[1], dy.shape[1]
         d.w_cos, d.w_cis = dw.stride(0), dw.stride(1)
         _fill_desc(d, x, dy, None, None)
-        L.spaa_conv_bwd_weight(ctypes.byref(d), _p(x), _p(dy), _p(dw), _p(db), _stream()); _count(2 if db is not None else 1)
+        gathered, pointwise, g_real, g_off, p_real = x, dy, spec.cin, x_offset, spec.cout
     else:
         # dWt[ci,co,r,s] = sum in[iy,ci] * dOut[iy*s-p+r, co]: the gathered operand is dOut, the pointwise one is `x`
-        d.Cin, d.Cout = spec.cout, spec.cin
+        d.Cin, d.Cout = dy.shape[1], x.shape[1]
         d.w_cis, d.w_cos = dw.stride(1), dw.stride(0)
         _fill_desc(d, dy, x, None, None)
+        gathered, pointwise, g_real, g_off, p_real = dy, x, spec.cout, 0, spec.cin
+    if use_tc and L.spaa_conv_wgrad_tc_supported(ctypes.byref(d)) == 1:
+        with _Probe("bwd_weight_tc", spec):
+            L.spaa_conv_wgrad_tc(ctypes.byref(d), _p(gathered), _p(pointwise), _p(dw), g_real, g_off, p_real, _stream())
+        _count()
+        if db is not None:
+            if spec.kind == "conv":
+                L.spaa_channel_sum_nhwc16(_p(dy), _dt(dy), dy.shape[0] * dy.shape[2] * dy.shape[3], dy.shape[1], _p(_bias_scratch(db, dy.shape[1])), _stream()); _count()
+                _bias_fold(db, dy.shape[1])
+            else:
+                channel_sum(dy, db)
+        return
+    if x.shape[1] != spec.cin or dy.shape[1] != spec.cout:
+        raise RuntimeError("zero-padded channel operands are only implemented on the tensor-core backward-weight path")
+    if spec.kind == "conv":
+        L.spaa_conv_bwd_weight(ctypes.byref(d), _p(x), _p(dy), _p(dw), _p(db), _stream()); _count(2 if db is not None else 1)
+    else:
         L.spaa_conv_bwd_weight(ctypes.byref(d), _p(dy), _p(x), _p(dw), None, _stream()); _count()
         if db is not None:
             channel_sum(dy, db)
 
 
+_bias_tmp: Dict[Tuple[int, int], Tensor] = {}
+
+
+def _bias_scratch(db: Tensor, c: int) -> Tensor:
+    """Bias gradients of zero-padded outputs (3 real of 16 channels) are summed into a padded scratch vector first."""
+    if db.numel() == c:
+        return db
+    key = (db.device.index or 0, c)
+    t = _bias_tmp.get(key)
+    if t is None:
+        t = torch.zeros(c, dtype=torch.float32, device=db.device)
+        _bias_tmp[key] = t
+    else:
+        t.zero_()
+    return t
+
+
+def _bias_fold(db: Tensor, c: int) -> None:
+    if db.numel() != c:
+        db += _bias_tmp[(db.device.index or 0, c)][:db.numel()]
+
+
 def channel_sum(x: Tensor, out: Tensor) -> None:
     """out[c] += sum over batch and pixels of x[:, c]."""
+    if _dense_nhwc16(x) and out.numel() == x.shape[1]:
+        lib().spaa_channel_sum_nhwc16(_p(x), _dt(x), x.shape[0] * x.shape[2] * x.shape[3], x.shape[1], _p(out), _stream()); _count()
+        return
     bs, ps, cs = _act_strides(x)
     lib().spaa_channel_sum(_p(x), _dt(x), x.shape[0], x.shape[1], x.shape[2] * x.shape[3], bs, ps, cs, _p(out), _stream()); _count()
 

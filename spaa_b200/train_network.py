@@ -194,7 +194,7 @@ def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter,
             idx = shard_indices(idx, rank, world)
         it = torch.as_tensor(idx, device=device)
         x_batch, y_batch = inputs.index_select(0, it), targets.index_select(0, it)
-        cfg["loss"] = loss_of_iter(iters)
+        cfg["loss"] = loss_of_iter(iters + cfg.get("iter_offset", 0))      # iter_offset: resume / benchmark a later phase of the schedule
         model.train()
         infer = model(x_batch, scene_batch)
         loss, l2 = compute_loss(infer, y_batch, cfg["loss"])

@@ -136,3 +136,70 @@ def test_tc_padded_input_and_planar_output(dtype):
     wantc = torch.zeros(B, 16, H, W, device=dev)
     wantc[:, :3] = ops.select_cotangent(g0, g1, sel, act, ops.MASK_OPEN01, torch.empty_like(g0))
     close(outp.float(), wantc.to(torch.bfloat16).float(), 0, 0, "packed cotangent")
+
+
+WG_CASES = [
+    # kind, cin, cout, k, stride, pad, outpad, H, W
+    ("conv", 128, 256, 3, 1, 1, 0, 20, 24), ("conv", 256, 128, 3, 1, 1, 0, 17, 9), ("conv", 64, 128, 3, 1, 1, 0, 16, 32),
+    ("conv", 32, 64, 1, 1, 0, 0, 24, 32), ("conv", 32, 64, 3, 2, 1, 0, 26, 38), ("conv", 64, 64, 3, 2, 1, 0, 16, 32),
+    ("convT", 128, 64, 3, 2, 1, 1, 7, 11), ("convT", 64, 32, 2, 2, 0, 0, 12, 16), ("conv", 32, 16, 3, 1, 1, 0, 20, 36),
+    ("conv", 16, 32, 3, 2, 1, 0, 20, 36),
+]
+
+
+@pytest.mark.parametrize("mix", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", WG_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_tc_backward_weight(case, mix):
+    """tcgen05 MN-major backward-weight kernel vs autograd in float64 on the same 16-bit-rounded operands."""
+    from spaa_b200 import ops
+    kind, cin, cout, k, stride, pad, outpad, H, W = case
+    B = 3
+    spec = ops.ConvSpec(kind, cin, cout, k, stride, pad, outpad)
+    adt = torch.float16 if mix == "fp16" else torch.bfloat16
+    x = synth.randn(31, "wg.x", (B, cin, H, W)).to(adt)
+    w = torch.zeros(spec.weight_shape(), dtype=torch.double, requires_grad=True)
+    pre = F.conv2d(x.double(), w, None, stride, pad) if kind == "conv" else F.conv_transpose2d(x.double(), w, None, stride, pad, outpad)
+    dy = synth.randn(32, "wg.dy", pre.shape).to(adt)
+    gw, = torch.autograd.grad((pre * dy.double()).sum(), w)
+    dw = torch.zeros(spec.weight_shape(), device="cuda:0")
+    db = torch.zeros(cout, device="cuda:0")
+    probe = ops.set_probe(lambda kd, sp: kd == "bwd_weight_tc")
+    ops.conv_backward_weight(spec, cl(x, adt), cl(dy, adt), dw, db)
+    ops.set_probe(None)
+    assert len(probe["events"]) == 1, "the tensor-core backward-weight kernel was not used"
+    scale = gw.abs().max().item()
+    close(dw, gw, 2e-3 * scale, 1e-3, f"dW {case}")
+    close(db, dy.double().sum((0, 2, 3)), 1e-2 * max(1.0, dy.double().sum((0, 2, 3)).abs().max().item()), 1e-3, "dbias")
+    # accumulation semantics: a second call adds
+    ops.conv_backward_weight(spec, cl(x, adt), cl(dy, adt), dw, None)
+    close(dw, 2 * gw, 4e-3 * scale, 1e-3, "dW accumulates")
+
+
+def test_tc_backward_weight_padded_channels():
+    """conv1_s-like (6 real input channels at 3..8 of a 16-channel tensor) and conv6-like (3 real output-gradient channels of 16)."""
+    from spaa_b200 import ops
+    B, H, W = 2, 20, 36
+    spec = ops.ConvSpec("conv", 6, 32, 3, 2, 1)
+    x16 = torch.zeros(B, 16, H, W)
+    x16[:, 3:9] = synth.randn(41, "wgp.x", (B, 6, H, W))
+    x16 = x16.to(torch.bfloat16)
+    w = torch.zeros(spec.weight_shape(), dtype=torch.double, requires_grad=True)
+    pre = F.conv2d(x16[:, 3:9].double(), w, None, 2, 1)
+    dy = synth.randn(42, "wgp.dy", pre.shape).to(torch.bfloat16)
+    gw, = torch.autograd.grad((pre * dy.double()).sum(), w)
+    dw = torch.zeros(spec.weight_shape(), device="cuda:0")
+    ops.conv_backward_weight(spec, cl(x16), cl(dy), dw, None, x_offset=3)
+    close(dw, gw, 2e-3 * gw.abs().max().item(), 1e-3, "padded-input dW")
+    spec6 = ops.ConvSpec("conv", 32, 3, 3, 1, 1)
+    x7 = synth.randn(43, "wgp.x7", (B, 32, H, W)).to(torch.bfloat16)
+    w6 = torch.zeros(spec6.weight_shape(), dtype=torch.double, requires_grad=True)
+    pre6 = F.conv2d(x7.double(), w6, None, 1, 1)
+    cot = torch.zeros(B, 16, H, W)
+    cot[:, :3] = synth.randn(44, "wgp.cot", (B, 3, H, W))
+    cot = cot.to(torch.bfloat16)
+    gw6, = torch.autograd.grad((pre6 * cot[:, :3].double()).sum(), w6)
+    dw6 = torch.zeros(spec6.weight_shape(), device="cuda:0")
+    db6 = torch.zeros(3, device="cuda:0")
+    ops.conv_backward_weight(spec6, cl(x7), cl(cot), dw6, db6)
+    close(dw6, gw6, 2e-3 * gw6.abs().max().item(), 1e-3, "padded-gradient dW")
+    close(db6, cot[:, :3].double().sum((0, 2, 3)), 1e-2, 1e-3, "padded-gradient dbias")
