@@ -220,6 +220,11 @@ int spaa_select_cotangent(const float* g0, const float* g1, const uint8_t* sel, 
  * (the operand of the tensor-core backward of the network's last convolution).  dtype: 1 bf16, 2 fp16. */
 int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t* sel, const float* act, int mask_mode,
                                  void* out16, int dtype, int64_t B, int64_t HW, spaa_stream_t stream);
+/* [x | surf | 0]: fp32 NCHW images x [B,Cx,HW] and surf [B or 1,Cs,HW] (nullable, Cx+Cs <= 16) written as ONE zero-padded
+ * 16-channel 16-bit NHWC tensor [B,HW,16] -- the operand of the tensor-core conv1 / conv1_s (forward and backward-weight)
+ * when the images come from the nn.Module API instead of the fused warp kernel.  dtype: 1 bf16, 2 fp16. */
+int spaa_pack_nhwc16(const float* x, int Cx, const float* surf, int Cs, int64_t surf_bstride, void* out16, int dtype, int64_t B,
+                     int64_t HW, spaa_stream_t stream);
 /* PerC-AL projection: delta = clamp(base+delta,0,1)-base ; xsum (nullable) = base+delta ;
  * xq = round((base+delta)*255)/255 ; l2sum[b] = sum_p ||delta[b,:,p]||_2   (perc_al/__init__.py:211-215, :15-18).
  * Tensors [B,3,HW]; base_bstride may be 0. */

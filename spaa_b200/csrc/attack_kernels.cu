@@ -135,6 +135,33 @@ __global__ void __launch_bounds__(kThreads) select_cot_packed_kernel(const float
     }
 }
 
+// [x (Cx planes) | surf (Cs planes) | 0] fp32 NCHW -> zero-padded 16-channel 16-bit NHWC (the tensor-core conv1 / conv1_s operand in training)
+template <bool F16>
+__global__ void __launch_bounds__(kThreads) pack_nhwc16_kernel(const float* __restrict__ x, int Cx, const float* __restrict__ surf, int Cs, int64_t surf_bs,
+                                                               uint4* __restrict__ out16, int64_t HW) {
+    const int b = blockIdx.y;
+    const float* xb = x + (int64_t)b * Cx * HW;
+    const float* sb = surf ? surf + (int64_t)b * surf_bs : nullptr;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float t = 0.f;
+            if (c < Cx) t = __ldg(xb + (int64_t)c * HW + p);
+            else if (sb && c < Cx + Cs) t = __ldg(sb + (int64_t)(c - Cx) * HW + p);
+            v[c] = t;
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if constexpr (F16) { const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<const uint32_t*>(&h); }
+            else { const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<const uint32_t*>(&h); }
+        }
+        uint4* o = out16 + ((int64_t)b * HW + p) * 2;
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]); o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // PerC-AL projection (perc_al/__init__.py:211-215, :15-18)
 __global__ void __launch_bounds__(kThreads) percal_project_kernel(const float* __restrict__ base, int64_t base_bs, float* __restrict__ delta,
                                                                   float* __restrict__ xq, float* __restrict__ xsum, float* __restrict__ l2sum, int64_t HW,
@@ -329,6 +356,16 @@ int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t
     if (dtype == 2) select_cot_packed_kernel<true><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
     else select_cot_packed_kernel<false><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
     SPAA_CHECK_LAUNCH("spaa_select_cotangent_packed");
+    return SPAA_OK;
+}
+
+int spaa_pack_nhwc16(const float* x, int Cx, const float* surf, int Cs, int64_t surf_bstride, void* out16, int dtype, int64_t B, int64_t HW,
+                     spaa_stream_t stream) {
+    SPAA_CHECK_ARG(x && out16 && Cx > 0 && Cs >= 0 && Cx + Cs <= 16 && (Cs == 0 || surf) && B > 0 && B < 65536 && HW > 0 && (dtype == 1 || dtype == 2),
+                   "spaa_pack_nhwc16: bad arguments");
+    if (dtype == 2) pack_nhwc16_kernel<true><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(x, Cx, Cs ? surf : nullptr, Cs, surf_bstride, (uint4*)out16, HW);
+    else pack_nhwc16_kernel<false><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(x, Cx, Cs ? surf : nullptr, Cs, surf_bstride, (uint4*)out16, HW);
+    SPAA_CHECK_LAUNCH("spaa_pack_nhwc16");
     return SPAA_OK;
 }
 

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) conv_bwd_weight_kernel(const WgP p) 
     }
 }
 
-// dbias[co] += sum over pixels of dout[pix][co]; grid = (splits), each block walks its pixel range
+// dbias[co] += sum over pixels of dout[pix][co]; grid = (pixel splits, Cout): one block reduction per (split, channel)
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads) bias_grad_kernel(const spaa_conv_desc d, const OutT* __restrict__ dout, float* __restrict__ dbias,
                                                              int64_t pix_per_split) {
@@ -323,15 +323,81 @@ __global__ void __launch_bounds__(kThreads) bias_grad_kernel(const spaa_conv_des
     const int64_t M = (int64_t)d.B * HWo;
     const int64_t P0 = (int64_t)blockIdx.x * pix_per_split;
     const int64_t P1 = (P0 + pix_per_split < M) ? P0 + pix_per_split : M;
-    for (int co = 0; co < d.Cout; ++co) {
-        float s = 0.f;
-        for (int64_t P = P0 + threadIdx.x; P < P1; P += kThreads) {
-            const int b = (int)(P / HWo);
-            const int pix = (int)(P - (int64_t)b * HWo);
-            s += ld_f(dout + (int64_t)b * d.out_bs + (int64_t)pix * d.out_ps + (int64_t)co * d.out_cs);
+    const int co = blockIdx.y;
+    float s = 0.f;
+    for (int64_t P = P0 + threadIdx.x; P < P1; P += kThreads) {
+        const int b = (int)(P / HWo);
+        const int pix = (int)(P - (int64_t)b * HWo);
+        s += ld_f(dout + (int64_t)b * d.out_bs + (int64_t)pix * d.out_ps + (int64_t)co * d.out_cs);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(dbias + co, s);
+}
+
+// Direct convolution for the 3 -> 3 channel full-resolution layers (skipConv1.*, models.py:243-247; forward and backward-data):
+// fp32 NCHW planes, stride 1, 1x1 or 3x3.  One thread per pixel computes all output channels from weights in shared memory; the
+// implicit-GEMM tile above spends a 256 x 4 tile on 3 channels and runs at 5 % of the HBM roofline for these layers.
+template <int K>
+__global__ void __launch_bounds__(256) conv_small_kernel(const ConvP p) {
+    constexpr int C = 3, KK = K * K;
+    __shared__ float sw[KK * C * C];
+    __shared__ float sb[C];
+    const spaa_conv_desc& d = p.d;
+    for (int i = threadIdx.x; i < KK * C * C; i += blockDim.x) {
+        const int tap = i / (C * C), ci = (i / C) % C, co = i % C;
+        const int r = tap / K, s = tap - r * K;
+        const int wtap = d.flip ? (K - 1 - r) * K + (K - 1 - s) : tap;
+        sw[i] = (ci < d.Cin && co < d.Cout) ? __ldg(p.w + (int64_t)wtap * d.w_ts + (int64_t)ci * d.w_cis + (int64_t)co * d.w_cos) : 0.f;
+    }
+    if (threadIdx.x < C) sb[threadIdx.x] = (p.bias && threadIdx.x < d.Cout) ? __ldg(p.bias + threadIdx.x) : 0.f;
+    __syncthreads();
+    const int H = d.Hout, W = d.Wout, HW = H * W;
+    const int64_t total = (int64_t)d.B * HW;
+    const float* in = (const float*)p.in;
+    const float* addp = (const float*)p.add;
+    const float* maskp = (const float*)p.mask;
+    const float* mask2p = (const float*)p.mask2;
+    float* outp = (float*)p.out;
+    float* out2p = (float*)p.out2;
+    const int ef = d.epi_flags;
+    for (int64_t P = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; P < total; P += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(P / HW);
+        const int pix = (int)(P - (int64_t)b * HW);
+        const int oy = pix / W, ox = pix - oy * W;
+        float acc[C] = {sb[0], sb[1], sb[2]};
+#pragma unroll
+        for (int r = 0; r < K; ++r)
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const int iy = oy + r - d.pad_h, ix = ox + s - d.pad_w;
+                if (iy < 0 || ix < 0 || iy >= d.Hin || ix >= d.Win) continue;
+                const float* src = in + (int64_t)b * d.in_bs + (int64_t)iy * d.Win + ix;
+#pragma unroll
+                for (int ci = 0; ci < C; ++ci) {
+                    if (ci < d.Cin) {
+                        const float xv = __ldg(src + (int64_t)ci * d.in_cs);
+#pragma unroll
+                        for (int co = 0; co < C; ++co) acc[co] = fmaf(xv, sw[((r * K + s) * C + ci) * C + co], acc[co]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int co = 0; co < C; ++co) {
+            if (co >= d.Cout) continue;
+            float v = acc[co];
+            float av = 0.f;
+            if (addp) av = __ldg(addp + (int64_t)b * d.add_bs + (int64_t)pix * d.add_ps + (int64_t)co * d.add_cs);
+            if (addp && !(ef & SPAA_EPI_ADD_AFTER_ACT)) v += av;
+            if (ef & SPAA_EPI_RELU) v = fmaxf(v, 0.f);
+            if (ef & SPAA_EPI_LEAKY01) v = v > 0.f ? v : 0.1f * v;
+            if (ef & SPAA_EPI_CLAMP_MAX1) v = fminf(v, 1.f);
+            if (addp && (ef & SPAA_EPI_ADD_AFTER_ACT)) v += av;
+            const int64_t mo = (int64_t)b * d.mask_bs + (int64_t)pix * d.mask_ps + (int64_t)co * d.mask_cs;
+            if (maskp) v = apply_mask(v, __ldg(maskp + mo), d.mask_mode);
+            const int64_t oo = (int64_t)b * d.out_bs + (int64_t)pix * d.out_ps + (int64_t)co * d.out_cs;
+            outp[oo] = v;
+            if (out2p) out2p[oo] = __ldg(mask2p + mo) > 0.f ? v : 0.f;
         }
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) atomicAdd(dbias + co, s);
     }
 }
 
@@ -408,6 +474,16 @@ int spaa_conv_fwd(const spaa_conv_desc* d, const void* in, const float* w, const
     SPAA_CHECK_ARG(d->mask_mode == SPAA_MASK_NONE || mask, "spaa_conv_fwd: mask_mode needs mask");
     ConvP p{*d, in, w, bias, add, mask, mask2, out, out2};
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->Cin <= 3 && d->Cout <= 3 && d->in_dtype == 0 && d->out_dtype == 0 && d->stride == 1 && d->up == 1 && d->in_ps == 1 &&
+        d->Hin == d->Hout && d->Win == d->Wout && d->KH == d->KW && (d->KH == 1 || d->KH == 3)) {
+        const int64_t M = (int64_t)d->B * d->Hout * d->Wout;
+        int64_t blocks = (M + 255) / 256;
+        if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+        if (d->KH == 1) conv_small_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(p);
+        else conv_small_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(p);
+        SPAA_CHECK_LAUNCH("spaa_conv_fwd(small)");
+        return SPAA_OK;
+    }
     if (d->Cout > 32) launch_cfg<128, 64, 8, 4>(p, st);
     else if (d->Cout > 16) launch_cfg<128, 32, 4, 4>(p, st);
     else if (d->Cout > 4) launch_cfg<256, 16, 4, 4>(p, st);
@@ -456,14 +532,15 @@ int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* do
 #undef SPAA_WG_CASE
     SPAA_CHECK_LAUNCH("spaa_conv_bwd_weight");
     if (dbias) {
-        int64_t bsplits = M / 4096;
+        int64_t bsplits = (4 * kNumSMs + d->Cout - 1) / d->Cout;
+        if (bsplits > (M + 1023) / 1024) bsplits = (M + 1023) / 1024;
         if (bsplits < 1) bsplits = 1;
-        if (bsplits > 2 * kNumSMs) bsplits = 2 * kNumSMs;
         const int64_t bpps = (M + bsplits - 1) / bsplits;
         bsplits = (M + bpps - 1) / bpps;
-        if (d->out_dtype == 0) bias_grad_kernel<float><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const float*)dout, dbias, bpps);
-        else if (d->out_dtype == 1) bias_grad_kernel<__nv_bfloat16><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const __nv_bfloat16*)dout, dbias, bpps);
-        else bias_grad_kernel<__half><<<(unsigned)bsplits, kThreads, 0, st>>>(*d, (const __half*)dout, dbias, bpps);
+        const dim3 bgrid((unsigned)bsplits, (unsigned)d->Cout);
+        if (d->out_dtype == 0) bias_grad_kernel<float><<<bgrid, kThreads, 0, st>>>(*d, (const float*)dout, dbias, bpps);
+        else if (d->out_dtype == 1) bias_grad_kernel<__nv_bfloat16><<<bgrid, kThreads, 0, st>>>(*d, (const __nv_bfloat16*)dout, dbias, bpps);
+        else bias_grad_kernel<__half><<<bgrid, kThreads, 0, st>>>(*d, (const __half*)dout, dbias, bpps);
         SPAA_CHECK_LAUNCH("spaa_conv_bwd_weight(bias)");
     }
     return SPAA_OK;
@@ -475,14 +552,15 @@ int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int
     d.B = (int)B; d.Cout = C; d.Hout = 1; d.Wout = (int)HW;
     d.out_bs = bs; d.out_ps = ps; d.out_cs = cs;
     const int64_t M = B * HW;
-    int64_t splits = M / 4096;
+    int64_t splits = (4 * kNumSMs + C - 1) / C;
+    if (splits > (M + 1023) / 1024) splits = (M + 1023) / 1024;
     if (splits < 1) splits = 1;
-    if (splits > 2 * kNumSMs) splits = 2 * kNumSMs;
     const int64_t pps = (M + splits - 1) / splits;
     splits = (M + pps - 1) / pps;
-    if (dtype == 0) bias_grad_kernel<float><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const float*)x, out, pps);
-    else if (dtype == 1) bias_grad_kernel<__nv_bfloat16><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const __nv_bfloat16*)x, out, pps);
-    else bias_grad_kernel<__half><<<(unsigned)splits, kThreads, 0, (cudaStream_t)stream>>>(d, (const __half*)x, out, pps);
+    const dim3 grid((unsigned)splits, (unsigned)C);
+    if (dtype == 0) bias_grad_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>(d, (const float*)x, out, pps);
+    else if (dtype == 1) bias_grad_kernel<__nv_bfloat16><<<grid, kThreads, 0, (cudaStream_t)stream>>>(d, (const __nv_bfloat16*)x, out, pps);
+    else bias_grad_kernel<__half><<<grid, kThreads, 0, (cudaStream_t)stream>>>(d, (const __half*)x, out, pps);
     SPAA_CHECK_LAUNCH("spaa_channel_sum");
     return SPAA_OK;
 }

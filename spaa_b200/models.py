@@ -97,6 +97,10 @@ class _Stack:
         surf on the tensor-core path.  Returns (out, saved activations)."""
         sp = net._specs
         W = lambda n: (_get(net, n).weight, _get(net, n).bias)
+        if packed is None and x is not None and x.dtype == torch.float32 and _Stack.act_dtype(net) != torch.float32 and x.shape[1] == 3 and \
+                (surf_acts is not None or (surf is not None and surf.dtype == torch.float32 and surf.shape[1] <= 6)):
+            # images from the nn.Module API: one pass writes [x | surf | 0] as the 16-channel NHWC operand of the tensor-core conv1 / conv1_s
+            packed = ops.pack_nhwc16(x, None if surf_acts is not None else surf, _Stack.act_dtype(net))
         S: dict = {"x": x, "surf": surf, "skip_in": skip_in, "packed": packed}
         if surf_acts is None:
             surf_acts = _Stack.surface_branch(net, surf, packed)
@@ -149,10 +153,7 @@ class _Stack:
                 if S.get("packed") is not None and S["packed"].dtype == gdt:
                     S["packed_bw"] = S["packed"]
                 else:
-                    xs = S["x"] if S["surf"] is None else torch.cat((S["x"], S["surf"].expand(B, -1, -1, -1)), 1)
-                    pk = torch.zeros((B, xs.shape[2], xs.shape[3], 16), dtype=gdt, device=xs.device).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
-                    pk[:, :xs.shape[1]] = xs
-                    S["packed_bw"] = pk
+                    S["packed_bw"] = ops.pack_nhwc16(S["x"], S["surf"], gdt)
             return S["packed_bw"]
 
         surf_live = S.get("surf_own", False) and (surf_grad_channels is not None or pg is not None)

@@ -255,6 +255,19 @@ def grid_sample_packed(img: Tensor, grid: Tensor, dtype, *, clamp01: bool = Fals
     return out
 
 
+def pack_nhwc16(x: Tensor, surf: Optional[Tensor], dtype) -> Tensor:
+    """[x | surf | 0] as a zero-padded 16-channel NHWC tensor of `dtype` (logical shape [B,16,H,W], channels-last)."""
+    x = _f32c(x)
+    B, Cx, H, W = x.shape
+    Cs, sb = 0, 0
+    if surf is not None:
+        surf = _f32c(surf)
+        Cs, sb = surf.shape[1], _bstride(surf, B)
+    out = torch.empty((B, 16, H, W), dtype=dtype, device=x.device, memory_format=torch.channels_last)
+    lib().spaa_pack_nhwc16(_p(x), Cx, _p(surf), Cs, sb, _p(out), _dt(out), B, H * W, _stream()); _count()
+    return out
+
+
 def select_cotangent_packed(g0: Tensor, g1: Optional[Tensor], sel: Optional[Tensor], act: Optional[Tensor], mask_mode: int, out: Tensor) -> Tensor:
     """select_cotangent for 3-channel images, written as zero-padded 16-channel NHWC (`out`: [B,16,H,W] channels-last)."""
     B, C, H, W = g0.shape

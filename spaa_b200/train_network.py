@@ -127,6 +127,9 @@ class FlatAdam:
         self.t += 1
         row = self.lr_table[min(self.t - 1, self.lr_table.shape[0] - 1)]
         ops.adam_step(self.param, self.grad, self.m, self.v, self.seg_end, row, self.seg_wd, self.t, grad_scale=grad_scale)
+        # the raw kernel updates the parameters without touching their autograd version counters: drop the packed 16-bit copies
+        # of the weights the tensor-core convolutions cache, or the next forward would run on the previous step's weights
+        ops.invalidate_packed_weights()
 
     def lr(self, group: int = 0) -> float:
         return self.lr_table_host[min(self.t, len(self.lr_table_host) - 1)][group]

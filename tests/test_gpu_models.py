@@ -490,3 +490,36 @@ def test_spaa_16bit_free_running_success_rate(precision):
     from spaa_b200.classifier import device_logits
     lg_dev = device_logits(clf, cam, (24, 24))
     assert torch.equal(lg_dev.argmax(1).cpu(), lg_cpu.argmax(1))
+
+
+def test_train_pcnet_bf16_tensor_core_tracks_fp32():
+    """Mixed-precision training (bf16 activations / gradients on tcgen05 incl. the backward-weight kernel, fp32 master weights):
+    the loss trajectory and the parameter update after a few steps stay close to the exact fp32 mode on the same batches
+    (this also guards the packed-weight cache: a stale cache makes the 16-bit run ignore the optimizer)."""
+    from spaa_b200 import models, train_network as tn
+    N, hw, phw = 6, (48, 64), (64, 64)
+    P = synth.pcnet_params(81, hw)
+    prj_train = synth.textured(82, "trb.prj", (N, 3, *phw))
+    scene = synth.textured(83, "trb.scene", (1, 3, *hw))
+    cam_train = synth.textured(84, "trb.cam", (N, 3, *hw))
+    res = {}
+    for prec in ("fp32", "bf16"):
+        wn = models.WarpingNet(out_size=hw)
+        m = models.PCNet(P["mask"], nn.DataParallel(wn), nn.DataParallel(models.ShadingNetSPAA()))
+        m.load_state_dict(P, strict=True)
+        m = nn.DataParallel(models.set_precision(m.to(dev()), prec), device_ids=[0])
+        cfg = tn.AttrDict(device="cuda:0", data_root=None, model_name="PCNet", num_train=N, batch_size=4, max_iters=6, lr=1e-3, lr_drop_ratio=0.2,
+                          lr_drop_rate=800, l2_reg=1e-4, plot_on=False, valid_rate=10 ** 9, iter_offset=401, save_checkpoint=False)
+        random.seed(5)
+        tn.train_pcnet(m, dict(cam_scene=scene, cam_train=cam_train, prj_train=prj_train, mask=P["mask"]), None, cfg, verbose=False)
+        res[prec] = (cfg["loss_history"][:, 0].cpu(), {k: v.detach().cpu().double() for k, v in m.module.state_dict().items()})
+    l32, l16 = res["fp32"][0], res["bf16"][0]
+    print("losses fp32", l32.tolist(), "bf16", l16.tolist())
+    assert (l32[0] - l32[-1]).item() > 1e-3, "fixture must make progress"
+    close(l16, l32, 5e-3, 0, "bf16 loss trajectory")
+    assert abs((l16[0] - l16[-1]).item() - (l32[0] - l32[-1]).item()) < 0.25 * (l32[0] - l32[-1]).item(), "bf16 run does not follow the optimizer"
+    for k in ("shading_net.conv4.weight", "shading_net.conv1_s.weight", "shading_net.conv6.weight", "shading_net.transConv1.weight"):
+        d32 = (res["fp32"][1][k] - P[k].double()).flatten()
+        d16 = (res["bf16"][1][k] - P[k].double()).flatten()
+        cos = torch.nn.functional.cosine_similarity(d32, d16, dim=0).item()
+        assert cos > 0.9, (k, cos)
