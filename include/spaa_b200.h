@@ -254,6 +254,18 @@ int spaa_percal_masks(const float* logits, int ncls, const int64_t* labels, int 
                       uint8_t* use_col, uint8_t* better, float* dis, float* best_dis, spaa_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------------------
+ * Classifier pre-processing (the step on either side of the external classifier): replaces classifier.py:55-59
+ * (centre crop, F.interpolate(mode='area'), ImageNet normalise) and its autograd graph.
+ *   img [B,3,H,W] fp32; crop rectangle (top, left, crop_h, crop_w) per img_proc.py:126-132; out [B,3,out_h,out_w]
+ *   (nhwc = 0) or [B,out_h,out_w,3] (nhwc = 1, what a channels_last cuDNN network reads); host_mean3 / host_std3: HOST float[3].
+ *   bwd: dimg [B,3,H,W] = adjoint applied to dout (zero outside the crop, every element written). Supported resize factors: shrink <= 3x, enlarge <= 2x.
+ * -------------------------------------------------------------------------------------------------------- */
+int spaa_clf_preprocess_fwd(const float* img, int64_t B, int H, int W, int top, int left, int crop_h, int crop_w, int out_h,
+                            int out_w, const float* host_mean3, const float* host_std3, int nhwc, float* out, spaa_stream_t stream);
+int spaa_clf_preprocess_bwd(const float* dout, int64_t B, int H, int W, int top, int left, int crop_h, int crop_w, int out_h,
+                            int out_w, const float* host_std3, int nhwc, float* dimg, spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
  * Optimiser: replaces optim.Adam.step over the parameter groups of train_network.py:253-255,145 with one
  * launch over a flat fp32 buffer split into segments with their own lr / weight decay.
  *   seg_end[nseg] (int64, device): exclusive end offsets; seg_lr / seg_wd [nseg] (float, device)

@@ -11,6 +11,7 @@ import os
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .img_proc import center_crop as cc, expand_4d, resize
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
@@ -26,6 +27,32 @@ def preprocess(im, crop_sz, input_sz):
     x = resize(cc(expand_4d(im), crop_sz), input_sz)
     mean, std = _norm_consts(x.dtype, x.device)
     return (x - mean) / std
+
+
+class _PreprocessFn(torch.autograd.Function):
+    """Fused crop + area resize + normalise (ops.clf_preprocess) with its adjoint as the backward."""
+
+    @staticmethod
+    def forward(ctx, im, crop, out_hw, channels_last):
+        ctx.crop, ctx.hw = crop, (im.shape[2], im.shape[3])
+        return ops.clf_preprocess(im, crop, out_hw, IMAGENET_MEAN, IMAGENET_STD, channels_last)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return ops.clf_preprocess_bwd(dout, ctx.hw, ctx.crop, IMAGENET_MEAN, IMAGENET_STD), None, None, None
+
+
+def preprocess_fused(im, crop_sz, input_sz, channels_last: bool = False):
+    """`preprocess` as one kernel (+ one for the backward) for fp32 CUDA image batches [B,3,H,W]; other inputs use `preprocess`."""
+    h, w = im.shape[-2:]
+    th, tw = int(crop_sz[0]), int(crop_sz[1])
+    ok = (torch.is_tensor(im) and im.is_cuda and im.dim() == 4 and im.shape[1] == 3 and im.dtype == torch.float32 and th <= h and tw <= w
+          and th <= 3 * input_sz[0] and tw <= 3 * input_sz[1] and input_sz[0] <= 2 * th and input_sz[1] <= 2 * tw)
+    if not ok:
+        x = preprocess(im, crop_sz, input_sz)
+        return x.contiguous(memory_format=torch.channels_last) if channels_last else x
+    top, left = int(round((h - th) / 2.0)), int(round((w - tw) / 2.0))          # img_proc.py:126-132
+    return _PreprocessFn.apply(im, (top, left, th, tw), (int(input_sz[0]), int(input_sz[1])), bool(channels_last))
 
 
 _NORM_CACHE = {}
@@ -101,9 +128,7 @@ def device_logits(classifier, im, crop_sz, channels_last: bool = False):
     cuDNN runs its NHWC tensor-core kernels without the per-layer NCHW<->NHWC transposes."""
     model, input_sz = getattr(classifier, "model", None), getattr(classifier, "input_sz", None)
     if model is not None and input_sz is not None:
-        x = preprocess(im, crop_sz, input_sz)
-        if channels_last:
-            x = x.contiguous(memory_format=torch.channels_last)
+        x = preprocess_fused(im, crop_sz, input_sz, channels_last)
         out = model(x)
         return out.logits if hasattr(out, "logits") else out
     return classifier(im, crop_sz)[0]

@@ -1,0 +1,134 @@
+// Classifier pre-processing, fused: centre crop -> area resize -> ImageNet normalise, forward and backward.
+// Replaces /root/reference/src/python/classifier.py:55-59 (cc(), resize() = F.interpolate(mode='area') = adaptive average
+// pooling, the per-sample normalize loop :51) and the autograd graph of those ops (slice backward = zero fill + copy,
+// adaptive_avg_pool2d backward with atomics, two elementwise kernels): 5 + 6 launches become 1 + 1, and the result can be
+// written NHWC so the cuDNN classifier needs no layout conversion of its input.
+//   window of output cell o along an axis of n_in -> n_out cells: [floor(o*n_in/n_out), ceil((o+1)*n_in/n_out))  (ATen)
+#include "common.cuh"
+#include "../../include/spaa_b200.h"
+
+using namespace spaa;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct PreP {
+    int B, H, W;               // image planes [B,3,H,W]
+    int top, left, ch, cw;     // crop rectangle
+    int oh, ow;                // network input size
+    int nhwc;                  // 1: out / dout are [B,oh,ow,3]; 0: [B,3,oh,ow]
+    float mean[3], inv_std[3];
+};
+
+SPAA_D int win_lo(int o, int n_in, int n_out) { return (int)(((int64_t)o * n_in) / n_out); }
+SPAA_D int win_hi(int o, int n_in, int n_out) { return (int)((((int64_t)(o + 1)) * n_in + n_out - 1) / n_out); }
+
+__global__ void __launch_bounds__(kThreads) preprocess_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const PreP p) {
+    const int64_t total = (int64_t)p.B * p.oh * p.ow;
+    const int64_t plane = (int64_t)p.H * p.W;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % p.ow);
+        const int oy = (int)((i / p.ow) % p.oh);
+        const int b = (int)(i / ((int64_t)p.ow * p.oh));
+        const int y0 = win_lo(oy, p.ch, p.oh), y1 = win_hi(oy, p.ch, p.oh);
+        const int x0 = win_lo(ox, p.cw, p.ow), x1 = win_hi(ox, p.cw, p.ow);
+        const float inv_area = 1.f / (float)((y1 - y0) * (x1 - x0));
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* src = img + ((int64_t)b * 3 + c) * plane + (int64_t)p.top * p.W + p.left;
+            float s = 0.f;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) s += __ldg(src + (int64_t)y * p.W + x);
+            v[c] = (s * inv_area - p.mean[c]) * p.inv_std[c];
+        }
+        if (p.nhwc) {
+            float* o = out + i * 3;
+            o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        } else {
+            const int64_t op = (int64_t)p.oh * p.ow;
+            float* o = out + (int64_t)b * 3 * op + (int64_t)oy * p.ow + ox;
+            o[0] = v[0]; o[op] = v[1]; o[2 * op] = v[2];
+        }
+    }
+}
+
+// gather form of the adjoint: every image pixel sums the cells whose window covers it (deterministic, no atomics); pixels
+// outside the crop get an explicit zero, so the caller needs no memset.
+__global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dimg, const PreP p) {
+    const int64_t plane = (int64_t)p.H * p.W;
+    const int64_t total = (int64_t)p.B * plane;
+    const int64_t op = (int64_t)p.oh * p.ow;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % p.W);
+        const int y = (int)((i / p.W) % p.H);
+        const int b = (int)(i / plane);
+        float g[3] = {0.f, 0.f, 0.f};
+        const int cy = y - p.top, cx = x - p.left;
+        if (cy >= 0 && cy < p.ch && cx >= 0 && cx < p.cw) {
+            // candidate cells: around floor(c * n_out / n_in); windows are at most ceil(n_in/n_out)+1 wide
+            const int oyc = (int)(((int64_t)cy * p.oh) / p.ch), oxc = (int)(((int64_t)cx * p.ow) / p.cw);
+            for (int oy = oyc - 1; oy <= oyc + 2; ++oy) {
+                if (oy < 0 || oy >= p.oh) continue;
+                const int y0 = win_lo(oy, p.ch, p.oh), y1 = win_hi(oy, p.ch, p.oh);
+                if (cy < y0 || cy >= y1) continue;
+                for (int ox = oxc - 1; ox <= oxc + 2; ++ox) {
+                    if (ox < 0 || ox >= p.ow) continue;
+                    const int x0 = win_lo(ox, p.cw, p.ow), x1 = win_hi(ox, p.cw, p.ow);
+                    if (cx < x0 || cx >= x1) continue;
+                    const float w = 1.f / (float)((y1 - y0) * (x1 - x0));
+                    if (p.nhwc) {
+                        const float* d = dout + (((int64_t)b * p.oh + oy) * p.ow + ox) * 3;
+                        g[0] += w * __ldg(d); g[1] += w * __ldg(d + 1); g[2] += w * __ldg(d + 2);
+                    } else {
+                        const float* d = dout + (int64_t)b * 3 * op + (int64_t)oy * p.ow + ox;
+                        g[0] += w * __ldg(d); g[1] += w * __ldg(d + op); g[2] += w * __ldg(d + 2 * op);
+                    }
+                }
+            }
+        }
+        float* o = dimg + (int64_t)b * 3 * plane + (int64_t)y * p.W + x;
+        o[0] = g[0] * p.inv_std[0]; o[plane] = g[1] * p.inv_std[1]; o[2 * plane] = g[2] * p.inv_std[2];
+    }
+}
+
+int fill(PreP& p, int64_t B, int H, int W, int top, int left, int ch, int cw, int oh, int ow, const float* mean, const float* stdv, int nhwc) {
+    if (!(B > 0 && B < (1 << 24) && H > 0 && W > 0 && ch > 0 && cw > 0 && oh > 0 && ow > 0 && top >= 0 && left >= 0 && top + ch <= H && left + cw <= W && mean && stdv)) return 0;
+    // the candidate search of the backward covers cells centre-1 .. centre+2: shrink by at most 3x, enlarge by at most 2x
+    if (ch > 3 * oh || cw > 3 * ow || oh > 2 * ch || ow > 2 * cw) return 0;
+    p.B = (int)B; p.H = H; p.W = W; p.top = top; p.left = left; p.ch = ch; p.cw = cw; p.oh = oh; p.ow = ow; p.nhwc = nhwc;
+    for (int c = 0; c < 3; ++c) { p.mean[c] = mean[c]; p.inv_std[c] = 1.f / stdv[c]; }
+    return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spaa_clf_preprocess_fwd(const float* img, int64_t B, int H, int W, int top, int left, int crop_h, int crop_w, int out_h, int out_w,
+                            const float* host_mean3, const float* host_std3, int nhwc, float* out, spaa_stream_t stream) {
+    PreP p;
+    SPAA_CHECK_ARG(img && out && fill(p, B, H, W, top, left, crop_h, crop_w, out_h, out_w, host_mean3, host_std3, nhwc), "spaa_clf_preprocess_fwd: bad arguments");
+    const int64_t total = B * out_h * out_w;
+    int64_t blocks = (total + kThreads - 1) / kThreads;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    preprocess_fwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(img, out, p);
+    SPAA_CHECK_LAUNCH("spaa_clf_preprocess_fwd");
+    return SPAA_OK;
+}
+
+int spaa_clf_preprocess_bwd(const float* dout, int64_t B, int H, int W, int top, int left, int crop_h, int crop_w, int out_h, int out_w,
+                            const float* host_std3, int nhwc, float* dimg, spaa_stream_t stream) {
+    PreP p;
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    SPAA_CHECK_ARG(dout && dimg && fill(p, B, H, W, top, left, crop_h, crop_w, out_h, out_w, zero3, host_std3, nhwc), "spaa_clf_preprocess_bwd: bad arguments");
+    const int64_t total = B * (int64_t)H * W;
+    int64_t blocks = (total + kThreads - 1) / kThreads;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    preprocess_bwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(dout, dimg, p);
+    SPAA_CHECK_LAUNCH("spaa_clf_preprocess_bwd");
+    return SPAA_OK;
+}
+
+}  // extern "C"

@@ -662,3 +662,39 @@ def percal_masks(logits: Tensor, labels: Tensor, mode: int, margin: float, l2sum
     B, ncls = logits.shape
     lib().spaa_percal_masks(_p(logits), ncls, _p(labels), mode, float(margin), _p(l2sum), hw, float(d_thr), float(p_thresh), _p(stats), B,
                             _p(isadv), _p(use_col), _p(better), _p(dis), _p(best_dis), _stream()); _count()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# classifier pre-processing (fused crop + area resize + normalise)
+# ------------------------------------------------------------------------------------------------------------
+
+def _f3(v):
+    return (ctypes.c_float * 3)(*[float(t) for t in v])
+
+
+def clf_preprocess(img: Tensor, crop, out_hw, mean, std, channels_last: bool) -> Tensor:
+    """Returns the network input as a logical [B,3,h,w] tensor (NCHW, or channels-last memory when `channels_last`)."""
+    img = _f32c(img)
+    B, C, H, W = img.shape
+    assert C == 3
+    top, left, ch, cw = crop
+    if channels_last:
+        out = torch.empty((B, out_hw[0], out_hw[1], 3), dtype=torch.float32, device=img.device)
+    else:
+        out = torch.empty((B, 3, out_hw[0], out_hw[1]), dtype=torch.float32, device=img.device)
+    lib().spaa_clf_preprocess_fwd(_p(img), B, H, W, top, left, ch, cw, out_hw[0], out_hw[1], _f3(mean), _f3(std), int(channels_last), _p(out), _stream()); _count()
+    return out.permute(0, 3, 1, 2) if channels_last else out
+
+
+def clf_preprocess_bwd(dout: Tensor, img_hw, crop, mean, std) -> Tensor:
+    """dout: logical [B,3,h,w], NCHW-contiguous or channels-last; returns d/d(img) [B,3,H,W] (zero outside the crop)."""
+    if dout.dtype != torch.float32:
+        dout = dout.float()
+    nhwc = dout.is_contiguous(memory_format=torch.channels_last) and not dout.is_contiguous()
+    if not nhwc and not dout.is_contiguous():
+        dout = dout.contiguous()
+    B, _, oh, ow = dout.shape
+    top, left, ch, cw = crop
+    dimg = torch.empty((B, 3, img_hw[0], img_hw[1]), dtype=torch.float32, device=dout.device)
+    lib().spaa_clf_preprocess_bwd(_p(dout), B, img_hw[0], img_hw[1], top, left, ch, cw, oh, ow, _f3(std), int(nhwc), _p(dimg), _stream()); _count()
+    return dimg

@@ -393,3 +393,29 @@ def test_attack_masks():
     ops.percal_masks(logits.to(dev()), target.to(dev()), 2, 40.0, l2sum.to(dev()), hw, 5.0, 0.9, stats.to(dev()), ia, u, bt, dis, bd)
     assert torch.equal(ia.cpu().bool(), isadv) and torch.equal(u.cpu().bool(), use)
     close(dis, stats[:, 2].sqrt(), 1e-6, 1e-6, "dis")
+
+
+@pytest.mark.parametrize("hw,crop,insz", [((240, 320), (240, 240), (224, 224)), ((240, 320), (240, 240), (299, 299)), ((24, 32), (24, 24), (20, 20)),
+                                          ((30, 41), (27, 33), (11, 40))])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fused_classifier_preprocess_vs_oracle(hw, crop, insz, channels_last):
+    """classifier.py:55-59 (centre crop, area resize, normalise) as one kernel, and its adjoint, against the oracle + autograd."""
+    from spaa_b200 import ops
+    from spaa_b200.classifier import preprocess_fused
+    B = 3
+    im = synth.rand(51, "pre.im", (B, 3, *hw))
+    ref_in = im.clone().double().requires_grad_(True)
+    ref = O.classifier_preprocess(ref_in, crop, insz)
+    cot = synth.randn(52, "pre.cot", ref.shape).double()
+    gref, = torch.autograd.grad((ref * cot).sum(), ref_in)
+    x = im.to(dev()).requires_grad_(True)
+    n0 = ops.launch_count()
+    y = preprocess_fused(x, crop, insz, channels_last)
+    assert ops.launch_count() == n0 + 1, "the fused kernel was not used"
+    assert y.shape == ref.shape and (y.is_contiguous(memory_format=torch.channels_last) if channels_last else y.is_contiguous())
+    close(y, ref, 2e-6, 1e-6, "preprocess forward")
+    c = cot.float().to(dev())
+    if channels_last:
+        c = c.contiguous(memory_format=torch.channels_last)
+    (y * c).sum().backward()
+    close(x.grad, gref, 1e-6, 1e-5, "preprocess backward")
