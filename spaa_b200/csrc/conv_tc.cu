@@ -331,6 +331,9 @@ struct HaloParams {
     int32_t tiles_x, tiles_y, total_tiles, kchunks;
     int32_t a_plane_bytes, a_stage_bytes, a_tx_bytes, b_slice_bytes;
     int32_t sa, sb, resident, nslots, use_base_off, ntap_total;
+    int32_t ctas_per_sm;
+    int32_t e_stage_bytes;             // output staging blocks of the 4 epilogue warps (16-bit NHWC output only)
+    int32_t e_slots, e_nops;           // epilogue operand ring: slots of e_nops x 8 KB (0 slots: no ring)
     uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
     int32_t epi_flags, out_planar;
     int64_t add_bs, mask_bs;
@@ -355,7 +358,7 @@ template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint
 }
 
 template <int BN, int BK, bool F16>
-__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+__global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ HaloParams P) {
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -364,7 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     uint8_t* a_ring = smem;
     uint8_t* b_base = smem + (size_t)SA * P.a_stage_bytes;
     const size_t b_bytes = P.resident ? (size_t)P.kchunks * P.nslots * P.b_slice_bytes : (size_t)SB * P.b_slice_bytes;
-    uint64_t* bars = (uint64_t*)(b_base + b_bytes);
+    uint8_t* e_ring = b_base + b_bytes;            // epilogue operand ring (see the epilogue)
+    uint64_t* bars = (uint64_t*)(e_ring + (size_t)P.e_slots * P.e_nops * 8192 + P.e_stage_bytes);
     uint64_t* a_full = bars;                       // [SA]
     uint64_t* a_empty = a_full + 8;                // [SA]
     uint64_t* b_full = a_empty + 8;                // [SB] (b_full[0] doubles as the "resident weights loaded" barrier)
@@ -496,15 +500,96 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         __syncwarp();
     } else {
         // ===================================== epilogue ============================================
-        // Operands that do not depend on the accumulator (residual, ReLU masks) are fetched one 32-channel chunk AHEAD of
-        // the TMEM read that needs them -- and for the first chunk of a tile before the wait for its MMAs -- so their
-        // global-memory latency is not paid once per chunk in series.
+        // Operands that do not depend on the accumulator (residual, ReLU masks) are streamed through a per-warp cp.async ring
+        // in shared memory, S-1 (tile, phase, 32-channel chunk) units AHEAD of the unit being written.  The first version fetched
+        // them one chunk ahead into registers, so every tile paid one exposed global-memory latency in series (conv6 backward:
+        // 1.4 us per 128-pixel tile = 30 % of HBM roofline), and every lane touched its own pixel row: 32 cache lines per
+        // 128-bit load / store instruction (ncu: 32 sectors per request, L1 wavefronts at 50-58 % of peak on conv5 backward).
+        // Now a warp moves its 32 rows x 64 B cooperatively -- instruction k covers rows 8k..8k+7 (8 consecutive x pixels), four
+        // lanes per row -- for the operand copies and, through a 2 KB staging block, for the output stores.  A warp copies and
+        // reads only ITS OWN 32 rows, so cp.async.wait_group + __syncwarp is all the synchronisation the ring needs.
+        // Block layout: [row][16-byte chunk c ^ ((row >> 1) & 3)] (conflict-free for the row-wise and the cooperative accesses).
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int j = row >> 3, i = row & 7;
         const int ef = P.epi_flags;
         const bool has_add = P.add != nullptr, has_mask = P.mask != nullptr, has_out2 = P.out2 != nullptr;
+        const bool planar = P.out_planar != 0;
+        constexpr int NCH = BN / 32;
+        const int nchu = planar ? 1 : NCH;                       // prefetch units per (tile, phase)
+        const int S = P.e_slots;                                 // 0: no ring (no operand / wide planar residual)
+        const uint32_t slot_bytes = (uint32_t)P.e_nops * 8192u;
+        const int ci = lane >> 2, cc = lane & 3;                 // cooperative mapping: x pixel within the row group, 16-byte chunk
+        const uint32_t e_warp = smem_u32(e_ring) + (uint32_t)q * 2048u;
+        uint32_t own_off[4], coop_off[4];                        // byte offsets inside a 2 KB warp block
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            own_off[g] = (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) * 16);
+            const int rk = 8 * g + ci;
+            coop_off[g] = (uint32_t)rk * 64u + (uint32_t)((cc ^ ((rk >> 1) & 3)) * 16);
+        }
+        const uint32_t o_stage = smem_u32(e_ring) + (uint32_t)S * slot_bytes + (uint32_t)q * 4096u;     // [out | out2] staging of this warp
+        const uint32_t e_row4 = smem_u32(e_ring) + (uint32_t)row * 4u;       // fp32 planar residual: [channel][row]
         struct Ops { uint4 a[4], m[4], m2[4]; };
+
+        int pf_tile = blockIdx.x, pf_ph = 0, pf_c = 0, pf_slot = 0, pf_b = 0, pf_ty = 0, pf_tx = 0;
+        auto pf_locate = [&]() {
+            if (pf_tile < P.total_tiles) {
+                pf_b = pf_tile / per_img;
+                const int t = pf_tile - pf_b * per_img;
+                pf_ty = t / P.tiles_x; pf_tx = t - pf_ty * P.tiles_x;
+            }
+        };
+        pf_locate();
+        auto issue = [&]() {
+            if (pf_tile < P.total_tiles) {
+                const int oy = (pf_ty * HTH + j) * P.up + P.ph[pf_ph].py, ox = (pf_tx * HTW + i) * P.up + P.ph[pf_ph].px;
+                if (oy < P.Hout && ox < P.Wout) {
+                    if (planar) {
+                        const int64_t hw = (int64_t)P.Hout * P.Wout;
+                        const float* ap = (const float*)P.add + (int64_t)pf_b * P.add_bs + (int64_t)oy * P.Wout + ox;
+                        const uint32_t d = e_row4 + (uint32_t)pf_slot * slot_bytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (k < P.Cout) cp_async4(d + k * 512, ap + k * hw);
+                    }
+                }
+                if (!planar && pf_c * 32 < P.Cout) {
+                    const int cox = (pf_tx * HTW + ci) * P.up + P.ph[pf_ph].px;
+                    const int coy0 = (pf_ty * HTH + q * 4) * P.up + P.ph[pf_ph].py;
+                    if (cox < P.Wout) {
+                        const int64_t pix0 = ((int64_t)coy0 * P.Wout + cox) * P.Cout + pf_c * 32 + cc * 8;
+                        const int64_t kstep = (int64_t)P.up * P.Wout * P.Cout;
+                        uint32_t d = e_warp + (uint32_t)pf_slot * slot_bytes;
+                        if (has_add) {
+                            const uint16_t* sp = (const uint16_t*)P.add + (int64_t)pf_b * P.add_bs + pix0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
+                            d += 8192;
+                        }
+                        if (has_mask) {
+                            const uint16_t* sp = P.mask + (int64_t)pf_b * P.mask_bs + pix0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
+                            d += 8192;
+                        }
+                        if (has_out2) {
+                            const uint16_t* sp = P.mask2 + (int64_t)pf_b * P.mask_bs + pix0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
+                        }
+                    }
+                }
+                if (++pf_c == nchu) {
+                    pf_c = 0;
+                    if (++pf_ph == NPH) { pf_ph = 0; pf_tile += gridDim.x; pf_locate(); }
+                }
+                if (++pf_slot == S) pf_slot = 0;
+            }
+            cp_async_commit();
+        };
+        if (S) for (int d = 0; d < S - 1; ++d) issue();
+        int cs = 0;                                              // ring slot of the unit being consumed
+
         int local = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
             const int b = tile / per_img;
@@ -516,16 +601,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             for (int ph = 0; ph < NPH; ++ph) {
                 const int oy = (ty * HTH + j) * P.up + P.ph[ph].py, ox = (tx * HTW + i) * P.up + P.ph[ph].px;
                 const bool valid = oy < P.Hout && ox < P.Wout;
-                const int64_t pix = ((int64_t)oy * P.Wout + ox) * P.Cout;
-                const int64_t o_off = (int64_t)b * P.Hout * P.Wout * P.Cout + pix;
-                if (P.out_planar) {
+                if (planar) {
                     // fp32 NCHW planes, Cout (<= 32) real channels: conv6 forward, conv1 / conv1_s backward-data
                     const int64_t hw = (int64_t)P.Hout * P.Wout;
                     const int64_t p = (int64_t)oy * P.Wout + ox;
                     float* op = (float*)P.out + (int64_t)b * P.Cout * hw + p;
                     const float* ap = has_add ? (const float*)P.add + (int64_t)b * P.add_bs + p : nullptr;
                     float av[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid && ap && P.Cout <= 4) {
+                    if (S) {
+                        cp_async_wait(S - 2);
+                        if (valid) {
+                            const uint32_t sa4 = e_row4 + (uint32_t)cs * slot_bytes;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (k < P.Cout) av[k] = lds32f(sa4 + k * 512);
+                        }
+                        issue();
+                        if (++cs == S) cs = 0;
+                    } else if (valid && ap && P.Cout <= 4) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) if (k < P.Cout) av[k] = __ldg(ap + k * hw);
                     }
@@ -557,34 +649,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                     }
                     continue;
                 }
-                auto fetch = [&](int c0, Ops& o) {
-                    if (!valid || c0 >= P.Cout) return;
-                    if (has_add) {
-                        const uint4* ap = reinterpret_cast<const uint4*>((const uint16_t*)P.add + (int64_t)b * P.add_bs + pix + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) o.a[g] = __ldg(ap + g);
-                    }
-                    if (has_mask) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask + (int64_t)b * P.mask_bs + pix + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) o.m[g] = __ldg(mp + g);
-                    }
-                    if (has_out2) {
-                        const uint4* mp = reinterpret_cast<const uint4*>(P.mask2 + (int64_t)b * P.mask_bs + pix + c0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) o.m2[g] = __ldg(mp + g);
-                    }
-                };
-                Ops cur, nxt;
-                fetch(0, cur);
-                if (!waited) { mbar_wait(tfull + acc, (local >> 1) & 1); tc_fence_after(); waited = true; }
-#pragma unroll
+                // cooperative store mapping of this (tile, phase): instruction k writes rows 8k..8k+7 of the warp
+                const int cox = (tx * HTW + ci) * P.up + P.ph[ph].px;
+                const int coy0 = (ty * HTH + q * 4) * P.up + P.ph[ph].py;
+                const int64_t co_off = (int64_t)b * P.Hout * P.Wout * P.Cout + ((int64_t)coy0 * P.Wout + cox) * P.Cout + cc * 8;
+                const int64_t kstep = (int64_t)P.up * P.Wout * P.Cout;
+                const bool cox_ok = cox < P.Wout;
+                // NOT unrolled: with the chunk loop unrolled the BN = 256 kernel was 10 400 SASS instructions and its epilogue warps
+                // (one per scheduler, nothing to hide a miss behind) spent 39 % of their samples in instruction-fetch stalls (ncu)
+#pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
+                    Ops cur;
+                    if (S) {
+                        cp_async_wait(S - 2);
+                        __syncwarp();
+                        if (c0 < P.Cout) {
+                            uint32_t sa16 = e_warp + (uint32_t)cs * slot_bytes;
+                            if (has_add) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) cur.a[g] = lds128(sa16 + own_off[g]);
+                                sa16 += 8192;
+                            }
+                            if (has_mask) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) cur.m[g] = lds128(sa16 + own_off[g]);
+                                sa16 += 8192;
+                            }
+                            if (has_out2) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) cur.m2[g] = lds128(sa16 + own_off[g]);
+                            }
+                        }
+                        issue();
+                        if (++cs == S) cs = 0;
+                    }
+                    if (!waited) { mbar_wait(tfull + acc, (local >> 1) & 1); tc_fence_after(); waited = true; }
                     uint32_t r[32];
-                    tmem_ld32_nowait(t_row + (uint32_t)(ph * BN + c0), r);
-                    if (c0 + 32 < BN) fetch(c0 + 32, nxt);
-                    tmem_wait_ld();
-                    if (valid && c0 < P.Cout) {
+                    tmem_ld32(t_row + (uint32_t)(ph * BN + c0), r);
+                    if (c0 < P.Cout) {
                         float v[32];
 #pragma unroll
                         for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]) + s_bias[c0 + k];
@@ -614,16 +716,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
                                 }
                             }
                         }
-                        uint4* op = reinterpret_cast<uint4*>((uint16_t*)P.out + o_off + c0);
+                        // own row -> staging block (row-wise), then the warp stores it cooperatively
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 u;
-                            u.x = pack2<F16>(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack2<F16>(v[g * 8 + 2], v[g * 8 + 3]);
-                            u.z = pack2<F16>(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack2<F16>(v[g * 8 + 6], v[g * 8 + 7]);
-                            op[g] = u;
-                        }
+                        for (int g = 0; g < 4; ++g)
+                            sts128(o_stage + own_off[g], make_uint4(pack2<F16>(v[g * 8 + 0], v[g * 8 + 1]), pack2<F16>(v[g * 8 + 2], v[g * 8 + 3]),
+                                                                    pack2<F16>(v[g * 8 + 4], v[g * 8 + 5]), pack2<F16>(v[g * 8 + 6], v[g * 8 + 7])));
                         if (has_out2) {
-                            uint4* op2 = reinterpret_cast<uint4*>((uint16_t*)P.out2 + o_off + c0);
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 const uint32_t w4[4] = {cur.m2[g].x, cur.m2[g].y, cur.m2[g].z, cur.m2[g].w};
@@ -631,17 +729,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
                                     o4[e] = pack2<F16>(pos16(w4[e] & 0xFFFFu) ? v[g * 8 + e * 2] : 0.f, pos16(w4[e] >> 16) ? v[g * 8 + e * 2 + 1] : 0.f);
-                                op2[g] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+                                sts128(o_stage + 2048u + own_off[g], make_uint4(o4[0], o4[1], o4[2], o4[3]));
                             }
                         }
+                        __syncwarp();
+                        if (cox_ok) {
+                            uint16_t* op = (uint16_t*)P.out + co_off + c0;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (coy0 + k * P.up < P.Hout) *reinterpret_cast<uint4*>(op + k * kstep) = lds128(o_stage + coop_off[k]);
+                            if (has_out2) {
+                                uint16_t* op2 = (uint16_t*)P.out2 + co_off + c0;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (coy0 + k * P.up < P.Hout) *reinterpret_cast<uint4*>(op2 + k * kstep) = lds128(o_stage + 2048u + coop_off[k]);
+                            }
+                        }
+                        __syncwarp();                                    // the staging block is rewritten by the next chunk
                     }
-                    if (c0 + 32 < BN) cur = nxt;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
         }
+        cp_async_wait(0);
     }
     tc_fence_before();
     __syncthreads();
@@ -722,9 +834,11 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& 
             set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
             return SPAA_ERR_CUDA;
         }
+        cudaFuncSetAttribute(conv_halo_kernel<BN, BK, F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         reserved = smem_bytes;
     }
-    const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
+    const int slots = kNumSMs * P.ctas_per_sm;
+    const int grid = P.total_tiles < slots ? P.total_tiles : slots;
     conv_halo_kernel<BN, BK, F16><<<grid, kThreads, smem_bytes, st>>>(ma, mb, P);
     return SPAA_OK;
 }
@@ -806,20 +920,49 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     P.a_plane_bytes = (P.halo_h * P.halo_w * rowb + 1023) & ~1023;
     P.a_stage_bytes = P.nplanes * P.a_plane_bytes;
     P.b_slice_bytes = BN * rowb;
-    const int budget = 200 * 1024;
+    // ---- shared-memory plan.  Layers whose accumulator is narrow (BN <= 64: the HBM-bound ones) run TWO CTAs per SM when two
+    // TMEM allocations and two half-size rings fit: twice the epilogue warps and loads in flight per SM.
+    const bool planar = d->out_dtype == 0;
+    P.e_nops = planar ? ((add && d->Cout <= 4) ? 1 : 0) : ((add ? 1 : 0) + (mask ? 1 : 0) + (mask2 ? 1 : 0));
+    P.e_stage_bytes = planar ? 0 : 4 * 4096;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2u * (uint32_t)(nph * BN)) tmem_cols <<= 1;
+    static const int max_ctas = [] { const char* e = getenv("SPAA_TC_CTAS"); return e ? atoi(e) : 2; }();
+    static const int e_kb = [] { const char* e = getenv("SPAA_TC_EKB"); return e ? atoi(e) : -1; }();
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
-    P.resident = res_bytes <= 80 * 1024 ? 1 : 0;
-    int64_t bbytes;
-    if (P.resident) { bbytes = res_bytes; P.sb = 1; }
-    else {
-        P.sb = P.b_slice_bytes <= 16 * 1024 ? 6 : 4;
-        while (P.sb > 2 && (int64_t)P.sb * P.b_slice_bytes + 2 * (int64_t)P.a_stage_bytes > budget) --P.sb;
-        bbytes = (int64_t)P.sb * P.b_slice_bytes;
+    int ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
+    size_t smem_bytes = 0;
+    for (;; --ctas) {
+        const int total = ctas == 2 ? 108 * 1024 : 222 * 1024;
+        P.resident = res_bytes <= (ctas == 2 ? 40 : 80) * 1024 ? 1 : 0;
+        P.e_slots = 0;
+        if (P.e_nops) {
+            const int eb = (e_kb >= 0 ? e_kb : (ctas == 2 ? 32 : (P.resident ? 48 : 32))) * 1024;
+            const int sl = eb / (P.e_nops * 8192);
+            P.e_slots = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
+        }
+        const int budget = total - P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
+        int64_t bbytes, sa;
+        if (P.resident) {
+            bbytes = res_bytes; P.sb = 1;
+            sa = (budget - bbytes) / P.a_stage_bytes;
+        } else {
+            // streamed weights: one A stage feeds KH*KW*BK/16 MMAs but one weight slice only BK/16 -- the depth belongs to the B ring
+            sa = 2;
+            const int64_t sbn = (budget - 2 * (int64_t)P.a_stage_bytes) / P.b_slice_bytes;
+            P.sb = (int)(sbn > 8 ? 8 : sbn);
+            if (P.sb < 2) sa = 0;
+            bbytes = (int64_t)P.sb * P.b_slice_bytes;
+        }
+        if (sa < 2) {
+            if (ctas == 1) return SPAA_ERR_UNSUPPORTED;
+            continue;
+        }
+        P.sa = (int)(sa > 6 ? 6 : sa);
+        smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
+        break;
     }
-    int64_t sa = (budget - bbytes) / P.a_stage_bytes;
-    if (sa < 2) return SPAA_ERR_UNSUPPORTED;
-    P.sa = (int)(sa > 6 ? 6 : sa);
-    const size_t smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + kHaloBarBytes + BN * 4 + 1024;
+    P.ctas_per_sm = ctas;
 
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -95,6 +95,41 @@ SPAA_D void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
 }
 SPAA_D void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// per-thread asynchronous global -> shared copies (LDGSTS): the epilogue's operand prefetch ring
+SPAA_D void cp_async16(uint32_t smem_addr, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+SPAA_D void cp_async4(uint32_t smem_addr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+SPAA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n of this thread's most recent groups are still in flight (n is a run-time value in [0, 7])
+SPAA_D void cp_async_wait(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+SPAA_D uint4 lds128(uint32_t smem_addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+    return v;
+}
+SPAA_D void sts128(uint32_t smem_addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SPAA_D float lds32f(uint32_t smem_addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr) : "memory");
+    return v;
+}
+
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

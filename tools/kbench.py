@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--markdown", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="one forward + backward of the conv stack between cudaProfilerStart/Stop "
+                    "(ncu --profile-from-start off), no timing")
     args = ap.parse_args()
     import synth
     from spaa_b200 import models, ops
@@ -67,6 +69,19 @@ def main():
         bench("grid_sample_fwd_packed", lambda: ops.grid_sample_packed(prj, grid, adt, clamp01=True, mask=mask, rough=scene, out=packed),
               nbytes=B * (3 * PHW * 4 + 16 * HW * 2))
         cam, S = _Stack.forward(sh, None, None, None, skip_acts=skip, packed=packed)
+        if args.profile:
+            ops.grid_sample_packed(prj, grid, adt, clamp01=True, mask=mask, rough=scene, out=packed)
+            d_pk = torch.empty((B, 16, *CAM), dtype=gdt, device=dev, memory_format=torch.channels_last).zero_()
+            d_pk[:, :3].normal_()
+            for rep in range(3):
+                if rep == 2:
+                    torch.cuda.synchronize(); flush.zero_(); torch.cuda.synchronize()
+                    torch.cuda.profiler.start()
+                cam, S = _Stack.forward(sh, None, None, None, skip_acts=skip, packed=packed)
+                _Stack.backward(sh, S, None, need_dx=True, surf_grad_channels=(3, 6), d_pre6_packed=d_pk)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return
         sp = sh._specs
         W = lambda n: (getattr(sh, n).weight, getattr(sh, n).bias)
         esz = 2
