@@ -159,9 +159,12 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def config_dict(n_gpus: int, precision: str):
+def config_dict(n_gpus: int, precision: str, fold_bn: bool = False):
     return {"workload": "spaa_attack resnet18 B=32 targets/GPU, prj 256x256, cam 240x320, camdE_caml2 d_thr=5 (BASELINE configs[1])",
-            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "precision": precision, "classifier": "torchvision resnet18 (cuDNN, external operand)",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "precision": precision,
+            "classifier": "torchvision resnet18 (cuDNN, external operand, channels_last, TF32 as torch defaults"
+                          + ("; inference-mode BatchNorm folded into the preceding cuDNN convolutions in a private copy, see side leg stock_classifier)"
+                             if fold_bn else ")"),
             "l2": "per-iteration working set (~3 GB of activations at B=32) is far larger than the 126 MB L2; no explicit flush",
             "parallelism": f"{n_gpus} independent attack jobs, no collective"}
 
@@ -276,7 +279,8 @@ def run_ours(args):
     clf = make_classifier(dev)
 
     # the engine spaa() itself would build for this job (kept warm across calls of a sweep: buffers + captured CUDA graph)
-    A = attack_engine(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=not args.no_graph)
+    fold_bn = not args.no_fold_bn and args.precision != "fp32"
+    A = attack_engine(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=not args.no_graph, fold_bn=fold_bn)
     for _ in range(args.warmup):                            # 2 eager iterations, then the CUDA graph is captured and replayed
         A.step()
     torch.cuda.synchronize()
@@ -307,7 +311,7 @@ def run_ours(args):
 
     # ---- roofline kernel: the same K iterations re-run WITHOUT graph replay so that every launch of the dominant kernel family
     # (conv4 / conv4_s / conv5 forward + backward-data) can be bracketed by a CUDA-event pair on the launching stream --------------
-    Ap = SpaaAttack(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=False)
+    Ap = SpaaAttack(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=False, fold_bn=fold_bn)
     for _ in range(3):
         Ap.step()
     probe = ops.set_probe(lambda kind, spec: spec.k == 3 and {spec.cin, spec.cout} == {128, 256})
@@ -323,7 +327,7 @@ def run_ours(args):
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     for _ in range(5):
-        _adv_grad(clf, A.cam, CROP, A.target, True, A.clf_cl)
+        _adv_grad(A.classifier, A.cam, CROP, A.target, True, A.clf_cl)
     c1.record()
     torch.cuda.synchronize()
     clf_ms = c0.elapsed_time(c1) / 5
@@ -335,7 +339,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     cam_best, prj_best = spaa(pcnet, clf, None, targets, True, scene_host.to(dev, non_blocking=True), D_THR, STEALTH, dev, SETUP, iters=args.steps,
-                              graph=not args.no_graph)
+                              graph=not args.no_graph, fold_bn=fold_bn)
     out_cam.copy_(cam_best, non_blocking=True)
     out_prj.copy_(prj_best, non_blocking=True)
     torch.cuda.synchronize()
@@ -367,7 +371,7 @@ def run_ours(args):
     achieved = flop / (k_ms * 1e-3) / 1e12 if k_ms else 0.0
     line = {"metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world, args.precision),
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world, args.precision, fold_bn),
             "sample_iters_per_sec": its * BATCH, "classifier_ms_per_step": clf_ms,
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
@@ -384,6 +388,19 @@ def run_ours(args):
     if world == 1 and not args.skip_side_legs:
         # side legs (not the headline): the exact fp32 mode of the same engine, and the reference algorithm on stock PyTorch-CUDA ops
         # (cuDNN TF32 convolutions + ~1.3k ATen kernels per iteration = what the reference executes on a GPU), same batch, same box
+        if fold_bn:
+            As = SpaaAttack(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, fold_bn=False)
+            ns = max(5, min(args.steps, 20))
+            for _ in range(3):
+                As.step()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); f0.record()
+            for _ in range(ns):
+                As.step()
+            f1.record(); torch.cuda.synchronize()
+            line["stock_classifier"] = {"value": ns / (f0.elapsed_time(f1) / 1e3), "unit": "it/s", "steps": ns,
+                                        "note": "same engine and CUDA-graph replay with the classifier's BatchNorm layers left unfolded (the stock module)"}
+            del As
         if args.precision != "fp32":
             models.set_precision(pcnet, "fp32")
             A32 = SpaaAttack(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP)
@@ -431,6 +448,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--skip-train", action="store_true", help="omit the PCNet training leg")
     ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--no-fold-bn", action="store_true", help="run the external classifier as the stock module (BatchNorm layers not folded)")
     ap.add_argument("--skip-side-legs", action="store_true", help="profiling runs only: omit the fp32 and torch-CUDA side measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     args = ap.parse_args()

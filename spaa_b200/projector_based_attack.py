@@ -17,7 +17,7 @@ from typing import List, Optional
 import torch
 
 from . import ops
-from .classifier import device_logits, use_channels_last
+from .classifier import device_logits, fold_batchnorm, use_channels_last
 from .img_proc import expand_4d
 from .models import PCNet, _Stack, set_precision
 from .ops import MASK_OPEN01
@@ -44,11 +44,14 @@ class SpaaAttack:
     `SpaaAttack(...)`, `iters` x `step()`, `result()`; bench.py drives `step()` directly to time exactly K iterations."""
 
     def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
-                 graph: Optional[bool] = None):
+                 graph: Optional[bool] = None, fold_bn: Optional[bool] = None):
         """graph: replay one captured CUDA graph per iteration (default: on for the fused PCNet path).  An iteration is a fixed
         sequence of ~80 of our launches + ~300 cuDNN/ATen launches of the external classifier with no host decision in
         between, so after two eager iterations (which fill the packed-weight / workspace caches) the third is captured and
-        every later step() is a single cudaGraphLaunch."""
+        every later step() is a single cudaGraphLaunch.
+        fold_bn: run the frozen external classifier through a private copy with its inference-mode BatchNorm layers folded into
+        the preceding cuDNN convolutions (classifier.fold_batchnorm).  Default (None): on exactly when cuDNN may use TF32
+        (torch's default, the reference's setting) -- i.e. off in the exact-fp32 parity mode, like the channels_last layout."""
         device = torch.device(device)
         if precision is not None:
             set_precision(_unwrap(pcnet), precision)
@@ -109,6 +112,9 @@ class SpaaAttack:
         self.scene_b = scene.expand(B, -1, -1, -1)
         self.cam = self.logits = None
         self.clf_cl = use_channels_last(classifier) if device.type == "cuda" else False
+        self.fold_bn = bool(torch.backends.cudnn.allow_tf32) if fold_bn is None else bool(fold_bn)
+        if self.fold_bn:
+            self.classifier = fold_batchnorm(classifier)
         self.use_graph = self.fused if graph is None else (bool(graph) and self.fused)
         self._graph, self._n_eager = None, 0
 
@@ -244,25 +250,26 @@ def _state_version(module) -> int:
 
 
 def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
-                  graph: Optional[bool] = None) -> SpaaAttack:
+                  graph: Optional[bool] = None, fold_bn: Optional[bool] = None) -> SpaaAttack:
     """A SpaaAttack for this job.  Sweeps call spaa() many times with the same model, classifier, batch size and loss
     configuration (run_projector_based_attack, projector_based_attack.py:83-129): the engine -- its buffers and its captured
     CUDA graph -- is kept (LRU of 2) and only reset() for the new scene / targets.  A model whose parameters changed in
     between (version counters) gets a new engine."""
     net = _unwrap(pcnet)
     if not isinstance(net, PCNet) or graph is False:
-        return SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph)
+        return SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph,
+                          fold_bn=fold_bn)
     if precision is not None:
         set_precision(net, precision)
     scene_shape = tuple(expand_4d(cam_scene).shape)
     key = (id(net), _state_version(net), id(getattr(classifier, "model", classifier)), len(target_idx), bool(targeted), stealth_loss, float(d_thr),
            tuple(setup_info["classifier_crop_sz"]), tuple(setup_info["prj_im_sz"]), float(setup_info["prj_brightness"]), scene_shape,
-           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32))
+           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32), fold_bn)
     hit = _ENGINES.get(key)
     if hit is not None and hit[0]() is net and hit[1]() is getattr(classifier, "model", classifier):
         _ENGINES.move_to_end(key)
         return hit[2].reset(cam_scene, target_idx)
-    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, graph=graph)
+    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, graph=graph, fold_bn=fold_bn)
     try:
         _ENGINES[key] = (weakref.ref(net), weakref.ref(getattr(classifier, "model", classifier)), A)
     except TypeError:               # classifier object without weak-reference support: do not cache
@@ -278,11 +285,13 @@ def clear_engines() -> None:
 
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,
          iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None,
-         precision: Optional[str] = None, graph: Optional[bool] = None):
+         precision: Optional[str] = None, graph: Optional[bool] = None, fold_bn: Optional[bool] = None):
     """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1)).
     Keyword-only extras (reference defaults): iters=50; precision None (keep the model's), 'fp32', 'fp16' or 'bf16';
-    graph None (CUDA-graph replay of the iteration when the fused PCNet path is used), True or False."""
-    A = attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph)
+    graph None (CUDA-graph replay of the iteration when the fused PCNet path is used), True or False; fold_bn None (fold the
+    frozen classifier's inference-mode BatchNorm into its convolutions when cuDNN may use TF32), True or False."""
+    A = attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph,
+                      fold_bn=fold_bn)
     for it in range(iters):
         if forced_prj is not None:
             A.prj_adv.copy_(forced_prj[it])

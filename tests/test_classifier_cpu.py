@@ -1,0 +1,67 @@
+"""Host-side checks of the external-classifier handling (no GPU): BatchNorm folding keeps the function and the user's module."""
+import copy
+
+import pytest
+import torch
+
+
+def _randomise_bn(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.bias.data.copy_(0.1 * torch.randn(m.num_features, generator=g))
+
+
+@pytest.mark.parametrize("name", ["resnet18", "inception_v3", "vgg16"])
+def test_fold_batchnorm_keeps_logits_gradients_and_the_users_module(name):
+    from spaa_b200.classifier import Classifier, fold_batchnorm
+    clf = Classifier(name, "cpu", [0])
+    _randomise_bn(clf.model, 3)
+    before = copy.deepcopy(clf.model.state_dict())
+    view = fold_batchnorm(clf)
+    if name == "vgg16":                                   # no BatchNorm: nothing to fold, the classifier itself comes back
+        assert view is clf
+        return
+    assert view is not clf and view.input_sz == clf.input_sz
+    assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in view.model.modules())
+    for k, v in clf.model.state_dict().items():           # the user's network is untouched
+        assert torch.equal(v, before[k])
+    x = torch.rand(2, 3, *clf.input_sz, generator=torch.Generator().manual_seed(5))
+    outs, grads = [], []
+    for net in (clf.model, view.model):
+        leaf = x.clone().requires_grad_(True)
+        y = net(leaf)
+        y = y.logits if hasattr(y, "logits") else y
+        g, = torch.autograd.grad(y[:, 7].sum(), leaf)
+        outs.append(y.detach()); grads.append(g)
+    scale = outs[0].abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-5 * max(scale, 1.0)            # fp32 re-association only
+    assert torch.equal(outs[0].argmax(1), outs[1].argmax(1))
+    # random-init inception_v3 (94 conv layers, no trained scales) has input gradients of ~1e-11 whose rounding noise is amplified
+    # layer by layer: it is held to a relative Frobenius bound, resnet18 to max-abs
+    if name == "resnet18":
+        assert (grads[0] - grads[1]).abs().max().item() <= 1e-4 * grads[0].abs().max().item()
+    else:
+        rel = ((grads[0] - grads[1]).double().norm() / grads[0].double().norm()).item()
+        assert rel <= 5e-2, rel
+
+
+def test_fold_batchnorm_leaves_opaque_and_training_classifiers_alone():
+    from spaa_b200.classifier import fold_batchnorm
+
+    class Opaque:
+        def __call__(self, im, crop):
+            return im
+
+    o = Opaque()
+    assert fold_batchnorm(o) is o
+
+    class Training:
+        model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4)).train()
+        input_sz = (8, 8)
+
+    t = Training()
+    assert fold_batchnorm(t) is t
