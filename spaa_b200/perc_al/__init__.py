@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..classifier import device_logits
+from ..classifier import device_logits, fold_batchnorm, use_channels_last
 from .differential_color_functions import ciede2000_diff, deltaE, rgb2lab_diff  # noqa: F401  (re-exported like the reference)
 
 
@@ -104,7 +104,12 @@ class PerC_AL:
 
     def adversary_projector(self, classifier, inputs: torch.Tensor, labels: torch.Tensor, imagenet_labels, d_thr, targeted: bool = True,
                             cp_sz=(240, 240), trace: Optional[List[dict]] = None) -> torch.Tensor:
-        """:133-256."""
+        """:133-256.  The frozen classifier is called as in spaa(): channels_last and BatchNorm-folded (private copy) when cuDNN may
+        use TF32 (torch's default), the stock module in the exact-fp32 parity mode."""
+        clf_cl = use_channels_last(classifier) if inputs.is_cuda else False
+        if torch.backends.cudnn.allow_tf32:
+            classifier = fold_batchnorm(classifier)
+
         def fn(x):
-            return device_logits(classifier, x, cp_sz)
+            return device_logits(classifier, x, cp_sz, clf_cl)
         return self._run(fn, inputs, labels, targeted, float(d_thr), 0.9, True, trace)
