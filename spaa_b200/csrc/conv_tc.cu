@@ -338,6 +338,7 @@ struct HaloParams {
     int32_t a_plane_bytes, a_stage_bytes, a_tx_bytes, b_slice_bytes;
     int32_t sa, sb, resident, nslots, use_base_off, ntap_total;
     int32_t ctas_per_sm;
+    int32_t egroups, nbuf;             // epilogue warp groups (1 or 2); accumulator buffers in TMEM (2, or 1 when 2 do not fit)
     int32_t e_stage_bytes;             // output staging blocks of the 4 epilogue warps (16-bit NHWC output only)
     int32_t e_slots, e_nops;           // epilogue operand ring: slots of e_nops x 8 KB (0 slots: no ring)
     uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
@@ -364,7 +365,7 @@ template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint
 }
 
 template <int BN, int BK, bool F16>
-__global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+__global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ HaloParams P) {
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
     uint8_t* b_base = smem + (size_t)SA * P.a_stage_bytes;
     const size_t b_bytes = P.resident ? (size_t)P.kchunks * P.nslots * P.b_slice_bytes : (size_t)SB * P.b_slice_bytes;
     uint8_t* e_ring = b_base + b_bytes;            // epilogue operand ring (see the epilogue)
-    uint64_t* bars = (uint64_t*)(e_ring + (size_t)P.e_slots * P.e_nops * 8192 + P.e_stage_bytes);
+    uint64_t* bars = (uint64_t*)(e_ring + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes);
     uint64_t* a_full = bars;                       // [SA]
     uint64_t* a_empty = a_full + 8;                // [SA]
     uint64_t* b_full = a_empty + 8;                // [SB] (b_full[0] doubles as the "resident weights loaded" barrier)
@@ -387,10 +388,11 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NPH = P.nphases;
-    for (int i = threadIdx.x; i < P.ntap_total; i += kThreads) s_tap[i] = P.tap_tab[i];
+    for (int i = threadIdx.x; i < P.ntap_total; i += blockDim.x) s_tap[i] = P.tap_tab[i];
     const uint32_t acc_cols = (uint32_t)(NPH * BN);                  // TMEM columns of one accumulator buffer
+    const bool dbuf = P.nbuf == 2;                                   // two accumulator buffers: the epilogue of tile i overlaps the MMAs of tile i+1
     uint32_t tmem_cols = 32;
-    while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)P.nbuf * acc_cols) tmem_cols <<= 1;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a);
         prefetch_tmap(&map_b);
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
-    for (int i = threadIdx.x; i < BN; i += kThreads) s_bias[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) s_bias[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -464,8 +466,8 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
             int local = 0;
             if (P.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
-                const int acc = local & 1;
-                mbar_wait(tempty + acc, ((local >> 1) & 1) ^ 1);
+                const int acc = dbuf ? (local & 1) : 0;
+                mbar_wait(tempty + acc, (((dbuf ? local >> 1 : local)) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + (uint32_t)acc * acc_cols;
                 for (int kc = 0; kc < P.kchunks; ++kc) {
@@ -515,18 +517,26 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
         // lanes per row -- for the operand copies and, through a 2 KB staging block, for the output stores.  A warp copies and
         // reads only ITS OWN 32 rows, so cp.async.wait_group + __syncwarp is all the synchronisation the ring needs.
         // Block layout: [row][16-byte chunk c ^ ((row >> 1) & 3)] (conflict-free for the row-wise and the cooperative accesses).
+        // EG epilogue groups of 4 warps (one warp per TMEM lane quarter): with EG == 2 (wide layers) group g owns the tiles with
+        // local index = g (mod 2), i.e. accumulator buffer g, and has its own operand ring and staging blocks -- a lone warp per
+        // scheduler issues one dependent instruction every ~5 clk, and the ~500-instruction chain of a 32-channel chunk was what
+        // bounded every layer between the HBM-bound and the MMA-bound ones (conv3: MMA pipe idle 80 % of the time).
+        const int EG = P.egroups;
+        const int eg = (warp - 2) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int j = row >> 3, i = row & 7;
         const int ef = P.epi_flags;
         const bool has_add = P.add != nullptr, has_mask = P.mask != nullptr, has_out2 = P.out2 != nullptr;
         const bool planar = P.out_planar != 0, has_bias = P.bias != nullptr;
+        const int tstep = EG * (int)gridDim.x, tile0 = (int)blockIdx.x + eg * (int)gridDim.x;
         constexpr int NCH = BN / 32;
         const int nchu = planar ? 1 : NCH;                       // prefetch units per (tile, phase)
         const int S = P.e_slots;                                 // 0: no ring (no operand / wide planar residual)
         const uint32_t slot_bytes = (uint32_t)P.e_nops * 8192u;
         const int ci = lane >> 2, cc = lane & 3;                 // cooperative mapping: x pixel within the row group, 16-byte chunk
-        const uint32_t e_warp = smem_u32(e_ring) + (uint32_t)q * 2048u;
+        const uint32_t e_group = smem_u32(e_ring) + (uint32_t)eg * (uint32_t)S * slot_bytes;      // this group's ring
+        const uint32_t e_warp = e_group + (uint32_t)q * 2048u;
         uint32_t own_off[4], coop_off[4];                        // byte offsets inside a 2 KB warp block
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -534,12 +544,12 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
             const int rk = 8 * g + ci;
             coop_off[g] = (uint32_t)rk * 64u + (uint32_t)((cc ^ ((rk >> 1) & 3)) * 16);
         }
-        const uint32_t o_stage = smem_u32(e_ring) + (uint32_t)S * slot_bytes + (uint32_t)q * 4096u;     // [out | out2] staging of this warp
-        const uint32_t e_row4 = smem_u32(e_ring) + (uint32_t)row * 4u;       // fp32 planar residual: [channel][row]
+        const uint32_t o_stage = smem_u32(e_ring) + (uint32_t)(EG * S) * slot_bytes + (uint32_t)((eg * 4 + q) * 4096);     // [out | out2] staging of this warp
+        const uint32_t e_row4 = e_group + (uint32_t)row * 4u;                // fp32 planar residual: [channel][row]
         struct Ops { uint4 a[4], m[4], m2[4]; };
 
         // tile -> (image, tile row, tile column) without per-tile divisions: a CTA's tiles are gridDim.x apart
-        const int g_db = (int)gridDim.x / per_img, g_rem = (int)gridDim.x - g_db * per_img;
+        const int g_db = tstep / per_img, g_rem = tstep - g_db * per_img;
         const int g_dty = g_rem / P.tiles_x, g_dtx = g_rem - g_dty * P.tiles_x;
         auto tile_step = [&](int& tb, int& tty, int& ttx) {
             ttx += g_dtx;
@@ -548,9 +558,9 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
             if (tty >= P.tiles_y) { tty -= P.tiles_y; ++tb; }
             tb += g_db;
         };
-        const int b0 = (int)blockIdx.x / per_img, t0 = (int)blockIdx.x - b0 * per_img;
+        const int b0 = tile0 / per_img, t0 = tile0 - b0 * per_img;
         const int ty0 = t0 / P.tiles_x, tx0 = t0 - ty0 * P.tiles_x;
-        int pf_tile = blockIdx.x, pf_ph = 0, pf_c = 0, pf_slot = 0, pf_b = b0, pf_ty = ty0, pf_tx = tx0;
+        int pf_tile = tile0, pf_ph = 0, pf_c = 0, pf_slot = 0, pf_b = b0, pf_ty = ty0, pf_tx = tx0;
         auto issue = [&]() {
             if (pf_tile < P.total_tiles) {
                 const int oy = (pf_ty * HTH + j) * P.up + P.ph[pf_ph].py, ox = (pf_tx * HTW + i) * P.up + P.ph[pf_ph].px;
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
                 }
                 if (++pf_c == nchu) {
                     pf_c = 0;
-                    if (++pf_ph == NPH) { pf_ph = 0; pf_tile += gridDim.x; tile_step(pf_b, pf_ty, pf_tx); }
+                    if (++pf_ph == NPH) { pf_ph = 0; pf_tile += tstep; tile_step(pf_b, pf_ty, pf_tx); }
                 }
                 if (++pf_slot == S) pf_slot = 0;
             }
@@ -600,10 +610,11 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
         if (S) for (int d = 0; d < S - 1; ++d) issue();
         int cs = 0;                                              // ring slot of the unit being consumed
 
-        int local = 0;
+        int local = eg;
         int b = b0, ty = ty0, tx = tx0;
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local, tile_step(b, ty, tx)) {
-            const int acc = local & 1;
+        for (int tile = tile0; tile < P.total_tiles && eg < EG; tile += tstep, local += EG, tile_step(b, ty, tx)) {
+            const int acc = dbuf ? (local & 1) : 0;
+            const uint32_t tpar = (uint32_t)((dbuf ? local >> 1 : local) & 1);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
             bool waited = false;
             for (int ph = 0; ph < NPH; ++ph) {
@@ -629,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
 #pragma unroll
                         for (int k = 0; k < 4; ++k) if (k < P.Cout) av[k] = __ldg(ap + k * hw);
                     }
-                    if (!waited) { mbar_wait(tfull + acc, (local >> 1) & 1); tc_fence_after(); waited = true; }
+                    if (!waited) { mbar_wait(tfull + acc, tpar); tc_fence_after(); waited = true; }
                     uint32_t r[32];
                     tmem_ld32(t_row + (uint32_t)(ph * BN), r);
                     if (!valid) continue;
@@ -691,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(c
                         issue();
                         if (++cs == S) cs = 0;
                     }
-                    if (!waited) { mbar_wait(tfull + acc, (local >> 1) & 1); tc_fence_after(); waited = true; }
+                    if (!waited) { mbar_wait(tfull + acc, tpar); tc_fence_after(); waited = true; }
                     uint32_t r[32];
                     tmem_ld32(t_row + (uint32_t)(ph * BN + c0), r);
                     if (c0 < P.Cout) {
@@ -846,7 +857,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& 
     }
     const int slots = kNumSMs * P.ctas_per_sm;
     const int grid = P.total_tiles < slots ? P.total_tiles : slots;
-    conv_halo_kernel<BN, BK, F16><<<grid, kThreads, smem_bytes, st>>>(ma, mb, P);
+    conv_halo_kernel<BN, BK, F16><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P);
     return SPAA_OK;
 }
 
@@ -859,7 +870,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
     const bool f16 = d->in_dtype == 2;
     const int nph = d->up * d->up;
-    if (nph * BN > 256) return SPAA_ERR_UNSUPPORTED;
+    if (nph * BN > 512) return SPAA_ERR_UNSUPPORTED;
     HaloParams P;
     memset(&P, 0, sizeof(P));
     P.B = d->B; P.Cin = d->Cin; P.Hin = d->Hin; P.Win = d->Win; P.Cout = d->Cout; P.Hout = d->Hout; P.Wout = d->Wout;
@@ -931,11 +942,21 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // TMEM allocations and two half-size rings fit: twice the epilogue warps and loads in flight per SM.
     const bool planar = d->out_dtype == 0;
     P.e_nops = planar ? ((add && d->Cout <= 4) ? 1 : 0) : ((add ? 1 : 0) + (mask ? 1 : 0) + (mask2 ? 1 : 0));
-    P.e_stage_bytes = planar ? 0 : 4 * 4096;
+    // accumulator buffers: two when they fit in half of TMEM's 512 columns (so that two CTAs can share an SM) or in all of it for
+    // the wide layers; a 4-phase BN = 64 layer (transConv1 forward) runs single-buffered in 256 columns with two CTAs per SM instead
+    // of double-buffered alone on its SM
+    P.nbuf = 2 * nph * BN <= (BN <= 64 ? 256 : 512) ? 2 : 1;
     uint32_t tmem_cols = 32;
-    while (tmem_cols < 2u * (uint32_t)(nph * BN)) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(P.nbuf * nph * BN)) tmem_cols <<= 1;
     static const int max_ctas = [] { const char* e = getenv("SPAA_TC_CTAS"); return e ? atoi(e) : 2; }();
+    static const int max_eg = [] { const char* e = getenv("SPAA_TC_EG"); return e ? atoi(e) : 2; }();
     static const int e_kb = [] { const char* e = getenv("SPAA_TC_EKB"); return e ? atoi(e) : -1; }();
+    // two epilogue groups for the wide layers (one CTA per SM), unless their rings and staging blocks would starve the weight ring
+    // (measured: it pays where the MMA work per tile is short next to the epilogue's -- conv3 / skipConv3 / conv3_s / conv4 forward,
+    // K per epilogue operand <= 640 -- and costs 3-8 % on the MMA-bound layers, whose issuing warp then shares its schedulers)
+    const int k_per_pass = P.nslots * d->Cin / (1 + P.e_nops);
+    P.egroups = (BN >= 128 && P.nbuf == 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
+    P.e_stage_bytes = planar ? 0 : P.egroups * 4 * 4096;
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
     int ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
     size_t smem_bytes = 0;
@@ -945,10 +966,10 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
         P.e_slots = 0;
         if (P.e_nops) {
             const int eb = (e_kb >= 0 ? e_kb : (ctas == 2 ? 32 : (P.resident ? 48 : 32))) * 1024;
-            const int sl = eb / (P.e_nops * 8192);
+            const int sl = eb / (P.e_nops * 8192 * P.egroups);             // slots PER GROUP
             P.e_slots = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
         }
-        const int budget = total - P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
+        const int budget = total - P.egroups * P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
         int64_t bbytes, sa;
         if (P.resident) {
             bbytes = res_bytes; P.sb = 1;
@@ -966,7 +987,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
             continue;
         }
         P.sa = (int)(sa > 6 ? 6 : sa);
-        smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
+        smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
         break;
     }
     P.ctas_per_sm = ctas;
