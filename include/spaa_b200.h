@@ -273,6 +273,13 @@ int spaa_clf_preprocess_bwd(const float* dout, int64_t B, int H, int W, int top,
 int spaa_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, const int64_t* seg_end,
                    const float* seg_lr, const float* seg_wd, int nseg, float beta1, float beta2, float eps, int step,
                    float grad_scale, spaa_stream_t stream);
+/* Same update with the step-dependent scalars read from DEVICE memory, so that the launch can be recorded once in a CUDA
+ * graph and replayed every step: bias_corr2 = {1 - beta1^t, sqrt(1 - beta2^t)} (float[2], device); seg_lr as above (the
+ * caller refreshes both buffers before each replay).  Replaces the same optim.Adam.step / scheduler.step calls
+ * (train_network.py:318-320,355-357). */
+int spaa_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t n, const int64_t* seg_end,
+                       const float* seg_lr, const float* seg_wd, int nseg, float beta1, float beta2, float eps,
+                       const float* bias_corr2, float grad_scale, spaa_stream_t stream);
 
 #ifdef __cplusplus
 }

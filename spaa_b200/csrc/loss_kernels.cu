@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(kThreads) ssim_l1_kernel(const float* __restri
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                         int64_t n, const int64_t* __restrict__ seg_end, const float* __restrict__ seg_lr,
                                                         const float* __restrict__ seg_wd, int nseg, float beta1, float beta2, float eps, float bc1,
-                                                        float bc2_sqrt, float grad_scale) {
+                                                        float bc2_sqrt, float grad_scale, const float* __restrict__ dyn) {
+    if (dyn) { bc1 = __ldg(dyn); bc2_sqrt = __ldg(dyn + 1); }          // per-step scalars kept on the device: the launch is CUDA-graph replayable
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int s = 0;
         while (s < nseg - 1 && i >= __ldg(seg_end + s)) ++s;
@@ -248,8 +249,19 @@ int spaa_adam_step(float* param, const float* grad, float* m, float* v, int64_t 
     int64_t blocks = (n + kThreads - 1) / kThreads;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
     adam_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, seg_end, seg_lr, seg_wd, nseg, beta1, beta2, eps, bc1, bc2s,
-                                                                        grad_scale);
+                                                                        grad_scale, nullptr);
     SPAA_CHECK_LAUNCH("spaa_adam_step");
+    return SPAA_OK;
+}
+
+int spaa_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t n, const int64_t* seg_end, const float* seg_lr, const float* seg_wd,
+                       int nseg, float beta1, float beta2, float eps, const float* bias_corr2, float grad_scale, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(param && grad && m && v && seg_end && seg_lr && seg_wd && bias_corr2 && n > 0 && nseg > 0, "spaa_adam_step_dev: bad arguments");
+    int64_t blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    adam_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, seg_end, seg_lr, seg_wd, nseg, beta1, beta2, eps, 1.f, 1.f,
+                                                                        grad_scale, bias_corr2);
+    SPAA_CHECK_LAUNCH("spaa_adam_step_dev");
     return SPAA_OK;
 }
 

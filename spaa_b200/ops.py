@@ -596,6 +596,15 @@ def adam_step(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, seg_end: Tensor
                          beta1, beta2, eps, int(step), float(grad_scale), _stream()); _count()
 
 
+def adam_step_dev(param: Tensor, grad: Tensor, m: Tensor, v: Tensor, seg_end: Tensor, seg_lr: Tensor, seg_wd: Tensor, bias_corr2: Tensor,
+                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    """adam_step with the per-step scalars (bias corrections, learning rates) in device buffers: CUDA-graph replayable."""
+    for t in (param, grad, m, v, seg_lr, bias_corr2):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    lib().spaa_adam_step_dev(_p(param), _p(grad), _p(m), _p(v), param.numel(), _p(seg_end), _p(seg_lr), _p(seg_wd), seg_end.numel(),
+                             beta1, beta2, eps, _p(bias_corr2), float(grad_scale), _stream()); _count()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # attack-loop updates
 # ------------------------------------------------------------------------------------------------------------

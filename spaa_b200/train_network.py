@@ -113,7 +113,13 @@ class FlatAdam:
                     row.append(lr * gamma ** sum(1 for m in milestones if s >= m))
             table.append(row)
         self.lr_table_host = table
-        self.lr_table = torch.tensor(table, device=dev)
+        self.beta1, self.beta2 = 0.9, 0.999
+        # per-step scalars as ONE device table, row t-1 = [1 - beta1^t, sqrt(1 - beta2^t), lr of every group at scheduler step t-1]:
+        # advance() copies the row of the coming step into `dyn` (device to device, no host value read), apply() launches the update
+        # with pointers into `dyn` -- so apply() can be recorded in a CUDA graph and replayed with fresh scalars every step
+        rows = [[1.0 - self.beta1 ** (t + 1), math.sqrt(1.0 - self.beta2 ** (t + 1))] + table[min(t, len(table) - 1)] for t in range(max_steps + 1)]
+        self.dyn_table = torch.tensor(rows, device=dev, dtype=torch.float32)
+        self.dyn = self.dyn_table[0].clone()
         self.t = 0
 
     def zero_grad(self):
@@ -122,14 +128,23 @@ class FlatAdam:
             if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
                 raise RuntimeError("a parameter's .grad was detached from the flat gradient buffer")
 
-    def step(self, grad_scale: float = 1.0):
-        """One Adam update with the learning rates of scheduler step `self.t` (then advances the schedule)."""
+    def advance(self):
+        """Host side of a step: move the schedule on and stage that step's scalars on the device (outside any CUDA graph)."""
         self.t += 1
-        row = self.lr_table[min(self.t - 1, self.lr_table.shape[0] - 1)]
-        ops.adam_step(self.param, self.grad, self.m, self.v, self.seg_end, row, self.seg_wd, self.t, grad_scale=grad_scale)
+        self.dyn.copy_(self.dyn_table[min(self.t - 1, self.dyn_table.shape[0] - 1)])
+
+    def apply(self, grad_scale: float = 1.0):
+        """Device side of a step: one Adam launch over the flat buffers with the staged scalars (CUDA-graph capturable)."""
+        ops.adam_step_dev(self.param, self.grad, self.m, self.v, self.seg_end, self.dyn[2:], self.seg_wd, self.dyn[:2], beta1=self.beta1,
+                          beta2=self.beta2, grad_scale=grad_scale)
         # the raw kernel updates the parameters without touching their autograd version counters: drop the packed 16-bit copies
         # of the weights the tensor-core convolutions cache, or the next forward would run on the previous step's weights
         ops.invalidate_packed_weights()
+
+    def step(self, grad_scale: float = 1.0):
+        """One Adam update with the learning rates of scheduler step `self.t` (then advances the schedule)."""
+        self.advance()
+        self.apply(grad_scale)
 
     def lr(self, group: int = 0) -> float:
         return self.lr_table_host[min(self.t, len(self.lr_table_host) - 1)][group]
@@ -179,6 +194,9 @@ def _resident(t: torch.Tensor, device) -> torch.Tensor:
     return t if t.device == device else t.to(device)
 
 
+_GRAPH_WARMUP = 3
+
+
 def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter, valid_data, title, verbose):
     device = torch.device(cfg["device"])
     rank, world = _world()
@@ -191,21 +209,58 @@ def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter,
     valid_psnr = valid_rmse = valid_ssim = 0.0
     print_rate = cfg.get("print_rate", 1 if verbose else 0)
     iters = 0
-    while iters < cfg["max_iters"]:
-        idx = random.sample(range(cfg["num_train"]), B)             # :295 (python RNG, same draw on every rank)
-        if dp_mode != "weak":
-            idx = shard_indices(idx, rank, world)
-        it = torch.as_tensor(idx, device=device)
-        x_batch, y_batch = inputs.index_select(0, it), targets.index_select(0, it)
-        cfg["loss"] = loss_of_iter(iters + cfg.get("iter_offset", 0))      # iter_offset: resume / benchmark a later phase of the schedule
+    # One training step = a fixed sequence of launches with no host decision inside (batch gather, forward, fused loss, zero_grad,
+    # backward, gradient all-reduce, Adam): after `_GRAPH_WARMUP` eager steps per loss phase (they fill the packed-weight / workspace
+    # caches) the step is recorded in a CUDA graph and replayed; per step the host only stages the batch indices and the scheduler row.
+    use_graph = bool(cfg.get("graph", device.type == "cuda"))
+    it_static = torch.zeros(local_B, dtype=torch.int64, device=device)
+    hist_slot = torch.zeros(2, device=device)
+    graphs, eager_steps, keep = {}, {}, []
+
+    def device_step(loss_option):
+        x_batch, y_batch = inputs.index_select(0, it_static), targets.index_select(0, it_static)
         model.train()
         infer = model(x_batch, scene_batch)
-        loss, l2 = compute_loss(infer, y_batch, cfg["loss"])
+        loss, l2 = compute_loss(infer, y_batch, loss_option)
         opt.zero_grad()
         loss.backward()
         scale = allreduce_grads(opt, world)
-        opt.step(grad_scale=scale)
-        history[iters, 0], history[iters, 1] = loss.detach(), l2
+        opt.apply(grad_scale=scale)
+        hist_slot[0], hist_slot[1] = loss.detach(), l2
+
+    on_step = cfg.get("on_step")                                     # optional host callback(iteration) before each step (progress / timing hooks)
+    while iters < cfg["max_iters"]:
+        if on_step is not None:
+            on_step(iters)
+        idx = random.sample(range(cfg["num_train"]), B)             # :295 (python RNG, same draw on every rank)
+        if dp_mode != "weak":
+            idx = shard_indices(idx, rank, world)
+        it_static.copy_(torch.as_tensor(idx), non_blocking=True)
+        cfg["loss"] = loss_of_iter(iters + cfg.get("iter_offset", 0))      # iter_offset: resume / benchmark a later phase of the schedule
+        opt.advance()
+        g = graphs.get(cfg["loss"])
+        if g is not None:
+            g.replay()
+            ops.invalidate_packed_weights()                         # eager code between steps (validation) must re-pack the updated weights
+        elif use_graph and eager_steps.get(cfg["loss"], 0) >= _GRAPH_WARMUP and "huber" not in cfg["loss"]:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    device_step(cfg["loss"])                        # records the launches; the replay below executes this step
+                finally:
+                    g.capture_end()
+            torch.cuda.current_stream(device).wait_stream(side)
+            keep.append(side)
+            graphs[cfg["loss"]] = g
+            g.replay()
+            ops.invalidate_packed_weights()
+        else:
+            device_step(cfg["loss"])
+            eager_steps[cfg["loss"]] = eager_steps.get(cfg["loss"], 0) + 1
+        history[iters].copy_(hist_slot)
         if valid_data is not None and (iters % cfg["valid_rate"] == 0 or iters == cfg["max_iters"] - 1):
             valid_psnr, valid_rmse, valid_ssim, _ = evaluate_model(model, valid_data)
         if print_rate and (iters % print_rate == 0 or iters == cfg["max_iters"] - 1) and rank == 0:

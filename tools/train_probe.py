@@ -41,3 +41,6 @@ tot = sum(k.device_time_total for k in prof.key_averages())
 print(f"total device time for 2 steps: {tot / 1e3:.2f} ms")
 for k in rows:
     print(f"{k.device_time_total / 2e3:9.3f} ms/step  x{k.count // 2:4d}  {k.key[:110]}")
+wg = [e for e in prof.events() if "conv_wgrad_tc_kernel" in e.name and e.device_time_total > 0]
+half = wg[len(wg) // 2:]
+print("conv_wgrad_tc_kernel launches of the last step (us):", [round(e.device_time_total, 1) for e in half])
