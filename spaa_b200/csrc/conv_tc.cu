@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
             const int rk = 8 * g + ci;
             coop_off[g] = (uint32_t)rk * 64u + (uint32_t)((cc ^ ((rk >> 1) & 3)) * 16);
         }
-        const uint32_t o_stage = smem_u32(e_ring) + (uint32_t)(EG * S) * slot_bytes + (uint32_t)((eg * 4 + q) * 4096);     // [out | out2] staging of this warp
+        const uint32_t o_stage = smem_u32(e_ring) + (uint32_t)(EG * S) * slot_bytes + (uint32_t)(eg * 4 + q) * (has_out2 ? 4096u : 2048u);     // [out | out2] staging of this warp
         const uint32_t e_row4 = e_group + (uint32_t)row * 4u;                // fp32 planar residual: [channel][row]
         struct Ops { uint4 a[4], m[4], m2[4]; };
 
@@ -956,7 +956,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // K per epilogue operand <= 640 -- and costs 3-8 % on the MMA-bound layers, whose issuing warp then shares its schedulers)
     const int k_per_pass = P.nslots * d->Cin / (1 + P.e_nops);
     P.egroups = (BN >= 128 && P.nbuf == 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
-    P.e_stage_bytes = planar ? 0 : P.egroups * 4 * 4096;
+    P.e_stage_bytes = planar ? 0 : P.egroups * 4 * (mask2 ? 4096 : 2048);
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
     int ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
     size_t smem_bytes = 0;
@@ -969,7 +969,12 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
             const int sl = eb / (P.e_nops * 8192 * P.egroups);             // slots PER GROUP
             P.e_slots = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
         }
-        const int budget = total - P.egroups * P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
+        int budget = total - P.egroups * P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
+        // big A stages (stride-2 layers load four parity planes): give the operand ring's depth back before giving up the kernel
+        while (P.e_slots > 2 && budget - 2 * P.a_stage_bytes < (P.resident ? res_bytes : 2 * (int64_t)P.b_slice_bytes)) {
+            --P.e_slots;
+            budget += P.egroups * P.e_nops * 8192;
+        }
         int64_t bbytes, sa;
         if (P.resident) {
             bbytes = res_bytes; P.sb = 1;
