@@ -18,7 +18,7 @@
 //     halo_w rows; stride-2 layers use the four input-parity planes);
 //   * M = 128 rows: Cx >= 128 -> 128 channels of one tap (two 64-channel atoms, LBO = box stride);
 //                   Cx == 64  -> TWO taps per MMA (atom 1 = the other tap's view: LBO = distance of the two start addresses);
-//                   Cx <= 32  -> one tap, the remaining atoms alias shifted rows (computed, ignored);
+//                   Cx <= 32  -> the taps of one filter row per MMA: atom k = the view shifted by k pixels (LBO = one row);
 //   * one launch accumulates up to 512 / Cy (tap, 128-channel) pairs; ops.py issues one launch per such set.
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -317,12 +317,27 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
             else a.g.a_lbo16 = (uint32_t)rowx >> 4;
         }
     } else {
+        // Cx <= 32: the 128 M rows hold 4 (8) atoms of 32 (16) channels, one smem row apart (LBO = one row), i.e. atom k reads the view
+        // shifted by k pixels in x: the taps (plane, qy, qx + k) of the SAME filter row ride along in the same MMA.  A 3x3 stride-1 layer
+        // needs 3 accumulators instead of 9 (conv6: one accumulator set instead of two, a third of the MMAs), a stride-2 one 6.
+        const int natoms = 128 / P.cxb;
+        bool used[9] = {false, false, false, false, false, false, false, false, false};
         for (int t = 0; t < ntaps; ++t) {
+            if (used[t]) continue;
+            bool is_base = true;                                  // start runs at their smallest qx
+            for (int u = 0; u < ntaps; ++u)
+                if (!used[u] && u != t && tp[u].plane == tp[t].plane && tp[u].qy == tp[t].qy && tp[u].qx == tp[t].qx - 1) is_base = false;
+            if (!is_base) continue;
             Acc& a = accs[nacc++];
             memset(&a, 0, sizeof(a));
             for (int k = 0; k < 8; ++k) a.g.tap[k] = -1;
             a.g.a_off16 = tap_off16(t, 0); a.g.a_lbo16 = (uint32_t)rowx >> 4; a.g.tap[0] = (int8_t)t;
+            used[t] = true;
+            for (int k = 1; k < natoms; ++k)
+                for (int u = 0; u < ntaps; ++u)
+                    if (!used[u] && tp[u].plane == tp[t].plane && tp[u].qy == tp[t].qy && tp[u].qx == tp[t].qx + k) { a.g.tap[k] = (int8_t)u; used[u] = true; }
         }
+        for (int t = 0; t < ntaps; ++t) SPAA_CHECK_ARG(used[t], "spaa_conv_wgrad_tc: internal error (tap not assigned to an accumulator)");
     }
     int max_per_set = 512 / Cy;
     if (max_per_set > 8) max_per_set = 8;

