@@ -11,6 +11,7 @@ Loop constants the reference recomputes every iteration (sampling grid, skipConv
 from __future__ import annotations
 
 import collections
+import os
 import weakref
 from typing import List, Optional
 
@@ -358,4 +359,58 @@ def gather_job_results(local_results, n_jobs: int):
     missing = [i for i, r in enumerate(out) if r is None]
     if missing:
         raise RuntimeError(f"attack jobs {missing} were not executed by any rank")
+    return out
+
+
+def to_attacker_cfg_str(attacker_name: str):
+    """projector_based_attack.py:194-210: the folder name the reference derives from the attacker and its model's training configuration."""
+    from .train_network import get_model_train_cfg
+    assert attacker_name in ("SPAA", "PerC-AL+CompenNet++"), f"{attacker_name} not supported!"
+    c = get_model_train_cfg(model_list=["PCNet" if attacker_name == "SPAA" else "CompenNet++"], single=True)
+    model_cfg_str = f"{c.model_name}_{c.loss}_{c.num_train}_{c.batch_size}_{c.max_iters}"
+    if attacker_name == "SPAA":
+        return f"{attacker_name}_{model_cfg_str}", model_cfg_str
+    return f"{attacker_name}_{c.loss}_{c.num_train}_{c.batch_size}_{c.max_iters}", model_cfg_str
+
+
+def run_attack_sweep(jobs, device, *, attacker_name: str = "SPAA", iters: int = 50, precision: Optional[str] = None, save: bool = True,
+                     rank: Optional[int] = None, world: Optional[int] = None):
+    """The job loop of run_projector_based_attack (projector_based_attack.py:83-141) for models that are already trained, sharded over ranks.
+
+    jobs: list of dicts, one per (setup, stealth_loss, d_thr, classifier) cell of the reference's nested loops:
+        model        PCNet (SPAA) or CompenNet++ (PerC-AL), frozen, on `device`
+        classifier   object with the reference's Classifier convention (.model / .input_sz / __call__)
+        cam_scene    [3,H,W] or [1,3,H,W]
+        target_idx   list of target class indices (the targeted batch, :121)
+        stealth_loss, d_thr, setup_info (classifier_crop_sz, prj_im_sz, prj_brightness)
+        setup_path, classifier_name   (only for `save`)  -> <setup_path>/{cam/infer/adv,prj/adv}/<attacker cfg>/<stealth_loss>/<d_thr>/<classifier_name>/
+    Every job runs the reference's two attacks -- untargeted against the scene's own top-1 label (:104-111), then the targeted batch (:121-125) -- and
+    stores the n targeted results followed by the untargeted one as img_0001.png .. (:137-138).  Jobs are independent: rank r runs jobs
+    r, r + world, ... with no data-path collective; attack engines (buffers + captured CUDA graph) are reused across jobs with the same model,
+    classifier and shapes.  Returns [(job index, dict(true_idx, n_targets, cam_infer [n+1,3,H,W] cpu, prj_adv [n+1,3,h,w] cpu)), ...] of this rank."""
+    from . import utils as ut
+    assert attacker_name in ("SPAA", "PerC-AL+CompenNet++"), f"{attacker_name} not supported!"
+    cfg_str = to_attacker_cfg_str(attacker_name)[0]
+    out = []
+    for ji, job in shard_jobs(jobs, rank, world):
+        scene = expand_4d(job["cam_scene"]).to(device)
+        setup, clf = job["setup_info"], job["classifier"]
+        cp_sz = setup["classifier_crop_sz"]
+        with torch.no_grad():
+            true_idx = int(device_logits(clf, scene, cp_sz).argmax(1)[0])          # :99-102 (top-1 of the un-attacked scene)
+        res = []
+        for targeted, tidx in ((True, list(job["target_idx"])), (False, [true_idx])):
+            if attacker_name == "SPAA":
+                cam, prj = spaa(job["model"], clf, None, tidx, targeted, scene, job["d_thr"], job["stealth_loss"], device, setup, iters=iters,
+                                precision=precision)
+            else:
+                cam, prj = perc_al_compennet_pp(job["model"], clf, None, tidx, targeted, scene, job["d_thr"], device, setup, iters=iters)
+            res.append((cam.detach().clone(), prj.detach().clone()))
+        cam_all = torch.cat([r[0] for r in res], 0).cpu()
+        prj_all = torch.cat([r[1] for r in res], 0).cpu()
+        if save and job.get("setup_path"):
+            folder = os.path.join(cfg_str, job["stealth_loss"], str(job["d_thr"]), job.get("classifier_name", getattr(clf, "name", "classifier")))
+            ut.save_imgs(cam_all, os.path.join(job["setup_path"], "cam/infer/adv", folder))
+            ut.save_imgs(prj_all, os.path.join(job["setup_path"], "prj/adv", folder))
+        out.append((ji, dict(true_idx=true_idx, n_targets=len(job["target_idx"]), cam_infer=cam_all, prj_adv=prj_all)))
     return out

@@ -1,5 +1,6 @@
 """GPU parity of the module-level API (models, losses, attack loops, training) against fixtures generated from the
 UNMODIFIED reference (tests/golden/*.npz, made by tests/golden/make_golden.py) and against the CPU oracle."""
+import os
 import random
 
 import numpy as np
@@ -591,3 +592,39 @@ def test_flat_adam_graph_replay_matches_eager_updates():
 
     for a, b in zip(run(False), run(True)):
         assert torch.equal(a, b)
+
+
+def test_run_attack_sweep_matches_direct_calls_and_writes_the_reference_layout(tmp_path):
+    """The sharded sweep driver (job loop of run_projector_based_attack, projector_based_attack.py:83-141): every job = targeted batch +
+    untargeted attack on the scene's own top-1; results equal the direct spaa() calls, land under the reference's folder names as
+    img_0001.. (targeted first, untargeted last), and the ranks' shards partition the jobs."""
+    from spaa_b200 import projector_based_attack as pba, utils as ut
+    from spaa_b200.classifier import device_logits
+    P, m, scene = _spaa_setup()
+    scene2 = synth.textured(63, "sweep.scene", (1, 3, *CAM_HW))
+    clf = TinyClf(1)
+    targets = [808, 969, 116]
+    jobs = [dict(model=m, classifier=clf, classifier_name="tiny", cam_scene=sc, target_idx=targets, stealth_loss=sl, d_thr=thr, setup_info=SETUP,
+                 setup_path=str(tmp_path / name)) for name, sc, sl, thr in (("s1", scene, "camdE_caml2", 2.0), ("s2", scene2, "caml2", 3.0), ("s1", scene, "camdE", 2.0))]
+    done = {}
+    for rank in range(2):
+        for ji, r in pba.run_attack_sweep(jobs, dev(), iters=4, rank=rank, world=2):
+            assert ji % 2 == rank and ji not in done
+            done[ji] = r
+    assert sorted(done) == [0, 1, 2]
+    cfg_str = pba.to_attacker_cfg_str("SPAA")[0]
+    for ji, job in enumerate(jobs):
+        r = done[ji]
+        sc = job["cam_scene"].to(dev())
+        true_idx = int(device_logits(clf, sc, SETUP["classifier_crop_sz"]).argmax(1)[0])
+        assert r["true_idx"] == true_idx and r["n_targets"] == 3 and r["cam_infer"].shape == (4, 3, *CAM_HW) and r["prj_adv"].shape == (4, 3, *PRJ_HW)
+        cam_t, prj_t = pba.spaa(m, clf, LABELS, targets, True, sc, job["d_thr"], job["stealth_loss"], dev(), SETUP, iters=4)
+        cam_u, prj_u = pba.spaa(m, clf, LABELS, [true_idx], False, sc, job["d_thr"], job["stealth_loss"], dev(), SETUP, iters=4)
+        close(r["cam_infer"], torch.cat((cam_t, cam_u)).cpu(), 1e-5, 0, f"job {ji} cam")       # (scatter-add order: not bit-exact run to run)
+        close(r["prj_adv"], torch.cat((prj_t, prj_u)).cpu(), 1e-4, 0, f"job {ji} prj")
+        folder = os.path.join(cfg_str, job["stealth_loss"], str(job["d_thr"]), "tiny")
+        for sub, ref in (("cam/infer/adv", r["cam_infer"]), ("prj/adv", r["prj_adv"])):
+            d = os.path.join(job["setup_path"], sub, folder)
+            assert sorted(os.listdir(d)) == [f"img_{k:04d}.png" for k in range(1, 5)]
+            back = ut.torch_imread(os.path.join(d, "img_0004.png"))                             # the untargeted result is stored last (:137-138)
+            assert (back - ref[3].clamp(0, 1)).abs().max().item() <= 1.0 / 255 + 1e-6
