@@ -87,6 +87,20 @@ int spaa_grid_sample_fwd(const float* img, int64_t B, int C, int Hi, int Wi, con
 int spaa_grid_sample_fwd_packed(const float* img, int64_t B, int Hi, int Wi, const float* grid, int64_t grid_bstride, int H,
                                 int W, int clamp01, const float* mask, const float* rough, int64_t rough_bstride, void* out16,
                                 int dtype, spaa_stream_t stream);
+/* Gather form of the same adjoint for a grid that stays FIXED over many calls (the attack loops: frozen model, one grid per attack).
+ * spaa_warp_taps lists for every output pixel p and bilinear tap k (entry k*H*W + p) the input pixel it reads (ent_q; Hi*Wi = unused tap)
+ * and its bilinear weight (ent_w).  The caller sorts the entries by ent_q once (stable), keeps p, the weight and mask[p] per entry (ent_p,
+ * ent_w, ent_m) and the CSR offsets row_ptr[Hi*Wi + 1]; spaa_grid_sample_bwd_gather then computes
+ *   dimg[b,c,q] = sum_{e in row q} ((dout[b,c,p_e] + dout2[b,c,p_e] * rough[b,c,p_e]) * m_e) * w_e          (no atomics, dimg fully overwritten)
+ * and, when sq != NULL, sq[b] = sum_{c,q} dimg[b,c,q]^2 over the entries whose x_for_clamp[b,c,q] lies in [lo,hi] (all if NULL): the backward of
+ * grid_sample (models.py:184) + clamp (projector_based_attack.py:265) and the norm of :307,315 in one pass.  ws: spaa_grid_sample_bwd_gather_ws_bytes, zeroed once. */
+int spaa_warp_taps(const float* grid, const float* mask, int Hi, int Wi, int H, int W, int32_t* ent_q, float* ent_w,
+                   spaa_stream_t stream);
+int64_t spaa_grid_sample_bwd_gather_ws_bytes(int64_t B, int Hi, int Wi);
+int spaa_grid_sample_bwd_gather(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,
+                                int64_t rough_bstride, const int32_t* row_ptr, const int32_t* ent_p, const float* ent_w,
+                                const float* ent_m, int64_t B, int C, int Hi, int Wi, int H, int W, const float* x_for_clamp,
+                                float lo, float hi, float* dimg, float* sq, void* ws, spaa_stream_t stream);
 /* dimg (+)= scatter of (dout + dout2*rough) * mask ; dimg must be zero-filled by the caller (atomic accumulate);
  * clamp01: zero the gradient where img is outside [0,1] is NOT applied here (applied by the consumer). */
 int spaa_grid_sample_bwd_input(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,

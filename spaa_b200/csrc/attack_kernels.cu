@@ -10,7 +10,7 @@ using namespace spaa;
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kPerBlock = 4096;   // elements per block in row reductions
+constexpr int kPerBlock = 8192;   // elements per block in row reductions (two 128-bit loads per operand and thread in flight)
 
 SPAA_D bool in_range(float x, float lo, float hi) { return x >= lo && x <= hi; }   // torch.clamp backward: inclusive
 
@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(kThreads) row_sqnorm_kernel(const float* __res
     if ((n & 3) == 0) {
         const float4* g4 = reinterpret_cast<const float4*>(gb);
         const float4* x4 = reinterpret_cast<const float4*>(xb);
+#pragma unroll 2
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
             float4 v = __ldg(g4 + i);
             if (xb) {
@@ -59,6 +60,31 @@ __global__ void __launch_bounds__(kThreads) row_step_kernel(float* __restrict__ 
     const float scale = step == 0.f ? 0.f : step / sqrtf(__ldg(sq + b));
     float* xb = x + (int64_t)b * n;
     const float* gb = g + (int64_t)b * n;
+    if ((n & 3) == 0 && (base_bs & 3) == 0) {
+        // 128-bit path (rows are 196 608 floats in the attack loops): same arithmetic per element
+        float4* x4 = reinterpret_cast<float4*>(xb);
+        const float4* g4 = reinterpret_cast<const float4*>(gb);
+        const float4* b4 = base ? reinterpret_cast<const float4*>(base + (int64_t)b * base_bs) : nullptr;
+        float4* s4 = sum_out ? reinterpret_cast<float4*>(sum_out + (int64_t)b * n) : nullptr;
+        float4* c4 = do_copy ? reinterpret_cast<float4*>(copy_dst + (int64_t)b * n) : nullptr;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+            float4 xv = x4[i];
+            if (step != 0.f) {
+                float4 gv = __ldg(g4 + i);
+                if (use_clamp) {
+                    if (!in_range(xv.x, lo, hi)) gv.x = 0.f;
+                    if (!in_range(xv.y, lo, hi)) gv.y = 0.f;
+                    if (!in_range(xv.z, lo, hi)) gv.z = 0.f;
+                    if (!in_range(xv.w, lo, hi)) gv.w = 0.f;
+                }
+                xv.x = xv.x + scale * gv.x; xv.y = xv.y + scale * gv.y; xv.z = xv.z + scale * gv.z; xv.w = xv.w + scale * gv.w;
+                x4[i] = xv;
+            }
+            if (s4) { const float4 bv = __ldg(b4 + i); s4[i] = make_float4(bv.x + xv.x, bv.y + xv.y, bv.z + xv.z, bv.w + xv.w); }
+            if (c4) c4[i] = xv;
+        }
+        return;
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float xv = xb[i];
         if (step != 0.f) {
@@ -111,6 +137,7 @@ __global__ void __launch_bounds__(kThreads) select_cot_packed_kernel(const float
     const int b = blockIdx.y;
     const float* src = ((sel && sel[b]) ? g1 : g0) + (int64_t)b * 3 * HW;
     const float* a = act ? act + (int64_t)b * 3 * HW : nullptr;
+#pragma unroll 4
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
         float v[3];
 #pragma unroll
@@ -329,7 +356,7 @@ int spaa_row_normalized_step(float* x, const float* g, const float* sq, const ui
     SPAA_CHECK_ARG(x && g && sq && step2 && B > 0 && B < 65536 && n > 0, "spaa_row_normalized_step: bad arguments");
     SPAA_CHECK_ARG((sum_out == nullptr) || base, "spaa_row_normalized_step: sum_out needs base");
     SPAA_CHECK_ARG((copy_dst == nullptr) == (copy_sel == nullptr), "spaa_row_normalized_step: copy_dst and copy_sel go together");
-    row_step_kernel<<<row_grid(n, B, 1), kThreads, 0, (cudaStream_t)stream>>>(x, g, sq, sel, step2, use_clamp_mask, lo, hi, base, base_bstride, sum_out,
+    row_step_kernel<<<row_grid(n, B, ((n & 3) == 0 && (base_bstride & 3) == 0) ? 4 : 1), kThreads, 0, (cudaStream_t)stream>>>(x, g, sq, sel, step2, use_clamp_mask, lo, hi, base, base_bstride, sum_out,
                                                                              copy_dst, copy_sel, n);
     SPAA_CHECK_LAUNCH("spaa_row_normalized_step");
     return SPAA_OK;

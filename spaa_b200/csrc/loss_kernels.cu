@@ -59,204 +59,219 @@ __global__ void __launch_bounds__(kThreads, 3) ssim_l1_kernel(const float* __res
     const float* xp = pred + (int64_t)plane * H * W;
     const float* yp = target + (int64_t)plane * H * W;
 
-    // ---- load with replicate-clamped coordinates: every thread issues all of its ~21 element copies asynchronously, then waits once
-    // (a load -> store loop exposed one global-memory latency per iteration: 25 % of the kernel's stall samples) ----------------
-    for (int e = tid; e < T2 * T2; e += kThreads) {
-        const int i = e / T2, j = e - i * T2;
-        int gy = ty0 - 2 * R + i, gx = tx0 - 2 * R + j;
-        gy = gy < 0 ? 0 : (gy > H - 1 ? H - 1 : gy);
-        gx = gx < 0 ? 0 : (gx > W - 1 ? W - 1 : gx);
-        tc::cp_async4(tc::smem_u32(sX + e), xp + (int64_t)gy * W + gx);
-        tc::cp_async4(tc::smem_u32(sY + e), yp + (int64_t)gy * W + gx);
-    }
-    tc::cp_async_commit();
-    tc::cp_async_wait(0);
-    __syncthreads();
-    // All four separable passes are REGISTER-BLOCKED: a thread produces a strip of SW consecutive outputs along the filter axis from
-    // SW + 10 inputs it reads once (sliding window), instead of 11 shared-memory reads per output and map.  The first version (one
-    // output per thread per pass) was bound by shared-memory bandwidth: ~300 LDS per pixel, 363 us for 24 images.
-    // ---- horizontal Gaussian of the five products: rows of R2, columns of R1 -------------------------
-    constexpr int SW = 11, NS = (T1 + SW - 1) / SW;        // 4 strips of 11 cover the 42 columns / rows of R1
-    for (int it = tid; it < T2 * NS; it += kThreads) {
-        const int i = it / NS, sidx = it - i * NS, j0 = sidx * SW;        // lanes: 8 rows x 4 strips -> conflict-free reads
-        float acc[5][SW];
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int o = 0; o < SW; ++o) acc[q][o] = 0.f;
-#pragma unroll
-        for (int t = 0; t < SW + 10; ++t) {
-            const int jj = min(j0 + t, T2 - 1);                         // columns past the halo only feed outputs that are dropped
-            const float x = sX[i * T2 + jj], y = sY[i * T2 + jj];
-            const float xx = x * x, yy = y * y, xy = x * y;
-#pragma unroll
-            for (int o = 0; o < SW; ++o) {
-                const int k = t - o;
-                if (k >= 0 && k < 11) {
-                    const float g = G.g[k];
-                    acc[0][o] = fmaf(g, x, acc[0][o]); acc[1][o] = fmaf(g, y, acc[1][o]);
-                    acc[2][o] = fmaf(g, xx, acc[2][o]); acc[3][o] = fmaf(g, yy, acc[3][o]); acc[4][o] = fmaf(g, xy, acc[4][o]);
-                }
-            }
+    float s_ssim = 0.f, s_l1 = 0.f, s_l2 = 0.f;
+    // The L1 phase of train_pcnet (iterations <= 400, train_network.py:300-303) asks for the gradient of an L1 (+ L2) loss only: with no SSIM
+    // weight, cotangent map or map output the windowed statistics are not needed at all and the tile reduces to a pointwise pass
+    // (sums[2] is 0 in that case; the metric calls, which want the SSIM value, pass grad == nullptr and take the full path).
+    const bool want_ssim = !(grad != nullptr && c_ssim == 0.f && cot_map == nullptr && ssim_map == nullptr);
+    if (!want_ssim) {
+        for (int e = tid; e < T * T; e += kThreads) {
+            const int i = e / T, j = e - i * T;
+            const int gy = ty0 + i, gx = tx0 + j;
+            if (gy >= H || gx >= W) continue;
+            const float d = __ldg(xp + (int64_t)gy * W + gx) - __ldg(yp + (int64_t)gy * W + gx);
+            s_l1 += fabsf(d); s_l2 += d * d;
+            const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+            grad[(int64_t)plane * H * W + (int64_t)gy * W + gx] = c_l1 * sg + c_l2 * 2.f * d;
         }
-#pragma unroll
-        for (int o = 0; o < SW; ++o) {
-            if (j0 + o < T1) {
-#pragma unroll
-                for (int q = 0; q < 5; ++q) sH[q * T2 * T1 + i * T1 + j0 + o] = acc[q][o];
-            }
+    } else {
+        // ---- load with replicate-clamped coordinates: every thread issues all of its ~21 element copies asynchronously, then waits once
+        // (a load -> store loop exposed one global-memory latency per iteration: 25 % of the kernel's stall samples) ----------------
+        for (int e = tid; e < T2 * T2; e += kThreads) {
+            const int i = e / T2, j = e - i * T2;
+            int gy = ty0 - 2 * R + i, gx = tx0 - 2 * R + j;
+            gy = gy < 0 ? 0 : (gy > H - 1 ? H - 1 : gy);
+            gx = gx < 0 ? 0 : (gx > W - 1 ? W - 1 : gx);
+            tc::cp_async4(tc::smem_u32(sX + e), xp + (int64_t)gy * W + gx);
+            tc::cp_async4(tc::smem_u32(sY + e), yp + (int64_t)gy * W + gx);
         }
-    }
-    __syncthreads();
-    // ---- vertical Gaussian -> moments -> SSIM and its partial derivatives on R1 ----------------------
-    float s_ssim = 0.f;
-    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-    for (int it = tid; it < NS * T1; it += kThreads) {
-        const int sidx = it / T1, j = it - sidx * T1, i0 = sidx * SW;    // lanes along a row: conflict-free
-        float m[5][SW];
-#pragma unroll
-        for (int q = 0; q < 5; ++q)
-#pragma unroll
-            for (int o = 0; o < SW; ++o) m[q][o] = 0.f;
-#pragma unroll
-        for (int t = 0; t < SW + 10; ++t) {
-            const int row = min(i0 + t, T2 - 1);
-            float v[5];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) v[q] = sH[q * T2 * T1 + row * T1 + j];
-#pragma unroll
-            for (int o = 0; o < SW; ++o) {
-                const int k = t - o;
-                if (k >= 0 && k < 11) {
-                    const float g = G.g[k];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) m[q][o] = fmaf(g, v[q], m[q][o]);
-                }
-            }
-        }
-        const int gx = tx0 - R + j;
-#pragma unroll
-        for (int o = 0; o < SW; ++o) {
-            const int i = i0 + o;
-            if (i >= T1) continue;
-            const int gy = ty0 - R + i;
-            float A = 0.f, Bv = 0.f, Cv = 0.f;
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                const float mu1 = m[0][o], mu2 = m[1][o];
-                const float s11 = m[2][o] - mu1 * mu1, s22 = m[3][o] - mu2 * mu2, s12 = m[4][o] - mu1 * mu2;
-                const float n1 = 2.f * mu1 * mu2 + C1, n2 = 2.f * s12 + C2;
-                const float d1 = mu1 * mu1 + mu2 * mu2 + C1, d2 = s11 + s22 + C2;
-                const float inv = 1.f / (d1 * d2);
-                const float S = n1 * n2 * inv;
-                const bool center = i >= R && i < R + T && j >= R && j < R + T;
-                if (center) {
-                    s_ssim += S;
-                    if (ssim_map) ssim_map[(int64_t)plane * H * W + (int64_t)gy * W + gx] = S;
-                }
-                const float cot = cot_map ? __ldg(cot_map + (int64_t)plane * H * W + (int64_t)gy * W + gx) : c_ssim;
-                A = cot * (2.f * mu2 * (n2 - n1) * inv - 2.f * mu1 * S * (d2 - d1) * inv);
-                Bv = cot * (-S / d2);
-                Cv = cot * (2.f * n1 * inv);
-            }
-            const int e = i * T1 + j;
-            sA[0 * T1 * T1 + e] = A; sA[1 * T1 * T1 + e] = Bv; sA[2 * T1 * T1 + e] = Cv;
-        }
-    }
-    __syncthreads();
-    float s_l1 = 0.f, s_l2 = 0.f;
-    if (grad) {
-        // ---- adjoint, horizontal: rows of R1, columns of the tile ------------------------------------
-        // interior image columns receive the mirrored window (= the window: it is symmetric); only the first / last image column
-        // collect the taps folded onto them by the replicate padding (adj_w), recomputed on a slow path
-        float* sHA = sH;    // [3][T1][T]
-        constexpr int AW = 8;
-        for (int it = tid; it < T1 * (T / AW); it += kThreads) {
-            const int i = it / (T / AW), q0 = (it - i * (T / AW)) * AW;
-            float a[3][AW];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int o = 0; o < AW; ++o) a[c][o] = 0.f;
-#pragma unroll
-            for (int t = 0; t < AW + 10; ++t) {
-                const int oo = i * T1 + q0 + t;                          // q0 + t <= 24 + 17 = 41 < T1
-                const float v0 = sA[oo], v1 = sA[T1 * T1 + oo], v2 = sA[2 * T1 * T1 + oo];
-#pragma unroll
-                for (int o = 0; o < AW; ++o) {
+        tc::cp_async_commit();
+        tc::cp_async_wait(0);
+        __syncthreads();
+        // All four separable passes are REGISTER-BLOCKED: a thread produces a strip of SW consecutive outputs along the filter axis from
+        // SW + 10 inputs it reads once (sliding window), instead of 11 shared-memory reads per output and map.  The first version (one
+        // output per thread per pass) was bound by shared-memory bandwidth: ~300 LDS per pixel, 363 us for 24 images.
+        // ---- horizontal Gaussian of the five products: rows of R2, columns of R1 -------------------------
+        constexpr int SW = 11, NS = (T1 + SW - 1) / SW;        // 4 strips of 11 cover the 42 columns / rows of R1
+        for (int it = tid; it < T2 * NS; it += kThreads) {
+            const int i = it / NS, sidx = it - i * NS, j0 = sidx * SW;        // lanes: 8 rows x 4 strips -> conflict-free reads
+            float acc[5][SW];
+    #pragma unroll
+            for (int q = 0; q < 5; ++q)
+    #pragma unroll
+                for (int o = 0; o < SW; ++o) acc[q][o] = 0.f;
+    #pragma unroll
+            for (int t = 0; t < SW + 10; ++t) {
+                const int jj = min(j0 + t, T2 - 1);                         // columns past the halo only feed outputs that are dropped
+                const float x = sX[i * T2 + jj], y = sY[i * T2 + jj];
+                const float xx = x * x, yy = y * y, xy = x * y;
+    #pragma unroll
+                for (int o = 0; o < SW; ++o) {
                     const int k = t - o;
                     if (k >= 0 && k < 11) {
-                        const float w = G.g[10 - k];
-                        a[0][o] = fmaf(w, v0, a[0][o]); a[1][o] = fmaf(w, v1, a[1][o]); a[2][o] = fmaf(w, v2, a[2][o]);
+                        const float g = G.g[k];
+                        acc[0][o] = fmaf(g, x, acc[0][o]); acc[1][o] = fmaf(g, y, acc[1][o]);
+                        acc[2][o] = fmaf(g, xx, acc[2][o]); acc[3][o] = fmaf(g, yy, acc[3][o]); acc[4][o] = fmaf(g, xy, acc[4][o]);
                     }
                 }
             }
-#pragma unroll
-            for (int o = 0; o < AW; ++o) {
-                const int q = q0 + o, gq = tx0 + q;
-                float a0 = a[0][o], a1 = a[1][o], a2 = a[2][o];
-                if (gq >= W) { a0 = a1 = a2 = 0.f; }
-                else if (gq == 0 || gq == W - 1) {
-                    a0 = a1 = a2 = 0.f;
-                    for (int k = 0; k < 11; ++k) {          // forward centre p = gq - 5 + k  <->  R1 column q + k
-                        const float w = adj_w(G, gq - R + k, gq, W);
-                        const int oo = i * T1 + q + k;
-                        a0 = fmaf(w, sA[oo], a0); a1 = fmaf(w, sA[T1 * T1 + oo], a1); a2 = fmaf(w, sA[2 * T1 * T1 + oo], a2);
-                    }
+    #pragma unroll
+            for (int o = 0; o < SW; ++o) {
+                if (j0 + o < T1) {
+    #pragma unroll
+                    for (int q = 0; q < 5; ++q) sH[q * T2 * T1 + i * T1 + j0 + o] = acc[q][o];
                 }
-                const int e = i * T + q;
-                sHA[e] = a0; sHA[T1 * T + e] = a1; sHA[2 * T1 * T + e] = a2;
             }
         }
         __syncthreads();
-        // ---- adjoint, vertical + assemble the gradient -----------------------------------------------
-        constexpr int VW = 4;
-        for (int it = tid; it < (T / VW) * T; it += kThreads) {
-            const int sidx = it / T, j = it - sidx * T, i0 = sidx * VW;
-            const int gx = tx0 + j;
-            float a[3][VW];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int o = 0; o < VW; ++o) a[c][o] = 0.f;
-#pragma unroll
-            for (int t = 0; t < VW + 10; ++t) {
-                const int oo = (i0 + t) * T + j;                         // i0 + t <= 28 + 13 = 41 < T1
-                const float v0 = sHA[oo], v1 = sHA[T1 * T + oo], v2 = sHA[2 * T1 * T + oo];
-#pragma unroll
-                for (int o = 0; o < VW; ++o) {
+        // ---- vertical Gaussian -> moments -> SSIM and its partial derivatives on R1 ----------------------
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+        for (int it = tid; it < NS * T1; it += kThreads) {
+            const int sidx = it / T1, j = it - sidx * T1, i0 = sidx * SW;    // lanes along a row: conflict-free
+            float m[5][SW];
+    #pragma unroll
+            for (int q = 0; q < 5; ++q)
+    #pragma unroll
+                for (int o = 0; o < SW; ++o) m[q][o] = 0.f;
+    #pragma unroll
+            for (int t = 0; t < SW + 10; ++t) {
+                const int row = min(i0 + t, T2 - 1);
+                float v[5];
+    #pragma unroll
+                for (int q = 0; q < 5; ++q) v[q] = sH[q * T2 * T1 + row * T1 + j];
+    #pragma unroll
+                for (int o = 0; o < SW; ++o) {
                     const int k = t - o;
                     if (k >= 0 && k < 11) {
-                        const float w = G.g[10 - k];
-                        a[0][o] = fmaf(w, v0, a[0][o]); a[1][o] = fmaf(w, v1, a[1][o]); a[2][o] = fmaf(w, v2, a[2][o]);
+                        const float g = G.g[k];
+    #pragma unroll
+                        for (int q = 0; q < 5; ++q) m[q][o] = fmaf(g, v[q], m[q][o]);
                     }
                 }
             }
-#pragma unroll
-            for (int o = 0; o < VW; ++o) {
-                const int i = i0 + o, gy = ty0 + i;
-                if (gy >= H || gx >= W) continue;
-                float a0 = a[0][o], a1 = a[1][o], a2 = a[2][o];
-                if (gy == 0 || gy == H - 1) {
-                    a0 = a1 = a2 = 0.f;
-                    for (int k = 0; k < 11; ++k) {
-                        const float w = adj_w(G, gy - R + k, gy, H);
-                        const int oo = (i + k) * T + j;
-                        a0 = fmaf(w, sHA[oo], a0); a1 = fmaf(w, sHA[T1 * T + oo], a1); a2 = fmaf(w, sHA[2 * T1 * T + oo], a2);
+            const int gx = tx0 - R + j;
+    #pragma unroll
+            for (int o = 0; o < SW; ++o) {
+                const int i = i0 + o;
+                if (i >= T1) continue;
+                const int gy = ty0 - R + i;
+                float A = 0.f, Bv = 0.f, Cv = 0.f;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    const float mu1 = m[0][o], mu2 = m[1][o];
+                    const float s11 = m[2][o] - mu1 * mu1, s22 = m[3][o] - mu2 * mu2, s12 = m[4][o] - mu1 * mu2;
+                    const float n1 = 2.f * mu1 * mu2 + C1, n2 = 2.f * s12 + C2;
+                    const float d1 = mu1 * mu1 + mu2 * mu2 + C1, d2 = s11 + s22 + C2;
+                    const float inv = 1.f / (d1 * d2);
+                    const float S = n1 * n2 * inv;
+                    const bool center = i >= R && i < R + T && j >= R && j < R + T;
+                    if (center) {
+                        s_ssim += S;
+                        if (ssim_map) ssim_map[(int64_t)plane * H * W + (int64_t)gy * W + gx] = S;
                     }
+                    const float cot = cot_map ? __ldg(cot_map + (int64_t)plane * H * W + (int64_t)gy * W + gx) : c_ssim;
+                    A = cot * (2.f * mu2 * (n2 - n1) * inv - 2.f * mu1 * S * (d2 - d1) * inv);
+                    Bv = cot * (-S / d2);
+                    Cv = cot * (2.f * n1 * inv);
                 }
-                const float x = __ldg(xp + (int64_t)gy * W + gx), y = __ldg(yp + (int64_t)gy * W + gx);      // (L2 hits: the tile was just read)
-                const float d = x - y;
-                s_l1 += fabsf(d); s_l2 += d * d;
-                const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-                grad[(int64_t)plane * H * W + (int64_t)gy * W + gx] = a0 + 2.f * x * a1 + y * a2 + c_l1 * sg + c_l2 * 2.f * d;
+                const int e = i * T1 + j;
+                sA[0 * T1 * T1 + e] = A; sA[1 * T1 * T1 + e] = Bv; sA[2 * T1 * T1 + e] = Cv;
             }
         }
-    } else {
-        for (int e = tid; e < T * T; e += kThreads) {
-            const int i = e / T, j = e - i * T;
-            if (ty0 + i >= H || tx0 + j >= W) continue;
-            const float d = __ldg(xp + (int64_t)(ty0 + i) * W + tx0 + j) - __ldg(yp + (int64_t)(ty0 + i) * W + tx0 + j);
-            s_l1 += fabsf(d); s_l2 += d * d;
+        __syncthreads();
+        if (grad) {
+            // ---- adjoint, horizontal: rows of R1, columns of the tile ------------------------------------
+            // interior image columns receive the mirrored window (= the window: it is symmetric); only the first / last image column
+            // collect the taps folded onto them by the replicate padding (adj_w), recomputed on a slow path
+            float* sHA = sH;    // [3][T1][T]
+            constexpr int AW = 8;
+            for (int it = tid; it < T1 * (T / AW); it += kThreads) {
+                const int i = it / (T / AW), q0 = (it - i * (T / AW)) * AW;
+                float a[3][AW];
+    #pragma unroll
+                for (int c = 0; c < 3; ++c)
+    #pragma unroll
+                    for (int o = 0; o < AW; ++o) a[c][o] = 0.f;
+    #pragma unroll
+                for (int t = 0; t < AW + 10; ++t) {
+                    const int oo = i * T1 + q0 + t;                          // q0 + t <= 24 + 17 = 41 < T1
+                    const float v0 = sA[oo], v1 = sA[T1 * T1 + oo], v2 = sA[2 * T1 * T1 + oo];
+    #pragma unroll
+                    for (int o = 0; o < AW; ++o) {
+                        const int k = t - o;
+                        if (k >= 0 && k < 11) {
+                            const float w = G.g[10 - k];
+                            a[0][o] = fmaf(w, v0, a[0][o]); a[1][o] = fmaf(w, v1, a[1][o]); a[2][o] = fmaf(w, v2, a[2][o]);
+                        }
+                    }
+                }
+    #pragma unroll
+                for (int o = 0; o < AW; ++o) {
+                    const int q = q0 + o, gq = tx0 + q;
+                    float a0 = a[0][o], a1 = a[1][o], a2 = a[2][o];
+                    if (gq >= W) { a0 = a1 = a2 = 0.f; }
+                    else if (gq == 0 || gq == W - 1) {
+                        a0 = a1 = a2 = 0.f;
+                        for (int k = 0; k < 11; ++k) {          // forward centre p = gq - 5 + k  <->  R1 column q + k
+                            const float w = adj_w(G, gq - R + k, gq, W);
+                            const int oo = i * T1 + q + k;
+                            a0 = fmaf(w, sA[oo], a0); a1 = fmaf(w, sA[T1 * T1 + oo], a1); a2 = fmaf(w, sA[2 * T1 * T1 + oo], a2);
+                        }
+                    }
+                    const int e = i * T + q;
+                    sHA[e] = a0; sHA[T1 * T + e] = a1; sHA[2 * T1 * T + e] = a2;
+                }
+            }
+            __syncthreads();
+            // ---- adjoint, vertical + assemble the gradient -----------------------------------------------
+            constexpr int VW = 4;
+            for (int it = tid; it < (T / VW) * T; it += kThreads) {
+                const int sidx = it / T, j = it - sidx * T, i0 = sidx * VW;
+                const int gx = tx0 + j;
+                float a[3][VW];
+    #pragma unroll
+                for (int c = 0; c < 3; ++c)
+    #pragma unroll
+                    for (int o = 0; o < VW; ++o) a[c][o] = 0.f;
+    #pragma unroll
+                for (int t = 0; t < VW + 10; ++t) {
+                    const int oo = (i0 + t) * T + j;                         // i0 + t <= 28 + 13 = 41 < T1
+                    const float v0 = sHA[oo], v1 = sHA[T1 * T + oo], v2 = sHA[2 * T1 * T + oo];
+    #pragma unroll
+                    for (int o = 0; o < VW; ++o) {
+                        const int k = t - o;
+                        if (k >= 0 && k < 11) {
+                            const float w = G.g[10 - k];
+                            a[0][o] = fmaf(w, v0, a[0][o]); a[1][o] = fmaf(w, v1, a[1][o]); a[2][o] = fmaf(w, v2, a[2][o]);
+                        }
+                    }
+                }
+    #pragma unroll
+                for (int o = 0; o < VW; ++o) {
+                    const int i = i0 + o, gy = ty0 + i;
+                    if (gy >= H || gx >= W) continue;
+                    float a0 = a[0][o], a1 = a[1][o], a2 = a[2][o];
+                    if (gy == 0 || gy == H - 1) {
+                        a0 = a1 = a2 = 0.f;
+                        for (int k = 0; k < 11; ++k) {
+                            const float w = adj_w(G, gy - R + k, gy, H);
+                            const int oo = (i + k) * T + j;
+                            a0 = fmaf(w, sHA[oo], a0); a1 = fmaf(w, sHA[T1 * T + oo], a1); a2 = fmaf(w, sHA[2 * T1 * T + oo], a2);
+                        }
+                    }
+                    const float x = __ldg(xp + (int64_t)gy * W + gx), y = __ldg(yp + (int64_t)gy * W + gx);      // (L2 hits: the tile was just read)
+                    const float d = x - y;
+                    s_l1 += fabsf(d); s_l2 += d * d;
+                    const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                    grad[(int64_t)plane * H * W + (int64_t)gy * W + gx] = a0 + 2.f * x * a1 + y * a2 + c_l1 * sg + c_l2 * 2.f * d;
+                }
+            }
+        } else {
+            for (int e = tid; e < T * T; e += kThreads) {
+                const int i = e / T, j = e - i * T;
+                if (ty0 + i >= H || tx0 + j >= W) continue;
+                const float d = __ldg(xp + (int64_t)(ty0 + i) * W + tx0 + j) - __ldg(yp + (int64_t)(ty0 + i) * W + tx0 + j);
+                s_l1 += fabsf(d); s_l2 += d * d;
+            }
         }
     }
     // ---- deterministic reduction of the three sums ----------------------------------------------------

@@ -263,6 +263,76 @@ __global__ void __launch_bounds__(kThreads) grid_sample_fwd_packed_kernel(const 
     }
 }
 
+// ---- gather form of the warp's adjoint for a FIXED grid (the attack loops: the model is frozen) -------------------------
+// warp_taps_kernel lists, per output pixel p and bilinear tap k, the input pixel q it reads and its weight (mask folded in; q = HWi marks an
+// unused tap).  Sorted by q once per attack (host side: a stable sort, so the summation order is fixed) this is the CSR matrix of the adjoint:
+// grid_sample_bwd_gather_kernel then gives every input pixel the sum of its contributions -- no atomics, no zero-fill of dimg, a deterministic
+// result -- and the per-sample squared norm of the (clamp-masked) gradient that the normalised step needs comes out of the same pass.
+__global__ void __launch_bounds__(kThreads) warp_taps_kernel(const float* __restrict__ grid, const float* __restrict__ mask, int Hi, int Wi, int H, int W,
+                                                             int* __restrict__ ent_q, float* __restrict__ ent_w) {
+    const int HW = H * W, HWi = Hi * Wi;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+        const warp::Taps<float> t = warp::make_taps<float>(__ldg(grid + p), __ldg(grid + HW + p), Hi, Wi);
+        const float wx0 = 1.f - t.wx1, wy0 = 1.f - t.wy1;
+        const float m = mask ? __ldg(mask + p) : 1.f;
+        const bool on = !(mask && m == 0.f);
+        const int o00 = t.y0 * Wi + t.x0;
+        const bool v[4] = {t.vy0 && t.vx0, t.vy0 && t.vx1, t.vy1 && t.vx0, t.vy1 && t.vx1};
+        const int q[4] = {o00, o00 + 1, o00 + Wi, o00 + Wi + 1};
+        const float w[4] = {wx0 * wy0, t.wx1 * wy0, wx0 * t.wy1, t.wx1 * t.wy1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool ok = on && v[k];
+            ent_q[k * HW + p] = ok ? q[k] : HWi;
+            ent_w[k * HW + p] = ok ? w[k] : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) grid_sample_bwd_gather_kernel(const float* __restrict__ dout, const float* __restrict__ dout2, int64_t dout2_bs,
+                                                                          const float* __restrict__ rough, int64_t rough_bs,
+                                                                          const int* __restrict__ row_ptr, const int* __restrict__ ent_p,
+                                                                          const float* __restrict__ ent_w, const float* __restrict__ ent_m, int C, int HWi,
+                                                                          int HW, const float* __restrict__ xclamp, float lo, float hi,
+                                                                          float* __restrict__ dimg, float* __restrict__ sq, float* __restrict__ partial,
+                                                                          unsigned* __restrict__ counter) {
+    __shared__ float red[32];
+    __shared__ bool is_last;
+    const int b = blockIdx.y;
+    const float* db = dout + (int64_t)b * C * HW;
+    const float* d2 = dout2 ? dout2 + (int64_t)b * dout2_bs : nullptr;
+    const float* rb = dout2 ? rough + (int64_t)b * rough_bs : nullptr;
+    float s[1] = {0.f};
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HWi; q += gridDim.x * blockDim.x) {
+        float acc[3] = {0.f, 0.f, 0.f};
+        const int e0 = __ldg(row_ptr + q), e1 = __ldg(row_ptr + q + 1);
+        for (int e = e0; e < e1; ++e) {
+            const int p = __ldg(ent_p + e);
+            const float w = __ldg(ent_w + e), m = __ldg(ent_m + e);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c < C) {
+                    float d = __ldg(db + (int64_t)c * HW + p);
+                    if (d2) d += __ldg(d2 + (int64_t)c * HW + p) * __ldg(rb + (int64_t)c * HW + p);
+                    d *= m;                                     // same factor order as the scatter kernel: ((dout + dout2 * rough) * mask) * weight
+                    acc[c] = fmaf(d, w, acc[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c < C) {
+                const int64_t o = ((int64_t)b * C + c) * HWi + q;
+                dimg[o] = acc[c];
+                float v = acc[c];
+                if (xclamp) { const float x = __ldg(xclamp + o); if (!(x >= lo && x <= hi)) v = 0.f; }
+                s[0] = fmaf(v, v, s[0]);
+            }
+        }
+    }
+    if (sq) row_reduce_finish<1>(s, b, partial, counter, sq, red, &is_last);
+}
+
 inline int blocks_for(int64_t n, int cap_mult = 8) {
     int64_t g = (n + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)kNumSMs * cap_mult;
@@ -398,6 +468,40 @@ int spaa_grid_sample_fwd_packed(const float* img, int64_t B, int Hi, int Wi, con
         grid_sample_fwd_packed_kernel<false><<<g, kThreads, 0, (cudaStream_t)stream>>>(img, Hi, Wi, grid, grid_bstride, H, W, clamp01, mask, rough, rough_bstride,
                                                                                      (uint4*)out16);
     SPAA_CHECK_LAUNCH("spaa_grid_sample_fwd_packed");
+    return SPAA_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int spaa_warp_taps(const float* grid, const float* mask, int Hi, int Wi, int H, int W, int32_t* ent_q, float* ent_w, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(grid && ent_q && ent_w && Hi > 0 && Wi > 0 && H > 0 && W > 0 && (int64_t)Hi * Wi < (1ll << 30) && (int64_t)H * W < (1ll << 28),
+                   "spaa_warp_taps: bad arguments");
+    warp_taps_kernel<<<blocks_for((int64_t)H * W), kThreads, 0, (cudaStream_t)stream>>>(grid, mask, Hi, Wi, H, W, ent_q, ent_w);
+    SPAA_CHECK_LAUNCH("spaa_warp_taps");
+    return SPAA_OK;
+}
+
+int64_t spaa_grid_sample_bwd_gather_ws_bytes(int64_t B, int Hi, int Wi) {
+    return row_reduce_ws_bytes(B, row_reduce_nblk((int64_t)Hi * Wi, 2048), 1);
+}
+
+int spaa_grid_sample_bwd_gather(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough, int64_t rough_bstride,
+                                const int32_t* row_ptr, const int32_t* ent_p, const float* ent_w, const float* ent_m, int64_t B, int C, int Hi, int Wi,
+                                int H, int W, const float* x_for_clamp, float lo, float hi, float* dimg, float* sq, void* ws, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(dout && row_ptr && ent_p && ent_w && ent_m && dimg && B > 0 && B < 65536 && C >= 1 && C <= 3 && Hi > 0 && Wi > 0 && H > 0 && W > 0,
+                   "spaa_grid_sample_bwd_gather: bad arguments");
+    SPAA_CHECK_ARG((dout2 == nullptr) || rough, "spaa_grid_sample_bwd_gather: dout2 needs rough");
+    SPAA_CHECK_ARG((sq == nullptr) || ws, "spaa_grid_sample_bwd_gather: sq needs the workspace");
+    const int HWi = Hi * Wi;
+    const int nblk = row_reduce_nblk(HWi, 2048);
+    float* partial = (float*)ws;
+    unsigned* counter = ws ? (unsigned*)(partial + B * nblk) : nullptr;
+    grid_sample_bwd_gather_kernel<<<dim3(nblk, (unsigned)B), kThreads, 0, (cudaStream_t)stream>>>(dout, dout2, dout2_bstride, rough, rough_bstride, row_ptr, ent_p,
+                                                                                                 ent_w, ent_m, C, HWi, H * W, x_for_clamp, lo, hi, dimg, sq,
+                                                                                                 partial, counter);
+    SPAA_CHECK_LAUNCH("spaa_grid_sample_bwd_gather");
     return SPAA_OK;
 }
 

@@ -293,6 +293,55 @@ def grid_sample_bwd_input(dout: Tensor, grid: Tensor, in_hw, *, mask: Optional[T
     return dimg
 
 
+class WarpAdjoint:
+    """CSR form of the adjoint of a FIXED bilinear warp (planar grid [2,H,W] shared by the batch, optional mask [H*W]): built once per attack,
+    then every backward is a gather (grid_sample_bwd_gather) -- deterministic, no atomics, no zero-fill, squared norm fused."""
+
+    def __init__(self, grid: Tensor, in_hw, mask: Optional[Tensor] = None):
+        grid = _f32c(grid)
+        assert grid.dim() == 3 and grid.shape[0] == 2, "WarpAdjoint needs one planar grid [2,H,W] shared by the batch"
+        _, H, W = grid.shape
+        Hi, Wi = int(in_hw[0]), int(in_hw[1])
+        HW, HWi = H * W, Hi * Wi
+        dev = grid.device
+        ent_q = torch.empty(4 * HW, dtype=torch.int32, device=dev)
+        ent_w = torch.empty(4 * HW, dtype=torch.float32, device=dev)
+        m = _f32c(mask).reshape(-1) if mask is not None else None
+        lib().spaa_warp_taps(_p(grid), _p(m), Hi, Wi, H, W, _p(ent_q), _p(ent_w), _stream()); _count()
+        # once per attack: stable sort by input pixel (fixes the summation order), CSR offsets by binary search -- plumbing, not the hot path
+        q_sorted, order = torch.sort(ent_q.long(), stable=True)
+        n_used = int((q_sorted < HWi).sum())
+        order = order[:n_used]
+        self.ent_p = (order % HW).to(torch.int32).contiguous()
+        self.ent_w = ent_w[order].contiguous()
+        self.ent_m = (m[self.ent_p.long()] if m is not None else torch.ones(n_used, device=dev)).contiguous()
+        self.row_ptr = torch.searchsorted(q_sorted[:n_used].contiguous(), torch.arange(HWi + 1, device=dev)).to(torch.int32).contiguous()
+        self.in_hw, self.out_hw = (Hi, Wi), (H, W)
+
+
+def grid_sample_bwd_gather(adj: WarpAdjoint, dout: Tensor, *, dout2: Optional[Tensor] = None, rough: Optional[Tensor] = None,
+                           dimg: Optional[Tensor] = None, sq: Optional[Tensor] = None, x_for_clamp: Optional[Tensor] = None, lo: float = 0.0,
+                           hi: float = 1.0) -> Tensor:
+    """dimg = adjoint-warp of (dout + dout2 * rough) * mask through `adj`; sq[b] (optional) = squared norm of dimg[b] over the entries whose
+    x_for_clamp lies in [lo,hi] (all entries without it)."""
+    dout = _f32c(dout)
+    B, C, H, W = dout.shape
+    assert (H, W) == adj.out_hw and C <= 3
+    Hi, Wi = adj.in_hw
+    if dimg is None:
+        dimg = torch.empty((B, C, Hi, Wi), dtype=torch.float32, device=dout.device)
+    db = rb = 0
+    if dout2 is not None:
+        assert dout2.stride(1) == H * W and dout2.stride(3) == 1 and rough.stride(1) == H * W
+        db, rb = dout2.stride(0), _bstride(rough, B)
+    L = lib()
+    ws = workspace("gs_gather", L.spaa_grid_sample_bwd_gather_ws_bytes(B, Hi, Wi), dout.device) if sq is not None else None
+    L.spaa_grid_sample_bwd_gather(_p(dout), _p(dout2), db, _p(rough) if dout2 is not None else None, rb, _p(adj.row_ptr), _p(adj.ent_p), _p(adj.ent_w),
+                                  _p(adj.ent_m), B, C, Hi, Wi, H, W, _p(_f32c(x_for_clamp)) if x_for_clamp is not None else None, float(lo), float(hi),
+                                  _p(dimg), _p(sq), _p(ws), _stream()); _count()
+    return dimg
+
+
 def grid_sample_bwd_grid(dout: Tensor, img: Tensor, grid: Tensor, *, clamp01: bool = False, mask: Optional[Tensor] = None,
                          dout2: Optional[Tensor] = None, rough: Optional[Tensor] = None) -> Tensor:
     dout, img, grid = _f32c(dout), _f32c(img), _f32c(grid)

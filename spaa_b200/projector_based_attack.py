@@ -45,8 +45,10 @@ class SpaaAttack:
     `SpaaAttack(...)`, `iters` x `step()`, `result()`; bench.py drives `step()` directly to time exactly K iterations."""
 
     def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
-                 graph: Optional[bool] = None, fold_bn: Optional[bool] = None):
-        """graph: replay one captured CUDA graph per iteration (default: on for the fused PCNet path).  An iteration is a fixed
+                 graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False):
+        """deterministic: the warp's backward runs as a gather through a per-attack CSR adjoint map instead of a scatter-add with atomics
+        (same result to fp32 rounding, bit-identical run to run, ~20 us slower per iteration at B=32).
+        graph: replay one captured CUDA graph per iteration (default: on for the fused PCNet path).  An iteration is a fixed
         sequence of ~80 of our launches + ~300 cuDNN/ATen launches of the external classifier with no host decision in
         between, so after two eager iterations (which fill the packed-weight / workspace caches) the third is captured and
         every later step() is a single cudaGraphLaunch.
@@ -91,11 +93,15 @@ class SpaaAttack:
         self.pcnet = pcnet
         self.net = net = _unwrap(pcnet)
         self.fused = isinstance(net, PCNet)
+        self.warp_adj = None
         if self.fused:
             with torch.no_grad():
                 self.sh = sh = net.shading_net
                 self.grid = net.warping_net.planar_grid(prj_hw).detach()
                 self.mask = net.flat_mask()
+                # measured at B=32: scatter-add (atomics) 52 us + norm 17 us + zero-fill vs 95 us for the gather form -- the gather is the
+                # opt-in, bit-reproducible variant
+                self.warp_adj = ops.WarpAdjoint(self.grid, prj_hw, self.mask) if deterministic else None
                 self.skip_acts = _Stack.skip1(sh, scene)                      # skipConv1(cam_scene): loop constant
                 self.xw = torch.empty(B, 3, H, W, device=device)
                 self.tc = _Stack.act_dtype(sh) != torch.float32          # tensor-core path: packed 16-channel boundary tensors
@@ -219,8 +225,14 @@ class SpaaAttack:
                     dxw, dsf, _ = _Stack.backward(self.sh, S, d_pre6, need_dx=True, surf_grad_channels=(3, 6), d_pre6_packed=d_pk)
                 else:
                     dxw, dsf, _ = _Stack.backward(self.sh, S, d_pre6, need_dx=True, d_pre6_packed=d_pk)
-                ops.grid_sample_bwd_input(dxw, self.grid, self.prj_hw, mask=self.mask, dout2=dsf, rough=scene if dsf is not None else None,
-                                          dimg=self.dprj)
+                if self.warp_adj is not None:
+                    # deterministic mode: adjoint of the warp as a gather through the per-attack CSR map (no atomics); without the prjl2 term the
+                    # per-sample squared norm of the clamp-masked gradient (:307,315) comes out of the same pass
+                    ops.grid_sample_bwd_gather(self.warp_adj, dxw, dout2=dsf, rough=scene if dsf is not None else None, dimg=self.dprj,
+                                               sq=None if self.w_prjl2 else self.sq, x_for_clamp=None if self.w_prjl2 else self.prj_adv)
+                else:
+                    ops.grid_sample_bwd_input(dxw, self.grid, self.prj_hw, mask=self.mask, dout2=dsf, rough=scene if dsf is not None else None,
+                                              dimg=self.dprj)
             S = None
         else:
             ops.select_cotangent(g_adv, self.g_col, self.use_col, None, 0, self.d_pre6)
@@ -232,7 +244,8 @@ class SpaaAttack:
             ops.chan_l2(self.prj_adv, self.gray, self.sq, c=self.w_prjl2 / self.hw_prj, sel=self.use_col, apply_clamp_mask=clamp_in_kernel,
                         grad=self.dprj)
             clamp_in_kernel = False
-        ops.row_sqnorm(self.dprj, self.sq, self.prj_adv if clamp_in_kernel else None)
+        if not (self.fused and self.warp_adj is not None and not self.w_prjl2):    # (deterministic mode without prjl2: the gather kernel produced sq)
+            ops.row_sqnorm(self.dprj, self.sq, self.prj_adv if clamp_in_kernel else None)
         ops.row_normalized_step(self.prj_adv, self.dprj, self.sq, self.step2, self.use_col, use_clamp_mask=clamp_in_kernel,
                                 copy_dst=self.prj_best, copy_sel=self.succ)
         ops.masked_copy_rows(self.cam_best, cam, self.succ)
@@ -251,7 +264,7 @@ def _state_version(module) -> int:
 
 
 def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
-                  graph: Optional[bool] = None, fold_bn: Optional[bool] = None) -> SpaaAttack:
+                  graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False) -> SpaaAttack:
     """A SpaaAttack for this job.  Sweeps call spaa() many times with the same model, classifier, batch size and loss
     configuration (run_projector_based_attack, projector_based_attack.py:83-129): the engine -- its buffers and its captured
     CUDA graph -- is kept (LRU of 2) and only reset() for the new scene / targets.  A model whose parameters changed in
@@ -259,18 +272,19 @@ def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, ste
     net = _unwrap(pcnet)
     if not isinstance(net, PCNet) or graph is False:
         return SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph,
-                          fold_bn=fold_bn)
+                          fold_bn=fold_bn, deterministic=deterministic)
     if precision is not None:
         set_precision(net, precision)
     scene_shape = tuple(expand_4d(cam_scene).shape)
     key = (id(net), _state_version(net), id(getattr(classifier, "model", classifier)), len(target_idx), bool(targeted), stealth_loss, float(d_thr),
            tuple(setup_info["classifier_crop_sz"]), tuple(setup_info["prj_im_sz"]), float(setup_info["prj_brightness"]), scene_shape,
-           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32), fold_bn)
+           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32), fold_bn, bool(deterministic))
     hit = _ENGINES.get(key)
     if hit is not None and hit[0]() is net and hit[1]() is getattr(classifier, "model", classifier):
         _ENGINES.move_to_end(key)
         return hit[2].reset(cam_scene, target_idx)
-    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, graph=graph, fold_bn=fold_bn)
+    A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, graph=graph, fold_bn=fold_bn,
+                   deterministic=deterministic)
     try:
         _ENGINES[key] = (weakref.ref(net), weakref.ref(getattr(classifier, "model", classifier)), A)
     except TypeError:               # classifier object without weak-reference support: do not cache
@@ -286,13 +300,14 @@ def clear_engines() -> None:
 
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,
          iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None,
-         precision: Optional[str] = None, graph: Optional[bool] = None, fold_bn: Optional[bool] = None):
+         precision: Optional[str] = None, graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False):
     """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1)).
     Keyword-only extras (reference defaults): iters=50; precision None (keep the model's), 'fp32', 'fp16' or 'bf16';
     graph None (CUDA-graph replay of the iteration when the fused PCNet path is used), True or False; fold_bn None (fold the
-    frozen classifier's inference-mode BatchNorm into its convolutions when cuDNN may use TF32), True or False."""
+    frozen classifier's inference-mode BatchNorm into its convolutions when cuDNN may use TF32), True or False; deterministic False (True: the
+    warp's backward as an atomics-free gather)."""
     A = attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph,
-                      fold_bn=fold_bn)
+                      fold_bn=fold_bn, deterministic=deterministic)
     for it in range(iters):
         if forced_prj is not None:
             A.prj_adv.copy_(forced_prj[it])

@@ -628,3 +628,17 @@ def test_run_attack_sweep_matches_direct_calls_and_writes_the_reference_layout(t
             assert sorted(os.listdir(d)) == [f"img_{k:04d}.png" for k in range(1, 5)]
             back = ut.torch_imread(os.path.join(d, "img_0004.png"))                             # the untargeted result is stored last (:137-138)
             assert (back - ref[3].clamp(0, 1)).abs().max().item() <= 1.0 / 255 + 1e-6
+
+
+def test_spaa_deterministic_mode_matches_default():
+    """deterministic=True swaps the scatter-add backward of the warp (atomics) for the gather through the per-attack CSR adjoint map with the
+    fused norm: same attack within fp32 rounding, for both stealth-loss families (with / without the projector L2 term)."""
+    from spaa_b200 import projector_based_attack as pba
+    P, m, scene = _spaa_setup()
+    targets = [808, 969, 116, 786]
+    for loss_name in ("camdE_caml2", "prjl2_caml2_camdE"):
+        pba.clear_engines()
+        cam_a, prj_a = pba.spaa(m, TinyClf(1), LABELS, targets, True, scene, 2.0, loss_name, dev(), SETUP, iters=6)
+        cam_b, prj_b = pba.spaa(m, TinyClf(1), LABELS, targets, True, scene, 2.0, loss_name, dev(), SETUP, iters=6, deterministic=True)
+        close_per_sample(prj_b, prj_a, 2e-4, f"{loss_name}: projector images")
+        close_per_sample(cam_b, cam_a, 2e-4, f"{loss_name}: camera images")

@@ -162,6 +162,20 @@ def test_grid_sample_forward_backward(shared_grid):
     dimg = ops.grid_sample_bwd_input(c1.to(dev()), gp.to(dev()), (Hi, Wi), mask=mask.flatten().to(dev()), dout2=c2.to(dev()), rough=rough.to(dev()))
     inside = ((img >= 0) & (img <= 1)).float()
     close(dimg.cpu() * inside, gx, 1e-5, 1e-5, "dimg")
+    if shared_grid:
+        # gather form through the per-attack CSR adjoint map: same gradient, no atomics; fused squared norm of the clamp-masked gradient
+        adj = ops.WarpAdjoint(gp.to(dev()), (Hi, Wi), mask.flatten().to(dev()))
+        sq = torch.empty(B, device=dev())
+        dimg2 = ops.grid_sample_bwd_gather(adj, c1.to(dev()), dout2=c2.to(dev()), rough=rough.to(dev()), sq=sq, x_for_clamp=img.to(dev()))
+        close(dimg2.cpu() * inside, gx, 1e-5, 1e-5, "dimg (gather)")
+        close(sq, (gx.double() ** 2).flatten(1).sum(1), 1e-5, 1e-5, "fused squared norm")
+        again = ops.grid_sample_bwd_gather(adj, c1.to(dev()), dout2=c2.to(dev()), rough=rough.to(dev()))
+        assert torch.equal(again, dimg2), "the gather adjoint must be deterministic"
+        no_mask = ops.WarpAdjoint(gp.to(dev()), (Hi, Wi))
+        d3 = ops.grid_sample_bwd_gather(no_mask, c1.to(dev()))
+        y3 = F.grid_sample(x, gq.expand(B, -1, -1, -1), align_corners=True)
+        g3, = torch.autograd.grad((y3 * c1).sum(), x)
+        close(d3, g3, 1e-5, 1e-5, "dimg (gather, no mask / rough / clamp)")
     dgrid = ops.grid_sample_bwd_grid(c1.to(dev()), img.to(dev()), gp.to(dev()), clamp01=True, mask=mask.flatten().to(dev()),
                                      dout2=c2.to(dev()), rough=rough.to(dev()))
     ref = gg.permute(0, 3, 1, 2)
