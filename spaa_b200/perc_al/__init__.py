@@ -32,7 +32,7 @@ class PerC_AL:
         self.device = torch.device(device)
 
     # ---------------------------------------------------------------------------------------------------------
-    def _run(self, logits_fn, inputs, labels, targeted, d_thr, p_thresh, projector_rules, trace):
+    def _run(self, logits_fn, inputs, labels, targeted, d_thr, p_thresh, projector_rules, trace, graph=True):
         if inputs.min() < 0 or inputs.max() > 1:
             raise ValueError("Input values should be in the [0, 1] range.")
         ops._need_cuda(inputs)
@@ -74,24 +74,53 @@ class PerC_AL:
             mode = 0
         if not projector_rules:                   # original `adversary`: no perturbation-size / confidence gates
             d_thr, p_thresh = -1.0, -1.0
-        for i in range(n_it):
+        # One iteration is a fixed launch sequence with no host decision (the step sizes of iteration i are staged into two device scalars
+        # first): after two eager iterations it is recorded in a CUDA graph and replayed -- the external classifier's two forward passes
+        # and one backward pass are ~100-300 small launches per iteration.
+        step_l, step_c = torch.empty(2, device=dev), torch.empty(2, device=dev)
+        use_graph = bool(graph) and trace is None and inputs.is_cuda
+        state = {}
+
+        def body():
             leaf = xs.detach().requires_grad_(True)
             with torch.enable_grad():
                 logits = logits_fn(leaf)
                 loss = sign * nn.functional.cross_entropy(logits, labels, reduction="sum")
                 g_a, = torch.autograd.grad(loss, leaf)
             ops.row_sqnorm(g_a, sq)
-            ops.row_normalized_step(delta, g_a, sq, tab_l[i], use_col, base=inputs, sum_out=xs2)
+            ops.row_normalized_step(delta, g_a, sq, step_l, use_col, base=inputs, sum_out=xs2)
             ops.color_loss(xs2, inputs, ref_lab, cam_is_lab2=True, de_weighting=True, c_de=1.0, c_l2=0.0, stats=stats, grad=g_c)
             ops.row_sqnorm(g_c, sq)
-            ops.row_normalized_step(delta, g_c, sq, tab_c[i], use_col)
+            ops.row_normalized_step(delta, g_c, sq, step_c, use_col)
             ops.percal_project(inputs, delta, xq, xs, l2sum)
             with torch.no_grad():
                 logits2 = logits_fn(xq)
             ops.percal_masks(logits2, labels, mode, 40.0, l2sum, hw, d_thr, p_thresh, stats, isadv, use_col, better, dis, best_dis)
             ops.masked_copy_rows(best, xq, isadv if projector_rules else better)      # :244-245 vs :128
+            state["g_a"] = g_a
+
+        g = None
+        for i in range(n_it):
+            step_l.copy_(tab_l[i])
+            step_c.copy_(tab_c[i])
+            if g is not None:
+                g.replay()
+            elif use_graph and i >= 2 and n_it - i >= 4 and not torch.cuda.is_current_stream_capturing():
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    g.capture_begin()
+                    try:
+                        body()                     # records the launches; the replay below executes this iteration
+                    finally:
+                        g.capture_end()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                g.replay()
+            else:
+                body()
             if trace is not None:
-                trace.append(dict(g_a=g_a.clone(), g_c=g_c.clone(), delta=delta.clone(), dis=dis.clone(), x_round=xq.clone(),
+                trace.append(dict(g_a=state["g_a"].clone(), g_c=g_c.clone(), delta=delta.clone(), dis=dis.clone(), x_round=xq.clone(),
                                   use_col=use_col.bool().clone(), isadv=isadv.bool().clone(), best=best.clone()))
         return best
 
@@ -103,7 +132,7 @@ class PerC_AL:
         return self._run(fn, inputs, labels, targeted, 0.0, 0.0, False, None)
 
     def adversary_projector(self, classifier, inputs: torch.Tensor, labels: torch.Tensor, imagenet_labels, d_thr, targeted: bool = True,
-                            cp_sz=(240, 240), trace: Optional[List[dict]] = None) -> torch.Tensor:
+                            cp_sz=(240, 240), trace: Optional[List[dict]] = None, graph: bool = True) -> torch.Tensor:
         """:133-256.  The frozen classifier is called as in spaa(): channels_last and BatchNorm-folded (private copy) when cuDNN may
         use TF32 (torch's default), the stock module in the exact-fp32 parity mode."""
         clf_cl = use_channels_last(classifier) if inputs.is_cuda else False
@@ -112,4 +141,4 @@ class PerC_AL:
 
         def fn(x):
             return device_logits(classifier, x, cp_sz, clf_cl)
-        return self._run(fn, inputs, labels, targeted, float(d_thr), 0.9, True, trace)
+        return self._run(fn, inputs, labels, targeted, float(d_thr), 0.9, True, trace, graph)
