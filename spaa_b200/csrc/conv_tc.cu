@@ -812,16 +812,16 @@ bool tc_supported(const spaa_conv_desc* d, const char** why) {
     if (planar) {
         if (d->Cout < 1 || d->Cout > 32) return fail("fp32 planar output supports up to 32 channels");
         const int64_t hw = (int64_t)d->Hout * d->Wout;
-        if (d->out_ps != 1 || d->out_cs != hw || d->out_bs != hw * d->Cout) return fail("fp32 output must be dense NCHW");
+        if (d->out_ps != 1 || d->out_cs != hw || (d->B > 1 && d->out_bs != hw * d->Cout)) return fail("fp32 output must be dense NCHW");
     } else {
         if (d->Cout % 32 != 0 || d->Cout > 256) return fail("Cout must be a multiple of 32 (<= 256)");
-        if (d->out_cs != 1 || d->out_ps != d->Cout || d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout) return fail("16-bit output must be dense NHWC");
+        if (d->out_cs != 1 || d->out_ps != d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout)) return fail("16-bit output must be dense NHWC");
     }
     if (d->Cin == 16 && bn_for(d->Cout) != 32) return fail("Cin == 16 is implemented for Cout <= 32");
     if (d->Cin == 32 && bn_for(d->Cout) > 64) return fail("Cin == 32 is implemented for Cout <= 64");
     if (!((d->up == 1 && (d->stride == 1 || d->stride == 2)) || (d->up == 2 && d->stride == 1))) return fail("unsupported stride / up combination");
     if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return fail("square kernels up to 3x3 only");
-    if (d->in_cs != 1 || d->in_ps != d->Cin || d->in_bs != (int64_t)d->Hin * d->Win * d->Cin) return fail("input must be dense NHWC");
+    if (d->in_cs != 1 || d->in_ps != d->Cin || (d->B > 1 && d->in_bs != (int64_t)d->Hin * d->Win * d->Cin)) return fail("input must be dense NHWC");   // (a single image: any batch stride)
     return true;
 }
 

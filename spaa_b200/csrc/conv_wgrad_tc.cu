@@ -228,8 +228,8 @@ int spaa_conv_wgrad_tc_supported(const spaa_conv_desc* d) {
     if (!okc(d->Cin) || !okc(d->Cout)) return 0;
     if (d->up != 1 || d->flip != 0 || !(d->stride == 1 || d->stride == 2)) return 0;
     if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return 0;
-    if (d->in_cs != 1 || d->in_ps != d->Cin || d->in_bs != (int64_t)d->Hin * d->Win * d->Cin) return 0;
-    if (d->out_cs != 1 || d->out_ps != d->Cout || d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout) return 0;
+    if (d->in_cs != 1 || d->in_ps != d->Cin || (d->B > 1 && d->in_bs != (int64_t)d->Hin * d->Win * d->Cin)) return 0;
+    if (d->out_cs != 1 || d->out_ps != d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout)) return 0;
     return 1;
 }
 

@@ -214,9 +214,15 @@ class _Stack:
         skip_params = pg is not None and "skipConv1.4.weight" in pg
         if S.get("skip_own", False) and (need_dskip or skip_params):
             t1, t2, res1 = S["t1"], S["t2"], S["res1"]
+            d_res = d_pre6
             if res1.shape[0] != B:
-                raise RuntimeError("gradients through a batch-broadcast skipConv1 branch are not supported; expand its input")
-            dr = ops.select_cotangent(d_pre6, None, None, res1, MASK_POS, torch.empty_like(d_pre6))
+                # skipConv1 ran ONCE on a surface image shared by the batch (training: the scene is expanded, train_network.py:297): its
+                # activations and ReLU masks are the same for every sample and the branch is linear given the masks, so the parameter
+                # gradients need only the batch SUM of the incoming gradient -- one reduction, then a B = 1 backward (24x less work)
+                if need_dskip:
+                    raise RuntimeError("the gradient wrt a batch-broadcast skipConv1 input is per sample; expand the input to get it")
+                d_res = d_pre6.sum(0, keepdim=True)
+            dr = ops.select_cotangent(d_res, None, None, res1, MASK_POS, torch.empty_like(d_res))
             dt2 = ops.conv_backward_data(sp["skipConv1.4"], dr, Wt("skipConv1.4"), hw(t2), mask=t2, mask_mode=MASK_POS)
             wgrad("skipConv1.4", t2, dr)
             dt1 = ops.conv_backward_data(sp["skipConv1.2"], dt2, Wt("skipConv1.2"), hw(t1), mask=t1, mask_mode=MASK_POS)
@@ -242,6 +248,8 @@ class _StackFn(torch.autograd.Function):
             surf_acts = tuple(t if t.dim() == 4 else t.unsqueeze(0) for t in (net.res1_s, net.res2_s, net.res3_s, net.res4_s))
         else:
             surf = ops._f32c(surf)
+        if skip_in.dim() == 4 and skip_in.shape[0] > 1 and skip_in.stride(0) == 0 and not ctx.needs_input_grad[3]:
+            skip_in = skip_in[:1]             # one image expanded over the batch: run skipConv1 once (see _Stack.backward)
         skip_in = ops._f32c(skip_in)
         with torch.no_grad():
             out, S = _Stack.forward(net, x, surf, skip_in, surf_acts=surf_acts, skip_acts=skip_acts)
@@ -282,7 +290,7 @@ def set_precision(model: nn.Module, precision: str) -> nn.Module:
     if precision not in ("fp32", "bf16", "fp16"):
         raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
     for m in model.modules():
-        if isinstance(m, _ConvStackNet):
+        if isinstance(m, (_ConvStackNet, WarpingNet)):
             m.precision = precision
     return model
 
@@ -384,35 +392,45 @@ class _RefineFn(torch.autograd.Function):
     def forward(ctx, net, coarse, *params):
         g = coarse.unsqueeze(0)
         w = [net.grid_refine_net[i] for i in _REFINE_IDX]
-        a1 = ops.conv_forward(_REFINE_SPECS[0], g, w[0].weight, w[0].bias, epi=EPI_RELU)
+        need_grad = any(p.requires_grad for p in params) or coarse.requires_grad
+        # bf16 TRAINING: the three inner layers run on the tensor-core kernels (2-channel grid zero-padded to 16 NHWC channels, bf16 activations
+        # and gradients, fp32 accumulation) -- on CUDA cores this B = 1 net cost 0.55 ms of a 4.1 ms step.  The last layer (LeakyReLU, residual
+        # after the activation, fp32 output added to the fp32 coarse grid) and every frozen-model use (the attacks) stay exact fp32.
+        tc = need_grad and getattr(net, "precision", "fp32") == "bf16" and ops.TC_ENABLED
+        gp = None
+        if tc:
+            gp = ops.pack_nhwc16(g, None, torch.bfloat16)
+            a1 = ops.conv_forward(_REFINE_SPECS[0], gp, w[0].weight, w[0].bias, epi=EPI_RELU, out_dtype=torch.bfloat16)
+        else:
+            a1 = ops.conv_forward(_REFINE_SPECS[0], g, w[0].weight, w[0].bias, epi=EPI_RELU)
         a2 = ops.conv_forward(_REFINE_SPECS[1], a1, w[1].weight, w[1].bias, epi=EPI_RELU)
         a3 = ops.conv_forward(_REFINE_SPECS[2], a2, w[2].weight, w[2].bias, epi=EPI_RELU)
         # last layer: LeakyReLU(0.1) then + coarse (residual added after the activation)
-        s = ops.conv_forward(_REFINE_SPECS[3], a3, w[3].weight, w[3].bias, add=g, epi=EPI_LEAKY01 | EPI_ADD_AFTER_ACT)
+        s = ops.conv_forward(_REFINE_SPECS[3], a3, w[3].weight, w[3].bias, add=g, epi=EPI_LEAKY01 | EPI_ADD_AFTER_ACT, out_dtype=torch.float32)
         pre4 = None
-        if any(p.requires_grad for p in params) or coarse.requires_grad:
+        if need_grad:
             pre4 = s - g            # leaky(pre): sign(pre) == sign(leaky(pre)) so it serves as the LeakyReLU mask
         fine = ops.grid_finish(s[0], None)
         ctx.net = net
-        ctx.saved = (g, a1, a2, a3, s, pre4)
+        ctx.saved = (g, a1, a2, a3, s, pre4, gp)
         return fine
 
     @staticmethod
     def backward(ctx, dfine):
         net = ctx.net
-        g, a1, a2, a3, s, pre4 = ctx.saved
+        g, a1, a2, a3, s, pre4, gp = ctx.saved
         w = [net.grid_refine_net[i] for i in _REFINE_IDX]
         ds = ops.grid_finish_bwd(s[0], None, dfine).unsqueeze(0)                 # clamp backward
         d4 = ops.select_cotangent(ds, None, None, pre4, MASK_LEAKY01, torch.empty_like(ds))
         grads = [torch.zeros_like(p) for m in w for p in (m.weight, m.bias)]
         ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7])
-        d3 = ops.conv_backward_data(_REFINE_SPECS[3], d4, w[3].weight, a3.shape[2:], mask=a3, mask_mode=MASK_POS)
+        d3 = ops.conv_backward_data(_REFINE_SPECS[3], d4, w[3].weight, a3.shape[2:], mask=a3, mask_mode=MASK_POS, out_dtype=a3.dtype)
         ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5])
         d2 = ops.conv_backward_data(_REFINE_SPECS[2], d3, w[2].weight, a2.shape[2:], mask=a2, mask_mode=MASK_POS)
         ops.conv_backward_weight(_REFINE_SPECS[1], a1, d2, grads[2], grads[3])
         d1 = ops.conv_backward_data(_REFINE_SPECS[1], d2, w[1].weight, a1.shape[2:], mask=a1, mask_mode=MASK_POS)
-        ops.conv_backward_weight(_REFINE_SPECS[0], g, d1, grads[0], grads[1])
-        dg = ops.conv_backward_data(_REFINE_SPECS[0], d1, w[0].weight, g.shape[2:], add=ds)      # + identity path
+        ops.conv_backward_weight(_REFINE_SPECS[0], gp if gp is not None else g, d1, grads[0], grads[1])
+        dg = ops.conv_backward_data(_REFINE_SPECS[0], d1, w[0].weight, g.shape[2:], add=ds, out_dtype=torch.float32)      # + identity path
         ctx.saved = None
         return (None, dg[0]) + tuple(grads)
 
@@ -474,6 +492,8 @@ class _WarpFn(torch.autograd.Function):
 
 
 class WarpingNet(nn.Module):
+    precision = "fp32"          # set_precision: 'bf16' moves the refinement net's inner layers to the tensor-core kernels while training
+
     def __init__(self, grid_shape=(6, 6), out_size=(256, 256), with_refine=True):
         super().__init__()
         self.grid_shape = grid_shape
