@@ -45,6 +45,7 @@ struct WgParams {
     int32_t B, Cx, Cy, Hy, Wy;
     int32_t stride, nplanes, halo_w, halo_h, org_x, org_y;
     int32_t tiles_x, tiles_y, total_tiles;
+    int32_t tile_h, ksteps;                // pixel tile = tile_h x 8 pixels = ksteps MMA K-steps of 16 pixels (16 rows, or 8 when a 16-row stage would leave no room for a second one)
     int32_t cxb, cyb;                      // channels per X / DY box (64, 32 or 16)
     int32_t x_boxes, y_boxes;              // boxes per plane of X loaded per stage; boxes of DY
     int32_t nsets;
@@ -108,12 +109,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
                 mbar_wait(empty + st, ph ^ 1);
                 uint8_t* dst = smem + (size_t)st * P.stage_bytes;
                 mbar_expect_tx(full + st, (uint32_t)P.tx_bytes);
-                const int x0 = (tx * WTW + P.org_x) * P.stride, y0 = (ty * WTH + P.org_y) * P.stride;
+                const int x0 = (tx * WTW + P.org_x) * P.stride, y0 = (ty * P.tile_h + P.org_y) * P.stride;
                 for (int pl = 0; pl < P.nplanes; ++pl)
                     for (int xb = 0; xb < P.x_boxes; ++xb)
                         tma_load_4d(dst + (size_t)(pl * P.x_boxes + xb) * P.x_plane_bytes, &map_x, full + st, x_ch0 + xb * P.cxb, x0 + (pl & 1), y0 + (pl >> 1), b);
                 for (int yb = 0; yb < P.y_boxes; ++yb)
-                    tma_load_4d(dst + P.x_bytes + (size_t)yb * P.y_box_bytes, &map_y, full + st, yb * P.cyb, tx * WTW, ty * WTH, b);
+                    tma_load_4d(dst + P.x_bytes + (size_t)yb * P.y_box_bytes, &map_y, full + st, yb * P.cyb, tx * WTW, ty * P.tile_h, b);
                 if (++st == S) { st = 0; ph ^= 1; }
             }
         }
@@ -128,23 +129,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid
             const uint32_t b_lbo16 = (uint32_t)P.y_box_bytes >> 4;
             const uint32_t la = layout_for(P.cxb), lb = layout_for(P.cyb);
             const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = (uint32_t)P.stage_bytes >> 4, xbytes16 = (uint32_t)P.x_bytes >> 4;
+            // Descriptors are built ONCE (stage 0, K-step 0) and advanced by adding 16-byte-unit offsets to their 14-bit start-address field
+            // (every operand lies below 228 KB, so the sum never carries out of the field).  The first version rebuilt both 64-bit descriptors
+            // from the parameter block for every MMA: ~100 clk of single-thread issue per MMA, more than an N <= 64 MMA takes to execute
+            // (conv6: 24 MMAs of N = 16 per tile, 146 us for 177 MB of operands).
+            uint64_t a_desc[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                a_desc[g] = g < ngroups ? make_mn_desc(smem16 + P.g[g0 + g].a_off16, P.g[g0 + g].a_lbo16, a_sbo16, la) : 0ull;
+            const uint64_t b_desc = make_mn_desc(smem16 + xbytes16, b_lbo16, b_sbo16, lb);
+            const uint32_t a_kstep = 2u * a_sbo16, b_kstep = 2u * b_sbo16, ncols = (uint32_t)P.n_cols;
+            const int ksteps = P.ksteps;
             int st = 0;
             uint32_t ph = 0;
-            bool first = true;
+            uint32_t accum = 0u;
             for (int tile = tile0; tile < P.total_tiles; tile += tile_step) {
                 mbar_wait(full + st, ph);
                 tc_fence_after();
-                const uint32_t base16 = smem16 + (uint32_t)st * stage16;
-#pragma unroll 1
+                const uint64_t so = (uint64_t)((uint32_t)st * stage16);
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {                             // 16 pixels (two tile rows) per MMA
-                    const uint64_t bdesc = make_mn_desc(base16 + xbytes16 + (uint32_t)ks * 2u * b_sbo16, b_lbo16, b_sbo16, lb);
-                    for (int g = 0; g < ngroups; ++g) {
-                        const uint64_t adesc = make_mn_desc(base16 + P.g[g0 + g].a_off16 + (uint32_t)ks * 2u * a_sbo16, P.g[g0 + g].a_lbo16, a_sbo16, la);
-                        umma_bf16(tmem_base + (uint32_t)(g * P.n_cols), adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
-                    }
+                    if (ks >= ksteps) break;
+                    const uint64_t bd = b_desc + so + (uint64_t)((uint32_t)ks * b_kstep);
+                    const uint64_t ao = so + (uint64_t)((uint32_t)ks * a_kstep);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if (g < ngroups) umma_bf16(tmem_base + (uint32_t)g * ncols, a_desc[g] + ao, bd, idesc, (ks == 0) ? accum : 1u);
                 }
                 umma_commit(empty + st);
-                first = false;
+                accum = 1u;
                 if (++st == S) { st = 0; ph ^= 1; }
             }
             umma_commit(tdone);
@@ -272,18 +285,27 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
             tp[ntaps++] = t;
         }
     P.org_x = qminx; P.org_y = qminy;
-    P.halo_w = WTW + (qmaxx - qminx); P.halo_h = WTH + (qmaxy - qminy);
-    P.tiles_y = (d->Hout + WTH - 1) / WTH; P.tiles_x = (d->Wout + WTW - 1) / WTW;
+    // a 16-row tile of a wide layer (conv4 / conv4_s: 46 KB of X halo + 64 KB of DY) fills shared memory with ONE stage, which serialises the
+    // TMA loads and the MMAs (measured 127 us for 34 us of MMA work); 8-row tiles give three stages
+    P.tile_h = WTH;
+    {
+        const int64_t hw16 = (int64_t)(WTW + (qmaxx - qminx)) * (WTH + (qmaxy - qminy));
+        const int64_t stage16 = (int64_t)d->stride * d->stride * (Cx >= 128 ? 2 : 1) * hw16 * (Cx >= 64 ? 128 : Cx * 2) + (int64_t)128 * Cy * 2;
+        if (2 * stage16 > 200 * 1024) P.tile_h = WTH / 2;
+    }
+    P.ksteps = P.tile_h / 2;
+    P.halo_w = WTW + (qmaxx - qminx); P.halo_h = P.tile_h + (qmaxy - qminy);
+    P.tiles_y = (d->Hout + P.tile_h - 1) / P.tile_h; P.tiles_x = (d->Wout + WTW - 1) / WTW;
     P.total_tiles = d->B * P.tiles_y * P.tiles_x;
     SPAA_CHECK_ARG(P.total_tiles > 0, "spaa_conv_wgrad_tc: empty problem");
     const int rowx = P.cxb * 2, rowy = P.cyb * 2;
     P.x_boxes = Cx >= 128 ? 2 : 1;                                   // one 128-channel chunk of X per launch
     P.x_plane_bytes = (P.halo_h * P.halo_w * rowx + 1023) & ~1023;
     P.x_bytes = P.nplanes * P.x_boxes * P.x_plane_bytes;
-    P.y_box_bytes = 128 * rowy;                                       // 16 x 8 pixels
+    P.y_box_bytes = P.tile_h * WTW * rowy;                            // tile_h x 8 pixels
     if (P.y_box_bytes & 1023) P.y_box_bytes = (P.y_box_bytes + 1023) & ~1023;
     P.stage_bytes = P.x_bytes + P.y_boxes * P.y_box_bytes;
-    P.tx_bytes = P.nplanes * P.x_boxes * P.halo_h * P.halo_w * rowx + P.y_boxes * 128 * rowy;
+    P.tx_bytes = P.nplanes * P.x_boxes * P.halo_h * P.halo_w * rowx + P.y_boxes * P.tile_h * WTW * rowy;
     P.nstages = (200 * 1024) / P.stage_bytes;
     if (P.nstages > 4) P.nstages = 4;
     SPAA_CHECK_ARG(P.nstages >= 1, "spaa_conv_wgrad_tc: stage does not fit in shared memory");
@@ -372,7 +394,7 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cy, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
         cuuint64_t strides[3] = {(cuuint64_t)Cy * 2, (cuuint64_t)d->Wout * Cy * 2, (cuuint64_t)d->Hout * d->Wout * Cy * 2};
-        cuuint32_t box[4] = {(cuuint32_t)P.cyb, (cuuint32_t)WTW, (cuuint32_t)WTH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)P.cyb, (cuuint32_t)WTW, (cuuint32_t)P.tile_h, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         const CUtensorMapSwizzle sw = P.cyb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.cyb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
         CUresult r = enc(&my, P.y_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, es,
