@@ -186,12 +186,12 @@ __global__ void __launch_bounds__(kThreads) grid_sample_bwd_grid_kernel(const fl
                                                                          int64_t dout2_bs, const float* __restrict__ rough, int64_t rough_bs,
                                                                          const float* __restrict__ mask, const float* __restrict__ img, int clamp01,
                                                                          const float* __restrict__ grid, int64_t grid_bs, int B, int C, int Hi,
-                                                                         int Wi, int H, int W, float* __restrict__ dgrid) {
+                                                                         int Wi, int H, int W, float* __restrict__ dgrid, int bchunk) {
     const int HW = H * W;
     const int64_t HWi = (int64_t)Hi * Wi;
-    const int nb_outer = grid_bs == 0 ? 1 : B;        // blockIdx.y indexes independent grids
-    const int bo = blockIdx.y;
-    (void)nb_outer;
+    // blockIdx.y: per-sample grids -> the sample; one grid shared by the batch -> a chunk of `bchunk` samples whose contribution is added
+    // to the (zero-filled) result atomically.  (One thread looping over all 24 training samples left the GPU a quarter full: 137 us.)
+    const int bo = grid_bs == 0 ? 0 : blockIdx.y;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
         const float* g = grid + (int64_t)bo * grid_bs;
         const warp::Taps<float> t = warp::make_taps<float>(__ldg(g + p), __ldg(g + HW + p), Hi, Wi);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) grid_sample_bwd_grid_kernel(const fl
         const float m = mask ? __ldg(mask + p) : 1.f;
         const int64_t o00 = (int64_t)t.y0 * Wi + t.x0;
         float gix = 0.f, giy = 0.f;
-        const int b_lo = grid_bs == 0 ? 0 : bo, b_hi = grid_bs == 0 ? B : bo + 1;
+        const int b_lo = grid_bs == 0 ? (int)blockIdx.y * bchunk : bo, b_hi = grid_bs == 0 ? min(B, b_lo + bchunk) : bo + 1;
         for (int b = b_lo; b < b_hi; ++b) {
             const float* ib = img + (int64_t)b * C * HWi;
             for (int c = 0; c < C; ++c) {
@@ -216,8 +216,13 @@ __global__ void __launch_bounds__(kThreads) grid_sample_bwd_grid_kernel(const fl
             }
         }
         float* dg = dgrid + (int64_t)bo * 2 * HW;
-        dg[p] = gix * 0.5f * (float)(Wi - 1);
-        dg[HW + p] = giy * 0.5f * (float)(Hi - 1);
+        if (grid_bs == 0 && bchunk < B) {
+            atomicAdd(dg + p, gix * 0.5f * (float)(Wi - 1));
+            atomicAdd(dg + HW + p, giy * 0.5f * (float)(Hi - 1));
+        } else {
+            dg[p] = gix * 0.5f * (float)(Wi - 1);
+            dg[HW + p] = giy * 0.5f * (float)(Hi - 1);
+        }
     }
 }
 
@@ -449,9 +454,17 @@ int spaa_grid_sample_bwd_grid(const float* dout, const float* dout2, int64_t dou
                               int Hi, int Wi, int H, int W, float* dgrid, spaa_stream_t stream) {
     SPAA_CHECK_ARG(dout && img && grid && dgrid && B > 0 && B < 65536 && C > 0 && Hi > 1 && Wi > 1, "spaa_grid_sample_bwd_grid: bad arguments");
     SPAA_CHECK_ARG((dout2 == nullptr) || rough, "spaa_grid_sample_bwd_grid: dout2 needs rough");
-    dim3 g(blocks_for((int64_t)H * W, 4), grid_bstride == 0 ? 1u : (unsigned)B);
+    int bchunk = (int)B;
+    if (grid_bstride == 0 && B >= 8) {
+        bchunk = 4;
+        if (cudaMemsetAsync(dgrid, 0, (size_t)2 * H * W * sizeof(float), (cudaStream_t)stream) != cudaSuccess) {
+            set_last_error("spaa_grid_sample_bwd_grid: cudaMemsetAsync failed");
+            return SPAA_ERR_CUDA;
+        }
+    }
+    dim3 g(blocks_for((int64_t)H * W, 4), grid_bstride == 0 ? (unsigned)((B + bchunk - 1) / bchunk) : (unsigned)B);
     grid_sample_bwd_grid_kernel<<<g, kThreads, 0, (cudaStream_t)stream>>>(dout, dout2, dout2_bstride, rough, rough_bstride, mask, img, clamp01,
-                                                                        grid, grid_bstride, (int)B, C, Hi, Wi, H, W, dgrid);
+                                                                        grid, grid_bstride, (int)B, C, Hi, Wi, H, W, dgrid, bchunk);
     SPAA_CHECK_LAUNCH("spaa_grid_sample_bwd_grid");
     return SPAA_OK;
 }
