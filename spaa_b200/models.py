@@ -265,8 +265,20 @@ class _StackFn(torch.autograd.Function):
         names = [n for n, _ in net.named_parameters()]
         pneed = ctx.needs_input_grad[5:]
         pg = None
+        direct = set()
         if any(pneed):
-            pg = {n: torch.zeros_like(p, dtype=torch.float32) for (n, p), need in zip(net.named_parameters(), pneed) if need}
+            # parameters managed by train_network.FlatAdam carry .grad views of one flat, already zeroed fp32 bucket: the backward-weight kernels
+            # accumulate straight into them (they are `+=` kernels) and autograd is told there is nothing to add -- otherwise 46 zero-fills
+            # and 46 accumulations per step exist only to move the same numbers once more
+            pg = {}
+            for (n, p), need in zip(net.named_parameters(), pneed):
+                if not need:
+                    continue
+                if _flat_grad_view(p):
+                    pg[n] = p.grad
+                    direct.add(n)
+                else:
+                    pg[n] = torch.zeros_like(p, dtype=torch.float32)
         dout = ops._f32c(dout)
         d_pre6 = ops.select_cotangent(dout, None, None, S["out"], MASK_OPEN01, torch.empty_like(S["out"]))
         packed = None
@@ -279,8 +291,14 @@ class _StackFn(torch.autograd.Function):
             dx, dsurf, dskip = _Stack.backward(net, S, d_pre6, need_dx=need_x, surf_grad_channels=(0, cs) if (need_surf and cs) else None,
                                                need_dskip=need_skip, param_grads=pg, d_pre6_packed=packed)
         ctx.S = None
-        pgr = tuple((pg.get(n) if pg is not None else None) for n in names)
+        pgr = tuple((pg.get(n) if (pg is not None and n not in direct) else None) for n in names)
         return (None, dx, dsurf, dskip, None) + pgr
+
+
+def _flat_grad_view(p) -> bool:
+    """True when `p.grad` is a live fp32 view that train_network.FlatAdam installed (and zero-fills before every backward)."""
+    g = p.grad
+    return bool(getattr(p, "_spaa_flat_grad", False)) and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape
 
 
 def set_precision(model: nn.Module, precision: str) -> nn.Module:
@@ -422,7 +440,9 @@ class _RefineFn(torch.autograd.Function):
         w = [net.grid_refine_net[i] for i in _REFINE_IDX]
         ds = ops.grid_finish_bwd(s[0], None, dfine).unsqueeze(0)                 # clamp backward
         d4 = ops.select_cotangent(ds, None, None, pre4, MASK_LEAKY01, torch.empty_like(ds))
-        grads = [torch.zeros_like(p) for m in w for p in (m.weight, m.bias)]
+        plist = [p for m in w for p in (m.weight, m.bias)]
+        direct = [_flat_grad_view(p) for p in plist]
+        grads = [p.grad if dflag else torch.zeros_like(p) for p, dflag in zip(plist, direct)]
         ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7])
         d3 = ops.conv_backward_data(_REFINE_SPECS[3], d4, w[3].weight, a3.shape[2:], mask=a3, mask_mode=MASK_POS, out_dtype=a3.dtype)
         ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5])
@@ -432,7 +452,7 @@ class _RefineFn(torch.autograd.Function):
         ops.conv_backward_weight(_REFINE_SPECS[0], gp if gp is not None else g, d1, grads[0], grads[1])
         dg = ops.conv_backward_data(_REFINE_SPECS[0], d1, w[0].weight, g.shape[2:], add=ds, out_dtype=torch.float32)      # + identity path
         ctx.saved = None
-        return (None, dg[0]) + tuple(grads)
+        return (None, dg[0]) + tuple(None if dflag else gr for gr, dflag in zip(grads, direct))
 
 
 class _ClampGridFn(torch.autograd.Function):

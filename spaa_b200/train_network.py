@@ -98,6 +98,7 @@ class FlatAdam:
                 self.param[off:off + k].copy_(p.data.reshape(-1))
                 p.data = self.param[off:off + k].view_as(p.data)
                 p.grad = self.grad[off:off + k].view_as(p.data)
+                p._spaa_flat_grad = True          # models._StackFn / _RefineFn accumulate into this view directly (zero_grad() clears it)
                 self.params.append(p)
                 off += k
             ends.append(off)
