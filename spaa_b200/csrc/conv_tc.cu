@@ -988,6 +988,12 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
             bbytes = (int64_t)P.sb * P.b_slice_bytes;
         }
         if (sa < 2) {
+            if (ctas == 1 && P.egroups == 2) {                   // a second epilogue group's ring and staging blocks do not fit: run with one
+                P.egroups = 1;
+                P.e_stage_bytes = planar ? 0 : 4 * (mask2 ? 4096 : 2048);
+                ++ctas;                                          // (undo the loop's decrement: plan again with one CTA per SM)
+                continue;
+            }
             if (ctas == 1) return SPAA_ERR_UNSUPPORTED;
             continue;
         }
