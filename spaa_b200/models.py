@@ -291,6 +291,9 @@ class _StackFn(torch.autograd.Function):
             dx, dsurf, dskip = _Stack.backward(net, S, d_pre6, need_dx=need_x, surf_grad_channels=(0, cs) if (need_surf and cs) else None,
                                                need_dskip=need_skip, param_grads=pg, d_pre6_packed=packed)
         ctx.S = None
+        hook = getattr(net, "_grads_ready_hook", None)
+        if hook is not None and pg is not None and len(direct) == len(pg):
+            hook()                 # every parameter gradient of this stack now sits, complete, in the flat bucket (train_network.GradOverlap)
         pgr = tuple((pg.get(n) if (pg is not None and n not in direct) else None) for n in names)
         return (None, dx, dsurf, dskip, None) + pgr
 

@@ -8,6 +8,7 @@ per-group learning rates read from a device-side schedule table.  No host synchr
 from __future__ import annotations
 
 import math
+import os
 import random
 import time
 from os.path import join
@@ -179,12 +180,72 @@ def shard_indices(idx: Sequence[int], rank: int, world: int) -> List[int]:
     return list(idx[rank::world])
 
 
-def allreduce_grads(opt: FlatAdam, world: int) -> float:
-    """Sum the flat gradient bucket over ranks; returns the scale that turns the sum into the global-batch mean."""
+def allreduce_grads(opt: FlatAdam, world: int, skip: Optional[Tuple[int, int]] = None) -> float:
+    """Sum the flat gradient bucket over ranks; returns the scale that turns the sum into the global-batch mean.
+    skip = (lo, hi): that slice has already been reduced (GradOverlap) -- only the rest is exchanged here."""
     if world > 1:
-        dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM)
+        if skip is None:
+            dist.all_reduce(opt.grad, op=dist.ReduceOp.SUM)
+        else:
+            lo, hi = skip
+            if lo > 0:
+                dist.all_reduce(opt.grad[:lo], op=dist.ReduceOp.SUM)
+            if hi < opt.grad.numel():
+                dist.all_reduce(opt.grad[hi:], op=dist.ReduceOp.SUM)
         return 1.0 / world
     return 1.0
+
+
+class GradOverlap:
+    """Overlap of the gradient exchange with the tail of the backward pass.  The conv stack (ShadingNet / CompenNet: 99 % of the parameters)
+    finishes its backward before the warp's adjoint, the refinement net and the grid generator run theirs (~0.35 ms at batch 24); its backward
+    accumulates straight into the flat bucket, so the moment it returns its slice of the bucket is final: the all-reduce of that slice starts there, on
+    a second stream, and the small remainder is exchanged when the backward is done.  Works inside the CUDA graph of the step (fork / join)."""
+
+    def __init__(self, model, opt: FlatAdam, device):
+        from .models import _ConvStackNet
+        self.opt, self.range, self.stack = opt, None, None
+        stacks = [m for m in model.modules() if isinstance(m, _ConvStackNet)]
+        if len(stacks) != 1 or torch.device(device).type != "cuda" or os.environ.get("SPAA_NO_GRAD_OVERLAP"):
+            return
+        base, esz = opt.grad.data_ptr(), opt.grad.element_size()
+        spans = []
+        for p in stacks[0].parameters():
+            if not getattr(p, "_spaa_flat_grad", False) or p.grad is None:
+                return
+            o = (p.grad.data_ptr() - base) // esz
+            spans.append((o, o + p.numel()))
+        lo, hi = min(a for a, _ in spans), max(b for _, b in spans)
+        if sum(b - a for a, b in spans) != hi - lo:
+            return                                   # the stack's gradients are not one contiguous slice of the bucket
+        self.range, self.stack = (lo, hi), stacks[0]
+        self.side = torch.cuda.Stream(device=device)
+        self.fired = False
+
+    def arm(self, world: int):
+        """Call before backward(): installs the hook the conv stack's backward fires when its parameter gradients are complete."""
+        self.fired = False
+        if self.range is None or world <= 1:
+            return
+
+        def hook():
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                lo, hi = self.range
+                dist.all_reduce(self.opt.grad[lo:hi], op=dist.ReduceOp.SUM)
+            self.fired = True
+        self.stack._grads_ready_hook = hook
+
+    def finish(self, world: int) -> float:
+        """Call after backward(): exchanges what the hook did not and joins the second stream."""
+        if self.stack is not None:
+            self.stack._grads_ready_hook = None
+        if self.fired:
+            scale = allreduce_grads(self.opt, world, skip=self.range)
+            torch.cuda.current_stream().wait_stream(self.side)
+            return scale
+        return allreduce_grads(self.opt, world)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -217,6 +278,7 @@ def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter,
     it_static = torch.zeros(local_B, dtype=torch.int64, device=device)
     hist_slot = torch.zeros(2, device=device)
     graphs, eager_steps, keep = {}, {}, []
+    overlap = GradOverlap(model, opt, device)
 
     def device_step(loss_option):
         x_batch, y_batch = inputs.index_select(0, it_static), targets.index_select(0, it_static)
@@ -224,8 +286,9 @@ def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter,
         infer = model(x_batch, scene_batch)
         loss, l2 = compute_loss(infer, y_batch, loss_option)
         opt.zero_grad()
+        overlap.arm(world)
         loss.backward()
-        scale = allreduce_grads(opt, world)
+        scale = overlap.finish(world)
         opt.apply(grad_scale=scale)
         hist_slot[0], hist_slot[1] = loss.detach(), l2
 
