@@ -163,7 +163,7 @@ def config_dict(n_gpus: int, precision: str, fold_bn: bool = False):
     return {"workload": "spaa_attack resnet18 B=32 targets/GPU, prj 256x256, cam 240x320, camdE_caml2 d_thr=5 (BASELINE configs[1])",
             "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "precision": precision,
             "classifier": "torchvision resnet18 (cuDNN, external operand, channels_last, TF32 as torch defaults"
-                          + ("; inference-mode BatchNorm folded into the preceding cuDNN convolutions in a private copy, see side leg stock_classifier)"
+                          + ("; private copy: inference-mode BatchNorm folded into the preceding cuDNN convolutions, stem ReLU + max-pooling on spaa_b200's fused kernels; see side leg stock_classifier)"
                              if fold_bn else ")"),
             "l2": "per-iteration working set (~3 GB of activations at B=32) is far larger than the 126 MB L2; no explicit flush",
             "parallelism": f"{n_gpus} independent attack jobs, no collective"}
@@ -403,7 +403,7 @@ def run_ours(args):
                 As.step()
             f1.record(); torch.cuda.synchronize()
             line["stock_classifier"] = {"value": ns / (f0.elapsed_time(f1) / 1e3), "unit": "it/s", "steps": ns,
-                                        "note": "same engine and CUDA-graph replay with the classifier's BatchNorm layers left unfolded (the stock module)"}
+                                        "note": "same engine and CUDA-graph replay with the classifier run as the stock module (BatchNorm layers unfolded, ATen pooling)"}
             del As
         if args.precision != "fp32":
             models.set_precision(pcnet, "fp32")

@@ -280,6 +280,20 @@ int spaa_clf_preprocess_bwd(const float* dout, int64_t B, int H, int W, int top,
                             int out_w, const float* host_std3, int nhwc, float* dimg, spaa_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------------------
+ * Fused ReLU + max-pooling on fp32 NHWC activations, forward and adjoint: the step right after the first convolution of the
+ * external classifier (torchvision ResNet stem relu -> maxpool(3,2,1), VGG ReLU -> MaxPool2d(2,2), Inception MaxPool2d(3,2);
+ * networks built at classifier.py:22-33).  Replaces ATen's relu / max_pool2d(channels_last) forward and their autograd
+ * (threshold_backward, max_pool2d_with_indices_backward) in the attack engines' PRIVATE copy of the frozen classifier.
+ *   x [N,H,W,C] fp32 (C % 4 == 0); y [N,Ho,Wo,C]; idx [N,Ho,Wo,C] uint8: tap number (r*k + q, row-major, first maximum wins as in
+ *   ATen) of the selected element, 255 = none (relu != 0 and the window maximum was <= 0); Ho = (H + 2*pad - k)/stride + 1.
+ *   bwd: dx [N,H,W,C] = adjoint applied to dy (every element written; no atomics).
+ * -------------------------------------------------------------------------------------------------------- */
+int spaa_relu_maxpool_nhwc_fwd(const float* x, int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                               int relu, float* y, uint8_t* idx, spaa_stream_t stream);
+int spaa_relu_maxpool_nhwc_bwd(const float* dy, const uint8_t* idx, int64_t N, int H, int W, int C, int k, int stride, int pad,
+                               int Ho, int Wo, float* dx, spaa_stream_t stream);
+
+/* ----------------------------------------------------------------------------------------------------------
  * Optimiser: replaces optim.Adam.step over the parameter groups of train_network.py:253-255,145 with one
  * launch over a flat fp32 buffer split into segments with their own lr / weight decay.
  *   seg_end[nseg] (int64, device): exclusive end offsets; seg_lr / seg_wd [nseg] (float, device)

@@ -7,6 +7,7 @@ reference's return convention `(raw_score, p_sorted numpy, idx numpy)`; the fuse
 from __future__ import annotations
 
 import os
+from typing import Optional
 
 import torch
 import torch.nn.functional as F
@@ -134,6 +135,84 @@ def device_logits(classifier, im, crop_sz, channels_last: bool = False):
     return classifier(im, crop_sz)[0]
 
 
+class _ReluMaxPoolFn(torch.autograd.Function):
+    """max_pool2d(relu(x)) (or max_pool2d(x)) and its adjoint as one kernel each (ops.relu_maxpool_nhwc)."""
+
+    @staticmethod
+    def forward(ctx, x, k, stride, pad, relu):
+        y, idx = ops.relu_maxpool_nhwc(x, k, stride, pad, relu)
+        ctx.save_for_backward(idx)
+        ctx.geom = (tuple(x.shape[2:]), k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        idx, = ctx.saved_tensors
+        hw, k, stride, pad = ctx.geom
+        return ops.relu_maxpool_nhwc_bwd(dy, idx, hw, k, stride, pad), None, None, None, None
+
+
+class FusedReLUMaxPool2d(torch.nn.Module):
+    """Stands in for `nn.ReLU -> nn.MaxPool2d(k, stride, pad)` (with_relu) or a lone `nn.MaxPool2d` inside the attack engines'
+    private copy of the frozen classifier.  CUDA fp32 channels_last inputs run the fused kernel; anything else runs the stock ops
+    the pair was made of, so the private copy computes the same function everywhere."""
+
+    def __init__(self, kernel_size: int, stride: int, padding: int, with_relu: bool):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding, self.with_relu = int(kernel_size), int(stride), int(padding), bool(with_relu)
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}, with_relu={self.with_relu}"
+
+    def forward(self, x):
+        if ops.relu_maxpool_supported(x, self.kernel_size, self.stride, self.padding):
+            return _ReluMaxPoolFn.apply(x, self.kernel_size, self.stride, self.padding, self.with_relu)
+        return F.max_pool2d(F.relu(x) if self.with_relu else x, self.kernel_size, self.stride, self.padding)
+
+
+def _plain_maxpool(m):
+    """(k, stride, pad) of an nn.MaxPool2d the fused kernel reproduces exactly, else None."""
+    if type(m) is not torch.nn.MaxPool2d or m.ceil_mode or m.return_indices:
+        return None
+
+    def one(v):
+        v = tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+        return int(v[0]) if len(v) == 2 and v[0] == v[1] else None
+    k, st, pd, dl = one(m.kernel_size), one(m.stride if m.stride is not None else m.kernel_size), one(m.padding), one(m.dilation)
+    if None in (k, st, pd, dl) or dl != 1 or not (1 <= k <= 15) or 2 * pd > k:
+        return None
+    return k, st, pd
+
+
+def fuse_relu_maxpool(model) -> int:
+    """In place: replace `ReLU -> MaxPool2d` pairs (torchvision ResNet stem, nn.Sequential neighbours as in VGG's `features`) and lone
+    MaxPool2d modules (Inception's maxpool1 / maxpool2) of `model` by FusedReLUMaxPool2d.  Returns the number of replacements."""
+    from torchvision.models import resnet
+    n = 0
+    for mod in list(model.modules()):
+        if isinstance(mod, resnet.ResNet) and type(mod._modules.get("relu")) is torch.nn.ReLU:
+            g = _plain_maxpool(mod._modules.get("maxpool"))
+            if g is not None:                      # ResNet._forward_impl: conv1 -> bn1 -> relu -> maxpool; `relu` is used nowhere else
+                mod._modules["relu"] = torch.nn.Identity()
+                mod._modules["maxpool"] = FusedReLUMaxPool2d(*g, with_relu=True)
+                n += 1
+        elif isinstance(mod, torch.nn.Sequential):
+            names = list(mod._modules.keys())
+            for a, b in zip(names, names[1:]):
+                g = _plain_maxpool(mod._modules[b])
+                if g is not None and type(mod._modules[a]) is torch.nn.ReLU:
+                    mod._modules[a] = torch.nn.Identity()
+                    mod._modules[b] = FusedReLUMaxPool2d(*g, with_relu=True)
+                    n += 1
+    for mod in list(model.modules()):
+        for name, child in list(mod._modules.items()):
+            g = _plain_maxpool(child)
+            if g is not None:
+                mod._modules[name] = FusedReLUMaxPool2d(*g, with_relu=False)
+                n += 1
+    return n
+
+
 class _FoldedView:
     """What the fused attack loops need of a classifier (`.model`, `.input_sz`), with a private BatchNorm-folded network."""
 
@@ -141,20 +220,28 @@ class _FoldedView:
         self.model, self.input_sz, self.name = model, input_sz, name
 
 
-def fold_batchnorm(classifier):
+def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None):
     """A view of `classifier` whose network is a PRIVATE copy with every inference-mode BatchNorm2d folded into the cuDNN
     convolution in front of it (torch.nn.utils.fusion.fuse_conv_bn_eval: w' = w * gamma / sqrt(var + eps), b' likewise).
     The classifier is frozen and in eval() (classifier.py:38-42), so its BatchNorm layers are per-channel affine maps: the
     folded network computes the same function (fp32 rounding differences ~1e-6 relative) while its forward AND input-gradient
     lose one elementwise pass per BatchNorm (resnet18, B=32: 20 x bn_fw_inf + 20 x batch_norm_backward + 20 x copy, ~1.1 of
-    2.9 ms, ncu launch list profiles/r1_fp16_v3_launches.md).  The user's module is not modified.  Returns `classifier`
-    itself when there is nothing to fold (vgg16, opaque callables, training-mode networks)."""
+    2.9 ms, ncu launch list profiles/r1_fp16_v3_launches.md).
+    fuse_pool (default: $SPAA_FUSE_POOL, on): the copy's `ReLU -> MaxPool2d` pairs and lone MaxPool2d modules become
+    FusedReLUMaxPool2d (fuse_relu_maxpool): exact max-pooling, one of our kernels each way instead of ATen's relu / max_pool2d /
+    threshold_backward / max_pool2d_backward passes over the largest activation of the iteration.
+    The user's module is not modified.  Returns `classifier` itself when there is nothing to change (opaque callables,
+    training-mode networks)."""
     import copy
     from torch.nn.utils.fusion import fuse_conv_bn_eval
     model, input_sz = getattr(classifier, "model", None), getattr(classifier, "input_sz", None)
+    if fuse_pool is None:
+        fuse_pool = os.environ.get("SPAA_FUSE_POOL", "1") != "0"
     if not isinstance(model, torch.nn.Module) or input_sz is None or model.training:
         return classifier
-    if not any(isinstance(m, torch.nn.BatchNorm2d) for m in model.modules()):
+    has_bn = any(isinstance(m, torch.nn.BatchNorm2d) for m in model.modules())
+    has_pool = fuse_pool and any(_plain_maxpool(m) is not None for m in model.modules())
+    if not has_bn and not has_pool:
         return classifier
     folded = copy.deepcopy(model)
     n = 0
@@ -169,6 +256,8 @@ def fold_batchnorm(classifier):
                 mod._modules[a] = fuse_conv_bn_eval(conv, bn)
                 mod._modules[b] = torch.nn.Identity()
                 n += 1
+    if fuse_pool:
+        n += fuse_relu_maxpool(folded)
     if n == 0:
         return classifier
     for p in folded.parameters():

@@ -1,0 +1,129 @@
+// Fused ReLU + max-pooling (forward and adjoint) on fp32 NHWC tensors -- the two steps that follow the first convolution of
+// the external classifier (torchvision ResNet stem: conv1 -> bn1 -> relu -> maxpool 3x3 s2 p1; VGG: ReLU -> MaxPool2d(2,2); Inception:
+// MaxPool2d(3, 2)), classifier.py:22-33 of the reference builds those networks.  They touch the largest activations of the whole attack
+// iteration (resnet18, B = 32: 103 MB in, 26 MB out) and ATen's channels_last kernels for them (max_pool_forward_nhwc 127 us,
+// max_pool_backward_nhwc 229 us, plus a ReLU pass and a threshold-backward pass over the 103 MB tensor; profiles/r1_final_launches.md)
+// run at a sixth of the HBM roofline.  Here: one pass each way, the arg-max kept as ONE byte per element (the tap number inside the
+// window, 255 = "no gradient": the ReLU was inactive), the adjoint in gather form (every input element written exactly once: no
+// zero-fill, no atomics).  max(relu(x)) == relu(max(x)) and the first maximum in row-major window order is kept, as ATen does.
+// HBM-bound: algorithmic bytes = 4*(in + out) + out (index bytes) forward; 4*(in + out) + out backward.
+#include "common.cuh"
+#include "../../include/spaa_b200.h"
+
+using namespace spaa;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct PoolGeom { int H, W, C4, k, s, p, Ho, Wo; };
+
+// grid = (ceil(Wo*C4 / kThreads), Ho, N): one thread = one output pixel x 4 channels
+// K: compile-time window size (2, 3: loops unrolled, the window's loads are independent and in flight together) or 0 (runtime g.k)
+template <bool RELU, int K>
+__global__ void __launch_bounds__(kThreads) relu_maxpool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, uint32_t* __restrict__ idx, PoolGeom g) {
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= g.Wo * g.C4) return;
+    const int ow = j / g.C4, c = j - ow * g.C4;
+    const int oh = blockIdx.y, n = blockIdx.z;
+    const int k = K ? K : g.k;
+    const int h0 = oh * g.s - g.p, w0 = ow * g.s - g.p;
+    const int r0 = h0 < 0 ? -h0 : 0, q0 = w0 < 0 ? -w0 : 0;
+    const float ninf = __int_as_float(0xff800000);
+    float m[4] = {ninf, ninf, ninf, ninf};
+    uint32_t a[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[e] = (uint32_t)(r0 * k + q0);
+    const float4* xn = x + (int64_t)n * g.H * g.W * g.C4 + c;
+#pragma unroll
+    for (int r = 0; r < k; ++r) {
+        const int ih = h0 + r;
+#pragma unroll
+        for (int q = 0; q < k; ++q) {
+            const int iw = w0 + q;
+            if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
+            const float4 v4 = __ldg(xn + ((int64_t)ih * g.W + iw) * g.C4);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            const uint32_t tap = (uint32_t)(r * k + q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (v[e] > m[e] || v[e] != v[e]) { m[e] = v[e]; a[e] = tap; }
+        }
+    }
+    if (RELU) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (!(m[e] > 0.f) && m[e] == m[e]) { m[e] = 0.f; a[e] = 255u; }     // inactive ReLU: value 0, no gradient (NaN propagates)
+    }
+    const int64_t o = (((int64_t)n * g.Ho + oh) * g.Wo + ow) * g.C4 + c;
+    y[o] = make_float4(m[0], m[1], m[2], m[3]);
+    idx[o] = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
+}
+
+// grid = (ceil(W*C4 / kThreads), H, N): one thread = one INPUT pixel x 4 channels; sums the (<= ceil(k/s)^2) windows that selected it
+__global__ void __launch_bounds__(kThreads) relu_maxpool_bwd_kernel(const float4* __restrict__ dy, const uint32_t* __restrict__ idx, float4* __restrict__ dx, PoolGeom g) {
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= g.W * g.C4) return;
+    const int iw = j / g.C4, c = j - iw * g.C4;
+    const int ih = blockIdx.y, n = blockIdx.z;
+    auto lo = [&](int i) { const int num = i + g.p - g.k + 1; return num <= 0 ? 0 : (num + g.s - 1) / g.s; };
+    const int oh_lo = lo(ih), ow_lo = lo(iw);
+    int oh_hi = (ih + g.p) / g.s, ow_hi = (iw + g.p) / g.s;
+    oh_hi = oh_hi < g.Ho ? oh_hi : g.Ho - 1;
+    ow_hi = ow_hi < g.Wo ? ow_hi : g.Wo - 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        const int r = ih - (oh * g.s - g.p);
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            const int q = iw - (ow * g.s - g.p);
+            const uint32_t tap = (uint32_t)(r * g.k + q);
+            const int64_t o = (((int64_t)n * g.Ho + oh) * g.Wo + ow) * g.C4 + c;
+            const uint32_t u = __ldg(idx + o);
+            const uint32_t hit = u ^ (tap * 0x01010101u);               // a zero byte marks a channel whose arg-max is this pixel
+            if (((hit - 0x01010101u) & ~hit & 0x80808080u) == 0u) continue;
+            const float4 d4 = __ldg(dy + o);
+            if ((hit & 0x000000ffu) == 0u) acc[0] += d4.x;
+            if ((hit & 0x0000ff00u) == 0u) acc[1] += d4.y;
+            if ((hit & 0x00ff0000u) == 0u) acc[2] += d4.z;
+            if ((hit & 0xff000000u) == 0u) acc[3] += d4.w;
+        }
+    }
+    dx[(((int64_t)n * g.H + ih) * g.W + iw) * g.C4 + c] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+bool pool_args_ok(int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
+    if (N < 1 || N > 65535 || H < 1 || W < 1 || C < 4 || (C & 3) || k < 1 || k > 15 || stride < 1 || pad < 0 || 2 * pad > k) return false;
+    if (Ho != (H + 2 * pad - k) / stride + 1 || Wo != (W + 2 * pad - k) / stride + 1 || Ho < 1 || Wo < 1 || H > 65535 || Ho > 65535) return false;
+    return (int64_t)W * (C / 4) < (int64_t)1 << 30;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spaa_relu_maxpool_nhwc_fwd(const float* x, int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int relu, float* y,
+                               uint8_t* idx, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(x && y && idx && pool_args_ok(N, H, W, C, k, stride, pad, Ho, Wo), "spaa_relu_maxpool_nhwc_fwd: bad arguments");
+    SPAA_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)idx & 3) == 0, "spaa_relu_maxpool_nhwc_fwd: misaligned pointer");
+    const PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo};
+    const dim3 grid((unsigned)((Wo * g.C4 + kThreads - 1) / kThreads), (unsigned)Ho, (unsigned)N);
+#define SPAA_POOL_LAUNCH(R, K_) relu_maxpool_fwd_kernel<R, K_><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, (uint32_t*)idx, g)
+    if (relu) { if (k == 3) SPAA_POOL_LAUNCH(true, 3); else if (k == 2) SPAA_POOL_LAUNCH(true, 2); else SPAA_POOL_LAUNCH(true, 0); }
+    else { if (k == 3) SPAA_POOL_LAUNCH(false, 3); else if (k == 2) SPAA_POOL_LAUNCH(false, 2); else SPAA_POOL_LAUNCH(false, 0); }
+#undef SPAA_POOL_LAUNCH
+    SPAA_CHECK_LAUNCH("spaa_relu_maxpool_nhwc_fwd");
+    return SPAA_OK;
+}
+
+int spaa_relu_maxpool_nhwc_bwd(const float* dy, const uint8_t* idx, int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                               float* dx, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(dy && dx && idx && pool_args_ok(N, H, W, C, k, stride, pad, Ho, Wo), "spaa_relu_maxpool_nhwc_bwd: bad arguments");
+    SPAA_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)idx & 3) == 0, "spaa_relu_maxpool_nhwc_bwd: misaligned pointer");
+    const PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo};
+    const dim3 grid((unsigned)((W * g.C4 + kThreads - 1) / kThreads), (unsigned)H, (unsigned)N);
+    relu_maxpool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)dy, (const uint32_t*)idx, (float4*)dx, g);
+    SPAA_CHECK_LAUNCH("spaa_relu_maxpool_nhwc_bwd");
+    return SPAA_OK;
+}
+
+}  // extern "C"

@@ -81,11 +81,39 @@ def _f32c(t: Tensor) -> Tensor:
 _ws_cache: Dict[Tuple[str, int, int], Tensor] = {}
 
 
+_ws_scope_id = 0
+
+
+class ws_scope:
+    """Workspaces requested inside `with ws_scope(k):` are private to scope k.  An attack engine runs its iteration inside its own
+    scope, so engines that execute concurrently on different streams (half-batch pipelining) never share a scratch buffer."""
+
+    def __init__(self, scope: int):
+        self.scope, self.prev = int(scope), 0
+
+    def __enter__(self):
+        global _ws_scope_id
+        self.prev, _ws_scope_id = _ws_scope_id, self.scope
+        return self
+
+    def __exit__(self, *exc):
+        global _ws_scope_id
+        _ws_scope_id = self.prev
+        return False
+
+
+def release_scope(scope: int) -> None:
+    """Drop the workspaces of a finished `ws_scope` (called when an attack engine is destroyed)."""
+    suffix = f"@{int(scope)}"
+    for k in [k for k in _ws_cache if k[0].endswith(suffix)]:
+        del _ws_cache[k]
+
+
 def workspace(tag: str, nbytes: int, device) -> Tensor:
     """Zero-initialised scratch owned by this module; kernels leave it zeroed (self-resetting counters), so it is
-    reused across launches on the same stream.  Distinct `tag`s never alias."""
+    reused across launches on the same stream.  Distinct `tag`s (and distinct `ws_scope`s) never alias."""
     dev = torch.device(device)
-    key = (tag, dev.index if dev.index is not None else torch.cuda.current_device(), int(nbytes))
+    key = (tag if _ws_scope_id == 0 else f"{tag}@{_ws_scope_id}", dev.index if dev.index is not None else torch.cuda.current_device(), int(nbytes))
     t = _ws_cache.get(key)
     if t is None:
         t = torch.zeros((int(nbytes) + 3) // 4, dtype=torch.int32, device=dev)
@@ -756,3 +784,52 @@ def clf_preprocess_bwd(dout: Tensor, img_hw, crop, mean, std) -> Tensor:
     dimg = torch.empty((B, 3, img_hw[0], img_hw[1]), dtype=torch.float32, device=dout.device)
     lib().spaa_clf_preprocess_bwd(_p(dout), B, img_hw[0], img_hw[1], top, left, ch, cw, oh, ow, _f3(std), int(nhwc), _p(dimg), _stream()); _count()
     return dimg
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused ReLU + max-pooling of the external classifier's first stage (channels_last fp32)
+# ------------------------------------------------------------------------------------------------------------
+
+def _nhwc_dense(x: Tensor) -> bool:
+    """Logical [N,C,H,W] tensor stored densely as [N,H,W,C] (strides of size-1 dimensions are arbitrary in torch and ignored)."""
+    N, C, H, W = x.shape
+    want = (H * W * C, 1, W * C, C)
+    return all(sz == 1 or st == w for sz, st, w in zip(x.shape, x.stride(), want))
+
+
+def relu_maxpool_supported(x: Tensor, k: int, stride: int, pad: int) -> bool:
+    """True when `x` is what spaa_relu_maxpool_nhwc_fwd reads in place: a CUDA fp32 [N,C,H,W] tensor in channels_last memory, C % 4 == 0."""
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+        return False
+    N, C, H, W = x.shape
+    if C % 4 or not (1 <= k <= 15) or stride < 1 or pad < 0 or 2 * pad > k or H + 2 * pad < k or W + 2 * pad < k or max(N, H) > 65535:
+        return False
+    return _nhwc_dense(x) and x.data_ptr() % 16 == 0
+
+
+def relu_maxpool_nhwc(x: Tensor, k: int, stride: int, pad: int, relu: bool):
+    """max_pool2d(relu(x) if relu else x, k, stride, pad) for a channels_last fp32 tensor.  Returns (y, idx): y logical [N,C,Ho,Wo] in
+    channels_last memory, idx uint8 [N,Ho,Wo,C] (the tap that was selected; 255: none) for relu_maxpool_nhwc_bwd."""
+    if not relu_maxpool_supported(x, k, stride, pad):
+        raise RuntimeError("relu_maxpool_nhwc needs a CUDA fp32 channels_last tensor with C % 4 == 0")
+    N, C, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
+    idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+    lib().spaa_relu_maxpool_nhwc_fwd(_p(x), N, H, W, C, k, stride, pad, Ho, Wo, int(bool(relu)), _p(y), _p(idx), _stream()); _count()
+    return y.permute(0, 3, 1, 2), idx
+
+
+def relu_maxpool_nhwc_bwd(dy: Tensor, idx: Tensor, in_hw, k: int, stride: int, pad: int) -> Tensor:
+    """Adjoint of relu_maxpool_nhwc: dy logical [N,C,Ho,Wo] -> dx logical [N,C,H,W] (channels_last memory)."""
+    _need_cuda(dy, idx)
+    if dy.dtype != torch.float32:
+        dy = dy.float()
+    N, C, Ho, Wo = dy.shape
+    if not _nhwc_dense(dy):
+        dy = dy.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    H, W = in_hw
+    assert idx.shape == (N, Ho, Wo, C) and idx.dtype == torch.uint8 and idx.is_contiguous()
+    dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dy.device)
+    lib().spaa_relu_maxpool_nhwc_bwd(_p(dy), _p(idx), N, H, W, C, k, stride, pad, Ho, Wo, _p(dx), _stream()); _count()
+    return dx.permute(0, 3, 1, 2)

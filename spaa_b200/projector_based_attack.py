@@ -11,6 +11,7 @@ Loop constants the reference recomputes every iteration (sampling grid, skipConv
 from __future__ import annotations
 
 import collections
+import itertools
 import os
 import weakref
 from typing import List, Optional
@@ -23,6 +24,9 @@ from .img_proc import expand_4d
 from .models import PCNet, _Stack, set_precision
 from .ops import MASK_OPEN01
 from .perc_al import PerC_AL
+
+
+_SCOPES = itertools.count(1)
 
 
 def _unwrap(m):
@@ -45,8 +49,12 @@ class SpaaAttack:
     `SpaaAttack(...)`, `iters` x `step()`, `result()`; bench.py drives `step()` directly to time exactly K iterations."""
 
     def __init__(self, pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
-                 graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False):
-        """deterministic: the warp's backward runs as a gather through a per-attack CSR adjoint map instead of a scatter-add with atomics
+                 graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False, overlap: Optional[bool] = None):
+        """overlap: run the fused colour loss (and the prjl2 term), which only need the PCNet output, on an auxiliary stream beside the
+        external classifier's forward + backward (fork / join, recorded as a parallel branch of the captured graph).  Same kernels
+        and arithmetic.  Opt-in (default None: $SPAA_OVERLAP, off): measured on B200 at B=32 it is 2 % SLOWER (290 vs 296 it/s,
+        profiles/r1_overlap_probe.md) -- the issue-bound colour kernel takes SM time from the cuDNN kernels it runs beside.
+        deterministic: the warp's backward runs as a gather through a per-attack CSR adjoint map instead of a scatter-add with atomics
         (same result to fp32 rounding, bit-identical run to run, ~20 us slower per iteration at B=32).
         graph: replay one captured CUDA graph per iteration (default: on for the fused PCNet path).  An iteration is a fixed
         sequence of ~80 of our launches + ~300 cuDNN/ATen launches of the external classifier with no host decision in
@@ -124,6 +132,9 @@ class SpaaAttack:
             self.classifier = fold_batchnorm(classifier)
         self.use_graph = self.fused if graph is None else (bool(graph) and self.fused)
         self._graph, self._n_eager = None, 0
+        self.overlap = (os.environ.get("SPAA_OVERLAP", "0") != "0") if overlap is None else bool(overlap)
+        self._aux = torch.cuda.Stream(device=device) if self.overlap else None
+        self._scope = next(_SCOPES)                 # private kernel workspaces: engines may run concurrently on different streams
 
     def step(self):
         """One iteration of the loop body (:265-328)."""
@@ -185,7 +196,23 @@ class SpaaAttack:
         self.cam = self.logits = None
         return self
 
+    def __del__(self):
+        try:
+            ops.release_scope(self._scope)
+        except Exception:
+            pass
+
     def _step_eager(self):
+        with ops.ws_scope(self._scope):
+            self._iteration()
+
+    def _stealth_terms(self, cam):
+        ops.color_loss(cam, self.scene, self.ref_lab, cam_is_lab2=False, de_weighting=False, c_de=self.w_camde / self.hw_cam,
+                       c_l2=self.w_caml2 / self.hw_cam, stats=self.stats, grad=self.g_col)
+        if self.w_prjl2:
+            ops.chan_l2(self.prj_adv, self.gray, self.prjl2sum)
+
+    def _iteration(self):
         net, scene = self.net, self.scene
         # ---- forward ---------------------------------------------------------------------------------
         if self.fused:
@@ -206,11 +233,16 @@ class SpaaAttack:
                 cam_g = self.pcnet(torch.clamp(prj_leaf, 0, 1), self.scene_b)
             cam = cam_g.detach()
         # ---- losses, masks ---------------------------------------------------------------------------
-        logits, g_adv = _adv_grad(self.classifier, cam, self.cp_sz, self.target, self.targeted, self.clf_cl)
-        ops.color_loss(cam, scene, self.ref_lab, cam_is_lab2=False, de_weighting=False, c_de=self.w_camde / self.hw_cam,
-                       c_l2=self.w_caml2 / self.hw_cam, stats=self.stats, grad=self.g_col)
-        if self.w_prjl2:
-            ops.chan_l2(self.prj_adv, self.gray, self.prjl2sum)
+        if self._aux is not None:
+            main = torch.cuda.current_stream(self.device)
+            self._aux.wait_stream(main)                                        # fork: cam is ready
+            with torch.cuda.stream(self._aux):
+                self._stealth_terms(cam)
+            logits, g_adv = _adv_grad(self.classifier, cam, self.cp_sz, self.target, self.targeted, self.clf_cl)
+            main.wait_stream(self._aux)                                        # join before the decisions read the statistics
+        else:
+            logits, g_adv = _adv_grad(self.classifier, cam, self.cp_sz, self.target, self.targeted, self.clf_cl)
+            self._stealth_terms(cam)
         ops.attack_masks(logits, self.target, self.targeted, self.stats, self.prjl2sum, self.hw_cam, self.hw_prj, self.w_prjl2, self.w_caml2,
                          self.w_camde, self.d_thr, self.p_thresh, self.use_col, self.succ, self.better, self.col_loss, self.best_col)
         # ---- one backward with the per-sample selected cotangent ---------------------------------------
@@ -264,7 +296,7 @@ def _state_version(module) -> int:
 
 
 def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=None,
-                  graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False) -> SpaaAttack:
+                  graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False, overlap: Optional[bool] = None) -> SpaaAttack:
     """A SpaaAttack for this job.  Sweeps call spaa() many times with the same model, classifier, batch size and loss
     configuration (run_projector_based_attack, projector_based_attack.py:83-129): the engine -- its buffers and its captured
     CUDA graph -- is kept (LRU of 2) and only reset() for the new scene / targets.  A model whose parameters changed in
@@ -272,19 +304,19 @@ def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, ste
     net = _unwrap(pcnet)
     if not isinstance(net, PCNet) or graph is False:
         return SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph,
-                          fold_bn=fold_bn, deterministic=deterministic)
+                          fold_bn=fold_bn, deterministic=deterministic, overlap=overlap)
     if precision is not None:
         set_precision(net, precision)
     scene_shape = tuple(expand_4d(cam_scene).shape)
     key = (id(net), _state_version(net), id(getattr(classifier, "model", classifier)), len(target_idx), bool(targeted), stealth_loss, float(d_thr),
            tuple(setup_info["classifier_crop_sz"]), tuple(setup_info["prj_im_sz"]), float(setup_info["prj_brightness"]), scene_shape,
-           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32), fold_bn, bool(deterministic))
+           getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32), fold_bn, bool(deterministic), overlap)
     hit = _ENGINES.get(key)
     if hit is not None and hit[0]() is net and hit[1]() is getattr(classifier, "model", classifier):
         _ENGINES.move_to_end(key)
         return hit[2].reset(cam_scene, target_idx)
     A = SpaaAttack(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, graph=graph, fold_bn=fold_bn,
-                   deterministic=deterministic)
+                   deterministic=deterministic, overlap=overlap)
     try:
         _ENGINES[key] = (weakref.ref(net), weakref.ref(getattr(classifier, "model", classifier)), A)
     except TypeError:               # classifier object without weak-reference support: do not cache
@@ -300,14 +332,15 @@ def clear_engines() -> None:
 
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,
          iters: int = 50, verbose: bool = False, trace: Optional[List[dict]] = None, forced_prj: Optional[List[torch.Tensor]] = None,
-         precision: Optional[str] = None, graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False):
+         precision: Optional[str] = None, graph: Optional[bool] = None, fold_bn: Optional[bool] = None, deterministic: bool = False,
+         overlap: Optional[bool] = None):
     """projector_based_attack.py:212-339.  Returns (cam_infer_best, clamp(prj_adv_best, 0, 1)).
     Keyword-only extras (reference defaults): iters=50; precision None (keep the model's), 'fp32', 'fp16' or 'bf16';
     graph None (CUDA-graph replay of the iteration when the fused PCNet path is used), True or False; fold_bn None (fold the
     frozen classifier's inference-mode BatchNorm into its convolutions when cuDNN may use TF32), True or False; deterministic False (True: the
-    warp's backward as an atomics-free gather)."""
+    warp's backward as an atomics-free gather); overlap None / False (True: the stealth-loss kernels on an auxiliary stream beside the classifier; measured slower)."""
     A = attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, precision=precision, graph=graph,
-                      fold_bn=fold_bn, deterministic=deterministic)
+                      fold_bn=fold_bn, deterministic=deterministic, overlap=overlap)
     for it in range(iters):
         if forced_prj is not None:
             A.prj_adv.copy_(forced_prj[it])

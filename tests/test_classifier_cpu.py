@@ -21,12 +21,18 @@ def test_fold_batchnorm_keeps_logits_gradients_and_the_users_module(name):
     clf = Classifier(name, "cpu", [0])
     _randomise_bn(clf.model, 3)
     before = copy.deepcopy(clf.model.state_dict())
+    from spaa_b200.classifier import FusedReLUMaxPool2d
+    if name == "vgg16":                                   # no BatchNorm and no pooling fusion: nothing to change, the classifier itself comes back
+        assert fold_batchnorm(clf, fuse_pool=False) is clf
     view = fold_batchnorm(clf)
-    if name == "vgg16":                                   # no BatchNorm: nothing to fold, the classifier itself comes back
-        assert view is clf
-        return
     assert view is not clf and view.input_sz == clf.input_sz
     assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in view.model.modules())
+    # the private copy's ReLU -> MaxPool2d pairs / lone MaxPool2d modules are the fused module (on CPU tensors it runs the stock ops)
+    fused = [m for m in view.model.modules() if isinstance(m, FusedReLUMaxPool2d)]
+    assert not any(type(m) is torch.nn.MaxPool2d for m in view.model.modules())
+    assert [(m.kernel_size, m.stride, m.padding, m.with_relu) for m in fused] == {
+        "resnet18": [(3, 2, 1, True)], "vgg16": [(2, 2, 0, True)] * 5, "inception_v3": [(3, 2, 0, False)] * 2}[name]
+    assert any(type(m) is torch.nn.MaxPool2d for m in clf.model.modules())
     for k, v in clf.model.state_dict().items():           # the user's network is untouched
         assert torch.equal(v, before[k])
     x = torch.rand(2, 3, *clf.input_sz, generator=torch.Generator().manual_seed(5))
@@ -42,7 +48,9 @@ def test_fold_batchnorm_keeps_logits_gradients_and_the_users_module(name):
     assert torch.equal(outs[0].argmax(1), outs[1].argmax(1))
     # random-init inception_v3 (94 conv layers, no trained scales) has input gradients of ~1e-11 whose rounding noise is amplified
     # layer by layer: it is held to a relative Frobenius bound, resnet18 to max-abs
-    if name == "resnet18":
+    if name == "vgg16":                                   # same stock ops in the same order
+        assert torch.equal(outs[0], outs[1]) and torch.equal(grads[0], grads[1])
+    elif name == "resnet18":
         assert (grads[0] - grads[1]).abs().max().item() <= 1e-4 * grads[0].abs().max().item()
     else:
         rel = ((grads[0] - grads[1]).double().norm() / grads[0].double().norm()).item()

@@ -433,3 +433,67 @@ def test_fused_classifier_preprocess_vs_oracle(hw, crop, insz, channels_last):
         c = c.contiguous(memory_format=torch.channels_last)
     (y * c).sum().backward()
     close(x.grad, gref, 1e-6, 1e-5, "preprocess backward")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused ReLU + max-pooling (the external classifier's first stage in the attack engines' private copy)
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("k,s,p,hw,C,relu", [(3, 2, 1, (112, 112), 64, True), (2, 2, 0, (56, 40), 128, True), (3, 2, 0, (147, 147), 64, False),
+                                             (3, 2, 1, (9, 7), 4, True), (2, 2, 0, (7, 9), 8, True), (3, 1, 1, (6, 5), 12, False), (3, 3, 1, (8, 8), 4, True)])
+def test_fused_relu_maxpool_vs_torch(k, s, p, hw, C, relu):
+    """Values are exact (max-pooling selects); gradients equal torch's relu + max_pool2d autograd (same arg-max convention: first maximum in
+    row-major window order; ties at 0 carry no gradient through the ReLU) up to the summation order of <= 4 overlapping windows.  Inputs are
+    quantised to multiples of 0.5 with a third of them zero, so ties -- positive ones and the all-zero windows a ReLU produces -- are everywhere."""
+    from spaa_b200.classifier import FusedReLUMaxPool2d
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, C, *hw, generator=g)
+    x = torch.round(x * 2) / 2
+    x[torch.rand(x.shape, generator=g) < 0.3] = 0.0
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(F.relu(xr) if relu else xr, k, s, p)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xd = x.to(dev()).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    m = FusedReLUMaxPool2d(k, s, p, with_relu=relu)
+    from spaa_b200 import ops
+    n0 = ops.launch_count()
+    y = m(xd)
+    assert ops.launch_count() == n0 + 1, "the fused kernel did not run"
+    assert y.is_contiguous(memory_format=torch.channels_last) or min(y.shape) == 1
+    y.backward(dy.to(dev()))
+    assert ops.launch_count() == n0 + 2
+    assert torch.equal(y.detach().cpu(), yr.detach()), "pooled values must be exact"
+    close(xd.grad, xr.grad, 1e-6, 1e-6, "fused relu+maxpool backward")
+    # NCHW-contiguous gradients are accepted too (converted), and non-channels_last inputs run the stock ops of the pair
+    xd2 = x.to(dev()).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    m(xd2).backward(dy.to(dev()).contiguous())
+    close(xd2.grad, xr.grad, 1e-6, 1e-6, "fused relu+maxpool backward (NCHW cotangent)")
+    if C > 1 and hw[0] > 1:
+        assert torch.equal(m(x.to(dev())).cpu(), yr.detach())
+
+
+@pytest.mark.parametrize("name", ["resnet18", "vgg16"])
+def test_private_classifier_copy_pool_fusion_on_gpu(name):
+    """The attack engines' private classifier copy with and without the fused ReLU + max-pooling modules (same cuDNN convolutions on both
+    sides, so only the pooling differs): logits agree to rounding of the re-ordered window sums downstream, top-1 is identical, and the
+    input gradient agrees to 1e-5 relative."""
+    from spaa_b200.classifier import Classifier, FusedReLUMaxPool2d, fold_batchnorm, use_channels_last, device_logits
+    clf = Classifier(name, dev(), [0])
+    clf.model.to(memory_format=torch.channels_last)       # (use_channels_last() declines in the exact-fp32 test configuration; the layout is what matters here)
+    cl = True
+    plain, fused = fold_batchnorm(clf, fuse_pool=False), fold_batchnorm(clf, fuse_pool=True)
+    assert any(isinstance(m, FusedReLUMaxPool2d) for m in fused.model.modules())
+    assert not any(isinstance(m, FusedReLUMaxPool2d) for m in getattr(plain, "model").modules())
+    x = torch.rand(4, 3, 240, 320, generator=torch.Generator().manual_seed(5)).to(dev())
+    outs, grads = [], []
+    for c in (plain, fused):
+        leaf = x.clone().requires_grad_(True)
+        y = device_logits(c, leaf, (240, 240), cl)
+        gq, = torch.autograd.grad(y[:, 7].sum(), leaf)
+        outs.append(y.detach()); grads.append(gq)
+    scale = max(outs[0].abs().max().item(), 1.0)
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-6 * scale
+    assert torch.equal(outs[0].argmax(1), outs[1].argmax(1))
+    rel = ((grads[0] - grads[1]).double().norm() / grads[0].double().norm()).item()
+    assert rel <= 1e-5, rel
