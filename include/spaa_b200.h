@@ -286,10 +286,16 @@ int spaa_clf_preprocess_bwd(const float* dout, int64_t B, int H, int W, int top,
  * (threshold_backward, max_pool2d_with_indices_backward) in the attack engines' PRIVATE copy of the frozen classifier.
  *   x [N,H,W,C] fp32 (C % 4 == 0); y [N,Ho,Wo,C]; idx [N,Ho,Wo,C] uint8: tap number (r*k + q, row-major, first maximum wins as in
  *   ATen) of the selected element, 255 = none (relu != 0 and the window maximum was <= 0); Ho = (H + 2*pad - k)/stride + 1.
+ *   bias [C] (nullable): per-channel constant added before the ReLU (the preceding convolution's bias: max(x) + b == max(x + b)).
  *   bwd: dx [N,H,W,C] = adjoint applied to dy (every element written; no atomics).
+ * spaa_bias_act_nhwc: y = act(x + bias[c] + res) over n = N*H*W*C elements (bias, res nullable; relu != 0: clamp at 0): replaces the
+ *   `output.add_(bias)` that follows every biased cuDNN convolution in PyTorch, `out += identity` and `relu` of torchvision's
+ *   BasicBlock / BasicConv2d / VGG `features` (its adjoint is ATen's threshold_backward on the saved output).
  * -------------------------------------------------------------------------------------------------------- */
-int spaa_relu_maxpool_nhwc_fwd(const float* x, int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
-                               int relu, float* y, uint8_t* idx, spaa_stream_t stream);
+int spaa_relu_maxpool_nhwc_fwd(const float* x, const float* bias, int64_t N, int H, int W, int C, int k, int stride, int pad,
+                               int Ho, int Wo, int relu, float* y, uint8_t* idx, spaa_stream_t stream);
+int spaa_bias_act_nhwc(const float* x, const float* bias, const float* res, int64_t n, int C, int relu, float* y,
+                       spaa_stream_t stream);
 int spaa_relu_maxpool_nhwc_bwd(const float* dy, const uint8_t* idx, int64_t N, int H, int W, int C, int k, int stride, int pad,
                                int Ho, int Wo, float* dx, spaa_stream_t stream);
 

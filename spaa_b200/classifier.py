@@ -139,8 +139,8 @@ class _ReluMaxPoolFn(torch.autograd.Function):
     """max_pool2d(relu(x)) (or max_pool2d(x)) and its adjoint as one kernel each (ops.relu_maxpool_nhwc)."""
 
     @staticmethod
-    def forward(ctx, x, k, stride, pad, relu):
-        y, idx = ops.relu_maxpool_nhwc(x, k, stride, pad, relu)
+    def forward(ctx, x, k, stride, pad, relu, bias):
+        y, idx = ops.relu_maxpool_nhwc(x, k, stride, pad, relu, bias)
         ctx.save_for_backward(idx)
         ctx.geom = (tuple(x.shape[2:]), k, stride, pad)
         return y
@@ -149,7 +149,35 @@ class _ReluMaxPoolFn(torch.autograd.Function):
     def backward(ctx, dy):
         idx, = ctx.saved_tensors
         hw, k, stride, pad = ctx.geom
-        return ops.relu_maxpool_nhwc_bwd(dy, idx, hw, k, stride, pad), None, None, None, None
+        return ops.relu_maxpool_nhwc_bwd(dy, idx, hw, k, stride, pad), None, None, None, None, None
+
+
+class _BiasActFn(torch.autograd.Function):
+    """relu?(x + bias[c] + res) as one kernel (ops.bias_act_nhwc); the adjoint is ATen's threshold_backward on the saved output.
+    bias is a frozen constant of the private classifier copy (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, res, relu):
+        y = ops.bias_act_nhwc(x, bias, res, relu)
+        ctx.relu, ctx.has_res = bool(relu), res is not None
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = torch.ops.aten.threshold_backward(dy, ctx.saved_tensors[0], 0) if ctx.relu else dy
+        return g, None, (g if ctx.has_res else None), None
+
+
+def bias_act(x, bias, res=None, relu: bool = True):
+    """relu?(x + bias.view(1,-1,1,1) + res): fused kernel for CUDA fp32 channels_last operands, the stock ops otherwise (same order of additions)."""
+    if ops.bias_act_supported(x, bias, res):
+        return _BiasActFn.apply(x, bias, res, relu)
+    y = x if bias is None else x + bias.view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res
+    return F.relu(y) if relu else y
 
 
 class FusedReLUMaxPool2d(torch.nn.Module):
@@ -157,17 +185,110 @@ class FusedReLUMaxPool2d(torch.nn.Module):
     private copy of the frozen classifier.  CUDA fp32 channels_last inputs run the fused kernel; anything else runs the stock ops
     the pair was made of, so the private copy computes the same function everywhere."""
 
-    def __init__(self, kernel_size: int, stride: int, padding: int, with_relu: bool):
+    def __init__(self, kernel_size: int, stride: int, padding: int, with_relu: bool, bias=None):
+        """bias: the bias of the (frozen) convolution in front, stripped from it and added here (max(x) + b == max(x + b) exactly)."""
         super().__init__()
         self.kernel_size, self.stride, self.padding, self.with_relu = int(kernel_size), int(stride), int(padding), bool(with_relu)
+        self.register_buffer("bias", None if bias is None else bias.detach().clone().contiguous())
 
     def extra_repr(self):
-        return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}, with_relu={self.with_relu}"
+        return (f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}, with_relu={self.with_relu}, "
+                f"bias={self.bias is not None}")
 
     def forward(self, x):
-        if ops.relu_maxpool_supported(x, self.kernel_size, self.stride, self.padding):
-            return _ReluMaxPoolFn.apply(x, self.kernel_size, self.stride, self.padding, self.with_relu)
+        if ops.relu_maxpool_supported(x, self.kernel_size, self.stride, self.padding) and ops._bias_ok(self.bias, x):
+            return _ReluMaxPoolFn.apply(x, self.kernel_size, self.stride, self.padding, self.with_relu, self.bias)
+        if self.bias is not None:
+            x = x + self.bias.view(1, -1, 1, 1)
         return F.max_pool2d(F.relu(x) if self.with_relu else x, self.kernel_size, self.stride, self.padding)
+
+
+class ConvBiasAct(torch.nn.Module):
+    """A frozen cuDNN convolution whose bias was stripped, followed by relu?(. + bias + residual) as ONE elementwise kernel (bias_act).
+    PyTorch adds a convolution's bias with a separate strided kernel; ReLU and the residual add are two more."""
+
+    def __init__(self, conv: torch.nn.Conv2d, relu: bool = True, extra_bias=None):
+        super().__init__()
+        self.conv, b = _strip_bias(conv)
+        if extra_bias is not None:
+            b = b + extra_bias
+        self.register_buffer("bias", b.detach().clone().contiguous())
+        self.relu = bool(relu)
+
+    def forward(self, x, res=None):
+        return bias_act(self.conv(x), self.bias, res, self.relu)
+
+
+class FusedBasicBlock(torch.nn.Module):
+    """torchvision BasicBlock (resnet.py: conv1-bn1-relu-conv2-bn2, += identity / downsample(x), relu) after BatchNorm folding: the same
+    three cuDNN convolutions, two fused elementwise kernels instead of seven.  The downsample branch's bias is folded into conv2's."""
+
+    def __init__(self, blk):
+        super().__init__()
+        ds = blk.downsample
+        self.dconv, bd = (None, None) if ds is None else _strip_bias(ds[0])
+        self.cba1 = ConvBiasAct(blk.conv1, relu=True)
+        self.cba2 = ConvBiasAct(blk.conv2, relu=True, extra_bias=bd)
+
+    def forward(self, x):
+        out = self.cba1(x)
+        return self.cba2(out, x if self.dconv is None else self.dconv(x))
+
+
+def _strip_bias(conv: torch.nn.Conv2d):
+    """(the same convolution sharing `conv`'s weight but without bias, its bias tensor)."""
+    c = torch.nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups, bias=False,
+                        padding_mode=conv.padding_mode, device=conv.weight.device, dtype=conv.weight.dtype)
+    c.weight = conv.weight
+    return c, conv.bias.detach()
+
+
+def _biased_conv(m) -> bool:
+    return type(m) is torch.nn.Conv2d and m.bias is not None and isinstance(m.padding, tuple)
+
+
+def fuse_bias_act(model) -> int:
+    """In place, on a BatchNorm-folded private copy: strip the bias of every cuDNN convolution whose consumer is known and add it in the fused
+    kernel that follows -- ResNet stem (conv1 -> relu -> maxpool), BasicBlock, Inception's BasicConv2d, `Conv2d -> ReLU [-> MaxPool2d]` runs of an
+    nn.Sequential (VGG `features`).  Returns the number of rewritten sites."""
+    from torchvision.models import inception, resnet
+    ident = lambda m: type(m) is torch.nn.Identity
+    n = 0
+    for mod in list(model.modules()):
+        kids = mod._modules
+        if isinstance(mod, resnet.ResNet) and _biased_conv(kids.get("conv1")) and ident(kids.get("bn1")) and type(kids.get("relu")) is torch.nn.ReLU:
+            g = _plain_maxpool(kids.get("maxpool"))
+            if g is not None:
+                kids["conv1"], b = _strip_bias(kids["conv1"])
+                kids["relu"] = torch.nn.Identity()
+                kids["maxpool"] = FusedReLUMaxPool2d(*g, with_relu=True, bias=b)
+                n += 1
+        if isinstance(mod, torch.nn.Sequential):
+            names = list(kids.keys())
+            for i in range(len(names) - 1):
+                conv, act = kids[names[i]], kids[names[i + 1]]
+                if not (_biased_conv(conv) and type(act) is torch.nn.ReLU):
+                    continue
+                g = _plain_maxpool(kids[names[i + 2]]) if i + 2 < len(names) else None
+                if g is not None:
+                    kids[names[i]], b = _strip_bias(conv)
+                    kids[names[i + 1]] = torch.nn.Identity()
+                    kids[names[i + 2]] = FusedReLUMaxPool2d(*g, with_relu=True, bias=b)
+                else:
+                    kids[names[i]] = ConvBiasAct(conv, relu=True)
+                    kids[names[i + 1]] = torch.nn.Identity()
+                n += 1
+        for name, child in list(kids.items()):
+            if (type(child) is resnet.BasicBlock and _biased_conv(child.conv1) and _biased_conv(child.conv2) and ident(child.bn1) and ident(child.bn2)
+                    and type(child.relu) is torch.nn.ReLU
+                    and (child.downsample is None or (isinstance(child.downsample, torch.nn.Sequential) and len(child.downsample) == 2
+                                                      and _biased_conv(child.downsample[0]) and ident(child.downsample[1])))):
+                kids[name] = FusedBasicBlock(child)
+                n += 1
+            elif type(child) is inception.BasicConv2d and _biased_conv(child.conv) and ident(child.bn):
+                kids[name] = ConvBiasAct(child.conv, relu=True)           # BasicConv2d.forward: conv -> bn -> F.relu
+                n += 1
+    return n
 
 
 def _plain_maxpool(m):
@@ -220,7 +341,7 @@ class _FoldedView:
         self.model, self.input_sz, self.name = model, input_sz, name
 
 
-def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None):
+def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Optional[bool] = None):
     """A view of `classifier` whose network is a PRIVATE copy with every inference-mode BatchNorm2d folded into the cuDNN
     convolution in front of it (torch.nn.utils.fusion.fuse_conv_bn_eval: w' = w * gamma / sqrt(var + eps), b' likewise).
     The classifier is frozen and in eval() (classifier.py:38-42), so its BatchNorm layers are per-channel affine maps: the
@@ -230,6 +351,8 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None):
     fuse_pool (default: $SPAA_FUSE_POOL, on): the copy's `ReLU -> MaxPool2d` pairs and lone MaxPool2d modules become
     FusedReLUMaxPool2d (fuse_relu_maxpool): exact max-pooling, one of our kernels each way instead of ATen's relu / max_pool2d /
     threshold_backward / max_pool2d_backward passes over the largest activation of the iteration.
+    fuse_bias (default: $SPAA_FUSE_BIAS, on): the folded biases leave the cuDNN convolutions and are added, together with the residual and the
+    ReLU, by one kernel per convolution (fuse_bias_act: ConvBiasAct / FusedBasicBlock) instead of ATen's two or three elementwise passes.
     The user's module is not modified.  Returns `classifier` itself when there is nothing to change (opaque callables,
     training-mode networks)."""
     import copy
@@ -237,11 +360,15 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None):
     model, input_sz = getattr(classifier, "model", None), getattr(classifier, "input_sz", None)
     if fuse_pool is None:
         fuse_pool = os.environ.get("SPAA_FUSE_POOL", "1") != "0"
+    if fuse_bias is None:
+        fuse_bias = os.environ.get("SPAA_FUSE_BIAS", "1") != "0"
     if not isinstance(model, torch.nn.Module) or input_sz is None or model.training:
         return classifier
     has_bn = any(isinstance(m, torch.nn.BatchNorm2d) for m in model.modules())
     has_pool = fuse_pool and any(_plain_maxpool(m) is not None for m in model.modules())
-    if not has_bn and not has_pool:
+    has_bias = fuse_bias and isinstance(model, torch.nn.Module) and any(isinstance(m, torch.nn.Sequential) and any(_biased_conv(c) for c in m.children())
+                                                                        for m in model.modules())
+    if not has_bn and not has_pool and not has_bias:
         return classifier
     folded = copy.deepcopy(model)
     n = 0
@@ -256,6 +383,8 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None):
                 mod._modules[a] = fuse_conv_bn_eval(conv, bn)
                 mod._modules[b] = torch.nn.Identity()
                 n += 1
+    if fuse_bias:
+        n += fuse_bias_act(folded)
     if fuse_pool:
         n += fuse_relu_maxpool(folded)
     if n == 0:

@@ -1,4 +1,4 @@
-// Fused ReLU + max-pooling (forward and adjoint) on fp32 NHWC tensors -- the two steps that follow the first convolution of
+// Classifier glue kernels.  (1) Fused [bias +] ReLU + max-pooling (forward and adjoint) on fp32 NHWC tensors -- the two steps that follow the first convolution of
 // the external classifier (torchvision ResNet stem: conv1 -> bn1 -> relu -> maxpool 3x3 s2 p1; VGG: ReLU -> MaxPool2d(2,2); Inception:
 // MaxPool2d(3, 2)), classifier.py:22-33 of the reference builds those networks.  They touch the largest activations of the whole attack
 // iteration (resnet18, B = 32: 103 MB in, 26 MB out) and ATen's channels_last kernels for them (max_pool_forward_nhwc 127 us,
@@ -7,6 +7,9 @@
 // window, 255 = "no gradient": the ReLU was inactive), the adjoint in gather form (every input element written exactly once: no
 // zero-fill, no atomics).  max(relu(x)) == relu(max(x)) and the first maximum in row-major window order is kept, as ATen does.
 // HBM-bound: algorithmic bytes = 4*(in + out) + out (index bytes) forward; 4*(in + out) + out backward.
+// (2) bias_act_kernel: y = relu(x + bias[c] + residual) in one pass -- after BatchNorm folding every cuDNN convolution of the private copy
+// carries a bias, which PyTorch adds with a separate (strided, non-vectorised) elementwise kernel, followed by ATen's residual add and ReLU
+// kernels: 44 elementwise launches per resnet18 forward (profiles/r1_final_launches.md) become 16.
 #include "common.cuh"
 #include "../../include/spaa_b200.h"
 
@@ -21,7 +24,8 @@ struct PoolGeom { int H, W, C4, k, s, p, Ho, Wo; };
 // grid = (ceil(Wo*C4 / kThreads), Ho, N): one thread = one output pixel x 4 channels
 // K: compile-time window size (2, 3: loops unrolled, the window's loads are independent and in flight together) or 0 (runtime g.k)
 template <bool RELU, int K>
-__global__ void __launch_bounds__(kThreads) relu_maxpool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, uint32_t* __restrict__ idx, PoolGeom g) {
+__global__ void __launch_bounds__(kThreads) relu_maxpool_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ bias, float4* __restrict__ y,
+                                                                    uint32_t* __restrict__ idx, PoolGeom g) {
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= g.Wo * g.C4) return;
     const int ow = j / g.C4, c = j - ow * g.C4;
@@ -49,6 +53,10 @@ __global__ void __launch_bounds__(kThreads) relu_maxpool_fwd_kernel(const float4
             for (int e = 0; e < 4; ++e)
                 if (v[e] > m[e] || v[e] != v[e]) { m[e] = v[e]; a[e] = tap; }
         }
+    }
+    if (bias) {                                  // max(x) + b == max(x + b) exactly (rounding is monotonic), and the arg-max does not move
+        const float4 b4 = __ldg(bias + c);
+        m[0] += b4.x; m[1] += b4.y; m[2] += b4.z; m[3] += b4.w;
     }
     if (RELU) {
 #pragma unroll
@@ -91,6 +99,22 @@ __global__ void __launch_bounds__(kThreads) relu_maxpool_bwd_kernel(const float4
     dx[(((int64_t)n * g.H + ih) * g.W + iw) * g.C4 + c] = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
+// y = act(x + bias[c] + res) on a dense NHWC tensor (n4 float4 elements, C4 = C / 4): the glue between two cuDNN convolutions of the
+// classifier's private copy (folded-BatchNorm bias, residual add, ReLU) in one pass instead of ATen's three.
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads) bias_act_kernel(const float4* __restrict__ x, const float4* __restrict__ bias, const float4* __restrict__ res,
+                                                            float4* __restrict__ y, uint32_t n4, uint32_t C4) {
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n4; i += gridDim.x * kThreads) {
+        float4 v = __ldg(x + i);
+        if (bias) { const float4 b = __ldg(bias + i % C4); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (res) { const float4 r = __ldg(res + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        if (RELU) {               // clamp_min semantics: NaN propagates
+            v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y; v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+        }
+        y[i] = v;
+    }
+}
+
 bool pool_args_ok(int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
     if (N < 1 || N > 65535 || H < 1 || W < 1 || C < 4 || (C & 3) || k < 1 || k > 15 || stride < 1 || pad < 0 || 2 * pad > k) return false;
     if (Ho != (H + 2 * pad - k) / stride + 1 || Wo != (W + 2 * pad - k) / stride + 1 || Ho < 1 || Wo < 1 || H > 65535 || Ho > 65535) return false;
@@ -101,17 +125,33 @@ bool pool_args_ok(int64_t N, int H, int W, int C, int k, int stride, int pad, in
 
 extern "C" {
 
-int spaa_relu_maxpool_nhwc_fwd(const float* x, int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int relu, float* y,
-                               uint8_t* idx, spaa_stream_t stream) {
+int spaa_relu_maxpool_nhwc_fwd(const float* x, const float* bias, int64_t N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int relu,
+                               float* y, uint8_t* idx, spaa_stream_t stream) {
     SPAA_CHECK_ARG(x && y && idx && pool_args_ok(N, H, W, C, k, stride, pad, Ho, Wo), "spaa_relu_maxpool_nhwc_fwd: bad arguments");
-    SPAA_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)idx & 3) == 0, "spaa_relu_maxpool_nhwc_fwd: misaligned pointer");
+    SPAA_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)idx & 3) == 0 && ((uintptr_t)bias & 15) == 0,
+                   "spaa_relu_maxpool_nhwc_fwd: misaligned pointer");
     const PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo};
     const dim3 grid((unsigned)((Wo * g.C4 + kThreads - 1) / kThreads), (unsigned)Ho, (unsigned)N);
-#define SPAA_POOL_LAUNCH(R, K_) relu_maxpool_fwd_kernel<R, K_><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, (uint32_t*)idx, g)
+#define SPAA_POOL_LAUNCH(R, K_) relu_maxpool_fwd_kernel<R, K_><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)bias, (float4*)y, (uint32_t*)idx, g)
     if (relu) { if (k == 3) SPAA_POOL_LAUNCH(true, 3); else if (k == 2) SPAA_POOL_LAUNCH(true, 2); else SPAA_POOL_LAUNCH(true, 0); }
     else { if (k == 3) SPAA_POOL_LAUNCH(false, 3); else if (k == 2) SPAA_POOL_LAUNCH(false, 2); else SPAA_POOL_LAUNCH(false, 0); }
 #undef SPAA_POOL_LAUNCH
     SPAA_CHECK_LAUNCH("spaa_relu_maxpool_nhwc_fwd");
+    return SPAA_OK;
+}
+
+int spaa_bias_act_nhwc(const float* x, const float* bias, const float* res, int64_t n, int C, int relu, float* y, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(x && y && n > 0 && C >= 4 && (C & 3) == 0 && n % C == 0 && n / 4 < ((int64_t)1 << 32), "spaa_bias_act_nhwc: bad arguments");
+    SPAA_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)res) & 15) == 0, "spaa_bias_act_nhwc: misaligned pointer");
+    const uint32_t n4 = (uint32_t)(n / 4);
+    int64_t blocks = ((int64_t)n4 + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)kNumSMs * 32;
+    if (blocks > cap) blocks = cap;
+    if (relu)
+        bias_act_kernel<true><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)bias, (const float4*)res, (float4*)y, n4, (uint32_t)(C / 4));
+    else
+        bias_act_kernel<false><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)bias, (const float4*)res, (float4*)y, n4, (uint32_t)(C / 4));
+    SPAA_CHECK_LAUNCH("spaa_bias_act_nhwc");
     return SPAA_OK;
 }
 

@@ -807,16 +807,41 @@ def relu_maxpool_supported(x: Tensor, k: int, stride: int, pad: int) -> bool:
     return _nhwc_dense(x) and x.data_ptr() % 16 == 0
 
 
-def relu_maxpool_nhwc(x: Tensor, k: int, stride: int, pad: int, relu: bool):
-    """max_pool2d(relu(x) if relu else x, k, stride, pad) for a channels_last fp32 tensor.  Returns (y, idx): y logical [N,C,Ho,Wo] in
-    channels_last memory, idx uint8 [N,Ho,Wo,C] (the tap that was selected; 255: none) for relu_maxpool_nhwc_bwd."""
-    if not relu_maxpool_supported(x, k, stride, pad):
+def _bias_ok(bias: Optional[Tensor], x: Tensor) -> bool:
+    return bias is None or (bias.is_cuda and bias.dtype == torch.float32 and bias.dim() == 1 and bias.shape[0] == x.shape[1] and bias.is_contiguous()
+                            and bias.data_ptr() % 16 == 0)
+
+
+def bias_act_supported(x: Tensor, bias: Optional[Tensor], res: Optional[Tensor]) -> bool:
+    """True when spaa_bias_act_nhwc reads these operands in place: CUDA fp32 [N,C,H,W] in channels_last memory, C % 4 == 0."""
+    if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.numel() > 0):
+        return False
+    if not (_nhwc_dense(x) and x.data_ptr() % 16 == 0 and _bias_ok(bias, x) and x.numel() // 4 < 2 ** 32):
+        return False
+    return res is None or (res.is_cuda and res.dtype == torch.float32 and res.shape == x.shape and _nhwc_dense(res) and res.data_ptr() % 16 == 0)
+
+
+def bias_act_nhwc(x: Tensor, bias: Optional[Tensor], res: Optional[Tensor], relu: bool) -> Tensor:
+    """relu?(x + bias[c] + res) in one pass; a new tensor with x's (channels_last) layout."""
+    if not bias_act_supported(x, bias, res):
+        raise RuntimeError("bias_act_nhwc needs CUDA fp32 channels_last tensors with C % 4 == 0")
+    y = torch.empty_like(x)          # preserve_format: dense channels_last like x
+    if not _nhwc_dense(y):
+        y = torch.empty(x.shape, dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+    lib().spaa_bias_act_nhwc(_p(x), _p(bias), _p(res), x.numel(), x.shape[1], int(bool(relu)), _p(y), _stream()); _count()
+    return y
+
+
+def relu_maxpool_nhwc(x: Tensor, k: int, stride: int, pad: int, relu: bool, bias: Optional[Tensor] = None):
+    """max_pool2d(relu(x + bias) if relu else x + bias, k, stride, pad) for a channels_last fp32 tensor.  Returns (y, idx): y logical
+    [N,C,Ho,Wo] in channels_last memory, idx uint8 [N,Ho,Wo,C] (the tap that was selected; 255: none) for relu_maxpool_nhwc_bwd."""
+    if not relu_maxpool_supported(x, k, stride, pad) or not _bias_ok(bias, x):
         raise RuntimeError("relu_maxpool_nhwc needs a CUDA fp32 channels_last tensor with C % 4 == 0")
     N, C, H, W = x.shape
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     y = torch.empty((N, Ho, Wo, C), dtype=torch.float32, device=x.device)
     idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device)
-    lib().spaa_relu_maxpool_nhwc_fwd(_p(x), N, H, W, C, k, stride, pad, Ho, Wo, int(bool(relu)), _p(y), _p(idx), _stream()); _count()
+    lib().spaa_relu_maxpool_nhwc_fwd(_p(x), _p(bias), N, H, W, C, k, stride, pad, Ho, Wo, int(bool(relu)), _p(y), _p(idx), _stream()); _count()
     return y.permute(0, 3, 1, 2), idx
 
 

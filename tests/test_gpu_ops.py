@@ -455,7 +455,12 @@ def test_fused_relu_maxpool_vs_torch(k, s, p, hw, C, relu):
     dy = torch.randn(yr.shape, generator=g)
     yr.backward(dy)
     xd = x.to(dev()).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    m = FusedReLUMaxPool2d(k, s, p, with_relu=relu)
+    bias = (torch.round(torch.randn(C, generator=g) * 2) / 2) if (relu and C >= 8) else None     # the stripped bias of the convolution in front
+    if bias is not None:
+        xr = x.clone().requires_grad_(True)
+        yr = F.max_pool2d(F.relu(xr + bias.view(1, -1, 1, 1)), k, s, p)
+        yr.backward(dy)
+    m = FusedReLUMaxPool2d(k, s, p, with_relu=relu, bias=bias).to(dev())
     from spaa_b200 import ops
     n0 = ops.launch_count()
     y = m(xd)
@@ -473,19 +478,55 @@ def test_fused_relu_maxpool_vs_torch(k, s, p, hw, C, relu):
         assert torch.equal(m(x.to(dev())).cpu(), yr.detach())
 
 
-@pytest.mark.parametrize("name", ["resnet18", "vgg16"])
+@pytest.mark.parametrize("shape,with_bias,with_res,relu", [((3, 64, 56, 56), True, True, True), ((2, 128, 7, 9), True, False, True),
+                                                           ((1, 4, 5, 3), False, True, True), ((2, 192, 35, 35), True, False, False),
+                                                           ((5, 8, 1, 1), True, True, True)])
+def test_fused_bias_act_vs_torch(shape, with_bias, with_res, relu):
+    """relu?(x + bias + res) in one kernel: bit-identical to the stock ops applied in the same order; adjoint = threshold_backward."""
+    from spaa_b200 import ops
+    from spaa_b200.classifier import bias_act
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(shape, generator=g)
+    bias = torch.randn(shape[1], generator=g) if with_bias else None
+    res = torch.randn(shape, generator=g) if with_res else None
+    dy = torch.randn(shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if with_res else None
+    yr = bias_act(xr, bias, rr, relu)                      # CPU tensors: the stock-op branch
+    yr.backward(dy)
+    cl = lambda t: t.to(dev()).contiguous(memory_format=torch.channels_last)
+    xd = cl(x).requires_grad_(True)
+    rd = cl(res).requires_grad_(True) if with_res else None
+    n0 = ops.launch_count()
+    y = bias_act(xd, bias.to(dev()) if with_bias else None, rd, relu)
+    assert ops.launch_count() == n0 + 1, "the fused kernel did not run"
+    y.backward(dy.to(dev()))
+    assert torch.equal(y.detach().cpu(), yr.detach())
+    assert torch.equal(xd.grad.cpu(), xr.grad)
+    if with_res:
+        assert torch.equal(rd.grad.cpu(), rr.grad)
+
+
+@pytest.mark.parametrize("name", ["resnet18", "vgg16", "inception_v3"])
 def test_private_classifier_copy_pool_fusion_on_gpu(name):
     """The attack engines' private classifier copy with and without the fused ReLU + max-pooling modules (same cuDNN convolutions on both
-    sides, so only the pooling differs): logits agree to rounding of the re-ordered window sums downstream, top-1 is identical, and the
-    input gradient agrees to 1e-5 relative."""
+    sides, so only the elementwise glue and the pooling differ): logits agree to fp32 rounding (the downsample branch's bias is folded into
+    conv2's; window sums are re-ordered in the pooling adjoint), top-1 is identical, the input gradient agrees to 1e-4 relative, and every
+    convolution of the copy is followed by exactly one of our kernels."""
     from spaa_b200.classifier import Classifier, FusedReLUMaxPool2d, fold_batchnorm, use_channels_last, device_logits
     clf = Classifier(name, dev(), [0])
     clf.model.to(memory_format=torch.channels_last)       # (use_channels_last() declines in the exact-fp32 test configuration; the layout is what matters here)
     cl = True
-    plain, fused = fold_batchnorm(clf, fuse_pool=False), fold_batchnorm(clf, fuse_pool=True)
+    plain, fused = fold_batchnorm(clf, fuse_pool=False, fuse_bias=False), fold_batchnorm(clf, fuse_pool=True, fuse_bias=True)
     assert any(isinstance(m, FusedReLUMaxPool2d) for m in fused.model.modules())
     assert not any(isinstance(m, FusedReLUMaxPool2d) for m in getattr(plain, "model").modules())
     x = torch.rand(4, 3, 240, 320, generator=torch.Generator().manual_seed(5)).to(dev())
+    from spaa_b200 import ops
+    n0 = ops.launch_count()
+    with torch.no_grad():
+        device_logits(fused, x, (240, 240), cl)
+    n_fused_launches = ops.launch_count() - n0 - 1                                        # (- the pre-processing kernel)
+    assert n_fused_launches == {"resnet18": 17, "vgg16": 13, "inception_v3": 96}[name], n_fused_launches
     outs, grads = [], []
     for c in (plain, fused):
         leaf = x.clone().requires_grad_(True)
@@ -493,7 +534,7 @@ def test_private_classifier_copy_pool_fusion_on_gpu(name):
         gq, = torch.autograd.grad(y[:, 7].sum(), leaf)
         outs.append(y.detach()); grads.append(gq)
     scale = max(outs[0].abs().max().item(), 1.0)
-    assert (outs[0] - outs[1]).abs().max().item() <= 1e-6 * scale
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-5 * scale
     assert torch.equal(outs[0].argmax(1), outs[1].argmax(1))
     rel = ((grads[0] - grads[1]).double().norm() / grads[0].double().norm()).item()
-    assert rel <= 1e-5, rel
+    assert rel <= 1e-4, rel

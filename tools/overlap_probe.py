@@ -1,5 +1,7 @@
 """Attack iterations/s of the bench workload (resnet18, 32 targets) for the stream-level schedules of one iteration:
-  stock / fused pools   the private classifier copy without / with the fused ReLU + max-pooling kernels; one engine, one stream
+  stock glue / fused pools / + bias/act   the private classifier copy with ATen's elementwise glue, with the fused ReLU + max-pooling kernels,
+            and with every convolution's bias / residual add / ReLU in one kernel; one engine, one stream
+  (SCHEDULES=1 adds:)
   overlap   stealth-loss kernels on an auxiliary stream beside the classifier (SpaaAttack(overlap=True))
   pipeN     N engines over target slices on N streams (SpaaAttackPipelined), with / without overlap
 Prints it/s (CUDA events around K iterations, all streams joined) and the largest difference of the attacked projector images
@@ -96,20 +98,23 @@ def run(name, make):
     return prj.clone()
 
 
-def with_env(fuse, make):
+def with_env(fuse_pool, fuse_bias, make):
     def f():
-        os.environ["SPAA_FUSE_POOL"] = "1" if fuse else "0"          # read when the engine builds its private classifier copy
+        os.environ["SPAA_FUSE_POOL"] = "1" if fuse_pool else "0"          # read when the engine builds its private classifier copy
+        os.environ["SPAA_FUSE_BIAS"] = "1" if fuse_bias else "0"
         return make()
     return f
 
 
-cfgs = [("stock pools", with_env(False, lambda: SpaaAttack(*args, overlap=False))),
-        ("fused pools", with_env(True, lambda: SpaaAttack(*args, overlap=False))),
-        ("fused pools + overlap", with_env(True, lambda: SpaaAttack(*args, overlap=True))),
-        ("pipe2", with_env(True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=False))),
-        ("pipe2 + overlap", with_env(True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=True))),
-        ("pipe4 + overlap", with_env(True, lambda: SpaaAttackPipelined(*args, pipeline=4, overlap=True))),
-        ("stock pools (again)", with_env(False, lambda: SpaaAttack(*args, overlap=False)))]
+cfgs = [("stock glue", with_env(False, False, lambda: SpaaAttack(*args, overlap=False))),
+        ("fused pools", with_env(True, False, lambda: SpaaAttack(*args, overlap=False))),
+        ("fused pools + bias/act", with_env(True, True, lambda: SpaaAttack(*args, overlap=False)))]
+if os.environ.get("SCHEDULES", "0") != "0":
+    cfgs += [("fused + overlap", with_env(True, True, lambda: SpaaAttack(*args, overlap=True))),
+             ("pipe2", with_env(True, True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=False))),
+             ("pipe2 + overlap", with_env(True, True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=True))),
+             ("pipe4 + overlap", with_env(True, True, lambda: SpaaAttackPipelined(*args, pipeline=4, overlap=True)))]
+cfgs += [("stock glue (again)", with_env(False, False, lambda: SpaaAttack(*args, overlap=False)))]
 ref = None
 for name, make in cfgs:
     try:
