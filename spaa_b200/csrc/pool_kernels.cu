@@ -19,16 +19,18 @@ namespace {
 
 constexpr int kThreads = 256;
 
-struct PoolGeom { int H, W, C4, k, s, p, Ho, Wo; };
+struct PoolGeom { int H, W, C4, k, s, p, Ho, Wo, nchunk; };
 
-// grid = (ceil(Wo*C4 / kThreads), Ho, N): one thread = one output pixel x 4 channels
+// grid = (ceil(Wo / blockDim.y) * nchunk, Ho, N): one thread = one output pixel x 4 channels
 // K: compile-time window size (2, 3: loops unrolled, the window's loads are independent and in flight together) or 0 (runtime g.k)
 template <bool RELU, int K>
 __global__ void __launch_bounds__(kThreads) relu_maxpool_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ bias, float4* __restrict__ y,
                                                                     uint32_t* __restrict__ idx, PoolGeom g) {
-    const int j = blockIdx.x * kThreads + threadIdx.x;
-    if (j >= g.Wo * g.C4) return;
-    const int ow = j / g.C4, c = j - ow * g.C4;
+    // blockDim = (bx, 256 / bx): x = 4-channel group inside a chunk of bx groups (consecutive lanes -> consecutive 16-byte words), y = pixel of the row.
+    // No per-thread division (the first version spent its time in j / C4 and the window-range divisions: 92 us for the adjoint at resnet18 B=32).
+    const int chunk = blockIdx.x % g.nchunk, pblk = blockIdx.x / g.nchunk;
+    const int c = chunk * blockDim.x + threadIdx.x, ow = pblk * blockDim.y + threadIdx.y;
+    if (ow >= g.Wo) return;
     const int oh = blockIdx.y, n = blockIdx.z;
     const int k = K ? K : g.k;
     const int h0 = oh * g.s - g.p, w0 = ow * g.s - g.p;
@@ -68,24 +70,30 @@ __global__ void __launch_bounds__(kThreads) relu_maxpool_fwd_kernel(const float4
     idx[o] = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
 }
 
-// grid = (ceil(W*C4 / kThreads), H, N): one thread = one INPUT pixel x 4 channels; sums the (<= ceil(k/s)^2) windows that selected it
+// grid = (ceil(W / blockDim.y) * nchunk, H, N): one thread = one INPUT pixel x 4 channels; sums the (<= ceil(k/s)^2) windows that selected it.
+// K, S: compile-time window / stride (3,2 and 2,2: at most ceil(K/S)^2 windows, unrolled, their loads independent) or 0,0 (runtime loops).
+template <int K, int S>
 __global__ void __launch_bounds__(kThreads) relu_maxpool_bwd_kernel(const float4* __restrict__ dy, const uint32_t* __restrict__ idx, float4* __restrict__ dx, PoolGeom g) {
-    const int j = blockIdx.x * kThreads + threadIdx.x;
-    if (j >= g.W * g.C4) return;
-    const int iw = j / g.C4, c = j - iw * g.C4;
+    const int chunk = blockIdx.x % g.nchunk, pblk = blockIdx.x / g.nchunk;
+    const int c = chunk * blockDim.x + threadIdx.x, iw = pblk * blockDim.y + threadIdx.y;
+    if (iw >= g.W) return;
     const int ih = blockIdx.y, n = blockIdx.z;
-    auto lo = [&](int i) { const int num = i + g.p - g.k + 1; return num <= 0 ? 0 : (num + g.s - 1) / g.s; };
-    const int oh_lo = lo(ih), ow_lo = lo(iw);
-    int oh_hi = (ih + g.p) / g.s, ow_hi = (iw + g.p) / g.s;
-    oh_hi = oh_hi < g.Ho ? oh_hi : g.Ho - 1;
-    ow_hi = ow_hi < g.Wo ? ow_hi : g.Wo - 1;
+    const int k = K ? K : g.k, s = S ? S : g.s;
+    // windows o with o*s - p <= i <= o*s - p + k - 1, i.e. tap r = i + p - o*s in [0, k): o = floor((i + p) / s) - a, a = 0 .. ceil(k/s) - 1
+    const int oh_top = (int)((unsigned)(ih + g.p) / (unsigned)s), ow_top = (int)((unsigned)(iw + g.p) / (unsigned)s);
+    const int nw = K ? (K + S - 1) / S : (k + s - 1) / s;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
-        const int r = ih - (oh * g.s - g.p);
-        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-            const int q = iw - (ow * g.s - g.p);
-            const uint32_t tap = (uint32_t)(r * g.k + q);
-            const int64_t o = (((int64_t)n * g.Ho + oh) * g.Wo + ow) * g.C4 + c;
+    const int64_t img = (int64_t)n * g.Ho * g.Wo;
+#pragma unroll
+    for (int a = nw - 1; a >= 0; --a) {                      // ascending window order
+        const int oh = oh_top - a, r = ih + g.p - oh * s;
+        if (oh < 0 || oh >= g.Ho || r >= k) continue;
+#pragma unroll
+        for (int b = nw - 1; b >= 0; --b) {
+            const int ow = ow_top - b, q = iw + g.p - ow * s;
+            if (ow < 0 || ow >= g.Wo || q >= k) continue;
+            const uint32_t tap = (uint32_t)(r * k + q);
+            const int64_t o = (img + (int64_t)oh * g.Wo + ow) * g.C4 + c;
             const uint32_t u = __ldg(idx + o);
             const uint32_t hit = u ^ (tap * 0x01010101u);               // a zero byte marks a channel whose arg-max is this pixel
             if (((hit - 0x01010101u) & ~hit & 0x80808080u) == 0u) continue;
@@ -97,6 +105,14 @@ __global__ void __launch_bounds__(kThreads) relu_maxpool_bwd_kernel(const float4
         }
     }
     dx[(((int64_t)n * g.H + ih) * g.W + iw) * g.C4 + c] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// thread-block shape for a row of `C4` 4-channel groups: bx = the largest power of two dividing C4 (<= 64), by = kThreads / bx pixels
+inline dim3 pool_block(int C4, int* nchunk) {
+    int bx = 1;
+    while (bx < 64 && C4 % (bx * 2) == 0) bx *= 2;
+    *nchunk = C4 / bx;
+    return dim3((unsigned)bx, (unsigned)(kThreads / bx), 1);
 }
 
 // y = act(x + bias[c] + res) on a dense NHWC tensor (n4 float4 elements, C4 = C / 4): the glue between two cuDNN convolutions of the
@@ -130,9 +146,10 @@ int spaa_relu_maxpool_nhwc_fwd(const float* x, const float* bias, int64_t N, int
     SPAA_CHECK_ARG(x && y && idx && pool_args_ok(N, H, W, C, k, stride, pad, Ho, Wo), "spaa_relu_maxpool_nhwc_fwd: bad arguments");
     SPAA_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)idx & 3) == 0 && ((uintptr_t)bias & 15) == 0,
                    "spaa_relu_maxpool_nhwc_fwd: misaligned pointer");
-    const PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo};
-    const dim3 grid((unsigned)((Wo * g.C4 + kThreads - 1) / kThreads), (unsigned)Ho, (unsigned)N);
-#define SPAA_POOL_LAUNCH(R, K_) relu_maxpool_fwd_kernel<R, K_><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)bias, (float4*)y, (uint32_t*)idx, g)
+    PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo, 1};
+    const dim3 block = pool_block(g.C4, &g.nchunk);
+    const dim3 grid((unsigned)((Wo + (int)block.y - 1) / (int)block.y * g.nchunk), (unsigned)Ho, (unsigned)N);
+#define SPAA_POOL_LAUNCH(R, K_) relu_maxpool_fwd_kernel<R, K_><<<grid, block, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)bias, (float4*)y, (uint32_t*)idx, g)
     if (relu) { if (k == 3) SPAA_POOL_LAUNCH(true, 3); else if (k == 2) SPAA_POOL_LAUNCH(true, 2); else SPAA_POOL_LAUNCH(true, 0); }
     else { if (k == 3) SPAA_POOL_LAUNCH(false, 3); else if (k == 2) SPAA_POOL_LAUNCH(false, 2); else SPAA_POOL_LAUNCH(false, 0); }
 #undef SPAA_POOL_LAUNCH
@@ -159,9 +176,14 @@ int spaa_relu_maxpool_nhwc_bwd(const float* dy, const uint8_t* idx, int64_t N, i
                                float* dx, spaa_stream_t stream) {
     SPAA_CHECK_ARG(dy && dx && idx && pool_args_ok(N, H, W, C, k, stride, pad, Ho, Wo), "spaa_relu_maxpool_nhwc_bwd: bad arguments");
     SPAA_CHECK_ARG(((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)idx & 3) == 0, "spaa_relu_maxpool_nhwc_bwd: misaligned pointer");
-    const PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo};
-    const dim3 grid((unsigned)((W * g.C4 + kThreads - 1) / kThreads), (unsigned)H, (unsigned)N);
-    relu_maxpool_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)dy, (const uint32_t*)idx, (float4*)dx, g);
+    PoolGeom g{H, W, C / 4, k, stride, pad, Ho, Wo, 1};
+    const dim3 block = pool_block(g.C4, &g.nchunk);
+    const dim3 grid((unsigned)((W + (int)block.y - 1) / (int)block.y * g.nchunk), (unsigned)H, (unsigned)N);
+#define SPAA_POOLB_LAUNCH(K_, S_) relu_maxpool_bwd_kernel<K_, S_><<<grid, block, 0, (cudaStream_t)stream>>>((const float4*)dy, (const uint32_t*)idx, (float4*)dx, g)
+    if (k == 3 && stride == 2) SPAA_POOLB_LAUNCH(3, 2);
+    else if (k == 2 && stride == 2) SPAA_POOLB_LAUNCH(2, 2);
+    else SPAA_POOLB_LAUNCH(0, 0);
+#undef SPAA_POOLB_LAUNCH
     SPAA_CHECK_LAUNCH("spaa_relu_maxpool_nhwc_bwd");
     return SPAA_OK;
 }
