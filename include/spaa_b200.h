@@ -271,7 +271,10 @@ int spaa_percal_masks(const float* logits, int ncls, const int64_t* labels, int 
  * Classifier pre-processing (the step on either side of the external classifier): replaces classifier.py:55-59
  * (centre crop, F.interpolate(mode='area'), ImageNet normalise) and its autograd graph.
  *   img [B,3,H,W] fp32; crop rectangle (top, left, crop_h, crop_w) per img_proc.py:126-132; out [B,3,out_h,out_w]
- *   (nhwc = 0) or [B,out_h,out_w,3] (nhwc = 1, what a channels_last cuDNN network reads); host_mean3 / host_std3: HOST float[3].
+ *   (nhwc = 0) or [B,out_h,out_w,3] (nhwc = 1, what a channels_last cuDNN network reads) or, nhwc = 2, the 2x2 space-to-depth fold
+ *   [B,out_h/2+3,out_w/2+3,16]: cell (I,J), channel (dy*2+dx)*3+c = pixel (2(I-2)+dy, 2(J-2)+dx) channel c, channels 12..15 and the border cells
+ *   (2 before, 1 after each axis) zero -- the input of the 4x4 stride-1 form of a 7x7 stride-2 pad-3 stem convolution (out_h, out_w even);
+ *   host_mean3 / host_std3: HOST float[3].
  *   bwd: dimg [B,3,H,W] = adjoint applied to dout (zero outside the crop, every element written). Supported resize factors: shrink <= 3x, enlarge <= 2x.
  * -------------------------------------------------------------------------------------------------------- */
 int spaa_clf_preprocess_fwd(const float* img, int64_t B, int H, int W, int top, int left, int crop_h, int crop_w, int out_h,

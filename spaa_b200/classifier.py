@@ -34,17 +34,19 @@ class _PreprocessFn(torch.autograd.Function):
     """Fused crop + area resize + normalise (ops.clf_preprocess) with its adjoint as the backward."""
 
     @staticmethod
-    def forward(ctx, im, crop, out_hw, channels_last):
-        ctx.crop, ctx.hw = crop, (im.shape[2], im.shape[3])
-        return ops.clf_preprocess(im, crop, out_hw, IMAGENET_MEAN, IMAGENET_STD, channels_last)
+    def forward(ctx, im, crop, out_hw, channels_last, s2d):
+        ctx.crop, ctx.hw, ctx.s2d = crop, (im.shape[2], im.shape[3]), s2d
+        return ops.clf_preprocess(im, crop, out_hw, IMAGENET_MEAN, IMAGENET_STD, channels_last, s2d)
 
     @staticmethod
     def backward(ctx, dout):
-        return ops.clf_preprocess_bwd(dout, ctx.hw, ctx.crop, IMAGENET_MEAN, IMAGENET_STD), None, None, None
+        return ops.clf_preprocess_bwd(dout, ctx.hw, ctx.crop, IMAGENET_MEAN, IMAGENET_STD, ctx.s2d), None, None, None, None
 
 
-def preprocess_fused(im, crop_sz, input_sz, channels_last: bool = False):
-    """`preprocess` as one kernel (+ one for the backward) for fp32 CUDA image batches [B,3,H,W]; other inputs use `preprocess`."""
+def preprocess_fused(im, crop_sz, input_sz, channels_last: bool = False, s2d: bool = False):
+    """`preprocess` as one kernel (+ one for the backward) for fp32 CUDA image batches [B,3,H,W]; other inputs use `preprocess`.
+    s2d: write the 2x2 space-to-depth fold an `S2DStem` reads ([B,16,h/2+3,w/2+3], channels_last) instead of the image; inputs the kernel
+    does not cover come back as the plain image (an S2DStem folds those itself)."""
     h, w = im.shape[-2:]
     th, tw = int(crop_sz[0]), int(crop_sz[1])
     ok = (torch.is_tensor(im) and im.is_cuda and im.dim() == 4 and im.shape[1] == 3 and im.dtype == torch.float32 and th <= h and tw <= w
@@ -53,7 +55,8 @@ def preprocess_fused(im, crop_sz, input_sz, channels_last: bool = False):
         x = preprocess(im, crop_sz, input_sz)
         return x.contiguous(memory_format=torch.channels_last) if channels_last else x
     top, left = int(round((h - th) / 2.0)), int(round((w - tw) / 2.0))          # img_proc.py:126-132
-    return _PreprocessFn.apply(im, (top, left, th, tw), (int(input_sz[0]), int(input_sz[1])), bool(channels_last))
+    s2d = bool(s2d) and input_sz[0] % 2 == 0 and input_sz[1] % 2 == 0
+    return _PreprocessFn.apply(im, (top, left, th, tw), (int(input_sz[0]), int(input_sz[1])), bool(channels_last), s2d)
 
 
 _NORM_CACHE = {}
@@ -129,7 +132,7 @@ def device_logits(classifier, im, crop_sz, channels_last: bool = False):
     cuDNN runs its NHWC tensor-core kernels without the per-layer NCHW<->NHWC transposes."""
     model, input_sz = getattr(classifier, "model", None), getattr(classifier, "input_sz", None)
     if model is not None and input_sz is not None:
-        x = preprocess_fused(im, crop_sz, input_sz, channels_last)
+        x = preprocess_fused(im, crop_sz, input_sz, channels_last, s2d=bool(channels_last and getattr(classifier, "stem_s2d", False)))
         out = model(x)
         return out.logits if hasattr(out, "logits") else out
     return classifier(im, crop_sz)[0]
@@ -233,6 +236,60 @@ class FusedBasicBlock(torch.nn.Module):
     def forward(self, x):
         out = self.cba1(x)
         return self.cba2(out, x if self.dconv is None else self.dconv(x))
+
+
+def s2d_fold(x):
+    """The 2x2 space-to-depth fold of layout 2 of spaa_clf_preprocess_fwd in torch ops: [B,3,H,W] (H, W even) -> [B,16,H/2+3,W/2+3]; channel
+    (dy*2 + dx)*3 + c of cell (I,J) = pixel (2(I-2)+dy, 2(J-2)+dx), channel c; 2 zero cells before, 1 after each axis; channels 12..15 zero."""
+    B, C, H, W = x.shape
+    lo, hi = ops.S2D_PAD_LO, ops.S2D_PAD_HI
+    xp = F.pad(x, (2 * lo, 2 * hi, 2 * lo, 2 * hi))
+    Hs, Ws = H // 2 + lo + hi, W // 2 + lo + hi
+    y = xp.reshape(B, C, Hs, 2, Ws, 2).permute(0, 3, 5, 1, 2, 4).reshape(B, 4 * C, Hs, Ws)
+    return F.pad(y, (0, 0, 0, 0, 0, ops.S2D_C - 4 * C))
+
+
+class S2DStem(torch.nn.Module):
+    """A frozen 7x7 stride-2 pad-3 convolution on 3 channels (torchvision ResNet `conv1`) as the 4x4 stride-1 pad-0 cuDNN convolution over the
+    space-to-depth fold of its input: tap k of the 7 is tap (K, d) = ((k + 1) // 2, (k + 1) % 2) of the fold, the 8th (k = -1) has weight 0.
+    Same products, still cuDNN -- but a shape with tensor-core NHWC kernels (B=32: 275 vs 532 us forward + input gradient).
+    forward() takes the folded input [B,16,h/2+3,w/2+3] (what the fused pre-processing kernel writes) or the plain image (folded here with torch
+    ops; odd sizes run the original convolution)."""
+
+    def __init__(self, conv: torch.nn.Conv2d):
+        super().__init__()
+        self.orig = conv
+        w = conv.weight.detach()
+        co = w.shape[0]
+        w8 = F.pad(w, (1, 0, 1, 0))                                            # taps k' = k + 1 in [0, 8), k' = 0 is the zero tap
+        w4 = w8.reshape(co, 3, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4).reshape(co, 12, 4, 4)      # [co, (dy, dx, c), Ky, Kx]
+        self.conv = torch.nn.Conv2d(ops.S2D_C, co, 4, 1, 0, bias=conv.bias is not None, device=w.device, dtype=w.dtype)
+        with torch.no_grad():
+            self.conv.weight.copy_(F.pad(w4, (0, 0, 0, 0, 0, ops.S2D_C - 12)))
+            if conv.bias is not None:
+                self.conv.bias.copy_(conv.bias)
+        for p in self.conv.parameters():
+            p.requires_grad = False
+
+    def forward(self, x):
+        if x.shape[1] == ops.S2D_C:
+            return self.conv(x)
+        if x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            return self.conv(s2d_fold(x))
+        return self.orig(x)
+
+
+def fuse_s2d_stem(model) -> int:
+    """In place: torchvision ResNet `conv1` (7x7, stride 2, pad 3, 3 input channels) -> S2DStem."""
+    from torchvision.models import resnet
+    n = 0
+    for mod in list(model.modules()):
+        c = mod._modules.get("conv1") if isinstance(mod, resnet.ResNet) else None
+        if (type(c) is torch.nn.Conv2d and c.in_channels == 3 and tuple(c.kernel_size) == (7, 7) and tuple(c.stride) == (2, 2) and c.padding == (3, 3)
+                and tuple(c.dilation) == (1, 1) and c.groups == 1 and c.padding_mode == "zeros"):
+            mod._modules["conv1"] = S2DStem(c)
+            n += 1
+    return n
 
 
 def _strip_bias(conv: torch.nn.Conv2d):
@@ -341,7 +398,7 @@ class _FoldedView:
         self.model, self.input_sz, self.name = model, input_sz, name
 
 
-def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Optional[bool] = None):
+def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Optional[bool] = None, fuse_stem: Optional[bool] = None):
     """A view of `classifier` whose network is a PRIVATE copy with every inference-mode BatchNorm2d folded into the cuDNN
     convolution in front of it (torch.nn.utils.fusion.fuse_conv_bn_eval: w' = w * gamma / sqrt(var + eps), b' likewise).
     The classifier is frozen and in eval() (classifier.py:38-42), so its BatchNorm layers are per-channel affine maps: the
@@ -351,6 +408,8 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Opti
     fuse_pool (default: $SPAA_FUSE_POOL, on): the copy's `ReLU -> MaxPool2d` pairs and lone MaxPool2d modules become
     FusedReLUMaxPool2d (fuse_relu_maxpool): exact max-pooling, one of our kernels each way instead of ATen's relu / max_pool2d /
     threshold_backward / max_pool2d_backward passes over the largest activation of the iteration.
+    fuse_stem (default: $SPAA_FUSE_STEM, on): a ResNet's 7x7 stride-2 stem convolution runs as the equivalent 4x4 stride-1 cuDNN convolution over
+    the space-to-depth fold of the input, which the fused pre-processing kernel writes directly (S2DStem).
     fuse_bias (default: $SPAA_FUSE_BIAS, on): the folded biases leave the cuDNN convolutions and are added, together with the residual and the
     ReLU, by one kernel per convolution (fuse_bias_act: ConvBiasAct / FusedBasicBlock) instead of ATen's two or three elementwise passes.
     The user's module is not modified.  Returns `classifier` itself when there is nothing to change (opaque callables,
@@ -362,6 +421,8 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Opti
         fuse_pool = os.environ.get("SPAA_FUSE_POOL", "1") != "0"
     if fuse_bias is None:
         fuse_bias = os.environ.get("SPAA_FUSE_BIAS", "1") != "0"
+    if fuse_stem is None:
+        fuse_stem = os.environ.get("SPAA_FUSE_STEM", "1") != "0"
     if not isinstance(model, torch.nn.Module) or input_sz is None or model.training:
         return classifier
     has_bn = any(isinstance(m, torch.nn.BatchNorm2d) for m in model.modules())
@@ -387,6 +448,8 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Opti
         n += fuse_bias_act(folded)
     if fuse_pool:
         n += fuse_relu_maxpool(folded)
+    n_stem = fuse_s2d_stem(folded) if fuse_stem else 0
+    n += n_stem
     if n == 0:
         return classifier
     for p in folded.parameters():
@@ -394,7 +457,9 @@ def fold_batchnorm(classifier, fuse_pool: Optional[bool] = None, fuse_bias: Opti
     if next(model.parameters()).is_contiguous(memory_format=torch.channels_last) or any(
             p.dim() == 4 and p.shape[1] > 1 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous() for p in model.parameters()):
         folded.to(memory_format=torch.channels_last)
-    return _FoldedView(folded.eval(), input_sz, getattr(classifier, "name", type(model).__name__))
+    view = _FoldedView(folded.eval(), input_sz, getattr(classifier, "name", type(model).__name__))
+    view.stem_s2d = n_stem > 0            # device_logits() then asks the pre-processing kernel for the folded input
+    return view
 
 
 def _applied_back_to_back(mod, conv_name: str, bn_name: str) -> bool:

@@ -17,14 +17,53 @@ struct PreP {
     int B, H, W;               // image planes [B,3,H,W]
     int top, left, ch, cw;     // crop rectangle
     int oh, ow;                // network input size
-    int nhwc;                  // 1: out / dout are [B,oh,ow,3]; 0: [B,3,oh,ow]
+    int nhwc;                  // 1: out / dout are [B,oh,ow,3]; 0: [B,3,oh,ow]; 2: space-to-depth [B,oh/2+3,ow/2+3,16] (see below)
     float mean[3], inv_std[3];
 };
+
+// Layout 2 (kS2D): the 2x2 space-to-depth fold of the network input, zero-padded by kS2DPadLo cells before and kS2DPadHi cells after each axis, 16
+// channels per cell: channel (dy*2 + dx)*3 + c = pixel (2*(I - kS2DPadLo) + dy, 2*(J - kS2DPadLo) + dx), channel c; channels 12..15 are zero.
+// A 7x7 stride-2 pad-3 convolution over the image is exactly a 4x4 stride-1 pad-0 convolution over this tensor (tap k of the 7 = tap 2K + d - 1 of
+// the fold; classifier.S2DStem re-arranges the frozen weights), a shape for which cuDNN has tensor-core NHWC kernels: 275 vs 532 us forward + input
+// gradient at B=32 (tools/stem_probe.py).
+constexpr int kS2D = 2, kS2DPadLo = 2, kS2DPadHi = 1, kS2DC = 16;
 
 // 32-bit arithmetic: fill() bounds every extent by 2^15, so o * n_in < 2^30 (64-bit integer division costs ~100 instructions and
 // the first version of the backward kernel executed ~40 of them per pixel: 99 us for 49 MB of traffic)
 SPAA_D int win_lo(int o, int n_in, int n_out) { return (int)(((unsigned)o * (unsigned)n_in) / (unsigned)n_out); }
 SPAA_D int win_hi(int o, int n_in, int n_out) { return (int)(((unsigned)(o + 1) * (unsigned)n_in + (unsigned)n_out - 1u) / (unsigned)n_out); }
+
+// one thread = one cell of the folded tensor (border cells included: they are written as zeros every call)
+__global__ void __launch_bounds__(kThreads) preprocess_fwd_s2d_kernel(const float* __restrict__ img, float4* __restrict__ out, const PreP p) {
+    const int64_t plane = (int64_t)p.H * p.W;
+    const int Hs = p.oh / 2 + kS2DPadLo + kS2DPadHi, Ws = p.ow / 2 + kS2DPadLo + kS2DPadHi;
+    const int b = blockIdx.y;
+    for (int rc = blockIdx.x * blockDim.x + threadIdx.x; rc < Hs * Ws; rc += gridDim.x * blockDim.x) {
+        const int I = rc / Ws, J = rc - I * Ws;
+        float v[kS2DC];
+#pragma unroll
+        for (int e = 0; e < kS2DC; ++e) v[e] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int oy = 2 * (I - kS2DPadLo) + (d >> 1), ox = 2 * (J - kS2DPadLo) + (d & 1);
+            if (oy < 0 || oy >= p.oh || ox < 0 || ox >= p.ow) continue;
+            const int y0 = win_lo(oy, p.ch, p.oh), y1 = win_hi(oy, p.ch, p.oh);
+            const int x0 = win_lo(ox, p.cw, p.ow), x1 = win_hi(ox, p.cw, p.ow);
+            const float inv_area = 1.f / (float)((y1 - y0) * (x1 - x0));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* src = img + ((int64_t)b * 3 + c) * plane + (int64_t)p.top * p.W + p.left;
+                float sum = 0.f;
+                for (int y = y0; y < y1; ++y)
+                    for (int x = x0; x < x1; ++x) sum += __ldg(src + (int64_t)y * p.W + x);
+                v[d * 3 + c] = (sum * inv_area - p.mean[c]) * p.inv_std[c];
+            }
+        }
+        float4* o = out + ((int64_t)b * Hs * Ws + rc) * (kS2DC / 4);
+#pragma unroll
+        for (int e = 0; e < kS2DC / 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+    }
+}
 
 __global__ void __launch_bounds__(kThreads) preprocess_fwd_kernel(const float* __restrict__ img, float* __restrict__ out, const PreP p) {
     const int64_t plane = (int64_t)p.H * p.W;
@@ -82,7 +121,11 @@ __global__ void __launch_bounds__(kThreads) preprocess_bwd_kernel(const float* _
                     const int x0 = xlo[ox], x1 = xhi[ox];
                     if (cx < x0 || cx >= x1) continue;
                     const float w = 1.f / (float)((y1 - y0) * (x1 - x0));
-                    if (p.nhwc) {
+                    if (p.nhwc == kS2D) {
+                        const int Ws = p.ow / 2 + kS2DPadLo + kS2DPadHi, Hs = p.oh / 2 + kS2DPadLo + kS2DPadHi;
+                        const float* d = dout + (((int64_t)b * Hs + (oy >> 1) + kS2DPadLo) * Ws + (ox >> 1) + kS2DPadLo) * kS2DC + ((oy & 1) * 2 + (ox & 1)) * 3;
+                        g[0] += w * __ldg(d); g[1] += w * __ldg(d + 1); g[2] += w * __ldg(d + 2);
+                    } else if (p.nhwc) {
                         const float* d = dout + (((int64_t)b * p.oh + oy) * p.ow + ox) * 3;
                         g[0] += w * __ldg(d); g[1] += w * __ldg(d + 1); g[2] += w * __ldg(d + 2);
                     } else {
@@ -101,6 +144,7 @@ int fill(PreP& p, int64_t B, int H, int W, int top, int left, int ch, int cw, in
     if (!(B > 0 && B < (1 << 24) && H > 0 && W > 0 && H < (1 << 15) && W < (1 << 15) && oh < (1 << 15) && ow < (1 << 15) && ch > 0 && cw > 0 && oh > 0 && ow > 0 && top >= 0 && left >= 0 && top + ch <= H && left + cw <= W && mean && stdv)) return 0;
     // the candidate search of the backward covers cells centre-1 .. centre+2: shrink by at most 3x, enlarge by at most 2x
     if (ch > 3 * oh || cw > 3 * ow || oh > 2 * ch || ow > 2 * cw) return 0;
+    if (nhwc < 0 || nhwc > kS2D || (nhwc == kS2D && ((oh | ow) & 1))) return 0;      // the fold needs even extents
     p.B = (int)B; p.H = H; p.W = W; p.top = top; p.left = left; p.ch = ch; p.cw = cw; p.oh = oh; p.ow = ow; p.nhwc = nhwc;
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean[c]; p.inv_std[c] = 1.f / stdv[c]; }
     return 1;
@@ -117,7 +161,14 @@ int spaa_clf_preprocess_fwd(const float* img, int64_t B, int H, int W, int top, 
     int64_t blocks = ((int64_t)out_h * out_w + kThreads - 1) / kThreads;
     if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
     SPAA_CHECK_ARG(B <= 65535, "spaa_clf_preprocess_fwd: batch too large");
-    preprocess_fwd_kernel<<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, (cudaStream_t)stream>>>(img, out, p);
+    if (nhwc == kS2D) {
+        SPAA_CHECK_ARG(((uintptr_t)out & 15) == 0, "spaa_clf_preprocess_fwd: misaligned output");
+        const int64_t cells = (int64_t)(out_h / 2 + kS2DPadLo + kS2DPadHi) * (out_w / 2 + kS2DPadLo + kS2DPadHi);
+        blocks = (cells + kThreads - 1) / kThreads;
+        if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+        preprocess_fwd_s2d_kernel<<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, (cudaStream_t)stream>>>(img, (float4*)out, p);
+    } else
+        preprocess_fwd_kernel<<<dim3((unsigned)blocks, (unsigned)B), kThreads, 0, (cudaStream_t)stream>>>(img, out, p);
     SPAA_CHECK_LAUNCH("spaa_clf_preprocess_fwd");
     return SPAA_OK;
 }

@@ -758,12 +758,22 @@ def _f3(v):
     return (ctypes.c_float * 3)(*[float(t) for t in v])
 
 
-def clf_preprocess(img: Tensor, crop, out_hw, mean, std, channels_last: bool) -> Tensor:
-    """Returns the network input as a logical [B,3,h,w] tensor (NCHW, or channels-last memory when `channels_last`)."""
+S2D_PAD_LO, S2D_PAD_HI, S2D_C = 2, 1, 16          # layout 2 of spaa_clf_preprocess_fwd (include/spaa_b200.h)
+
+
+def clf_preprocess(img: Tensor, crop, out_hw, mean, std, channels_last: bool, s2d: bool = False) -> Tensor:
+    """Returns the network input as a logical [B,3,h,w] tensor (NCHW, or channels-last memory when `channels_last`); with `s2d` the
+    2x2 space-to-depth fold a classifier.S2DStem reads: logical [B,16,h/2+3,w/2+3] in channels_last memory."""
     img = _f32c(img)
     B, C, H, W = img.shape
     assert C == 3
     top, left, ch, cw = crop
+    if s2d:
+        assert out_hw[0] % 2 == 0 and out_hw[1] % 2 == 0
+        pad = S2D_PAD_LO + S2D_PAD_HI
+        out = torch.empty((B, out_hw[0] // 2 + pad, out_hw[1] // 2 + pad, S2D_C), dtype=torch.float32, device=img.device)
+        lib().spaa_clf_preprocess_fwd(_p(img), B, H, W, top, left, ch, cw, out_hw[0], out_hw[1], _f3(mean), _f3(std), 2, _p(out), _stream()); _count()
+        return out.permute(0, 3, 1, 2)
     if channels_last:
         out = torch.empty((B, out_hw[0], out_hw[1], 3), dtype=torch.float32, device=img.device)
     else:
@@ -772,10 +782,22 @@ def clf_preprocess(img: Tensor, crop, out_hw, mean, std, channels_last: bool) ->
     return out.permute(0, 3, 1, 2) if channels_last else out
 
 
-def clf_preprocess_bwd(dout: Tensor, img_hw, crop, mean, std) -> Tensor:
-    """dout: logical [B,3,h,w], NCHW-contiguous or channels-last; returns d/d(img) [B,3,H,W] (zero outside the crop)."""
+def clf_preprocess_bwd(dout: Tensor, img_hw, crop, mean, std, s2d: bool = False) -> Tensor:
+    """dout: logical [B,3,h,w], NCHW-contiguous or channels-last (s2d: the gradient of the folded input, logical [B,16,h/2+3,w/2+3]); returns
+    d/d(img) [B,3,H,W] (zero outside the crop)."""
     if dout.dtype != torch.float32:
         dout = dout.float()
+    if s2d:
+        assert dout.shape[1] == S2D_C
+        if not _nhwc_dense(dout):
+            dout = dout.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        B = dout.shape[0]
+        pad = S2D_PAD_LO + S2D_PAD_HI
+        oh, ow = 2 * (dout.shape[2] - pad), 2 * (dout.shape[3] - pad)
+        top, left, ch, cw = crop
+        dimg = torch.empty((B, 3, img_hw[0], img_hw[1]), dtype=torch.float32, device=dout.device)
+        lib().spaa_clf_preprocess_bwd(_p(dout), B, img_hw[0], img_hw[1], top, left, ch, cw, oh, ow, _f3(std), 2, _p(dimg), _stream()); _count()
+        return dimg
     nhwc = dout.is_contiguous(memory_format=torch.channels_last) and not dout.is_contiguous()
     if not nhwc and not dout.is_contiguous():
         dout = dout.contiguous()

@@ -23,7 +23,7 @@ def test_fold_batchnorm_keeps_logits_gradients_and_the_users_module(name):
     before = copy.deepcopy(clf.model.state_dict())
     from spaa_b200.classifier import ConvBiasAct, FusedBasicBlock, FusedReLUMaxPool2d
     if name == "vgg16":                                   # no BatchNorm and no fusion asked for: nothing to change, the classifier itself comes back
-        assert fold_batchnorm(clf, fuse_pool=False, fuse_bias=False) is clf
+        assert fold_batchnorm(clf, fuse_pool=False, fuse_bias=False, fuse_stem=False) is clf
     view = fold_batchnorm(clf)
     assert view is not clf and view.input_sz == clf.input_sz
     assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in view.model.modules())
@@ -33,10 +33,13 @@ def test_fold_batchnorm_keeps_logits_gradients_and_the_users_module(name):
     assert [(m.kernel_size, m.stride, m.padding, m.with_relu) for m in fused] == {
         "resnet18": [(3, 2, 1, True)], "vgg16": [(2, 2, 0, True)] * 5, "inception_v3": [(3, 2, 0, False)] * 2}[name]
     assert any(type(m) is torch.nn.MaxPool2d for m in clf.model.modules())
+    from spaa_b200.classifier import S2DStem
+    assert getattr(view, "stem_s2d", False) == (name == "resnet18") and (type(getattr(view.model, "conv1", None)) is S2DStem) == (name == "resnet18")
     # every cuDNN convolution of the copy lost its bias to the fused kernel behind it (pooling kernel or ConvBiasAct)
     kinds = [type(m) for m in view.model.modules()]
     assert (kinds.count(FusedBasicBlock), kinds.count(ConvBiasAct)) == {"resnet18": (8, 16), "vgg16": (0, 8), "inception_v3": (0, 96)}[name]
     assert not any(type(m) is torch.nn.Conv2d and m.bias is not None for m in view.model.modules())
+    assert fold_batchnorm(clf, fuse_pool=False, fuse_bias=False, fuse_stem=False) is not view
     assert all(fm.bias is not None for fm in fused) == (name != "inception_v3")
     for k, v in clf.model.state_dict().items():           # the user's network is untouched
         assert torch.equal(v, before[k])
@@ -78,3 +81,26 @@ def test_fold_batchnorm_leaves_opaque_and_training_classifiers_alone():
 
     t = Training()
     assert fold_batchnorm(t) is t
+
+
+@pytest.mark.parametrize("hw", [(16, 20), (15, 17), (224, 224)])
+def test_s2d_stem_equals_the_7x7_stride_2_convolution(hw):
+    """The re-parameterised stem (4x4 stride-1 convolution over the 2x2 space-to-depth fold) against the convolution it replaces: values and
+    input gradient, even sizes (folded) and odd sizes (the original convolution runs)."""
+    from spaa_b200.classifier import S2DStem, s2d_fold
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(3, 8, 7, 2, 3)
+    stem = S2DStem(conv)
+    x = torch.randn(2, 3, *hw)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = conv(xa), stem(xb)
+    assert ya.shape == yb.shape and (ya - yb).abs().max().item() <= 1e-5
+    cot = torch.randn_like(ya)
+    ya.backward(cot); yb.backward(cot)
+    assert (xa.grad - xb.grad).abs().max().item() <= 1e-5
+    if hw[0] % 2 == 0 and hw[1] % 2 == 0:
+        f = s2d_fold(x)
+        assert f.shape == (2, 16, hw[0] // 2 + 3, hw[1] // 2 + 3)
+        assert torch.equal(f[:, 12:], torch.zeros_like(f[:, 12:])) and torch.equal(f[:, :, :2], torch.zeros_like(f[:, :, :2]))
+        assert torch.equal(f[:, 0:3, 2, 2], x[:, :, 0, 0]) and torch.equal(f[:, 9:12, 2, 2], x[:, :, 1, 1]) and torch.equal(f[:, 3:6, 3, 2], x[:, :, 2, 1])
+        assert (stem(f) - ya.detach()).abs().max().item() <= 1e-5

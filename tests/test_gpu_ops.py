@@ -517,7 +517,8 @@ def test_private_classifier_copy_pool_fusion_on_gpu(name):
     clf = Classifier(name, dev(), [0])
     clf.model.to(memory_format=torch.channels_last)       # (use_channels_last() declines in the exact-fp32 test configuration; the layout is what matters here)
     cl = True
-    plain, fused = fold_batchnorm(clf, fuse_pool=False, fuse_bias=False), fold_batchnorm(clf, fuse_pool=True, fuse_bias=True)
+    plain, fused = fold_batchnorm(clf, fuse_pool=False, fuse_bias=False, fuse_stem=False), fold_batchnorm(clf, fuse_pool=True, fuse_bias=True, fuse_stem=True)
+    assert getattr(fused, "stem_s2d", False) == (name == "resnet18")
     assert any(isinstance(m, FusedReLUMaxPool2d) for m in fused.model.modules())
     assert not any(isinstance(m, FusedReLUMaxPool2d) for m in getattr(plain, "model").modules())
     x = torch.rand(4, 3, 240, 320, generator=torch.Generator().manual_seed(5)).to(dev())
@@ -538,3 +539,28 @@ def test_private_classifier_copy_pool_fusion_on_gpu(name):
     assert torch.equal(outs[0].argmax(1), outs[1].argmax(1))
     rel = ((grads[0] - grads[1]).double().norm() / grads[0].double().norm()).item()
     assert rel <= 1e-4, rel
+
+
+@pytest.mark.parametrize("hw,crop,insz", [((240, 320), (240, 240), (224, 224)), ((200, 260), (180, 200), (96, 128))])
+def test_fused_preprocess_space_to_depth_layout(hw, crop, insz):
+    """Layout 2 of the pre-processing kernel = the torch fold (classifier.s2d_fold) of its plain output, bit for bit; the adjoint through the
+    folded layout equals the adjoint through the plain one; an S2DStem fed either way equals the 7x7 stride-2 convolution it stands for."""
+    from spaa_b200.classifier import S2DStem, preprocess_fused, s2d_fold
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(3, 3, *hw, generator=g).to(dev())
+    x1, x2 = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    plain = preprocess_fused(x1, crop, insz, True)
+    folded = preprocess_fused(x2, crop, insz, True, s2d=True)
+    assert folded.shape == (3, 16, insz[0] // 2 + 3, insz[1] // 2 + 3) and folded.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(folded.detach(), s2d_fold(plain.detach()))
+    cot = torch.randn(folded.shape, generator=g).to(dev())
+    folded.backward(cot)
+    s2d_fold(plain).backward(cot)
+    close(x2.grad, x1.grad, 1e-6, 1e-6, "adjoint through the folded layout")
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3).to(dev())
+    stem = S2DStem(conv).to(dev())
+    with torch.no_grad():
+        ref = conv(plain.detach())
+        close(stem(folded.detach()), ref, 2e-5, 1e-5, "S2DStem on the kernel's folded input")
+        close(stem(plain.detach()), ref, 2e-5, 1e-5, "S2DStem folding a plain input itself")

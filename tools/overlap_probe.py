@@ -98,23 +98,25 @@ def run(name, make):
     return prj.clone()
 
 
-def with_env(fuse_pool, fuse_bias, make):
+def with_env(fuse_pool, fuse_bias, fuse_stem, make):
     def f():
         os.environ["SPAA_FUSE_POOL"] = "1" if fuse_pool else "0"          # read when the engine builds its private classifier copy
         os.environ["SPAA_FUSE_BIAS"] = "1" if fuse_bias else "0"
+        os.environ["SPAA_FUSE_STEM"] = "1" if fuse_stem else "0"
         return make()
     return f
 
 
-cfgs = [("stock glue", with_env(False, False, lambda: SpaaAttack(*args, overlap=False))),
-        ("fused pools", with_env(True, False, lambda: SpaaAttack(*args, overlap=False))),
-        ("fused pools + bias/act", with_env(True, True, lambda: SpaaAttack(*args, overlap=False)))]
+cfgs = [("stock glue", with_env(False, False, False, lambda: SpaaAttack(*args, overlap=False))),
+        ("fused pools", with_env(True, False, False, lambda: SpaaAttack(*args, overlap=False))),
+        ("fused pools + bias/act", with_env(True, True, False, lambda: SpaaAttack(*args, overlap=False))),
+        ("... + space-to-depth stem", with_env(True, True, True, lambda: SpaaAttack(*args, overlap=False)))]
 if os.environ.get("SCHEDULES", "0") != "0":
-    cfgs += [("fused + overlap", with_env(True, True, lambda: SpaaAttack(*args, overlap=True))),
-             ("pipe2", with_env(True, True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=False))),
-             ("pipe2 + overlap", with_env(True, True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=True))),
-             ("pipe4 + overlap", with_env(True, True, lambda: SpaaAttackPipelined(*args, pipeline=4, overlap=True)))]
-cfgs += [("stock glue (again)", with_env(False, False, lambda: SpaaAttack(*args, overlap=False)))]
+    cfgs += [("fused + overlap", with_env(True, True, True, lambda: SpaaAttack(*args, overlap=True))),
+             ("pipe2", with_env(True, True, True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=False))),
+             ("pipe2 + overlap", with_env(True, True, True, lambda: SpaaAttackPipelined(*args, pipeline=2, overlap=True))),
+             ("pipe4 + overlap", with_env(True, True, True, lambda: SpaaAttackPipelined(*args, pipeline=4, overlap=True)))]
+cfgs += [("stock glue (again)", with_env(False, False, False, lambda: SpaaAttack(*args, overlap=False)))]
 ref = None
 for name, make in cfgs:
     try:
