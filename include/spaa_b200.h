@@ -28,7 +28,9 @@ int spaa_abi_version(void);
  * (hpf_diff, dhpf_diff, ahpf_diff, ciede2000_diff) and their autograd graphs.
  * Tensors are [B,3,HW] planar fp32.  *_bstride = elements between consecutive batch items (0 = broadcast).
  * -------------------------------------------------------------------------------------------------------- */
-int spaa_rgb2lab_fwd(const float* rgb, float* lab, int64_t B, int64_t HW, spaa_stream_t stream);
+/* fast != 0: the hardware-approximation arithmetic of spaa_color_loss_fwd_bwd(fast = 1) -- a reference Lab image for that mode must be
+ * computed with it, so that a pixel equal to its reference keeps dE = 0 exactly. */
+int spaa_rgb2lab_fwd(const float* rgb, float* lab, int64_t B, int64_t HW, int fast, spaa_stream_t stream);
 int spaa_rgb2lab_bwd(const float* rgb, const float* dlab, float* drgb, int64_t B, int64_t HW, spaa_stream_t stream);
 int spaa_de2000_fwd(const float* lab1, int64_t lab1_bstride, const float* lab2, int64_t lab2_bstride, float* de,
                     int64_t B, int64_t HW, spaa_stream_t stream);
@@ -44,11 +46,15 @@ int spaa_de2000_bwd(const float* lab1, int64_t lab1_bstride, const float* lab2, 
  *   stats      [B,4] out: sum_p dE, sum_p ||cam-ref||_2, sum_p dE^2, 0        (sums over pixels, not means)
  *   grad       [B,3,HW] out or NULL: c_de * d(sum_p w_p dE_p)/dcam + c_l2 * d(sum_p ||.||_2)/dcam,
  *              with w_p = 1 (de_weighting 0) or w_p = dE_p (de_weighting 1: gradient of 0.5*sum dE^2)
+ *   fast       0: IEEE division / square root and accurate powf, cbrtf, sincosf, expf (the arithmetic held to 1e-5 against the reference);
+ *              1: hardware approximations (relative error ~1e-6) for the 16-bit tensor-core modes, whose camera image already carries
+ *              ~3e-4 of rounding: the kernel is bound by instruction issue and executes ~40 % fewer instructions (measured +1.3 % it/s);
+ *              ref_lab must then come from spaa_rgb2lab_fwd(fast = 1)
  *   ws         workspace of spaa_color_loss_ws_bytes(B,HW) bytes, zero-initialised once by the caller
  */
 int64_t spaa_color_loss_ws_bytes(int64_t B, int64_t HW);
 int spaa_color_loss_fwd_bwd(const float* cam, const float* ref_rgb, const float* ref_lab, int64_t ref_bstride,
-                            int64_t B, int64_t HW, int cam_is_lab2, int de_weighting, float c_de, float c_l2,
+                            int64_t B, int64_t HW, int cam_is_lab2, int de_weighting, float c_de, float c_l2, int fast,
                             float* stats, float* grad, void* ws, spaa_stream_t stream);
 
 /* ----------------------------------------------------------------------------------------------------------

@@ -10,13 +10,17 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Fast: the arithmetic of color_loss_kernel<., true> (the SAME operation sequence: a pixel equal to its reference gets bit-identical Lab values,
+// hence dE = 0 and a zero gradient, as with the exact arithmetic).
+template <bool Fast>
 __global__ void __launch_bounds__(kThreads) lab_fwd_kernel(const float* __restrict__ rgb, float* __restrict__ lab, int64_t B, int64_t HW) {
     const int64_t total = B * HW;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = i / HW, p = i - b * HW;
         const float* s = rgb + b * 3 * HW + p;
         float L, A, Bv;
-        color::rgb_to_lab<float>(__ldg(s), __ldg(s + HW), __ldg(s + 2 * HW), L, A, Bv);
+        if (Fast) { color::LabJac<float> J; color::rgb_to_lab_jac<float, true>(__ldg(s), __ldg(s + HW), __ldg(s + 2 * HW), L, A, Bv, J); }
+        else color::rgb_to_lab<float>(__ldg(s), __ldg(s + HW), __ldg(s + 2 * HW), L, A, Bv);
         float* d = lab + b * 3 * HW + p;
         d[0] = L; d[HW] = A; d[2 * HW] = Bv;
     }
@@ -70,7 +74,8 @@ __host__ __device__ inline int color_nblk(int64_t HW) {
 
 // Fused: Lab(cam) -> dE vs ref_lab, channel-L2 vs ref_rgb, per-sample sums, gradient wrt cam.
 // grid = (nblk, B).  Deterministic: per-block partials, last block of each sample adds them in fixed order.
-template <bool WithGrad>
+// Fast: MUFU-approximation arithmetic (color_math.cuh, M<float, true>) for the 16-bit tensor-core modes.
+template <bool WithGrad, bool Fast>
 __global__ void __launch_bounds__(kThreads) color_loss_kernel(const float* __restrict__ cam, const float* __restrict__ ref_rgb,
                                                               const float* __restrict__ ref_lab, int64_t ref_bs, int64_t HW, int cam_is_lab2,
                                                               int de_weighting, float c_de, float c_l2, float* __restrict__ stats,
@@ -88,20 +93,20 @@ __global__ void __launch_bounds__(kThreads) color_loss_kernel(const float* __res
         const float L0 = __ldg(rl + p), A0 = __ldg(rl + HW + p), B0 = __ldg(rl + 2 * HW + p);
         float L, A, Bv;
         color::LabJac<float> J;
-        if (WithGrad) color::rgb_to_lab_jac<float>(r, g, bl, L, A, Bv, J);
+        if (WithGrad) color::rgb_to_lab_jac<float, Fast>(r, g, bl, L, A, Bv, J);
         else color::rgb_to_lab<float>(r, g, bl, L, A, Bv);
         float gc[3], gr[3];
         float de;
-        if (cam_is_lab2) de = color::de2000<float, WithGrad>(L0, A0, B0, L, A, Bv, gr, gc);
-        else de = color::de2000<float, WithGrad>(L, A, Bv, L0, A0, B0, gc, gr);
+        if (cam_is_lab2) de = color::de2000<float, WithGrad, Fast>(L0, A0, B0, L, A, Bv, gr, gc);
+        else de = color::de2000<float, WithGrad, Fast>(L, A, Bv, L0, A0, B0, gc, gr);
         const float dr = r - __ldg(rr + p), dg = g - __ldg(rr + HW + p), db = bl - __ldg(rr + 2 * HW + p);
-        const float nrm = sqrtf(dr * dr + dg * dg + db * db);
+        const float nrm = color::M<float, Fast>::sqrt_(dr * dr + dg * dg + db * db);
         s_de += de; s_l2 += nrm; s_de2 += de * de;
         if (WithGrad) {
             const float w = c_de * (de_weighting ? de : 1.f);
             float gr_, gg_, gb_;
             color::lab_jac_bwd<float>(J, w * gc[0], w * gc[1], w * gc[2], gr_, gg_, gb_);
-            const float inv = nrm > 0.f ? c_l2 / nrm : 0.f;   // torch.norm sub-gradient 0 at 0
+            const float inv = nrm > 0.f ? color::M<float, Fast>::div(c_l2, nrm) : 0.f;   // torch.norm sub-gradient 0 at 0
             gb[p] = gr_ + inv * dr;
             gb[HW + p] = gg_ + inv * dg;
             gb[2 * HW + p] = gb_ + inv * db;
@@ -141,9 +146,10 @@ inline int grid_for(int64_t total) {
 
 extern "C" {
 
-int spaa_rgb2lab_fwd(const float* rgb, float* lab, int64_t B, int64_t HW, spaa_stream_t stream) {
+int spaa_rgb2lab_fwd(const float* rgb, float* lab, int64_t B, int64_t HW, int fast, spaa_stream_t stream) {
     SPAA_CHECK_ARG(rgb && lab && B > 0 && HW > 0, "spaa_rgb2lab_fwd: bad arguments");
-    lab_fwd_kernel<<<grid_for(B * HW), kThreads, 0, (cudaStream_t)stream>>>(rgb, lab, B, HW);
+    if (fast) lab_fwd_kernel<true><<<grid_for(B * HW), kThreads, 0, (cudaStream_t)stream>>>(rgb, lab, B, HW);
+    else lab_fwd_kernel<false><<<grid_for(B * HW), kThreads, 0, (cudaStream_t)stream>>>(rgb, lab, B, HW);
     SPAA_CHECK_LAUNCH("spaa_rgb2lab_fwd");
     return SPAA_OK;
 }
@@ -173,19 +179,22 @@ int spaa_de2000_bwd(const float* lab1, int64_t bs1, const float* lab2, int64_t b
 int64_t spaa_color_loss_ws_bytes(int64_t B, int64_t HW) { return B * (int64_t)color_nblk(HW) * 4 * sizeof(float) + B * sizeof(unsigned); }
 
 int spaa_color_loss_fwd_bwd(const float* cam, const float* ref_rgb, const float* ref_lab, int64_t ref_bstride, int64_t B, int64_t HW,
-                            int cam_is_lab2, int de_weighting, float c_de, float c_l2, float* stats, float* grad, void* ws,
+                            int cam_is_lab2, int de_weighting, float c_de, float c_l2, int fast, float* stats, float* grad, void* ws,
                             spaa_stream_t stream) {
     SPAA_CHECK_ARG(cam && ref_rgb && ref_lab && stats && ws && B > 0 && B < 65536 && HW > 0, "spaa_color_loss_fwd_bwd: bad arguments");
     const int nblk = color_nblk(HW);
     float* partial = (float*)ws;
     unsigned* counter = (unsigned*)(partial + B * nblk * 4);
     dim3 grid(nblk, (unsigned)B);
-    if (grad)
-        color_loss_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cam, ref_rgb, ref_lab, ref_bstride, HW, cam_is_lab2, de_weighting,
-                                                                             c_de, c_l2, stats, grad, partial, counter);
+    if (grad && fast)
+        color_loss_kernel<true, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cam, ref_rgb, ref_lab, ref_bstride, HW, cam_is_lab2, de_weighting,
+                                                                                   c_de, c_l2, stats, grad, partial, counter);
+    else if (grad)
+        color_loss_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cam, ref_rgb, ref_lab, ref_bstride, HW, cam_is_lab2, de_weighting,
+                                                                                    c_de, c_l2, stats, grad, partial, counter);
     else
-        color_loss_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cam, ref_rgb, ref_lab, ref_bstride, HW, cam_is_lab2, de_weighting,
-                                                                              c_de, c_l2, stats, nullptr, partial, counter);
+        color_loss_kernel<false, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cam, ref_rgb, ref_lab, ref_bstride, HW, cam_is_lab2, de_weighting,
+                                                                                     c_de, c_l2, stats, nullptr, partial, counter);
     SPAA_CHECK_LAUNCH("spaa_color_loss_fwd_bwd");
     return SPAA_OK;
 }

@@ -49,12 +49,88 @@ template <typename R> SPAA_HD void rsincos(R x, R& sn, R& cs) {
 #endif
 }
 
+// Math policy.  F = false: IEEE division / square root and the accurate powf / cbrtf / sincosf / expf -- the 1e-5 parity arithmetic.
+// F = true (device, float only; chosen by the 16-bit tensor-core modes, whose PCNet output already carries ~3e-4 of rounding): MUFU-based
+// approximations (relative error ~1e-6): ~1 200 -> ~500 instructions per pixel for the fused loss, which is bound by instruction issue.
+template <typename R, bool F> struct M {
+    static SPAA_HD R div(R a, R b) { return a / b; }
+    static SPAA_HD R sqrt_(R x) { return sqrt(x); }
+    static SPAA_HD R pow24(R y) { return rpow(y, R(2.4)); }
+    static SPAA_HD R cbrt_(R x) { return rcbrt(x); }
+    static SPAA_HD R exp_(R x) { return exp(x); }
+    static SPAA_HD void sincos_(R x, R& sn, R& cs) { rsincos(x, sn, cs); }
+    static SPAA_HD R cos_(R x) { return cos(x); }
+    static SPAA_HD R sin_(R x) { return sin(x); }
+};
+#if defined(__CUDACC__)
+template <> struct M<float, true> {
+    static SPAA_HD float div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fdividef(a, b);
+#else
+        return a / b;
+#endif
+    }
+    static SPAA_HD float sqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+        float r;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+#else
+        return sqrtf(x);
+#endif
+    }
+    static SPAA_HD float pow24(float y) {
+#if defined(__CUDA_ARCH__)
+        return __powf(y, 2.4f);
+#else
+        return powf(y, 2.4f);
+#endif
+    }
+    static SPAA_HD float cbrt_(float x) {          // x > 0.008856 here
+#if defined(__CUDA_ARCH__)
+        return exp2f(__log2f(x) * (1.0f / 3.0f));
+#else
+        return cbrtf(x);
+#endif
+    }
+    static SPAA_HD float exp_(float x) {
+#if defined(__CUDA_ARCH__)
+        return __expf(x);
+#else
+        return expf(x);
+#endif
+    }
+    static SPAA_HD void sincos_(float x, float& sn, float& cs) {
+#if defined(__CUDA_ARCH__)
+        __sincosf(x, &sn, &cs);
+#else
+        sn = sinf(x); cs = cosf(x);
+#endif
+    }
+    static SPAA_HD float cos_(float x) {
+#if defined(__CUDA_ARCH__)
+        return __cosf(x);
+#else
+        return cosf(x);
+#endif
+    }
+    static SPAA_HD float sin_(float x) {
+#if defined(__CUDA_ARCH__)
+        return __sinf(x);
+#else
+        return sinf(x);
+#endif
+    }
+};
+#endif
+
 // ---- sRGB channel -> 100 * linear, value and derivative  (differential_color_functions.py:16-20) -------
 // y^1.4 of the derivative is y^2.4 / y: one powf serves both.
-template <typename R> SPAA_HD void srgb_lin100_vg(R c, R& v, R& g) {
+template <typename R, bool F = false> SPAA_HD void srgb_lin100_vg(R c, R& v, R& g) {
     if (c > R(0.0405)) {
-        const R y = (c + R(0.055)) / R(1.055);
-        const R p = rpow(y, R(2.4));
+        const R y = F ? (c + R(0.055)) * R(1.0 / 1.055) : (c + R(0.055)) / R(1.055);
+        const R p = M<R, F>::pow24(y);
         v = R(100) * p;
         g = R(100.0 * 2.4 / 1.055) * fdiv(p, y);
     } else {
@@ -67,9 +143,9 @@ template <typename R> SPAA_HD R srgb_lin100(R c) {
 }
 
 // ---- Lab f()  (:27-36), value and derivative: exact zero -> 0 with zero slope -------------------------
-template <typename R> SPAA_HD void lab_f_vg(R t, R& f, R& g) {
+template <typename R, bool F = false> SPAA_HD void lab_f_vg(R t, R& f, R& g) {
     if (t == R(0)) { f = R(0); g = R(0); return; }
-    if (t > R(0.008856)) { f = rcbrt(t); g = fdiv(R(1.0 / 3.0), f * f); }      // d t^(1/3) = t^(-2/3) / 3
+    if (t > R(0.008856)) { f = M<R, F>::cbrt_(t); g = fdiv(R(1.0 / 3.0), f * f); }      // d t^(1/3) = t^(-2/3) / 3
     else { f = R(7.787) * t + R(16.0 / 116.0); g = R(7.787); }
 }
 template <typename R> SPAA_HD R lab_f(R t) {
@@ -95,14 +171,18 @@ template <typename R> SPAA_HD void rgb_to_lab(R r, R g, R b, R& L, R& A, R& B) {
 
 // Forward that keeps the six local derivatives the reverse pass needs (no transcendental is evaluated twice).
 template <typename R> struct LabJac { R gr, gg, gb, jx, jy, jz; };     // d lin/d c per channel; f'(t)/white per axis
-template <typename R> SPAA_HD void rgb_to_lab_jac(R r, R g, R b, R& L, R& A, R& B, LabJac<R>& J) {
+template <typename R, bool F = false> SPAA_HD void rgb_to_lab_jac(R r, R g, R b, R& L, R& A, R& B, LabJac<R>& J) {
     R lr, lg, lb;
-    srgb_lin100_vg(r, lr, J.gr); srgb_lin100_vg(g, lg, J.gg); srgb_lin100_vg(b, lb, J.gb);
+    srgb_lin100_vg<R, F>(r, lr, J.gr); srgb_lin100_vg<R, F>(g, lg, J.gg); srgb_lin100_vg<R, F>(b, lb, J.gb);
     const R X = R(0.4124) * lr + R(0.3576) * lg + R(0.1805) * lb;
     const R Y = R(0.2126) * lr + R(0.7152) * lg + R(0.0722) * lb;
     const R Z = R(0.0193) * lr + R(0.1192) * lg + R(0.9504) * lb;
     R fx, fy, fz;
-    lab_f_vg(X / White<R>::xn, fx, J.jx); lab_f_vg(Y / White<R>::yn, fy, J.jy); lab_f_vg(Z / White<R>::zn, fz, J.jz);
+    if (F) {
+        lab_f_vg<R, F>(X * R(1.0 / 95.0489), fx, J.jx); lab_f_vg<R, F>(Y * R(1.0 / 100.0), fy, J.jy); lab_f_vg<R, F>(Z * R(1.0 / 108.8840), fz, J.jz);
+    } else {
+        lab_f_vg(X / White<R>::xn, fx, J.jx); lab_f_vg(Y / White<R>::yn, fy, J.jy); lab_f_vg(Z / White<R>::zn, fz, J.jz);
+    }
     J.jx = J.jx * R(1.0 / 95.0489); J.jy = J.jy * R(1.0 / 100.0); J.jz = J.jz * R(1.0 / 108.8840);
     L = R(116) * fy - R(16);
     A = R(500) * (fx - fy);
@@ -133,24 +213,24 @@ template <typename R> SPAA_HD R hue_deg(R y, R x) {
 
 // ---- ciede2000_diff (:109-180), forward; optionally reverse mode -------------------------------------
 // g1[3], g2[3] receive d(dE)/d(L1,A1,B1) and d(dE)/d(L2,A2,B2) (multiply by the cotangent outside).
-template <typename R, bool WithGrad>
+template <typename R, bool WithGrad, bool F = false>
 SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     const R P25_7 = R(6103515625.0);  // 25^7
     const bool n1 = (A1 == R(0)) && (B1 == R(0));
     const bool n2 = (A2 == R(0)) && (B2 == R(0));
     if (n1) B1 += R(0.0001);
     if (n2) B2 += R(0.0001);
-    const R C1 = sqrt(A1 * A1 + B1 * B1);
-    const R C2 = sqrt(A2 * A2 + B2 * B2);
+    const R C1 = M<R, F>::sqrt_(A1 * A1 + B1 * B1);
+    const R C2 = M<R, F>::sqrt_(A2 * A2 + B2 * B2);
     const R cbar = (C1 + C2) * R(0.5);
     R c6, c7;
     pow67(cbar, c6, c7);
-    const R u = c7 / (c7 + P25_7);
-    const R su = sqrt(u);
+    const R u = M<R, F>::div(c7, c7 + P25_7);
+    const R su = M<R, F>::sqrt_(u);
     const R G = R(0.5) * (R(1) - su);
     const R a1p = (R(1) + G) * A1, a2p = (R(1) + G) * A2;
-    const R c1p = sqrt(a1p * a1p + B1 * B1);
-    const R c2p = sqrt(a2p * a2p + B2 * B2);
+    const R c1p = M<R, F>::sqrt_(a1p * a1p + B1 * B1);
+    const R c2p = M<R, F>::sqrt_(a2p * a2p + B2 * B2);
     const R h1p = n1 ? R(0) : hue_deg(B1, a1p);
     const R h2p = n2 ? R(0) : hue_deg(B2, a2p);
     const bool nz = (C1 * C2) != R(0);
@@ -160,10 +240,10 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     const R dh = h2p - h1p;
     R dhp = R(0);
     if (nz) dhp = (fabs(dh) <= R(180)) ? dh : (dh > R(180) ? dh - R(360) : dh + R(360));
-    const R sq12 = sqrt(c1p * c2p);
+    const R sq12 = M<R, F>::sqrt_(c1p * c2p);
     const R half_ang = K<R>::rad * dhp * R(0.5);
     R sn, cs_half;
-    rsincos(half_ang, sn, cs_half);
+    M<R, F>::sincos_(half_ang, sn, cs_half);
     const R dHp = on ? R(2) * sq12 * sn : R(0);
     const R Lbar = (L1 + L2) * R(0.5);
     const R cpbar = (c1p + c2p) * R(0.5);
@@ -177,30 +257,30 @@ SPAA_HD R de2000(R L1, R A1, R B1, R L2, R A2, R B2, R* g1, R* g2) {
     const R ang1 = K<R>::rad * (hbar - R(39)), ang2 = K<R>::rad * (R(2) * hbar);
     const R ang3 = K<R>::rad * (R(3) * hbar + R(6)), ang4 = K<R>::rad * (R(4) * hbar - R(63));
     R s1, k1, s2, k2, s3, k3, s4, k4;
-    if (WithGrad) { rsincos(ang1, s1, k1); rsincos(ang2, s2, k2); rsincos(ang3, s3, k3); rsincos(ang4, s4, k4); }
-    else { k1 = cos(ang1); k2 = cos(ang2); k3 = cos(ang3); k4 = cos(ang4); s1 = s2 = s3 = s4 = R(0); }
+    if (WithGrad) { M<R, F>::sincos_(ang1, s1, k1); M<R, F>::sincos_(ang2, s2, k2); M<R, F>::sincos_(ang3, s3, k3); M<R, F>::sincos_(ang4, s4, k4); }
+    else { k1 = M<R, F>::cos_(ang1); k2 = M<R, F>::cos_(ang2); k3 = M<R, F>::cos_(ang3); k4 = M<R, F>::cos_(ang4); s1 = s2 = s3 = s4 = R(0); }
     const R T = R(1) - R(0.17) * k1 + R(0.24) * k2 + R(0.32) * k3 - R(0.2) * k4;
     const R hq = (hbar - R(275)) / R(25);
-    const R ex = exp(-(hq * hq));
+    const R ex = M<R, F>::exp_(-(hq * hq));
     const R dtheta = R(30) * ex;
     R cp6, cp7;
     pow67(cpbar, cp6, cp7);
-    const R v = cp7 / (cp7 + P25_7);
-    const R rC = sqrt(v);
+    const R v = M<R, F>::div(cp7, cp7 + P25_7);
+    const R rC = M<R, F>::sqrt_(v);
     const R Lm = Lbar - R(50);
     const R q = Lm * Lm;
-    const R sq20 = sqrt(R(20) + q);
-    const R sL = R(1) + (R(0.015) * q) / sq20;
+    const R sq20 = M<R, F>::sqrt_(R(20) + q);
+    const R sL = R(1) + M<R, F>::div(R(0.015) * q, sq20);
     const R sC = R(1) + R(0.045) * cpbar;
     const R sH = R(1) + R(0.015) * cpbar * T;
     const R ang5 = K<R>::rad * (R(2) * dtheta);
     R s5, k5;
-    if (WithGrad) rsincos(ang5, s5, k5); else { s5 = sin(ang5); k5 = R(0); }
+    if (WithGrad) M<R, F>::sincos_(ang5, s5, k5); else { s5 = M<R, F>::sin_(ang5); k5 = R(0); }
     const R rT = R(-2) * rC * s5;
-    const R tl = dLp / sL, tc = dCp / sC, th = dHp / sH;
+    const R tl = M<R, F>::div(dLp, sL), tc = M<R, F>::div(dCp, sC), th = M<R, F>::div(dHp, sH);
     const R sq = on ? (tl * tl + tc * tc + th * th + rT * tc * th) : (tl * tl);
     const bool pos = sq > R(0);
-    const R res = pos ? sqrt(sq) : R(0);
+    const R res = pos ? M<R, F>::sqrt_(sq) : R(0);
     if (!WithGrad) return res;
 
     // ------------------------------- reverse mode ---------------------------------------------------

@@ -125,12 +125,12 @@ def workspace(tag: str, nbytes: int, device) -> Tensor:
 # colour
 # ------------------------------------------------------------------------------------------------------------
 
-def rgb2lab(rgb: Tensor) -> Tensor:
+def rgb2lab(rgb: Tensor, fast: bool = False) -> Tensor:
     rgb = _f32c(rgb)
     B, C, H, W = rgb.shape
     assert C == 3
     lab = torch.empty_like(rgb)
-    lib().spaa_rgb2lab_fwd(_p(rgb), _p(lab), B, H * W, _stream()); _count()
+    lib().spaa_rgb2lab_fwd(_p(rgb), _p(lab), B, H * W, int(bool(fast)), _stream()); _count()
     return lab
 
 
@@ -175,8 +175,9 @@ def de2000_bwd(lab1: Tensor, lab2: Tensor, cot: Tensor, need1: bool = True, need
 
 
 def color_loss(cam: Tensor, ref_rgb: Tensor, ref_lab: Tensor, *, cam_is_lab2: bool, de_weighting: bool, c_de: float,
-               c_l2: float, stats: Optional[Tensor] = None, grad: Optional[Tensor] = None, want_grad: bool = True):
-    """Fused Lab + dE2000 + channel-L2 statistics and gradient (spaa_color_loss_fwd_bwd).
+               c_l2: float, stats: Optional[Tensor] = None, grad: Optional[Tensor] = None, want_grad: bool = True, fast: bool = False):
+    """Fused Lab + dE2000 + channel-L2 statistics and gradient (spaa_color_loss_fwd_bwd).  fast: hardware-approximation arithmetic (opt-in beside a 16-bit PCNet; never the fp32
+    parity mode); `ref_lab` must then be rgb2lab(ref_rgb, fast=True).
     Returns (stats [B,4] = sum dE, sum ||.||_2, sum dE^2, 0 ; grad [B,3,H,W] or None)."""
     cam, ref_rgb, ref_lab = _f32c(cam), _f32c(ref_rgb), _f32c(ref_lab)
     B, _, H, W = cam.shape
@@ -188,7 +189,7 @@ def color_loss(cam: Tensor, ref_rgb: Tensor, ref_lab: Tensor, *, cam_is_lab2: bo
     L = lib()
     ws = workspace("color_loss", L.spaa_color_loss_ws_bytes(B, H * W), cam.device)
     L.spaa_color_loss_fwd_bwd(_p(cam), _p(ref_rgb), _p(ref_lab), _bstride(ref_rgb, B), B, H * W, int(cam_is_lab2),
-                              int(de_weighting), float(c_de), float(c_l2), _p(stats), _p(grad), _p(ws), _stream()); _count()
+                              int(de_weighting), float(c_de), float(c_l2), int(bool(fast) and grad is not None), _p(stats), _p(grad), _p(ws), _stream()); _count()
     return stats, grad
 
 

@@ -94,7 +94,7 @@ class SpaaAttack:
         self.sq = torch.empty(B, device=device)
         self.prjl2sum = torch.empty(B, device=device) if self.w_prjl2 else None
         self.step2 = torch.tensor([-self.adv_lr, -self.col_lr], device=device)
-        self.ref_lab = ops.rgb2lab(scene)
+        self.ref_lab = None                        # set below, once the colour arithmetic is known
         self.g_col = torch.empty(B, 3, H, W, device=device)
         self.d_pre6 = torch.empty(B, 3, H, W, device=device)
         self.dprj = torch.empty(B, 3, *prj_hw, device=device)
@@ -134,6 +134,10 @@ class SpaaAttack:
         self._graph, self._n_eager = None, 0
         self.overlap = (os.environ.get("SPAA_OVERLAP", "0") != "0") if overlap is None else bool(overlap)
         self._aux = torch.cuda.Stream(device=device) if self.overlap else None
+        # colour arithmetic: exact by default; $SPAA_FAST_COLOR=1 opts a 16-bit PCNet mode into the hardware approximations (~1e-6 relative;
+        # measured +1.3 % it/s at B=32: 352 vs 348) -- the reference Lab image is then computed with the same arithmetic
+        self.fast_color = bool(self.fused and getattr(self, "tc", False) and os.environ.get("SPAA_FAST_COLOR", "0") != "0")
+        self.ref_lab = ops.rgb2lab(scene, fast=self.fast_color)
         self._scope = next(_SCOPES)                 # private kernel workspaces: engines may run concurrently on different streams
 
     def step(self):
@@ -184,7 +188,7 @@ class SpaaAttack:
             self.best_col.fill_(1e6)
             for t in (self.use_col, self.succ, self.better):
                 t.zero_()
-            self.ref_lab.copy_(ops.rgb2lab(self.scene))
+            self.ref_lab.copy_(ops.rgb2lab(self.scene, fast=self.fast_color))
             if self.fused:
                 for dst, src in zip(self.skip_acts, _Stack.skip1(self.sh, self.scene)):
                     dst.copy_(src)
@@ -208,7 +212,7 @@ class SpaaAttack:
 
     def _stealth_terms(self, cam):
         ops.color_loss(cam, self.scene, self.ref_lab, cam_is_lab2=False, de_weighting=False, c_de=self.w_camde / self.hw_cam,
-                       c_l2=self.w_caml2 / self.hw_cam, stats=self.stats, grad=self.g_col)
+                       c_l2=self.w_caml2 / self.hw_cam, stats=self.stats, grad=self.g_col, fast=self.fast_color)
         if self.w_prjl2:
             ops.chan_l2(self.prj_adv, self.gray, self.prjl2sum)
 

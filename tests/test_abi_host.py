@@ -51,10 +51,10 @@ def test_host_only_entry_points_and_error_convention():
     d.in_dtype, d.Cin, d.in_ps, d.in_bs = 1, 48, 48, 60 * 80 * 48      # unsupported channel count
     assert L.spaa_conv_tc_supported(ctypes.byref(d)) == 0
     # argument errors: negative return code, message retrievable, surfaced as SpaaError by the binding (no launch happens)
-    rc = L.cdll.spaa_rgb2lab_fwd(None, None, 1, 16, None)
+    rc = L.cdll.spaa_rgb2lab_fwd(None, None, 1, 16, 0, None)
     assert rc < 0 and len(L.cdll.spaa_last_error()) > 0
     with pytest.raises(SpaaError):
-        L.spaa_rgb2lab_fwd(None, None, 1, 16, None)
+        L.spaa_rgb2lab_fwd(None, None, 1, 16, 0, None)
 
 
 def test_product_refuses_cpu_tensors():

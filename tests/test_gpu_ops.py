@@ -95,6 +95,18 @@ def test_fused_colour_loss(cam_is_lab2, de_weighting):
     stats2, _ = ops.color_loss(cam.to(dev()), scene.to(dev()), ref_lab, cam_is_lab2=cam_is_lab2, de_weighting=de_weighting,
                                c_de=c_de, c_l2=c_l2, want_grad=False)
     assert torch.equal(stats, stats2)
+    # the hardware-approximation arithmetic of the 16-bit modes against the exact kernel: statistics to 2e-5 relative, the gradient to 1e-3 of
+    # its largest entry plus 1 % (the hue terms amplify a 1e-6 relative error of Lab near neutral colours)
+    ref_lab_f = ops.rgb2lab(scene.to(dev()), fast=True)          # same arithmetic on both sides: equal pixels -> equal Lab -> dE = 0 exactly
+    close(ref_lab_f, ref_lab, 2e-4, 2e-6, "fast-arithmetic Lab")
+    stats_f, grad_f = ops.color_loss(cam.to(dev()), scene.to(dev()), ref_lab_f, cam_is_lab2=cam_is_lab2, de_weighting=de_weighting,
+                                     c_de=c_de, c_l2=c_l2, fast=True)
+    close(stats_f[:, :3], stats[:, :3], 1e-3, 2e-5, "fast-arithmetic statistics")
+    assert torch.isfinite(grad_f).all()
+    assert torch.equal(grad_f[0, :, :5], torch.zeros_like(grad_f[0, :, :5])), "identical pixels keep an exactly zero gradient"
+    close(grad_f, grad, 1e-3 * grad.abs().max().item(), 1e-2, "fast-arithmetic gradient")
+    rel = ((grad_f - grad).double().norm() / grad.double().norm()).item()
+    assert rel <= 1e-4, rel
 
 
 # ---------------------------------------------------------------------------------------------------------
