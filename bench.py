@@ -225,25 +225,32 @@ def train_leg(dev, rank, world, steps, warmup, precision="bf16"):
                      if precision != "fp32" else "exact fp32 CUDA-core convolutions; ") + "value = L1+SSIM phase (1600 of the reference's 2000 steps)"}
 
 
-def torch_cuda_train_step_ms(dev, steps=5):
-    """The reference's training step on stock PyTorch-CUDA ops (oracle port: F.conv2d/grid_sample/SSIM via autograd, torch.optim.Adam)."""
+def torch_cuda_train_step_ms(dev, steps=5, batch=TRAIN_BATCH, warm=3):
+    """The reference's training step on stock PyTorch ops (oracle port: F.conv2d/grid_sample/SSIM via autograd, torch.optim.Adam) on `dev`:
+    the GPU (the torch-CUDA side leg) or the host cores (`train.cpu_baseline`, with a bounded `batch`)."""
     import synth
     from oracle import spaa_oracle as O
+    dev = torch.device(dev)
     P = {k: v.to(dev).requires_grad_(v.dtype.is_floating_point and k not in ("mask", "warping_net.ctrl_pts")) for k, v in synth.pcnet_params(300, CAM_HW).items()}
     params = [v for v in P.values() if v.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-4)
     g = torch.Generator(device=dev).manual_seed(7)
-    prj = torch.rand(TRAIN_BATCH, 3, *PRJ_HW, device=dev, generator=g)
-    cam = torch.rand(TRAIN_BATCH, 3, *CAM_HW, device=dev, generator=g)
-    scene = synth.textured(0, "bench.train.scene", (1, 3, *CAM_HW)).to(dev).expand(TRAIN_BATCH, -1, -1, -1)
+    prj = torch.rand(batch, 3, *PRJ_HW, device=dev, generator=g)
+    cam = torch.rand(batch, 3, *CAM_HW, device=dev, generator=g)
+    scene = synth.textured(0, "bench.train.scene", (1, 3, *CAM_HW)).to(dev).expand(batch, -1, -1, -1)
 
     def step():
         opt.zero_grad()
         loss, _ = O.training_loss(O.pcnet(P, prj, scene, CAM_HW), cam, "l1+ssim")
         loss.backward()
         opt.step()
-    for _ in range(3):
+    for _ in range(warm):
         step()
+    if dev.type != "cuda":
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        return (time.perf_counter() - t0) / steps * 1e3
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -456,6 +463,15 @@ def run_ours(args):
         sec = cpu_reference_run(sample_B, 1, 3)
         line["cpu_baseline"] = {"value": 1.0 / (sec * BATCH / sample_B), "unit": "it/s", "cores": cores, "kind": "port",
                                 "sample": f"{sample_B} of {BATCH} targets x 3 timed iterations (+1 warm-up) of the oracle port, scaled x{BATCH // sample_B}"}
+        if train is not None:
+            try:                                 # the training step of the reference on the host cores, bounded: 4 of the 24 images, 2 steps
+                tb = 4
+                tms = torch_cuda_train_step_ms("cpu", steps=2, batch=tb, warm=1)
+                train["cpu_baseline"] = {"value": tb / (tms / 1e3), "unit": "img/s", "cores": cores, "kind": "port",
+                                         "sample": f"batch of {tb} (of {TRAIN_BATCH}) x 2 timed steps (+1 warm-up) of the oracle port of train_pcnet's step (L1+SSIM, Adam); "
+                                                   "img/s does not depend on the batch size on the CPU"}
+            except Exception as e:               # a reported side number: never lose the bench line over it
+                train["cpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
