@@ -456,6 +456,16 @@ def run_ours(args):
         line["torch_cuda_reference"] = {"value": 1.0 / sec, "unit": "it/s", "steps": 5,
                                         "note": "oracle port of projector_based_attack.py:212-339 on stock PyTorch-CUDA ops (cuDNN, allow_tf32 default), "
                                                 "B=32, two backward passes per iteration as in the reference; wall clock with synchronize"}
+        try:                                     # the same with exact fp32 cuDNN / cuBLAS (SURVEY.md 8d asks for both): the denominator of fp32_mode
+            tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                sec32 = cpu_reference_run(BATCH, 1, 3, device=str(dev))
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+            line["torch_cuda_reference"]["exact_fp32"] = {"value": 1.0 / sec32, "unit": "it/s", "steps": 3, "note": "allow_tf32 = False"}
+        except Exception as e:                   # a reported side number: never lose the bench line over it
+            line["torch_cuda_reference"]["exact_fp32"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
