@@ -1,0 +1,246 @@
+"""GPU parity at the BASELINE shapes (projector 256x256, camera 240x320, crop 240x240, /root/reference/src/python/main.py:21-27; B = 32 targets,
+torchvision resnet18): the configuration bench.py times.  At B = 32 every BN >= 128 layer of the persistent tcgen05 kernel runs 1 280 output tiles
+on 148 CTAs (~8.6 tiles per CTA: TMEM double buffering across tiles, mbarrier ring wraps, the second epilogue group), which the toy-size tests
+of test_gpu_models.py / test_gpu_conv_tc.py never reach.
+
+Oracle: oracle/spaa_oracle.py (pinned to the unmodified reference by tests/test_oracle_golden.py) evaluated on the GPU in exact fp32
+(conftest.py switches TF32 off), cross-checked on the CPU for a 2-sample slice.  Tolerances are BASELINE.json's: fp32 1e-5 max-abs on PCNet
+outputs, 16-bit 2e-3 (fp16 storage) with identical classifier top-1; pure-bf16 storage is bounded at 4e-3."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import synth
+from oracle import spaa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CAM_HW, PRJ_HW, CROP = (240, 320), (256, 256), (240, 240)
+B = 32
+SETUP = {"classifier_crop_sz": CROP, "prj_brightness": 0.5, "prj_im_sz": PRJ_HW}
+LAYERS = ("r1s", "r2s", "r3s", "r4s", "x1", "res2", "x2", "res3", "x3", "x4", "x5", "x6", "x7")
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def maxerr(a, b):
+    return (a.detach().double().cpu() - b.detach().double().cpu()).abs().max().item()
+
+
+def make_pcnet(P, precision):
+    from spaa_b200 import models
+    m = models.PCNet(P["mask"], nn.DataParallel(models.WarpingNet(out_size=CAM_HW)), nn.DataParallel(models.ShadingNetSPAA()))
+    m.load_state_dict(P, strict=True)
+    m = models.set_precision(m.to(dev()).eval(), precision)
+    for p in m.parameters():
+        p.requires_grad = False
+    return m
+
+
+def inputs(seed=0, batch=B):
+    scene = synth.textured(seed, "full.scene", (1, 3, *CAM_HW))
+    prj = synth.textured(seed + 1, "full.prj", (batch, 3, *PRJ_HW), lo=-0.05, hi=1.05)       # some pixels outside [0,1]: the clamp mask matters
+    return scene, prj
+
+
+def fused_forward(m, prj, scene):
+    """The forward schedule of SpaaAttack._iteration (projector_based_attack.py of this repo) with the saved activations returned."""
+    from spaa_b200 import ops
+    from spaa_b200.models import _Stack
+    sh = m.shading_net
+    grid = m.warping_net.planar_grid(PRJ_HW).detach()
+    mask = m.flat_mask()
+    skip = _Stack.skip1(sh, scene)
+    nb = prj.shape[0]
+    with torch.no_grad():
+        if _Stack.act_dtype(sh) != torch.float32:
+            packed = ops.grid_sample_packed(prj, grid, _Stack.act_dtype(sh), clamp01=True, mask=mask, rough=scene)
+            cam, S = _Stack.forward(sh, None, None, None, skip_acts=skip, packed=packed)
+        else:
+            xw = torch.empty(nb, 3, *CAM_HW, device=prj.device)
+            sfeat = torch.empty(nb, 6, *CAM_HW, device=prj.device)
+            sfeat[:, :3] = scene
+            ops.grid_sample(prj, grid, clamp01=True, mask=mask, out=xw, rough=scene, out2=sfeat[:, 3:])
+            cam, S = _Stack.forward(sh, xw, sfeat, None, skip_acts=skip)
+    return cam, S
+
+
+# precision, PCNet output bound (max-abs), per-layer bound relative to the layer's largest activation, d/dprj relative Frobenius bound
+MODES = [("fp32", 1e-5, 1e-5, 2e-4), ("fp16", 2e-3, 4e-3, 0.06), ("bf16", 4e-3, 3e-2, 0.15)]
+
+
+@pytest.mark.parametrize("precision,tol_out,tol_layer,tol_grad", MODES)
+def test_pcnet_fullsize_per_layer_and_gradient(precision, tol_out, tol_layer, tol_grad):
+    """PCNet forward (every saved activation) and d/dprj at 256x256 -> 240x320, B = 32, against the oracle on the same inputs."""
+    from spaa_b200 import ops
+    P = synth.pcnet_params(100, CAM_HW)
+    Pd = {k: v.to(dev()) for k, v in P.items()}
+    scene, prj = inputs()
+    scene_d, prj_d = scene.to(dev()), prj.to(dev())
+    m = make_pcnet(P, precision)
+    probe = ops.set_probe(lambda kind, spec: kind.endswith("_tc"))
+    cam, S = fused_forward(m, prj_d, scene_d)
+    n_tc = len(probe["events"])
+    ops.set_probe(None)
+    assert (n_tc >= 14) == (precision != "fp32"), f"{n_tc} tcgen05 launches in mode {precision}"
+    tr = {}
+    with torch.no_grad():
+        ref = O.pcnet(Pd, prj_d.clamp(0, 1), scene_d.expand(B, -1, -1, -1), CAM_HW, trace=tr)
+    report = []
+    for k in LAYERS:
+        a, r = S[k].float(), tr[k]
+        scale = r.abs().max().item()
+        e = maxerr(a, r)
+        report.append(f"{k}:{e / scale:.1e}")
+        assert a.shape == r.shape and e <= tol_layer * max(1.0, scale), f"{precision} layer {k}: max abs err {e:.3e} (layer max {scale:.3g})"
+    e_out = maxerr(cam, ref)
+    print(f"fullsize[{precision}] PCNet output max abs err {e_out:.2e}; per-layer relative: " + " ".join(report))
+    assert e_out <= tol_out, e_out
+    # the GPU oracle itself against the CPU arithmetic of the reference, on a 2-sample slice
+    with torch.no_grad():
+        ref_cpu = O.pcnet(P, prj[:2].clamp(0, 1), scene.expand(2, -1, -1, -1), CAM_HW)
+    assert maxerr(ref[:2], ref_cpu) <= 2e-6
+    assert maxerr(cam[:2], ref_cpu) <= tol_out
+    # ---- gradient wrt the projector image through the nn.Module API (one autograd node per network) ----
+    cot = synth.randn(7, "full.cot", (B, 3, *CAM_HW)).to(dev())
+    x = prj_d.clone().requires_grad_(True)
+    y = m(torch.clamp(x, 0, 1), scene_d.expand(B, -1, -1, -1))
+    assert maxerr(y, cam) <= (0 if precision == "fp32" else tol_out)
+    g, = torch.autograd.grad((y * cot).sum(), x)
+    xr = prj_d.clone().requires_grad_(True)
+    with torch.enable_grad():
+        yr = O.pcnet(Pd, torch.clamp(xr, 0, 1), scene_d.expand(B, -1, -1, -1), CAM_HW)
+        gr, = torch.autograd.grad((yr * cot).sum(), xr)
+    rel = ((g - gr).double().norm() / gr.double().norm()).item()
+    cos = torch.nn.functional.cosine_similarity(g.flatten(1).double(), gr.flatten(1).double(), dim=1).min().item()
+    print(f"fullsize[{precision}] d/dprj relative Frobenius err {rel:.2e}, min per-sample cosine {cos:.6f}, max abs err {maxerr(g, gr):.2e} of {gr.abs().max().item():.2e}")
+    assert rel <= tol_grad and cos >= 1 - 2 * tol_grad, (rel, cos)
+    if precision == "fp32":
+        # well-conditioned entries to 1e-5 of the gradient's scale; the rest are ReLU / clamp masks of pre-activations within rounding of 0
+        # (the two fp32 evaluation orders switch a receptive field on or off): bounded in number
+        bad = ((g - gr).abs() > 1e-5 * gr.abs().max() + 1e-4 * gr.abs())
+        assert bad.float().mean().item() <= 1e-3, bad.float().mean().item()
+
+
+class RefClf:
+    """Reference-convention classifier object (classifier.py:15-33 fields used by the engines: model, input_sz)."""
+
+    def __init__(self, net):
+        self.model, self.input_sz = net, (224, 224)
+
+
+def resnet18(seed=0):
+    from torchvision import models as tvm
+    torch.manual_seed(seed)
+    net = tvm.resnet18(weights=None).to(dev()).eval()
+    for p in net.parameters():
+        p.requires_grad = False
+    return net
+
+
+@pytest.mark.parametrize("precision,tol_cam,graph,fold_bn", [("fp32", 1e-5, False, False), ("fp32", 1e-5, True, True), ("fp16", 2e-3, True, True),
+                                                             ("fp16", 2e-3, False, False), ("bf16", 4e-3, True, True)])
+def test_spaa_fullsize_teacher_forced_resnet18(precision, tol_cam, graph, fold_bn):
+    """Five teacher-forced iterations of the B = 32 resnet18 attack bench.py times (eager x2, capture, graph replay x3 when `graph`), every
+    iteration started from the oracle's projector image: camera image, top-1, losses, decision masks, update direction."""
+    from spaa_b200 import projector_based_attack as pba
+    iters = 5
+    P = synth.pcnet_params(100, CAM_HW)
+    Pd = {k: v.to(dev()) for k, v in P.items()}
+    scene = synth.textured(0, "bench.scene", (1, 3, *CAM_HW)).to(dev())
+    targets = [synth.SPAA_TARGETS10[i % 10] for i in range(B)]
+    net = resnet18()
+    otrace, trace = [], []
+
+    def classify(im):
+        logits = net(O.classifier_preprocess(im, CROP, (224, 224)))
+        ps, idx = torch.softmax(logits, 1).detach().sort(descending=True)
+        return logits, ps, idx
+    O.spaa_attack(lambda x, s: O.pcnet(Pd, x, s, CAM_HW), classify, targets, True, scene, 5.0, "camdE_caml2", prj_hw=PRJ_HW, iters=iters, trace=otrace)
+    m = make_pcnet(P, precision)
+    pba.clear_engines()
+    pba.spaa(m, RefClf(net), None, targets, True, scene, 5.0, "camdE_caml2", dev(), SETUP, iters=iters, trace=trace,
+             forced_prj=[t["prj_in"].to(dev()) for t in otrace], graph=graph, fold_bn=fold_bn)
+    pba.clear_engines()
+    hw = CAM_HW[0] * CAM_HW[1]
+    worst_cam = worst_cos = 0.0
+    for i, (a, o) in enumerate(zip(trace, otrace)):
+        e = maxerr(a["cam"], o["cam"])
+        worst_cam = max(worst_cam, e)
+        assert e <= tol_cam, f"it{i} cam: {e:.3e} ({precision}, graph={graph})"
+        # identical classifier top-1 on every attacked image (a sample whose two best logits are closer than the logit error is a tie)
+        lo = o["logits"].float()
+        top2 = lo.topk(2, 1)[0]
+        tie = (top2[:, 0] - top2[:, 1]) < 4 * maxerr(a["logits"], lo) + 1e-6
+        assert torch.equal(a["logits"].argmax(1)[~tie], lo.argmax(1)[~tie]), f"it{i} top-1"
+        assert int(tie.sum()) <= 1, f"it{i}: {int(tie.sum())} near-tied samples"
+        ltol = 1e-3 if precision == "fp32" else 0.05
+        assert maxerr(a["logits"], lo) <= ltol * max(1.0, lo.abs().max().item()), f"it{i} logits {maxerr(a['logits'], lo):.3e}"
+        de_tol, l2_tol = (2e-5, 1e-6) if precision == "fp32" else (5e-3, 2e-4)
+        assert maxerr(a["stats"][:, 0] / hw, o["camde"]) <= de_tol * max(1.0, o["camde"].abs().max().item()), f"it{i} camdE"
+        assert maxerr(a["stats"][:, 1] / hw, o["caml2"]) <= l2_tol * max(1.0, o["caml2"].abs().max().item()), f"it{i} caml2"
+        # decisions away from their thresholds (p_top1 = 0.9, caml2 * 255 = d_thr)
+        p1 = torch.softmax(lo, 1).max(1)[0]
+        edge = ((p1 - 0.9).abs() < (1e-4 if precision == "fp32" else 2e-2)) | ((o["caml2"] * 255 - 5.0).abs() < (1e-4 if precision == "fp32" else 5e-2)) | tie
+        assert torch.equal(a["use_col"][~edge], o["use_col"][~edge].to(dev())), f"it{i} use_col"
+        assert torch.equal(a["succ"][~edge], o["succ"][~edge].to(dev())), f"it{i} succ"
+        same = (a["use_col"] == o["use_col"].to(dev()))
+        sa = (a["prj_out"] - a["prj_in"])[same].flatten(1).double()
+        so = (o["prj_out"] - o["prj_in"]).to(dev())[same].flatten(1).double()
+        cos = torch.nn.functional.cosine_similarity(sa, so, dim=1)
+        worst_cos = max(worst_cos, (1 - cos).max().item())
+        assert (cos >= (0.9999 if precision == "fp32" else 0.97)).all(), f"it{i} update direction: min cosine {cos.min().item():.5f}"
+        assert (sa.norm(dim=1) - so.norm(dim=1)).abs().max().item() <= 1e-3, f"it{i} step length"
+    print(f"fullsize spaa[{precision}, graph={graph}, fold_bn={fold_bn}] worst cam err {worst_cam:.2e}, worst 1-cos(update) {worst_cos:.2e}")
+
+
+def test_fullsize_colour_loss_ssim_warp_vs_oracle():
+    """The fused loss / warp kernels at the camera resolution (240x320, B = 32 / 24) against the oracle on the same device."""
+    from spaa_b200 import ops
+    scene = synth.textured(5, "fl.scene", (1, 3, *CAM_HW)).to(dev())
+    cam = (scene + synth.randn(6, "fl.cam", (B, 3, *CAM_HW), 0.04).to(dev())).clamp(0, 1)
+    c = 1.0 / (CAM_HW[0] * CAM_HW[1])
+    x = cam.clone().requires_grad_(True)
+    la, lb = O.srgb_to_lab(x), O.srgb_to_lab(scene.expand(B, -1, -1, -1))
+    de = O.de2000_variant(la, lb)
+    l2 = torch.norm(x - scene, dim=1)
+    gref, = torch.autograd.grad(c * de.sum() + c * l2.sum(), x)
+    stats, grad = ops.color_loss(cam, scene, ops.rgb2lab(scene), cam_is_lab2=False, de_weighting=False, c_de=c, c_l2=c)
+    assert maxerr(stats[:, 0] * c, de.mean((1, 2))) <= 2e-5 * max(1.0, de.mean((1, 2)).max().item())
+    assert maxerr(stats[:, 1] * c, l2.mean((1, 2))) <= 1e-6
+    fin = torch.isfinite(gref)
+    assert torch.isfinite(grad).all() and fin.float().mean().item() > 0.999
+    rel = ((grad - gref)[fin].double().norm() / gref[fin].double().norm()).item()
+    assert rel <= 2e-3, rel                       # (the reference's own fp32 gradient is ill-conditioned near neutral colours, test_gpu_ops.py)
+    # SSIM + L1 (training loss, batch 24)
+    pred = synth.textured(8, "fl.pred", (24, 3, *CAM_HW)).to(dev())
+    tgt = (pred + synth.randn(9, "fl.tgt", pred.shape, 0.05).to(dev())).clamp(0, 1)
+    p = pred.clone().requires_grad_(True)
+    loss, _ = O.training_loss(p, tgt, "l1+ssim")
+    gl, = torch.autograd.grad(loss, p)
+    from spaa_b200 import train_network
+    p2 = pred.clone().requires_grad_(True)
+    got, _ = train_network.compute_loss(p2, tgt, "l1+ssim")
+    g2, = torch.autograd.grad(got, p2)
+    assert abs(got.item() - loss.item()) <= 2e-6 * max(1.0, abs(loss.item())), (got.item(), loss.item())
+    rel = ((g2 - gl).double().norm() / gl.double().norm()).item()
+    assert rel <= 1e-4 and maxerr(g2, gl) <= 2e-3 * gl.abs().max().item(), (rel, maxerr(g2, gl))
+    # warp forward / adjoint with the model's own grid
+    P = synth.pcnet_params(100, CAM_HW)
+    Pd = {k: v.to(dev()) for k, v in P.items()}
+    m = make_pcnet(P, "fp32")
+    prj = synth.textured(1, "full.prj", (B, 3, *PRJ_HW)).to(dev())
+    grid = m.warping_net.planar_grid(PRJ_HW).detach()
+    ref_grid = O.warping_fine_grid(Pd, PRJ_HW, CAM_HW)
+    assert maxerr(grid.permute(1, 2, 0), ref_grid[0]) <= 2e-6
+    pr = prj.clone().requires_grad_(True)
+    wr = O.warp(Pd, pr, CAM_HW) * Pd["mask"]
+    out = ops.grid_sample(prj, grid, mask=m.flat_mask())
+    assert maxerr(out, wr) <= 1e-5
+    cot = synth.randn(11, "fl.cot", out.shape).to(dev())
+    gpr, = torch.autograd.grad((wr * cot).sum(), pr)
+    dimg = ops.grid_sample_bwd_input(cot, grid, PRJ_HW, mask=m.flat_mask())
+    assert maxerr(dimg, gpr) <= 1e-4 * max(1.0, gpr.abs().max().item())
