@@ -73,7 +73,7 @@ def _norm_consts(dtype, device):
 
 
 class Classifier(object):
-    def __init__(self, model_name, device, device_ids, fix_params=True, sort_results=True, weights_dir=None, seed=0):
+    def __init__(self, model_name, device, device_ids, fix_params=True, sort_results=True, weights_dir=None, seed=0, allow_random_init=None):
         from torchvision import models
         self.name = model_name
         self.fix_params = fix_params
@@ -87,8 +87,12 @@ class Classifier(object):
             ctor = lambda: models.inception_v3(weights=None, init_weights=False, transform_input=True, aux_logits=True)
         else:
             raise ValueError(f"unknown classifier {model_name}")
-        # The reference downloads ImageNet weights (classifier.py:36).  Offline: load them from `weights_dir` (or
-        # $SPAA_WEIGHTS_DIR / torch hub cache) when present, otherwise use a seeded random initialisation.
+        # The reference downloads the ImageNet weights and insists on exactly those (classifier.py:36).  Offline: load them from `weights_dir`
+        # (or $SPAA_WEIGHTS_DIR / the torch hub cache).  When the checkpoint is missing this raises FileNotFoundError -- attack results against a
+        # random network are meaningless -- unless the caller opts in with allow_random_init=True (or $SPAA_ALLOW_RANDOM_INIT=1): benchmarks and
+        # tests, where only throughput / parity matter, use a seeded random initialisation; `self.pretrained` records which one was used.
+        if allow_random_init is None:
+            allow_random_init = os.environ.get("SPAA_ALLOW_RANDOM_INIT", "0") not in ("", "0")
         rng = torch.random.get_rng_state()
         torch.manual_seed(seed)
         self.model = ctor()
@@ -99,6 +103,12 @@ class Classifier(object):
                 self.model.load_state_dict(torch.load(os.path.join(d, _URLS[self.name]), map_location="cpu"))
                 self.pretrained = True
                 break
+        if not self.pretrained:
+            if not allow_random_init:
+                raise FileNotFoundError(f"pretrained weights {_URLS[self.name]} for {self.name} not found in weights_dir, $SPAA_WEIGHTS_DIR or "
+                                        f"{os.path.join(torch.hub.get_dir(), 'checkpoints')}; pass allow_random_init=True to run on a seeded random network")
+            import warnings
+            warnings.warn(f"Classifier('{self.name}'): pretrained weights not found, using a seeded RANDOM initialisation (allow_random_init)")
         self.model = self.model.to(self.device)
         if len(device_ids) > 1:
             self.model = torch.nn.DataParallel(self.model, device_ids=device_ids)

@@ -47,6 +47,28 @@ void set_last_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// Dynamic shared memory opt-in of one kernel, tracked PER DEVICE and under a mutex: cudaFuncSetAttribute applies to the current device
+// only, so a process that drives several GPUs (nn.DataParallel callers, device='cuda:1' with current device 0) must opt in on each.
+// Usage: `static SmemOptIn opt; if (!opt.ensure(kernel, bytes, carveout)) error;` right before the launch.
+struct SmemOptIn {
+    static constexpr int kMaxDevices = 64;
+    size_t reserved[kMaxDevices];
+    int lock;
+    template <class K> bool ensure(K kernel, size_t bytes, bool max_carveout = false) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+        while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {}
+        bool ok = true;
+        if (bytes > reserved[dev]) {
+            ok = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+            if (ok && max_carveout) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (ok) reserved[dev] = bytes;
+        }
+        __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
+        return ok;
+    }
+};
+
 SPAA_D float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -828,13 +828,10 @@ bool tc_supported(const spaa_conv_desc* d, const char** why) {
 template <int BN, int BK, bool F16>
 int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, cudaStream_t st) {
     using L = SmemLayout<BN, BK>;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc_kernel<BN, BK, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
-            set_last_error("spaa_conv_tc_fwd: cannot reserve %d bytes of shared memory", L::kTotal);
-            return SPAA_ERR_CUDA;
-        }
-        attr = true;
+    static SmemOptIn opt;
+    if (!opt.ensure(conv_tc_kernel<BN, BK, F16>, (size_t)L::kTotal)) {
+        set_last_error("spaa_conv_tc_fwd: cannot reserve %d bytes of shared memory", L::kTotal);
+        return SPAA_ERR_CUDA;
     }
     const int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
     conv_tc_kernel<BN, BK, F16><<<grid, kThreads, L::kTotal, st>>>(ma, mb, P);
@@ -846,14 +843,10 @@ constexpr int kHaloBarBytes = (8 * 4 + 4) * 8 + 16 + kMaxTaps * kMaxPhases * 4; 
 
 template <int BN, int BK, bool F16>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, size_t smem_bytes, cudaStream_t st) {
-    static size_t reserved = 0;
-    if (smem_bytes > reserved) {
-        if (cudaFuncSetAttribute(conv_halo_kernel<BN, BK, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
-            set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
-            return SPAA_ERR_CUDA;
-        }
-        cudaFuncSetAttribute(conv_halo_kernel<BN, BK, F16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        reserved = smem_bytes;
+    static SmemOptIn opt;
+    if (!opt.ensure(conv_halo_kernel<BN, BK, F16>, smem_bytes, true)) {
+        set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
+        return SPAA_ERR_CUDA;
     }
     const int slots = kNumSMs * P.ctas_per_sm;
     const int grid = P.total_tiles < slots ? P.total_tiles : slots;

@@ -402,13 +402,10 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_wgrad_tc: cuTensorMapEncodeTiled(dy) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
     const size_t smem_bytes = (size_t)P.nstages * P.stage_bytes + 128 + 1024;
-    static size_t reserved = 0;
-    if (smem_bytes > reserved) {
-        if (cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess) {
-            set_last_error("spaa_conv_wgrad_tc: cannot reserve shared memory");
-            return SPAA_ERR_CUDA;
-        }
-        reserved = 220 * 1024;
+    static SmemOptIn opt;
+    if (smem_bytes > 220 * 1024 || !opt.ensure(conv_wgrad_tc_kernel, (size_t)(220 * 1024))) {
+        set_last_error("spaa_conv_wgrad_tc: cannot reserve shared memory");
+        return SPAA_ERR_CUDA;
     }
     int grid = kNumSMs;
     if ((int64_t)P.total_tiles * P.nsets < grid) grid = P.total_tiles * P.nsets;

@@ -329,14 +329,11 @@ int64_t spaa_ssim_l1_ws_bytes(int64_t N, int H, int W) {
 int spaa_ssim_l1_fwd_bwd(const float* pred, const float* target, int64_t N, int H, int W, float w_l1, float w_l2, float w_ssim, const float* cot_map,
                          float* sums, float* ssim_map, float* grad, void* ws, spaa_stream_t stream) {
     SPAA_CHECK_ARG(pred && target && sums && ws && N > 0 && N < 65536 && H > 1 && W > 1, "spaa_ssim_l1_fwd_bwd: bad arguments");
-    static bool attr_set = false;
+    static SmemOptIn opt;
     const int smem = kSmemFloats * (int)sizeof(float);
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(ssim_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-            set_last_error("spaa_ssim_l1_fwd_bwd: cannot reserve %d bytes of shared memory", smem);
-            return SPAA_ERR_CUDA;
-        }
-        attr_set = true;
+    if (!opt.ensure(ssim_l1_kernel, (size_t)smem)) {
+        set_last_error("spaa_ssim_l1_fwd_bwd: cannot reserve %d bytes of shared memory", smem);
+        return SPAA_ERR_CUDA;
     }
     Gauss G;
     float sum = 0.f;

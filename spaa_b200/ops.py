@@ -249,6 +249,19 @@ def _grid_bs(grid: Tensor, B: int) -> int:
     return _bstride(grid, B)
 
 
+def _check_warp_shapes(grid: Tensor, B: int, H: int, W: int, mask, out, out_shape, rough, what: str = "grid_sample") -> None:
+    """Where the reference would raise a shape error (F.grid_sample / broadcasting, models.py:184,340-342) the raw-pointer kernels would read
+    or write out of bounds: check every operand against the grid's H x W."""
+    if grid.dim() not in (3, 4) or grid.shape[-3] != 2 or (grid.dim() == 4 and grid.shape[0] not in (1, B)):
+        raise ValueError(f"{what}: grid must be planar [2,H,W] or [B,2,H,W] (B = {B}); got {tuple(grid.shape)}")
+    if mask is not None and mask.numel() != H * W:
+        raise ValueError(f"{what}: mask has {mask.numel()} elements, the sampling grid is {H}x{W}")
+    if tuple(out.shape) != tuple(out_shape):
+        raise ValueError(f"{what}: output buffer has shape {tuple(out.shape)}, expected {tuple(out_shape)}")
+    if rough is not None and (rough.dim() != 4 or rough.shape[0] not in (1, B) or tuple(rough.shape[-2:]) != (H, W)):
+        raise ValueError(f"{what}: the surface image has shape {tuple(rough.shape)}, the sampling grid is {H}x{W} (batch {B})")
+
+
 def grid_sample(img: Tensor, grid: Tensor, *, clamp01: bool = False, mask: Optional[Tensor] = None,
                 out: Optional[Tensor] = None, rough: Optional[Tensor] = None, out2: Optional[Tensor] = None) -> Tensor:
     """img [B,C,Hi,Wi]; grid planar [2,H,W] (shared) or [B,2,H,W]; mask [H*W] floats; out [B,C,H,W].
@@ -258,10 +271,13 @@ def grid_sample(img: Tensor, grid: Tensor, *, clamp01: bool = False, mask: Optio
     H, W = grid.shape[-2:]
     if out is None:
         out = torch.empty((B, C, H, W), dtype=torch.float32, device=img.device)
+    _check_warp_shapes(grid, B, H, W, mask, out, (B, C, H, W), rough if out2 is not None else None)
     assert out.is_contiguous()
     rb = ob = 0
     if out2 is not None:
         assert rough is not None and rough.dtype == torch.float32 and out2.dtype == torch.float32
+        if tuple(out2.shape) != (B, C, H, W):
+            raise ValueError(f"grid_sample: out2 has shape {tuple(out2.shape)}, expected {(B, C, H, W)}")
         assert rough.stride(1) == H * W and rough.stride(3) == 1 and out2.stride(1) == H * W and out2.stride(3) == 1
         rb, ob = _bstride(rough, B), out2.stride(0)
     lib().spaa_grid_sample_fwd(_p(img), B, C, Hi, Wi, _p(grid), _grid_bs(grid, B), H, W, int(clamp01), _p(mask), _p(out),
@@ -279,6 +295,9 @@ def grid_sample_packed(img: Tensor, grid: Tensor, dtype, *, clamp01: bool = Fals
     H, W = grid.shape[-2:]
     if out is None:
         out = torch.empty((B, 16, H, W), dtype=dtype, device=img.device, memory_format=torch.channels_last)
+    _check_warp_shapes(grid, B, H, W, mask, out, (B, 16, H, W), rough)
+    if not out.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("grid_sample_packed: `out` must be a dense channels_last [B,16,H,W] tensor")
     lib().spaa_grid_sample_fwd_packed(_p(img), B, Hi, Wi, _p(grid), _grid_bs(grid, B), H, W, int(clamp01), _p(mask), _p(rough),
                                       _bstride(rough, B) if rough is not None else 0, _p(out), _dt(out), _stream()); _count()
     return out
@@ -313,6 +332,11 @@ def grid_sample_bwd_input(dout: Tensor, grid: Tensor, in_hw, *, mask: Optional[T
         dimg = torch.zeros((B, C, in_hw[0], in_hw[1]), dtype=torch.float32, device=dout.device)
     else:
         dimg.zero_()
+    _check_warp_shapes(grid, B, H, W, mask, dimg, (B, C, int(in_hw[0]), int(in_hw[1])), rough if dout2 is not None else None, what="grid_sample_bwd_input")
+    if tuple(grid.shape[-2:]) != (H, W):
+        raise ValueError(f"grid_sample_bwd_input: the grid is {tuple(grid.shape[-2:])} but the output gradient is {(H, W)}")
+    if dout2 is not None and tuple(dout2.shape) != (B, C, H, W):
+        raise ValueError(f"grid_sample_bwd_input: dout2 has shape {tuple(dout2.shape)}, expected {(B, C, H, W)}")
     db = rb = 0
     if dout2 is not None:
         assert dout2.stride(1) == H * W and dout2.stride(3) == 1 and rough.stride(1) == H * W
@@ -451,8 +475,19 @@ _packed_cache: Dict[tuple, Tensor] = {}
 TC_ENABLED = True          # tests flip this to compare the tensor-core path against the CUDA-core path
 
 
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    """Incremented whenever parameters were updated behind autograd's back (raw Adam kernel): part of the attack engines' cache key."""
+    return _weights_epoch
+
+
 def invalidate_packed_weights() -> None:
-    """Drop the bf16 packed-weight cache (call after parameters were updated in place by a raw kernel)."""
+    """Drop the 16-bit packed-weight cache and bump the weights epoch (call after parameters were updated in place by a raw kernel, which
+    leaves their autograd version counters unchanged): engines / CUDA graphs built from the previous weights are then never reused."""
+    global _weights_epoch
+    _weights_epoch += 1
     _packed_cache.clear()
 
 
@@ -881,3 +916,44 @@ def relu_maxpool_nhwc_bwd(dy: Tensor, idx: Tensor, in_hw, k: int, stride: int, p
     dx = torch.empty((N, H, W, C), dtype=torch.float32, device=dy.device)
     lib().spaa_relu_maxpool_nhwc_bwd(_p(dy), _p(idx), N, H, W, C, k, stride, pad, Ho, Wo, _p(dx), _stream()); _count()
     return dx.permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# device guard: every wrapper above launches on `torch.cuda.current_stream()` of the CURRENT device, while the reference API takes
+# `device` / `device_ids` arguments (spaa(..., device='cuda:1'), cfg.device) independent of it.  Each public op therefore runs with the
+# device of its tensor operands made current, and refuses operands that live on different devices.
+# ------------------------------------------------------------------------------------------------------------
+
+def _operand_device(args, kwargs):
+    dev = None
+    for a in list(args) + list(kwargs.values()):
+        if torch.is_tensor(a) and a.is_cuda:
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise ValueError(f"spaa_b200 op called with tensors on different devices ({dev} and {a.device})")
+    return dev
+
+
+def _device_guarded(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _operand_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name in ("rgb2lab", "rgb2lab_bwd", "de2000", "de2000_bwd", "color_loss", "tps_grid", "coarse_grid", "coarse_grid_bwd", "grid_finish",
+              "grid_finish_bwd", "grid_sample", "grid_sample_packed", "pack_nhwc16", "select_cotangent_packed", "grid_sample_bwd_input",
+              "grid_sample_bwd_gather", "grid_sample_bwd_grid", "conv_forward", "conv_backward_data", "conv_backward_weight", "channel_sum",
+              "ssim_l1", "adam_step", "adam_step_dev", "row_sqnorm", "row_normalized_step", "masked_copy_rows", "select_cotangent",
+              "percal_project", "chan_l2", "attack_masks", "percal_masks", "clf_preprocess", "clf_preprocess_bwd", "bias_act_nhwc",
+              "relu_maxpool_nhwc", "relu_maxpool_nhwc_bwd"):
+    globals()[_name] = _device_guarded(globals()[_name])
+WarpAdjoint.__init__ = _device_guarded(WarpAdjoint.__init__)
+del _name

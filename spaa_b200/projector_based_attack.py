@@ -76,6 +76,12 @@ class SpaaAttack:
         if scene.shape[0] != 1:
             raise ValueError("cam_scene must be a single image (3xHxW or 1x3xHxW)")
         H, W = scene.shape[2:]
+        net_ = _unwrap(pcnet)
+        if isinstance(net_, PCNet):
+            if tuple(net_.warping_net.out_size) != (H, W):
+                raise ValueError(f"the PCNet warps to {tuple(net_.warping_net.out_size)} but cam_scene is {(H, W)} (the reference fails in models.py:340-342)")
+            if net_.use_mask and net_.mask.numel() != H * W:
+                raise ValueError(f"the PCNet mask has {net_.mask.numel()} elements but cam_scene is {H}x{W}")
         self.hw_cam, self.hw_prj = H * W, prj_hw[0] * prj_hw[1]
         self.target = torch.as_tensor(list(target_idx), dtype=torch.int64, device=device)
         self.gray = setup_info["prj_brightness"] * torch.ones(B, 3, *prj_hw, device=device)
@@ -312,7 +318,10 @@ def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, ste
     if precision is not None:
         set_precision(net, precision)
     scene_shape = tuple(expand_4d(cam_scene).shape)
-    key = (id(net), _state_version(net), id(getattr(classifier, "model", classifier)), len(target_idx), bool(targeted), stealth_loss, float(d_thr),
+    # ops.weights_epoch(): FlatAdam updates parameters with a raw kernel that does not bump their version counters (train_pcnet between two
+    # spaa() calls on the same model object); simplify() adds buffers that start at version 0 -- both must miss the cache
+    key = (id(net), _state_version(net), ops.weights_epoch(), net.warping_net.fine_grid is None, net.shading_net.res1_s is None,
+           id(getattr(classifier, "model", classifier)), len(target_idx), bool(targeted), stealth_loss, float(d_thr),
            tuple(setup_info["classifier_crop_sz"]), tuple(setup_info["prj_im_sz"]), float(setup_info["prj_brightness"]), scene_shape,
            getattr(net.shading_net, "precision", "fp32"), str(torch.device(device)), bool(torch.backends.cudnn.allow_tf32), fold_bn, bool(deterministic), overlap)
     hit = _ENGINES.get(key)

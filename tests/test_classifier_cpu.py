@@ -18,7 +18,7 @@ def _randomise_bn(model, seed):
 @pytest.mark.parametrize("name", ["resnet18", "inception_v3", "vgg16"])
 def test_fold_batchnorm_keeps_logits_gradients_and_the_users_module(name):
     from spaa_b200.classifier import Classifier, fold_batchnorm
-    clf = Classifier(name, "cpu", [0])
+    clf = Classifier(name, "cpu", [0], allow_random_init=True)
     _randomise_bn(clf.model, 3)
     before = copy.deepcopy(clf.model.state_dict())
     from spaa_b200.classifier import ConvBiasAct, FusedBasicBlock, FusedReLUMaxPool2d
@@ -104,3 +104,18 @@ def test_s2d_stem_equals_the_7x7_stride_2_convolution(hw):
         assert torch.equal(f[:, 12:], torch.zeros_like(f[:, 12:])) and torch.equal(f[:, :, :2], torch.zeros_like(f[:, :, :2]))
         assert torch.equal(f[:, 0:3, 2, 2], x[:, :, 0, 0]) and torch.equal(f[:, 9:12, 2, 2], x[:, :, 1, 1]) and torch.equal(f[:, 3:6, 3, 2], x[:, :, 2, 1])
         assert (stem(f) - ya.detach()).abs().max().item() <= 1e-5
+
+
+def test_classifier_requires_pretrained_weights_unless_opted_in(tmp_path, monkeypatch):
+    """The reference always loads the exact ImageNet weights (classifier.py:36); a missing checkpoint must not silently become a random network."""
+    import pytest
+    import torch
+    from spaa_b200.classifier import Classifier
+    monkeypatch.delenv("SPAA_WEIGHTS_DIR", raising=False)
+    monkeypatch.delenv("SPAA_ALLOW_RANDOM_INIT", raising=False)
+    monkeypatch.setattr(torch.hub, "get_dir", lambda: str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        Classifier("resnet18", "cpu", [0])
+    with pytest.warns(UserWarning):
+        c = Classifier("resnet18", "cpu", [0], allow_random_init=True)
+    assert c.pretrained is False

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 CAM_HW, PRJ_HW, CROP = (240, 320), (256, 256), (240, 240)
 B = 32
 SETUP = {"classifier_crop_sz": CROP, "prj_brightness": 0.5, "prj_im_sz": PRJ_HW}
-LAYERS = ("r1s", "r2s", "r3s", "r4s", "x1", "res2", "x2", "res3", "x3", "x4", "x5", "x6", "x7")
+LAYERS = ("r1s", "r2s", "r3s", "r4s", "x1", "x2", "x3", "x4", "x5", "x6", "x7")      # (the skip tensors res2 / res3 are consumed by x6 / x5 and not kept)
 
 
 def dev():

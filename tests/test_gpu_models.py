@@ -642,3 +642,43 @@ def test_spaa_deterministic_mode_matches_default():
         cam_b, prj_b = pba.spaa(m, TinyClf(1), LABELS, targets, True, scene, 2.0, loss_name, dev(), SETUP, iters=6, deterministic=True)
         close_per_sample(prj_b, prj_a, 2e-4, f"{loss_name}: projector images")
         close_per_sample(cam_b, cam_a, 2e-4, f"{loss_name}: camera images")
+
+
+def test_attack_engine_cache_sees_training_updates_and_simplify():
+    """spaa() -> train_pcnet() on the same model object -> spaa() must not reuse the cached engine (its captured CUDA graph holds the
+    old packed weights, its grid / skip activations were computed from the old parameters); FlatAdam's raw kernel does not bump version counters."""
+    from spaa_b200 import projector_based_attack as pba, train_network as tn, models
+    P = synth.pcnet_params(61, CAM_HW)
+    m = make_pcnet(P, CAM_HW)
+    models.set_precision(m, "fp16")
+    scene = synth.textured(62, "spaa.scene", (1, 3, *CAM_HW))
+    targets = [3, 5, 7, 11]
+    pba.clear_engines()
+
+    def attack():
+        m.eval()
+        for p in m.parameters():
+            p.requires_grad = False
+        return pba.spaa(m, TinyClf(1), LABELS, targets, True, scene, 2.0, "camdE_caml2", dev(), SETUP, iters=4)
+    cam0, _ = attack()
+    n_engines = len(pba._ENGINES)
+    for p in m.parameters():
+        p.requires_grad = True
+    N = 6
+    cfg = tn.AttrDict(device="cuda:0", data_root=None, setup_name="synth", model_name="PCNet", num_train=N, batch_size=4, max_iters=2, lr=1e-2,
+                      lr_drop_ratio=0.2, lr_drop_rate=800, l2_reg=1e-4, plot_on=False, train_plot_rate=50, valid_rate=10 ** 9, loss="l1+ssim",
+                      save_checkpoint=False)
+    random.seed(5)
+    tn.train_pcnet(nn.DataParallel(m, device_ids=[0]), dict(cam_scene=scene, cam_train=synth.textured(84, "tr.cam", (N, 3, *CAM_HW)),
+                                                          prj_train=synth.textured(82, "tr.prj", (N, 3, *PRJ_HW)), mask=P["mask"]), None, cfg, verbose=False)
+    cam1, _ = attack()                                   # same model object, updated weights
+    pba.clear_engines()
+    cam_fresh, _ = attack()
+    close(cam1, cam_fresh, 1e-6, 0, "attack after training vs a fresh engine")
+    assert (cam1 - cam0).abs().max().item() > 1e-4, "training did not change the model: the test does not exercise the cache"
+    # simplify() adds buffers (version 0): a different key as well
+    m.warping_net.simplify(torch.zeros(1, 3, *PRJ_HW, device=dev()))
+    cam2, _ = attack()
+    close(cam2, cam_fresh, 1e-5, 0, "attack with a simplified WarpingNet")
+    pba.clear_engines()
+    models.set_precision(m, "fp32")

@@ -13,7 +13,7 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 dev = torch.device("cuda:0")
 B = 32
 scene = synth.textured(0, "pp.scene", (1, 3, 240, 320)).to(dev)
-clf = Classifier(name, dev, [0])
+clf = Classifier(name, dev, [0], allow_random_init=True)
 targets = torch.tensor([(7 * i) % 1000 for i in range(B)], device=dev)
 for graph in (False, True):
     atk = perc_al.PerC_AL(device=dev, max_iterations=iters, alpha_l_init=1, alpha_c_init=0.5, confidence=0)
