@@ -45,15 +45,25 @@ def synthetic_inputs(seed: int):
 
 
 def make_classifier(device, name="resnet18"):
+    """Seeded random-init torchvision classifier (no pretrained weights offline) in the reference's convention: .model / .input_sz / .name
+    (classifier.py:15-33; inception_v3 with transform_input=True, :31)."""
     from torchvision import models
+    rng = torch.random.get_rng_state()
     torch.manual_seed(0)
-    net = getattr(models, name)(weights=None).to(device).eval()
+    if name == "inception_v3":
+        net = models.inception_v3(weights=None, init_weights=False, transform_input=True, aux_logits=True)
+    else:
+        net = getattr(models, name)(weights=None)
+    torch.random.set_rng_state(rng)
+    net = net.to(device).eval()
     for p in net.parameters():
         p.requires_grad = False
 
-    class C:                                   # reference convention: .model / .input_sz (classifier.py:15-33)
-        model, input_sz = net, (224, 224)
-    return C()
+    class C:
+        pass
+    c = C()
+    c.model, c.input_sz, c.name = net, ((299, 299) if name == "inception_v3" else (224, 224)), name
+    return c
 
 
 class ClockSampler:
@@ -140,21 +150,65 @@ def cpu_reference_run(sample_B: int, warmup: int, steps: int, device="cpu"):
     return sum(per_it) / len(per_it)
 
 
+def reference_modules():
+    """(R, rh): the UNMODIFIED reference imported through tests/golden/ref_harness.py from /root/reference (build container) or its git-ignored copy
+    baseline/_ref (GPU box); None when neither exists (then the oracle port stands in, `kind: "port"`)."""
+    import ref_harness as rh
+    if not rh.available():
+        return None
+    with open(os.devnull, "w") as nul:
+        import contextlib, warnings
+        with contextlib.redirect_stderr(nul), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return rh.load_reference(), rh
+
+
+def reference_spaa_objects(R, rh, device, clf_name="resnet18"):
+    """The reference's own objects for the bench workload: DataParallel-wrapped PCNet (train_network.py:550-552) and its Classifier wrapper
+    (classifier.py:12-75, DataParallel-wrapped model :39) around the same seeded random-init networks our arm uses."""
+    scene, P, targets = synthetic_inputs(0)
+    dev = torch.device(device)
+    ids = [dev.index or 0] if dev.type == "cuda" else None
+    m = rh.ref_pcnet(R, P, CAM_HW, dev).eval()
+    m = torch.nn.DataParallel(m, device_ids=ids) if ids else torch.nn.DataParallel(m)
+    for p in m.parameters():                     # projector_based_attack.py:63-67
+        p.requires_grad = False
+    net = make_classifier(dev, clf_name).model
+    insz = (299, 299) if clf_name == "inception_v3" else (224, 224)
+    clf = rh.ref_classifier(R, torch.nn.DataParallel(net, device_ids=ids) if ids else net, insz, dev, clf_name)
+    return m, clf, scene.to(dev), targets
+
+
+def reference_cpu_spaa(sample_B: int, warmup: int, steps: int, budget_s: float):
+    """The reference's CPU path for the bench workload: (seconds per iteration of `sample_B` targets, iterations timed, kind)."""
+    mods = reference_modules()
+    if mods is None:
+        return cpu_reference_run(sample_B, warmup, steps), steps, "port"
+    R, rh = mods
+    m, clf, scene, targets = reference_spaa_objects(R, rh, "cpu")
+    sec, n = rh.time_reference_spaa(R, m, clf, targets[:sample_B], scene, D_THR, STEALTH, "cpu", SETUP, warmup=warmup, steps=steps, budget_s=budget_s)
+    return sec, n, "reference"
+
+
 def run_reference(args):
+    """Reference arm: the reference's own `spaa` (projector_based_attack.py:212-339, unmodified, imported from baseline/_ref) on the box's host cores,
+    all threads, on the FULL bench workload (32 targets, resnet18, 256x256 / 240x320).  One CPU iteration of that batch takes ~10-15 s, so the
+    run is bounded in time, not in batch: 1 warm-up iteration, then as many of the requested `--steps` as fit in ~150 s (at least 2)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_B = 4
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    sec = cpu_reference_run(sample_B, warmup, steps)
-    its = 1.0 / (sec * BATCH / sample_B)            # iterations/s of the full 32-target batch (CPU time scales linearly in B)
-    sample = f"{sample_B} of {BATCH} targets x {steps} timed iterations (+{warmup} warm-up), scaled x{BATCH // sample_B} to the full batch"
-    line = {"impl": "reference", "metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+    warmup = max(1, min(args.warmup, 1))
+    sec, n, kind = reference_cpu_spaa(BATCH, warmup, max(2, args.steps), budget_s=150.0)
+    its = 1.0 / sec
+    sample = (f"full batch of {BATCH} targets x {n} timed iterations (+{warmup} warm-up) of the "
+              + ("UNMODIFIED reference spaa() imported from baseline/_ref" if kind == "reference" else "oracle port (baseline/_ref absent)")
+              + f"; {args.steps} steps requested, bounded to ~150 s of CPU time")
+    line = {"impl": "reference", "metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus, "steps": n, "warmup": warmup,
             "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(1, "fp32"),
-            "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -259,6 +313,175 @@ def torch_cuda_train_step_ms(dev, steps=5, batch=TRAIN_BATCH, warm=3):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps
+
+# ---------------------------------------------------------------------------------------------------------------
+# the UNMODIFIED reference on the same B200 through stock PyTorch-CUDA (the denominator of the north-star's ">= 10x" target), with the
+# reference's own settings: cudnn.benchmark = True / deterministic = False (utils.py:79-81 set_torch_reproducibility(False)), three
+# device->host syncs per iteration, the refinement net on B copies of the grid, two backward passes
+# ---------------------------------------------------------------------------------------------------------------
+
+class _RefSettings:
+    def __init__(self, exact_fp32: bool):
+        self.exact = exact_fp32
+
+    def __enter__(self):
+        b = torch.backends
+        self.saved = (b.cudnn.benchmark, b.cudnn.deterministic, b.cudnn.allow_tf32, b.cuda.matmul.allow_tf32)
+        b.cudnn.benchmark, b.cudnn.deterministic = True, False
+        if self.exact:
+            b.cudnn.allow_tf32 = b.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *a):
+        b = torch.backends
+        b.cudnn.benchmark, b.cudnn.deterministic, b.cudnn.allow_tf32, b.cuda.matmul.allow_tf32 = self.saved
+
+
+def torch_cuda_reference_spaa(dev, exact_fp32: bool):
+    mods = reference_modules()
+    if mods is None:                              # baseline/_ref absent: the oracle port of the same algorithm on the same stock ops
+        with _RefSettings(exact_fp32):
+            sec = cpu_reference_run(BATCH, 2, 5, device=str(dev))
+        return {"value": 1.0 / sec, "unit": "it/s", "steps": 5, "kind": "port", "note": "oracle port on stock PyTorch-CUDA ops (baseline/_ref absent)"}
+    R, rh = mods
+    with _RefSettings(exact_fp32):
+        m, clf, scene, targets = reference_spaa_objects(R, rh, dev)
+        sec, n = rh.time_reference_spaa(R, m, clf, targets, scene, D_THR, STEALTH, dev, SETUP, warmup=10, steps=40)
+    del m, clf
+    torch.cuda.empty_cache()
+    return {"value": 1.0 / sec, "unit": "it/s", "steps": n, "kind": "reference",
+            "note": "UNMODIFIED reference spaa() (baseline/_ref, projector_based_attack.py:212-339) on stock PyTorch-CUDA, B=32, one call of 50 iterations: 10 untimed "
+                    "(cuDNN autotune, cudnn.benchmark=True as utils.py:79-81) + 40 timed; wall clock with synchronize per iteration; "
+                    + ("allow_tf32 = False (exact fp32 cuDNN / cuBLAS)" if exact_fp32 else "TF32 as torch defaults (cudnn.allow_tf32=True)")}
+
+
+def torch_cuda_reference_train(dev):
+    """The reference's train_pcnet step (train_network.py:293-320: batch 24 gathered from CPU-resident data, forward, L1+SSIM, three Adam optimisers)."""
+    import tempfile
+    import synth
+    mods = reference_modules()
+    if mods is None:
+        tms = torch_cuda_train_step_ms(dev)
+        return {"img_per_s": TRAIN_BATCH / (tms / 1e3), "ms_per_step": tms, "kind": "port", "note": "oracle port on stock PyTorch-CUDA ops (baseline/_ref absent)"}
+    R, rh = mods
+    dev = torch.device(dev)
+    P = synth.pcnet_params(300, CAM_HW)
+    with _RefSettings(False):
+        model = torch.nn.DataParallel(rh.ref_pcnet(R, P, CAM_HW, dev), device_ids=[dev.index or 0])
+        g = torch.Generator().manual_seed(7)
+        n = 96                                   # CPU-resident like the reference's (train_network.py:296-297 copies each batch H2D); 96 of the 500 pairs bound the host RAM / time
+        td = dict(cam_scene=synth.textured(0, "bench.train.scene", (1, 3, *CAM_HW)), cam_train=torch.rand(n, 3, *CAM_HW, generator=g),
+                  prj_train=torch.rand(n, 3, *PRJ_HW, generator=g), mask=P["mask"])
+        tmp = tempfile.mkdtemp()
+        os.makedirs(os.path.join(tmp, "data"), exist_ok=True)
+        cfg = R.DictConfig(dict(device=str(dev), data_root=os.path.join(tmp, "data"), setup_name="synth", model_name="PCNet", num_train=n, batch_size=TRAIN_BATCH,
+                                max_iters=0, lr=1e-3, lr_drop_ratio=0.2, lr_drop_rate=800, l2_reg=1e-4, plot_on=False, train_plot_rate=50, valid_rate=200, loss="l1+ssim"))
+        import random
+        random.seed(123)
+        sec = rh.time_reference_train_step(R, model, td, cfg, warmup=4, steps=10)
+    del model
+    torch.cuda.empty_cache()
+    return {"img_per_s": TRAIN_BATCH / sec, "ms_per_step": sec * 1e3, "kind": "reference",
+            "note": "UNMODIFIED reference train_pcnet (baseline/_ref, train_network.py:235-363) on stock PyTorch-CUDA, batch 24, L1+SSIM phase (iteration counter started at 401), "
+                    "cudnn.benchmark=True, TF32 default, batches copied from CPU-resident data every step as the reference does; 4 untimed + 9 timed steps"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: PerC-AL + CompenNet++ with vgg16 and inception_v3 (projector_based_attack.py:342-359)
+# ---------------------------------------------------------------------------------------------------------------
+PERCAL_D_THR = 11.0                               # projector_based_attack.py:186-187
+
+
+def percal_leg(dev, name, precision, with_reference=True):
+    import synth
+    from spaa_b200 import models
+    from spaa_b200.projector_based_attack import perc_al_compennet_pp
+    scene, _, targets = synthetic_inputs(0)
+    scene = scene.to(dev)
+    C = synth.compennet_pp_params(200)
+    cm = models.CompenNetPlusplus(torch.nn.DataParallel(models.WarpingNet(out_size=PRJ_HW)), torch.nn.DataParallel(models.CompenNet()))
+    cm.load_state_dict(C, strict=True)
+    cm = models.set_precision(cm.to(dev).eval(), precision)
+    for p in cm.parameters():
+        p.requires_grad = False
+    clf = make_classifier(dev, name)
+    perc_al_compennet_pp(cm, clf, None, targets, True, scene, PERCAL_D_THR, dev, SETUP, iters=8)          # warm-up call (cuDNN plans, packed weights)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cam_best, prj_best = perc_al_compennet_pp(cm, clf, None, targets, True, scene, PERCAL_D_THR, dev, SETUP)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    out = {"value": 50 / sec, "unit": "it/s", "iters": 50, "ms_per_iter": sec / 50 * 1e3,
+           "note": "one perc_al_compennet_pp() call = 50 PerC-AL iterations (classifier forward+backward, fused dE2000 forward+backward, second classifier forward) + one "
+                   "CompenNet++ forward; wall clock of the whole call, B=32, d_thr=11"}
+    del cm
+    mods = reference_modules() if with_reference else None
+    if mods is not None:
+        R, rh = mods
+        labels = {i: f"class{i}" for i in range(1000)}
+        with _RefSettings(False):
+            rcm = torch.nn.DataParallel(rh.ref_compennet_pp(R, C, PRJ_HW, dev).eval(), device_ids=[dev.index or 0])
+            for p in rcm.parameters():
+                p.requires_grad = False
+            rclf = rh.ref_classifier(R, torch.nn.DataParallel(clf.model, device_ids=[dev.index or 0]), clf.input_sz, dev, name)
+            import contextlib, io
+            warm = rh.patched(R.pba, "perc_al_compennet_pp", "max_iterations=50", "max_iterations=8")
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                warm(rcm, rclf, labels, targets, True, scene, PERCAL_D_THR, dev, SETUP)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                R.pba.perc_al_compennet_pp(rcm, rclf, labels, targets, True, scene, PERCAL_D_THR, dev, SETUP)
+                torch.cuda.synchronize()
+                rsec = time.perf_counter() - t0
+        out["torch_cuda_reference"] = {"value": 50 / rsec, "unit": "it/s", "kind": "reference",
+                                       "note": "UNMODIFIED reference perc_al_compennet_pp() on stock PyTorch-CUDA, same inputs, cudnn.benchmark=True, TF32 default; wall clock of the whole call"}
+        del rcm, rclf
+    del clf
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: batched attack sweep, 3 classifiers x setups x 100 targets as independent jobs sharded over ranks
+# (the job loop of run_projector_based_attack, projector_based_attack.py:83-141), no collective
+# ---------------------------------------------------------------------------------------------------------------
+
+def sweep_leg(dev, rank, world, precision, pcnet):
+    import torch.distributed as dist
+    import synth
+    from spaa_b200.projector_based_attack import run_attack_sweep, clear_engines
+    n_setups = {1: 1, 2: 3, 4: 5}.get(world, 10)             # 30 jobs at 8 GPUs (the BASELINE sweep); a bounded share of it on fewer GPUs
+    names = ("resnet18", "vgg16", "inception_v3")
+    clfs = {n: make_classifier(dev, n) for n in names}
+    targets = list(range(0, 1000, 10))                        # 100 targets (SURVEY.md 8d)
+    jobs = []
+    for su in range(n_setups):
+        scene = synth.textured(su, "bench.scene", (1, 3, *CAM_HW))
+        for n in names:
+            jobs.append(dict(model=pcnet, classifier=clfs[n], cam_scene=scene, target_idx=targets, stealth_loss=STEALTH, d_thr=D_THR, setup_info=SETUP,
+                             classifier_name=n))
+    jobs.sort(key=lambda j: j["classifier_name"])             # same-classifier jobs adjacent per rank: engines (buffers + CUDA graph) are reused
+    clear_engines()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = run_attack_sweep(jobs, dev, iters=50, precision=precision, save=False, rank=rank, world=world)
+    torch.cuda.synchronize()
+    mine = time.perf_counter() - t0
+    t = torch.tensor([mine], device=dev)
+    tmin = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    clear_engines()
+    torch.cuda.empty_cache()
+    return {"jobs": len(jobs), "jobs_per_s": len(jobs) / t.item(), "seconds": t.item(), "targets_per_job": len(targets) + 1, "iters": 50,
+            "attack_iterations_per_s": len(jobs) * 2 * 50 / t.item(), "idle_fraction_of_fastest_rank": 1.0 - tmin.item() / t.item(),
+            "jobs_this_rank": len(res),
+            "note": f"{len(names)} classifiers x {n_setups} synthetic setups, each job = the reference's targeted batch of 100 targets + the untargeted attack of the scene's "
+                    "top-1 (projector_based_attack.py:104-125), 50 iterations each, results copied to the host; jobs round-robin over ranks, no collective; "
+                    "wall clock of the slowest rank incl. engine construction and CUDA-graph capture per (classifier, batch size)"}
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # our arm
