@@ -200,23 +200,24 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     warmup = max(1, min(args.warmup, 1))
-    sec, n, kind = reference_cpu_spaa(BATCH, warmup, max(2, args.steps), budget_s=150.0)
+    sec, n, kind = reference_cpu_spaa(BATCH, warmup, max(2, args.steps), budget_s=float(os.environ.get("SPAA_BENCH_REF_BUDGET_S", "150")))
     its = 1.0 / sec
     sample = (f"full batch of {BATCH} targets x {n} timed iterations (+{warmup} warm-up) of the "
               + ("UNMODIFIED reference spaa() imported from baseline/_ref" if kind == "reference" else "oracle port (baseline/_ref absent)")
               + f"; {args.steps} steps requested, bounded to ~150 s of CPU time")
     line = {"impl": "reference", "metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus, "steps": n, "warmup": warmup,
             "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(1, "fp32"),
+            "config": config_dict(1, "fp32", cpu=True),
             "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def config_dict(n_gpus: int, precision: str, fold_bn: bool = False):
+def config_dict(n_gpus: int, precision: str, fold_bn: bool = False, cpu: bool = False):
     return {"workload": "spaa_attack resnet18 B=32 targets/GPU, prj 256x256, cam 240x320, camdE_caml2 d_thr=5 (BASELINE configs[1])",
             "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "precision": precision,
-            "classifier": "torchvision resnet18 (cuDNN, external operand, channels_last, TF32 as torch defaults"
+            "classifier": "torchvision resnet18, seeded random init (the reference's stock module on the host cores)" if cpu else
+                          "torchvision resnet18 (cuDNN, external operand, channels_last, TF32 as torch defaults"
                           + ("; private copy: inference-mode BatchNorm folded into the preceding cuDNN convolutions, stem ReLU + max-pooling on spaa_b200's fused kernels; see side leg stock_classifier)"
                              if fold_bn else ")"),
             "l2": "per-iteration working set (~3 GB of activations at B=32) is far larger than the 126 MB L2; no explicit flush",
@@ -230,7 +231,7 @@ def config_dict(n_gpus: int, precision: str, fold_bn: bool = False):
 TRAIN_BATCH, TRAIN_N = 24, 500
 
 
-def train_leg(dev, rank, world, steps, warmup, precision="bf16"):
+def train_leg(dev, rank, world, steps, warmup, precision="bf16", dp_mode="weak", phases=(("l1", 0), ("l1+ssim", 401))):
     """img/s of `train_pcnet` (batch 24 per GPU, weak scaling; 500 synthetic pairs resident in HBM) in the L1 phase (iterations
     <= 400) and the L1+SSIM phase (> 400), timed with CUDA events around exactly `steps` optimizer steps (max over ranks)."""
     import random
@@ -247,7 +248,8 @@ def train_leg(dev, rank, world, steps, warmup, precision="bf16"):
     model.load_state_dict(P, strict=True)
     model = models.set_precision(model.to(dev), precision)
     out = {}
-    for phase, offset in (("l1", 0), ("l1+ssim", 401)):
+    gb = TRAIN_BATCH * world if dp_mode == "weak" else TRAIN_BATCH
+    for phase, offset in phases:
         # one train_pcnet call of W + K steps; the first W (>= 5: three eager steps fill the caches, the fourth records the CUDA graph of the
         # step) are untimed, CUDA events bracket exactly the last K
         W = max(5, warmup)
@@ -260,7 +262,7 @@ def train_leg(dev, rank, world, steps, warmup, precision="bf16"):
                 torch.cuda.synchronize()
                 e0.record()
         cfg = tn.AttrDict(device=str(dev), data_root=None, model_name="PCNet", num_train=TRAIN_N, batch_size=TRAIN_BATCH, max_iters=W + steps, lr=1e-3,
-                          lr_drop_ratio=0.2, lr_drop_rate=800, l2_reg=1e-4, plot_on=False, valid_rate=10 ** 9, dp_mode="weak", iter_offset=offset,
+                          lr_drop_ratio=0.2, lr_drop_rate=800, l2_reg=1e-4, plot_on=False, valid_rate=10 ** 9, dp_mode=dp_mode, iter_offset=offset,
                           save_checkpoint=False, on_step=on_step)
         random.seed(123)
         tn.train_pcnet(model, dict(cam_scene=scene, cam_train=cam, prj_train=prj, mask=P["mask"]), None, cfg, verbose=False)
@@ -271,9 +273,9 @@ def train_leg(dev, rank, world, steps, warmup, precision="bf16"):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item() / steps
-        out[phase] = {"img_per_s": TRAIN_BATCH * world / (ms / 1e3), "ms_per_step": ms}
+        out[phase] = {"img_per_s": gb / (ms / 1e3), "ms_per_step": ms}
     return {"metric": "pcnet_train_img_per_sec", "value": out["l1+ssim"]["img_per_s"], "unit": "img/s", "phases": out, "steps": steps,
-            "batch_per_gpu": TRAIN_BATCH, "global_batch": TRAIN_BATCH * world, "scaling": "weak", "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[precision],
+            "batch_per_gpu": gb / world, "global_batch": gb, "scaling": "weak" if dp_mode == "weak" else "strong", "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[precision],
             "note": "train_pcnet (3 Adam groups in one flat fp32 bucket, one NCCL all-reduce per step when N>1); " +
                     ("bf16 activations / gradients on tcgen05 (forward, backward-data, backward-weight), fp32 master weights and accumulation; "
                      if precision != "fp32" else "exact fp32 CUDA-core convolutions; ") + "value = L1+SSIM phase (1600 of the reference's 2000 steps)"}
@@ -487,6 +489,32 @@ def sweep_leg(dev, rank, world, precision, pcnet):
 # our arm
 # ---------------------------------------------------------------------------------------------------------------
 
+def parity_check(A, P, scene, clf, dev, precision):
+    """Numerical self-check of the EXACT configuration that was just timed (same engine, same captured CUDA graph, the projector images the timed
+    iterations left behind): one more replayed iteration against the fp32 oracle (oracle/spaa_oracle.py, exact fp32 cuDNN) on the same inputs."""
+    from oracle import spaa_oracle as O
+    prj0 = A.prj_adv.clone()
+    A.step()
+    cam, logits = A.cam.clone(), A.logits.clone()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        Pd = {k: v.to(dev) for k, v in P.items()}
+        with torch.no_grad():
+            ref = O.pcnet(Pd, prj0.clamp(0, 1), scene.expand(BATCH, -1, -1, -1), CAM_HW)
+            lo_ref = clf.model(O.classifier_preprocess(ref, CROP, clf.input_sz))
+            lo_ours = clf.model(O.classifier_preprocess(cam, CROP, clf.input_sz))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    err = (cam - ref).abs()
+    tol = 1e-5 if precision == "fp32" else 2e-3
+    return {"what": "PCNet output of one replayed iteration of the timed engine vs the fp32 oracle on the same projector images; top-1 of the stock classifier "
+                    "(exact fp32) on both camera images, and of the engine's own logits (TF32 cuDNN, folded BatchNorm)",
+            "cam_max_abs_err": err.max().item(), "cam_mean_abs_err": err.mean().item(), "tolerance": tol, "within_tolerance": bool(err.max().item() <= tol),
+            "top1_agree": int((lo_ref.argmax(1) == lo_ours.argmax(1)).sum()), "top1_agree_engine_logits": int((lo_ref.argmax(1) == logits.argmax(1)).sum()),
+            "of": BATCH, "distinct_projector_images": int(torch.unique(prj0.flatten(1)[:, ::4099], dim=0).shape[0])}
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -512,8 +540,22 @@ def run_ours(args):
         p.requires_grad = False
     clf = make_classifier(dev)
 
-    # the engine spaa() itself would build for this job (kept warm across calls of a sweep: buffers + captured CUDA graph)
     fold_bn = not args.no_fold_bn and args.precision != "fp32"
+    # ---- e2e_cold: the FIRST spaa() call of this process -- the reference's unit of work, one 50-iteration call per (setup, classifier, loss, d_thr),
+    # projector_based_attack.py:107-125 -- with host buffers: engine construction, weight packing, cuDNN plan selection and the CUDA-graph capture
+    # are all inside the timed region
+    scene_host = scene.clone().pin_memory()
+    out_cam = torch.empty(BATCH, 3, *CAM_HW).pin_memory()
+    out_prj = torch.empty(BATCH, 3, *PRJ_HW).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cam_best, prj_best = spaa(pcnet, clf, None, targets, True, scene_host.to(dev, non_blocking=True), D_THR, STEALTH, dev, SETUP, iters=50,
+                              graph=not args.no_graph, fold_bn=fold_bn)
+    out_cam.copy_(cam_best, non_blocking=True)
+    out_prj.copy_(prj_best, non_blocking=True)
+    torch.cuda.synchronize()
+    cold_s = time.perf_counter() - t0
+    # the engine spaa() built for this job (kept warm across calls of a sweep: buffers + captured CUDA graph)
     A = attack_engine(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=not args.no_graph, fold_bn=fold_bn)
     for _ in range(args.warmup):                            # 2 eager iterations, then the CUDA graph is captured and replayed
         A.step()
@@ -542,6 +584,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     its = args.steps / (ms / 1e3) * world                   # whole-job iterations/s (each rank runs its own 32-target batch)
+
+    parity = parity_check(A, P, scene.to(dev), clf, dev, args.precision)
 
     # ---- roofline kernel: the same K iterations re-run WITHOUT graph replay so that every launch of the dominant kernel family
     # (conv4 / conv4_s / conv5 forward + backward-data) can be bracketed by a CUDA-event pair on the launching stream --------------
@@ -588,9 +632,6 @@ def run_ours(args):
     clf_ms = c0.elapsed_time(c1) / 10
 
     # ---- e2e: the public spaa() call with HOST buffers, copies inside the timed region -----------------------------
-    scene_host = scene.clone().pin_memory()
-    out_cam = torch.empty(BATCH, 3, *CAM_HW).pin_memory()
-    out_prj = torch.empty(BATCH, 3, *PRJ_HW).pin_memory()
     barrier()
     t0 = time.perf_counter()
     cam_best, prj_best = spaa(pcnet, clf, None, targets, True, scene_host.to(dev, non_blocking=True), D_THR, STEALTH, dev, SETUP, iters=args.steps,
@@ -613,9 +654,25 @@ def run_ours(args):
         del A
         torch.cuda.empty_cache()
         train = train_leg(dev, rank, world, max(3, min(args.steps, 10)), 2, args.train_precision)
+        # BASELINE configs[3] with the reference's own batch: ONE global batch of 24 (train_network.py:293-297) sharded over the ranks (strong scaling);
+        # at N = 1 it is the same step as the weak leg
+        if world > 1:
+            st = train_leg(dev, rank, world, max(3, min(args.steps, 10)), 2, args.train_precision, dp_mode="global", phases=(("l1+ssim", 401),))
+            train["strong"] = {"img_per_s": st["value"], "ms_per_step": st["phases"]["l1+ssim"]["ms_per_step"], "global_batch": TRAIN_BATCH,
+                               "batch_per_gpu": TRAIN_BATCH / world, "scaling": "strong",
+                               "note": "dp_mode='global': every rank draws the same seeded 24-image sample and takes a strided share; one NCCL all-reduce of the flat bucket"}
+        else:
+            train["strong"] = {"img_per_s": train["value"], "ms_per_step": train["phases"]["l1+ssim"]["ms_per_step"], "global_batch": TRAIN_BATCH,
+                               "batch_per_gpu": TRAIN_BATCH, "scaling": "strong", "note": "N = 1: identical to the weak-scaling step"}
         if world == 1 and not args.skip_side_legs and args.train_precision != "fp32":
             t32 = train_leg(dev, rank, world, 3, 1, "fp32")
             train["fp32_mode"] = {"img_per_s": t32["value"], "ms_per_step": t32["phases"]["l1+ssim"]["ms_per_step"]}
+    sweep = None
+    if not args.skip_sweep:
+        try:
+            sweep = sweep_leg(dev, rank, world, args.precision, pcnet)
+        except Exception as e:                                  # a reported side leg: never lose the bench line over it
+            sweep = {"unavailable": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -624,6 +681,10 @@ def run_ours(args):
     k_ms = sum(kern_ms) / max(1, len(kern_ms))
     flop = HEAVY_FLOP_PER_SAMPLE * BATCH
     achieved = flop / (k_ms * 1e-3) / 1e12 if k_ms else 0.0
+    # denominator: the BURST cuBLAS figure when the timed region held the maximum SM clock (a 60 ms region does not reach the power cap),
+    # the sustained one when the clocks sagged under load (B200_PROFILING.md)
+    burst = bool(clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] >= 0.95 * clk["sm_max_mhz"] and "sw_power_cap" not in clk.get("reasons", []))
+    peak_tf, peak_name = (pk["bf16_tflops"], "burst") if burst else (pk["bf16_tflops_sustained"], "sustained")
     line = {"metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world, args.precision, fold_bn),
@@ -633,13 +694,19 @@ def run_ours(args):
                     "note": "one spaa() call of `steps` iterations on a warm engine (as in a sweep): scene H2D from pinned memory + results D2H inside the timed region; bytes are per call / steps"},
             "roofline": {"bound": "tensor", "kernel": ("conv_halo_kernel<{128,256},64> (tcgen05.mma M128 x N{128,256} x K16, halo-tile TMA) on the 128<->256-channel 3x3 layers" if args.precision != "fp32"
                                     else "conv_gather_kernel<128,64,8,4> on the 128<->256-channel 3x3 layers (fp32 CUDA-core path)"),
-                         "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
                          "traffic": (NCU_HEAVY_DRAM_BYTES if args.precision != "fp32" else None), "traffic_unit": "bytes per launch (dram read + write, ncu --set full: profiles/r1_halo_v5_ncu_full.md)",
-                         "algorithmic_flop_per_launch": flop, "launches_timed": len(kern_ms), "avg_launch_ms": k_ms, "peak_source": pk["source"] + " bf16 sustained",
+                         "algorithmic_flop_per_launch": flop, "launches_timed": len(kern_ms), "avg_launch_ms": k_ms, "peak_source": pk["source"] + " bf16 " + peak_name,
                          "note": "per-launch CUDA events need host-launched kernels: timed over the same K iterations re-run without graph replay"},
-            "cuda_graph": not args.no_graph}
+            "cuda_graph": not args.no_graph,
+            "e2e_cold": {"value": 50 / cold_s, "unit": "it/s", "seconds": cold_s, "iters": 50,
+                         "note": "FIRST spaa(iters=50) call of the process with host buffers: engine construction, weight packing, cuDNN plan selection, two eager "
+                                 "iterations and the CUDA-graph capture inside the timed region (rank 0)"},
+            "parity_check": parity}
     if train is not None:
         line["train"] = train
+    if sweep is not None:
+        line["sweep"] = sweep
     if world == 1 and not args.skip_side_legs:
         # side legs (not the headline): the exact fp32 mode of the same engine, and the reference algorithm on stock PyTorch-CUDA ops
         # (cuDNN TF32 convolutions + ~1.3k ATen kernels per iteration = what the reference executes on a GPU), same batch, same box
@@ -671,31 +738,27 @@ def run_ours(args):
                                  "note": "same engine, exact CUDA-core fp32 convolutions (the 1e-5 parity mode)"}
             models.set_precision(pcnet, args.precision)
             del A32
-        if train is not None:
-            tms = torch_cuda_train_step_ms(dev)
-            train["torch_cuda_reference"] = {"img_per_s": TRAIN_BATCH / (tms / 1e3), "ms_per_step": tms,
-                                             "note": "oracle port of the reference training step on stock PyTorch-CUDA ops (cuDNN TF32 default), batch 24, L1+SSIM"}
-        sec = cpu_reference_run(BATCH, 2, 5, device=str(dev))
-        line["torch_cuda_reference"] = {"value": 1.0 / sec, "unit": "it/s", "steps": 5,
-                                        "note": "oracle port of projector_based_attack.py:212-339 on stock PyTorch-CUDA ops (cuDNN, allow_tf32 default), "
-                                                "B=32, two backward passes per iteration as in the reference; wall clock with synchronize"}
-        try:                                     # the same with exact fp32 cuDNN / cuBLAS (SURVEY.md 8d asks for both): the denominator of fp32_mode
-            tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        def leg(fn, *a_):
             try:
-                sec32 = cpu_reference_run(BATCH, 1, 3, device=str(dev))
-            finally:
-                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
-            line["torch_cuda_reference"]["exact_fp32"] = {"value": 1.0 / sec32, "unit": "it/s", "steps": 3, "note": "allow_tf32 = False"}
-        except Exception as e:                   # a reported side number: never lose the bench line over it
-            line["torch_cuda_reference"]["exact_fp32"] = {"unavailable": f"{type(e).__name__}: {e}"}
+                return fn(*a_)
+            except Exception as e:               # reported side numbers: never lose the bench line over one
+                return {"unavailable": f"{type(e).__name__}: {e}"}
+        if train is not None:
+            train["torch_cuda_reference"] = leg(torch_cuda_reference_train, dev)
+        line["torch_cuda_reference"] = leg(torch_cuda_reference_spaa, dev, False)
+        if isinstance(line["torch_cuda_reference"], dict):
+            line["torch_cuda_reference"]["exact_fp32"] = leg(torch_cuda_reference_spaa, dev, True)      # SURVEY.md 8d asks for both TF32 settings
+        # BASELINE configs[2]: PerC-AL + CompenNet++ with vgg16 and inception_v3, ours and the unmodified reference on the same GPU
+        line["percal"] = {n: leg(percal_leg, dev, n, args.precision) for n in ("vgg16", "inception_v3")}
     if world == 1 and not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        sample_B = 4
-        sec = cpu_reference_run(sample_B, 1, 3)
-        line["cpu_baseline"] = {"value": 1.0 / (sec * BATCH / sample_B), "unit": "it/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample_B} of {BATCH} targets x 3 timed iterations (+1 warm-up) of the oracle port, scaled x{BATCH // sample_B}"}
+        sample_B = 8
+        sec, n_it, kind = reference_cpu_spaa(sample_B, 1, 3, budget_s=60.0)
+        line["cpu_baseline"] = {"value": 1.0 / (sec * BATCH / sample_B), "unit": "it/s", "cores": cores, "kind": kind,
+                                "sample": f"{sample_B} of {BATCH} targets x {n_it} timed iterations (+1 warm-up) of "
+                                          + ("the UNMODIFIED reference spaa() (baseline/_ref)" if kind == "reference" else "the oracle port")
+                                          + f" on the host cores, scaled x{BATCH // sample_B} (CPU time is linear in the batch); the full batch: `bench.py --impl reference`"}
         if train is not None:
             try:                                 # the training step of the reference on the host cores, bounded: 4 of the 24 images, 2 steps
                 tb = 4
@@ -725,6 +788,7 @@ def main():
     ap.add_argument("--no-fold-bn", action="store_true", help="run the external classifier as the stock module (BatchNorm layers not folded)")
     ap.add_argument("--skip-side-legs", action="store_true", help="profiling runs only: omit the fp32 and torch-CUDA side measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")
+    ap.add_argument("--skip-sweep", action="store_true", help="omit the attack-sweep leg (BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
