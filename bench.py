@@ -207,21 +207,27 @@ def run_reference(args):
               + f"; {args.steps} steps requested, bounded to ~150 s of CPU time")
     line = {"impl": "reference", "metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": args.gpus, "steps": n, "warmup": warmup,
             "ms_per_step": 1e3 / its, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(1, "fp32", cpu=True),
+            "config": config_dict(args.gpus), "arm": arm_dict("fp32", cpu=True),
             "cpu_baseline": {"value": its, "unit": "it/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": its, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def config_dict(n_gpus: int, precision: str, fold_bn: bool = False, cpu: bool = False):
+def config_dict(n_gpus: int):
+    """Names the workload only, identically for both arms (`--impl ours` / `--impl reference`); how each arm runs it is in `arm`."""
     return {"workload": "spaa_attack resnet18 B=32 targets/GPU, prj 256x256, cam 240x320, camdE_caml2 d_thr=5 (BASELINE configs[1])",
-            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "precision": precision,
-            "classifier": "torchvision resnet18, seeded random init (the reference's stock module on the host cores)" if cpu else
-                          "torchvision resnet18 (cuDNN, external operand, channels_last, TF32 as torch defaults"
-                          + ("; private copy: inference-mode BatchNorm folded into the preceding cuDNN convolutions, stem ReLU + max-pooling on spaa_b200's fused kernels; see side leg stock_classifier)"
-                             if fold_bn else ")"),
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus,
             "l2": "per-iteration working set (~3 GB of activations at B=32) is far larger than the 126 MB L2; no explicit flush",
             "parallelism": f"{n_gpus} independent attack jobs, no collective"}
+
+
+def arm_dict(precision: str, fold_bn: bool = False, cpu: bool = False):
+    if cpu:
+        return {"precision": "fp32", "classifier": "torchvision resnet18, seeded random init, the reference's stock module on the host cores"}
+    return {"precision": precision,
+            "classifier": "torchvision resnet18 (cuDNN, external operand, channels_last, TF32 as torch defaults"
+                          + ("; private copy: inference-mode BatchNorm folded into the preceding cuDNN convolutions, stem ReLU + max-pooling on spaa_b200's fused kernels; see side leg stock_classifier)"
+                             if fold_bn else ")")}
 
 
 
@@ -687,7 +693,7 @@ def run_ours(args):
     peak_tf, peak_name = (pk["bf16_tflops"], "burst") if burst else (pk["bf16_tflops_sustained"], "sustained")
     line = {"metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world, args.precision, fold_bn),
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world), "arm": arm_dict(args.precision, fold_bn),
             "sample_iters_per_sec": its * BATCH, "classifier_ms_per_step": clf_ms, "classifier_timing": clf_how,
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,

@@ -203,7 +203,8 @@ class SpaaAttack:
                 elif self.sh.res1_s is None:
                     for dst, src in zip(self.surf_acts, _Stack.surface_branch(self.sh, self.scene)):
                         dst.copy_(src)
-        self.cam = self.logits = None
+        if self._graph is None:                   # (a captured graph keeps writing the same `cam` / `logits` buffers: they stay valid across jobs)
+            self.cam = self.logits = None
         return self
 
     def __del__(self):

@@ -682,3 +682,99 @@ def test_attack_engine_cache_sees_training_updates_and_simplify():
     close(cam2, cam_fresh, 1e-5, 0, "attack with a simplified WarpingNet")
     pba.clear_engines()
     models.set_precision(m, "fp32")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# API corners pinned to the unmodified reference (tests/golden/extra.npz, make_golden.py gen_extra)
+# ---------------------------------------------------------------------------------------------------------
+
+def test_tps_full_form_and_batched_vs_reference(golden):
+    """pytorch_tps.tps / tps_grid (pytorch_tps.py:29-106): full-form theta (T+3 rows), a batch of two TPS, per-sample control points, gradient."""
+    from spaa_b200 import pytorch_tps
+    g = golden("extra")
+    T = 36
+    ctrl = pytorch_tps.uniform_grid((6, 6)).view(-1, 2).to(dev())
+    th_full = synth.randn(101, "tps.full", (2, T + 3, 2), 0.01).to(dev()).requires_grad_(True)
+    th_red = synth.randn(102, "tps.red", (2, T + 2, 2), 0.01).to(dev())
+    ctrl_b = torch.stack((ctrl.cpu(), (ctrl.cpu() + synth.randn(103, "tps.ctrl", ctrl.shape, 0.01)).clamp(0, 1))).to(dev())
+    gf = pytorch_tps.tps_grid(th_full, ctrl, (2, 3, 12, 16))
+    close(gf, g["tps_grid_full"], 2e-6, 0, "tps_grid full form")
+    close(pytorch_tps.tps_grid(th_red, ctrl_b, (2, 3, 12, 16)), g["tps_grid_red_b"], 2e-6, 0, "tps_grid batched ctrl")
+    g3 = torch.ones(2, 12, 16, 3, device=dev())
+    g3[..., 1] = torch.linspace(0, 1, 16)
+    g3[..., 2] = torch.linspace(0, 1, 12).unsqueeze(-1)
+    close(pytorch_tps.tps(th_full, ctrl, g3), g["tps_z_full"], 2e-6, 0, "tps() full form")
+    cot = synth.randn(104, "tps.cot", (2, 12, 16, 2)).to(dev())
+    (gf * cot).sum().backward()
+    ref = T(g["tps_grid_full_gtheta"])
+    close(th_full.grad, ref, 2e-5 * max(1.0, ref.abs().max().item()), 1e-4, "d tps_grid / d theta (full form)")
+    with pytest.raises(NotImplementedError):
+        pytorch_tps.tps(th_full, ctrl, g3 * 0.9)
+
+
+def test_ssim_mask_and_weights_branches_vs_reference(golden):
+    """pytorch_ssim/__init__.py:53-67: pixel weights, boolean mask with size_average, float mask per sample -- values and d/d img1."""
+    from spaa_b200 import pytorch_ssim
+    g = golden("extra")
+    a0 = synth.textured(111, "sx.a", (2, 3, 24, 32))
+    b = (a0 + synth.randn(112, "sx.b", a0.shape, 0.1)).clamp(0, 1).to(dev())
+    w, mb = T(g["ssim_w"]).to(dev()), T(g["ssim_mask"]).to(dev())
+    for tag, kw, avg in (("w_avg", dict(weights=w), True), ("m_avg", dict(mask=mb), True), ("wm_avg", dict(mask=mb, weights=w), True),
+                         ("m_per", dict(mask=mb.float()), False), ("w_per", dict(weights=w), False)):
+        a = a0.clone().to(dev()).requires_grad_(True)
+        v = pytorch_ssim.SSIM(size_average=avg).to(dev())(a, b, **kw)
+        v.sum().backward()
+        close(v, g["ssim_" + tag], 2e-5, 0, "ssim " + tag)
+        ref = T(g["ssim_" + tag + "_g"])
+        close(a.grad, ref, 2e-3 * ref.abs().max().item(), 2e-3, "ssim grad " + tag)
+
+
+def test_simplify_paths_vs_reference(golden):
+    """ShadingNetSPAA.simplify / PCNet.simplify / CompenNetPlusplus.simplify (models.py:149-161, 268-277, 330-333, 199-202)."""
+    g = golden("extra")
+    Pn = synth.pcnet_params(36, CAM_HW, use_rough=False)
+    m = make_pcnet(Pn, CAM_HW, use_rough=False).eval()
+    prj = synth.textured(32, "pc.prj", (2, 3, *PRJ_HW)).to(dev())
+    scene1 = synth.textured(33, "pc.s", (1, 3, *CAM_HW)).to(dev())
+    with torch.no_grad():
+        x = synth.textured(35, "sn.x", (2, 3, *CAM_HW)).to(dev())
+        close(m.shading_net(x, scene1.expand(2, -1, -1, -1)), g["shading_norough_y"], 1e-5, 0, "shading (no rough) y")
+        m.shading_net.simplify(scene1)
+        close(m.shading_net.res1_s, g["res1_s"], 1e-5, 0, "res1_s")
+        close(m.shading_net.res4_s, g["res4_s"], 1e-5, 0, "res4_s")
+        assert "res1_s" in m.shading_net.state_dict()                        # buffers appear in the state dict after simplify, like the reference's
+        close(m.shading_net(x, scene1.expand(2, -1, -1, -1)), g["shading_simplified_y"], 1e-5, 0, "simplified shading y")
+        m2 = make_pcnet(Pn, CAM_HW, use_rough=False).eval()
+        m2.simplify(scene1)
+        close(m2.warping_net.fine_grid, g["pcnet_simplified_grid"], 1e-5, 0, "simplified fine_grid")
+        close(m2(prj, scene1.expand(2, -1, -1, -1)), g["pcnet_simplified_y"], 1e-5, 0, "simplified PCNet y")
+        C = synth.compennet_pp_params(37)
+        cm = make_cpp(C, PRJ_HW).eval()
+        cam = synth.textured(38, "cpp.cam", (2, 3, *CAM_HW)).to(dev())
+        cm.simplify(scene1)
+        close(cm(cam, scene1.expand(2, -1, -1, -1)), g["cpp_simplified_y"], 1e-5, 0, "simplified CompenNet++ y")
+
+
+def test_percal_adversary_original_variant_vs_reference(golden):
+    """PerC_AL.adversary (perc_al/__init__.py:53-131): the digital attack against a bare model fed (x - 0.5) / 0.5; targeted, untargeted and the
+    confidence-40 untargeted variant.  Outputs are quantised to k/255: isolated one-level flips at .5 rounding boundaries are allowed."""
+    from spaa_b200 import perc_al
+    g = golden("extra")
+    tiny = synth.TinyClassifier(3).to(dev())
+    net = nn.Sequential(nn.AdaptiveAvgPool2d((20, 20)), tiny)
+    imgs = synth.textured(121, "adv.x", (4, 3, 24, 32)).to(dev())
+    true_lab, tgt_lab = T(g["adv_true"]).to(dev()), T(g["adv_tgt"]).to(dev())
+    with torch.no_grad():
+        order = net((imgs - 0.5) / 0.5).argsort(1, descending=True)
+    assert torch.equal(order[:, 0], true_lab) and torch.equal(order[:, 2], tgt_lab)
+    changed = 0
+    for tag, labels, targeted, conf in (("t", tgt_lab, True, 0), ("u", true_lab, False, 0), ("u40", true_lab, False, 40)):
+        atk = perc_al.PerC_AL(device=dev(), max_iterations=12, alpha_l_init=1, alpha_c_init=0.5, confidence=conf)
+        out = atk.adversary(net, imgs.clone(), labels, targeted)
+        ref = T(g["adv_" + tag])
+        diff = (out.cpu() - ref).abs()
+        assert diff.max().item() <= 1.01 / 255 and (diff > 1e-6).float().mean().item() < 2e-3, (tag, diff.max().item(), (diff > 1e-6).float().mean().item())
+        changed += int((ref != imgs.cpu()).any())
+    assert changed >= 1, "no variant produced an adversarial image: the fixture does not exercise the best-so-far copy"
+    with pytest.raises(ValueError):
+        atk.adversary(net, imgs + 1.0, true_lab, False)
