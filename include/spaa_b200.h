@@ -151,6 +151,11 @@ typedef struct spaa_conv_desc {
     int64_t add_bs, add_ps, add_cs;      /* strides of `add` (add_bs = 0 broadcasts over the batch) */
     int64_t mask_bs, mask_ps, mask_cs;   /* mask and mask2 (mask_bs = 0 broadcasts) */
     int32_t epi_flags, mask_mode;
+    int32_t split;                       /* tensor-core path only. 1: bf16x3 split-precision ("fp32-accurate") operands: every logical channel c of the
+                                          * input / add / masks / 16-bit output is stored as three bf16 parts h, m, l (v = h + m + l to 24 bits) at
+                                          * physical channels c, C + c, 2C + c of a dense NHWC tensor with 3C channels; Cin / Cout stay LOGICAL
+                                          * counts, the *_ps strides are physical (3C); weights are packed with 6 * Cin input channels (the six part
+                                          * products, see spaa_b200/ops.py:_split_weights).  fp32 planar outputs are unchanged. */
 } spaa_conv_desc;
 /* v = sum + bias; [v += add]; activation; [clamp]; [v += add if ADD_AFTER_ACT]; v *= mask(mask_mode); out = v;
  * out2 (nullable) = v * (mask2 > 0).
@@ -245,6 +250,11 @@ int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t
  * when the images come from the nn.Module API instead of the fused warp kernel.  dtype: 1 bf16, 2 fp16. */
 int spaa_pack_nhwc16(const float* x, int Cx, const float* surf, int Cs, int64_t surf_bstride, void* out16, int dtype, int64_t B,
                      int64_t HW, spaa_stream_t stream);
+/* The same operand for the split-precision ("fp32-accurate", spaa_conv_desc.split) tensor-core mode: [B,HW,48] bf16 = three parts h, m, l of every
+ * one of the 16 (zero-padded) channels, [h(16) | m(16) | l(16)] per pixel, v = h + m + l to 24 significand bits.  Stands where the reference's fp32
+ * F.conv2d reads its fp32 input (models.py:223,231,239). */
+int spaa_pack_nhwc16_split3(const float* x, int Cx, const float* surf, int Cs, int64_t surf_bstride, void* out48, int64_t B, int64_t HW,
+                            spaa_stream_t stream);
 /* PerC-AL projection: delta = clamp(base+delta,0,1)-base ; xsum (nullable) = base+delta ;
  * xq = round((base+delta)*255)/255 ; l2sum[b] = sum_p ||delta[b,:,p]||_2   (perc_al/__init__.py:211-215, :15-18).
  * Tensors [B,3,HW]; base_bstride may be 0. */

@@ -24,7 +24,7 @@ class ConvDesc(ctypes.Structure):
                                                "KH", "KW", "stride", "up", "pad_h", "pad_w", "flip")]
                 + [(n, ctypes.c_int64) for n in ("in_bs", "in_ps", "in_cs", "w_ts", "w_cis", "w_cos", "out_bs", "out_ps",
                                                  "out_cs", "add_bs", "add_ps", "add_cs", "mask_bs", "mask_ps", "mask_cs")]
-                + [(n, ctypes.c_int32) for n in ("epi_flags", "mask_mode")])
+                + [(n, ctypes.c_int32) for n in ("epi_flags", "mask_mode", "split")])
 
 
 def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[str]]]:

@@ -189,6 +189,38 @@ __global__ void __launch_bounds__(kThreads) pack_nhwc16_kernel(const float* __re
     }
 }
 
+// The same operand for the split-precision ("fp32-accurate") tensor-core mode: every value as three bf16 parts h = bf16(v), m = bf16(v - h),
+// l = bf16(v - h - m), written as [h(16) | m(16) | l(16)] = 48 NHWC channels per pixel (include/spaa_b200.h, spaa_conv_desc.split)
+__global__ void __launch_bounds__(kThreads) pack_nhwc16_split3_kernel(const float* __restrict__ x, int Cx, const float* __restrict__ surf, int Cs, int64_t surf_bs,
+                                                                      uint4* __restrict__ out48, int64_t HW) {
+    const int b = blockIdx.y;
+    const float* xb = x + (int64_t)b * Cx * HW;
+    const float* sb = surf ? surf + (int64_t)b * surf_bs : nullptr;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float t = 0.f;
+            if (c < Cx) t = __ldg(xb + (int64_t)c * HW + p);
+            else if (sb && c < Cx + Cs) t = __ldg(sb + (int64_t)(c - Cx) * HW + p);
+            v[c] = t;
+        }
+        uint4* o = out48 + ((int64_t)b * HW + p) * 6;
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                w[k] = *reinterpret_cast<const uint32_t*>(&h);
+                const float2 f = __bfloat1622float2(h);
+                v[2 * k] -= f.x; v[2 * k + 1] -= f.y;
+            }
+            o[2 * part] = make_uint4(w[0], w[1], w[2], w[3]); o[2 * part + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+}
+
 // PerC-AL projection (perc_al/__init__.py:211-215, :15-18)
 __global__ void __launch_bounds__(kThreads) percal_project_kernel(const float* __restrict__ base, int64_t base_bs, float* __restrict__ delta,
                                                                   float* __restrict__ xq, float* __restrict__ xsum, float* __restrict__ l2sum, int64_t HW,
@@ -383,6 +415,13 @@ int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t
     if (dtype == 2) select_cot_packed_kernel<true><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
     else select_cot_packed_kernel<false><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
     SPAA_CHECK_LAUNCH("spaa_select_cotangent_packed");
+    return SPAA_OK;
+}
+
+int spaa_pack_nhwc16_split3(const float* x, int Cx, const float* surf, int Cs, int64_t surf_bstride, void* out48, int64_t B, int64_t HW, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(x && out48 && B > 0 && B < 65536 && HW > 0 && Cx >= 1 && Cs >= 0 && Cx + Cs <= 16 && (Cs == 0 || surf), "spaa_pack_nhwc16_split3: bad arguments");
+    pack_nhwc16_split3_kernel<<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(x, Cx, Cs ? surf : nullptr, Cs, surf_bstride, (uint4*)out48, HW);
+    SPAA_CHECK_LAUNCH("spaa_pack_nhwc16_split3");
     return SPAA_OK;
 }
 

@@ -33,6 +33,7 @@ namespace {
 constexpr int TH = 8, TW = 16, BM = TH * TW;      // output tile = 128 MMA rows
 constexpr int kThreads = 192;                      // 6 warps
 constexpr int kMaxTaps = 9, kMaxPhases = 4;
+constexpr int kMaxKChunks = 24;                    // 256 channels / 64 per chunk x 6 part products
 
 struct Tap { int8_t dy, dx, slot, pad; };
 struct Phase {
@@ -343,6 +344,9 @@ struct HaloParams {
     int32_t e_slots, e_nops;           // epilogue operand ring: slots of e_nops x 8 KB (0 slots: no ring)
     uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
     int32_t epi_flags, out_planar;
+    int32_t split;                     // 1: bf16x3 split-precision operands (see the SPLIT template parameter of conv_halo_kernel)
+    int32_t out_ps;                    // pixel stride (elements) of out / out2 / add / mask / mask2 for 16-bit NHWC output: Cout, or 3 * Cout when split
+    int32_t a_chunk[kMaxKChunks];      // first input channel of K chunk kc (TMA coordinate): kc * BK, or the part table of the split mode
     int64_t add_bs, mask_bs;
     HPhase ph[kMaxPhases];
     const float* bias;
@@ -364,9 +368,18 @@ template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint
     return d;
 }
 
-template <int BN, int BK, bool F16>
+// SPLIT (bf16 only): "fp32-accurate" split-precision mode.  Every fp32 activation / gradient / weight value v is stored as THREE bf16 numbers
+// h = bf16(v), m = bf16(v - h), l = bf16(v - h - m)  (3 x 8 = 24 significand bits, fp32's exponent range), an NHWC tensor of logical C channels
+// as [h(C) | m(C) | l(C)] = 3C physical channels.  A product v*w is the sum of the six part products hh + hm + mh + mm + hl + lh (the dropped
+// ml + lm + ll are < 2^-23 relative), i.e. the SAME implicit GEMM with a six times longer K: the producer walks the input's parts through the
+// chunk table P.a_chunk, the weights are packed with 6C input channels in the matching order (smallest products first, so that the fp32
+// accumulator in TMEM holds small values while the small terms arrive), and the MMA issuer is unchanged.  The epilogue sums the three parts of
+// the residual operand in fp32, and writes its fp32 result v as three bf16 parts (masks act on every part; the sign of v is the sign of h).
+template <int BN, int BK, bool F16, bool SPLIT>
 __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                                 const __grid_constant__ HaloParams P) {
+    static_assert(!(SPLIT && F16), "the split-precision mode stores bf16 parts");
+    constexpr int NPART = SPLIT ? 3 : 1;
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -428,8 +441,9 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                     mbar_wait(a_empty + sa, pa ^ 1);
                     uint8_t* dst = a_ring + (size_t)sa * P.a_stage_bytes;
                     mbar_expect_tx(a_full + sa, (uint32_t)P.a_tx_bytes);
+                    const int ch0 = P.a_chunk[kc];
                     for (int pl = 0; pl < P.nplanes; ++pl)
-                        tma_load_4d(dst + (size_t)pl * P.a_plane_bytes, &map_a, a_full + sa, kc * BK, x0 + (pl & 1), y0 + (pl >> 1), b);
+                        tma_load_4d(dst + (size_t)pl * P.a_plane_bytes, &map_a, a_full + sa, ch0, x0 + (pl & 1), y0 + (pl >> 1), b);
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                     if (!P.resident) {
                         for (int ph = 0; ph < NPH; ++ph)
@@ -577,14 +591,17 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                     const int cox = (pf_tx * HTW + ci) * P.up + P.ph[pf_ph].px;
                     const int coy0 = (pf_ty * HTH + q * 4) * P.up + P.ph[pf_ph].py;
                     if (cox < P.Wout) {
-                        const int64_t pix0 = ((int64_t)coy0 * P.Wout + cox) * P.Cout + pf_c * 32 + cc * 8;
-                        const int64_t kstep = (int64_t)P.up * P.Wout * P.Cout;
+                        const int64_t pix0 = ((int64_t)coy0 * P.Wout + cox) * P.out_ps + pf_c * 32 + cc * 8;
+                        const int64_t kstep = (int64_t)P.up * P.Wout * P.out_ps;
                         uint32_t d = e_warp + (uint32_t)pf_slot * slot_bytes;
                         if (has_add) {
-                            const uint16_t* sp = (const uint16_t*)P.add + (int64_t)pf_b * P.add_bs + pix0;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
-                            d += 8192;
+                            for (int part = 0; part < NPART; ++part) {          // split mode: the residual's h, m and l parts (P.Cout channels apart)
+                                const uint16_t* sp = (const uint16_t*)P.add + (int64_t)pf_b * P.add_bs + pix0 + part * P.Cout;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
+                                d += 8192;
+                            }
                         }
                         if (has_mask) {
                             const uint16_t* sp = P.mask + (int64_t)pf_b * P.mask_bs + pix0;
@@ -671,23 +688,43 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                 // cooperative store mapping of this (tile, phase): instruction k writes rows 8k..8k+7 of the warp
                 const int cox = (tx * HTW + ci) * P.up + P.ph[ph].px;
                 const int coy0 = (ty * HTH + q * 4) * P.up + P.ph[ph].py;
-                const int64_t co_off = (int64_t)b * P.Hout * P.Wout * P.Cout + ((int64_t)coy0 * P.Wout + cox) * P.Cout + cc * 8;
-                const int64_t kstep = (int64_t)P.up * P.Wout * P.Cout;
+                const int64_t co_off = ((int64_t)b * P.Hout * P.Wout + (int64_t)coy0 * P.Wout + cox) * P.out_ps + cc * 8;
+                const int64_t kstep = (int64_t)P.up * P.Wout * P.out_ps;
                 const bool cox_ok = cox < P.Wout;
                 // NOT unrolled: with the chunk loop unrolled the BN = 256 kernel was 10 400 SASS instructions and its epilogue warps
                 // (one per scheduler, nothing to hide a miss behind) spent 39 % of their samples in instruction-fetch stalls (ncu)
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     Ops cur;
+                    float asum[SPLIT ? 32 : 1];                      // split mode: h + m + l of the residual, summed in fp32
                     if (S) {
                         cp_async_wait(S - 2);
                         __syncwarp();
                         if (c0 < P.Cout) {
                             uint32_t sa16 = e_warp + (uint32_t)cs * slot_bytes;
                             if (has_add) {
+                                if constexpr (SPLIT) {
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) cur.a[g] = lds128(sa16 + own_off[g]);
-                                sa16 += 8192;
+                                    for (int k = 0; k < 32; ++k) asum[k] = 0.f;
+#pragma unroll
+                                    for (int part = 0; part < 3; ++part) {
+#pragma unroll
+                                        for (int g = 0; g < 4; ++g) {
+                                            const uint4 t = lds128(sa16 + own_off[g]);
+                                            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                const float2 f = unpack2<false>(w4[e]);
+                                                asum[g * 8 + e * 2] += f.x; asum[g * 8 + e * 2 + 1] += f.y;
+                                            }
+                                        }
+                                        sa16 += 8192;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g) cur.a[g] = lds128(sa16 + own_off[g]);
+                                    sa16 += 8192;
+                                }
                             }
                             if (has_mask) {
 #pragma unroll
@@ -715,19 +752,77 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                             for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
                         }
                         if (has_add) {
+                            if constexpr (SPLIT) {
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                const uint32_t w4[4] = {cur.a[g].x, cur.a[g].y, cur.a[g].z, cur.a[g].w};
+                                for (int k = 0; k < 32; ++k) v[k] += asum[k];
+                            } else {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 f = unpack2<F16>(w4[e]);
-                                    v[g * 8 + e * 2] += f.x; v[g * 8 + e * 2 + 1] += f.y;
+                                for (int g = 0; g < 4; ++g) {
+                                    const uint32_t w4[4] = {cur.a[g].x, cur.a[g].y, cur.a[g].z, cur.a[g].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = unpack2<F16>(w4[e]);
+                                        v[g * 8 + e * 2] += f.x; v[g * 8 + e * 2 + 1] += f.y;
+                                    }
                                 }
                             }
                         }
                         if (ef & SPAA_EPI_RELU) {
 #pragma unroll
                             for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
+                        }
+                        if constexpr (SPLIT) {
+                            // three bf16 parts of the fp32 result, each staged and stored like the single 16-bit output below; the ReLU masks
+                            // (sign of the mask operand's h part) zero every part
+                            uint32_t mk[16], mk2[16];
+                            if (has_mask) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    mk[g * 4 + 0] = posmask2(cur.m[g].x); mk[g * 4 + 1] = posmask2(cur.m[g].y);
+                                    mk[g * 4 + 2] = posmask2(cur.m[g].z); mk[g * 4 + 3] = posmask2(cur.m[g].w);
+                                }
+                            }
+                            if (has_out2) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    mk2[g * 4 + 0] = posmask2(cur.m2[g].x); mk2[g * 4 + 1] = posmask2(cur.m2[g].y);
+                                    mk2[g * 4 + 2] = posmask2(cur.m2[g].z); mk2[g * 4 + 3] = posmask2(cur.m2[g].w);
+                                }
+                            }
+#pragma unroll 1
+                            for (int part = 0; part < 3; ++part) {
+                                uint32_t pk[16];
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) {
+                                    pk[k] = pack2<false>(v[2 * k], v[2 * k + 1]);
+                                    const float2 f = unpack2<false>(pk[k]);
+                                    v[2 * k] -= f.x; v[2 * k + 1] -= f.y;              // exact: the next part rounds what this one left
+                                    if (has_mask) pk[k] &= mk[k];
+                                }
+                                if (has_out2) {
+#pragma unroll
+                                    for (int g = 0; g < 4; ++g)
+                                        sts128(o_stage + 2048u + own_off[g], make_uint4(pk[g * 4 + 0] & mk2[g * 4 + 0], pk[g * 4 + 1] & mk2[g * 4 + 1],
+                                                                                        pk[g * 4 + 2] & mk2[g * 4 + 2], pk[g * 4 + 3] & mk2[g * 4 + 3]));
+                                }
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) sts128(o_stage + own_off[g], make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+                                __syncwarp();
+                                if (cox_ok) {
+                                    uint16_t* op = (uint16_t*)P.out + co_off + c0 + part * P.Cout;
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (coy0 + k * P.up < P.Hout) *reinterpret_cast<uint4*>(op + k * kstep) = lds128(o_stage + coop_off[k]);
+                                    if (has_out2) {
+                                        uint16_t* op2 = (uint16_t*)P.out2 + co_off + c0 + part * P.Cout;
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            if (coy0 + k * P.up < P.Hout) *reinterpret_cast<uint4*>(op2 + k * kstep) = lds128(o_stage + 2048u + coop_off[k]);
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            continue;
                         }
                         // pack to 16 bit, then apply the ReLU masks of the backward pass on the packed pairs (AND with a per-half
                         // "> 0" bit mask: same bits as selecting 0.f before the conversion, ~6x fewer instructions)
@@ -806,6 +901,8 @@ int bn_for(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <= 128 
 bool tc_supported(const spaa_conv_desc* d, const char** why) {
     auto fail = [&](const char* m) { if (why) *why = m; return false; };
     if (d->in_dtype != 1 && d->in_dtype != 2) return fail("tensor-core path needs bf16 or fp16 input activations");
+    const int np = d->split ? 3 : 1;              // physical channels per logical channel (bf16x3 split-precision operands)
+    if (d->split && d->in_dtype != 1) return fail("split-precision operands are bf16 parts");
     const bool planar = d->out_dtype == 0;
     if (!planar && d->out_dtype != d->in_dtype) return fail("16-bit output must have the input's type");
     if (!(d->Cin == 16 || d->Cin == 32 || (d->Cin >= 64 && d->Cin % 64 == 0))) return fail("Cin must be 16, 32 or a multiple of 64");
@@ -815,13 +912,14 @@ bool tc_supported(const spaa_conv_desc* d, const char** why) {
         if (d->out_ps != 1 || d->out_cs != hw || (d->B > 1 && d->out_bs != hw * d->Cout)) return fail("fp32 output must be dense NCHW");
     } else {
         if (d->Cout % 32 != 0 || d->Cout > 256) return fail("Cout must be a multiple of 32 (<= 256)");
-        if (d->out_cs != 1 || d->out_ps != d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout)) return fail("16-bit output must be dense NHWC");
+        if (d->out_cs != 1 || d->out_ps != np * d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout * np)) return fail("16-bit output must be dense NHWC");
     }
     if (d->Cin == 16 && bn_for(d->Cout) != 32) return fail("Cin == 16 is implemented for Cout <= 32");
     if (d->Cin == 32 && bn_for(d->Cout) > 64) return fail("Cin == 32 is implemented for Cout <= 64");
     if (!((d->up == 1 && (d->stride == 1 || d->stride == 2)) || (d->up == 2 && d->stride == 1))) return fail("unsupported stride / up combination");
     if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return fail("square kernels up to 3x3 only");
-    if (d->in_cs != 1 || d->in_ps != d->Cin || (d->B > 1 && d->in_bs != (int64_t)d->Hin * d->Win * d->Cin)) return fail("input must be dense NHWC");   // (a single image: any batch stride)
+    if (d->in_cs != 1 || d->in_ps != np * d->Cin || (d->B > 1 && d->in_bs != (int64_t)d->Hin * d->Win * d->Cin * np)) return fail("input must be dense NHWC");   // (a single image: any batch stride)
+    if (d->split && 6 * d->Cin / (d->Cin >= 64 ? 64 : d->Cin) > kMaxKChunks) return fail("too many K chunks for the split-precision mode");
     return true;
 }
 
@@ -841,16 +939,16 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, c
 // ---- v2 host side ---------------------------------------------------------------------------------------------
 constexpr int kHaloBarBytes = (8 * 4 + 4) * 8 + 16 + kMaxTaps * kMaxPhases * 4;      // a_full/a_empty/b_full/b_empty [8] + tfull/tempty [2] + tmem slot
 
-template <int BN, int BK, bool F16>
+template <int BN, int BK, bool F16, bool SPLIT = false>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, size_t smem_bytes, cudaStream_t st) {
     static SmemOptIn opt;
-    if (!opt.ensure(conv_halo_kernel<BN, BK, F16>, smem_bytes, true)) {
+    if (!opt.ensure(conv_halo_kernel<BN, BK, F16, SPLIT>, smem_bytes, true)) {
         set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
         return SPAA_ERR_CUDA;
     }
     const int slots = kNumSMs * P.ctas_per_sm;
     const int grid = P.total_tiles < slots ? P.total_tiles : slots;
-    conv_halo_kernel<BN, BK, F16><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P);
+    conv_halo_kernel<BN, BK, F16, SPLIT><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P);
     return SPAA_OK;
 }
 
@@ -867,7 +965,19 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     HaloParams P;
     memset(&P, 0, sizeof(P));
     P.B = d->B; P.Cin = d->Cin; P.Hin = d->Hin; P.Win = d->Win; P.Cout = d->Cout; P.Hout = d->Hout; P.Wout = d->Wout;
-    P.up = d->up; P.stride = d->stride; P.nphases = nph; P.nplanes = d->stride * d->stride; P.kchunks = d->Cin / BK;
+    const int np = d->split ? 3 : 1;
+    const int cchunks = d->Cin / BK;               // K chunks of one part
+    P.up = d->up; P.stride = d->stride; P.nphases = nph; P.nplanes = d->stride * d->stride; P.kchunks = (d->split ? 6 : 1) * cchunks;
+    P.split = d->split ? 1 : 0;
+    P.out_ps = np * d->Cout;
+    if (P.kchunks > kMaxKChunks) return SPAA_ERR_UNSUPPORTED;
+    {
+        // part of the INPUT each of the six part products reads; the weights are packed with the matching part of the filter in the same order
+        // (spaa_b200/ops.py: _split_weights): smallest products first -- l*h, h*l, m*m, m*h, h*m, h*h
+        static const int a_part[6] = {2, 0, 1, 1, 0, 0};
+        for (int kc = 0; kc < P.kchunks; ++kc)
+            P.a_chunk[kc] = d->split ? a_part[kc / cchunks] * d->Cin + (kc % cchunks) * BK : kc * BK;
+    }
     P.nslots = d->KH * d->KW;
     P.epi_flags = d->epi_flags; P.out_planar = d->out_dtype == 0 ? 1 : 0;
     P.add_bs = d->add_bs; P.mask_bs = d->mask_bs;
@@ -934,7 +1044,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // ---- shared-memory plan.  Layers whose accumulator is narrow (BN <= 64: the HBM-bound ones) run TWO CTAs per SM when two
     // TMEM allocations and two half-size rings fit: twice the epilogue warps and loads in flight per SM.
     const bool planar = d->out_dtype == 0;
-    P.e_nops = planar ? ((add && d->Cout <= 4) ? 1 : 0) : ((add ? 1 : 0) + (mask ? 1 : 0) + (mask2 ? 1 : 0));
+    P.e_nops = planar ? ((add && d->Cout <= 4) ? 1 : 0) : ((add ? np : 0) + (mask ? 1 : 0) + (mask2 ? 1 : 0));
     // accumulator buffers: two when they fit in half of TMEM's 512 columns (so that two CTAs can share an SM) or in all of it for
     // the wide layers; a 4-phase BN = 64 layer (transConv1 forward) runs single-buffered in 256 columns with two CTAs per SM instead
     // of double-buffered alone on its SM
@@ -947,7 +1057,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // two epilogue groups for the wide layers (one CTA per SM), unless their rings and staging blocks would starve the weight ring
     // (measured: it pays where the MMA work per tile is short next to the epilogue's -- conv3 / skipConv3 / conv3_s / conv4 forward,
     // K per epilogue operand <= 640 -- and costs 3-8 % on the MMA-bound layers, whose issuing warp then shares its schedulers)
-    const int k_per_pass = P.nslots * d->Cin / (1 + P.e_nops);
+    const int k_per_pass = P.nslots * d->Cin * (d->split ? 6 : 1) / (1 + P.e_nops);
     P.egroups = (BN >= 128 && P.nbuf == 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
     P.e_stage_bytes = planar ? 0 : P.egroups * 4 * (mask2 ? 4096 : 2048);
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
@@ -1000,8 +1110,9 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
-        cuuint64_t strides[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2};
+        const cuuint64_t cphys = (cuuint64_t)np * d->Cin;          // physical channels of the NHWC input
+        cuuint64_t dims[4] = {cphys, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {cphys * 2, (cuuint64_t)d->Win * cphys * 2, (cuuint64_t)d->Hin * d->Win * cphys * 2};
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(P.halo_w * d->stride), (cuuint32_t)(P.halo_h * d->stride), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         CUresult r = enc(&ma, dt, 4, const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1009,8 +1120,9 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(halo input) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->KH * d->KW * BN};
-        cuuint64_t strides[1] = {(cuuint64_t)d->Cin * 2};
+        const cuuint64_t wk = (cuuint64_t)(d->split ? 6 : 1) * d->Cin;      // K extent of the packed weights
+        cuuint64_t dims[2] = {wk, (cuuint64_t)d->KH * d->KW * BN};
+        cuuint64_t strides[1] = {wk * 2};
         cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
         cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&mb, dt, 2, const_cast<void*>(wpacked), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1018,7 +1130,8 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
     int rc = SPAA_OK;
-#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? launch_halo<BN_, BK_, true>(ma, mb, P, smem_bytes, st) : launch_halo<BN_, BK_, false>(ma, mb, P, smem_bytes, st)
+#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? launch_halo<BN_, BK_, true>(ma, mb, P, smem_bytes, st) : \
+    (d->split ? launch_halo<BN_, BK_, false, true>(ma, mb, P, smem_bytes, st) : launch_halo<BN_, BK_, false>(ma, mb, P, smem_bytes, st))
     if (BK == 64) {
         if (BN == 32) SPAA_HALO_LAUNCH(32, 64);
         else if (BN == 64) SPAA_HALO_LAUNCH(64, 64);
@@ -1056,7 +1169,7 @@ int spaa_conv_tc_supported(const spaa_conv_desc* d) { return (d && tc_supported(
 
 int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d) {
     if (!d) return 0;
-    return (int64_t)d->KH * d->KW * bn_for(d->Cout) * d->Cin;
+    return (int64_t)d->KH * d->KW * bn_for(d->Cout) * d->Cin * (d->split ? 6 : 1);
 }
 
 int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, int cin_real, int cin_offset, void* packed, spaa_stream_t stream) {
@@ -1090,8 +1203,9 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
         SPAA_CHECK_ARG(!mask && !mask2, "spaa_conv_tc_fwd: masks are not implemented for fp32 planar output");
         SPAA_CHECK_ARG(!add || (d->add_ps == 1 && d->add_cs == (int64_t)d->Hout * d->Wout), "spaa_conv_tc_fwd: add must be fp32 NCHW planes");
     } else {
-        SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == d->Cout), "spaa_conv_tc_fwd: add must be dense NHWC");
-        SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == d->Cout), "spaa_conv_tc_fwd: masks must be dense NHWC");
+        const int np = d->split ? 3 : 1;
+        SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == np * d->Cout), "spaa_conv_tc_fwd: add must be dense NHWC");
+        SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == np * d->Cout), "spaa_conv_tc_fwd: masks must be dense NHWC");
     }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled is unavailable in this driver"); return SPAA_ERR_CUDA; }
@@ -1101,6 +1215,7 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
         if (rc2 == SPAA_OK) { SPAA_CHECK_LAUNCH("spaa_conv_tc_fwd (halo kernel)"); return SPAA_OK; }
         if (rc2 != SPAA_ERR_UNSUPPORTED) return rc2;
     }
+    SPAA_CHECK_ARG(!d->split, "spaa_conv_tc_fwd: the split-precision mode is implemented by the halo kernel only (this shape needs the fallback kernel)");
     const int BN = bn_for(d->Cout);
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
     const bool f16 = d->in_dtype == 2;

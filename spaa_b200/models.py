@@ -59,7 +59,12 @@ class _Stack:
     @staticmethod
     def act_dtype(net):
         """Storage type of the forward activations: fp32 NCHW (exact CUDA-core path) or 16-bit NHWC (tcgen05 path)."""
-        return {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}[getattr(net, "precision", "fp32")]
+        return {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16, "bf16x3": torch.bfloat16}[getattr(net, "precision", "fp32")]
+
+    @staticmethod
+    def split(net) -> bool:
+        """'bf16x3': every activation / gradient tensor of the stack carries three bf16 parts per logical channel (ops.conv_forward, split=True)."""
+        return getattr(net, "precision", "fp32") == "bf16x3"
 
     @staticmethod
     def grad_dtype(net):
@@ -70,14 +75,18 @@ class _Stack:
     def surface_branch(net, surf: Tensor, packed: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         sp = net._specs
         ad = _Stack.act_dtype(net)
+        s3 = _Stack.split(net)
         W = lambda n: (_get(net, n).weight, _get(net, n).bias)
-        if packed is not None:          # [x | s | x*s | 0] 16-channel NHWC: the surface features start at channel 3
-            r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=3)
+        if s3 and packed is None:
+            packed = ops.pack_nhwc16(surf, None, ad, split=True)               # surface image(s) alone (simplify(), no-rough models): channels 0..Cs-1
+            r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=0, split=True)
+        elif packed is not None:          # [x | s | x*s | 0] 16-channel NHWC: the surface features start at channel 3
+            r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=3, split=s3)
         else:
             r1s = ops.conv_forward(sp["conv1_s"], surf, *W("conv1_s"), epi=EPI_RELU, out_dtype=ad)
-        r2s = ops.conv_forward(sp["conv2_s"], r1s, *W("conv2_s"), epi=EPI_RELU)
-        r3s = ops.conv_forward(sp["conv3_s"], r2s, *W("conv3_s"), epi=EPI_RELU)
-        r4s = ops.conv_forward(sp["conv4_s"], r3s, *W("conv4_s"), epi=EPI_RELU)
+        r2s = ops.conv_forward(sp["conv2_s"], r1s, *W("conv2_s"), epi=EPI_RELU, split=s3)
+        r3s = ops.conv_forward(sp["conv3_s"], r2s, *W("conv3_s"), epi=EPI_RELU, split=s3)
+        r4s = ops.conv_forward(sp["conv4_s"], r3s, *W("conv4_s"), epi=EPI_RELU, split=s3)
         return r1s, r2s, r3s, r4s
 
     @staticmethod
@@ -100,7 +109,8 @@ class _Stack:
         if packed is None and x is not None and x.dtype == torch.float32 and _Stack.act_dtype(net) != torch.float32 and x.shape[1] == 3 and \
                 (surf_acts is not None or (surf is not None and surf.dtype == torch.float32 and surf.shape[1] <= 6)):
             # images from the nn.Module API: one pass writes [x | surf | 0] as the 16-channel NHWC operand of the tensor-core conv1 / conv1_s
-            packed = ops.pack_nhwc16(x, None if surf_acts is not None else surf, _Stack.act_dtype(net))
+            packed = ops.pack_nhwc16(x, None if surf_acts is not None else surf, _Stack.act_dtype(net), split=_Stack.split(net))
+        s3 = _Stack.split(net)
         S: dict = {"x": x, "surf": surf, "skip_in": skip_in, "packed": packed}
         if surf_acts is None:
             surf_acts = _Stack.surface_branch(net, surf, packed)
@@ -111,18 +121,18 @@ class _Stack:
             S["skip_own"] = True
         t1, t2, res1 = skip_acts
         if packed is not None:
-            x1 = ops.conv_forward(sp["conv1"], packed, *W("conv1"), add=r1s, epi=EPI_RELU, cin_offset=0)
+            x1 = ops.conv_forward(sp["conv1"], packed, *W("conv1"), add=r1s, epi=EPI_RELU, cin_offset=0, split=s3)
         else:
             x1 = ops.conv_forward(sp["conv1"], x, *W("conv1"), add=r1s, epi=EPI_RELU, out_dtype=r1s.dtype)
-        res2 = ops.conv_forward(sp["skipConv2"], x1, *W("skipConv2"))
-        x2 = ops.conv_forward(sp["conv2"], x1, *W("conv2"), add=r2s, epi=EPI_RELU)
-        res3 = ops.conv_forward(sp["skipConv3"], x2, *W("skipConv3"))
-        x3 = ops.conv_forward(sp["conv3"], x2, *W("conv3"), add=r3s, epi=EPI_RELU)
-        x4 = ops.conv_forward(sp["conv4"], x3, *W("conv4"), add=r4s, epi=EPI_RELU)
-        x5 = ops.conv_forward(sp["conv5"], x4, *W("conv5"), add=res3, epi=EPI_RELU)
-        x6 = ops.conv_forward(sp["transConv1"], x5, *W("transConv1"), add=res2, epi=EPI_RELU)
-        x7 = ops.conv_forward(sp["transConv2"], x6, *W("transConv2"), epi=EPI_RELU)
-        out = ops.conv_forward(sp["conv6"], x7, *W("conv6"), add=res1, epi=EPI_RELU | EPI_CLAMP_MAX1, out_dtype=torch.float32)
+        res2 = ops.conv_forward(sp["skipConv2"], x1, *W("skipConv2"), split=s3)
+        x2 = ops.conv_forward(sp["conv2"], x1, *W("conv2"), add=r2s, epi=EPI_RELU, split=s3)
+        res3 = ops.conv_forward(sp["skipConv3"], x2, *W("skipConv3"), split=s3)
+        x3 = ops.conv_forward(sp["conv3"], x2, *W("conv3"), add=r3s, epi=EPI_RELU, split=s3)
+        x4 = ops.conv_forward(sp["conv4"], x3, *W("conv4"), add=r4s, epi=EPI_RELU, split=s3)
+        x5 = ops.conv_forward(sp["conv5"], x4, *W("conv5"), add=res3, epi=EPI_RELU, split=s3)
+        x6 = ops.conv_forward(sp["transConv1"], x5, *W("transConv1"), add=res2, epi=EPI_RELU, split=s3)
+        x7 = ops.conv_forward(sp["transConv2"], x6, *W("transConv2"), epi=EPI_RELU, split=s3)
+        out = ops.conv_forward(sp["conv6"], x7, *W("conv6"), add=res1, epi=EPI_RELU | EPI_CLAMP_MAX1, out_dtype=torch.float32, split=s3)
         S.update(r1s=r1s, r2s=r2s, r3s=r3s, r4s=r4s, t1=t1, t2=t2, res1=res1, x1=x1, x2=x2, x3=x3, x4=x4, x5=x5, x6=x6, x7=x7, out=out)
         return out, S
 
@@ -137,6 +147,10 @@ class _Stack:
         sp = net._specs
         Wt = lambda n: _get(net, n).weight
         pg = param_grads
+        s3 = _Stack.split(net)
+        if s3 and pg is not None and any(not k.startswith("skipConv1") for k in pg):
+            raise NotImplementedError("precision 'bf16x3' (split-precision tensor-core mode) implements forward and backward-data (the attack loops, inference); "
+                                      "train in 'fp32' (exact) or 'bf16'")
         hw = lambda t: (t.shape[2], t.shape[3])
         B = (d_pre6 if d_pre6 is not None else d_pre6_packed).shape[0]
 
@@ -163,32 +177,32 @@ class _Stack:
         gdt = _Stack.grad_dtype(net)
         in_hw = hw(S["packed"]) if S.get("packed") is not None else hw(S["x"])
         d7 = ops.conv_backward_data(sp["conv6"], d_pre6_packed if d_pre6_packed is not None else d_pre6, Wt("conv6"), hw(x7), mask=x7,
-                                    mask_mode=MASK_POS, out_dtype=gdt)
+                                    mask_mode=MASK_POS, out_dtype=gdt, split=s3)
         if d_pre6_packed is not None and d_pre6_packed.dtype == x7.dtype:
             wgrad("conv6", x7, d_pre6_packed)                       # tensor-core backward-weight: padded 16-channel cotangent (3 real)
         elif d_pre6 is not None:
             wgrad("conv6", x7, d_pre6)
-        d6 = ops.conv_backward_data(sp["transConv2"], d7, Wt("transConv2"), hw(x6), mask=x6, mask_mode=MASK_POS)
+        d6 = ops.conv_backward_data(sp["transConv2"], d7, Wt("transConv2"), hw(x6), mask=x6, mask_mode=MASK_POS, split=s3)
         wgrad("transConv2", x6, d7)
-        d5 = ops.conv_backward_data(sp["transConv1"], d6, Wt("transConv1"), hw(x5), mask=x5, mask_mode=MASK_POS)
+        d5 = ops.conv_backward_data(sp["transConv1"], d6, Wt("transConv1"), hw(x5), mask=x5, mask_mode=MASK_POS, split=s3)
         wgrad("transConv1", x5, d6)
         d4s = torch.empty_like(x4, dtype=gdt) if surf_live else None
         d4 = ops.conv_backward_data(sp["conv5"], d5, Wt("conv5"), hw(x4), mask=x4, mask_mode=MASK_POS,
-                                    mask2=S["r4s"] if surf_live else None, out2=d4s)
+                                    mask2=S["r4s"] if surf_live else None, out2=d4s, split=s3)
         wgrad("conv5", x4, d5)
-        d3 = ops.conv_backward_data(sp["conv4"], d4, Wt("conv4"), hw(x3), mask=x3, mask_mode=MASK_POS)
+        d3 = ops.conv_backward_data(sp["conv4"], d4, Wt("conv4"), hw(x3), mask=x3, mask_mode=MASK_POS, split=s3)
         wgrad("conv4", x3, d4)
-        t2_ = ops.conv_backward_data(sp["conv3"], d3, Wt("conv3"), hw(x2))
+        t2_ = ops.conv_backward_data(sp["conv3"], d3, Wt("conv3"), hw(x2), split=s3)
         wgrad("conv3", x2, d3)
-        d2 = ops.conv_backward_data(sp["skipConv3"], d5, Wt("skipConv3"), hw(x2), add=t2_, mask=x2, mask_mode=MASK_POS)
+        d2 = ops.conv_backward_data(sp["skipConv3"], d5, Wt("skipConv3"), hw(x2), add=t2_, mask=x2, mask_mode=MASK_POS, split=s3)
         wgrad("skipConv3", x2, d5)
-        t1_ = ops.conv_backward_data(sp["conv2"], d2, Wt("conv2"), hw(x1))
+        t1_ = ops.conv_backward_data(sp["conv2"], d2, Wt("conv2"), hw(x1), split=s3)
         wgrad("conv2", x1, d2)
-        d1 = ops.conv_backward_data(sp["skipConv2"], d6, Wt("skipConv2"), hw(x1), add=t1_, mask=x1, mask_mode=MASK_POS)
+        d1 = ops.conv_backward_data(sp["skipConv2"], d6, Wt("skipConv2"), hw(x1), add=t1_, mask=x1, mask_mode=MASK_POS, split=s3)
         wgrad("skipConv2", x1, d6)
         dx = None
         if need_dx:
-            dx = ops.conv_backward_data(sp["conv1"], d1, Wt("conv1"), in_hw, out_dtype=torch.float32)
+            dx = ops.conv_backward_data(sp["conv1"], d1, Wt("conv1"), in_hw, out_dtype=torch.float32, split=s3)
         tc_bw = pg is not None and d1.dtype in (torch.bfloat16, torch.float16) and d1.dtype == gdt and (S["x"] is not None or S.get("packed") is not None)
         if tc_bw:
             wgrad("conv1", packed_input(), d1, 0)
@@ -197,15 +211,15 @@ class _Stack:
         dsurf = None
         if surf_live:
             r3s, r2s, r1s = S["r3s"], S["r2s"], S["r1s"]
-            d3s = ops.conv_backward_data(sp["conv4_s"], d4s, Wt("conv4_s"), hw(r3s), add=d3, mask=r3s, mask_mode=MASK_POS)
+            d3s = ops.conv_backward_data(sp["conv4_s"], d4s, Wt("conv4_s"), hw(r3s), add=d3, mask=r3s, mask_mode=MASK_POS, split=s3)
             wgrad("conv4_s", r3s, d4s)
-            d2s = ops.conv_backward_data(sp["conv3_s"], d3s, Wt("conv3_s"), hw(r2s), add=d2, mask=r2s, mask_mode=MASK_POS)
+            d2s = ops.conv_backward_data(sp["conv3_s"], d3s, Wt("conv3_s"), hw(r2s), add=d2, mask=r2s, mask_mode=MASK_POS, split=s3)
             wgrad("conv3_s", r2s, d3s)
-            d1s = ops.conv_backward_data(sp["conv2_s"], d2s, Wt("conv2_s"), hw(r1s), add=d1, mask=r1s, mask_mode=MASK_POS)
+            d1s = ops.conv_backward_data(sp["conv2_s"], d2s, Wt("conv2_s"), hw(r1s), add=d1, mask=r1s, mask_mode=MASK_POS, split=s3)
             wgrad("conv2_s", r1s, d2s)
             if surf_grad_channels is not None:
                 lo, hi = surf_grad_channels
-                dsurf = ops.conv_backward_data(sp["conv1_s"], d1s, Wt("conv1_s")[:, lo:hi], in_hw, out_dtype=torch.float32)
+                dsurf = ops.conv_backward_data(sp["conv1_s"], d1s, Wt("conv1_s")[:, lo:hi], in_hw, out_dtype=torch.float32, split=s3)
             if tc_bw:
                 wgrad("conv1_s", packed_input(), d1s, 3)
             elif S["surf"] is not None:
@@ -284,8 +298,11 @@ class _StackFn(torch.autograd.Function):
         packed = None
         if _Stack.act_dtype(net) != torch.float32:
             Bq, _, Hq, Wq = dout.shape
-            packed = torch.empty((Bq, 16, Hq, Wq), dtype=_Stack.grad_dtype(net), device=dout.device, memory_format=torch.channels_last)
-            ops.select_cotangent_packed(dout, None, None, S["out"], MASK_OPEN01, packed)
+            if _Stack.split(net):
+                packed = ops.pack_nhwc16(d_pre6, None, torch.bfloat16, split=True)
+            else:
+                packed = torch.empty((Bq, 16, Hq, Wq), dtype=_Stack.grad_dtype(net), device=dout.device, memory_format=torch.channels_last)
+                ops.select_cotangent_packed(dout, None, None, S["out"], MASK_OPEN01, packed)
         cs = S["surf"].shape[1] if (S["surf"] is not None and ctx.surf_given) else 0
         with torch.no_grad():
             dx, dsurf, dskip = _Stack.backward(net, S, d_pre6, need_dx=need_x, surf_grad_channels=(0, cs) if (need_surf and cs) else None,
@@ -307,9 +324,11 @@ def _flat_grad_view(p) -> bool:
 def set_precision(model: nn.Module, precision: str) -> nn.Module:
     """'fp32': exact CUDA-core convolutions, fp32 NCHW activations (1e-5 parity mode).
     'bf16': tcgen05 tensor-core convolutions, bf16 NHWC activations and gradients, fp32 accumulation.
-    'fp16': the same kernels with fp16 forward activations (3 more mantissa bits) and bf16 gradients."""
-    if precision not in ("fp32", "bf16", "fp16"):
-        raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
+    'fp16': the same kernels with fp16 forward activations (3 more mantissa bits) and bf16 gradients.
+    'bf16x3': fp32-accurate split-precision tensor-core mode -- every value as three bf16 parts (24 significand bits), every product as the six
+              leading part products, fp32 accumulation in TMEM (include/spaa_b200.h, spaa_conv_desc.split); forward + backward-data."""
+    if precision not in ("fp32", "bf16", "fp16", "bf16x3"):
+        raise ValueError("precision must be 'fp32', 'bf16', 'fp16' or 'bf16x3'")
     for m in model.modules():
         if isinstance(m, (_ConvStackNet, WarpingNet)):
             m.precision = precision

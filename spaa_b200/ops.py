@@ -7,6 +7,7 @@ tensors and the library must be built (spaa_b200.build) -- otherwise an exceptio
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
@@ -303,14 +304,21 @@ def grid_sample_packed(img: Tensor, grid: Tensor, dtype, *, clamp01: bool = Fals
     return out
 
 
-def pack_nhwc16(x: Tensor, surf: Optional[Tensor], dtype) -> Tensor:
-    """[x | surf | 0] as a zero-padded 16-channel NHWC tensor of `dtype` (logical shape [B,16,H,W], channels-last)."""
+def pack_nhwc16(x: Tensor, surf: Optional[Tensor], dtype, split: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    """[x | surf | 0] as a zero-padded 16-channel NHWC tensor of `dtype` (logical shape [B,16,H,W], channels-last); split: the bf16x3
+    split-precision form [h(16) | m(16) | l(16)] (logical shape [B,48,H,W])."""
     x = _f32c(x)
     B, Cx, H, W = x.shape
     Cs, sb = 0, 0
     if surf is not None:
         surf = _f32c(surf)
         Cs, sb = surf.shape[1], _bstride(surf, B)
+    if split:
+        if out is None:
+            out = torch.empty((B, 48, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        assert out.shape == (B, 48, H, W) and out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
+        lib().spaa_pack_nhwc16_split3(_p(x), Cx, _p(surf), Cs, sb, _p(out), B, H * W, _stream()); _count()
+        return out
     out = torch.empty((B, 16, H, W), dtype=dtype, device=x.device, memory_format=torch.channels_last)
     lib().spaa_pack_nhwc16(_p(x), Cx, _p(surf), Cs, sb, _p(out), _dt(out), B, H * W, _stream()); _count()
     return out
@@ -451,7 +459,8 @@ def _act_strides(t: Tensor) -> Tuple[int, int, int]:
     return (0 if t.shape[0] == 1 else sb), sw, sc
 
 
-def _fill_desc(d: ConvDesc, x: Tensor, out: Tensor, add: Optional[Tensor], mask: Optional[Tensor]) -> None:
+def _fill_desc(d: ConvDesc, x: Tensor, out: Tensor, add: Optional[Tensor], mask: Optional[Tensor], split: bool = False) -> None:
+    d.split = int(bool(split))
     d.in_dtype, d.out_dtype = _dt(x), _dt(out)
     d.B = out.shape[0]
     d.Hin, d.Win = x.shape[2], x.shape[3]
@@ -497,13 +506,17 @@ def _tc_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int) -> Tensor:
     allocated at the same address after the first one was freed can never hit a stale entry, and in-place updates are
     caught by the version counter."""
     base = w._base if w._base is not None else w
-    key = (id(base), w.data_ptr(), tuple(w.shape), tuple(w.stride()), d.flip, d.w_cis, d.w_cos, d.KH, d.Cin, d.Cout, d.in_dtype, cin_real, cin_off)
+    key = (id(base), w.data_ptr(), tuple(w.shape), tuple(w.stride()), d.flip, d.w_cis, d.w_cos, d.KH, d.Cin, d.Cout, d.in_dtype, cin_real, cin_off, d.split)
     hit = _packed_cache.get(key)
     if hit is not None and hit[0]() is base and hit[1] == base._version:
         return hit[2]
     L = lib()
     t = torch.empty(L.spaa_conv_tc_packed_elems(ctypes.byref(d)), dtype=torch.int16, device=w.device)
-    L.spaa_conv_tc_pack_weights(ctypes.byref(d), _p(w), cin_real, cin_off, _p(t), _stream()); _count()
+    if d.split:
+        w6, d6 = _split_weights(d, w, cin_real, cin_off)
+        L.spaa_conv_tc_pack_weights(ctypes.byref(d6), _p(w6), 6 * d.Cin, 0, _p(t), _stream()); _count()
+    else:
+        L.spaa_conv_tc_pack_weights(ctypes.byref(d), _p(w), cin_real, cin_off, _p(t), _stream()); _count()
     if len(_packed_cache) > 512:
         for k in [k for k, v in _packed_cache.items() if v[0]() is None]:
             del _packed_cache[k]
@@ -511,6 +524,41 @@ def _tc_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int) -> Tensor:
             _packed_cache.clear()
     _packed_cache[key] = (weakref.ref(base), base._version, t)
     return t
+
+
+# bf16x3 split-precision mode (spaa_conv_desc.split): the six part products of input x filter in the order the kernel's chunk table walks the INPUT
+# parts (conv_tc.cu: a_part = l, h, m, m, h, h): smallest products first
+_SPLIT_W_PART = (0, 2, 1, 0, 1, 0)          # filter part (0 = h, 1 = m, 2 = l) of product k
+
+
+def split3(v: Tensor):
+    """(h, m, l): the three bf16 parts of an fp32 tensor, as fp32 tensors; h + m + l == v to 24 significand bits."""
+    h = v.bfloat16().float()
+    m = (v - h).bfloat16().float()
+    return h, m, (v - h - m).bfloat16().float()
+
+
+def _split_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int):
+    """fp32 filter -> the 6 * Cin input-channel filter of the split mode (each block: one bf16 part of the filter, the real channels at
+    [cin_off, cin_off + cin_real) of the zero-padded Cin) + the descriptor that packs it with the ordinary pack kernel."""
+    ci_dim = 0 if d.w_cis == w.stride(0) else 1
+    if w.shape[ci_dim] != cin_real:
+        raise RuntimeError("split-precision weights: cannot identify the contracted dimension of the filter")
+    parts = split3(w.detach().float())
+    shape = list(w.shape)
+    shape[ci_dim] = 6 * d.Cin
+    w6 = torch.zeros(shape, dtype=torch.float32, device=w.device)
+    for k, pb in enumerate(_SPLIT_W_PART):
+        w6.narrow(ci_dim, k * d.Cin + cin_off, cin_real).copy_(parts[pb])
+    d6 = ConvDesc()
+    ctypes.memmove(ctypes.byref(d6), ctypes.byref(d), ctypes.sizeof(ConvDesc))
+    d6.split, d6.Cin = 0, 6 * d.Cin
+    d6.w_ts = 1
+    if ci_dim == 0:
+        d6.w_cis, d6.w_cos = w6.stride(0), w6.stride(1)
+    else:
+        d6.w_cis, d6.w_cos = w6.stride(1), w6.stride(0)
+    return w6, d6
 
 
 def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, out2, cin_real: Optional[int] = None, cin_off: int = 0) -> None:
@@ -521,6 +569,8 @@ def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, o
               and not (planar and (mask is not None or mask2 is not None)) and L.spaa_conv_tc_supported(ctypes.byref(d)) == 1)
     padded = cin_real is not None and cin_real != d.Cin
     if not use_tc:
+        if d.split:
+            raise RuntimeError("split-precision (bf16x3) operands exist on the tensor-core path only, and this layer shape is not covered by it")
         if padded:
             raise RuntimeError("zero-padded channel inputs are only implemented on the tensor-core path")
         for m in (mask, mask2):
@@ -543,17 +593,21 @@ def _new_act(shape, dtype, device) -> Tensor:
 
 
 def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, out: Optional[Tensor] = None,
-                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None, cin_offset: int = 0) -> Tensor:
+                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None, cin_offset: int = 0, split: bool = False) -> Tensor:
     """Forward of nn.Conv2d / nn.ConvTranspose2d with the fused epilogue `epi` (bias, residual add, activation, clamp).
     `x` may carry more channels than spec.cin (a zero-padded 16-channel NHWC tensor): the layer then reads channels
-    [cin_offset, cin_offset + spec.cin) (tensor-core path only)."""
+    [cin_offset, cin_offset + spec.cin) (tensor-core path only).
+    split: bf16x3 split-precision operands (tensor-core path): x / add / a 16-bit out carry three bf16 parts per logical channel
+    ([h | m | l], 3x the channels); an fp32 `out_dtype` output is the plain fp32 result."""
     _need_cuda(x, w)
     B, _, H, W = x.shape
     Ho, Wo = spec.out_hw(H, W)
+    np_ = 3 if split else 1
+    odt = out_dtype or x.dtype
     if out is None:
-        out = _new_act((B, spec.cout, Ho, Wo), out_dtype or x.dtype, x.device)
+        out = _new_act((B, spec.cout * (np_ if odt != torch.float32 else 1), Ho, Wo), odt, x.device)
     d = ConvDesc()
-    d.Cin, d.Cout, d.KH, d.KW = x.shape[1], spec.cout, spec.k, spec.k
+    d.Cin, d.Cout, d.KH, d.KW = x.shape[1] // np_, spec.cout, spec.k, spec.k
     s0, s1 = _w_strides(w, spec.k)
     d.w_ts = 1
     if spec.kind == "conv":
@@ -564,23 +618,25 @@ def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, o
         d.pad_h = d.pad_w = spec.k - 1 - spec.pad
         d.w_cis, d.w_cos = s0, s1
     d.epi_flags, d.mask_mode = epi, MASK_NONE
-    _fill_desc(d, x, out, add, None)
+    _fill_desc(d, x, out, add, None, split)
     _launch_conv("fwd", spec, d, x, w, b, add, None, None, out, None, cin_real=spec.cin, cin_off=cin_offset)
     return out
 
 
 def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Optional[Tensor] = None, add: Optional[Tensor] = None,
                        mask: Optional[Tensor] = None, mask_mode: int = MASK_NONE, mask2: Optional[Tensor] = None,
-                       out2: Optional[Tensor] = None, out_dtype=None) -> Tensor:
+                       out2: Optional[Tensor] = None, out_dtype=None, split: bool = False) -> Tensor:
     """Gradient wrt the layer input: out = mask(mask_mode) * (bwd_data(dy) + add); out2 = out * (mask2 > 0).
     `w` may be a channel-sliced view of the parameter (to produce only some input channels' gradients)."""
     _need_cuda(dy, w)
     B = dy.shape[0]
     cin = w.shape[1] if spec.kind == "conv" else w.shape[0]      # possibly sliced
+    np_ = 3 if split else 1
+    odt = out_dtype or dy.dtype
     if out is None:
-        out = _new_act((B, cin, in_hw[0], in_hw[1]), out_dtype or dy.dtype, dy.device)
+        out = _new_act((B, cin * (np_ if odt != torch.float32 else 1), in_hw[0], in_hw[1]), odt, dy.device)
     d = ConvDesc()
-    d.Cin, d.Cout, d.KH, d.KW = dy.shape[1], cin, spec.k, spec.k      # dy may be zero-padded to 16 channels (tensor-core path)
+    d.Cin, d.Cout, d.KH, d.KW = dy.shape[1] // np_, cin, spec.k, spec.k      # dy may be zero-padded to 16 channels (tensor-core path)
     s0, s1 = _w_strides(w, spec.k)
     d.w_ts = 1
     if spec.kind == "conv":       # dX = gather conv of dY with flipped taps, up = stride
@@ -591,7 +647,7 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
         d.stride, d.up, d.pad_h, d.pad_w, d.flip = spec.stride, 1, spec.pad, spec.pad, 0
         d.w_cos, d.w_cis = s0, s1
     d.epi_flags, d.mask_mode = 0, (mask_mode if mask is not None else MASK_NONE)
-    _fill_desc(d, dy, out, add, mask if mask is not None else mask2)
+    _fill_desc(d, dy, out, add, mask if mask is not None else mask2, split)
     if mask2 is not None:
         assert out2 is not None and out2.stride() == out.stride()
         if mask is not None:
@@ -935,16 +991,26 @@ def _operand_device(args, kwargs):
     return dev
 
 
+NVTX = os.environ.get("SPAA_NVTX", "0") not in ("", "0")      # one NVTX range per op wrapper (= per kernel family) for nsys / ncu --nvtx timelines
+
+
 def _device_guarded(fn):
     import functools
+    name = "spaa." + fn.__name__
 
     @functools.wraps(fn)
     def wrapper(*args, **kwargs):
         dev = _operand_device(args, kwargs)
-        if dev is None or dev.index == torch.cuda.current_device():
-            return fn(*args, **kwargs)
-        with torch.cuda.device(dev):
-            return fn(*args, **kwargs)
+        if NVTX:
+            torch.cuda.nvtx.range_push(name)
+        try:
+            if dev is None or dev.index == torch.cuda.current_device():
+                return fn(*args, **kwargs)
+            with torch.cuda.device(dev):
+                return fn(*args, **kwargs)
+        finally:
+            if NVTX:
+                torch.cuda.nvtx.range_pop()
     return wrapper
 
 

@@ -119,9 +119,11 @@ class SpaaAttack:
                 self.skip_acts = _Stack.skip1(sh, scene)                      # skipConv1(cam_scene): loop constant
                 self.xw = torch.empty(B, 3, H, W, device=device)
                 self.tc = _Stack.act_dtype(sh) != torch.float32          # tensor-core path: packed 16-channel boundary tensors
+                self.split = _Stack.split(sh)                            # 'bf16x3': three bf16 parts per channel (48 physical channels)
                 if self.tc:
-                    self.packed = torch.empty((B, 16, H, W), dtype=_Stack.act_dtype(sh), device=device, memory_format=torch.channels_last)
-                    self.d_pre6_packed = torch.empty((B, 16, H, W), dtype=_Stack.grad_dtype(sh), device=device, memory_format=torch.channels_last)
+                    pc = 48 if self.split else 16
+                    self.packed = torch.empty((B, pc, H, W), dtype=_Stack.act_dtype(sh), device=device, memory_format=torch.channels_last)
+                    self.d_pre6_packed = torch.empty((B, pc, H, W), dtype=_Stack.grad_dtype(sh), device=device, memory_format=torch.channels_last)
                 if net.use_rough:
                     self.sfeat = torch.empty(B, 6, H, W, device=device)
                     self.sfeat[:, :3] = scene
@@ -228,7 +230,18 @@ class SpaaAttack:
         # ---- forward ---------------------------------------------------------------------------------
         if self.fused:
             with torch.no_grad():
-                if self.tc:
+                if self.tc and self.split:
+                    # exact fp32 warp, then ONE pass that writes [x | s | x*s | 0] as three bf16 parts per channel
+                    if net.use_rough:
+                        ops.grid_sample(self.prj_adv, self.grid, clamp01=True, mask=self.mask, out=self.xw, rough=scene, out2=self.sfeat[:, 3:])
+                        ops.pack_nhwc16(self.xw, self.sfeat, self.packed.dtype, split=True, out=self.packed)
+                    else:
+                        ops.grid_sample(self.prj_adv, self.grid, clamp01=True, mask=self.mask, out=self.xw)
+                        ops.pack_nhwc16(self.xw, None, self.packed.dtype, split=True, out=self.packed)
+                    cam, S = _Stack.forward(self.sh, None, None, None, surf_acts=self.surf_acts, skip_acts=self.skip_acts, packed=self.packed)
+                    if net.use_rough:
+                        S["surf_own"] = True
+                elif self.tc:
                     ops.grid_sample_packed(self.prj_adv, self.grid, self.packed.dtype, clamp01=True, mask=self.mask, rough=scene, out=self.packed)
                     cam, S = _Stack.forward(self.sh, None, None, None, surf_acts=self.surf_acts, skip_acts=self.skip_acts, packed=self.packed)
                 elif net.use_rough:
@@ -259,7 +272,10 @@ class SpaaAttack:
         # ---- one backward with the per-sample selected cotangent ---------------------------------------
         if self.fused:
             d_pre6 = d_pk = None
-            if self.tc:
+            if self.tc and self.split:
+                ops.select_cotangent(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6)
+                d_pk = ops.pack_nhwc16(self.d_pre6, None, self.d_pre6_packed.dtype, split=True, out=self.d_pre6_packed)
+            elif self.tc:
                 d_pk = ops.select_cotangent_packed(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6_packed)
             else:
                 d_pre6 = ops.select_cotangent(g_adv, self.g_col, self.use_col, cam, MASK_OPEN01, self.d_pre6)

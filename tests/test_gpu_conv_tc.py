@@ -203,3 +203,114 @@ def test_tc_backward_weight_padded_channels():
     ops.conv_backward_weight(spec6, cl(x7), cl(cot), dw6, db6)
     close(dw6, gw6, 2e-3 * gw6.abs().max().item(), 1e-3, "padded-gradient dW")
     close(db6, cot[:, :3].double().sum((0, 2, 3)), 1e-2, 1e-3, "padded-gradient dbias")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bf16x3 split-precision ("fp32-accurate") mode: three bf16 parts per value, six part products per multiply, fp32 accumulation in TMEM
+# ---------------------------------------------------------------------------------------------------------
+
+def split_cl(t):
+    """fp32 [B,C,H,W] -> the split-precision operand: bf16 [B,3C,H,W] channels-last, channels [h(C) | m(C) | l(C)]."""
+    from spaa_b200 import ops
+    h, m, l = ops.split3(t.to("cuda:0").float())
+    return torch.cat((h, m, l), 1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def unsplit(t):
+    c = t.shape[1] // 3
+    return t[:, :c].double() + t[:, c:2 * c].double() + t[:, 2 * c:].double()
+
+
+def test_split3_parts_reconstruct_fp32():
+    from spaa_b200 import ops
+    v = synth.randn(1, "sp.v", (4, 8, 6, 5)) * torch.tensor([1e-6, 1e-3, 1.0, 37.0, 1e3, 1e-2, 5.0, 0.3]).view(1, 8, 1, 1)
+    s = split_cl(v)
+    assert (unsplit(s).float().cpu() - v).abs().max().item() == 0.0       # 3 x 8 significand bits hold an fp32 value exactly
+    packed = ops.pack_nhwc16(v[:, :3].to("cuda:0"), v[:, 3:8].to("cuda:0"), torch.bfloat16, split=True)
+    assert packed.shape == (4, 48, 6, 5)
+    got = packed[:, 0:16].double() + packed[:, 16:32].double() + packed[:, 32:48].double()
+    assert (got[:, :8].float().cpu() - v).abs().max().item() == 0.0 and got[:, 8:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(map(str, c)))
+def test_tc_split_precision_conv_forward_and_backward_data(case):
+    """Against float64 on the SAME fp32 operands (no bf16 rounding of anything): the tensor-core result must be fp32-accurate."""
+    from spaa_b200 import ops
+    ops.invalidate_packed_weights()
+    kind, cin, cout, k, stride, pad, outpad, H, W = case
+    B = 3
+    spec = ops.ConvSpec(kind, cin, cout, k, stride, pad, outpad)
+    x = synth.randn(1, "tc.x", (B, cin, H, W))
+    w = synth.randn(2, "tc.w", spec.weight_shape(), (2.0 / (cin * k * k)) ** 0.5)
+    b = synth.randn(3, "tc.b", (cout,), 0.1)
+    xd = x.double().requires_grad_(True)
+    pre = F.conv2d(xd, w.double(), b.double(), stride, pad) if kind == "conv" else F.conv_transpose2d(xd, w.double(), b.double(), stride, pad, outpad)
+    add = synth.randn(4, "tc.add", pre.shape, 0.5)
+    ref = F.relu(pre + add.double())
+    probe = ops.set_probe(lambda kind_, spec_: kind_.endswith("_tc"))
+    got = ops.conv_forward(spec, split_cl(x), w.to("cuda:0"), b.to("cuda:0"), add=split_cl(add), epi=ops.EPI_RELU, split=True)
+    assert len(probe["events"]) == 1, "the split-precision layer did not run on the tensor-core kernel"
+    ops.set_probe(None)
+    assert got.dtype == torch.bfloat16 and got.shape[1] == 3 * cout and got.is_contiguous(memory_format=torch.channels_last)
+    err = (unsplit(got).cpu() - ref).abs().max().item()
+    # the exact-fp32 CUDA-core kernel on the same operands: the yardstick for "fp32-accurate"
+    simt = ops.conv_forward(spec, x.to("cuda:0"), w.to("cuda:0"), b.to("cuda:0"), add=add.to("cuda:0"), epi=ops.EPI_RELU)
+    err_simt = (simt.double().cpu() - ref).abs().max().item()
+    print(f"split-precision fwd {case}: max abs err vs float64 {err:.2e} (CUDA-core fp32 kernel: {err_simt:.2e}, output scale {ref.abs().max().item():.2f})")
+    assert err <= max(3 * err_simt, 2e-6 * ref.abs().max().item()), (err, err_simt)
+    # backward-data with skip sum, ReLU mask and the dual-mask second output
+    cot = synth.randn(5, "tc.cot", pre.shape)
+    gx, = torch.autograd.grad((pre * cot.double()).sum(), xd)
+    extra = synth.randn(6, "tc.extra", x.shape, 0.5)
+    m, m2 = synth.randn(7, "tc.m", x.shape), synth.randn(8, "tc.m2", x.shape)
+    out2 = torch.empty_like(split_cl(x))
+    dx = ops.conv_backward_data(spec, split_cl(cot), w.to("cuda:0"), (H, W), add=split_cl(extra), mask=split_cl(m), mask_mode=ops.MASK_POS,
+                                mask2=split_cl(m2), out2=out2, split=True)
+    refb = (gx + extra.double()) * (m.double() > 0)
+    scale = max(1.0, refb.abs().max().item())
+    eb = (unsplit(dx).cpu() - refb).abs().max().item()
+    eb2 = (unsplit(out2).cpu() - refb * (m2.double() > 0)).abs().max().item()
+    print(f"split-precision bwd {case}: max abs err {eb:.2e} / out2 {eb2:.2e} (scale {scale:.2f})")
+    assert eb <= 3e-6 * scale and eb2 <= 3e-6 * scale, (eb, eb2, scale)
+
+
+def test_tc_split_precision_padded_input_and_planar_output():
+    """The boundary layers: conv1 / conv1_s read the 48-channel [x | s | x*s | 0] operand, conv6 writes fp32 planes (+ fp32 residual, ReLU, clamp),
+    conv6's backward reads the padded 3-channel cotangent, conv1's backward writes fp32 planes."""
+    from spaa_b200 import ops
+    ops.invalidate_packed_weights()
+    B, H, W = 2, 20, 24
+    x3 = synth.randn(1, "sp.x3", (B, 3, H, W))
+    s6 = synth.randn(2, "sp.s6", (B, 6, H, W))
+    packed = ops.pack_nhwc16(x3.to("cuda:0"), s6.to("cuda:0"), torch.bfloat16, split=True)
+    for name, spec, cin_off, src in (("conv1", ops.ConvSpec("conv", 3, 32, 3, 2, 1), 0, x3), ("conv1_s", ops.ConvSpec("conv", 6, 32, 3, 2, 1), 3, s6)):
+        w = synth.randn(3, "sp.w" + name, spec.weight_shape(), 0.2)
+        b = synth.randn(4, "sp.b" + name, (32,), 0.1)
+        ref = F.relu(F.conv2d(src.double(), w.double(), b.double(), 2, 1))
+        got = ops.conv_forward(spec, packed, w.to("cuda:0"), b.to("cuda:0"), epi=ops.EPI_RELU, cin_offset=cin_off, split=True)
+        e = (unsplit(got).cpu() - ref).abs().max().item()
+        assert e <= 2e-6 * max(1.0, ref.abs().max().item()), (name, e)
+        # backward of the strided layer to fp32 planes
+        cot = synth.randn(5, "sp.cot" + name, ref.shape)
+        xd = src.double().requires_grad_(True)
+        gx, = torch.autograd.grad((F.conv2d(xd, w.double(), None, 2, 1) * cot.double()).sum(), xd)
+        dx = ops.conv_backward_data(spec, split_cl(cot), w.to("cuda:0"), (H, W), out_dtype=torch.float32, split=True)
+        assert dx.dtype == torch.float32 and dx.shape == src.shape
+        e = (dx.double().cpu() - gx).abs().max().item()
+        assert e <= 3e-6 * max(1.0, gx.abs().max().item()), (name + " bwd", e)
+    spec6 = ops.ConvSpec("conv", 32, 3, 3, 1, 1)
+    x7 = synth.randn(6, "sp.x7", (B, 32, H, W)).relu()
+    w6, b6 = synth.randn(7, "sp.w6", spec6.weight_shape(), 0.1), synth.randn(8, "sp.b6", (3,), 0.1)
+    res1 = synth.randn(9, "sp.res1", (1, 3, H, W), 0.3)
+    ref = torch.clamp(F.relu(F.conv2d(x7.double(), w6.double(), b6.double(), 1, 1) + res1.double()), max=1)
+    got = ops.conv_forward(spec6, split_cl(x7), w6.to("cuda:0"), b6.to("cuda:0"), add=res1.to("cuda:0"), epi=ops.EPI_RELU | ops.EPI_CLAMP_MAX1,
+                           out_dtype=torch.float32, split=True)
+    assert got.dtype == torch.float32 and got.shape == (B, 3, H, W)
+    assert (got.double().cpu() - ref).abs().max().item() <= 2e-6
+    cot3 = synth.randn(10, "sp.cot3", (B, 3, H, W))
+    d_pk = ops.pack_nhwc16(cot3.to("cuda:0"), None, torch.bfloat16, split=True)
+    xd = x7.double().requires_grad_(True)
+    gx, = torch.autograd.grad((F.conv2d(xd, w6.double(), None, 1, 1) * cot3.double()).sum(), xd)
+    d7 = ops.conv_backward_data(spec6, d_pk, w6.to("cuda:0"), (H, W), mask=split_cl(x7), mask_mode=ops.MASK_POS, split=True)
+    e = (unsplit(d7).cpu() - gx * (x7.double() > 0)).abs().max().item()
+    assert e <= 3e-6 * max(1.0, gx.abs().max().item()), e
