@@ -184,6 +184,14 @@ int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d);
  * [cin_offset, cin_offset + cin_real) of a zero-padded d->Cin-channel NHWC activation (3-, 6-channel images padded to 16). */
 int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, int cin_real, int cin_offset, void* packed,
                               spaa_stream_t stream);
+/* Multi-tensor re-pack (training: after every optimiser step all layers' packed copies are refreshed by ONE launch instead of one launch per layer
+ * and direction).  spaa_conv_tc_pack_job writes an opaque job record (spaa_conv_tc_pack_job_bytes() bytes, HOST memory) describing the call
+ * spaa_conv_tc_pack_weights(d, w, cin_real, cin_offset, packed) would make; the caller uploads an array of such records to the device once and
+ * launches spaa_conv_tc_pack_weights_multi(jobs_dev, njobs) whenever the fp32 parameters changed.  Replaces nothing in the reference (cuDNN reads the
+ * fp32 parameters directly, models.py:223-252); it exists because the tensor-core kernels read 16-bit [tap][Cout][Cin] copies. */
+int64_t spaa_conv_tc_pack_job_bytes(void);
+int spaa_conv_tc_pack_job(const spaa_conv_desc* d, const float* w, int cin_real, int cin_offset, void* packed, void* job_host);
+int spaa_conv_tc_pack_weights_multi(const void* jobs_dev, int njobs, spaa_stream_t stream);
 int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add,
                      const void* mask, const void* mask2, void* out, void* out2, spaa_stream_t stream);
 /* Tensor-core backward-weight (training): tcgen05.mma with BOTH operands MN-major (the contraction index is the pixel),

@@ -893,6 +893,29 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
     }
 }
 
+// Multi-tensor form: ONE launch re-packs every cached layer after an optimiser step (blockIdx.y = job).  A training step used to spend 34
+// launches (one per layer and direction) on this.
+struct PackJob {
+    const float* w;
+    uint16_t* out;
+    int64_t w_ts, w_cis, w_cos, total;
+    int32_t KH, KW, Cin, cin_real, cin_off, Cout, BN, flip, f16, pad_;
+};
+__global__ void pack_weights_multi_kernel(const PackJob* __restrict__ jobs) {
+    const PackJob J = jobs[blockIdx.y];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < J.total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % J.Cin);
+        const int co = (int)((e / J.Cin) % J.BN);
+        const int tap = (int)(e / ((int64_t)J.Cin * J.BN));
+        const int r = tap / J.KW, s2 = tap - r * J.KW;
+        const int wtap = J.flip ? (J.KH - 1 - r) * J.KW + (J.KW - 1 - s2) : tap;
+        const int ci = c - J.cin_off;
+        const float v = (co < J.Cout && ci >= 0 && ci < J.cin_real) ? J.w[(int64_t)wtap * J.w_ts + (int64_t)ci * J.w_cis + (int64_t)co * J.w_cos] : 0.f;
+        if (J.f16) { const __half h = __float2half_rn(v); J.out[e] = *reinterpret_cast<const uint16_t*>(&h); }
+        else { const __nv_bfloat16 h = __float2bfloat16_rn(v); J.out[e] = *reinterpret_cast<const uint16_t*>(&h); }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -1185,6 +1208,28 @@ int spaa_conv_tc_pack_weights(const spaa_conv_desc* d, const float* w, int cin_r
         pack_weights_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w, (uint16_t*)packed, d->KH, d->KW, d->Cin, cin_real, cin_offset, d->Cout,
                                                                                       BN, d->flip, d->w_ts, d->w_cis, d->w_cos);
     SPAA_CHECK_LAUNCH("spaa_conv_tc_pack_weights");
+    return SPAA_OK;
+}
+
+int64_t spaa_conv_tc_pack_job_bytes(void) { return (int64_t)sizeof(PackJob); }
+
+int spaa_conv_tc_pack_job(const spaa_conv_desc* d, const float* w, int cin_real, int cin_offset, void* packed, void* job_host) {
+    SPAA_CHECK_ARG(d && w && packed && job_host && !d->split && cin_real > 0 && cin_offset >= 0 && cin_offset + cin_real <= d->Cin,
+                   "spaa_conv_tc_pack_job: bad arguments");
+    PackJob J;
+    memset(&J, 0, sizeof(J));
+    J.w = w; J.out = (uint16_t*)packed;
+    J.w_ts = d->w_ts; J.w_cis = d->w_cis; J.w_cos = d->w_cos; J.total = spaa_conv_tc_packed_elems(d);
+    J.KH = d->KH; J.KW = d->KW; J.Cin = d->Cin; J.cin_real = cin_real; J.cin_off = cin_offset; J.Cout = d->Cout; J.BN = bn_for(d->Cout);
+    J.flip = d->flip; J.f16 = d->in_dtype == 2 ? 1 : 0;
+    memcpy(job_host, &J, sizeof(J));
+    return SPAA_OK;
+}
+
+int spaa_conv_tc_pack_weights_multi(const void* jobs_dev, int njobs, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(jobs_dev && njobs > 0 && njobs < 65536, "spaa_conv_tc_pack_weights_multi: bad arguments");
+    pack_weights_multi_kernel<<<dim3(64, (unsigned)njobs), 256, 0, (cudaStream_t)stream>>>((const PackJob*)jobs_dev);
+    SPAA_CHECK_LAUNCH("spaa_conv_tc_pack_weights_multi");
     return SPAA_OK;
 }
 

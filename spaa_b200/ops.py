@@ -495,9 +495,44 @@ def weights_epoch() -> int:
 def invalidate_packed_weights() -> None:
     """Drop the 16-bit packed-weight cache and bump the weights epoch (call after parameters were updated in place by a raw kernel, which
     leaves their autograd version counters unchanged): engines / CUDA graphs built from the previous weights are then never reused."""
-    global _weights_epoch
+    global _weights_epoch, _repack_table
     _weights_epoch += 1
     _packed_cache.clear()
+    _repack_table = None
+
+
+_repack_table = None          # (cache keys it covers, device table of pack jobs, njobs)
+_repack_keep: list = []
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def repack_packed_weights() -> None:
+    """After an in-place parameter update by a raw kernel (FlatAdam): refresh EVERY cached 16-bit weight copy from its fp32 parameter with ONE
+    launch (spaa_conv_tc_pack_weights_multi) instead of dropping the cache and re-packing layer by layer (34 launches per training step).  The
+    packed tensors keep their addresses, so a CUDA graph that recorded this call stays valid.  Bumps the weights epoch like
+    invalidate_packed_weights()."""
+    global _weights_epoch, _repack_table
+    _weights_epoch += 1
+    for k in [k for k, v in _packed_cache.items() if v[3] is None or v[0]() is None]:      # split-precision copies / dead parameters: rebuilt lazily
+        del _packed_cache[k]
+    if not _packed_cache:
+        _repack_table = None
+        return
+    if _repack_table is None or _repack_table[0] != tuple(_packed_cache.keys()):
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the set of packed weights changed inside a CUDA-graph capture")
+        dev = next(iter(_packed_cache.values()))[2].device
+        blob = b"".join(v[3] for v in _packed_cache.values())
+        table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        _repack_table = (tuple(_packed_cache.keys()), table, len(_packed_cache))
+        _repack_keep.append((table, [v[2] for v in _packed_cache.values()]))       # a captured CUDA graph may hold these addresses
+        del _repack_keep[:-8]
+    _, table, n = _repack_table
+    lib().spaa_conv_tc_pack_weights_multi(_p(table), n, _stream()); _count()
 
 
 def _tc_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int) -> Tensor:
@@ -512,17 +547,21 @@ def _tc_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int) -> Tensor:
         return hit[2]
     L = lib()
     t = torch.empty(L.spaa_conv_tc_packed_elems(ctypes.byref(d)), dtype=torch.int16, device=w.device)
+    job = None
     if d.split:
         w6, d6 = _split_weights(d, w, cin_real, cin_off)
         L.spaa_conv_tc_pack_weights(ctypes.byref(d6), _p(w6), 6 * d.Cin, 0, _p(t), _stream()); _count()
     else:
         L.spaa_conv_tc_pack_weights(ctypes.byref(d), _p(w), cin_real, cin_off, _p(t), _stream()); _count()
+        buf = ctypes.create_string_buffer(int(L.spaa_conv_tc_pack_job_bytes()))
+        L.spaa_conv_tc_pack_job(ctypes.byref(d), _p(w), cin_real, cin_off, _p(t), buf)
+        job = buf.raw
     if len(_packed_cache) > 512:
         for k in [k for k, v in _packed_cache.items() if v[0]() is None]:
             del _packed_cache[k]
         if len(_packed_cache) > 512:
             _packed_cache.clear()
-    _packed_cache[key] = (weakref.ref(base), base._version, t)
+    _packed_cache[key] = (weakref.ref(base), base._version, t, job)
     return t
 
 

@@ -139,9 +139,10 @@ class FlatAdam:
         """Device side of a step: one Adam launch over the flat buffers with the staged scalars (CUDA-graph capturable)."""
         ops.adam_step_dev(self.param, self.grad, self.m, self.v, self.seg_end, self.dyn[2:], self.seg_wd, self.dyn[:2], beta1=self.beta1,
                           beta2=self.beta2, grad_scale=grad_scale)
-        # the raw kernel updates the parameters without touching their autograd version counters: drop the packed 16-bit copies
-        # of the weights the tensor-core convolutions cache, or the next forward would run on the previous step's weights
-        ops.invalidate_packed_weights()
+        # the raw kernel updates the parameters without touching their autograd version counters: refresh the packed 16-bit copies of the
+        # weights the tensor-core convolutions cache (one multi-tensor launch, recorded with the step's CUDA graph), or the next forward
+        # would run on the previous step's weights
+        ops.repack_packed_weights()
 
     def step(self, grad_scale: float = 1.0):
         """One Adam update with the learning rates of scheduler step `self.t` (then advances the schedule)."""
@@ -305,7 +306,7 @@ def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter,
         g = graphs.get(cfg["loss"])
         if g is not None:
             g.replay()
-            ops.invalidate_packed_weights()                         # eager code between steps (validation) must re-pack the updated weights
+            ops.bump_weights_epoch()                                # (the replay re-packed the 16-bit weight copies; attack engines built before it are stale)
         elif use_graph and eager_steps.get(cfg["loss"], 0) >= _GRAPH_WARMUP and "huber" not in cfg["loss"]:
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(device=device)
@@ -320,7 +321,7 @@ def _train_loop(model, inputs, targets, scene, cfg, opt: FlatAdam, loss_of_iter,
             keep.append(side)
             graphs[cfg["loss"]] = g
             g.replay()
-            ops.invalidate_packed_weights()
+            ops.bump_weights_epoch()
         else:
             device_step(cfg["loss"])
             eager_steps[cfg["loss"]] = eager_steps.get(cfg["loss"], 0) + 1
