@@ -199,7 +199,8 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
  * conv as for spaa_conv_bwd_weight; x (gathered operand) and dy (pointwise operand) are dense 16-bit NHWC with 16, 32, 64,
  * 128 or 256 channels, both bf16 or both fp16 (tcgen05 kind::f16 traps on mixed operand formats); cx_real / cx_off / cy_real describe zero-padded operands (real X channels
  * at [cx_off, cx_off + cx_real), real DY channels [0, cy_real)); dw is addressed by d->w_ts / w_cis (X channel) / w_cos
- * (DY channel).  Replaces cudnnConvolutionBackwardFilter for models.py:18-46,223-252 under train_network.py:304-320. */
+ * (DY channel).  d->split: x and dy point at ONE bf16 part each (Cin / Cout logical channels, pixel strides 3 * Cin / 3 * Cout) of split-precision
+ * operands; the caller launches the six part products (they all accumulate into dw).  Replaces cudnnConvolutionBackwardFilter for models.py:18-46,223-252 under train_network.py:304-320. */
 int spaa_conv_wgrad_tc_supported(const spaa_conv_desc* d);
 int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real,
                        spaa_stream_t stream);

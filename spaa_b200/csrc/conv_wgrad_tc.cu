@@ -241,8 +241,11 @@ int spaa_conv_wgrad_tc_supported(const spaa_conv_desc* d) {
     if (!okc(d->Cin) || !okc(d->Cout)) return 0;
     if (d->up != 1 || d->flip != 0 || !(d->stride == 1 || d->stride == 2)) return 0;
     if (d->KH != d->KW || d->KH > 3 || d->pad_h != d->pad_w) return 0;
-    if (d->in_cs != 1 || d->in_ps != d->Cin || (d->B > 1 && d->in_bs != (int64_t)d->Hin * d->Win * d->Cin)) return 0;
-    if (d->out_cs != 1 || d->out_ps != d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout)) return 0;
+    // split (bf16x3 split-precision operands): x / dy point at ONE part (Cin / Cout logical channels) of tensors whose pixels hold three parts
+    const int np = d->split ? 3 : 1;
+    if (d->split && d->in_dtype != 1) return 0;
+    if (d->in_cs != 1 || d->in_ps != np * d->Cin || (d->B > 1 && d->in_bs != (int64_t)d->Hin * d->Win * d->Cin * np)) return 0;
+    if (d->out_cs != 1 || d->out_ps != np * d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout * np)) return 0;
     return 1;
 }
 
@@ -382,8 +385,9 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
     }
     CUtensorMap mx, my;
     {
+        const cuuint64_t cphys = (cuuint64_t)d->in_ps;             // physical channels per pixel (3 * Cx for split-precision operands)
         cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
-        cuuint64_t strides[3] = {(cuuint64_t)Cx * 2, (cuuint64_t)d->Win * Cx * 2, (cuuint64_t)d->Hin * d->Win * Cx * 2};
+        cuuint64_t strides[3] = {cphys * 2, (cuuint64_t)d->Win * cphys * 2, (cuuint64_t)d->Hin * d->Win * cphys * 2};
         cuuint32_t box[4] = {(cuuint32_t)P.cxb, (cuuint32_t)(P.halo_w * d->stride), (cuuint32_t)(P.halo_h * d->stride), 1};
         cuuint32_t es[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         const CUtensorMapSwizzle sw = P.cxb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.cxb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -392,8 +396,9 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
     {
+        const cuuint64_t cphys = (cuuint64_t)d->out_ps;
         cuuint64_t dims[4] = {(cuuint64_t)Cy, (cuuint64_t)d->Wout, (cuuint64_t)d->Hout, (cuuint64_t)d->B};
-        cuuint64_t strides[3] = {(cuuint64_t)Cy * 2, (cuuint64_t)d->Wout * Cy * 2, (cuuint64_t)d->Hout * d->Wout * Cy * 2};
+        cuuint64_t strides[3] = {cphys * 2, (cuuint64_t)d->Wout * cphys * 2, (cuuint64_t)d->Hout * d->Wout * cphys * 2};
         cuuint32_t box[4] = {(cuuint32_t)P.cyb, (cuuint32_t)WTW, (cuuint32_t)P.tile_h, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         const CUtensorMapSwizzle sw = P.cyb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (P.cyb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

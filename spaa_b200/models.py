@@ -148,9 +148,6 @@ class _Stack:
         Wt = lambda n: _get(net, n).weight
         pg = param_grads
         s3 = _Stack.split(net)
-        if s3 and pg is not None and any(not k.startswith("skipConv1") for k in pg):
-            raise NotImplementedError("precision 'bf16x3' (split-precision tensor-core mode) implements forward and backward-data (the attack loops, inference); "
-                                      "train in 'fp32' (exact) or 'bf16'")
         hw = lambda t: (t.shape[2], t.shape[3])
         B = (d_pre6 if d_pre6 is not None else d_pre6_packed).shape[0]
 
@@ -158,7 +155,7 @@ class _Stack:
             if pg is not None and (name + ".weight") in pg:
                 if inp.shape[0] == 1 and B > 1:
                     inp = inp.expand(B, -1, -1, -1)
-                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset)
+                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset, split=s3 and inp.dtype != torch.float32)
 
         def packed_input():
             """[x | surf | 0] as one zero-padded 16-channel NHWC tensor in the gradient dtype: the X operand of the tensor-core

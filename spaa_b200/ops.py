@@ -695,46 +695,71 @@ def conv_backward_data(spec: ConvSpec, dy: Tensor, w: Tensor, in_hw, *, out: Opt
     return out
 
 
-def _dense_nhwc16(t: Tensor) -> bool:
-    return t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(memory_format=torch.channels_last) and t.shape[1] in (16, 32, 64, 128, 256)
+def _dense_nhwc16(t: Tensor, np_: int = 1) -> bool:
+    return t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(memory_format=torch.channels_last) and t.shape[1] % np_ == 0 and \
+        t.shape[1] // np_ in (16, 32, 64, 128, 256)
 
 
-def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor], *, x_offset: int = 0) -> None:
+_SPLIT_WGRAD_PARTS = ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0))        # (x part, dy part) of the six part products, smallest first
+
+
+def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor], *, x_offset: int = 0, split: bool = False) -> None:
     """dw += d(loss)/d(weight), db += d(loss)/d(bias); dw/db are fp32 accumulators in the parameter's own layout.
     16-bit dense NHWC operands go to the tcgen05 backward-weight kernel; `x` / `dy` may then be zero-padded to 16 channels
-    (the layer's real input channels sit at [x_offset, x_offset + spec.cin) of `x`, the real output channels at [0, spec.cout) of `dy`)."""
+    (the layer's real input channels sit at [x_offset, x_offset + spec.cin) of `x`, the real output channels at [0, spec.cout) of `dy`).
+    split: bf16x3 split-precision operands (three bf16 parts per logical channel): the six leading part products are six launches of the same
+    kernel on the parts, all accumulating into dw."""
     _need_cuda(x, dy, dw)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
+    np_ = 3 if split else 1
     d = ConvDesc()
     d.KH = d.KW = spec.k
     d.stride, d.up, d.pad_h, d.pad_w, d.flip = spec.stride, 1, spec.pad, spec.pad, 0
     d.w_ts = 1
     L = lib()
-    use_tc = TC_ENABLED and _dense_nhwc16(x) and _dense_nhwc16(dy) and x.dtype == dy.dtype      # tcgen05 kind::f16: both operands one format
+    use_tc = TC_ENABLED and _dense_nhwc16(x, np_) and _dense_nhwc16(dy, np_) and x.dtype == dy.dtype      # tcgen05 kind::f16: both operands one format
+    if split and not use_tc:
+        raise RuntimeError("split-precision (bf16x3) operands exist on the tensor-core path only")
+    cx_l, cy_l = x.shape[1] // np_, dy.shape[1] // np_                     # logical (per-part) channel counts
     if not use_tc and (x.shape[1] != spec.cin or dy.shape[1] != spec.cout):
         raise RuntimeError("zero-padded channel operands are only implemented on the tensor-core backward-weight path")
     if spec.kind == "conv":
-        d.Cin, d.Cout = x.shape[1], dy.shape[1]
+        d.Cin, d.Cout = cx_l, cy_l
         d.w_cos, d.w_cis = dw.stride(0), dw.stride(1)
-        _fill_desc(d, x, dy, None, None)
+        _fill_desc(d, x, dy, None, None, split)
         gathered, pointwise, g_real, g_off, p_real = x, dy, spec.cin, x_offset, spec.cout
     else:
         # dWt[ci,co,r,s] = sum in[iy,ci] * dOut[iy*s-p+r, co]: the gathered operand is dOut, the pointwise one is `x`
-        d.Cin, d.Cout = dy.shape[1], x.shape[1]
+        d.Cin, d.Cout = cy_l, cx_l
         d.w_cis, d.w_cos = dw.stride(1), dw.stride(0)
-        _fill_desc(d, dy, x, None, None)
+        _fill_desc(d, dy, x, None, None, split)
         gathered, pointwise, g_real, g_off, p_real = dy, x, spec.cout, 0, spec.cin
     if use_tc and L.spaa_conv_wgrad_tc_supported(ctypes.byref(d)) == 1:
         with _Probe("bwd_weight_tc", spec):
-            L.spaa_conv_wgrad_tc(ctypes.byref(d), _p(gathered), _p(pointwise), _p(dw), g_real, g_off, p_real, _stream())
-        _count()
+            if split:
+                cg, cp = gathered.shape[1] // 3, pointwise.shape[1] // 3
+                for pg_, pp_ in _SPLIT_WGRAD_PARTS:
+                    L.spaa_conv_wgrad_tc(ctypes.byref(d), ctypes.c_void_p(gathered.data_ptr() + pg_ * cg * 2), ctypes.c_void_p(pointwise.data_ptr() + pp_ * cp * 2),
+                                         _p(dw), g_real, g_off, p_real, _stream())
+                    _count()
+            else:
+                L.spaa_conv_wgrad_tc(ctypes.byref(d), _p(gathered), _p(pointwise), _p(dw), g_real, g_off, p_real, _stream())
+                _count()
         if db is not None:
-            if spec.kind == "conv":
+            if split:
+                # bias gradient = sum over pixels of dy = of its three parts (real channels at [0, spec.cout) of each part)
+                bs, ps, cs = _act_strides(dy)
+                for part in range(3):
+                    L.spaa_channel_sum(ctypes.c_void_p(dy.data_ptr() + part * cy_l * 2), _dt(dy), dy.shape[0], db.numel(), dy.shape[2] * dy.shape[3], bs, ps, cs,
+                                       _p(db), _stream()); _count()
+            elif spec.kind == "conv":
                 L.spaa_channel_sum_nhwc16(_p(dy), _dt(dy), dy.shape[0] * dy.shape[2] * dy.shape[3], dy.shape[1], _p(_bias_scratch(db, dy.shape[1])), _stream()); _count()
                 _bias_fold(db, dy.shape[1])
             else:
                 channel_sum(dy, db)
         return
+    if split:
+        raise RuntimeError("split-precision backward-weight: this layer shape is not covered by the tensor-core kernel")
     if x.shape[1] != spec.cin or dy.shape[1] != spec.cout:
         raise RuntimeError("zero-padded channel operands are only implemented on the tensor-core backward-weight path")
     if spec.kind == "conv":

@@ -314,3 +314,26 @@ def test_tc_split_precision_padded_input_and_planar_output():
     d7 = ops.conv_backward_data(spec6, d_pk, w6.to("cuda:0"), (H, W), mask=split_cl(x7), mask_mode=ops.MASK_POS, split=True)
     e = (unsplit(d7).cpu() - gx * (x7.double() > 0)).abs().max().item()
     assert e <= 3e-6 * max(1.0, gx.abs().max().item()), e
+
+
+@pytest.mark.parametrize("case", WG_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_tc_split_precision_backward_weight(case):
+    """Six launches of the tcgen05 backward-weight kernel on the bf16 parts vs float64 autograd on the same fp32 operands."""
+    from spaa_b200 import ops
+    kind, cin, cout, k, stride, pad, outpad, H, W = case
+    B = 3
+    spec = ops.ConvSpec(kind, cin, cout, k, stride, pad, outpad)
+    x = synth.randn(31, "wg.x", (B, cin, H, W))
+    w = torch.zeros(spec.weight_shape(), dtype=torch.double, requires_grad=True)
+    pre = F.conv2d(x.double(), w, None, stride, pad) if kind == "conv" else F.conv_transpose2d(x.double(), w, None, stride, pad, outpad)
+    dy = synth.randn(32, "wg.dy", pre.shape)
+    gw, = torch.autograd.grad((pre * dy.double()).sum(), w)
+    dw = torch.zeros(spec.weight_shape(), device="cuda:0")
+    db = torch.zeros(cout, device="cuda:0")
+    ops.conv_backward_weight(spec, split_cl(x), split_cl(dy), dw, db, split=True)
+    scale = gw.abs().max().item()
+    e = (dw.double().cpu() - gw).abs().max().item()
+    print(f"split-precision dW {case}: max abs err {e:.2e} of {scale:.2e}")
+    assert e <= 3e-6 * scale, (e, scale)              # sums of up to 10^4 products: fp32-level
+    ref_b = dy.double().sum((0, 2, 3))
+    assert (db.double().cpu() - ref_b).abs().max().item() <= 1e-5 * max(1.0, ref_b.abs().max().item())

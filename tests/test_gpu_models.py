@@ -778,3 +778,44 @@ def test_percal_adversary_original_variant_vs_reference(golden):
     assert changed >= 1, "no variant produced an adversarial image: the fixture does not exercise the best-so-far copy"
     with pytest.raises(ValueError):
         atk.adversary(net, imgs + 1.0, true_lab, False)
+
+
+def test_bf16x3_split_precision_mode_meets_the_fp32_fixtures(golden):
+    """precision='bf16x3' (tensor cores, three bf16 parts per value, fp32 accumulation in TMEM) against the SAME fixtures and tolerances as the exact
+    fp32 mode: PCNet / CompenNet++ outputs and input gradients (models.npz), the training loss trajectory and parameters after 3 Adam steps (train.npz)."""
+    from spaa_b200 import models, ops, train_network as tn
+    g = golden("models")
+    P = synth.pcnet_params(31, CAM_HW)
+    m = models.set_precision(make_pcnet(P, CAM_HW), "bf16x3")
+    prj = synth.textured(32, "pc.prj", (2, 3, *PRJ_HW)).to(dev()).requires_grad_(True)
+    scene = synth.textured(33, "pc.s", (1, 3, *CAM_HW)).expand(2, -1, -1, -1).to(dev())
+    probe = ops.set_probe(lambda kind, spec: kind.endswith("_tc"))
+    y = m(prj, scene)
+    close(y, g["pcnet_y"], 1e-5, 0, "pcnet y (bf16x3)")
+    cot = synth.randn(34, "pc.cot", y.shape).to(dev())
+    (y * cot).sum().backward()
+    n_tc = len(probe["events"])
+    ops.set_probe(None)
+    assert n_tc >= 40, f"only {n_tc} launches went through the tcgen05 kernels"
+    close(prj.grad, g["pcnet_gprj"], 2e-5, 1e-4, "pcnet gprj (bf16x3)")
+    check_param_grads(g, "pcnet", m)
+    C = synth.compennet_pp_params(37)
+    cm = models.set_precision(make_cpp(C, PRJ_HW), "bf16x3")
+    cam = synth.textured(38, "cpp.cam", (2, 3, *CAM_HW)).to(dev()).requires_grad_(True)
+    yc = cm(cam, scene)
+    close(yc, g["cpp_y"], 1e-5, 0, "cpp y (bf16x3)")
+    (yc * synth.randn(39, "cpp.cot", yc.shape).to(dev())).sum().backward()
+    close(cam.grad, g["cpp_gcam"], 2e-5, 1e-4, "cpp gcam (bf16x3)")
+    check_param_grads(g, "cpp", cm)
+    # training trajectory
+    gt = golden("train")
+    N = 6
+    Pt = synth.pcnet_params(81, CAM_HW)
+    mt = nn.DataParallel(models.set_precision(make_pcnet(Pt, CAM_HW), "bf16x3"), device_ids=[0])
+    cfg = tn.AttrDict(device="cuda:0", data_root=None, setup_name="synth", model_name="PCNet", num_train=N, batch_size=4, max_iters=3, lr=1e-3,
+                      lr_drop_ratio=0.2, lr_drop_rate=800, l2_reg=1e-4, plot_on=False, train_plot_rate=50, valid_rate=200, loss="l1+ssim")
+    random.seed(5)
+    tn.train_pcnet(mt, dict(cam_scene=synth.textured(83, "tr.scene", (1, 3, *CAM_HW)), cam_train=synth.textured(84, "tr.cam", (N, 3, *CAM_HW)),
+                            prj_train=synth.textured(82, "tr.prj", (N, 3, *PRJ_HW)), mask=Pt["mask"]), None, cfg, verbose=False)
+    close(cfg["loss_history"][:, 0], gt["pcnet_losses"], 1e-4, 0, "pcnet losses (bf16x3)")
+    _check_after(gt, "pcnet", mt.module, Pt, 3e-4)
