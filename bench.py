@@ -194,13 +194,13 @@ def reference_cpu_spaa(sample_B: int, warmup: int, steps: int, budget_s: float):
 def run_reference(args):
     """Reference arm: the reference's own `spaa` (projector_based_attack.py:212-339, unmodified, imported from baseline/_ref) on the box's host cores,
     all threads, on the FULL bench workload (32 targets, resnet18, 256x256 / 240x320).  One CPU iteration of that batch takes ~10-15 s, so the
-    run is bounded in time, not in batch: 1 warm-up iteration, then as many of the requested `--steps` as fit in ~150 s (at least 2)."""
+    run is bounded in time, not in batch: the requested warm-up iterations (at most 5), then as many of the requested `--steps` as fit in ~150 s (at least 2)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    warmup = max(1, min(args.warmup, 1))
+    warmup = max(1, min(args.warmup, 5))
     sec, n, kind = reference_cpu_spaa(BATCH, warmup, max(2, args.steps), budget_s=float(os.environ.get("SPAA_BENCH_REF_BUDGET_S", "150")))
     its = 1.0 / sec
     sample = (f"full batch of {BATCH} targets x {n} timed iterations (+{warmup} warm-up) of the "
@@ -674,6 +674,11 @@ def run_ours(args):
         if world == 1 and not args.skip_side_legs and args.train_precision != "fp32":
             t32 = train_leg(dev, rank, world, 3, 1, "fp32")
             train["fp32_mode"] = {"img_per_s": t32["value"], "ms_per_step": t32["phases"]["l1+ssim"]["ms_per_step"]}
+            try:                                      # fp32-accurate training on the tensor cores (split-precision operands, forward + backward-data + backward-weight)
+                tx3 = train_leg(dev, rank, world, 5, 1, "bf16x3", phases=(("l1+ssim", 401),))
+                train["bf16x3_mode"] = {"img_per_s": tx3["value"], "ms_per_step": tx3["phases"]["l1+ssim"]["ms_per_step"]}
+            except Exception as e:
+                train["bf16x3_mode"] = {"unavailable": f"{type(e).__name__}: {e}"}
     sweep = None
     if not args.skip_sweep:
         try:

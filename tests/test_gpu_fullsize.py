@@ -124,7 +124,12 @@ def test_pcnet_fullsize_per_layer_and_gradient(precision, tol_out, tol_layer, to
     close_but_ramp(ref[:2], ref_cpu, 2e-6, what="GPU oracle vs CPU oracle")
     close_but_ramp(cam[:2], ref_cpu, tol_out, what="PCNet output vs CPU oracle")
     # ---- gradient wrt the projector image through the nn.Module API (one autograd node per network) ----
-    cot = synth.randn(7, "full.cot", (B, 3, *CAM_HW)).to(dev())
+    # The output activation clamp(relu(.), max=1) passes the cotangent where 0 < out < 1.  Outputs within rounding of 0 or 1 (the random-init net
+    # saturates many pixels: about one of the 7.4 M outputs of this batch per 1e-7 of margin) flip that mask between two exact-fp32 evaluations and
+    # switch a pixel's whole O(1) cotangent on or off -- measured: half of the 32 samples differ from the GPU oracle by 2e-4 .. 4e-3 relative because
+    # of it, identically in the fp32 and the bf16x3 mode.  The comparison therefore uses a cotangent that is zero where the oracle's output is within
+    # 1e-4 of a threshold; ReLU flips INSIDE the net (one receptive field each, ~1e-5 relative) remain and are covered by the tolerance.
+    cot = synth.randn(7, "full.cot", (B, 3, *CAM_HW)).to(dev()) * ((ref > 1e-4) & (ref < 1 - 1e-4)).float()
     x = prj_d.clone().requires_grad_(True)
     y = m(torch.clamp(x, 0, 1), scene_d.expand(B, -1, -1, -1))
     assert maxerr(y, cam) <= (0 if precision in ("fp32", "bf16x3") else tol_out)
@@ -135,24 +140,15 @@ def test_pcnet_fullsize_per_layer_and_gradient(precision, tol_out, tol_layer, to
         gr, = torch.autograd.grad((yr * cot).sum(), xr)
     rel_b = ((g - gr).double().flatten(1).norm(dim=1) / gr.double().flatten(1).norm(dim=1))
     cos = torch.nn.functional.cosine_similarity(g.flatten(1).double(), gr.flatten(1).double(), dim=1).min().item()
-    # How far apart are two exact-fp32 evaluations of the SAME oracle?  ReLU / clamp masks of values within rounding of a threshold flip between
-    # evaluation orders.  Inside the net such a flip switches one receptive field of gradient on or off (1e-5-level relative change of a sample's
-    # gradient); at the OUTPUT clamp (relu(.) <= 1: values within 1e-7 of 0 or 1, about one of the 7.4 M outputs of this batch) it switches that
-    # pixel's whole O(1) cotangent and changes the sample's gradient by ~1e-2 relative, locally.  So: the CPU-vs-GPU distance of the oracle itself
-    # (2-sample slice) calibrates the typical level, and a few samples of the batch may carry one output-clamp flip each.
+    # the same distance between two evaluations of the ORACLE (CPU = the reference's arithmetic, vs GPU), 2-sample slice: what "equal" can mean
     xc = prj[:2].clone().requires_grad_(True)
     yc = O.pcnet(P, torch.clamp(xc, 0, 1), scene.expand(2, -1, -1, -1), CAM_HW)
     gc, = torch.autograd.grad((yc * cot[:2].cpu()).sum(), xc)
     rel_oracle = ((gr[:2].cpu() - gc).double().norm() / gc.double().norm()).item()
     tol_s = max(tol_grad, 3 * rel_oracle)
-    flipped = rel_b > tol_s
-    print(f"fullsize[{precision}] d/dprj per-sample relative Frobenius err: median {rel_b.median().item():.2e}, max {rel_b.max().item():.2e}, {int(flipped.sum())} of {B} "
-          f"samples above {tol_s:.1e}; min cosine {cos:.6f}; oracle GPU vs oracle CPU {rel_oracle:.2e}")
-    n_flip_ok = 4 if precision in ("fp32", "bf16x3") else 0
-    assert int(flipped.sum()) <= n_flip_ok and rel_b.max().item() <= max(0.05, tol_s) and cos >= 1 - 2 * max(tol_grad, 2e-3), (rel_b.tolist(), cos)
-    for bi in torch.nonzero(flipped).flatten().tolist():          # a flipped sample differs LOCALLY (one output pixel's cone), not globally
-        e = (g[bi] - gr[bi]).abs()
-        assert (e > 1e-4 * gr[bi].abs().max()).float().mean().item() <= 0.05, f"sample {bi}: the gradient differs over {(e > 1e-4 * gr[bi].abs().max()).float().mean().item():.3f} of the image"
+    print(f"fullsize[{precision}] d/dprj per-sample relative Frobenius err: median {rel_b.median().item():.2e}, max {rel_b.max().item():.2e} (bound {tol_s:.1e}); "
+          f"min cosine {cos:.6f}; oracle GPU vs oracle CPU {rel_oracle:.2e}")
+    assert rel_b.max().item() <= tol_s and cos >= 1 - 2 * tol_grad, (rel_b.tolist(), cos)
 
 
 class RefClf:

