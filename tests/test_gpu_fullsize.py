@@ -84,6 +84,38 @@ def fused_forward(m, prj, scene):
     return cam, S
 
 
+def as_saved(t, precision):
+    """An fp32 NCHW activation of the oracle in the storage format of `precision` (what _Stack.forward would have saved)."""
+    from spaa_b200 import ops
+    if precision == "fp32":
+        return t.contiguous()
+    if precision == "bf16x3":
+        h, m_, l = ops.split3(t.float())
+        return torch.cat((h, m_, l), 1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    return t.to(torch.float16 if precision == "fp16" else torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+def backward_with_given_masks(m, S, cot_pre6, scene, prj, precision):
+    """The backward schedule of SpaaAttack._iteration: d(loss)/d(prj) for the cotangent `cot_pre6` of conv6's pre-activation, with the ReLU masks
+    taken from the activations in `S`."""
+    from spaa_b200 import ops
+    from spaa_b200.models import _Stack
+    sh = m.shading_net
+    grid = m.warping_net.planar_grid(PRJ_HW).detach()
+    with torch.no_grad():
+        if precision == "fp32":
+            dxw, dsf, _ = _Stack.backward(sh, S, cot_pre6.contiguous(), need_dx=True, surf_grad_channels=(3, 6))
+        else:
+            if precision == "bf16x3":
+                d_pk = ops.pack_nhwc16(cot_pre6.contiguous(), None, torch.bfloat16, split=True)
+            else:
+                d_pk = torch.empty((cot_pre6.shape[0], 16, *CAM_HW), dtype=torch.bfloat16, device=cot_pre6.device, memory_format=torch.channels_last)
+                ops.select_cotangent_packed(cot_pre6.contiguous(), None, None, None, 0, d_pk)
+            dxw, dsf, _ = _Stack.backward(sh, S, None, need_dx=True, surf_grad_channels=(3, 6), d_pre6_packed=d_pk)
+        dprj = ops.grid_sample_bwd_input(dxw, grid, PRJ_HW, mask=m.flat_mask(), dout2=dsf, rough=scene)
+    return dprj * ((prj >= 0) & (prj <= 1)).float()            # backward of clamp(prj, 0, 1) (torch passes the gradient on the closed interval)
+
+
 # precision, PCNet output bound (max-abs), per-layer bound relative to the layer's largest activation, d/dprj relative Frobenius bound
 MODES = [("fp32", 1e-5, 1e-5, 2e-4), ("bf16x3", 1e-5, 1e-5, 2e-4), ("fp16", 2e-3, 4e-3, 0.06), ("bf16", 4e-3, 3e-2, 0.15)]
 
@@ -123,32 +155,35 @@ def test_pcnet_fullsize_per_layer_and_gradient(precision, tol_out, tol_layer, to
         ref_cpu = O.pcnet(P, prj[:2].clamp(0, 1), scene.expand(2, -1, -1, -1), CAM_HW)
     close_but_ramp(ref[:2], ref_cpu, 2e-6, what="GPU oracle vs CPU oracle")
     close_but_ramp(cam[:2], ref_cpu, tol_out, what="PCNet output vs CPU oracle")
-    # ---- gradient wrt the projector image through the nn.Module API (one autograd node per network) ----
-    # The output activation clamp(relu(.), max=1) passes the cotangent where 0 < out < 1.  Outputs within rounding of 0 or 1 (the random-init net
-    # saturates many pixels: about one of the 7.4 M outputs of this batch per 1e-7 of margin) flip that mask between two exact-fp32 evaluations and
-    # switch a pixel's whole O(1) cotangent on or off -- measured: half of the 32 samples differ from the GPU oracle by 2e-4 .. 4e-3 relative because
-    # of it, identically in the fp32 and the bf16x3 mode.  The comparison therefore uses a cotangent that is zero where the oracle's output is within
-    # 1e-4 of a threshold; ReLU flips INSIDE the net (one receptive field each, ~1e-5 relative) remain and are covered by the tolerance.
+    # ---- backward: d(loss)/d(prj) -----------------------------------------------------------------------------------------------------
+    # A cotangent that is zero where the oracle's output is within 1e-4 of the output clamp's thresholds (0 < out < 1 passes the gradient).
     cot = synth.randn(7, "full.cot", (B, 3, *CAM_HW)).to(dev()) * ((ref > 1e-4) & (ref < 1 - 1e-4)).float()
-    x = prj_d.clone().requires_grad_(True)
-    y = m(torch.clamp(x, 0, 1), scene_d.expand(B, -1, -1, -1))
-    assert maxerr(y, cam) <= (0 if precision in ("fp32", "bf16x3") else tol_out)
-    g, = torch.autograd.grad((y * cot).sum(), x)
     xr = prj_d.clone().requires_grad_(True)
     with torch.enable_grad():
         yr = O.pcnet(Pd, torch.clamp(xr, 0, 1), scene_d.expand(B, -1, -1, -1), CAM_HW)
         gr, = torch.autograd.grad((yr * cot).sum(), xr)
+    # (1) ARITHMETIC of the backward kernels: the same ReLU masks on both sides -- the saved activations are replaced by the oracle's (in this
+    # precision's storage format), so no mask can differ and only rounding remains
+    S2 = dict(S)
+    for k in LAYERS:
+        S2[k] = as_saved(tr[k], precision)
+    g_forced = backward_with_given_masks(m, S2, cot, scene_d, prj_d, precision)
+    rel_f = ((g_forced - gr).double().flatten(1).norm(dim=1) / gr.double().flatten(1).norm(dim=1))
+    tol_forced = {"fp32": 2e-5, "bf16x3": 2e-5}.get(precision, tol_grad)
+    print(f"fullsize[{precision}] d/dprj with the oracle's ReLU masks: per-sample relative Frobenius err median {rel_f.median().item():.2e}, max {rel_f.max().item():.2e} (bound {tol_forced:.0e})")
+    assert rel_f.max().item() <= tol_forced, rel_f.tolist()
+    # (2) END TO END through the nn.Module API (one autograd node per network), masks from our own forward.  Every sample has a handful of the
+    # 12 M pre-activations within the fp32 evaluation noise (~1e-6) of zero; their ReLU masks differ between any two fp32 evaluation orders and
+    # each switches one neuron's gradient path on or off: measured 2e-4 median / 4e-3 max per-sample relative difference to the cuDNN-fp32 oracle
+    # in BOTH the fp32 and the bf16x3 mode, localised and with cosine > 0.99999 -- not an arithmetic error (see (1)).
+    x = prj_d.clone().requires_grad_(True)
+    y = m(torch.clamp(x, 0, 1), scene_d.expand(B, -1, -1, -1))
+    assert maxerr(y, cam) <= (0 if precision in ("fp32", "bf16x3") else tol_out)
+    g, = torch.autograd.grad((y * cot).sum(), x)
     rel_b = ((g - gr).double().flatten(1).norm(dim=1) / gr.double().flatten(1).norm(dim=1))
     cos = torch.nn.functional.cosine_similarity(g.flatten(1).double(), gr.flatten(1).double(), dim=1).min().item()
-    # the same distance between two evaluations of the ORACLE (CPU = the reference's arithmetic, vs GPU), 2-sample slice: what "equal" can mean
-    xc = prj[:2].clone().requires_grad_(True)
-    yc = O.pcnet(P, torch.clamp(xc, 0, 1), scene.expand(2, -1, -1, -1), CAM_HW)
-    gc, = torch.autograd.grad((yc * cot[:2].cpu()).sum(), xc)
-    rel_oracle = ((gr[:2].cpu() - gc).double().norm() / gc.double().norm()).item()
-    tol_s = max(tol_grad, 3 * rel_oracle)
-    print(f"fullsize[{precision}] d/dprj per-sample relative Frobenius err: median {rel_b.median().item():.2e}, max {rel_b.max().item():.2e} (bound {tol_s:.1e}); "
-          f"min cosine {cos:.6f}; oracle GPU vs oracle CPU {rel_oracle:.2e}")
-    assert rel_b.max().item() <= tol_s and cos >= 1 - 2 * tol_grad, (rel_b.tolist(), cos)
+    print(f"fullsize[{precision}] d/dprj end to end: per-sample relative Frobenius err median {rel_b.median().item():.2e}, max {rel_b.max().item():.2e}; min cosine {cos:.6f}")
+    assert rel_b.max().item() <= max(2e-2, tol_grad) and rel_b.median().item() <= max(2e-3, tol_grad) and cos >= 1 - max(1e-4, 2 * tol_grad), (rel_b.tolist(), cos)
 
 
 class RefClf:
