@@ -282,10 +282,11 @@ def train_leg(dev, rank, world, steps, warmup, precision="bf16", dp_mode="weak",
         ms = t.item() / steps
         out[phase] = {"img_per_s": gb / (ms / 1e3), "ms_per_step": ms}
     return {"metric": "pcnet_train_img_per_sec", "value": out["l1+ssim"]["img_per_s"], "unit": "img/s", "phases": out, "steps": steps,
-            "batch_per_gpu": gb / world, "global_batch": gb, "scaling": "weak" if dp_mode == "weak" else "strong", "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[precision],
+            "batch_per_gpu": gb / world, "global_batch": gb, "scaling": "weak" if dp_mode == "weak" else "strong", "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "bf16x3": "bf16x3 (fp32-accurate)"}[precision],
             "note": "train_pcnet (3 Adam groups in one flat fp32 bucket, one NCCL all-reduce per step when N>1); " +
                     ("bf16 activations / gradients on tcgen05 (forward, backward-data, backward-weight), fp32 master weights and accumulation; "
-                     if precision != "fp32" else "exact fp32 CUDA-core convolutions; ") + "value = L1+SSIM phase (1600 of the reference's 2000 steps)"}
+                     if precision not in ("fp32", "bf16x3") else ("exact fp32 CUDA-core convolutions; " if precision == "fp32" else
+                                                                  "split-precision (three bf16 parts per value) fp32-accurate convolutions on tcgen05; ")) + "value = L1+SSIM phase (1600 of the reference's 2000 steps)"}
 
 
 def torch_cuda_train_step_ms(dev, steps=5, batch=TRAIN_BATCH, warm=3):
@@ -699,7 +700,7 @@ def run_ours(args):
     peak_tf, peak_name = (pk["bf16_tflops"], "burst") if burst else (pk["bf16_tflops_sustained"], "sustained")
     line = {"metric": "spaa_attack_iters_per_sec", "value": its, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "config": config_dict(world), "arm": arm_dict(args.precision, fold_bn),
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16", "bf16x3": "bf16x3"}[args.precision], "data": "synthetic", "config": config_dict(world), "arm": arm_dict(args.precision, fold_bn),
             "sample_iters_per_sec": its * BATCH, "classifier_ms_per_step": clf_ms, "classifier_timing": clf_how,
             "clocks": clk, "gpu_launches": launches,
             "e2e": {"value": e2e_its, "unit": "it/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
@@ -813,7 +814,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16", "fp16"],
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16", "fp16", "bf16x3"],
                     help="fp16 (default): tcgen05 convolutions, fp16 activations / bf16 gradients, fp32 accumulation -- the 16-bit mode that meets "
                          "BASELINE.json's 2e-3 bar; bf16: pure bf16 storage; fp32: exact CUDA-core convolutions (1e-5 parity mode)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
