@@ -409,14 +409,27 @@ def perc_al_compennet_pp(compennet_pp, classifier, imgnet_labels, target_idx, ta
 # multi-GPU: attack jobs are independent -- shard them over ranks, no data-path collective
 # ------------------------------------------------------------------------------------------------------------
 
-def shard_jobs(jobs, rank: Optional[int] = None, world: Optional[int] = None):
-    """Round-robin share of an attack sweep (the (setup, classifier, stealth_loss, d_thr, targets) tuples that
-    run_projector_based_attack iterates serially, projector_based_attack.py:83-129) for this rank.
-    Returns [(global job index, job), ...]."""
+def shard_jobs(jobs, rank: Optional[int] = None, world: Optional[int] = None, costs=None):
+    """This rank's share of an attack sweep (the (setup, classifier, stealth_loss, d_thr, targets) tuples that
+    run_projector_based_attack iterates serially, projector_based_attack.py:83-129).  Returns [(global job index, job), ...].
+    Default: round-robin.  costs (one relative cost per job, the same list on every rank): longest-processing-time-first -- jobs in order of
+    decreasing cost, each to the least loaded rank (ties: lowest rank; deterministic, so every rank computes the same partition without a
+    collective) -- a vgg16 job costs ~3x a resnet18 job, and round-robin leaves the fastest rank idle for a third of the sweep."""
     import torch.distributed as dist
     if rank is None or world is None:
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
-    return [(i, jobs[i]) for i in range(rank, len(jobs), world)]
+    if costs is None:
+        return [(i, jobs[i]) for i in range(rank, len(jobs), world)]
+    if len(costs) != len(jobs):
+        raise ValueError("shard_jobs: one cost per job")
+    load = [0.0] * world
+    mine = []
+    for i in sorted(range(len(jobs)), key=lambda i: (-float(costs[i]), i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        load[r] += float(costs[i])
+        if r == rank:
+            mine.append(i)
+    return [(i, jobs[i]) for i in sorted(mine)]
 
 
 def gather_job_results(local_results, n_jobs: int):
@@ -452,7 +465,7 @@ def to_attacker_cfg_str(attacker_name: str):
 
 
 def run_attack_sweep(jobs, device, *, attacker_name: str = "SPAA", iters: int = 50, precision: Optional[str] = None, save: bool = True,
-                     rank: Optional[int] = None, world: Optional[int] = None):
+                     rank: Optional[int] = None, world: Optional[int] = None, costs=None):
     """The job loop of run_projector_based_attack (projector_based_attack.py:83-141) for models that are already trained, sharded over ranks.
 
     jobs: list of dicts, one per (setup, stealth_loss, d_thr, classifier) cell of the reference's nested loops:
@@ -470,7 +483,7 @@ def run_attack_sweep(jobs, device, *, attacker_name: str = "SPAA", iters: int = 
     assert attacker_name in ("SPAA", "PerC-AL+CompenNet++"), f"{attacker_name} not supported!"
     cfg_str = to_attacker_cfg_str(attacker_name)[0]
     out = []
-    for ji, job in shard_jobs(jobs, rank, world):
+    for ji, job in shard_jobs(jobs, rank, world, costs):           # costs: optional relative job costs for a balanced static partition
         scene = expand_4d(job["cam_scene"]).to(device)
         setup, clf = job["setup_info"], job["classifier"]
         cp_sz = setup["classifier_crop_sz"]

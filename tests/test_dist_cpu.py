@@ -85,3 +85,21 @@ def test_sharding_single_process_defaults():
     assert shard_jobs(jobs) == list(enumerate(jobs))
     assert shard_jobs(jobs, 1, 2) == [(1, "b"), (3, "d")]
     assert gather_job_results([(i, j.upper()) for i, j in shard_jobs(jobs)], 5) == list("ABCDE")
+
+
+def test_shard_jobs_cost_balanced_partition_is_deterministic_and_complete():
+    """The cost-aware job partition (longest-processing-time-first) of an attack sweep: every rank computes it locally, the shares are disjoint,
+    cover the sweep and are better balanced than round-robin for the 3-classifier cost mix."""
+    from spaa_b200.projector_based_attack import shard_jobs
+    jobs = [(c, s) for s in range(10) for c in ("resnet18", "vgg16", "inception_v3")]
+    cost = {"resnet18": 1.0, "inception_v3": 2.2, "vgg16": 2.8}
+    costs = [cost[c] for c, _ in jobs]
+    for world in (1, 2, 4, 8):
+        parts = [shard_jobs(jobs, r, world, costs) for r in range(world)]
+        idx = sorted(i for p in parts for i, _ in p)
+        assert idx == list(range(len(jobs)))
+        assert parts == [shard_jobs(jobs, r, world, costs) for r in range(world)]
+        load = [sum(costs[i] for i, _ in p) for p in parts]
+        rr = [sum(costs[i] for i in range(r, len(jobs), world)) for r in range(world)]
+        assert max(load) <= max(rr) + 1e-9 and max(load) - min(load) <= 2.8 + 1e-9, (world, load, rr)
+    assert shard_jobs(jobs, 1, 4) == [(i, jobs[i]) for i in range(1, 30, 4)]            # default stays round-robin

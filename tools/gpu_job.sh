@@ -1,13 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_multi.py -q -m gpu -s > gpurun_out/r2_multi.log 2>&1
-grep -n "^FAILED\|^E  \|passed\|failed\|skipped" gpurun_out/r2_multi.log | cut -c1-300
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_b_2gpu.json 2> gpurun_out/r2_b_2gpu.err
-tail -4 gpurun_out/r2_b_2gpu.err | cut -c1-300
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_b_2gpu.json').read().strip().splitlines()[-1])
-print(d['value'], d['n_gpus'], d['e2e']['value'], d['train']['value'], d['train']['strong'], d['sweep'])
-PY
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/r2_b_2gpu_ref.json 2> gpurun_out/r2_b_2gpu_ref.err
-wc -l gpurun_out/r2_b_2gpu_ref.json; tail -2 gpurun_out/r2_b_2gpu_ref.err | cut -c1-200
+CMD="python bench.py --steps 2 --warmup 3 --no-graph --skip-train --skip-side-legs --skip-cpu-baseline --skip-sweep --skip-cold"
+$CMD > gpurun_out/plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_r2.csv $CMD > gpurun_out/ncu1.log 2>&1
+echo "launch list rc=$?"; wc -l gpurun_out/launches_r2.csv
+CMD2="python tools/kbench.py --profile"
+$CMD2 > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_halo -o gpurun_out/r2_halo $CMD2 > gpurun_out/ncu2.log 2>&1
+echo "set full rc=$?"; ls -la gpurun_out/r2_halo.ncu-rep; tail -3 gpurun_out/ncu2.log
+python tools/kbench.py --markdown > gpurun_out/r2_kbench.md 2> gpurun_out/r2_kbench.err; tail -45 gpurun_out/r2_kbench.md
