@@ -32,8 +32,8 @@ STEALTH, D_THR = "camdE_caml2", 5.0
 # algorithmic work of the dominant layer family (conv4 / conv4_s / conv5 and their backward-data passes):
 # 2 * Hout * Wout * Cout * Cin * k^2 FLOP per sample
 HEAVY_FLOP_PER_SAMPLE = 2 * 60 * 80 * 256 * 128 * 9
-# mean dram__bytes_read.sum + dram__bytes_write.sum of those launches at B=32, one `ncu --set full` capture (profiles/r1_halo_v5_ncu_full.md)
-NCU_HEAVY_DRAM_BYTES = 168.6e6
+# mean dram__bytes_read.sum + dram__bytes_write.sum of those launches at B=32, one `ncu --set full` capture (profiles/r2_halo_ncu_full.md)
+NCU_HEAVY_DRAM_BYTES = 168.1e6
 
 
 def synthetic_inputs(seed: int):
@@ -712,7 +712,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": ("conv_halo_kernel<{128,256},64> (tcgen05.mma M128 x N{128,256} x K16, halo-tile TMA) on the 128<->256-channel 3x3 layers" if args.precision != "fp32"
                                     else "conv_gather_kernel<128,64,8,4> on the 128<->256-channel 3x3 layers (fp32 CUDA-core path)"),
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
-                         "traffic": (NCU_HEAVY_DRAM_BYTES if args.precision != "fp32" else None), "traffic_unit": "bytes per launch (dram read + write, ncu --set full: profiles/r1_halo_v5_ncu_full.md)",
+                         "traffic": (NCU_HEAVY_DRAM_BYTES if args.precision != "fp32" else None), "traffic_unit": "bytes per launch (dram read + write, ncu --set full: profiles/r2_halo_ncu_full.md)",
                          "algorithmic_flop_per_launch": flop, "launches_timed": len(kern_ms), "avg_launch_ms": k_ms, "peak_source": pk["source"] + " bf16 " + peak_name,
                          "note": "per-launch CUDA events need host-launched kernels: timed over the same K iterations re-run without graph replay"},
             "cuda_graph": not args.no_graph,
