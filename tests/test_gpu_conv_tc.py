@@ -346,3 +346,70 @@ def test_tc_split_precision_backward_weight(case):
     assert e <= 3e-6 * scale, (e, scale)              # sums of up to 10^4 products: fp32-level
     ref_b = dy.double().sum((0, 2, 3))
     assert (db.double().cpu() - ref_b).abs().max().item() <= 1e-5 * max(1.0, ref_b.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# compute-sanitizer is closed on this GPU pool (profiles/r2_sanitizer.md): own out-of-bounds-write check with guard bands
+# ---------------------------------------------------------------------------------------------------------
+
+def _guarded(shape, dtype, channels_last=True, guard=4096):
+    """A tensor of `shape` carved out of the middle of a larger buffer filled with a canary pattern; returns (view, check())."""
+    n = 1
+    for s_ in shape:
+        n *= s_
+    buf = torch.full((n + 2 * guard,), -12345.0, dtype=dtype, device="cuda:0")
+    B, C, H, W = shape
+    if channels_last:
+        view = buf[guard:guard + n].view(B, H, W, C).permute(0, 3, 1, 2)
+    else:
+        view = buf[guard:guard + n].view(B, C, H, W)
+
+    def check(what):
+        torch.cuda.synchronize()
+        lo, hi = buf[:guard].float(), buf[guard + n:].float()
+        assert bool((lo == -12345.0).all()) and bool((hi == -12345.0).all()), f"{what}: wrote outside its output buffer"
+    return view, check
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("case", [("conv", 64, 128, 3, 1, 1, 0, 13, 21), ("conv", 32, 64, 3, 2, 1, 0, 27, 37), ("convT", 64, 32, 2, 2, 0, 0, 11, 15),
+                                  ("convT", 128, 64, 3, 2, 1, 1, 7, 11), ("conv", 32, 64, 1, 1, 0, 0, 9, 5)], ids=lambda c: "-".join(map(str, c)))
+def test_tc_conv_writes_stay_inside_ragged_outputs(case, split):
+    """Ragged sizes (tiles hang over every edge) with the outputs placed between canary guard bands: the persistent tcgen05 kernel's cooperative
+    128-bit stores, the parity-phase stores of the up-sampling layers and the three-part stores of the split mode must not touch a byte outside."""
+    from spaa_b200 import ops
+    ops.invalidate_packed_weights()
+    kind, cin, cout, k, stride, pad, outpad, H, W = case
+    B, np_ = 2, (3 if split else 1)
+    spec = ops.ConvSpec(kind, cin, cout, k, stride, pad, outpad)
+    Ho, Wo = spec.out_hw(H, W)
+    x = synth.randn(1, "gb.x", (B, cin, H, W))
+    w = synth.randn(2, "gb.w", spec.weight_shape(), 0.05).to("cuda:0")
+    xin = split_cl(x) if split else cl(x)
+    out, chk = _guarded((B, cout * np_, Ho, Wo), torch.bfloat16)
+    ops.conv_forward(spec, xin, w, None, out=out, epi=ops.EPI_RELU, split=split)
+    chk("forward")
+    assert torch.isfinite(out.float()).all() and float(out.float().abs().max()) < 1e3
+    dy = synth.randn(3, "gb.dy", (B, cout, Ho, Wo))
+    dyin = split_cl(dy) if split else cl(dy)
+    dx, chk2 = _guarded((B, cin * np_, H, W), torch.bfloat16)
+    m = split_cl(x) if split else cl(x)
+    ops.conv_backward_data(spec, dyin, w, (H, W), out=dx, mask=m, mask_mode=ops.MASK_POS, split=split)
+    chk2("backward-data")
+    assert torch.isfinite(dx.float()).all()
+
+
+def test_planar_and_pack_kernels_write_inside_their_outputs():
+    from spaa_b200 import ops
+    ops.invalidate_packed_weights()
+    B, H, W = 2, 19, 23
+    spec6 = ops.ConvSpec("conv", 32, 3, 3, 1, 1)
+    x7 = synth.randn(6, "gb.x7", (B, 32, H, W)).relu()
+    w6 = synth.randn(7, "gb.w6", spec6.weight_shape(), 0.1).to("cuda:0")
+    for split in (False, True):
+        out, chk = _guarded((B, 3, H, W), torch.float32, channels_last=False)
+        ops.conv_forward(spec6, split_cl(x7) if split else cl(x7), w6, None, out=out, epi=ops.EPI_RELU | ops.EPI_CLAMP_MAX1, out_dtype=torch.float32, split=split)
+        chk(f"planar conv6 forward (split={split})")
+    pk, chk = _guarded((B, 48, H, W), torch.bfloat16)
+    ops.pack_nhwc16(synth.randn(8, "gb.p", (B, 3, H, W)).to("cuda:0"), synth.randn(9, "gb.s", (B, 6, H, W)).to("cuda:0"), torch.bfloat16, split=True, out=pk)
+    chk("pack_nhwc16 split")
