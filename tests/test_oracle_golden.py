@@ -276,3 +276,36 @@ def test_training_steps(golden):
     for k, v in after.items():
         if "cpp_after_" + k in g:
             close(v, g["cpp_after_" + k], 2e-4, 0, k)
+
+
+def test_api_corners_extra_fixture(golden):
+    """Round-2 fixtures (tests/golden/extra.npz, make_golden.py gen_extra): the oracle's full-form TPS, its SSIM mask / weights branches and the
+    identity "simplify() does not change the output" against the unmodified reference."""
+    g = golden("extra")
+    T = lambda a: torch.from_numpy(np.asarray(a))
+    nT = 36
+    ctrl = O.uniform_ctrl((6, 6)).view(-1, 2)
+    th_full = synth.randn(101, "tps.full", (2, nT + 3, 2), 0.01)
+    th_red = synth.randn(102, "tps.red", (2, nT + 2, 2), 0.01)
+    ctrl_b = torch.stack((ctrl, (ctrl + synth.randn(103, "tps.ctrl", ctrl.shape, 0.01)).clamp(0, 1)))
+    for n in range(2):
+        got = O.tps_sampling_grid(th_full[n:n + 1], ctrl, 12, 16)
+        assert (got[0] - T(g["tps_grid_full"])[n]).abs().max().item() <= 2e-6
+        got = O.tps_sampling_grid(th_red[n:n + 1], ctrl_b[n], 12, 16)
+        assert (got[0] - T(g["tps_grid_red_b"])[n]).abs().max().item() <= 2e-6
+    a = synth.textured(111, "sx.a", (2, 3, 24, 32))
+    b = (a + synth.randn(112, "sx.b", a.shape, 0.1)).clamp(0, 1)
+    w, mb = T(g["ssim_w"]), T(g["ssim_mask"])
+    for tag, kw, avg in (("w_avg", dict(weights=w), True), ("m_avg", dict(mask=mb), True), ("wm_avg", dict(mask=mb, weights=w), True),
+                         ("m_per", dict(mask=mb.float()), False), ("w_per", dict(weights=w), False)):
+        got = O.ssim_index(a, b, size_average=avg, **kw)
+        assert (got - T(g["ssim_" + tag])).abs().max().item() <= 2e-6, tag
+    # simplify() caches loop constants only: the reference's simplified outputs equal the oracle's plain forward
+    cam_hw, prj_hw = (24, 32), (32, 32)
+    Pn = synth.pcnet_params(36, cam_hw, use_rough=False)
+    prj = synth.textured(32, "pc.prj", (2, 3, *prj_hw))
+    scene = synth.textured(33, "pc.s", (1, 3, *cam_hw)).expand(2, -1, -1, -1)
+    x = synth.textured(35, "sn.x", (2, 3, *cam_hw))
+    with torch.no_grad():
+        assert (O.shading_net(Pn, x, scene) - T(g["shading_norough_y"])).abs().max().item() <= 1e-5
+        assert (O.shading_net(Pn, x, scene) - T(g["shading_simplified_y"])).abs().max().item() <= 1e-5
