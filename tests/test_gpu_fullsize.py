@@ -168,8 +168,8 @@ def test_pcnet_fullsize_per_layer_and_gradient(precision, tol_out, tol_layer, to
     # precision's storage format), so no mask can differ and only rounding remains.  d/d(warped image) isolates the conv stack (14 backward-data
     # launches); d/dprj adds the warp's adjoint, whose bilinear weights inherit the grid's 1e-5-level differences on the zero-padding ramp.
     S2 = dict(S)
-    for k in LAYERS:
-        S2[k] = as_saved(tr[k], precision)
+    for k in LAYERS:                                  # (tr2: the very forward pass whose autograd graph produced gw / gr)
+        S2[k] = as_saved(tr2[k].detach(), precision)
     gw_forced, g_forced = backward_with_given_masks(m, S2, cot, scene_d, prj_d, precision)
     rel_w = ((gw_forced - gw).double().flatten(1).norm(dim=1) / gw.double().flatten(1).norm(dim=1))
     rel_f = ((g_forced - gr).double().flatten(1).norm(dim=1) / gr.double().flatten(1).norm(dim=1))
