@@ -538,8 +538,8 @@ def perc_al_attack(classifier_fn, inputs: Tensor, labels: Tensor, d_thr: float, 
     best = inputs.clone()
     lab0 = srgb_to_lab(inputs)
     delta = torch.zeros_like(inputs, requires_grad=True)
-    use_col = torch.zeros(B, dtype=torch.bool)
-    best_dis = torch.ones(B, dtype=inputs.dtype) * 100000
+    use_col = torch.zeros(B, dtype=torch.bool, device=inputs.device)
+    best_dis = torch.ones(B, dtype=inputs.dtype, device=inputs.device) * 100000
     if targeted and confidence != 0:
         return None                                                       # :176-178
     for it in range(max_iterations):

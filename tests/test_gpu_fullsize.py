@@ -310,3 +310,86 @@ def test_fullsize_colour_loss_ssim_warp_vs_oracle():
     gpr, = torch.autograd.grad((wr * cot).sum(), pr)
     dimg = ops.grid_sample_bwd_input(cot, grid, PRJ_HW, mask=m.flat_mask())
     assert maxerr(dimg, gpr) <= 1e-4 * max(1.0, gpr.abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["vgg16", "inception_v3"])
+def test_percal_fullsize_first_iterations_vs_oracle(name):
+    """BASELINE configs[2] at its shapes: PerC_AL.adversary_projector on a 240x320 scene, B = 8 targets, torchvision vgg16 / inception_v3 (seeded random
+    init, exact fp32 cuDNN), the first iterations against the oracle (perc_al/__init__.py:133-256) free-running on the same GPU: the perturbation, the
+    colour distance, the decision masks; then one CompenNet++ forward at 240x320 -> 256x256 in every precision."""
+    from torchvision import models as tvm
+    from spaa_b200 import perc_al, models
+    torch.manual_seed(0)
+    net = (tvm.inception_v3(weights=None, init_weights=False, transform_input=True, aux_logits=True) if name == "inception_v3" else tvm.vgg16(weights=None)).to(dev()).eval()
+    for p in net.parameters():
+        p.requires_grad = False
+    insz = (299, 299) if name == "inception_v3" else (224, 224)
+    scene = synth.textured(0, "bench.scene", (1, 3, *CAM_HW)).to(dev())
+    nb, iters = 8, 4
+    with torch.no_grad():
+        order = net(O.classifier_preprocess(scene, CROP, insz)).argsort(1, descending=True)[0]
+    labels = order[1:1 + nb].clone()                       # the classifier's own runners-up: reachable targets
+
+    def classify(im):
+        logits = net(O.classifier_preprocess(im, CROP, insz))
+        ps, idx = torch.softmax(logits, 1).detach().sort(descending=True)
+        return logits, ps, idx
+    otrace, trace = [], []
+    O.perc_al_attack(classify, scene.expand(nb, -1, -1, -1), labels, 11.0, True, max_iterations=iters, trace=otrace)
+
+    class Clf:
+        model, input_sz = net, insz
+    atk = perc_al.PerC_AL(device=dev(), max_iterations=iters, alpha_l_init=1, alpha_c_init=0.5, confidence=0)
+    atk.adversary_projector(Clf(), scene.expand(nb, -1, -1, -1), labels, None, 11.0, True, CROP, trace=trace)
+    for i, (a, o) in enumerate(zip(trace, otrace)):
+        e = maxerr(a["delta"], o["delta"])
+        assert e <= 1e-4, f"it{i} delta: {e:.2e}"              # steps of length 1 / 0.5 along unit gradients through an fp32 classifier
+        assert maxerr(a["dis"], o["dis"]) <= 1e-4 * max(1.0, o["dis"].abs().max().item()) + 2e-2, f"it{i} colour distance"
+        assert torch.equal(a["use_col"], o["use_col"]) and torch.equal(a["isadv"], o["isadv"]), f"it{i} masks"
+        q = (a["x_round"] - o["x_round"]).abs()
+        assert q.max().item() <= 1.01 / 255 and (q > 1e-6).float().mean().item() < 2e-3, f"it{i} quantised image"
+    # CompenNet++ forward at the BASELINE shapes
+    C = synth.compennet_pp_params(200)
+    Cd = {k: v.to(dev()) for k, v in C.items()}
+    cam = otrace[-1]["x_round"]
+    with torch.no_grad():
+        ref = O.compennet_pp(Cd, cam, scene.expand(nb, -1, -1, -1), PRJ_HW)
+    for precision, tol in (("fp32", 1e-5), ("bf16x3", 1e-5), ("fp16", 2e-3)):
+        cm = models.CompenNetPlusplus(nn.DataParallel(models.WarpingNet(out_size=PRJ_HW)), nn.DataParallel(models.CompenNet()))
+        cm.load_state_dict(C, strict=True)
+        cm = models.set_precision(cm.to(dev()).eval(), precision)
+        with torch.no_grad():
+            got = cm(cam, scene.expand(nb, -1, -1, -1))
+        close_but_ramp(got, ref, tol, what=f"CompenNet++ output ({precision})")
+
+
+@pytest.mark.parametrize("precision,tol_loss,tol_grad", [("fp32", 1e-5, 5e-3), ("bf16x3", 1e-5, 5e-3), ("bf16", 2e-3, 0.15)])
+def test_training_step_fullsize_vs_oracle(precision, tol_loss, tol_grad):
+    """BASELINE configs[3] at its shapes: one PCNet training step's loss (L1 + SSIM, batch 24, 256x256 -> 240x320) and parameter gradients against
+    autograd through the oracle on the same GPU.  Gradients are sums over 24 x 76 800 pixels: ReLU masks on their thresholds (see the gradient test
+    above) bound the agreement at the 1e-3 level even between two exact-fp32 evaluations; the loss value is held to 1e-5."""
+    from spaa_b200 import models, train_network as tn
+    nb = 24
+    P = synth.pcnet_params(300, CAM_HW)
+    g = torch.Generator().manual_seed(7)
+    prj = torch.rand(nb, 3, *PRJ_HW, generator=g).to(dev())
+    cam = torch.rand(nb, 3, *CAM_HW, generator=g).to(dev())
+    scene = synth.textured(0, "bench.train.scene", (1, 3, *CAM_HW)).to(dev()).expand(nb, -1, -1, -1)
+    Pd = {k: v.to(dev()).requires_grad_(v.dtype.is_floating_point and k not in ("mask", "warping_net.ctrl_pts")) for k, v in P.items()}
+    loss_o, _ = O.training_loss(O.pcnet(Pd, prj, scene, CAM_HW), cam, "l1+ssim")
+    names = [k for k, v in Pd.items() if v.requires_grad]
+    go = dict(zip(names, torch.autograd.grad(loss_o, [Pd[k] for k in names])))
+    m = models.PCNet(P["mask"], nn.DataParallel(models.WarpingNet(out_size=CAM_HW)), nn.DataParallel(models.ShadingNetSPAA()))
+    m.load_state_dict(P, strict=True)
+    m = models.set_precision(m.to(dev()).train(), precision)
+    loss, _ = tn.compute_loss(m(prj, scene), cam, "l1+ssim")
+    loss.backward()
+    assert abs(loss.item() - loss_o.item()) <= tol_loss * max(1.0, abs(loss_o.item())), (loss.item(), loss_o.item())
+    worst = ("", 0.0)
+    for n, p in m.named_parameters():
+        ref = go[n]
+        rel = ((p.grad - ref).double().norm() / (ref.double().norm() + 1e-30)).item()
+        if rel > worst[1]:
+            worst = (n, rel)
+    print(f"fullsize training step [{precision}]: loss {loss.item():.6f} vs {loss_o.item():.6f}; worst parameter-gradient relative Frobenius err {worst[1]:.2e} ({worst[0]})")
+    assert worst[1] <= tol_grad, worst
