@@ -367,7 +367,8 @@ def test_percal_fullsize_first_iterations_vs_oracle(name):
         cm = models.set_precision(cm.to(dev()).eval(), precision)
         with torch.no_grad():
             got = cm(cam, scene.expand(nb, -1, -1, -1))
-        close_but_ramp(got, ref, tol, what=f"CompenNet++ output ({precision})")
+        # (CompenNet++ warps BOTH of its inputs, and its affine shrinks the grid: 0.2 % of the output pixels see the zero-padding ramp)
+        close_but_ramp(got, ref, tol, frac=5e-3, what=f"CompenNet++ output ({precision})")
 
 
 @pytest.mark.parametrize("precision,tol_loss,tol_grad", [("fp32", 1e-5, 5e-3), ("bf16x3", 1e-5, 5e-3), ("bf16", 2e-3, 0.3)])
