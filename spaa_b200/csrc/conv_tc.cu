@@ -339,7 +339,9 @@ struct HaloParams {
     int32_t a_plane_bytes, a_stage_bytes, a_tx_bytes, b_slice_bytes;
     int32_t sa, sb, resident, nslots, use_base_off, ntap_total;
     int32_t ctas_per_sm;
-    int32_t egroups, nbuf;             // epilogue warp groups (1 or 2); accumulator buffers in TMEM (2, or 1 when 2 do not fit)
+    int32_t egroups, nbuf;             // epilogue warp groups (1 or 2); accumulator buffers in TMEM (1, 2 or 4): tile number k of a CTA uses buffer k % nbuf
+    int32_t pair;                      // 1: the MMA issuer works on TWO tiles per weight pass (see conv_halo_kernel); a_pair_bytes = offset of the second tile's A planes in a stage
+    int32_t a_pair_bytes;
     int32_t e_stage_bytes;             // output staging blocks of the 4 epilogue warps (16-bit NHWC output only)
     int32_t e_slots, e_nops;           // epilogue operand ring: slots of e_nops x 8 KB (0 slots: no ring)
     uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
@@ -393,9 +395,9 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
     uint64_t* a_empty = a_full + 8;                // [SA]
     uint64_t* b_full = a_empty + 8;                // [SB] (b_full[0] doubles as the "resident weights loaded" barrier)
     uint64_t* b_empty = b_full + 8;                // [SB]
-    uint64_t* tfull = b_empty + 8;                 // [2]
-    uint64_t* tempty = tfull + 2;                  // [2]
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* tfull = b_empty + 8;                 // [4]
+    uint64_t* tempty = tfull + 4;                  // [4]
+    uint32_t* tmem_slot = (uint32_t*)(tempty + 4);
     uint32_t* s_tap = tmem_slot + 4;               // [kMaxTaps * kMaxPhases]
     float* s_bias = (float*)(s_tap + kMaxTaps * kMaxPhases);
 
@@ -403,14 +405,14 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
     const int NPH = P.nphases;
     for (int i = threadIdx.x; i < P.ntap_total; i += blockDim.x) s_tap[i] = P.tap_tab[i];
     const uint32_t acc_cols = (uint32_t)(NPH * BN);                  // TMEM columns of one accumulator buffer
-    const bool dbuf = P.nbuf == 2;                                   // two accumulator buffers: the epilogue of tile i overlaps the MMAs of tile i+1
+    const int NACC = P.nbuf;                                         // accumulator buffers: the epilogue of tile i overlaps the MMAs of the tiles after it
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)P.nbuf * acc_cols) tmem_cols <<= 1;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a);
         prefetch_tmap(&map_b);
         for (int i = 0; i < 8; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
@@ -432,18 +434,29 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
             }
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-                const int b = tile / per_img;
-                const int t = tile - b * per_img;
-                const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
-                const int x0 = (tx * HTW + P.org_x) * P.stride, y0 = (ty * HTH + P.org_y) * P.stride;
+            // NT tiles per pipeline step: in pair mode one stage holds the halo boxes of TWO tiles (this CTA's tiles number 2k and 2k+1), and every
+            // weight slice that arrives is used for both (see the MMA issuer)
+            const int NT = P.pair ? 2 : 1;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += NT * (int)gridDim.x) {
+                int bb[2], xx0[2], yy0[2];
+                int nt = 0;
+                for (int j = 0; j < NT; ++j) {
+                    const int tj = tile + j * (int)gridDim.x;
+                    if (tj >= P.total_tiles) break;
+                    const int b = tj / per_img;
+                    const int t = tj - b * per_img;
+                    const int ty = t / P.tiles_x, tx = t - ty * P.tiles_x;
+                    bb[j] = b; xx0[j] = (tx * HTW + P.org_x) * P.stride; yy0[j] = (ty * HTH + P.org_y) * P.stride;
+                    ++nt;
+                }
                 for (int kc = 0; kc < P.kchunks; ++kc) {
                     mbar_wait(a_empty + sa, pa ^ 1);
                     uint8_t* dst = a_ring + (size_t)sa * P.a_stage_bytes;
-                    mbar_expect_tx(a_full + sa, (uint32_t)P.a_tx_bytes);
+                    mbar_expect_tx(a_full + sa, (uint32_t)(P.a_tx_bytes * nt));
                     const int ch0 = P.a_chunk[kc];
-                    for (int pl = 0; pl < P.nplanes; ++pl)
-                        tma_load_4d(dst + (size_t)pl * P.a_plane_bytes, &map_a, a_full + sa, ch0, x0 + (pl & 1), y0 + (pl >> 1), b);
+                    for (int j = 0; j < nt; ++j)
+                        for (int pl = 0; pl < P.nplanes; ++pl)
+                            tma_load_4d(dst + (size_t)j * P.a_pair_bytes + (size_t)pl * P.a_plane_bytes, &map_a, a_full + sa, ch0, xx0[j] + (pl & 1), yy0[j] + (pl >> 1), bb[j]);
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                     if (!P.resident) {
                         for (int ph = 0; ph < NPH; ++ph)
@@ -477,13 +490,28 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
             for (int e = 0; e < kMaxTaps; ++e) taps[e] = e < ntap ? s_tap[e] : 0u;
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
-            int local = 0;
+            int local = 0;                                   // this CTA's tile counter: tile k uses accumulator buffer k % NACC, for the (k / NACC)-th time
             if (P.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++local) {
-                const int acc = dbuf ? (local & 1) : 0;
-                mbar_wait(tempty + acc, (((dbuf ? local >> 1 : local)) & 1) ^ 1);
+            // Pair mode (wide layers whose weights do not fit in shared memory: the K = 1152 / 2304 layers stream 590 KB of weights per 128-pixel
+            // tile from L2, 85 % of the kernel's L2->SM bytes, and ran at the L2->SM bandwidth (~10 TB/s, profiles/r2_halo_ncu_full.md) with the tensor
+            // pipe 63 % active): every weight slice that lands is multiplied with the A views of TWO tiles, into two accumulator buffers -- an
+            // M = 256 step without a CTA pair -- which halves the weight traffic per output pixel.
+            const int NT = P.pair ? 2 : 1;
+            const uint32_t pair16 = (uint32_t)P.a_pair_bytes >> 4;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += NT * (int)gridDim.x, local += NT) {
+                const int nt = (NT == 2 && tile + (int)gridDim.x < P.total_tiles) ? 2 : 1;
+                uint32_t d_base[2];
+                int acc[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j < nt) {
+                        const int lj = local + j;
+                        acc[j] = lj % NACC;
+                        mbar_wait(tempty + acc[j], (uint32_t)(((lj / NACC) & 1) ^ 1));
+                        d_base[j] = tmem_base + (uint32_t)acc[j] * acc_cols;
+                    }
+                }
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)acc * acc_cols;
                 for (int kc = 0; kc < P.kchunks; ++kc) {
                     mbar_wait(a_full + sa, pa);
                     tc_fence_after();
@@ -500,13 +528,18 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                                 tc_fence_after();
                                 b_lo = b_base_lo + (uint32_t)sb * b_slice16;
                             }
-                            const uint32_t d_tmem = d_base + ((te >> 20) & 3u) * (uint32_t)BN;
-                            const uint32_t at = a_lo + (te & 0xFFFFu);
                             const uint32_t fresh = (kc == 0 && (te & (1u << 22))) ? 1u : 0u;
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (uint64_t)(at + 2 * k), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2 * k), idesc,
-                                          (k == 0 && fresh) ? 0u : 1u);
+                            for (int j = 0; j < 2; ++j) {
+                                if (j < nt) {
+                                    const uint32_t d_tmem = d_base[j] + ((te >> 20) & 3u) * (uint32_t)BN;
+                                    const uint32_t at = a_lo + (uint32_t)j * pair16 + (te & 0xFFFFu);
+#pragma unroll
+                                    for (int k = 0; k < BK / 16; ++k)
+                                        umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (uint64_t)(at + 2 * k), ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2 * k), idesc,
+                                                  (k == 0 && fresh) ? 0u : 1u);
+                                }
+                            }
                             if (!P.resident) {
                                 umma_commit(b_empty + sb);
                                 if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -514,7 +547,10 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                         }
                     }
                     umma_commit(a_empty + sa);
-                    if (kc == P.kchunks - 1) umma_commit(tfull + acc);
+                    if (kc == P.kchunks - 1) {
+                        umma_commit(tfull + acc[0]);
+                        if (nt == 2) umma_commit(tfull + acc[1]);
+                    }
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
             }
@@ -630,8 +666,8 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
         int local = eg;
         int b = b0, ty = ty0, tx = tx0;
         for (int tile = tile0; tile < P.total_tiles && eg < EG; tile += tstep, local += EG, tile_step(b, ty, tx)) {
-            const int acc = dbuf ? (local & 1) : 0;
-            const uint32_t tpar = (uint32_t)((dbuf ? local >> 1 : local) & 1);
+            const int acc = local % NACC;
+            const uint32_t tpar = (uint32_t)((local / NACC) & 1);
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
             bool waited = false;
             for (int ph = 0; ph < NPH; ++ph) {
@@ -960,7 +996,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, c
 }
 
 // ---- v2 host side ---------------------------------------------------------------------------------------------
-constexpr int kHaloBarBytes = (8 * 4 + 4) * 8 + 16 + kMaxTaps * kMaxPhases * 4;      // a_full/a_empty/b_full/b_empty [8] + tfull/tempty [2] + tmem slot
+constexpr int kHaloBarBytes = (8 * 4 + 8) * 8 + 16 + kMaxTaps * kMaxPhases * 4;      // a_full/a_empty/b_full/b_empty [8] + tfull/tempty [4] + tmem slot
 
 template <int BN, int BK, bool F16, bool SPLIT = false>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, size_t smem_bytes, cudaStream_t st) {
@@ -1062,71 +1098,83 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     const int rowb = BK * 2;
     P.a_tx_bytes = P.nplanes * P.halo_h * P.halo_w * rowb;
     P.a_plane_bytes = (P.halo_h * P.halo_w * rowb + 1023) & ~1023;
-    P.a_stage_bytes = P.nplanes * P.a_plane_bytes;
     P.b_slice_bytes = BN * rowb;
     // ---- shared-memory plan.  Layers whose accumulator is narrow (BN <= 64: the HBM-bound ones) run TWO CTAs per SM when two
     // TMEM allocations and two half-size rings fit: twice the epilogue warps and loads in flight per SM.
     const bool planar = d->out_dtype == 0;
     P.e_nops = planar ? ((add && d->Cout <= 4) ? 1 : 0) : ((add ? np : 0) + (mask ? 1 : 0) + (mask2 ? 1 : 0));
-    // accumulator buffers: two when they fit in half of TMEM's 512 columns (so that two CTAs can share an SM) or in all of it for
-    // the wide layers; a 4-phase BN = 64 layer (transConv1 forward) runs single-buffered in 256 columns with two CTAs per SM instead
-    // of double-buffered alone on its SM
-    P.nbuf = 2 * nph * BN <= (BN <= 64 ? 256 : 512) ? 2 : 1;
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(P.nbuf * nph * BN)) tmem_cols <<= 1;
     static const int max_ctas = [] { const char* e = getenv("SPAA_TC_CTAS"); return e ? atoi(e) : 2; }();
     static const int max_eg = [] { const char* e = getenv("SPAA_TC_EG"); return e ? atoi(e) : 2; }();
     static const int e_kb = [] { const char* e = getenv("SPAA_TC_EKB"); return e ? atoi(e) : -1; }();
-    // two epilogue groups for the wide layers (one CTA per SM), unless their rings and staging blocks would starve the weight ring
-    // (measured: it pays where the MMA work per tile is short next to the epilogue's -- conv3 / skipConv3 / conv3_s / conv4 forward,
-    // K per epilogue operand <= 640 -- and costs 3-8 % on the MMA-bound layers, whose issuing warp then shares its schedulers)
-    const int k_per_pass = P.nslots * d->Cin * (d->split ? 6 : 1) / (1 + P.e_nops);
-    P.egroups = (BN >= 128 && P.nbuf == 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
-    P.e_stage_bytes = planar ? 0 : P.egroups * 4 * (mask2 ? 4096 : 2048);
+    static const int use_pair = [] { const char* e = getenv("SPAA_TC_PAIR"); return e ? atoi(e) : 1; }();
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
-    int ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
+    // Pair mode (two tiles per weight pass, see the MMA issuer): for the wide single-phase layers whose weights are streamed, when the launch has
+    // at least two tiles per CTA.  Planned first; if its two-tile A stages leave no room for a weight ring the single-tile plan follows.
+    const bool pair_ok = use_pair && BN >= 128 && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
+    int ctas = 1;
     size_t smem_bytes = 0;
-    for (;; --ctas) {
-        const int total = ctas == 2 ? 108 * 1024 : 222 * 1024;
-        P.resident = res_bytes <= (ctas == 2 ? 40 : 80) * 1024 ? 1 : 0;
-        P.e_slots = 0;
-        if (P.e_nops) {
-            const int eb = (e_kb >= 0 ? e_kb : (ctas == 2 ? 32 : (P.resident ? 48 : 32))) * 1024;
-            const int sl = eb / (P.e_nops * 8192 * P.egroups);             // slots PER GROUP
-            P.e_slots = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
-        }
-        int budget = total - P.egroups * P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
-        // big A stages (stride-2 layers load four parity planes): give the operand ring's depth back before giving up the kernel
-        while (P.e_slots > 2 && budget - 2 * P.a_stage_bytes < (P.resident ? res_bytes : 2 * (int64_t)P.b_slice_bytes)) {
-            --P.e_slots;
-            budget += P.egroups * P.e_nops * 8192;
-        }
-        int64_t bbytes, sa;
-        if (P.resident) {
-            bbytes = res_bytes; P.sb = 1;
-            sa = (budget - bbytes) / P.a_stage_bytes;
-        } else {
-            // streamed weights: one A stage feeds KH*KW*BK/16 MMAs but one weight slice only BK/16 -- the depth belongs to the B ring
-            sa = 2;
-            const int64_t sbn = (budget - 2 * (int64_t)P.a_stage_bytes) / P.b_slice_bytes;
-            P.sb = (int)(sbn > 8 ? 8 : sbn);
-            if (P.sb < 2) sa = 0;
-            bbytes = (int64_t)P.sb * P.b_slice_bytes;
-        }
-        if (sa < 2) {
-            if (ctas == 1 && P.egroups == 2) {                   // a second epilogue group's ring and staging blocks do not fit: run with one
-                P.egroups = 1;
-                P.e_stage_bytes = planar ? 0 : 4 * (mask2 ? 4096 : 2048);
-                ++ctas;                                          // (undo the loop's decrement: plan again with one CTA per SM)
+    bool planned = false;
+    for (int try_pair = pair_ok ? 1 : 0; try_pair >= 0 && !planned; --try_pair) {
+        P.pair = try_pair;
+        P.a_pair_bytes = P.nplanes * P.a_plane_bytes;
+        P.a_stage_bytes = (try_pair ? 2 : 1) * P.a_pair_bytes;
+        // accumulator buffers: two when they fit in half of TMEM's 512 columns (so that two CTAs can share an SM) or in all of it for
+        // the wide layers; a 4-phase BN = 64 layer (transConv1 forward) runs single-buffered in 256 columns with two CTAs per SM instead
+        // of double-buffered alone on its SM; pair mode: four (BN = 128: two pairs in flight) or two (BN = 256)
+        P.nbuf = try_pair ? (4 * BN <= 512 ? 4 : 2) : (2 * nph * BN <= (BN <= 64 ? 256 : 512) ? 2 : 1);
+        uint32_t tmem_cols = 32;
+        while (tmem_cols < (uint32_t)(P.nbuf * nph * BN)) tmem_cols <<= 1;
+        // two epilogue groups for the wide layers (one CTA per SM), unless their rings and staging blocks would starve the weight ring
+        // (measured: it pays where the MMA work per tile is short next to the epilogue's -- conv3 / skipConv3 / conv3_s / conv4 forward,
+        // K per epilogue operand <= 640 -- and costs 3-8 % on the MMA-bound layers, whose issuing warp then shares its schedulers)
+        const int k_per_pass = P.nslots * d->Cin * (d->split ? 6 : 1) / (1 + P.e_nops);
+        P.egroups = (BN >= 128 && P.nbuf >= 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
+        P.e_stage_bytes = planar ? 0 : P.egroups * 4 * (mask2 ? 4096 : 2048);
+        ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
+        for (;; --ctas) {
+            const int total = ctas == 2 ? 108 * 1024 : 222 * 1024;
+            P.resident = res_bytes <= (ctas == 2 ? 40 : 80) * 1024 ? 1 : 0;
+            P.e_slots = 0;
+            if (P.e_nops) {
+                const int eb = (e_kb >= 0 ? e_kb : (ctas == 2 ? 32 : (P.resident ? 48 : 32))) * 1024;
+                const int sl = eb / (P.e_nops * 8192 * P.egroups);             // slots PER GROUP
+                P.e_slots = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
+            }
+            int budget = total - P.egroups * P.e_slots * P.e_nops * 8192 - P.e_stage_bytes;
+            // big A stages (stride-2 layers load four parity planes): give the operand ring's depth back before giving up the kernel
+            while (P.e_slots > 2 && budget - 2 * P.a_stage_bytes < (P.resident ? res_bytes : 2 * (int64_t)P.b_slice_bytes)) {
+                --P.e_slots;
+                budget += P.egroups * P.e_nops * 8192;
+            }
+            int64_t bbytes, sa;
+            if (P.resident) {
+                bbytes = res_bytes; P.sb = 1;
+                sa = (budget - bbytes) / P.a_stage_bytes;
+            } else {
+                // streamed weights: one A stage feeds KH*KW*BK/16 MMAs but one weight slice only BK/16 -- the depth belongs to the B ring
+                sa = 2;
+                const int64_t sbn = (budget - 2 * (int64_t)P.a_stage_bytes) / P.b_slice_bytes;
+                P.sb = (int)(sbn > 8 ? 8 : sbn);
+                if (P.sb < (try_pair ? 3 : 2)) sa = 0;               // (pair mode is only worth it with a weight ring of depth >= 3)
+                bbytes = (int64_t)P.sb * P.b_slice_bytes;
+            }
+            if (sa < 2) {
+                if (ctas == 1 && P.egroups == 2) {                   // a second epilogue group's ring and staging blocks do not fit: run with one
+                    P.egroups = 1;
+                    P.e_stage_bytes = planar ? 0 : 4 * (mask2 ? 4096 : 2048);
+                    ++ctas;                                          // (undo the loop's decrement: plan again with one CTA per SM)
+                    continue;
+                }
+                if (ctas == 1) break;                                // this mode does not fit
                 continue;
             }
-            if (ctas == 1) return SPAA_ERR_UNSUPPORTED;
-            continue;
+            P.sa = (int)(sa > 6 ? 6 : sa);
+            smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
+            planned = true;
+            break;
         }
-        P.sa = (int)(sa > 6 ? 6 : sa);
-        smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
-        break;
     }
+    if (!planned) return SPAA_ERR_UNSUPPORTED;
     P.ctas_per_sm = ctas;
 
     CUtensorMap ma, mb;

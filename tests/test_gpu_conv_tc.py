@@ -413,3 +413,47 @@ def test_planar_and_pack_kernels_write_inside_their_outputs():
     pk, chk = _guarded((B, 48, H, W), torch.bfloat16)
     ops.pack_nhwc16(synth.randn(8, "gb.p", (B, 3, H, W)).to("cuda:0"), synth.randn(9, "gb.s", (B, 6, H, W)).to("cuda:0"), torch.bfloat16, split=True, out=pk)
     chk("pack_nhwc16 split")
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("case", [("conv", 128, 256, 3, 96, 104), ("conv", 256, 128, 3, 96, 104), ("conv", 64, 128, 3, 100, 100)], ids=lambda c: "-".join(map(str, c)))
+def test_tc_conv_pair_mode_many_tiles(case, split):
+    """Wide layers with streamed weights and >= 2 tiles per CTA run in PAIR mode (two tiles per weight pass, four / two accumulator buffers in TMEM;
+    conv_tc.cu): 312-350 tiles on 148 persistent CTAs, so CTAs own 2 or 3 tiles (a pair plus a single), rings wrap and accumulator buffers are reused.
+    Forward with residual + ReLU and backward-data with mask (+ second masked output) against the exact CUDA-core kernel on the same operands."""
+    from spaa_b200 import ops
+    ops.invalidate_packed_weights()
+    kind, cin, cout, k, H, W = case
+    B = 4
+    spec = ops.ConvSpec(kind, cin, cout, k, 1, 1, 0)
+    x = synth.randn(1, "pm.x", (B, cin, H, W))
+    w = synth.randn(2, "pm.w", spec.weight_shape(), (2.0 / (cin * k * k)) ** 0.5).to("cuda:0")
+    b = synth.randn(3, "pm.b", (cout,), 0.1).to("cuda:0")
+    add = synth.randn(4, "pm.add", (B, cout, H, W), 0.5)
+    if split:
+        got = unsplit(ops.conv_forward(spec, split_cl(x), w, b, add=split_cl(add), epi=ops.EPI_RELU, split=True)).float()
+        ref = ops.conv_forward(spec, x.to("cuda:0"), w, b, add=add.to("cuda:0"), epi=ops.EPI_RELU).float()
+        tol_a, tol_r = 3e-5, 0.0
+    else:
+        xq, aq = x.to(torch.bfloat16), add.to(torch.bfloat16)
+        got = ops.conv_forward(spec, cl(xq), w, b, add=cl(aq), epi=ops.EPI_RELU).float()
+        ref = ops.conv_forward(spec, xq.float().to("cuda:0"), w.to(torch.bfloat16).float(), b, add=aq.float().to("cuda:0"), epi=ops.EPI_RELU).float()
+        tol_a, tol_r = 3e-2, 1e-2
+    err = (got - ref).abs() - tol_r * ref.abs()
+    assert err.max().item() <= tol_a, f"forward: max abs err {(got - ref).abs().max().item():.3e}"
+    # every image and every tile position must be right (a mis-paired tile would be wrong as a whole): per-image, per-16-row-band maxima
+    band = (got - ref).abs().amax(dim=(1, 3))
+    assert (band <= tol_a + tol_r * ref.abs().max()).all()
+    dy = synth.randn(5, "pm.dy", (B, cout, H, W))
+    m = synth.randn(6, "pm.m", (B, cin, H, W))
+    if split:
+        dx = unsplit(ops.conv_backward_data(spec, split_cl(dy), w, (H, W), mask=split_cl(m), mask_mode=ops.MASK_POS, split=True)).float()
+        refb = ops.conv_backward_data(spec, dy.to("cuda:0"), w, (H, W), mask=m.to("cuda:0"), mask_mode=ops.MASK_POS).float()
+        tol_a, tol_r = 1e-4, 0.0
+    else:
+        dq, mq = dy.to(torch.bfloat16), m.to(torch.bfloat16)
+        dx = ops.conv_backward_data(spec, cl(dq), w, (H, W), mask=cl(mq), mask_mode=ops.MASK_POS).float()
+        refb = ops.conv_backward_data(spec, dq.float().to("cuda:0"), w.to(torch.bfloat16).float(), (H, W), mask=mq.float().to("cuda:0"), mask_mode=ops.MASK_POS).float()
+        tol_a, tol_r = 0.1, 1e-2
+    errb = (dx - refb).abs() - tol_r * refb.abs()
+    assert errb.max().item() <= tol_a, f"backward-data: max abs err {(dx - refb).abs().max().item():.3e}"
