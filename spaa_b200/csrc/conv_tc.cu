@@ -1110,7 +1110,10 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
     // Pair mode (two tiles per weight pass, see the MMA issuer): for the wide single-phase layers whose weights are streamed, when the launch has
     // at least two tiles per CTA.  Planned first; if its two-tile A stages leave no room for a weight ring the single-tile plan follows.
-    const bool pair_ok = use_pair && BN >= 128 && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
+    // BN = 128 only: four accumulator buffers keep the epilogue of one pair overlapped with the MMAs of the next.  With BN = 256 a pair fills all 512
+    // TMEM columns, the overlap is lost and the layer gets SLOWER (measured: conv4_s forward 73.8 -> 100.5 us, conv4 forward unchanged), while
+    // BN = 128 gains (conv5 forward 84.0 -> 72.5 us).  $SPAA_TC_PAIR=2 forces it for BN = 256 too.
+    const bool pair_ok = use_pair && (BN == 128 || (BN == 256 && use_pair >= 2)) && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
     int ctas = 1;
     size_t smem_bytes = 0;
     bool planned = false;
