@@ -971,9 +971,7 @@ bool tc_supported(const spaa_conv_desc* d, const char** why) {
         if (d->out_ps != 1 || d->out_cs != hw || (d->B > 1 && d->out_bs != hw * d->Cout)) return fail("fp32 output must be dense NCHW");
     } else {
         if (d->Cout % 32 != 0 || d->Cout > 256) return fail("Cout must be a multiple of 32 (<= 256)");
-        // (a channel slice of a wider dense NHWC tensor is fine: pixel stride > Cout; the split mode needs its three parts exactly Cout apart)
-        if (d->out_cs != 1 || d->out_ps < np * d->Cout || (d->split && d->out_ps != np * d->Cout) || (d->out_ps & 7) ||
-            (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->out_ps)) return fail("16-bit output must be dense NHWC (or a channel slice of one)");
+        if (d->out_cs != 1 || d->out_ps != np * d->Cout || (d->B > 1 && d->out_bs != (int64_t)d->Hout * d->Wout * d->Cout * np)) return fail("16-bit output must be dense NHWC");
     }
     if (d->Cin == 16 && bn_for(d->Cout) != 32) return fail("Cin == 16 is implemented for Cout <= 32");
     if (d->Cin == 32 && bn_for(d->Cout) > 64) return fail("Cin == 32 is implemented for Cout <= 64");
@@ -1030,7 +1028,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     const int cchunks = d->Cin / BK;               // K chunks of one part
     P.up = d->up; P.stride = d->stride; P.nphases = nph; P.nplanes = d->stride * d->stride; P.kchunks = (d->split ? 6 : 1) * cchunks;
     P.split = d->split ? 1 : 0;
-    P.out_ps = (int32_t)d->out_ps;
+    P.out_ps = np * d->Cout;
     if (P.kchunks > kMaxKChunks) return SPAA_ERR_UNSUPPORTED;
     {
         // part of the INPUT each of the six part products reads; the weights are packed with the matching part of the filter in the same order
@@ -1302,8 +1300,8 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
         SPAA_CHECK_ARG(!add || (d->add_ps == 1 && d->add_cs == (int64_t)d->Hout * d->Wout), "spaa_conv_tc_fwd: add must be fp32 NCHW planes");
     } else {
         const int np = d->split ? 3 : 1;
-        SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == d->out_ps), "spaa_conv_tc_fwd: add must be NHWC with the output's pixel stride");
-        SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == d->out_ps), "spaa_conv_tc_fwd: masks must be NHWC with the output's pixel stride");
+        SPAA_CHECK_ARG(!add || (d->add_cs == 1 && d->add_ps == np * d->Cout), "spaa_conv_tc_fwd: add must be dense NHWC");
+        SPAA_CHECK_ARG(!(mask || mask2) || (d->mask_cs == 1 && d->mask_ps == np * d->Cout), "spaa_conv_tc_fwd: masks must be dense NHWC");
     }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled is unavailable in this driver"); return SPAA_ERR_CUDA; }

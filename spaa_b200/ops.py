@@ -481,7 +481,6 @@ def _w_strides(w: Tensor, k: int):
 
 
 _packed_cache: Dict[tuple, Tensor] = {}
-NSPLIT_256 = os.environ.get("SPAA_TC_NSPLIT", "1") not in ("", "0")      # 256-output-channel tensor-core layers as two 128-channel launches (see _launch_conv)
 TC_ENABLED = True          # tests flip this to compare the tensor-core path against the CUDA-core path
 
 
@@ -617,22 +616,7 @@ def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, o
             if m is not None and m.dtype != out.dtype:
                 raise RuntimeError("the CUDA-core conv path needs masks of the output's dtype")
     with _Probe(kind + ("_tc" if use_tc else ""), spec):
-        if use_tc and NSPLIT_256 and d.Cout == 256 and not d.split and not planar and d.up == 1 and d.B * d.Hout * d.Wout >= 2 * 148 * 128:
-            # A 256-output-channel layer as two 128-channel halves: the BN = 128 kernel runs in pair mode (two tiles per streamed weight slice, four
-            # accumulator buffers), which the BN = 256 kernel cannot (a pair would fill TMEM and lose the MMA / epilogue overlap).  Per tile the
-            # weight bytes from L2 halve; the input tile is read twice.  Channel-slice views: same pixel stride, pointers 128 channels apart.
-            co_dim = 0 if d.w_cos == w.stride(0) else 1
-            for h in (0, 1):
-                dh = ConvDesc()
-                ctypes.memmove(ctypes.byref(dh), ctypes.byref(d), ctypes.sizeof(ConvDesc))
-                dh.Cout = 128
-                wh = w.narrow(co_dim, 128 * h, 128)
-                wp = _tc_weights(dh, wh, cin_real if cin_real is not None else d.Cin, cin_off)
-                po = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() + 128 * h * t.element_size())
-                L.spaa_conv_tc_fwd(ctypes.byref(dh), _p(x), _p(wp), po(b), po(add), po(mask), po(mask2), po(out), po(out2), _stream())
-                _count()
-            _count(-1)                                # (the common _count() below)
-        elif use_tc:
+        if use_tc:
             wp = _tc_weights(d, w, cin_real if cin_real is not None else d.Cin, cin_off)
             L.spaa_conv_tc_fwd(ctypes.byref(d), _p(x), _p(wp), _p(b), _p(add), _p(mask), _p(mask2), _p(out), _p(out2), _stream())
         else:
