@@ -416,6 +416,10 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    // PDL: the next kernel of the stream may start its own prologue as soon as this grid's CTAs free their SMs; this grid's first access to global
+    // memory (bias, then the TMA loads / operand copies / stores of the three roles) waits for the previous grid to complete
+    pdl_launch_dependents();
+    pdl_wait();
     for (int i = threadIdx.x; i < BN; i += blockDim.x) s_bias[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
@@ -1007,6 +1011,25 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& 
     }
     const int slots = kNumSMs * P.ctas_per_sm;
     const int grid = P.total_tiles < slots ? P.total_tiles : slots;
+    static const int use_pdl = [] { const char* e = getenv("SPAA_PDL"); return e ? atoi(e) : 1; }();
+    if (use_pdl) {
+        // programmatic dependent launch: this kernel's prologue overlaps the tail of the previous kernel in the stream (tc_ptx.cuh: pdl_wait)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)(64 + 128 * P.egroups));
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, BK, F16, SPLIT>, ma, mb, P) != cudaSuccess) {
+            set_last_error("spaa_conv_tc_fwd: cudaLaunchKernelEx failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return SPAA_ERR_CUDA;
+        }
+        return SPAA_OK;
+    }
     conv_halo_kernel<BN, BK, F16, SPLIT><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P);
     return SPAA_OK;
 }

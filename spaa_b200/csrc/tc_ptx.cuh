@@ -116,6 +116,13 @@ SPAA_D void cp_async_wait(int n) {
         default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
     }
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its
+// predecessor in the stream is still running: everything before pdl_wait() (barrier initialisation, TMEM allocation, tensor-map prefetch) overlaps the
+// predecessor's tail; pdl_wait() returns when the predecessor grid has completed and its memory operations are visible.  Without the launch
+// attribute both are no-ops.
+SPAA_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SPAA_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 SPAA_D uint4 lds128(uint32_t smem_addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
