@@ -823,7 +823,7 @@ def main():
                          "BASELINE.json's 2e-3 bar; bf16: pure bf16 storage; fp32: exact CUDA-core convolutions (1e-5 parity mode)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the captured CUDA graph")
     ap.add_argument("--skip-train", action="store_true", help="omit the PCNet training leg")
-    ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16", "fp16", "bf16x3"])
     ap.add_argument("--no-fold-bn", action="store_true", help="run the external classifier as the stock module (BatchNorm layers not folded)")
     ap.add_argument("--skip-side-legs", action="store_true", help="profiling runs only: omit the fp32 and torch-CUDA side measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")

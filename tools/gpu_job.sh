@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_fullsize.py -q -m gpu -k "pair_mode or split or (per_layer and bf16x3) or (teacher_forced and bf16x3)" > gpurun_out/r2_t11.log 2>&1
-grep -n "^FAILED\|^E  \|passed\|failed" gpurun_out/r2_t11.log | cut -c1-300 | tail -6
 python bench.py --steps 10 --warmup 3 --skip-sweep --skip-cpu-baseline --precision bf16x3 --train-precision bf16x3 --skip-side-legs > gpurun_out/r2_b7.json 2> gpurun_out/r2_b7.err; tail -2 gpurun_out/r2_b7.err
 python - <<'PY'
 import json
