@@ -1138,9 +1138,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // BN = 128 only: four accumulator buffers keep the epilogue of one pair overlapped with the MMAs of the next.  With BN = 256 a pair fills all 512
     // TMEM columns, the overlap is lost and the layer gets SLOWER (measured: conv4_s forward 73.8 -> 100.5 us, conv4 forward unchanged), while
     // BN = 128 gains (conv5 forward 84.0 -> 72.5 us).  $SPAA_TC_PAIR=2 forces it for BN = 256 too.
-    // Split-precision mode: six times the weight bytes per tile (3.5 MB for conv4) and six times the MMA work per accumulator -- the lost overlap
-    // is negligible there and the halved weight traffic is not, so BN = 256 pairs too.
-    const bool pair_ok = use_pair && (BN == 128 || (BN == 256 && (use_pair >= 2 || d->split))) && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
+    const bool pair_ok = use_pair && (BN == 128 || (BN == 256 && use_pair >= 2)) && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
     int ctas = 1;
     size_t smem_bytes = 0;
     bool planned = false;
@@ -1185,7 +1183,7 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
                 sa = 2;
                 const int64_t sbn = (budget - 2 * (int64_t)P.a_stage_bytes) / P.b_slice_bytes;
                 P.sb = (int)(sbn > 8 ? 8 : sbn);
-                if (P.sb < ((try_pair && !d->split) ? 3 : 2)) sa = 0;   // (pair mode is only worth it with a weight ring of depth >= 3; split mode: 2)
+                if (P.sb < (try_pair ? 3 : 2)) sa = 0;               // (pair mode is only worth it with a weight ring of depth >= 3)
                 bbytes = (int64_t)P.sb * P.b_slice_bytes;
             }
             if (sa < 2) {
