@@ -107,6 +107,16 @@ int spaa_grid_sample_bwd_gather(const float* dout, const float* dout2, int64_t d
                                 int64_t rough_bstride, const int32_t* row_ptr, const int32_t* ent_p, const float* ent_w,
                                 const float* ent_m, int64_t B, int C, int Hi, int Wi, int H, int W, const float* x_for_clamp,
                                 float lo, float hi, float* dimg, float* sq, void* ws, spaa_stream_t stream);
+/* Tiled form of spaa_grid_sample_bwd_gather (bit-identical results): a block owns a 32 x 32 tile of input pixels and first copies the compact
+ * rectangle of output pixels that contribute to it into shared memory.  boxes[tile] = (y0, x0, h, w) of that rectangle (int32 x 4 per tile, tiles
+ * row-major over ceil(Hi/32) x ceil(Wi/32)); ent_l[e] = (p_e / W - y0) * w + (p_e % W - x0) for the tile of entry e's row; max_region = max h * w
+ * (C * max_region floats of shared memory).  ws: spaa_grid_sample_bwd_gather_tiled_ws_bytes, zeroed once. */
+int64_t spaa_grid_sample_bwd_gather_tiled_ws_bytes(int64_t B, int Hi, int Wi);
+int spaa_grid_sample_bwd_gather_tiled(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,
+                                      int64_t rough_bstride, const int32_t* row_ptr, const int32_t* ent_l, const float* ent_w,
+                                      const float* ent_m, const int32_t* boxes, int max_region, int64_t B, int C, int Hi, int Wi, int H,
+                                      int W, const float* x_for_clamp, float lo, float hi, float* dimg, float* sq, void* ws,
+                                      spaa_stream_t stream);
 /* dimg (+)= scatter of (dout + dout2*rough) * mask ; dimg must be zero-filled by the caller (atomic accumulate);
  * clamp01: zero the gradient where img is outside [0,1] is NOT applied here (applied by the consumer). */
 int spaa_grid_sample_bwd_input(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough,

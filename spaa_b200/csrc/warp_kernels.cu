@@ -338,6 +338,79 @@ __global__ void __launch_bounds__(kThreads) grid_sample_bwd_gather_kernel(const 
     if (sq) row_reduce_finish<1>(s, b, partial, counter, sq, red, &is_last);
 }
 
+// Tiled form of the same gather.  The plain kernel above reads, per entry, three scattered words of dout (+ dout2, rough): 4-8 cache lines per warp
+// request, 95 us at B = 32 against 75 us for the atomics path.  Here a block owns a 32 x 32 tile of INPUT pixels; the output pixels that contribute to
+// it lie in one compact rectangle (the warp is smooth), which the block first copies -- coalesced rows, dout + dout2 * rough combined -- into shared
+// memory; every entry then reads shared memory through a tile-local index precomputed with the CSR (ent_l).  Same entries, same order, same
+// arithmetic as the plain kernel: bit-identical results.
+constexpr int kGT = 32;
+__global__ void __launch_bounds__(256) grid_sample_bwd_gather_tiled_kernel(const float* __restrict__ dout, const float* __restrict__ dout2, int64_t dout2_bs,
+                                                                           const float* __restrict__ rough, int64_t rough_bs, const int* __restrict__ row_ptr,
+                                                                           const int* __restrict__ ent_l, const float* __restrict__ ent_w,
+                                                                           const float* __restrict__ ent_m, const int4* __restrict__ boxes, int C, int Hi,
+                                                                           int Wi, int W, int HW, int tiles_x, const float* __restrict__ xclamp, float lo,
+                                                                           float hi, float* __restrict__ dimg, float* __restrict__ sq,
+                                                                           float* __restrict__ partial, unsigned* __restrict__ counter) {
+    extern __shared__ float s_reg[];                       // [C][h * w] of this tile's region
+    __shared__ float red[32];
+    __shared__ bool is_last;
+    const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int4 bx = __ldg(boxes + tile);                   // y0, x0, h, w of the contributing output rectangle (h = 0: no contribution)
+    const int n = bx.z * bx.w;
+    const float* db = dout + (int64_t)b * C * HW;
+    const float* d2 = dout2 ? dout2 + (int64_t)b * dout2_bs : nullptr;
+    const float* rb = dout2 ? rough + (int64_t)b * rough_bs : nullptr;
+    for (int idx = tid; idx < n; idx += 256) {
+        const int ry = idx / bx.w, rx = idx - ry * bx.w;
+        const int p = (bx.x + ry) * W + bx.y + rx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c < C) {
+                float d = __ldg(db + (int64_t)c * HW + p);
+                if (d2) d += __ldg(d2 + (int64_t)c * HW + p) * __ldg(rb + (int64_t)c * HW + p);
+                s_reg[c * n + idx] = d;
+            }
+        }
+    }
+    __syncthreads();
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int HWi = Hi * Wi;
+    float s[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < (kGT * kGT) / 256; ++k) {
+        const int l = tid + k * 256;
+        const int qy = ty * kGT + (l >> 5), qx = tx * kGT + (l & 31);
+        if (qy < Hi && qx < Wi) {
+            const int q = qy * Wi + qx;
+            float acc[3] = {0.f, 0.f, 0.f};
+            const int e0 = __ldg(row_ptr + q), e1 = __ldg(row_ptr + q + 1);
+            for (int e = e0; e < e1; ++e) {
+                const int li = __ldg(ent_l + e);
+                const float w = __ldg(ent_w + e), m = __ldg(ent_m + e);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (c < C) {
+                        float d = s_reg[c * n + li];
+                        d *= m;                                 // same factor order as the plain gather and the scatter kernel
+                        acc[c] = fmaf(d, w, acc[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (c < C) {
+                    const int64_t o = ((int64_t)b * C + c) * HWi + q;
+                    dimg[o] = acc[c];
+                    float v = acc[c];
+                    if (xclamp) { const float x = __ldg(xclamp + o); if (!(x >= lo && x <= hi)) v = 0.f; }
+                    s[0] = fmaf(v, v, s[0]);
+                }
+            }
+        }
+    }
+    if (sq) row_reduce_finish<1>(s, b, partial, counter, sq, red, &is_last);
+}
+
 inline int blocks_for(int64_t n, int cap_mult = 8) {
     int64_t g = (n + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)kNumSMs * cap_mult;
@@ -498,6 +571,35 @@ int spaa_warp_taps(const float* grid, const float* mask, int Hi, int Wi, int H, 
 
 int64_t spaa_grid_sample_bwd_gather_ws_bytes(int64_t B, int Hi, int Wi) {
     return row_reduce_ws_bytes(B, row_reduce_nblk((int64_t)Hi * Wi, 2048), 1);
+}
+
+int64_t spaa_grid_sample_bwd_gather_tiled_ws_bytes(int64_t B, int Hi, int Wi) {
+    return row_reduce_ws_bytes(B, ((Hi + kGT - 1) / kGT) * ((Wi + kGT - 1) / kGT), 1);
+}
+
+int spaa_grid_sample_bwd_gather_tiled(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough, int64_t rough_bstride,
+                                      const int32_t* row_ptr, const int32_t* ent_l, const float* ent_w, const float* ent_m, const int32_t* boxes,
+                                      int max_region, int64_t B, int C, int Hi, int Wi, int H, int W, const float* x_for_clamp, float lo, float hi,
+                                      float* dimg, float* sq, void* ws, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(dout && row_ptr && ent_l && ent_w && ent_m && boxes && dimg && B > 0 && B < 65536 && C >= 1 && C <= 3 && Hi > 0 && Wi > 0 && H > 0 && W > 0,
+                   "spaa_grid_sample_bwd_gather_tiled: bad arguments");
+    SPAA_CHECK_ARG((dout2 == nullptr) || rough, "spaa_grid_sample_bwd_gather_tiled: dout2 needs rough");
+    SPAA_CHECK_ARG((sq == nullptr) || ws, "spaa_grid_sample_bwd_gather_tiled: sq needs the workspace");
+    const size_t smem = (size_t)C * (size_t)max_region * sizeof(float);
+    SPAA_CHECK_ARG(max_region > 0 && smem <= 160 * 1024, "spaa_grid_sample_bwd_gather_tiled: a tile's source region does not fit in shared memory (use the plain gather)");
+    static SmemOptIn opt;
+    if (smem > 48 * 1024 && !opt.ensure(grid_sample_bwd_gather_tiled_kernel, smem)) {
+        set_last_error("spaa_grid_sample_bwd_gather_tiled: cannot reserve %zu bytes of shared memory", smem);
+        return SPAA_ERR_CUDA;
+    }
+    const int tiles_x = (Wi + kGT - 1) / kGT, tiles_y = (Hi + kGT - 1) / kGT;
+    float* partial = (float*)ws;
+    unsigned* counter = ws ? (unsigned*)(partial + B * tiles_x * tiles_y) : nullptr;
+    grid_sample_bwd_gather_tiled_kernel<<<dim3((unsigned)(tiles_x * tiles_y), (unsigned)B), 256, smem, (cudaStream_t)stream>>>(
+        dout, dout2, dout2_bstride, rough, rough_bstride, row_ptr, ent_l, ent_w, ent_m, (const int4*)boxes, C, Hi, Wi, W, H * W, tiles_x, x_for_clamp, lo, hi,
+        dimg, sq, partial, counter);
+    SPAA_CHECK_LAUNCH("spaa_grid_sample_bwd_gather_tiled");
+    return SPAA_OK;
 }
 
 int spaa_grid_sample_bwd_gather(const float* dout, const float* dout2, int64_t dout2_bstride, const float* rough, int64_t rough_bstride,

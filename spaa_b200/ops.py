@@ -354,6 +354,9 @@ def grid_sample_bwd_input(dout: Tensor, grid: Tensor, in_hw, *, mask: Optional[T
     return dimg
 
 
+GATHER_TILED = os.environ.get("SPAA_GATHER_TILED", "1") not in ("", "0")      # tiled (shared-memory staged) form of the deterministic warp adjoint
+
+
 class WarpAdjoint:
     """CSR form of the adjoint of a FIXED bilinear warp (planar grid [2,H,W] shared by the batch, optional mask [H*W]): built once per attack,
     then every backward is a gather (grid_sample_bwd_gather) -- deterministic, no atomics, no zero-fill, squared norm fused."""
@@ -378,6 +381,26 @@ class WarpAdjoint:
         self.ent_m = (m[self.ent_p.long()] if m is not None else torch.ones(n_used, device=dev)).contiguous()
         self.row_ptr = torch.searchsorted(q_sorted[:n_used].contiguous(), torch.arange(HWi + 1, device=dev)).to(torch.int32).contiguous()
         self.in_hw, self.out_hw = (Hi, Wi), (H, W)
+        # tiled gather (spaa_grid_sample_bwd_gather_tiled): per 32 x 32 tile of input pixels the rectangle of output pixels that contribute to it,
+        # and every entry's index inside its tile's rectangle
+        GT = 32
+        tx_n, ty_n = (Wi + GT - 1) // GT, (Hi + GT - 1) // GT
+        q_used = q_sorted[:n_used]
+        tile = (q_used // Wi) // GT * tx_n + (q_used % Wi) // GT
+        py, px = self.ent_p.long() // W, self.ent_p.long() % W
+        nt = tx_n * ty_n
+        big = torch.full((nt,), 1 << 30, dtype=torch.long, device=dev)
+        y0 = big.clone().scatter_reduce_(0, tile, py, "amin")
+        x0 = big.clone().scatter_reduce_(0, tile, px, "amin")
+        y1 = torch.full((nt,), -1, dtype=torch.long, device=dev).scatter_reduce_(0, tile, py, "amax")
+        x1 = torch.full((nt,), -1, dtype=torch.long, device=dev).scatter_reduce_(0, tile, px, "amax")
+        empty = y1 < 0
+        hh = torch.where(empty, torch.zeros_like(y1), y1 - y0 + 1)
+        ww = torch.where(empty, torch.zeros_like(x1), x1 - x0 + 1)
+        y0, x0 = torch.where(empty, torch.zeros_like(y0), y0), torch.where(empty, torch.zeros_like(x0), x0)
+        self.boxes = torch.stack((y0, x0, hh, ww), 1).to(torch.int32).contiguous()
+        self.ent_l = ((py - y0[tile]) * ww[tile] + (px - x0[tile])).to(torch.int32).contiguous()
+        self.max_region = int((hh * ww).max().item()) if nt else 0
 
 
 def grid_sample_bwd_gather(adj: WarpAdjoint, dout: Tensor, *, dout2: Optional[Tensor] = None, rough: Optional[Tensor] = None,
@@ -396,6 +419,12 @@ def grid_sample_bwd_gather(adj: WarpAdjoint, dout: Tensor, *, dout2: Optional[Te
         assert dout2.stride(1) == H * W and dout2.stride(3) == 1 and rough.stride(1) == H * W
         db, rb = dout2.stride(0), _bstride(rough, B)
     L = lib()
+    if GATHER_TILED and 0 < adj.max_region * C * 4 <= 160 * 1024:
+        ws = workspace("gs_gather_tiled", L.spaa_grid_sample_bwd_gather_tiled_ws_bytes(B, Hi, Wi), dout.device) if sq is not None else None
+        L.spaa_grid_sample_bwd_gather_tiled(_p(dout), _p(dout2), db, _p(rough) if dout2 is not None else None, rb, _p(adj.row_ptr), _p(adj.ent_l), _p(adj.ent_w),
+                                            _p(adj.ent_m), _p(adj.boxes), adj.max_region, B, C, Hi, Wi, H, W,
+                                            _p(_f32c(x_for_clamp)) if x_for_clamp is not None else None, float(lo), float(hi), _p(dimg), _p(sq), _p(ws), _stream()); _count()
+        return dimg
     ws = workspace("gs_gather", L.spaa_grid_sample_bwd_gather_ws_bytes(B, Hi, Wi), dout.device) if sq is not None else None
     L.spaa_grid_sample_bwd_gather(_p(dout), _p(dout2), db, _p(rough) if dout2 is not None else None, rb, _p(adj.row_ptr), _p(adj.ent_p), _p(adj.ent_w),
                                   _p(adj.ent_m), B, C, Hi, Wi, H, W, _p(_f32c(x_for_clamp)) if x_for_clamp is not None else None, float(lo), float(hi),

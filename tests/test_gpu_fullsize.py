@@ -310,6 +310,14 @@ def test_fullsize_colour_loss_ssim_warp_vs_oracle():
     gpr, = torch.autograd.grad((wr * cot).sum(), pr)
     dimg = ops.grid_sample_bwd_input(cot, grid, PRJ_HW, mask=m.flat_mask())
     assert maxerr(dimg, gpr) <= 1e-4 * max(1.0, gpr.abs().max().item())
+    # deterministic gather form of the same adjoint (per-attack CSR map; tiled kernel) with the fused clamp-masked squared norm
+    adj = ops.WarpAdjoint(grid, PRJ_HW, m.flat_mask())
+    assert adj.max_region * 3 * 4 <= 160 * 1024, adj.max_region
+    sq = torch.empty(B, device=dev())
+    dg = ops.grid_sample_bwd_gather(adj, cot, sq=sq, x_for_clamp=prj)
+    assert maxerr(dg, gpr) <= 1e-4 * max(1.0, gpr.abs().max().item())
+    assert maxerr(sq, (gpr.double() ** 2).flatten(1).sum(1)) <= 1e-4 * (gpr.double() ** 2).flatten(1).sum(1).max().item()
+    assert torch.equal(dg, ops.grid_sample_bwd_gather(adj, cot))
 
 
 @pytest.mark.parametrize("name", ["vgg16", "inception_v3"])

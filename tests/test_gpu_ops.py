@@ -183,6 +183,15 @@ def test_grid_sample_forward_backward(shared_grid):
         close(sq, (gx.double() ** 2).flatten(1).sum(1), 1e-5, 1e-5, "fused squared norm")
         again = ops.grid_sample_bwd_gather(adj, c1.to(dev()), dout2=c2.to(dev()), rough=rough.to(dev()))
         assert torch.equal(again, dimg2), "the gather adjoint must be deterministic"
+        # the tiled (shared-memory staged) kernel and the plain one run the same entries in the same order: bit-identical gradient and norm
+        assert ops.GATHER_TILED and adj.max_region > 0
+        ops.GATHER_TILED = False
+        try:
+            sq_p = torch.empty(B, device=dev())
+            plain = ops.grid_sample_bwd_gather(adj, c1.to(dev()), dout2=c2.to(dev()), rough=rough.to(dev()), sq=sq_p, x_for_clamp=img.to(dev()))
+        finally:
+            ops.GATHER_TILED = True
+        assert torch.equal(plain, dimg2) and torch.allclose(sq_p, sq, rtol=1e-6, atol=0), "tiled and plain gather differ"
         no_mask = ops.WarpAdjoint(gp.to(dev()), (Hi, Wi))
         d3 = ops.grid_sample_bwd_gather(no_mask, c1.to(dev()))
         y3 = F.grid_sample(x, gq.expand(B, -1, -1, -1), align_corners=True)
