@@ -562,13 +562,14 @@ def run_ours(args):
     cold_iters = 0 if args.skip_cold else 50
     if cold_iters:
         cam_best, prj_best = spaa(pcnet, clf, None, targets, True, scene_host.to(dev, non_blocking=True), D_THR, STEALTH, dev, SETUP, iters=cold_iters,
-                                  graph=not args.no_graph, fold_bn=fold_bn)
+                                  graph=not args.no_graph, fold_bn=fold_bn, deterministic=args.deterministic)
         out_cam.copy_(cam_best, non_blocking=True)
         out_prj.copy_(prj_best, non_blocking=True)
     torch.cuda.synchronize()
     cold_s = time.perf_counter() - t0
     # the engine spaa() built for this job (kept warm across calls of a sweep: buffers + captured CUDA graph)
-    A = attack_engine(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=not args.no_graph, fold_bn=fold_bn)
+    A = attack_engine(pcnet, clf, targets, True, scene.to(dev), D_THR, STEALTH, dev, SETUP, graph=not args.no_graph, fold_bn=fold_bn,
+                      deterministic=args.deterministic)
     for _ in range(args.warmup):                            # 2 eager iterations, then the CUDA graph is captured and replayed
         A.step()
     torch.cuda.synchronize()
@@ -828,6 +829,7 @@ def main():
     ap.add_argument("--skip-side-legs", action="store_true", help="profiling runs only: omit the fp32 and torch-CUDA side measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     ap.add_argument("--skip-sweep", action="store_true", help="omit the attack-sweep leg (BASELINE configs[4])")
+    ap.add_argument("--deterministic", action="store_true", help="warp adjoint as the atomics-free tiled gather (bit-reproducible run to run)")
     ap.add_argument("--skip-cold", action="store_true", help="profiling runs only: omit the cold first spaa(iters=50) call (e2e_cold)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
