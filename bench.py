@@ -648,7 +648,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     cam_best, prj_best = spaa(pcnet, clf, None, targets, True, scene_host.to(dev, non_blocking=True), D_THR, STEALTH, dev, SETUP, iters=args.steps,
-                              graph=not args.no_graph, fold_bn=fold_bn)
+                              graph=not args.no_graph, fold_bn=fold_bn, deterministic=args.deterministic)
     out_cam.copy_(cam_best, non_blocking=True)
     out_prj.copy_(prj_best, non_blocking=True)
     torch.cuda.synchronize()
