@@ -269,6 +269,9 @@ int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t
  * when the images come from the nn.Module API instead of the fused warp kernel.  dtype: 1 bf16, 2 fp16. */
 int spaa_pack_nhwc16(const float* x, int Cx, const float* surf, int Cs, int64_t surf_bstride, void* out16, int dtype, int64_t B,
                      int64_t HW, spaa_stream_t stream);
+/* dst (bf16) = src (fp16), n elements (a multiple of 8), same layout: the X operand of the tensor-core backward-weight kernel in the 'fp16' training mode
+ * (fp16 forward activations, bf16 gradients; tcgen05 kind::f16 needs both operands in one format).  No reference counterpart (cuDNN wgrad reads fp32). */
+int spaa_half_to_bf16(const void* src, void* dst, int64_t n, spaa_stream_t stream);
 /* The same operand for the split-precision ("fp32-accurate", spaa_conv_desc.split) tensor-core mode: [B,HW,48] bf16 = three parts h, m, l of every
  * one of the 16 (zero-padded) channels, [h(16) | m(16) | l(16)] per pixel, v = h + m + l to 24 significand bits.  Stands where the reference's fp32
  * F.conv2d reads its fp32 input (models.py:223,231,239). */

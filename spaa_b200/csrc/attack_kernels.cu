@@ -221,6 +221,24 @@ __global__ void __launch_bounds__(kThreads) pack_nhwc16_split3_kernel(const floa
     }
 }
 
+// fp16 -> bf16 copy of an activation tensor (any dense layout: n elements, n % 8 == 0).  The 'fp16' training mode keeps its forward activations in fp16
+// (the storage that meets the 2e-3 bar) while its gradients are bf16, and tcgen05 kind::f16 wants both backward-weight operands in one format: the X
+// operand is re-rounded to bf16 right before the backward-weight launch (3 fewer mantissa bits in the weight gradient only).
+__global__ void __launch_bounds__(kThreads) half_to_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n8) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 u = __ldg(src + i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+            o[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // PerC-AL projection (perc_al/__init__.py:211-215, :15-18)
 __global__ void __launch_bounds__(kThreads) percal_project_kernel(const float* __restrict__ base, int64_t base_bs, float* __restrict__ delta,
                                                                   float* __restrict__ xq, float* __restrict__ xsum, float* __restrict__ l2sum, int64_t HW,
@@ -415,6 +433,15 @@ int spaa_select_cotangent_packed(const float* g0, const float* g1, const uint8_t
     if (dtype == 2) select_cot_packed_kernel<true><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
     else select_cot_packed_kernel<false><<<row_grid(HW, B, 1), kThreads, 0, (cudaStream_t)stream>>>(g0, g1, sel, act, mask_mode, (uint4*)out16, HW);
     SPAA_CHECK_LAUNCH("spaa_select_cotangent_packed");
+    return SPAA_OK;
+}
+
+int spaa_half_to_bf16(const void* src, void* dst, int64_t n, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(src && dst && n > 0 && (n & 7) == 0, "spaa_half_to_bf16: n must be a positive multiple of 8");
+    int64_t blocks = (n / 8 + kThreads - 1) / kThreads;
+    if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+    half_to_bf16_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, n / 8);
+    SPAA_CHECK_LAUNCH("spaa_half_to_bf16");
     return SPAA_OK;
 }
 

@@ -151,10 +151,18 @@ class _Stack:
         hw = lambda t: (t.shape[2], t.shape[3])
         B = (d_pre6 if d_pre6 is not None else d_pre6_packed).shape[0]
 
+        bf16_of = {}                                   # 'fp16' mode: bf16 copies of the fp16 forward activations, one per tensor (x1, x2 feed two layers each)
+
         def wgrad(name, inp, dy, x_offset=0):
             if pg is not None and (name + ".weight") in pg:
                 if inp.shape[0] == 1 and B > 1:
                     inp = inp.expand(B, -1, -1, -1)
+                if inp.dtype == torch.float16 and dy.dtype == torch.bfloat16 and inp.is_contiguous(memory_format=torch.channels_last) and inp.numel() % 8 == 0:
+                    # tcgen05 kind::f16 wants both backward-weight operands in one format: re-round the fp16 activation to bf16 (weight gradient only)
+                    key = inp.data_ptr()
+                    if key not in bf16_of:
+                        bf16_of[key] = ops.half_to_bf16(inp)
+                    inp = bf16_of[key]
                 ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset, split=s3 and inp.dtype != torch.float32)
 
         def packed_input():
@@ -175,7 +183,7 @@ class _Stack:
         in_hw = hw(S["packed"]) if S.get("packed") is not None else hw(S["x"])
         d7 = ops.conv_backward_data(sp["conv6"], d_pre6_packed if d_pre6_packed is not None else d_pre6, Wt("conv6"), hw(x7), mask=x7,
                                     mask_mode=MASK_POS, out_dtype=gdt, split=s3)
-        if d_pre6_packed is not None and d_pre6_packed.dtype == x7.dtype:
+        if d_pre6_packed is not None and (d_pre6_packed.dtype == x7.dtype or (x7.dtype == torch.float16 and d_pre6_packed.dtype == torch.bfloat16)):
             wgrad("conv6", x7, d_pre6_packed)                       # tensor-core backward-weight: padded 16-channel cotangent (3 real)
         elif d_pre6 is not None:
             wgrad("conv6", x7, d_pre6)

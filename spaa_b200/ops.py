@@ -324,6 +324,15 @@ def pack_nhwc16(x: Tensor, surf: Optional[Tensor], dtype, split: bool = False, o
     return out
 
 
+def half_to_bf16(x: Tensor) -> Tensor:
+    """bf16 copy of a dense fp16 tensor (same memory format)."""
+    assert x.dtype == torch.float16 and x.numel() % 8 == 0
+    out = torch.empty_like(x, dtype=torch.bfloat16)           # preserve_format: same strides
+    assert out.stride() == x.stride()
+    lib().spaa_half_to_bf16(_p(x), _p(out), x.numel(), _stream()); _count()
+    return out
+
+
 def select_cotangent_packed(g0: Tensor, g1: Optional[Tensor], sel: Optional[Tensor], act: Optional[Tensor], mask_mode: int, out: Tensor) -> Tensor:
     """select_cotangent for 3-channel images, written as zero-padded 16-channel NHWC (`out`: [B,16,H,W] channels-last)."""
     B, C, H, W = g0.shape

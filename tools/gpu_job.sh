@@ -1,11 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for i in 1 2; do
-python bench.py --steps 20 --warmup 5 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-train > gpurun_out/r2_b8_a$i.json 2> gpurun_out/r2_b8.err
-python bench.py --steps 20 --warmup 5 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-train --deterministic > gpurun_out/r2_b8_d$i.json 2>> gpurun_out/r2_b8.err
+python -m pytest tests/test_gpu_models.py -q -m gpu -s -k "train_pcnet" > gpurun_out/r2_t13.log 2>&1
+grep -n "^FAILED\|^E  \|passed\|failed\|^losses" gpurun_out/r2_t13.log | cut -c1-300 | tail -12
+for tp in fp16 bf16; do
+python bench.py --steps 10 --warmup 3 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-cold --train-precision $tp > gpurun_out/r2_b9_$tp.json 2> gpurun_out/r2_b9.err; tail -1 gpurun_out/r2_b9.err
 done
 python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r2_b8_*.json')):
-    d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['e2e']['value'], d['e2e_cold']['value'])
+import json
+for tp in ('fp16','bf16'):
+    d=json.loads(open(f'gpurun_out/r2_b9_{tp}.json').read().strip().splitlines()[-1]); print(tp, d['train']['value'], d['train']['phases'])
 PY
