@@ -438,10 +438,10 @@ class _RefineFn(torch.autograd.Function):
         g = coarse.unsqueeze(0)
         w = [net.grid_refine_net[i] for i in _REFINE_IDX]
         need_grad = any(p.requires_grad for p in params) or coarse.requires_grad
-        # bf16 TRAINING: the three inner layers run on the tensor-core kernels (2-channel grid zero-padded to 16 NHWC channels, bf16 activations
+        # 16-bit TRAINING ('bf16' and 'fp16' modes): the three inner layers run on the tensor-core kernels (2-channel grid zero-padded to 16 NHWC channels, bf16 activations
         # and gradients, fp32 accumulation) -- on CUDA cores this B = 1 net cost 0.55 ms of a 4.1 ms step.  The last layer (LeakyReLU, residual
         # after the activation, fp32 output added to the fp32 coarse grid) and every frozen-model use (the attacks) stay exact fp32.
-        tc = need_grad and getattr(net, "precision", "fp32") == "bf16" and ops.TC_ENABLED
+        tc = need_grad and getattr(net, "precision", "fp32") in ("bf16", "fp16") and ops.TC_ENABLED       # (bf16 inside, in both 16-bit training modes)
         gp = None
         if tc:
             gp = ops.pack_nhwc16(g, None, torch.bfloat16)
