@@ -189,6 +189,11 @@ int spaa_conv_bwd_weight(const spaa_conv_desc* d, const void* in, const void* do
  * Weights are packed once per layer and direction into bf16 [tap][Cout][Cin] by spaa_conv_tc_pack_weights (which reads
  * the fp32 parameter through d->w_* / d->flip). */
 int spaa_conv_tc_supported(const spaa_conv_desc* d);
+/* The launch plan spaa_conv_tc_fwd would use for this layer (host arithmetic only, no CUDA call; SPAA_ERR_UNSUPPORTED when the halo kernel
+ * does not cover it).  plan[12] = {CTAs per SM, epilogue warp groups, TMEM accumulator buffers, input stages, weight-ring slices (0 = weights
+ * resident in shared memory), operand-ring slots per group, staging blocks per warp - 1, pair mode, dynamic shared memory bytes, tiles,
+ * threads per CTA, weights resident}.  has_* say which epilogue operands the call will pass. */
+int spaa_conv_tc_plan(const spaa_conv_desc* d, int has_add, int has_mask, int has_mask2, int32_t* plan);
 int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d);
 /* cin_real / cin_offset: the fp32 parameter has cin_real input channels which sit at tensor channels
  * [cin_offset, cin_offset + cin_real) of a zero-padded d->Cin-channel NHWC activation (3-, 6-channel images padded to 16). */

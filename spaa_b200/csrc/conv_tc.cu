@@ -21,6 +21,7 @@
 #include "tc_ptx.cuh"
 #include "../../include/spaa_b200.h"
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 #include <string>
 #include <cstring>
@@ -343,6 +344,7 @@ struct HaloParams {
     int32_t pair;                      // 1: the MMA issuer works on TWO tiles per weight pass (see conv_halo_kernel); a_pair_bytes = offset of the second tile's A planes in a stage
     int32_t a_pair_bytes;
     int32_t e_stage_bytes;             // output staging blocks of the 4 epilogue warps (16-bit NHWC output only)
+    int32_t e_dbuf;                    // 1: two staging blocks per warp (epilogue_nhwc16)
     int32_t e_slots, e_nops;           // epilogue operand ring: slots of e_nops x 8 KB (0 slots: no ring)
     uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
     int32_t epi_flags, out_planar;
@@ -370,6 +372,200 @@ template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint
     return d;
 }
 
+// Tensor maps of the 16-bit NHWC outputs, one per output phase (the sub-lattice (py, px) of an up-sampling layer is its own strided view):
+// m[ph] = out, m[4 + ph] = out2.  Box = {32 channels, 8 x, 4 y, 1 image} = the 2 KB staging block of one epilogue warp, 64-byte swizzle.
+struct alignas(64) HaloOutMaps { CUtensorMap m[2 * kMaxPhases]; };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue of the 16-bit NHWC layers (every mode but the split-precision one), round 2.
+// The round-1 epilogue spent ~250-390 warp instructions per (32 rows x 32 channels) unit -- 64-bit index arithmetic recomputed per unit,
+// 32 generic loads for the bias, a staged LDS + STG copy with per-row predicates -- on 8 epilogue warps per SM whose dependent chains ran at
+// ~8 clk per instruction (ncu source page, profiles/r2_epilogue_sass.md): the narrow layers reached 0.35 of the HBM roofline with every pipe idle.
+// This version: 32-bit element offsets with everything tile-invariant hoisted, bias through LDS.128, operands read from the ring 8 channels at
+// a time right where they are used (half the registers, so more epilogue warps per SM), and the output block leaves through ONE TMA tile store
+// per unit issued by lane 0 (edge clipping by the tensor map, no per-row predicates, no L1 round trip).  The accumulator buffer is released right
+// after the last tcgen05.ld of the tile, not after its stores.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, bool F16>
+SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t tmem_base, uint32_t e_ring, uint32_t bias_u32, uint64_t* tfull,
+                            uint64_t* tempty, int warp, int lane) {
+    const int EG = P.egroups, NPH = P.nphases;
+    const int eg = (warp - 2) >> 2, q = warp & 3;
+    if (eg >= EG) return;
+    const uint32_t acc_cols = (uint32_t)(NPH * BN);
+    const int nacc_mask = P.nbuf - 1;                               // nbuf is 1, 2 or 4
+    const int nacc_shift = P.nbuf == 4 ? 2 : (P.nbuf == 2 ? 1 : 0);
+    const int per_img = P.tiles_x * P.tiles_y;
+    const bool has_add = P.add != nullptr, has_mask = P.mask != nullptr, has_out2 = P.out2 != nullptr, has_bias = P.bias != nullptr;
+    const bool relu = (P.epi_flags & SPAA_EPI_RELU) != 0;
+    constexpr int NCH = BN / 32;
+    const int S = P.e_slots;                                        // 0: no operand ring
+    const uint32_t slot_bytes = (uint32_t)P.e_nops * 8192u;
+    const int ci = lane >> 2, cc = lane & 3;                        // cooperative copy mapping: x pixel of the row group, 16-byte chunk
+    const uint32_t e_warp = e_ring + (uint32_t)(eg * S) * slot_bytes + (uint32_t)q * 2048u;
+    uint32_t own_off[4], coop_off[4];                               // byte offsets inside a 2 KB warp block: [row][16-byte chunk ^ ((row >> 1) & 3)]
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        own_off[g] = (uint32_t)lane * 64u + (uint32_t)((g ^ ((lane >> 1) & 3)) * 16);
+        const int rk = 8 * g + ci;
+        coop_off[g] = (uint32_t)rk * 64u + (uint32_t)((cc ^ ((rk >> 1) & 3)) * 16);
+    }
+    // output staging: TWO blocks per warp ([out | out2] each), so that the TMA store of one unit is still reading while the next unit is written
+    const uint32_t stage_blk = has_out2 ? 4096u : 2048u, stage_flip = P.e_dbuf ? stage_blk : 0u;
+    const uint32_t o_stage = e_ring + (uint32_t)(EG * S) * slot_bytes + (uint32_t)(eg * 4 + q) * (P.e_dbuf ? 2u : 1u) * stage_blk;
+    uint32_t stage_sel = 0;
+    const uint32_t mask_slot_off = has_add ? 8192u : 0u, mask2_slot_off = mask_slot_off + (has_mask ? 8192u : 0u);
+    // geometry in 32-bit ELEMENT offsets (the host routes tensors of >= 2^31 elements elsewhere)
+    const int up = P.up;
+    const uint32_t ps = (uint32_t)P.out_ps;
+    const uint32_t row_el = (uint32_t)P.Wout * ps;
+    const uint32_t kstep = (uint32_t)up * row_el;
+    const uint32_t add_bs = (uint32_t)P.add_bs, mask_bs = (uint32_t)P.mask_bs;
+    const uint16_t* const add_p = (const uint16_t*)P.add;
+
+    const int tstep = EG * (int)gridDim.x, tile0 = (int)blockIdx.x + eg * (int)gridDim.x;
+    // tile -> (image, tile row, tile column) without per-tile divisions: a group's tiles are tstep apart
+    const int g_db = tstep / per_img, g_rem = tstep - g_db * per_img;
+    const int g_dty = g_rem / P.tiles_x, g_dtx = g_rem - g_dty * P.tiles_x;
+    auto tile_step = [&](int& tb, int& tty, int& ttx) {
+        ttx += g_dtx;
+        if (ttx >= P.tiles_x) { ttx -= P.tiles_x; ++tty; }
+        tty += g_dty;
+        if (tty >= P.tiles_y) { tty -= P.tiles_y; ++tb; }
+        tb += g_db;
+    };
+    const int b0 = tile0 / per_img, t0 = tile0 - b0 * per_img;
+    const int ty0 = t0 / P.tiles_x, tx0 = t0 - ty0 * P.tiles_x;
+
+    // operand prefetch: unit = (tile, phase, 32-channel chunk), S - 1 units ahead of the unit being written, one cp.async group per unit
+    int pf_tile = tile0, pf_ph = 0, pf_c = 0, pf_slot = 0, pf_b = b0, pf_ty = ty0, pf_tx = tx0;
+    auto issue = [&]() {
+        if (pf_tile < P.total_tiles) {
+            const int cox = (pf_tx * HTW + ci) * up + (pf_ph & 1);
+            const int coy0 = (pf_ty * HTH + q * 4) * up + (pf_ph >> 1);
+            if (cox < P.Wout && pf_c * 32 < P.Cout) {
+                const uint32_t pix = (uint32_t)coy0 * row_el + (uint32_t)cox * ps + (uint32_t)(pf_c * 32 + cc * 8);
+                const int nrow = P.Hout - coy0;                     // row k of the warp's four exists iff k * up < nrow
+                uint32_t d = e_warp + (uint32_t)pf_slot * slot_bytes;
+                if (has_add) {
+                    const uint16_t* sp = add_p + ((uint32_t)pf_b * add_bs + pix);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (k * up < nrow) cp_async16(d + coop_off[k], sp + k * kstep);
+                    d += 8192;
+                }
+                if (has_mask) {
+                    const uint16_t* sp = P.mask + ((uint32_t)pf_b * mask_bs + pix);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (k * up < nrow) cp_async16(d + coop_off[k], sp + k * kstep);
+                    d += 8192;
+                }
+                if (has_out2) {
+                    const uint16_t* sp = P.mask2 + ((uint32_t)pf_b * mask_bs + pix);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (k * up < nrow) cp_async16(d + coop_off[k], sp + k * kstep);
+                }
+            }
+            if (++pf_c == NCH) {
+                pf_c = 0;
+                if (++pf_ph == NPH) { pf_ph = 0; pf_tile += tstep; tile_step(pf_b, pf_ty, pf_tx); }
+            }
+            if (++pf_slot == S) pf_slot = 0;
+        }
+        cp_async_commit();
+    };
+    if (S) for (int d = 0; d < S - 1; ++d) issue();
+    int cs = 0;                                                     // ring slot of the unit being consumed
+
+    int local = eg;
+    int b = b0, ty = ty0, tx = tx0;
+    for (int tile = tile0; tile < P.total_tiles; tile += tstep, local += EG, tile_step(b, ty, tx)) {
+        const int acc = local & nacc_mask;
+        const uint32_t tpar = (uint32_t)((local >> nacc_shift) & 1);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols;
+        const int x0 = tx * HTW, y0 = ty * HTH + q * 4;            // the warp's 8 x 4 pixel block in the phase's (sub-sampled) output view
+        bool waited = false;
+        for (int ph = 0; ph < NPH; ++ph) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t sa16 = e_warp + (uint32_t)cs * slot_bytes;
+                if (S) {
+                    cp_async_wait(S - 2);                          // this unit's operands have landed (every lane waits for its own copies) ...
+                    __syncwarp();                                   // ... and everybody's; all lanes are also done reading the previous unit's slot,
+                    issue();                                        // which the prefetch S - 1 units ahead now overwrites
+                    if (++cs == S) cs = 0;
+                }
+                if (!waited) { mbar_wait(tfull + acc, tpar); tc_fence_after(); waited = true; }
+                uint32_t r[32];
+                tmem_ld32(t_row + (uint32_t)(ph * BN + c0), r);
+                if (ph == NPH - 1 && c0 == BN - 32) {              // last read of this accumulator buffer: hand it back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + acc);
+                }
+                if (c0 >= P.Cout) continue;
+                if (lane == 0) {                                    // the TMA store that last read THIS staging block is done with it
+                    if (stage_flip) bulk_wait_read1(); else bulk_wait_read0();
+                }
+                __syncwarp();
+                const uint32_t stg = o_stage + stage_sel;
+                uint4 ca, cm, cm2;                                  // operands of the 8-channel group being processed, fetched one group ahead
+                ca = cm = cm2 = make_uint4(0, 0, 0, 0);
+                if (has_add) ca = lds128(sa16 + own_off[0]);
+                if (has_mask) cm = lds128(sa16 + mask_slot_off + own_off[0]);
+                if (has_out2) cm2 = lds128(sa16 + mask2_slot_off + own_off[0]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 na, nm, nm2;
+                    na = nm = nm2 = make_uint4(0, 0, 0, 0);
+                    if (g < 3) {
+                        if (has_add) na = lds128(sa16 + own_off[g + 1]);
+                        if (has_mask) nm = lds128(sa16 + mask_slot_off + own_off[g + 1]);
+                        if (has_out2) nm2 = lds128(sa16 + mask2_slot_off + own_off[g + 1]);
+                    }
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[g * 8 + k]);
+                    if (has_bias) {
+                        const uint4 ba = lds128_const(bias_u32 + (uint32_t)(c0 + g * 8) * 4u), bb = lds128_const(bias_u32 + (uint32_t)(c0 + g * 8 + 4) * 4u);
+                        v[0] += __uint_as_float(ba.x); v[1] += __uint_as_float(ba.y); v[2] += __uint_as_float(ba.z); v[3] += __uint_as_float(ba.w);
+                        v[4] += __uint_as_float(bb.x); v[5] += __uint_as_float(bb.y); v[6] += __uint_as_float(bb.z); v[7] += __uint_as_float(bb.w);
+                    }
+                    if (has_add) {
+                        const uint32_t w4[4] = {ca.x, ca.y, ca.z, ca.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = unpack2<F16>(w4[e]);
+                            v[e * 2] += f.x; v[e * 2 + 1] += f.y;
+                        }
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+                    }
+                    // pack to 16 bit, then apply the ReLU masks of the backward pass on the packed pairs (AND with a per-half "> 0" bit mask:
+                    // the same bits as selecting 0.f before the conversion)
+                    uint4 pk = make_uint4(pack2<F16>(v[0], v[1]), pack2<F16>(v[2], v[3]), pack2<F16>(v[4], v[5]), pack2<F16>(v[6], v[7]));
+                    if (has_mask) { pk.x &= posmask2(cm.x); pk.y &= posmask2(cm.y); pk.z &= posmask2(cm.z); pk.w &= posmask2(cm.w); }
+                    if (has_out2)
+                        sts128(stg + 2048u + own_off[g], make_uint4(pk.x & posmask2(cm2.x), pk.y & posmask2(cm2.y), pk.z & posmask2(cm2.z), pk.w & posmask2(cm2.w)));
+                    sts128(stg + own_off[g], pk);
+                    ca = na; cm = nm; cm2 = nm2;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&OM.m[ph], stg, c0, x0, y0, b);
+                    if (has_out2) tma_store_4d(&OM.m[kMaxPhases + ph], stg + 2048u, c0, x0, y0, b);
+                    bulk_commit();
+                }
+                stage_sel ^= stage_flip;
+            }
+        }
+    }
+    cp_async_wait(0);
+    if (lane == 0) bulk_wait0();
+}
+
 // SPLIT (bf16 only): "fp32-accurate" split-precision mode.  Every fp32 activation / gradient / weight value v is stored as THREE bf16 numbers
 // h = bf16(v), m = bf16(v - h), l = bf16(v - h - m)  (3 x 8 = 24 significand bits, fp32's exponent range), an NHWC tensor of logical C channels
 // as [h(C) | m(C) | l(C)] = 3C physical channels.  A product v*w is the sum of the six part products hh + hm + mh + mm + hl + lh (the dropped
@@ -378,9 +574,14 @@ template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint
 // accumulator in TMEM holds small values while the small terms arrive), and the MMA issuer is unchanged.  The epilogue sums the three parts of
 // the residual operand in fp32, and writes its fp32 result v as three bf16 parts (masks act on every part; the sign of v is the sign of h).
 template <int BN, int BK, bool F16, bool SPLIT>
-__global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 64 ? 2 : 1) conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                                const __grid_constant__ HaloParams P) {
+__global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : (SPLIT ? kThreads : 640), (SPLIT && BN <= 64) ? 2 : 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloParams P,
+                 const __grid_constant__ HaloOutMaps OM) {
     static_assert(!(SPLIT && F16), "the split-precision mode stores bf16 parts");
+    // narrow layers outside the split mode: register-lean epilogue with TMA stores (epilogue_nhwc16), up to four epilogue groups.  The wide layers keep
+    // the round-1 epilogue: measured on the same box, the TMA-store epilogue cost them 4-14 % (conv4_s forward 74.0 -> 84.8 us: with one staging block
+    // per warp every chunk waits for the previous store to leave shared memory, and a second block costs a stage of the weight ring).
+    constexpr bool LEAN = !SPLIT && BN <= 64;
     constexpr int NPART = SPLIT ? 3 : 1;
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -438,6 +639,36 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
             }
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            if (P.resident && !P.pair && P.kchunks == 1) {
+                // narrow layers: ONE box set per tile and nothing else, so the per-tile cost of this loop is what bounds the layer once the epilogue
+                // keeps up -- tile coordinates advance incrementally (the two integer divisions per tile were ~70 of its ~130 instructions)
+                const int step = (int)gridDim.x;
+                const int s_db = step / per_img, s_rem = step - s_db * per_img;
+                const int s_dty = s_rem / P.tiles_x, s_dtx = s_rem - s_dty * P.tiles_x;
+                int tb = (int)blockIdx.x / per_img;
+                const int t0 = (int)blockIdx.x - tb * per_img;
+                int tty = t0 / P.tiles_x, ttx = t0 - tty * P.tiles_x;
+                const int ch0 = P.a_chunk[0], npl = P.nplanes;
+                const uint32_t tx_bytes = (uint32_t)P.a_tx_bytes;
+                for (int tile = blockIdx.x; tile < P.total_tiles; tile += step) {
+                    const int xx = (ttx * HTW + P.org_x) * P.stride, yy = (tty * HTH + P.org_y) * P.stride;
+                    mbar_wait(a_empty + sa, pa ^ 1);
+                    uint8_t* dst = a_ring + (size_t)sa * P.a_stage_bytes;
+                    mbar_expect_tx(a_full + sa, tx_bytes);
+                    tma_load_4d(dst, &map_a, a_full + sa, ch0, xx, yy, tb);
+                    if (npl == 4) {
+                        tma_load_4d(dst + (size_t)P.a_plane_bytes, &map_a, a_full + sa, ch0, xx + 1, yy, tb);
+                        tma_load_4d(dst + 2 * (size_t)P.a_plane_bytes, &map_a, a_full + sa, ch0, xx, yy + 1, tb);
+                        tma_load_4d(dst + 3 * (size_t)P.a_plane_bytes, &map_a, a_full + sa, ch0, xx + 1, yy + 1, tb);
+                    }
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    ttx += s_dtx;
+                    if (ttx >= P.tiles_x) { ttx -= P.tiles_x; ++tty; }
+                    tty += s_dty;
+                    if (tty >= P.tiles_y) { tty -= P.tiles_y; ++tb; }
+                    tb += s_db;
+                }
+            } else {
             // NT tiles per pipeline step: in pair mode one stage holds the halo boxes of TWO tiles (this CTA's tiles number 2k and 2k+1), and every
             // weight slice that arrives is used for both (see the MMA issuer)
             const int NT = P.pair ? 2 : 1;
@@ -473,6 +704,7 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                     }
                 }
             }
+            }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer ==========================================
@@ -496,6 +728,51 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
             uint32_t pa = 0, pb = 0;
             int local = 0;                                   // this CTA's tile counter: tile k uses accumulator buffer k % NACC, for the (k / NACC)-th time
             if (P.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
+            // Narrow layers (weights resident, one K chunk, no pair mode): a 128-pixel tile is 4-18 small MMAs, and the generic loop below spent ~23
+            // instructions per tap on run-time tap counts, the resident / streamed branch and re-materialised constants (~270 per tile at ~6 clk each:
+            // as long as the loads and the MMAs themselves).  Here the tap count is a compile-time constant and every per-tap quantity is a register.
+            bool fast_done = false;
+            if constexpr (BN <= 64) {
+                if (P.resident && !P.pair && P.kchunks == 1) {
+                    auto fast = [&](auto ntap_c) {
+                        constexpr int NTAP = decltype(ntap_c)::value;
+                        uint32_t ab[NTAP], df[NTAP];          // packed per-tap constants: A offset | weight slice address << 16;  TMEM column offset | first-of-phase << 16
+#pragma unroll
+                        for (int e = 0; e < NTAP; ++e) {
+                            const uint32_t te = taps[e];
+                            ab[e] = (te & 0xFFFFu) | ((b_base_lo + ((te >> 16) & 15u) * b_slice16) << 16);
+                            df[e] = (((te >> 20) & 3u) * (uint32_t)BN) | (((te >> 22) & 1u) << 16);
+                        }
+                        const int nacc_mask = NACC - 1, nacc_shift = NACC == 4 ? 2 : (NACC == 2 ? 1 : 0);
+                        for (int tile = blockIdx.x; tile < P.total_tiles; tile += (int)gridDim.x, ++local) {
+                            const int acc = local & nacc_mask;
+                            mbar_wait(tempty + acc, (uint32_t)(((local >> nacc_shift) & 1) ^ 1));
+                            const uint32_t d_base = tmem_base + (uint32_t)acc * acc_cols;
+                            mbar_wait(a_full + sa, pa);
+                            tc_fence_after();
+                            const uint32_t a_lo = a_ring_lo + (uint32_t)sa * a_stage16;
+#pragma unroll
+                            for (int e = 0; e < NTAP; ++e) {
+                                const uint32_t at = a_lo + (ab[e] & 0xFFFFu), bt = ab[e] >> 16;
+                                const uint32_t dt = d_base + (df[e] & 0xFFFFu), fresh = df[e] >> 16;
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_bf16(dt, ((uint64_t)a_hi << 32) | (uint64_t)(at + 2 * k), ((uint64_t)b_hi << 32) | (uint64_t)(bt + 2 * k), idesc,
+                                              (k == 0 && fresh) ? 0u : 1u);
+                            }
+                            umma_commit(a_empty + sa);
+                            umma_commit(tfull + acc);
+                            if (++sa == SA) { sa = 0; pa ^= 1; }
+                        }
+                    };
+                    fast_done = true;
+                    if (ntap == 9) fast(std::integral_constant<int, 9>{});
+                    else if (ntap == 4) fast(std::integral_constant<int, 4>{});
+                    else if (ntap == 1) fast(std::integral_constant<int, 1>{});
+                    else fast_done = false;
+                }
+            }
+            if (!fast_done) {
             // Pair mode (wide layers whose weights do not fit in shared memory: the K = 1152 / 2304 layers stream 590 KB of weights per 128-pixel
             // tile from L2, 85 % of the kernel's L2->SM bytes, and ran at the L2->SM bandwidth (~10 TB/s, profiles/r2_halo_ncu_full.md) with the tensor
             // pipe 63 % active): every weight slice that lands is multiplied with the A views of TWO tiles, into two accumulator buffers -- an
@@ -558,6 +835,7 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
             }
+            }   // !fast_done
         }
         __syncwarp();
     } else {
@@ -575,6 +853,14 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
         // local index = g (mod 2), i.e. accumulator buffer g, and has its own operand ring and staging blocks -- a lone warp per
         // scheduler issues one dependent instruction every ~5 clk, and the ~500-instruction chain of a 32-channel chunk was what
         // bounded every layer between the HBM-bound and the MMA-bound ones (conv3: MMA pipe idle 80 % of the time).
+        bool lean_done = false;
+        if constexpr (LEAN) {
+            if (!P.out_planar) {                                     // the 16-bit NHWC outputs of the narrow layers (fp16 / bf16 modes)
+                epilogue_nhwc16<BN, F16>(P, OM, tmem_base, smem_u32(e_ring), smem_u32(s_bias), tfull, tempty, warp, lane);
+                lean_done = true;
+            }
+        }
+        if (!lean_done) {
         const int EG = P.egroups;
         const int eg = (warp - 2) >> 2;
         const int q = warp & 3;
@@ -725,6 +1011,7 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                     }
                     continue;
                 }
+                if constexpr (!LEAN) {
                 // cooperative store mapping of this (tile, phase): instruction k writes rows 8k..8k+7 of the warp
                 const int cox = (tx * HTW + ci) * P.up + P.ph[ph].px;
                 const int coy0 = (ty * HTH + q * 4) * P.up + P.ph[ph].py;
@@ -901,12 +1188,14 @@ __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : kThreads, BN <= 6
                         __syncwarp();                                    // the staging block is rewritten by the next chunk
                     }
                 }
+                }   // !LEAN
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
         }
         cp_async_wait(0);
+        }   // !lean_done
     }
     tc_fence_before();
     __syncthreads();
@@ -1003,7 +1292,7 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, c
 constexpr int kHaloBarBytes = (8 * 4 + 8) * 8 + 16 + kMaxTaps * kMaxPhases * 4;      // a_full/a_empty/b_full/b_empty [8] + tfull/tempty [4] + tmem slot
 
 template <int BN, int BK, bool F16, bool SPLIT = false>
-int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, size_t smem_bytes, cudaStream_t st) {
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, const HaloOutMaps& OM, size_t smem_bytes, cudaStream_t st) {
     static SmemOptIn opt;
     if (!opt.ensure(conv_halo_kernel<BN, BK, F16, SPLIT>, smem_bytes, true)) {
         set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
@@ -1026,27 +1315,26 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, BK, F16, SPLIT>, ma, mb, P) != cudaSuccess) {
+        if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, BK, F16, SPLIT>, ma, mb, P, OM) != cudaSuccess) {
             set_last_error("spaa_conv_tc_fwd: cudaLaunchKernelEx failed: %s", cudaGetErrorString(cudaGetLastError()));
             return SPAA_ERR_CUDA;
         }
         return SPAA_OK;
     }
-    conv_halo_kernel<BN, BK, F16, SPLIT><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P);
+    conv_halo_kernel<BN, BK, F16, SPLIT><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P, OM);
     return SPAA_OK;
 }
 
 inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
+// The launch plan of the halo kernel for one layer: tap tables, tile grid, shared-memory / TMEM split, CTAs per SM, epilogue groups.  Depends on the
+// descriptor and on WHICH epilogue operands are present only (host arithmetic, no CUDA call: spaa_conv_tc_plan exposes it to the CPU test-suite).
 // Returns SPAA_ERR_UNSUPPORTED when the halo kernel does not cover the case (the caller then uses v1).
-int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add, const void* mask, const void* mask2,
-              void* out, void* out2, cudaStream_t st, EncodeTiledFn enc) {
+int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloParams& P, size_t& smem_bytes) {
     const int BN = bn_for(d->Cout);
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
-    const bool f16 = d->in_dtype == 2;
     const int nph = d->up * d->up;
     if (nph * BN > 512) return SPAA_ERR_UNSUPPORTED;
-    HaloParams P;
     memset(&P, 0, sizeof(P));
     P.B = d->B; P.Cin = d->Cin; P.Hin = d->Hin; P.Win = d->Win; P.Cout = d->Cout; P.Hout = d->Hout; P.Wout = d->Wout;
     const int np = d->split ? 3 : 1;
@@ -1065,7 +1353,6 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     P.nslots = d->KH * d->KW;
     P.epi_flags = d->epi_flags; P.out_planar = d->out_dtype == 0 ? 1 : 0;
     P.add_bs = d->add_bs; P.mask_bs = d->mask_bs;
-    P.bias = bias; P.add = add; P.mask = (const uint16_t*)mask; P.mask2 = (const uint16_t*)mask2; P.out = out; P.out2 = out2;
     // Measured on B200: the MMA unit applies the 128/64/32-byte swizzle to the ABSOLUTE shared-memory address bits (the same
     // function TMA used when it wrote the box), so a start address shifted by whole rows needs NO base-offset correction;
     // setting the descriptor's base_offset field to (addr >> 7) & 7 gives wrong results (tests/test_gpu_conv_tc.py).
@@ -1127,11 +1414,20 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // ---- shared-memory plan.  Layers whose accumulator is narrow (BN <= 64: the HBM-bound ones) run TWO CTAs per SM when two
     // TMEM allocations and two half-size rings fit: twice the epilogue warps and loads in flight per SM.
     const bool planar = d->out_dtype == 0;
+    const bool lean = !planar && !d->split && BN <= 64;          // epilogue_nhwc16: 32-bit element offsets, TMA tile stores
+    if (lean) {
+        const int64_t img = (int64_t)d->Hout * d->Wout * d->Cout, lim = (int64_t)1 << 31;
+        if ((int64_t)d->B * img >= lim || (add && (int64_t)(d->B - 1) * d->add_bs + img >= lim) || ((mask || mask2) && (int64_t)(d->B - 1) * d->mask_bs + img >= lim))
+            return SPAA_ERR_UNSUPPORTED;
+        if (d->up > 1 && (d->Hout < d->up || d->Wout < d->up)) return SPAA_ERR_UNSUPPORTED;
+    }
     P.e_nops = planar ? ((add && d->Cout <= 4) ? 1 : 0) : ((add ? np : 0) + (mask ? 1 : 0) + (mask2 ? 1 : 0));
     static const int max_ctas = [] { const char* e = getenv("SPAA_TC_CTAS"); return e ? atoi(e) : 2; }();
     static const int max_eg = [] { const char* e = getenv("SPAA_TC_EG"); return e ? atoi(e) : 2; }();
     static const int e_kb = [] { const char* e = getenv("SPAA_TC_EKB"); return e ? atoi(e) : -1; }();
     static const int use_pair = [] { const char* e = getenv("SPAA_TC_PAIR"); return e ? atoi(e) : 1; }();
+    static const int narrow_ctas = [] { const char* e = getenv("SPAA_TC_NCTAS"); return e ? atoi(e) : 0; }();      // experiments: force one narrow-layer plan
+    static const int narrow_eg = [] { const char* e = getenv("SPAA_TC_NEG"); return e ? atoi(e) : 0; }();
     const int64_t res_bytes = (int64_t)P.kchunks * P.nslots * P.b_slice_bytes;
     // Pair mode (two tiles per weight pass, see the MMA issuer): for the wide single-phase layers whose weights are streamed, when the launch has
     // at least two tiles per CTA.  Planned first; if its two-tile A stages leave no room for a weight ring the single-tile plan follows.
@@ -1140,8 +1436,68 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     // BN = 128 gains (conv5 forward 84.0 -> 72.5 us).  $SPAA_TC_PAIR=2 forces it for BN = 256 too.
     const bool pair_ok = use_pair && (BN == 128 || (BN == 256 && use_pair >= 2)) && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
     int ctas = 1;
-    size_t smem_bytes = 0;
+    smem_bytes = 0;
     bool planned = false;
+    if (BN <= 64 && !d->split) {
+        // ---- narrow layers (register-lean epilogue, up to 640 threads per CTA).  A plan = (CTAs per SM, epilogue groups, staging blocks per warp);
+        // accumulator buffers = what TMEM holds for that many CTAs, at least one per group.  Measured per layer at the BASELINE shapes on one box
+        // (tools/kbench.py under $SPAA_TC_NCTAS / $SPAA_TC_NEG, profiles/r2_narrow_plans.md): one CTA with four epilogue groups wins wherever its
+        // rings leave >= 3 input stages (one producer / issuer pair with the whole shared memory, weights loaded once); the fp32-planar outputs
+        // (short epilogue, no operand ring worth the name) prefer two CTAs with two groups; layers whose weights must be streamed keep the
+        // round-1 shape (two CTAs, one group, everything else for the weight ring).
+        struct Cand { int c, eg, dbuf; };
+        static const Cand nhwc_c[] = {{1, 4, 1}, {1, 4, 0}, {1, 2, 1}, {2, 2, 1}, {1, 2, 0}, {2, 2, 0}, {2, 1, 1}, {2, 1, 0}, {1, 1, 0}};
+        static const Cand planar_c[] = {{2, 2, 0}, {2, 1, 0}, {1, 2, 0}, {1, 1, 0}};
+        static const Cand stream_c[] = {{2, 1, 1}, {2, 1, 0}, {1, 2, 0}, {1, 1, 0}};
+        const bool streamed = res_bytes > 80 * 1024;
+        const Cand forced[] = {{narrow_ctas >= 2 ? 2 : 1, narrow_eg < 1 ? 1 : narrow_eg, 1}, {narrow_ctas >= 2 ? 2 : 1, narrow_eg < 1 ? 1 : narrow_eg, 0}};
+        const Cand* cands = narrow_ctas ? forced : (streamed ? stream_c : (planar ? planar_c : nhwc_c));
+        const int ncand = narrow_ctas ? 2 : (streamed ? 4 : (planar ? 4 : 9));
+        P.pair = 0;
+        P.a_pair_bytes = P.nplanes * P.a_plane_bytes;
+        P.a_stage_bytes = P.a_pair_bytes;
+        for (int pass = 0; pass < 2 && !planned; ++pass)            // pass 0: plans with a comfortable pipeline depth only; pass 1: anything that fits
+            for (int ic = 0; ic < ncand && !planned; ++ic) {
+                const Cand& C = cands[ic];
+                int nb = (512 / C.c) / (nph * BN);
+                if (nb < 1) continue;
+                if (streamed && nb > 2) nb = 2;
+                const int nbuf = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
+                if (C.eg > nbuf) continue;
+                const int total = C.c == 2 ? 108 * 1024 : 222 * 1024;
+                const int resident = res_bytes <= (C.c == 2 ? 40 : 80) * 1024 ? 1 : 0;
+                int S = 0;
+                if (P.e_nops) {
+                    const int eb = (e_kb >= 0 ? e_kb : (C.c == 2 ? 32 : 48)) * 1024;
+                    const int sl = eb / (P.e_nops * 8192 * C.eg);
+                    S = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
+                }
+                const int stage = planar ? 0 : (1 + C.dbuf) * C.eg * 4 * (mask2 ? 4096 : 2048);
+                int64_t budget = (int64_t)total - (int64_t)C.eg * S * P.e_nops * 8192 - stage;
+                while (S > 2 && budget - 2 * P.a_stage_bytes < (resident ? res_bytes : 2 * (int64_t)P.b_slice_bytes)) {
+                    --S;
+                    budget += (int64_t)C.eg * P.e_nops * 8192;
+                }
+                int64_t sa, sb, bbytes;
+                if (resident) {
+                    bbytes = res_bytes; sb = 1;
+                    sa = (budget - bbytes) / P.a_stage_bytes;
+                    if (sa < (pass == 0 ? 3 : 2)) continue;
+                } else {
+                    sa = 2;
+                    sb = (budget - 2 * (int64_t)P.a_stage_bytes) / P.b_slice_bytes;
+                    if (sb > 8) sb = 8;
+                    if (sb < (pass == 0 ? 4 : 2)) continue;
+                    bbytes = sb * P.b_slice_bytes;
+                }
+                P.nbuf = nbuf; P.egroups = C.eg; P.e_dbuf = (!planar && C.dbuf) ? 1 : 0; P.e_stage_bytes = stage; P.e_slots = S;
+                P.resident = resident; P.sb = (int)sb; P.sa = (int)(sa > 6 ? 6 : sa);
+                ctas = C.c;
+                smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
+                planned = true;
+            }
+        if (!planned) return SPAA_ERR_UNSUPPORTED;
+    }
     for (int try_pair = pair_ok ? 1 : 0; try_pair >= 0 && !planned; --try_pair) {
         P.pair = try_pair;
         P.a_pair_bytes = P.nplanes * P.a_plane_bytes;
@@ -1157,7 +1513,8 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
         // K per epilogue operand <= 640 -- and costs 3-8 % on the MMA-bound layers, whose issuing warp then shares its schedulers)
         const int k_per_pass = P.nslots * d->Cin * (d->split ? 6 : 1) / (1 + P.e_nops);
         P.egroups = (BN >= 128 && P.nbuf >= 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
-        P.e_stage_bytes = planar ? 0 : P.egroups * 4 * (mask2 ? 4096 : 2048);
+        P.e_dbuf = 0;
+        P.e_stage_bytes = planar ? 0 : (1 + P.e_dbuf) * P.egroups * 4 * (mask2 ? 4096 : 2048);
         ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
         for (;; --ctas) {
             const int total = ctas == 2 ? 108 * 1024 : 222 * 1024;
@@ -1187,6 +1544,12 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
                 bbytes = (int64_t)P.sb * P.b_slice_bytes;
             }
             if (sa < 2) {
+                if (P.e_dbuf) {                                      // single staging block per warp before giving up a CTA or an epilogue group
+                    P.e_dbuf = 0;
+                    P.e_stage_bytes /= 2;
+                    ++ctas;
+                    continue;
+                }
                 if (ctas == 1 && P.egroups == 2) {                   // a second epilogue group's ring and staging blocks do not fit: run with one
                     P.egroups = 1;
                     P.e_stage_bytes = planar ? 0 : 4 * (mask2 ? 4096 : 2048);
@@ -1204,6 +1567,22 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
     }
     if (!planned) return SPAA_ERR_UNSUPPORTED;
     P.ctas_per_sm = ctas;
+    return SPAA_OK;
+}
+
+int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, const float* bias, const void* add, const void* mask, const void* mask2,
+              void* out, void* out2, cudaStream_t st, EncodeTiledFn enc) {
+    HaloParams P;
+    size_t smem_bytes = 0;
+    const int prc = halo_plan(d, add != nullptr, mask != nullptr, mask2 != nullptr, P, smem_bytes);
+    if (prc != SPAA_OK) return prc;
+    const int BN = bn_for(d->Cout);
+    const int BK = d->Cin >= 64 ? 64 : d->Cin;
+    const bool f16 = d->in_dtype == 2;
+    const int nph = d->up * d->up;
+    const int np = d->split ? 3 : 1;
+    const bool lean = d->out_dtype != 0 && !d->split && BN <= 64;
+    P.bias = bias; P.add = add; P.mask = (const uint16_t*)mask; P.mask2 = (const uint16_t*)mask2; P.out = out; P.out2 = out2;
 
     CUtensorMap ma, mb;
     const CUtensorMapSwizzle swz = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -1228,9 +1607,27 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r); return SPAA_ERR_CUDA; }
     }
+    HaloOutMaps OM;
+    memset(&OM, 0, sizeof(OM));
+    if (lean) {
+        // one strided view per output phase: pixel (y', x') of phase (py, px) is output pixel (up * y' + py, up * x' + px)
+        const cuuint64_t C = (cuuint64_t)d->Cout;
+        for (int o = 0; o < (out2 ? 2 : 1); ++o)
+            for (int ph = 0; ph < nph; ++ph) {
+                const int py = ph / d->up, px = ph % d->up;
+                uint16_t* base = (uint16_t*)(o ? out2 : out) + ((int64_t)py * d->Wout + px) * d->Cout;
+                cuuint64_t dims[4] = {C, (cuuint64_t)((d->Wout - px + d->up - 1) / d->up), (cuuint64_t)((d->Hout - py + d->up - 1) / d->up), (cuuint64_t)d->B};
+                cuuint64_t strides[3] = {(cuuint64_t)d->up * C * 2, (cuuint64_t)d->up * d->Wout * C * 2, (cuuint64_t)d->Hout * d->Wout * C * 2};
+                cuuint32_t box[4] = {32, (cuuint32_t)HTW, 4, 1};
+                cuuint32_t es[4] = {1, 1, 1, 1};
+                CUresult r = enc(&OM.m[o * kMaxPhases + ph], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { set_last_error("spaa_conv_tc_fwd: cuTensorMapEncodeTiled(output, phase %d) failed with %d", ph, (int)r); return SPAA_ERR_CUDA; }
+            }
+    }
     int rc = SPAA_OK;
-#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? launch_halo<BN_, BK_, true>(ma, mb, P, smem_bytes, st) : \
-    (d->split ? launch_halo<BN_, BK_, false, true>(ma, mb, P, smem_bytes, st) : launch_halo<BN_, BK_, false>(ma, mb, P, smem_bytes, st))
+#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? launch_halo<BN_, BK_, true>(ma, mb, P, OM, smem_bytes, st) : \
+    (d->split ? launch_halo<BN_, BK_, false, true>(ma, mb, P, OM, smem_bytes, st) : launch_halo<BN_, BK_, false>(ma, mb, P, OM, smem_bytes, st))
     if (BK == 64) {
         if (BN == 32) SPAA_HALO_LAUNCH(32, 64);
         else if (BN == 64) SPAA_HALO_LAUNCH(64, 64);
@@ -1265,6 +1662,19 @@ EncodeTiledFn get_encode() {
 extern "C" {
 
 int spaa_conv_tc_supported(const spaa_conv_desc* d) { return (d && tc_supported(d, nullptr)) ? 1 : 0; }
+
+int spaa_conv_tc_plan(const spaa_conv_desc* d, int has_add, int has_mask, int has_mask2, int32_t* plan) {
+    SPAA_CHECK_ARG(d && plan, "spaa_conv_tc_plan: null argument");
+    const char* why = "";
+    SPAA_CHECK_ARG(tc_supported(d, &why), "spaa_conv_tc_plan: %s", why);
+    HaloParams P;
+    size_t smem = 0;
+    const int rc = halo_plan(d, has_add != 0, has_mask != 0, has_mask2 != 0, P, smem);
+    if (rc != SPAA_OK) return rc;
+    plan[0] = P.ctas_per_sm; plan[1] = P.egroups; plan[2] = P.nbuf; plan[3] = P.sa; plan[4] = P.resident ? 0 : P.sb; plan[5] = P.e_slots;
+    plan[6] = P.e_dbuf; plan[7] = P.pair; plan[8] = (int32_t)smem; plan[9] = P.total_tiles; plan[10] = 64 + 128 * P.egroups; plan[11] = P.resident;
+    return SPAA_OK;
+}
 
 int64_t spaa_conv_tc_packed_elems(const spaa_conv_desc* d) {
     if (!d) return 0;

@@ -123,11 +123,31 @@ SPAA_D void cp_async_wait(int n) {
 SPAA_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 SPAA_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// TMA tile STORE (shared -> global through a tensor map; parts of the box outside the tensor are clipped) and its bulk async-group bookkeeping.
+// The issuing thread's earlier st.shared writes by OTHER threads must be made visible to the async proxy first: every writer executes
+// fence_proxy_async_smem(), then the warp / CTA synchronises, then one thread issues the store.
+SPAA_D void tma_store_4d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map), "r"(smem_src), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+SPAA_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+SPAA_D void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }     // sources may be overwritten
+SPAA_D void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }               // writes complete
+SPAA_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 SPAA_D uint4 lds128(uint32_t smem_addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
     return v;
 }
+// read-only shared data written before the CTA-wide barrier of the prologue (bias): the compiler may schedule / hoist these loads freely
+SPAA_D uint4 lds128_const(uint32_t smem_addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+    return v;
+}
+SPAA_D void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 SPAA_D void sts128(uint32_t smem_addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
