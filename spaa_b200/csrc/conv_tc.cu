@@ -345,7 +345,8 @@ struct HaloParams {
     int32_t a_pair_bytes;
     int32_t e_stage_bytes;             // output staging blocks of the 4 epilogue warps (16-bit NHWC output only)
     int32_t e_dbuf;                    // 1: two staging blocks per warp (epilogue_nhwc16)
-    int32_t e_slots, e_nops;           // epilogue operand ring: slots of e_nops x 8 KB (0 slots: no ring)
+    int32_t e_slots, e_nops;           // epilogue operand ring: e_slots slots per group (0: no ring) of e_slot_bytes = e_nops x 8 KB (2 KB for the fp32-planar residual)
+    int32_t e_slot_bytes;
     uint32_t tap_tab[kMaxTaps * kMaxPhases];     // flattened (phase, tap) list, see the MMA issuer
     int32_t epi_flags, out_planar;
     int32_t split;                     // 1: bf16x3 split-precision operands (see the SPLIT template parameter of conv_halo_kernel)
@@ -400,7 +401,7 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
     const bool relu = (P.epi_flags & SPAA_EPI_RELU) != 0;
     constexpr int NCH = BN / 32;
     const int S = P.e_slots;                                        // 0: no operand ring
-    const uint32_t slot_bytes = (uint32_t)P.e_nops * 8192u;
+    const uint32_t slot_bytes = (uint32_t)P.e_slot_bytes;
     const int ci = lane >> 2, cc = lane & 3;                        // cooperative copy mapping: x pixel of the row group, 16-byte chunk
     const uint32_t e_warp = e_ring + (uint32_t)(eg * S) * slot_bytes + (uint32_t)q * 2048u;
     uint32_t own_off[4], coop_off[4];                               // byte offsets inside a 2 KB warp block: [row][16-byte chunk ^ ((row >> 1) & 3)]
@@ -591,7 +592,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t* b_base = smem + (size_t)SA * P.a_stage_bytes;
     const size_t b_bytes = P.resident ? (size_t)P.kchunks * P.nslots * P.b_slice_bytes : (size_t)SB * P.b_slice_bytes;
     uint8_t* e_ring = b_base + b_bytes;            // epilogue operand ring (see the epilogue)
-    uint64_t* bars = (uint64_t*)(e_ring + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes);
+    uint64_t* bars = (uint64_t*)(e_ring + (size_t)P.egroups * P.e_slots * P.e_slot_bytes + P.e_stage_bytes);
     uint64_t* a_full = bars;                       // [SA]
     uint64_t* a_empty = a_full + 8;                // [SA]
     uint64_t* b_full = a_empty + 8;                // [SB] (b_full[0] doubles as the "resident weights loaded" barrier)
@@ -873,7 +874,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr int NCH = BN / 32;
         const int nchu = planar ? 1 : NCH;                       // prefetch units per (tile, phase)
         const int S = P.e_slots;                                 // 0: no ring (no operand / wide planar residual)
-        const uint32_t slot_bytes = (uint32_t)P.e_nops * 8192u;
+        const uint32_t slot_bytes = (uint32_t)P.e_slot_bytes;
         const int ci = lane >> 2, cc = lane & 3;                 // cooperative mapping: x pixel within the row group, 16-byte chunk
         const uint32_t e_group = smem_u32(e_ring) + (uint32_t)eg * (uint32_t)S * slot_bytes;      // this group's ring
         const uint32_t e_warp = e_group + (uint32_t)q * 2048u;
@@ -1466,23 +1467,38 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                 if (C.eg > nbuf) continue;
                 const int total = C.c == 2 ? 108 * 1024 : 222 * 1024;
                 const int resident = res_bytes <= (C.c == 2 ? 40 : 80) * 1024 ? 1 : 0;
+                const int slot = planar ? 2048 : P.e_nops * 8192;       // (the fp32-planar residual of a tile is 4 channels x 128 rows x 4 bytes)
                 int S = 0;
                 if (P.e_nops) {
                     const int eb = (e_kb >= 0 ? e_kb : (C.c == 2 ? 32 : 48)) * 1024;
-                    const int sl = eb / (P.e_nops * 8192 * C.eg);
-                    S = sl < 2 ? 2 : (sl > 8 ? 8 : sl);
+                    const int sl = eb / (slot * C.eg);
+                    S = (resident || sl < 2) ? 2 : (sl > 8 ? 8 : sl);          // resident weights: minimal ring first, deepened below with what is left
                 }
                 const int stage = planar ? 0 : (1 + C.dbuf) * C.eg * 4 * (mask2 ? 4096 : 2048);
-                int64_t budget = (int64_t)total - (int64_t)C.eg * S * P.e_nops * 8192 - stage;
+                int64_t budget = (int64_t)total - (int64_t)C.eg * S * slot - stage;
                 while (S > 2 && budget - 2 * P.a_stage_bytes < (resident ? res_bytes : 2 * (int64_t)P.b_slice_bytes)) {
                     --S;
-                    budget += (int64_t)C.eg * P.e_nops * 8192;
+                    budget += (int64_t)C.eg * slot;
                 }
                 int64_t sa, sb, bbytes;
                 if (resident) {
                     bbytes = res_bytes; sb = 1;
                     sa = (budget - bbytes) / P.a_stage_bytes;
                     if (sa < (pass == 0 ? 3 : 2)) continue;
+                    if (sa > 8) sa = 8;
+                    // These layers run at (bytes in flight) / (memory latency): measured, conv6 forward 86 us with 69 KB of input stages per SM and 68 us
+                    // with 92 KB.  Whatever shared memory is left goes to the pipeline that holds fewer TILES -- input stages or the operand ring
+                    // (one slot = one 32-channel unit of one phase of one tile, S - 1 of them in flight per epilogue group).
+                    int64_t left = budget - bbytes - sa * P.a_stage_bytes;
+                    const int units = nph * (BN / 32);
+                    for (;;) {
+                        const bool can_a = sa < 8 && left >= P.a_stage_bytes;
+                        const bool can_e = S > 0 && S < 8 && left >= (int64_t)C.eg * slot;
+                        if (!can_a && !can_e) break;
+                        const bool pick_e = can_e && (!can_a || (int64_t)C.eg * (S - 1) < sa * units);
+                        if (pick_e) { ++S; left -= (int64_t)C.eg * slot; }
+                        else { ++sa; left -= P.a_stage_bytes; }
+                    }
                 } else {
                     sa = 2;
                     sb = (budget - 2 * (int64_t)P.a_stage_bytes) / P.b_slice_bytes;
@@ -1490,10 +1506,10 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                     if (sb < (pass == 0 ? 4 : 2)) continue;
                     bbytes = sb * P.b_slice_bytes;
                 }
-                P.nbuf = nbuf; P.egroups = C.eg; P.e_dbuf = (!planar && C.dbuf) ? 1 : 0; P.e_stage_bytes = stage; P.e_slots = S;
-                P.resident = resident; P.sb = (int)sb; P.sa = (int)(sa > 6 ? 6 : sa);
+                P.nbuf = nbuf; P.egroups = C.eg; P.e_dbuf = (!planar && C.dbuf) ? 1 : 0; P.e_stage_bytes = stage; P.e_slots = S; P.e_slot_bytes = slot;
+                P.resident = resident; P.sb = (int)sb; P.sa = (int)sa;
                 ctas = C.c;
-                smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
+                smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * slot + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
                 planned = true;
             }
         if (!planned) return SPAA_ERR_UNSUPPORTED;
@@ -1560,6 +1576,7 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                 continue;
             }
             P.sa = (int)(sa > 6 ? 6 : sa);
+            P.e_slot_bytes = P.e_nops * 8192;
             smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * P.e_nops * 8192 + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
             planned = true;
             break;

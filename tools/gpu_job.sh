@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_conv_tc.py -x -q -m gpu > gpurun_out/r2_lean_t5.log 2>&1
-tail -3 gpurun_out/r2_lean_t5.log | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_conv_tc.py -x -q -m gpu > gpurun_out/r2_lean_t6.log 2>&1
+tail -3 gpurun_out/r2_lean_t6.log | cut -c1-300
 B="--steps 10 --warmup 3 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-cold"
 run() { # name dir env...
   name=$1; dir=$2; shift 2
@@ -18,5 +18,3 @@ run new1 . X=1
 run new2 . X=1
 python tools/kbench.py --reps 12 > gpurun_out/ab_kb_new.log 2>&1
 grep -i conv gpurun_out/ab_kb_new.log | cut -c1-62
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2_lean_full.log 2>&1
-tail -4 gpurun_out/r2_lean_full.log | cut -c1-300
