@@ -142,7 +142,9 @@ enum {
     SPAA_EPI_RELU = 1,        /* v = max(v,0) */
     SPAA_EPI_LEAKY01 = 2,     /* v = v>0 ? v : 0.1 v                    (models.py:138) */
     SPAA_EPI_CLAMP_MAX1 = 4,  /* v = min(v,1) after the activation      (models.py:301) */
-    SPAA_EPI_ADD_AFTER_ACT = 8 /* add `add` after the activation instead of before */
+    SPAA_EPI_ADD_AFTER_ACT = 8, /* add `add` after the activation instead of before */
+    SPAA_EPI_OUT2_BF16 = 16   /* spaa_conv_tc_fwd, fp16 NHWC output only: out2 (no mask2) receives the SAME fp32 result rounded to bf16 -- the
+                                 operand format of the tensor-core backward-weight kernel in the fp16 training mode (gradients are bf16) */
 };
 enum {
     SPAA_MASK_NONE = 0,

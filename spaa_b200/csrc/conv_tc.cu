@@ -398,6 +398,7 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
     const int nacc_shift = P.nbuf == 4 ? 2 : (P.nbuf == 2 ? 1 : 0);
     const int per_img = P.tiles_x * P.tiles_y;
     const bool has_add = P.add != nullptr, has_mask = P.mask != nullptr, has_out2 = P.out2 != nullptr, has_bias = P.bias != nullptr;
+    const bool has_m2 = P.mask2 != nullptr;                          // out2 = out * (mask2 > 0), or (SPAA_EPI_OUT2_BF16, no mask2) the bf16 rounding of the result
     const bool relu = (P.epi_flags & SPAA_EPI_RELU) != 0;
     constexpr int NCH = BN / 32;
     const int S = P.e_slots;                                        // 0: no operand ring
@@ -460,7 +461,7 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
                     for (int k = 0; k < 4; ++k) if (k * up < nrow) cp_async16(d + coop_off[k], sp + k * kstep);
                     d += 8192;
                 }
-                if (has_out2) {
+                if (has_m2) {
                     const uint16_t* sp = P.mask2 + ((uint32_t)pf_b * mask_bs + pix);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) if (k * up < nrow) cp_async16(d + coop_off[k], sp + k * kstep);
@@ -513,7 +514,7 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
                 ca = cm = cm2 = make_uint4(0, 0, 0, 0);
                 if (has_add) ca = lds128(sa16 + own_off[0]);
                 if (has_mask) cm = lds128(sa16 + mask_slot_off + own_off[0]);
-                if (has_out2) cm2 = lds128(sa16 + mask2_slot_off + own_off[0]);
+                if (has_m2) cm2 = lds128(sa16 + mask2_slot_off + own_off[0]);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 na, nm, nm2;
@@ -521,7 +522,7 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
                     if (g < 3) {
                         if (has_add) na = lds128(sa16 + own_off[g + 1]);
                         if (has_mask) nm = lds128(sa16 + mask_slot_off + own_off[g + 1]);
-                        if (has_out2) nm2 = lds128(sa16 + mask2_slot_off + own_off[g + 1]);
+                        if (has_m2) nm2 = lds128(sa16 + mask2_slot_off + own_off[g + 1]);
                     }
                     float v[8];
 #pragma unroll
@@ -547,8 +548,12 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
                     // the same bits as selecting 0.f before the conversion)
                     uint4 pk = make_uint4(pack2<F16>(v[0], v[1]), pack2<F16>(v[2], v[3]), pack2<F16>(v[4], v[5]), pack2<F16>(v[6], v[7]));
                     if (has_mask) { pk.x &= posmask2(cm.x); pk.y &= posmask2(cm.y); pk.z &= posmask2(cm.z); pk.w &= posmask2(cm.w); }
-                    if (has_out2)
-                        sts128(stg + 2048u + own_off[g], make_uint4(pk.x & posmask2(cm2.x), pk.y & posmask2(cm2.y), pk.z & posmask2(cm2.z), pk.w & posmask2(cm2.w)));
+                    if (has_out2) {
+                        if (has_m2)
+                            sts128(stg + 2048u + own_off[g], make_uint4(pk.x & posmask2(cm2.x), pk.y & posmask2(cm2.y), pk.z & posmask2(cm2.z), pk.w & posmask2(cm2.w)));
+                        else
+                            sts128(stg + 2048u + own_off[g], make_uint4(pack2<false>(v[0], v[1]), pack2<false>(v[2], v[3]), pack2<false>(v[4], v[5]), pack2<false>(v[6], v[7])));
+                    }
                     sts128(stg + own_off[g], pk);
                     ca = na; cm = nm; cm2 = nm2;
                 }
@@ -575,14 +580,15 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
 // accumulator in TMEM holds small values while the small terms arrive), and the MMA issuer is unchanged.  The epilogue sums the three parts of
 // the residual operand in fp32, and writes its fp32 result v as three bf16 parts (masks act on every part; the sign of v is the sign of h).
 template <int BN, int BK, bool F16, bool SPLIT>
-__global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : (SPLIT ? kThreads : 640), (SPLIT && BN <= 64) ? 2 : 1)
+__global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : ((SPLIT || (BN == 64 && BK == 64)) ? kThreads : 640), (BN <= 64 && (SPLIT || (BN == 64 && BK == 64))) ? 2 : 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloParams P,
                  const __grid_constant__ HaloOutMaps OM) {
     static_assert(!(SPLIT && F16), "the split-precision mode stores bf16 parts");
     // narrow layers outside the split mode: register-lean epilogue with TMA stores (epilogue_nhwc16), up to four epilogue groups.  The wide layers keep
     // the round-1 epilogue: measured on the same box, the TMA-store epilogue cost them 4-14 % (conv4_s forward 74.0 -> 84.8 us: with one staging block
     // per warp every chunk waits for the previous store to leave shared memory, and a second block costs a stage of the weight ring).
-    constexpr bool LEAN = !SPLIT && BN <= 64;
+    // (BN = 64 with 64-channel K chunks = the 128 -> 64-channel layers, whose weights are streamed: same-box, conv3 backward 33 -> 39 us with it)
+    constexpr bool LEAN = !SPLIT && BN <= 64 && !(BN == 64 && BK == 64);
     constexpr int NPART = SPLIT ? 3 : 1;
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -870,6 +876,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int ef = P.epi_flags;
         const bool has_add = P.add != nullptr, has_mask = P.mask != nullptr, has_out2 = P.out2 != nullptr;
         const bool planar = P.out_planar != 0, has_bias = P.bias != nullptr;
+        const bool has_m2 = P.mask2 != nullptr;                  // (out2 without mask2: SPAA_EPI_OUT2_BF16, the bf16 rounding of the result)
         const int tstep = EG * (int)gridDim.x, tile0 = (int)blockIdx.x + eg * (int)gridDim.x;
         constexpr int NCH = BN / 32;
         const int nchu = planar ? 1 : NCH;                       // prefetch units per (tile, phase)
@@ -936,7 +943,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
                             d += 8192;
                         }
-                        if (has_out2) {
+                        if (has_m2) {
                             const uint16_t* sp = P.mask2 + (int64_t)pf_b * P.mask_bs + pix0;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) if (coy0 + k * P.up < P.Hout) cp_async16(d + coop_off[k], sp + k * kstep);
@@ -1059,7 +1066,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 for (int g = 0; g < 4; ++g) cur.m[g] = lds128(sa16 + own_off[g]);
                                 sa16 += 8192;
                             }
-                            if (has_out2) {
+                            if (has_m2) {
 #pragma unroll
                                 for (int g = 0; g < 4; ++g) cur.m2[g] = lds128(sa16 + own_off[g]);
                             }
@@ -1164,12 +1171,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 pk[g * 4 + 2] &= posmask2(cur.m[g].z); pk[g * 4 + 3] &= posmask2(cur.m[g].w);
                             }
                         }
-                        if (has_out2) {
+                        if (has_out2 && has_m2) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g)
                                 sts128(o_stage + 2048u + own_off[g],
                                        make_uint4(pk[g * 4 + 0] & posmask2(cur.m2[g].x), pk[g * 4 + 1] & posmask2(cur.m2[g].y),
                                                   pk[g * 4 + 2] & posmask2(cur.m2[g].z), pk[g * 4 + 3] & posmask2(cur.m2[g].w)));
+                        } else if (has_out2) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                sts128(o_stage + 2048u + own_off[g],
+                                       make_uint4(pack2<false>(v[g * 8 + 0], v[g * 8 + 1]), pack2<false>(v[g * 8 + 2], v[g * 8 + 3]),
+                                                  pack2<false>(v[g * 8 + 4], v[g * 8 + 5]), pack2<false>(v[g * 8 + 6], v[g * 8 + 7])));
                         }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) sts128(o_stage + own_off[g], make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
@@ -1331,7 +1344,7 @@ inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 // The launch plan of the halo kernel for one layer: tap tables, tile grid, shared-memory / TMEM split, CTAs per SM, epilogue groups.  Depends on the
 // descriptor and on WHICH epilogue operands are present only (host arithmetic, no CUDA call: spaa_conv_tc_plan exposes it to the CPU test-suite).
 // Returns SPAA_ERR_UNSUPPORTED when the halo kernel does not cover the case (the caller then uses v1).
-int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloParams& P, size_t& smem_bytes) {
+int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, bool out2, HaloParams& P, size_t& smem_bytes) {
     const int BN = bn_for(d->Cout);
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
     const int nph = d->up * d->up;
@@ -1415,7 +1428,8 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
     // ---- shared-memory plan.  Layers whose accumulator is narrow (BN <= 64: the HBM-bound ones) run TWO CTAs per SM when two
     // TMEM allocations and two half-size rings fit: twice the epilogue warps and loads in flight per SM.
     const bool planar = d->out_dtype == 0;
-    const bool lean = !planar && !d->split && BN <= 64;          // epilogue_nhwc16: 32-bit element offsets, TMA tile stores
+    const bool narrow = BN <= 64 && !d->split && !(BN == 64 && BK == 64);      // kernels with the register-lean epilogue (conv_halo_kernel: LEAN)
+    const bool lean = !planar && narrow;          // epilogue_nhwc16: 32-bit element offsets, TMA tile stores
     if (lean) {
         const int64_t img = (int64_t)d->Hout * d->Wout * d->Cout, lim = (int64_t)1 << 31;
         if ((int64_t)d->B * img >= lim || (add && (int64_t)(d->B - 1) * d->add_bs + img >= lim) || ((mask || mask2) && (int64_t)(d->B - 1) * d->mask_bs + img >= lim))
@@ -1435,11 +1449,14 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
     // BN = 128 only: four accumulator buffers keep the epilogue of one pair overlapped with the MMAs of the next.  With BN = 256 a pair fills all 512
     // TMEM columns, the overlap is lost and the layer gets SLOWER (measured: conv4_s forward 73.8 -> 100.5 us, conv4 forward unchanged), while
     // BN = 128 gains (conv5 forward 84.0 -> 72.5 us).  $SPAA_TC_PAIR=2 forces it for BN = 256 too.
-    const bool pair_ok = use_pair && (BN == 128 || (BN == 256 && use_pair >= 2)) && nph == 1 && res_bytes > 80 * 1024 && P.total_tiles >= 2 * kNumSMs;
+    // $SPAA_TC_RESMAX (KB): weights up to this size stay resident in shared memory when ONE CTA per SM can hold them next to two input stages
+    // (the 64 <-> 128-channel 3x3 layers: 147 KB); larger ones, or when that plan does not fit, are streamed per tile
+    static const int res_max = [] { const char* e = getenv("SPAA_TC_RESMAX"); return e ? atoi(e) : 80; }();
+    const bool pair_ok0 = use_pair && (BN == 128 || (BN == 256 && use_pair >= 2)) && nph == 1 && P.total_tiles >= 2 * kNumSMs;
     int ctas = 1;
     smem_bytes = 0;
     bool planned = false;
-    if (BN <= 64 && !d->split) {
+    if (narrow) {
         // ---- narrow layers (register-lean epilogue, up to 640 threads per CTA).  A plan = (CTAs per SM, epilogue groups, staging blocks per warp);
         // accumulator buffers = what TMEM holds for that many CTAs, at least one per group.  Measured per layer at the BASELINE shapes on one box
         // (tools/kbench.py under $SPAA_TC_NCTAS / $SPAA_TC_NEG, profiles/r2_narrow_plans.md): one CTA with four epilogue groups wins wherever its
@@ -1450,7 +1467,9 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
         static const Cand nhwc_c[] = {{1, 4, 1}, {1, 4, 0}, {1, 2, 1}, {2, 2, 1}, {1, 2, 0}, {2, 2, 0}, {2, 1, 1}, {2, 1, 0}, {1, 1, 0}};
         static const Cand planar_c[] = {{2, 2, 0}, {2, 1, 0}, {1, 2, 0}, {1, 1, 0}};
         static const Cand stream_c[] = {{2, 1, 1}, {2, 1, 0}, {1, 2, 0}, {1, 1, 0}};
-        const bool streamed = res_bytes > 80 * 1024;
+        {
+        const int lim_kb = 80;                                      // (larger resident weights were tried for the wide layers only, $SPAA_TC_RESMAX)
+        const bool streamed = res_bytes > lim_kb * 1024;
         const Cand forced[] = {{narrow_ctas >= 2 ? 2 : 1, narrow_eg < 1 ? 1 : narrow_eg, 1}, {narrow_ctas >= 2 ? 2 : 1, narrow_eg < 1 ? 1 : narrow_eg, 0}};
         const Cand* cands = narrow_ctas ? forced : (streamed ? stream_c : (planar ? planar_c : nhwc_c));
         const int ncand = narrow_ctas ? 2 : (streamed ? 4 : (planar ? 4 : 9));
@@ -1466,7 +1485,7 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                 const int nbuf = nb >= 4 ? 4 : (nb >= 2 ? 2 : 1);
                 if (C.eg > nbuf) continue;
                 const int total = C.c == 2 ? 108 * 1024 : 222 * 1024;
-                const int resident = res_bytes <= (C.c == 2 ? 40 : 80) * 1024 ? 1 : 0;
+                const int resident = res_bytes <= (C.c == 2 ? 40 : lim_kb) * 1024 ? 1 : 0;
                 const int slot = planar ? 2048 : P.e_nops * 8192;       // (the fp32-planar residual of a tile is 4 channels x 128 rows x 4 bytes)
                 int S = 0;
                 if (P.e_nops) {
@@ -1474,7 +1493,7 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                     const int sl = eb / (slot * C.eg);
                     S = (resident || sl < 2) ? 2 : (sl > 8 ? 8 : sl);          // resident weights: minimal ring first, deepened below with what is left
                 }
-                const int stage = planar ? 0 : (1 + C.dbuf) * C.eg * 4 * (mask2 ? 4096 : 2048);
+                const int stage = planar ? 0 : (1 + C.dbuf) * C.eg * 4 * (out2 ? 4096 : 2048);
                 int64_t budget = (int64_t)total - (int64_t)C.eg * S * slot - stage;
                 while (S > 2 && budget - 2 * P.a_stage_bytes < (resident ? res_bytes : 2 * (int64_t)P.b_slice_bytes)) {
                     --S;
@@ -1512,8 +1531,13 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                 smem_bytes = (size_t)P.sa * P.a_stage_bytes + (size_t)bbytes + (size_t)P.egroups * P.e_slots * slot + P.e_stage_bytes + kHaloBarBytes + BN * 4 + 1024;
                 planned = true;
             }
+        }
         if (!planned) return SPAA_ERR_UNSUPPORTED;
     }
+    for (int res_try = 0; res_try < 2 && !planned; ++res_try) {
+    const int res_lim = (res_try == 0 ? res_max : 80) * 1024;
+    if (res_try == 1 && res_max <= 80) break;
+    const bool pair_ok = pair_ok0 && res_bytes > res_lim;
     for (int try_pair = pair_ok ? 1 : 0; try_pair >= 0 && !planned; --try_pair) {
         P.pair = try_pair;
         P.a_pair_bytes = P.nplanes * P.a_plane_bytes;
@@ -1530,11 +1554,11 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
         const int k_per_pass = P.nslots * d->Cin * (d->split ? 6 : 1) / (1 + P.e_nops);
         P.egroups = (BN >= 128 && P.nbuf >= 2 && max_eg >= 2 && !(mask2 && BN == 256) && k_per_pass <= 640) ? 2 : 1;
         P.e_dbuf = 0;
-        P.e_stage_bytes = planar ? 0 : (1 + P.e_dbuf) * P.egroups * 4 * (mask2 ? 4096 : 2048);
+        P.e_stage_bytes = planar ? 0 : (1 + P.e_dbuf) * P.egroups * 4 * (out2 ? 4096 : 2048);
         ctas = (BN <= 64 && 2 * tmem_cols <= 512 && max_ctas >= 2) ? 2 : 1;
         for (;; --ctas) {
             const int total = ctas == 2 ? 108 * 1024 : 222 * 1024;
-            P.resident = res_bytes <= (ctas == 2 ? 40 : 80) * 1024 ? 1 : 0;
+            P.resident = res_bytes <= (ctas == 2 ? 40 * 1024 : res_lim) ? 1 : 0;
             P.e_slots = 0;
             if (P.e_nops) {
                 const int eb = (e_kb >= 0 ? e_kb : (ctas == 2 ? 32 : (P.resident ? 48 : 32))) * 1024;
@@ -1568,7 +1592,7 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
                 }
                 if (ctas == 1 && P.egroups == 2) {                   // a second epilogue group's ring and staging blocks do not fit: run with one
                     P.egroups = 1;
-                    P.e_stage_bytes = planar ? 0 : 4 * (mask2 ? 4096 : 2048);
+                    P.e_stage_bytes = planar ? 0 : 4 * (out2 ? 4096 : 2048);
                     ++ctas;                                          // (undo the loop's decrement: plan again with one CTA per SM)
                     continue;
                 }
@@ -1582,6 +1606,7 @@ int halo_plan(const spaa_conv_desc* d, bool add, bool mask, bool mask2, HaloPara
             break;
         }
     }
+    }   // res_try
     if (!planned) return SPAA_ERR_UNSUPPORTED;
     P.ctas_per_sm = ctas;
     return SPAA_OK;
@@ -1591,14 +1616,14 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
               void* out, void* out2, cudaStream_t st, EncodeTiledFn enc) {
     HaloParams P;
     size_t smem_bytes = 0;
-    const int prc = halo_plan(d, add != nullptr, mask != nullptr, mask2 != nullptr, P, smem_bytes);
+    const int prc = halo_plan(d, add != nullptr, mask != nullptr, mask2 != nullptr, out2 != nullptr, P, smem_bytes);
     if (prc != SPAA_OK) return prc;
     const int BN = bn_for(d->Cout);
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
     const bool f16 = d->in_dtype == 2;
     const int nph = d->up * d->up;
     const int np = d->split ? 3 : 1;
-    const bool lean = d->out_dtype != 0 && !d->split && BN <= 64;
+    const bool lean = d->out_dtype != 0 && !d->split && BN <= 64 && !(BN == 64 && BK == 64);
     P.bias = bias; P.add = add; P.mask = (const uint16_t*)mask; P.mask2 = (const uint16_t*)mask2; P.out = out; P.out2 = out2;
 
     CUtensorMap ma, mb;
@@ -1686,7 +1711,7 @@ int spaa_conv_tc_plan(const spaa_conv_desc* d, int has_add, int has_mask, int ha
     SPAA_CHECK_ARG(tc_supported(d, &why), "spaa_conv_tc_plan: %s", why);
     HaloParams P;
     size_t smem = 0;
-    const int rc = halo_plan(d, has_add != 0, has_mask != 0, has_mask2 != 0, P, smem);
+    const int rc = halo_plan(d, has_add != 0, has_mask != 0, has_mask2 != 0, has_mask2 != 0 || (d->epi_flags & SPAA_EPI_OUT2_BF16) != 0, P, smem);
     if (rc != SPAA_OK) return rc;
     plan[0] = P.ctas_per_sm; plan[1] = P.egroups; plan[2] = P.nbuf; plan[3] = P.sa; plan[4] = P.resident ? 0 : P.sb; plan[5] = P.e_slots;
     plan[6] = P.e_dbuf; plan[7] = P.pair; plan[8] = (int32_t)smem; plan[9] = P.total_tiles; plan[10] = 64 + 128 * P.egroups; plan[11] = P.resident;
@@ -1741,11 +1766,14 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
     SPAA_CHECK_ARG(d && in && wpacked && out, "spaa_conv_tc_fwd: null argument");
     const char* why = "";
     SPAA_CHECK_ARG(tc_supported(d, &why), "spaa_conv_tc_fwd: %s", why);
-    SPAA_CHECK_ARG((out2 == nullptr) == (mask2 == nullptr), "spaa_conv_tc_fwd: out2 and mask2 go together");
+    const bool copy2 = (d->epi_flags & SPAA_EPI_OUT2_BF16) != 0;
+    SPAA_CHECK_ARG(copy2 ? (out2 != nullptr && mask2 == nullptr && d->in_dtype == 2 && d->out_dtype == 2 && !d->split)
+                         : ((out2 == nullptr) == (mask2 == nullptr)),
+                   "spaa_conv_tc_fwd: out2 and mask2 go together, except with SPAA_EPI_OUT2_BF16 (fp16 NHWC layers: out2 alone)");
     SPAA_CHECK_ARG(d->mask_mode == SPAA_MASK_NONE || mask, "spaa_conv_tc_fwd: mask_mode needs mask");
     const bool planar = d->out_dtype == 0;
-    SPAA_CHECK_ARG(!(d->epi_flags & ~(SPAA_EPI_RELU | (planar ? SPAA_EPI_CLAMP_MAX1 : 0))),
-                   "spaa_conv_tc_fwd: epilogue flags: ReLU (and clamp for fp32 planar output) only");
+    SPAA_CHECK_ARG(!(d->epi_flags & ~(SPAA_EPI_RELU | (planar ? SPAA_EPI_CLAMP_MAX1 : SPAA_EPI_OUT2_BF16))),
+                   "spaa_conv_tc_fwd: epilogue flags: ReLU (and clamp for fp32 planar output, the bf16 copy for fp16 NHWC output) only");
     SPAA_CHECK_ARG(!mask || d->mask_mode == SPAA_MASK_POS, "spaa_conv_tc_fwd: only the ReLU mask (SPAA_MASK_POS) is implemented on the tensor-core path");
     if (planar) {
         SPAA_CHECK_ARG(!mask && !mask2, "spaa_conv_tc_fwd: masks are not implemented for fp32 planar output");
@@ -1764,6 +1792,7 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
         if (rc2 != SPAA_ERR_UNSUPPORTED) return rc2;
     }
     SPAA_CHECK_ARG(!d->split, "spaa_conv_tc_fwd: the split-precision mode is implemented by the halo kernel only (this shape needs the fallback kernel)");
+    SPAA_CHECK_ARG(!copy2, "spaa_conv_tc_fwd: SPAA_EPI_OUT2_BF16 is implemented by the halo kernel only (this shape needs the fallback kernel)");
     const int BN = bn_for(d->Cout);
     const int BK = d->Cin >= 64 ? 64 : d->Cin;
     const bool f16 = d->in_dtype == 2;

@@ -72,7 +72,7 @@ class _Stack:
         return torch.float32 if getattr(net, "precision", "fp32") == "fp32" else torch.bfloat16
 
     @staticmethod
-    def surface_branch(net, surf: Tensor, packed: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    def surface_branch(net, surf: Tensor, packed: Optional[Tensor] = None, bf16_copy: Optional[dict] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         sp = net._specs
         ad = _Stack.act_dtype(net)
         s3 = _Stack.split(net)
@@ -81,11 +81,11 @@ class _Stack:
             packed = ops.pack_nhwc16(surf, None, ad, split=True)               # surface image(s) alone (simplify(), no-rough models): channels 0..Cs-1
             r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=0, split=True)
         elif packed is not None:          # [x | s | x*s | 0] 16-channel NHWC: the surface features start at channel 3
-            r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=3, split=s3)
+            r1s = ops.conv_forward(sp["conv1_s"], packed, *W("conv1_s"), epi=EPI_RELU, cin_offset=3, split=s3, bf16_copy=bf16_copy)
         else:
             r1s = ops.conv_forward(sp["conv1_s"], surf, *W("conv1_s"), epi=EPI_RELU, out_dtype=ad)
-        r2s = ops.conv_forward(sp["conv2_s"], r1s, *W("conv2_s"), epi=EPI_RELU, split=s3)
-        r3s = ops.conv_forward(sp["conv3_s"], r2s, *W("conv3_s"), epi=EPI_RELU, split=s3)
+        r2s = ops.conv_forward(sp["conv2_s"], r1s, *W("conv2_s"), epi=EPI_RELU, split=s3, bf16_copy=bf16_copy)
+        r3s = ops.conv_forward(sp["conv3_s"], r2s, *W("conv3_s"), epi=EPI_RELU, split=s3, bf16_copy=bf16_copy)
         r4s = ops.conv_forward(sp["conv4_s"], r3s, *W("conv4_s"), epi=EPI_RELU, split=s3)
         return r1s, r2s, r3s, r4s
 
@@ -100,7 +100,7 @@ class _Stack:
 
     @staticmethod
     def forward(net, x: Optional[Tensor], surf: Optional[Tensor], skip_in: Optional[Tensor], *, surf_acts=None, skip_acts=None,
-                packed: Optional[Tensor] = None) -> Tuple[Tensor, dict]:
+                packed: Optional[Tensor] = None, bf16_copies: bool = False) -> Tuple[Tensor, dict]:
         """x [B,3,H,W]; surf [B or 1,Cs,H,W] (ignored when surf_acts given); skip_in [B or 1,3,H,W] (ignored when
         skip_acts given).  `packed`: the 16-channel NHWC tensor [x | s | x*s | 0] from ops.grid_sample_packed replaces x and
         surf on the tensor-core path.  Returns (out, saved activations)."""
@@ -112,8 +112,13 @@ class _Stack:
             packed = ops.pack_nhwc16(x, None if surf_acts is not None else surf, _Stack.act_dtype(net), split=_Stack.split(net))
         s3 = _Stack.split(net)
         S: dict = {"x": x, "surf": surf, "skip_in": skip_in, "packed": packed}
+        # 'fp16' training: every activation that is the input of a layer is also written as bf16 by the epilogue that produces it (the
+        # backward-weight kernel's operand format); backward() finds the copies in S["bf16_of"] by data pointer
+        bc = {} if (bf16_copies and _Stack.act_dtype(net) == torch.float16 and not s3) else None
+        if bc is not None:
+            S["bf16_of"] = bc
         if surf_acts is None:
-            surf_acts = _Stack.surface_branch(net, surf, packed)
+            surf_acts = _Stack.surface_branch(net, surf, packed, bf16_copy=bc)
             S["surf_own"] = True
         r1s, r2s, r3s, r4s = surf_acts
         if skip_acts is None:
@@ -121,17 +126,17 @@ class _Stack:
             S["skip_own"] = True
         t1, t2, res1 = skip_acts
         if packed is not None:
-            x1 = ops.conv_forward(sp["conv1"], packed, *W("conv1"), add=r1s, epi=EPI_RELU, cin_offset=0, split=s3)
+            x1 = ops.conv_forward(sp["conv1"], packed, *W("conv1"), add=r1s, epi=EPI_RELU, cin_offset=0, split=s3, bf16_copy=bc)
         else:
             x1 = ops.conv_forward(sp["conv1"], x, *W("conv1"), add=r1s, epi=EPI_RELU, out_dtype=r1s.dtype)
         res2 = ops.conv_forward(sp["skipConv2"], x1, *W("skipConv2"), split=s3)
-        x2 = ops.conv_forward(sp["conv2"], x1, *W("conv2"), add=r2s, epi=EPI_RELU, split=s3)
+        x2 = ops.conv_forward(sp["conv2"], x1, *W("conv2"), add=r2s, epi=EPI_RELU, split=s3, bf16_copy=bc)
         res3 = ops.conv_forward(sp["skipConv3"], x2, *W("skipConv3"), split=s3)
-        x3 = ops.conv_forward(sp["conv3"], x2, *W("conv3"), add=r3s, epi=EPI_RELU, split=s3)
-        x4 = ops.conv_forward(sp["conv4"], x3, *W("conv4"), add=r4s, epi=EPI_RELU, split=s3)
-        x5 = ops.conv_forward(sp["conv5"], x4, *W("conv5"), add=res3, epi=EPI_RELU, split=s3)
-        x6 = ops.conv_forward(sp["transConv1"], x5, *W("transConv1"), add=res2, epi=EPI_RELU, split=s3)
-        x7 = ops.conv_forward(sp["transConv2"], x6, *W("transConv2"), epi=EPI_RELU, split=s3)
+        x3 = ops.conv_forward(sp["conv3"], x2, *W("conv3"), add=r3s, epi=EPI_RELU, split=s3, bf16_copy=bc)
+        x4 = ops.conv_forward(sp["conv4"], x3, *W("conv4"), add=r4s, epi=EPI_RELU, split=s3, bf16_copy=bc)
+        x5 = ops.conv_forward(sp["conv5"], x4, *W("conv5"), add=res3, epi=EPI_RELU, split=s3, bf16_copy=bc)
+        x6 = ops.conv_forward(sp["transConv1"], x5, *W("transConv1"), add=res2, epi=EPI_RELU, split=s3, bf16_copy=bc)
+        x7 = ops.conv_forward(sp["transConv2"], x6, *W("transConv2"), epi=EPI_RELU, split=s3, bf16_copy=bc)
         out = ops.conv_forward(sp["conv6"], x7, *W("conv6"), add=res1, epi=EPI_RELU | EPI_CLAMP_MAX1, out_dtype=torch.float32, split=s3)
         S.update(r1s=r1s, r2s=r2s, r3s=r3s, r4s=r4s, t1=t1, t2=t2, res1=res1, x1=x1, x2=x2, x3=x3, x4=x4, x5=x5, x6=x6, x7=x7, out=out)
         return out, S
@@ -151,7 +156,9 @@ class _Stack:
         hw = lambda t: (t.shape[2], t.shape[3])
         B = (d_pre6 if d_pre6 is not None else d_pre6_packed).shape[0]
 
-        bf16_of = {}                                   # 'fp16' mode: bf16 copies of the fp16 forward activations, one per tensor (x1, x2 feed two layers each)
+        # 'fp16' mode: bf16 copies of the fp16 forward activations, one per tensor (x1, x2 feed two layers each): written by the forward epilogues
+        # (forward(bf16_copies=True)), else made here on first use
+        bf16_of = S.get("bf16_of") if S.get("bf16_of") is not None else {}
 
         def wgrad(name, inp, dy, x_offset=0):
             if pg is not None and (name + ".weight") in pg:
@@ -271,7 +278,7 @@ class _StackFn(torch.autograd.Function):
             skip_in = skip_in[:1]             # one image expanded over the batch: run skipConv1 once (see _Stack.backward)
         skip_in = ops._f32c(skip_in)
         with torch.no_grad():
-            out, S = _Stack.forward(net, x, surf, skip_in, surf_acts=surf_acts, skip_acts=skip_acts)
+            out, S = _Stack.forward(net, x, surf, skip_in, surf_acts=surf_acts, skip_acts=skip_acts, bf16_copies=any(ctx.needs_input_grad[5:]))
         ctx.net, ctx.S = net, S
         ctx.n_params = len(params)
         ctx.surf_given = not use_cached_surf

@@ -17,7 +17,7 @@ from ._lib import ConvDesc, lib
 
 Tensor = torch.Tensor
 
-EPI_RELU, EPI_LEAKY01, EPI_CLAMP_MAX1, EPI_ADD_AFTER_ACT = 1, 2, 4, 8
+EPI_RELU, EPI_LEAKY01, EPI_CLAMP_MAX1, EPI_ADD_AFTER_ACT, EPI_OUT2_BF16 = 1, 2, 4, 8, 16
 MASK_NONE, MASK_POS, MASK_LEAKY01, MASK_OPEN01 = 0, 1, 2, 3
 
 _launches = 0      # number of kernels launched through this module (bench.py reports it)
@@ -641,7 +641,7 @@ def _split_weights(d: ConvDesc, w: Tensor, cin_real: int, cin_off: int):
 def _launch_conv(kind: str, spec, d: ConvDesc, x, w, b, add, mask, mask2, out, out2, cin_real: Optional[int] = None, cin_off: int = 0) -> None:
     L = lib()
     planar = d.out_dtype == 0
-    allowed = EPI_RELU | (EPI_CLAMP_MAX1 if planar else 0)
+    allowed = EPI_RELU | (EPI_CLAMP_MAX1 if planar else EPI_OUT2_BF16)
     use_tc = (TC_ENABLED and d.in_dtype in (1, 2) and (d.epi_flags & ~allowed) == 0 and (mask is None or d.mask_mode == MASK_POS)
               and not (planar and (mask is not None or mask2 is not None)) and L.spaa_conv_tc_supported(ctypes.byref(d)) == 1)
     padded = cin_real is not None and cin_real != d.Cin
@@ -670,8 +670,11 @@ def _new_act(shape, dtype, device) -> Tensor:
 
 
 def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, out: Optional[Tensor] = None,
-                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None, cin_offset: int = 0, split: bool = False) -> Tensor:
+                 add: Optional[Tensor] = None, epi: int = 0, out_dtype=None, cin_offset: int = 0, split: bool = False,
+                 bf16_copy: Optional[dict] = None) -> Tensor:
     """Forward of nn.Conv2d / nn.ConvTranspose2d with the fused epilogue `epi` (bias, residual add, activation, clamp).
+    bf16_copy: a dict that receives {out.data_ptr(): bf16 rounding of the same result} when the output is fp16 NHWC (the fp16 training mode:
+    the backward-weight kernel wants its activation operand in the gradients' format); written by the same epilogue on the tensor-core path.
     `x` may carry more channels than spec.cin (a zero-padded 16-channel NHWC tensor): the layer then reads channels
     [cin_offset, cin_offset + spec.cin) (tensor-core path only).
     split: bf16x3 split-precision operands (tensor-core path): x / add / a 16-bit out carry three bf16 parts per logical channel
@@ -696,7 +699,15 @@ def conv_forward(spec: ConvSpec, x: Tensor, w: Tensor, b: Optional[Tensor], *, o
         d.w_cis, d.w_cos = s0, s1
     d.epi_flags, d.mask_mode = epi, MASK_NONE
     _fill_desc(d, x, out, add, None, split)
-    _launch_conv("fwd", spec, d, x, w, b, add, None, None, out, None, cin_real=spec.cin, cin_off=cin_offset)
+    out2 = None
+    if bf16_copy is not None and out.dtype == torch.float16 and not split:
+        if TC_ENABLED and x.dtype == torch.float16 and lib().spaa_conv_tc_supported(ctypes.byref(d)) == 1:
+            out2 = torch.empty_like(out, dtype=torch.bfloat16)
+            assert out2.stride() == out.stride()
+            d.epi_flags = epi | EPI_OUT2_BF16
+    _launch_conv("fwd", spec, d, x, w, b, add, None, None, out, out2, cin_real=spec.cin, cin_off=cin_offset)
+    if bf16_copy is not None and out.dtype == torch.float16 and not split:
+        bf16_copy[out.data_ptr()] = out2 if out2 is not None else half_to_bf16(out)
     return out
 
 

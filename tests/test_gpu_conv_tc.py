@@ -457,3 +457,32 @@ def test_tc_conv_pair_mode_many_tiles(case, split):
         tol_a, tol_r = 0.1, 1e-2
     errb = (dx - refb).abs() - tol_r * refb.abs()
     assert errb.max().item() <= tol_a, f"backward-data: max abs err {(dx - refb).abs().max().item():.3e}"
+
+
+@pytest.mark.parametrize("case", [("conv", 32, 64, 3, 2, 1, 0, 26, 38), ("conv", 64, 128, 3, 1, 1, 0, 16, 32), ("convT", 64, 32, 2, 2, 0, 0, 12, 16),
+                                  ("convT", 128, 64, 3, 2, 1, 1, 7, 11), ("conv", 32, 64, 1, 1, 0, 0, 24, 32)], ids=lambda c: "-".join(map(str, c)))
+def test_tc_forward_bf16_copy_of_fp16_output(case):
+    """SPAA_EPI_OUT2_BF16 (the fp16 training mode): the forward epilogue also writes the bf16 rounding of the SAME fp32 result -- both the
+    register-lean epilogue of the narrow layers (TMA stores) and the epilogue of the wide ones; the fp16 output itself is unchanged."""
+    from spaa_b200 import ops
+    ops.invalidate_packed_weights()
+    kind, cin, cout, k, stride, pad, outpad, H, W = case
+    B = 3
+    spec = ops.ConvSpec(kind, cin, cout, k, stride, pad, outpad)
+    x = cl(synth.randn(1, "c2.x", (B, cin, H, W)), torch.float16)
+    w = synth.randn(2, "c2.w", spec.weight_shape(), (2.0 / (cin * k * k)) ** 0.5).to("cuda:0")
+    b = synth.randn(3, "c2.b", (cout,), 0.1).to("cuda:0")
+    Ho, Wo = spec.out_hw(H, W)
+    add = cl(synth.randn(4, "c2.add", (B, cout, Ho, Wo), 0.5), torch.float16)
+    plain = ops.conv_forward(spec, x, w, b, add=add, epi=ops.EPI_RELU)
+    copies = {}
+    n0 = ops.launch_count()
+    got = ops.conv_forward(spec, x, w, b, add=add, epi=ops.EPI_RELU, bf16_copy=copies)
+    assert ops.launch_count() == n0 + 1, "the copy must come from the convolution's own epilogue, not from a second kernel"
+    c = copies[got.data_ptr()]
+    assert c.dtype == torch.bfloat16 and c.shape == got.shape and c.stride() == got.stride()
+    assert torch.equal(got, plain)
+    # both are roundings of one fp32 value v: |fp16(v) - bf16(v)| <= 2^-9 |v| + 2^-12 |v|; and the copy is zero exactly where ReLU cut
+    d = (c.float() - got.float()).abs()
+    assert (d <= got.float().abs() * (2.0 ** -8) + 1e-7).all(), d.max().item()
+    assert torch.equal(c == 0, got == 0) or ((c == 0) != (got == 0)).sum().item() <= 2      # (values below the fp16 subnormal range)

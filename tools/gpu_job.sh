@@ -1,7 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_conv_tc.py -x -q -m gpu > gpurun_out/r2_lean_t6.log 2>&1
-tail -3 gpurun_out/r2_lean_t6.log | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_conv_tc.py -x -q -m gpu > gpurun_out/r2_c2_t1.log 2>&1
+tail -5 gpurun_out/r2_c2_t1.log | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_models.py -x -q -m gpu -k "train" > gpurun_out/r2_c2_t2.log 2>&1
+tail -5 gpurun_out/r2_c2_t2.log | cut -c1-300
 B="--steps 10 --warmup 3 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-cold"
 run() { # name dir env...
   name=$1; dir=$2; shift 2
@@ -9,12 +11,10 @@ run() { # name dir env...
   python - <<PY
 import json
 try:
-    d=json.loads(open('gpurun_out/ab_$name.json').read().strip().splitlines()[-1]); print('$name', 'attack %.1f it/s'%d['value'], 'train', d.get('train',{}).get('value'), d.get('parity_check',{}).get('cam_max_abs_err'), d.get('parity_check',{}).get('top1_agree'))
+    d=json.loads(open('gpurun_out/ab_$name.json').read().strip().splitlines()[-1]); print('$name', 'attack %.1f it/s'%d['value'], 'train', d.get('train',{}).get('value'), d.get('train',{}).get('phases'), d.get('train',{}).get('bf16_mode'))
 except Exception as e: print('$name failed', e); print(open('gpurun_out/ab_$name.err').read()[-800:])
 PY
 }
 run old1 _ab_old X=1
 run new1 . X=1
 run new2 . X=1
-python tools/kbench.py --reps 12 > gpurun_out/ab_kb_new.log 2>&1
-grep -i conv gpurun_out/ab_kb_new.log | cut -c1-62

@@ -11,7 +11,7 @@ from spaa_b200 import ops  # noqa: E402
 from spaa_b200._lib import ConvDesc, lib  # noqa: E402
 from spaa_b200.models import _stack_specs  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+B = int(sys.argv[1]) if __name__ == "__main__" and len(sys.argv) > 1 else 32
 H, W = 240, 320
 
 
@@ -56,36 +56,43 @@ def bwd(spec, cout_t, hin, win, add=False, mask=False, mask2=False, planar=False
     return plan(d, add, mask, mask2)
 
 
-sp = _stack_specs("spaa", 6)
-rows = []
-names = "ctas eg nbuf sa sb S dbuf pair smem tiles threads resident".split()
-r, _ = fwd(sp["conv1_s"], 16, H, W); rows.append(("conv1_s f", r))
-r, _ = fwd(sp["conv2_s"], 32, 120, 160); rows.append(("conv2_s f", r))
-r, _ = fwd(sp["conv3_s"], 64, 60, 80); rows.append(("conv3_s f", r))
-r, _ = fwd(sp["conv4_s"], 128, 60, 80); rows.append(("conv4_s f", r))
-r, _ = fwd(sp["conv1"], 16, H, W, add=True); rows.append(("conv1 f", r))
-r, _ = fwd(sp["skipConv2"], 32, 120, 160); rows.append(("skipConv2 f", r))
-r, _ = fwd(sp["conv2"], 32, 120, 160, add=True); rows.append(("conv2 f", r))
-r, _ = fwd(sp["skipConv3"], 64, 60, 80); rows.append(("skipConv3 f", r))
-r, _ = fwd(sp["conv3"], 64, 60, 80, add=True); rows.append(("conv3 f", r))
-r, _ = fwd(sp["conv4"], 128, 60, 80, add=True); rows.append(("conv4 f", r))
-r, _ = fwd(sp["conv5"], 256, 60, 80, add=True); rows.append(("conv5 f", r))
-r, _ = fwd(sp["transConv1"], 128, 60, 80, add=True); rows.append(("transConv1 f", r))
-r, _ = fwd(sp["transConv2"], 64, 120, 160); rows.append(("transConv2 f", r))
-r, _ = fwd(sp["conv6"], 32, H, W, add=True, planar=True); rows.append(("conv6 f", r))
-rows.append(("conv6 b", bwd(sp["conv6"], 16, H, W, mask=True)))
-rows.append(("transConv2 b", bwd(sp["transConv2"], 32, 120, 160, mask=True)))
-rows.append(("transConv1 b", bwd(sp["transConv1"], 64, 60, 80, mask=True)))
-rows.append(("conv5 b", bwd(sp["conv5"], 128, 60, 80, mask=True, mask2=True)))
-rows.append(("conv4 b", bwd(sp["conv4"], 256, 60, 80, mask=True)))
-rows.append(("conv3 b", bwd(sp["conv3"], 128, 60, 80)))
-rows.append(("skipConv3 b", bwd(sp["skipConv3"], 128, 60, 80, add=True, mask=True)))
-rows.append(("conv2 b", bwd(sp["conv2"], 64, 120, 160)))
-rows.append(("skipConv2 b", bwd(sp["skipConv2"], 64, 120, 160, add=True, mask=True)))
-rows.append(("conv1 b", bwd(sp["conv1"], 32, H, W, planar=True, cin_out=3)))
-rows.append(("conv3_s b", bwd(sp["conv3_s"], 128, 60, 80, add=True, mask=True)))
-rows.append(("conv2_s b", bwd(sp["conv2_s"], 64, 120, 160, add=True, mask=True)))
-rows.append(("conv1_s b", bwd(sp["conv1_s"], 32, H, W, planar=True, cin_out=6)))
-print("%-14s " % "layer" + " ".join("%7s" % n for n in names))
-for n, r in rows:
-    print("%-14s " % n + (" ".join("%7d" % v for v in r) if r else "unsupported by the halo kernel"))
+def layer_plans():
+    """[(layer, plan or None)] for the 27 tensor-core launches of one ShadingNetSPAA forward + backward-data pass."""
+    sp = _stack_specs("shading", 6)
+    rows = []
+    names = "ctas eg nbuf sa sb S dbuf pair smem tiles threads resident".split()
+    r, _ = fwd(sp["conv1_s"], 16, H, W); rows.append(("conv1_s f", r))
+    r, _ = fwd(sp["conv2_s"], 32, 120, 160); rows.append(("conv2_s f", r))
+    r, _ = fwd(sp["conv3_s"], 64, 60, 80); rows.append(("conv3_s f", r))
+    r, _ = fwd(sp["conv4_s"], 128, 60, 80); rows.append(("conv4_s f", r))
+    r, _ = fwd(sp["conv1"], 16, H, W, add=True); rows.append(("conv1 f", r))
+    r, _ = fwd(sp["skipConv2"], 32, 120, 160); rows.append(("skipConv2 f", r))
+    r, _ = fwd(sp["conv2"], 32, 120, 160, add=True); rows.append(("conv2 f", r))
+    r, _ = fwd(sp["skipConv3"], 64, 60, 80); rows.append(("skipConv3 f", r))
+    r, _ = fwd(sp["conv3"], 64, 60, 80, add=True); rows.append(("conv3 f", r))
+    r, _ = fwd(sp["conv4"], 128, 60, 80, add=True); rows.append(("conv4 f", r))
+    r, _ = fwd(sp["conv5"], 256, 60, 80, add=True); rows.append(("conv5 f", r))
+    r, _ = fwd(sp["transConv1"], 128, 60, 80, add=True); rows.append(("transConv1 f", r))
+    r, _ = fwd(sp["transConv2"], 64, 120, 160); rows.append(("transConv2 f", r))
+    r, _ = fwd(sp["conv6"], 32, H, W, add=True, planar=True); rows.append(("conv6 f", r))
+    rows.append(("conv6 b", bwd(sp["conv6"], 16, H, W, mask=True)))
+    rows.append(("transConv2 b", bwd(sp["transConv2"], 32, 120, 160, mask=True)))
+    rows.append(("transConv1 b", bwd(sp["transConv1"], 64, 60, 80, mask=True)))
+    rows.append(("conv5 b", bwd(sp["conv5"], 128, 60, 80, mask=True, mask2=True)))
+    rows.append(("conv4 b", bwd(sp["conv4"], 256, 60, 80, mask=True)))
+    rows.append(("conv3 b", bwd(sp["conv3"], 128, 60, 80)))
+    rows.append(("skipConv3 b", bwd(sp["skipConv3"], 128, 60, 80, add=True, mask=True)))
+    rows.append(("conv2 b", bwd(sp["conv2"], 64, 120, 160)))
+    rows.append(("skipConv2 b", bwd(sp["skipConv2"], 64, 120, 160, add=True, mask=True)))
+    rows.append(("conv1 b", bwd(sp["conv1"], 32, H, W, planar=True, cin_out=3)))
+    rows.append(("conv3_s b", bwd(sp["conv3_s"], 128, 60, 80, add=True, mask=True)))
+    rows.append(("conv2_s b", bwd(sp["conv2_s"], 64, 120, 160, add=True, mask=True)))
+    rows.append(("conv1_s b", bwd(sp["conv1_s"], 32, H, W, planar=True, cin_out=6)))
+    return rows, names
+
+
+if __name__ == "__main__":
+    rows, names = layer_plans()
+    print("%-14s " % "layer" + " ".join("%7s" % n for n in names))
+    for n, r in rows:
+        print("%-14s " % n + (" ".join("%7d" % v for v in r) if r else "unsupported by the halo kernel"))
