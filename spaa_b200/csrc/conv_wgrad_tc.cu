@@ -24,6 +24,7 @@
 #include "tc_ptx.cuh"
 #include "../../include/spaa_b200.h"
 #include <cstring>
+#include <cstdlib>
 
 using namespace spaa;
 using namespace spaa::tc;
@@ -66,7 +67,7 @@ SPAA_D uint64_t make_mn_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16, ui
 }
 SPAA_HD uint32_t layout_for(int ch) { return ch == 64 ? 2u : (ch == 32 ? 4u : 6u); }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+__global__ void __launch_bounds__(kThreads, 3) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                                                                     const __grid_constant__ WgParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -309,9 +310,6 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
     if (P.y_box_bytes & 1023) P.y_box_bytes = (P.y_box_bytes + 1023) & ~1023;
     P.stage_bytes = P.x_bytes + P.y_boxes * P.y_box_bytes;
     P.tx_bytes = P.nplanes * P.x_boxes * P.halo_h * P.halo_w * rowx + P.y_boxes * P.tile_h * WTW * rowy;
-    P.nstages = (200 * 1024) / P.stage_bytes;
-    if (P.nstages > 4) P.nstages = 4;
-    SPAA_CHECK_ARG(P.nstages >= 1, "spaa_conv_wgrad_tc: stage does not fit in shared memory");
     auto tap_off16 = [&](int t, int xb) {
         return (uint32_t)(((tp[t].plane * P.x_boxes + xb) * P.x_plane_bytes + ((tp[t].qy - qminy) * P.halo_w + (tp[t].qx - qminx)) * rowx) >> 4);
     };
@@ -383,6 +381,19 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
         }
         i += n;
     }
+    // CTAs per SM: the narrow layers (conv6: 24 MMAs of N = 16 and 15 KB of operands per 128-pixel tile) are bound by the ONE thread that issues a CTA's
+    // MMAs and by the bytes one CTA keeps in flight, not by the tensor pipe or TMEM -- two or three CTAs share an SM when their accumulators
+    // (TMEM columns) and at least three stages each fit (measured, batch 24: conv6 106 -> 91 us, skipConv2 27.6 -> 23.5 us; the stride-2 layers
+    // conv1 / conv1_s got slower, 46 -> 52 us, and keep one).  $SPAA_WGRAD_CTAS caps it (1 = the round-1 shape).
+    static const int max_ctas = [] { const char* e = getenv("SPAA_WGRAD_CTAS"); return e ? atoi(e) : 3; }();
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(P.max_groups * P.n_cols)) cols <<= 1;
+    int ctas = 1;
+    for (int c = max_ctas < 3 ? max_ctas : 3; c >= 2; --c)
+        if (d->stride == 1 && (int)cols * c <= 512 && ((226 * 1024) / c - 2048) / P.stage_bytes >= 3) { ctas = c; break; }
+    P.nstages = (ctas == 1 ? 200 * 1024 : (226 * 1024) / ctas - 2048) / P.stage_bytes;
+    if (P.nstages > 4) P.nstages = 4;
+    SPAA_CHECK_ARG(P.nstages >= 1, "spaa_conv_wgrad_tc: stage does not fit in shared memory");
     CUtensorMap mx, my;
     {
         const cuuint64_t cphys = (cuuint64_t)d->in_ps;             // physical channels per pixel (3 * Cx for split-precision operands)
@@ -412,7 +423,7 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
         set_last_error("spaa_conv_wgrad_tc: cannot reserve shared memory");
         return SPAA_ERR_CUDA;
     }
-    int grid = kNumSMs;
+    int grid = kNumSMs * ctas;
     if ((int64_t)P.total_tiles * P.nsets < grid) grid = P.total_tiles * P.nsets;
     conv_wgrad_tc_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(mx, my, P);
     SPAA_CHECK_LAUNCH("spaa_conv_wgrad_tc");
