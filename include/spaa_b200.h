@@ -223,6 +223,11 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
                        spaa_stream_t stream);
 /* out[c] += sum over pixels of a dense 16-bit NHWC tensor [npix][C] (C in 8..256, power of two); dtype 1 bf16, 2 fp16 */
 int spaa_channel_sum_nhwc16(const void* x, int dtype, int64_t npix, int C, float* out, spaa_stream_t stream);
+/* n <= 24 of these sums in ONE launch (the bias gradients of a whole backward pass): outs[i][c] += sum over the npix[i] pixels of xs[i]
+ * (dense 16-bit NHWC with C[i] channels) for c < c_real[i] (zero-padded tensors: only the real channels are written).  One dtype for all.
+ * xs / npix / C / c_real / outs are HOST arrays, read during the call. */
+int spaa_channel_sum_nhwc16_multi(const void* const* xs, const int64_t* npix, const int32_t* C, const int32_t* c_real, float* const* outs, int dtype, int n,
+                                  spaa_stream_t stream);
 /* out[c] += sum_{b,p} x[b,p,c]  (bias gradient; x addressed by element strides, dtype 0 fp32 / 1 bf16) */
 int spaa_channel_sum(const void* x, int dtype, int64_t B, int C, int64_t HW, int64_t bs, int64_t ps, int64_t cs, float* out,
                      spaa_stream_t stream);

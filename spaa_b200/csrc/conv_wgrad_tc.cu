@@ -231,6 +231,49 @@ __global__ void __launch_bounds__(256) channel_sum_nhwc_kernel(const uint16_t* _
     }
 }
 
+// the same sum for up to kMaxSumJobs tensors in ONE launch (blockIdx.y = tensor): the bias gradients of a whole backward pass
+constexpr int kMaxSumJobs = 24;
+struct SumJobs {
+    const uint16_t* x[kMaxSumJobs];
+    float* out[kMaxSumJobs];
+    int64_t npix[kMaxSumJobs];
+    int32_t C[kMaxSumJobs], c_real[kMaxSumJobs];
+};
+template <bool F16>
+__global__ void __launch_bounds__(256) channel_sum_nhwc_multi_kernel(const __grid_constant__ SumJobs J) {
+    __shared__ float sacc[256 * 8];
+    const int job = blockIdx.y;
+    const int C = J.C[job];
+    const int64_t npix = J.npix[job];
+    const uint16_t* __restrict__ x = J.x[job];
+    const int vecs = C >> 3;
+    const int v = threadIdx.x % vecs, phase = threadIdx.x / vecs, nphase = 256 / vecs;
+    if ((int64_t)blockIdx.x * nphase >= npix) return;               // (whole CTA: this tensor has fewer pixel groups than the grid is wide)
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (phase < nphase) {
+        for (int64_t p = (int64_t)blockIdx.x * nphase + phase; p < npix; p += (int64_t)gridDim.x * nphase) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * C) + v);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 f;
+                if constexpr (F16) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                acc[e * 2] += f.x; acc[e * 2 + 1] += f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sacc[threadIdx.x * 8 + k] = (phase < nphase) ? acc[k] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < J.c_real[job]) {
+        const int c = threadIdx.x;
+        float s = 0.f;
+        for (int ph = 0; ph < nphase; ++ph) s += sacc[(ph * vecs + (c >> 3)) * 8 + (c & 7)];
+        atomicAdd(J.out[job] + c, s);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -441,6 +484,30 @@ int spaa_channel_sum_nhwc16(const void* x, int dtype, int64_t npix, int C, float
     if (dtype == 2) channel_sum_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, npix, C, out);
     else channel_sum_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)x, npix, C, out);
     SPAA_CHECK_LAUNCH("spaa_channel_sum_nhwc16");
+    return SPAA_OK;
+}
+
+/* n <= 24 such sums in one launch: outs[i][c] += sum over the npix[i] pixels of xs[i] (dense 16-bit NHWC, C[i] channels) for c < c_real[i]
+ * (zero-padded tensors: only the real channels are written).  All tensors of one dtype.  The arrays are HOST arrays, read during the call. */
+int spaa_channel_sum_nhwc16_multi(const void* const* xs, const int64_t* npix, const int32_t* C, const int32_t* c_real, float* const* outs, int dtype, int n,
+                                  spaa_stream_t stream) {
+    SPAA_CHECK_ARG(xs && npix && C && c_real && outs && n >= 1 && n <= kMaxSumJobs && (dtype == 1 || dtype == 2), "spaa_channel_sum_nhwc16_multi: bad arguments");
+    SumJobs J;
+    memset(&J, 0, sizeof(J));
+    int64_t blocks = 1;
+    for (int i = 0; i < n; ++i) {
+        SPAA_CHECK_ARG(xs[i] && outs[i] && npix[i] > 0 && C[i] >= 8 && C[i] <= 256 && (C[i] & 7) == 0 && (256 % (C[i] >> 3)) == 0 && c_real[i] >= 1 && c_real[i] <= C[i],
+                       "spaa_channel_sum_nhwc16_multi: bad tensor %d", i);
+        J.x[i] = (const uint16_t*)xs[i]; J.out[i] = outs[i]; J.npix[i] = npix[i]; J.C[i] = C[i]; J.c_real[i] = c_real[i];
+        const int nphase = 256 / (C[i] >> 3);
+        const int64_t b = (npix[i] + nphase * 8 - 1) / (nphase * 8);
+        if (b > blocks) blocks = b;
+    }
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    const dim3 grid((unsigned)blocks, (unsigned)n);
+    if (dtype == 2) channel_sum_nhwc_multi_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(J);
+    else channel_sum_nhwc_multi_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(J);
+    SPAA_CHECK_LAUNCH("spaa_channel_sum_nhwc16_multi");
     return SPAA_OK;
 }
 

@@ -160,6 +160,8 @@ class _Stack:
         # (forward(bf16_copies=True)), else made here on first use
         bf16_of = S.get("bf16_of") if S.get("bf16_of") is not None else {}
 
+        bias_jobs: list = []                           # (cotangent, bias gradient) of every tensor-core layer: summed in ONE launch at the end
+
         def wgrad(name, inp, dy, x_offset=0):
             if pg is not None and (name + ".weight") in pg:
                 if inp.shape[0] == 1 and B > 1:
@@ -170,7 +172,8 @@ class _Stack:
                     if key not in bf16_of:
                         bf16_of[key] = ops.half_to_bf16(inp)
                     inp = bf16_of[key]
-                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset, split=s3 and inp.dtype != torch.float32)
+                ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset, split=s3 and inp.dtype != torch.float32,
+                                         defer_bias=bias_jobs)
 
         def packed_input():
             """[x | surf | 0] as one zero-padded 16-channel NHWC tensor in the gradient dtype: the X operand of the tensor-core
@@ -256,6 +259,8 @@ class _Stack:
             if need_dskip:
                 dskip = ops.conv_backward_data(sp["skipConv1.0"], dt1, Wt("skipConv1.0"), hw(S["skip_in"]))
             wgrad("skipConv1.0", S["skip_in"], dt1)
+        if bias_jobs:
+            ops.channel_sum_multi(bias_jobs)
         return dx, dsurf, dskip
 
 

@@ -752,7 +752,8 @@ def _dense_nhwc16(t: Tensor, np_: int = 1) -> bool:
 _SPLIT_WGRAD_PARTS = ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0))        # (x part, dy part) of the six part products, smallest first
 
 
-def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor], *, x_offset: int = 0, split: bool = False) -> None:
+def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor], *, x_offset: int = 0, split: bool = False,
+                         defer_bias: Optional[list] = None) -> None:
     """dw += d(loss)/d(weight), db += d(loss)/d(bias); dw/db are fp32 accumulators in the parameter's own layout.
     16-bit dense NHWC operands go to the tcgen05 backward-weight kernel; `x` / `dy` may then be zero-padded to 16 channels
     (the layer's real input channels sit at [x_offset, x_offset + spec.cin) of `x`, the real output channels at [0, spec.cout) of `dy`).
@@ -801,6 +802,8 @@ def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: 
                 for part in range(3):
                     L.spaa_channel_sum(ctypes.c_void_p(dy.data_ptr() + part * cy_l * 2), _dt(dy), dy.shape[0], db.numel(), dy.shape[2] * dy.shape[3], bs, ps, cs,
                                        _p(db), _stream()); _count()
+            elif defer_bias is not None and _dense_nhwc16(dy):
+                defer_bias.append((dy, db))          # summed with the other layers' bias gradients in one launch: channel_sum_multi
             elif spec.kind == "conv":
                 L.spaa_channel_sum_nhwc16(_p(dy), _dt(dy), dy.shape[0] * dy.shape[2] * dy.shape[3], dy.shape[1], _p(_bias_scratch(db, dy.shape[1])), _stream()); _count()
                 _bias_fold(db, dy.shape[1])
@@ -839,6 +842,26 @@ def _bias_scratch(db: Tensor, c: int) -> Tensor:
 def _bias_fold(db: Tensor, c: int) -> None:
     if db.numel() != c:
         db += _bias_tmp[(db.device.index or 0, c)][:db.numel()]
+
+
+def channel_sum_multi(jobs: list) -> None:
+    """[(x, out)]: out[c] += sum over batch and pixels of x[:, c] for c < out.numel(), every x a dense 16-bit NHWC tensor (possibly zero-padded
+    beyond out.numel() channels); one launch per 24 tensors of one dtype (the bias gradients of a whole backward pass were 17 launches)."""
+    for dt in (torch.bfloat16, torch.float16):
+        sel = [(x, o) for x, o in jobs if x.dtype == dt]
+        for i in range(0, len(sel), 24):
+            part = sel[i:i + 24]
+            n = len(part)
+            xs = (ctypes.c_void_p * n)(*[x.data_ptr() for x, _ in part])
+            outs = (ctypes.c_void_p * n)(*[o.data_ptr() for _, o in part])
+            npix = (ctypes.c_int64 * n)(*[x.shape[0] * x.shape[2] * x.shape[3] for x, _ in part])
+            C = (ctypes.c_int32 * n)(*[x.shape[1] for x, _ in part])
+            cr = (ctypes.c_int32 * n)(*[o.numel() for _, o in part])
+            for x, o in part:
+                assert _dense_nhwc16(x) and o.dtype == torch.float32 and o.is_contiguous() and o.numel() <= x.shape[1] and o.device == x.device
+            with torch.cuda.device(part[0][0].device):
+                lib().spaa_channel_sum_nhwc16_multi(xs, npix, C, cr, outs, _dt(part[0][0]), n, _stream())
+            _count()
 
 
 def channel_sum(x: Tensor, out: Tensor) -> None:

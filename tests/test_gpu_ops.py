@@ -585,3 +585,23 @@ def test_fused_preprocess_space_to_depth_layout(hw, crop, insz):
         ref = conv(plain.detach())
         close(stem(folded.detach()), ref, 2e-5, 1e-5, "S2DStem on the kernel's folded input")
         close(stem(plain.detach()), ref, 2e-5, 1e-5, "S2DStem folding a plain input itself")
+
+
+def test_channel_sum_multi_matches_per_tensor_sums():
+    """Bias gradients of a whole backward pass in one launch: tensors of different widths and sizes, a zero-padded one (3 real of 16 channels),
+    both 16-bit types; += semantics."""
+    from spaa_b200 import ops
+    dev = torch.device("cuda:0")
+    shapes = [(2, 16, 24, 32, 3), (3, 32, 12, 16, 32), (1, 64, 7, 9, 64), (2, 256, 6, 8, 256), (4, 128, 5, 8, 128)]
+    for dt in (torch.bfloat16, torch.float16):
+        jobs, refs = [], []
+        for i, (b, c, h, w, cr) in enumerate(shapes):
+            x = synth.randn(40 + i, "csm.x", (b, c, h, w)).to(dev).to(dt).contiguous(memory_format=torch.channels_last)
+            out = torch.full((cr,), 0.5, device=dev)
+            jobs.append((x, out))
+            refs.append(0.5 + x.double().sum((0, 2, 3))[:cr])
+        n0 = ops.launch_count()
+        ops.channel_sum_multi(jobs)
+        assert ops.launch_count() == n0 + 1
+        for (x, out), ref in zip(jobs, refs):
+            assert (out.double() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), (x.shape, (out.double() - ref).abs().max().item())
