@@ -608,6 +608,10 @@ def run_ours(args):
         Ap.step()
     probe = ops.set_probe(lambda kind, spec: spec.k == 3 and {spec.cin, spec.cout} == {128, 256})
     for _ in range(args.steps):
+        # host-launched steps are bound by the host (~50 us of Python / ctypes / tensor-map encoding per launch), and an event pair around a launch the
+        # GPU is already waiting for would time that host work too: park the GPU on a ~30 ms spin first, so that the whole step is queued behind it and
+        # its kernels run back to back
+        torch.cuda._sleep(60_000_000)
         Ap.step()
     torch.cuda.synchronize()
     ops.set_probe(None)

@@ -376,6 +376,10 @@ template <int ROW_BYTES> SPAA_D uint64_t make_halo_desc(uint32_t smem_addr, uint
 // Tensor maps of the 16-bit NHWC outputs, one per output phase (the sub-lattice (py, px) of an up-sampling layer is its own strided view):
 // m[ph] = out, m[4 + ph] = out2.  Box = {32 channels, 8 x, 4 y, 1 image} = the 2 KB staging block of one epilogue warp, 64-byte swizzle.
 struct alignas(64) HaloOutMaps { CUtensorMap m[2 * kMaxPhases]; };
+struct HaloNoMaps { int32_t unused; };             // kernels that keep the round-1 epilogue take this instead (1 KB less of launch parameters)
+// which instantiations run the register-lean epilogue (see conv_halo_kernel)
+template <int BN, int BK, bool SPLIT> constexpr bool halo_lean_v = !SPLIT && BN <= 64 && !(BN == 64 && BK == 64);
+template <int BN, int BK, bool SPLIT> using HaloMapsT = std::conditional_t<halo_lean_v<BN, BK, SPLIT>, HaloOutMaps, HaloNoMaps>;
 
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue of the 16-bit NHWC layers (every mode but the split-precision one), round 2.
@@ -579,16 +583,16 @@ SPAA_D void epilogue_nhwc16(const HaloParams& P, const HaloOutMaps& OM, uint32_t
 // chunk table P.a_chunk, the weights are packed with 6C input channels in the matching order (smallest products first, so that the fp32
 // accumulator in TMEM holds small values while the small terms arrive), and the MMA issuer is unchanged.  The epilogue sums the three parts of
 // the residual operand in fp32, and writes its fp32 result v as three bf16 parts (masks act on every part; the sign of v is the sign of h).
-template <int BN, int BK, bool F16, bool SPLIT>
+template <int BN, int BK, bool F16, bool SPLIT, bool COPY2 = false>
 __global__ void __launch_bounds__(BN >= 128 ? kThreads + 128 : ((SPLIT || (BN == 64 && BK == 64)) ? kThreads : 640), (BN <= 64 && (SPLIT || (BN == 64 && BK == 64))) ? 2 : 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ HaloParams P,
-                 const __grid_constant__ HaloOutMaps OM) {
+                 const __grid_constant__ HaloMapsT<BN, BK, SPLIT> OM) {
     static_assert(!(SPLIT && F16), "the split-precision mode stores bf16 parts");
     // narrow layers outside the split mode: register-lean epilogue with TMA stores (epilogue_nhwc16), up to four epilogue groups.  The wide layers keep
     // the round-1 epilogue: measured on the same box, the TMA-store epilogue cost them 4-14 % (conv4_s forward 74.0 -> 84.8 us: with one staging block
     // per warp every chunk waits for the previous store to leave shared memory, and a second block costs a stage of the weight ring).
     // (BN = 64 with 64-channel K chunks = the 128 -> 64-channel layers, whose weights are streamed: same-box, conv3 backward 33 -> 39 us with it)
-    constexpr bool LEAN = !SPLIT && BN <= 64 && !(BN == 64 && BK == 64);
+    constexpr bool LEAN = halo_lean_v<BN, BK, SPLIT>;
     constexpr int NPART = SPLIT ? 3 : 1;
     constexpr int ROWB = BK * 2;
     extern __shared__ uint8_t smem_raw[];
@@ -739,7 +743,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // instructions per tap on run-time tap counts, the resident / streamed branch and re-materialised constants (~270 per tile at ~6 clk each:
             // as long as the loads and the MMAs themselves).  Here the tap count is a compile-time constant and every per-tap quantity is a register.
             bool fast_done = false;
-            if constexpr (BN <= 64) {
+            if constexpr (BN <= 64 && !(BN == 64 && BK == 64)) {      // (the 128 -> 64-channel layers always stream their weights: no dead code in their kernels)
                 if (P.resident && !P.pair && P.kchunks == 1) {
                     auto fast = [&](auto ntap_c) {
                         constexpr int NTAP = decltype(ntap_c)::value;
@@ -1159,6 +1163,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             }
                             continue;
                         }
+                        if constexpr (COPY2) {
+                            // SPAA_EPI_OUT2_BF16 (its own instantiation: as a run-time branch it cost the wide layers 3-4 us each, taken or not -- this
+                            // epilogue sits on its register cap): the bf16 rounding of the result goes to the second staging block FIRST, so that v[]
+                            // dies when pk[] is formed
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                sts128(o_stage + 2048u + own_off[g],
+                                       make_uint4(pack2<false>(v[g * 8 + 0], v[g * 8 + 1]), pack2<false>(v[g * 8 + 2], v[g * 8 + 3]),
+                                                  pack2<false>(v[g * 8 + 4], v[g * 8 + 5]), pack2<false>(v[g * 8 + 6], v[g * 8 + 7])));
+                        }
                         // pack to 16 bit, then apply the ReLU masks of the backward pass on the packed pairs (AND with a per-half
                         // "> 0" bit mask: same bits as selecting 0.f before the conversion, ~6x fewer instructions)
                         uint32_t pk[16];
@@ -1177,12 +1191,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 sts128(o_stage + 2048u + own_off[g],
                                        make_uint4(pk[g * 4 + 0] & posmask2(cur.m2[g].x), pk[g * 4 + 1] & posmask2(cur.m2[g].y),
                                                   pk[g * 4 + 2] & posmask2(cur.m2[g].z), pk[g * 4 + 3] & posmask2(cur.m2[g].w)));
-                        } else if (has_out2) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                sts128(o_stage + 2048u + own_off[g],
-                                       make_uint4(pack2<false>(v[g * 8 + 0], v[g * 8 + 1]), pack2<false>(v[g * 8 + 2], v[g * 8 + 3]),
-                                                  pack2<false>(v[g * 8 + 4], v[g * 8 + 5]), pack2<false>(v[g * 8 + 6], v[g * 8 + 7])));
                         }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) sts128(o_stage + own_off[g], make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
@@ -1305,10 +1313,13 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, c
 // ---- v2 host side ---------------------------------------------------------------------------------------------
 constexpr int kHaloBarBytes = (8 * 4 + 8) * 8 + 16 + kMaxTaps * kMaxPhases * 4;      // a_full/a_empty/b_full/b_empty [8] + tfull/tempty [4] + tmem slot
 
-template <int BN, int BK, bool F16, bool SPLIT = false>
-int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, const HaloOutMaps& OM, size_t smem_bytes, cudaStream_t st) {
+template <int BN, int BK, bool F16, bool SPLIT = false, bool COPY2 = false>
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& P, const HaloOutMaps& OM_full, size_t smem_bytes, cudaStream_t st) {
+    HaloMapsT<BN, BK, SPLIT> OM;
+    if constexpr (halo_lean_v<BN, BK, SPLIT>) OM = OM_full;
+    else OM.unused = 0;
     static SmemOptIn opt;
-    if (!opt.ensure(conv_halo_kernel<BN, BK, F16, SPLIT>, smem_bytes, true)) {
+    if (!opt.ensure(conv_halo_kernel<BN, BK, F16, SPLIT, COPY2>, smem_bytes, true)) {
         set_last_error("spaa_conv_tc_fwd: cannot reserve %zu bytes of shared memory", smem_bytes);
         return SPAA_ERR_CUDA;
     }
@@ -1329,13 +1340,13 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloParams& 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, BK, F16, SPLIT>, ma, mb, P, OM) != cudaSuccess) {
+        if (cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, BK, F16, SPLIT, COPY2>, ma, mb, P, OM) != cudaSuccess) {
             set_last_error("spaa_conv_tc_fwd: cudaLaunchKernelEx failed: %s", cudaGetErrorString(cudaGetLastError()));
             return SPAA_ERR_CUDA;
         }
         return SPAA_OK;
     }
-    conv_halo_kernel<BN, BK, F16, SPLIT><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P, OM);
+    conv_halo_kernel<BN, BK, F16, SPLIT, COPY2><<<grid, 64 + 128 * P.egroups, smem_bytes, st>>>(ma, mb, P, OM);
     return SPAA_OK;
 }
 
@@ -1668,7 +1679,11 @@ int conv_halo(const spaa_conv_desc* d, const void* in, const void* wpacked, cons
             }
     }
     int rc = SPAA_OK;
-#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? launch_halo<BN_, BK_, true>(ma, mb, P, OM, smem_bytes, st) : \
+    // the bf16 copy of an fp16 output (SPAA_EPI_OUT2_BF16) is a run-time flag in the register-lean epilogue of the narrow layers and a separate
+    // instantiation of the kernels that keep the round-1 epilogue
+    const bool copy2_wide = out2 != nullptr && mask2 == nullptr && !lean;
+#define SPAA_HALO_LAUNCH(BN_, BK_) rc = f16 ? ((copy2_wide && (BN_ >= 128 || (BN_ == 64 && BK_ == 64))) ? launch_halo<BN_, BK_, true, false, (BN_ >= 128 || (BN_ == 64 && BK_ == 64))>(ma, mb, P, OM, smem_bytes, st) \
+                                                                                              : launch_halo<BN_, BK_, true>(ma, mb, P, OM, smem_bytes, st)) : \
     (d->split ? launch_halo<BN_, BK_, false, true>(ma, mb, P, OM, smem_bytes, st) : launch_halo<BN_, BK_, false>(ma, mb, P, OM, smem_bytes, st))
     if (BK == 64) {
         if (BN == 32) SPAA_HALO_LAUNCH(32, 64);
