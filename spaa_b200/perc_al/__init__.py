@@ -127,8 +127,9 @@ class PerC_AL:
                 g = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
+                pool = ops.graph_pool(dev)
                 with torch.cuda.stream(side):
-                    g.capture_begin()
+                    g.capture_begin(pool=pool) if pool is not None else g.capture_begin()
                     try:
                         body()                     # records the launches; the replay below executes this iteration
                     finally:

@@ -173,8 +173,9 @@ class SpaaAttack:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         n0 = ops.launch_count()
+        pool = ops.graph_pool(self.device)
         with torch.cuda.stream(side):
-            g.capture_begin()
+            g.capture_begin(pool=pool) if pool is not None else g.capture_begin()
             try:
                 self._step_eager()                  # records the launches only; the caller's replay executes this iteration
             finally:
@@ -359,7 +360,11 @@ def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, ste
 
 
 def clear_engines() -> None:
+    """Drop every cached engine (and its CUDA graph); the shared graph memory pool goes with them (ops.graph_pool)."""
     _ENGINES.clear()
+    import gc
+    gc.collect()                                    # engines hold reference cycles (closures over themselves): their graphs must be gone before the pool
+    ops.release_graph_pools()
 
 
 def spaa(pcnet, classifier, imagenet_labels, target_idx, targeted, cam_scene, d_thr, stealth_loss, device, setup_info, *,

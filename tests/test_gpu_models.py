@@ -657,6 +657,42 @@ def test_spaa_deterministic_mode_matches_default():
         close_per_sample(cam_b, cam_a, 2e-4, f"{loss_name}: camera images")
 
 
+def test_engines_sharing_the_graph_memory_pool_do_not_disturb_each_other(monkeypatch):
+    """Two cached engines (targeted / untargeted, as in every sweep job) capture into ONE CUDA-graph memory pool (ops.graph_pool): the second capture
+    may take blocks the first one released, so their replays are interleaved here job by job -- results must equal the ones from private pools up to
+    the run-to-run noise of the fp32 atomics that remain in deterministic mode (measured 7e-7 after 8 iterations; a clobbered buffer shows as 1e-2 or
+    worse).  Also: clear_engines() releases the pool and the next capture starts a new one."""
+    from spaa_b200 import ops, projector_based_attack as pba
+    P, m, scene = _spaa_setup()
+    clf = TinyClf(1)
+    jobs = [([808, 969, 116, 786], True), ([5], False), ([1, 2, 3, 4], True), ([7], False)]
+
+    def run():
+        pba.clear_engines()
+        out = []
+        for targets, targeted in jobs:
+            cam, prj = pba.spaa(m, clf, LABELS, targets, targeted, scene, 2.0, "camdE_caml2", dev(), SETUP, iters=8, deterministic=True, graph=True)
+            out.append((cam.clone(), prj.clone()))
+        return out
+
+    def same(a, b, what):
+        for j, ((ca, pa), (cb, pb)) in enumerate(zip(a, b)):
+            dc, dp = (ca - cb).abs().max().item(), (pa - pb).abs().max().item()
+            assert dc <= 2e-5 and dp <= 2e-5, (what, j, dc, dp)
+
+    monkeypatch.setenv("SPAA_GRAPH_POOL", "0")
+    ref = run()
+    same(ref, run(), "private pools, run to run")
+    monkeypatch.setenv("SPAA_GRAPH_POOL", "1")
+    got = run()
+    assert len(ops._graph_pools) == 1
+    same(ref, got, "shared pool")
+    pba.clear_engines()
+    assert len(ops._graph_pools) == 0
+    same(ref, run(), "a fresh shared pool after the release")
+    pba.clear_engines()
+
+
 def test_attack_engine_cache_sees_training_updates_and_simplify():
     """spaa() -> train_pcnet() on the same model object -> spaa() must not reuse the cached engine (its captured CUDA graph holds the
     old packed weights, its grid / skip activations were computed from the old parameters); FlatAdam's raw kernel does not bump version counters."""
