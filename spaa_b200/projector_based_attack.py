@@ -354,8 +354,15 @@ def attack_engine(pcnet, classifier, target_idx, targeted, cam_scene, d_thr, ste
         _ENGINES[key] = (weakref.ref(net), weakref.ref(getattr(classifier, "model", classifier)), A)
     except TypeError:               # classifier object without weak-reference support: do not cache
         return A
+    evicted = False
     while len(_ENGINES) > _MAX_ENGINES:
         _ENGINES.popitem(last=False)
+        evicted = True
+    if evicted:
+        # an engine sits in reference cycles (autograd graph of the classifier leg <-> its buffers): without a collection its ~2 GB of buffers and its
+        # CUDA graph outlive the eviction by an arbitrary number of jobs (tools/capture_probe.py: +1.4 GB reserved per engine until gc ran)
+        import gc
+        gc.collect()
     return A
 
 
