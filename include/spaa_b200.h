@@ -221,6 +221,15 @@ int spaa_conv_tc_fwd(const spaa_conv_desc* d, const void* in, const void* wpacke
 int spaa_conv_wgrad_tc_supported(const spaa_conv_desc* d);
 int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real,
                        spaa_stream_t stream);
+/* The same backward-weight GEMM accumulated into a SCRATCH gradient of layout [tap][real X channel][d->Cout] (fp32, +=, 16-byte aligned,
+ * spaa_conv_wgrad_tc_scratch_elems floats, zero before the first use): the DY channel is contiguous there, so the kernel's final flush is four
+ * 16-byte reductions per thread instead of 16 scalar atomics.  spaa_wgrad_scatter_multi then adds the scratch gradients of up to 24 layers into
+ * the parameter gradients (dw[tap * w_ts + cx * w_xs + cy * w_ys] += scratch[(tap * cx_real + cx) * Cy + cy] for cy < cy_real) in ONE launch and
+ * zeroes the scratch for the next pass.  Its array arguments are HOST arrays, read during the call. */
+int64_t spaa_conv_wgrad_tc_scratch_elems(const spaa_conv_desc* d, int cx_real);
+int spaa_conv_wgrad_tc_scratch(const spaa_conv_desc* d, const void* x, const void* dy, float* scratch, int cx_real, int cx_off, int cy_real, spaa_stream_t stream);
+int spaa_wgrad_scatter_multi(const float* const* scratch, float* const* dw, const int32_t* ntap, const int32_t* cx_real, const int32_t* Cy, const int32_t* cy_real,
+                             const int64_t* w_ts, const int64_t* w_xs, const int64_t* w_ys, int n, spaa_stream_t stream);
 /* out[c] += sum over pixels of a dense 16-bit NHWC tensor [npix][C] (C in 8..256, power of two); dtype 1 bf16, 2 fp16 */
 int spaa_channel_sum_nhwc16(const void* x, int dtype, int64_t npix, int C, float* out, spaa_stream_t stream);
 /* n <= 24 of these sums in ONE launch (the bias gradients of a whole backward pass): outs[i][c] += sum over the npix[i] pixels of xs[i]

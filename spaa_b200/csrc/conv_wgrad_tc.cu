@@ -24,6 +24,7 @@
 #include "tc_ptx.cuh"
 #include "../../include/spaa_b200.h"
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 
 using namespace spaa;
@@ -56,6 +57,8 @@ struct WgParams {
     int32_t atom_rows;                     // rows of D per atom (= cxb, or 64 when Cx >= 128)
     int32_t cx_real, cx_off, cy_real;      // padded operands: real X channels sit at [cx_off, cx_off + cx_real); real DY channels [0, cy_real)
     int32_t x_f16, y_f16;
+    int32_t vec4;                          // 1: dw is the scratch layout (w_ys == 1, rows 16-byte aligned): flush with red.global.add.v4.f32
+    int32_t debug_noflush;                 // timing experiments only ($SPAA_WGRAD_NOFLUSH=1): skip the atomic flush (results are wrong)
     int64_t w_ts, w_xs, w_ys;
     float* dw;
     WgGroup g[kMaxGroups];
@@ -186,10 +189,22 @@ __global__ void __launch_bounds__(kThreads, 3) conv_wgrad_tc_kernel(const __grid
                           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                         : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * P.n_cols + c0)));
                     tmem_wait_ld();
-                    if (ok) {
+                    if (ok && !P.debug_noflush) {
+                        if (P.vec4) {
+                            // destination = the [tap][X channel][DY channel] scratch of spaa_conv_wgrad_tc_scratch: the thread's 16 columns are 64
+                            // contiguous bytes -> four 16-byte reductions instead of 16 scalar ones (the scalar flush of all CTAs at the end of the
+                            // kernel was 0.39 of the 0.97 ms the 17 launches of a training step took: tools/train_probe.py, $SPAA_WGRAD_NOFLUSH)
+                            float* q = dst + c0;
 #pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            if (c0 + k < P.cy_real) atomicAdd(dst + (int64_t)(c0 + k) * P.w_ys, __uint_as_float(r[k]));
+                            for (int k = 0; k < 16; k += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + k), "f"(__uint_as_float(r[k])), "f"(__uint_as_float(r[k + 1])),
+                                             "f"(__uint_as_float(r[k + 2])), "f"(__uint_as_float(r[k + 3]))
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k)
+                                if (c0 + k < P.cy_real) atomicAdd(dst + (int64_t)(c0 + k) * P.w_ys, __uint_as_float(r[k]));
+                        }
                     }
                 }
             }
@@ -274,6 +289,67 @@ __global__ void __launch_bounds__(256) channel_sum_nhwc_multi_kernel(const __gri
     }
 }
 
+// dw += scratch for up to kMaxScatterJobs layers in one launch (blockIdx.y = layer), and scratch = 0 for the next backward pass:
+// scratch is [tap][real X channel][Cy] (DY channel contiguous, zero-padded beyond cy_real), dw the parameter gradient in its own layout.
+constexpr int kMaxScatterJobs = 24;
+struct ScatterJobs {
+    float* scratch[kMaxScatterJobs];
+    float* dw[kMaxScatterJobs];
+    int64_t w_ts[kMaxScatterJobs], w_xs[kMaxScatterJobs], w_ys[kMaxScatterJobs];
+    int32_t ntap[kMaxScatterJobs], cx_real[kMaxScatterJobs], Cy[kMaxScatterJobs], cy_real[kMaxScatterJobs];
+    int32_t tiles[kMaxScatterJobs];                 // (X-channel blocks of 8) x (DY-channel blocks of 32)
+};
+// One CTA moves tiles of (all taps) x 8 X channels x 32 DY channels through shared memory: the scratch is read (and zeroed) along its contiguous DY
+// channel, the parameter gradient is updated along ITS contiguous (X channel, tap) runs -- for the usual layout w_ts == 1, w_xs == ntap, one run of
+// 8 * ntap floats per DY channel.  (A plain element-wise walk paid two 32-byte sectors per 4-byte element on one side or the other: 82 / 164 us per
+// training step instead of the ~25 us this takes.)  Other layouts take the same path with scattered, still correct, updates.
+constexpr int kScTX = 8, kScTY = 32;
+__global__ void __launch_bounds__(256) wgrad_scatter_multi_kernel(const __grid_constant__ ScatterJobs J) {
+    __shared__ float tile[kScTY][kScTX * 9 + 1];
+    const int job = blockIdx.y;
+    float* __restrict__ sc = J.scratch[job];
+    float* __restrict__ dw = J.dw[job];
+    const int ntap = J.ntap[job], cxr = J.cx_real[job], Cy = J.Cy[job], cyr = J.cy_real[job];
+    const int64_t ts = J.w_ts[job], xs = J.w_xs[job], ys = J.w_ys[job];
+    const int tiles_y = (cyr + kScTY - 1) / kScTY;
+    const int run = kScTX * ntap;
+    for (int t = blockIdx.x; t < J.tiles[job]; t += gridDim.x) {
+        const int cx0 = (t / tiles_y) * kScTX, cy0 = (t % tiles_y) * kScTY;
+        // (tap, 8 x 32) = 256 elements per pass and exactly one per thread: all loads of a phase are issued before anything depends on them
+        const int cy_l = threadIdx.x % kScTY, cx_l = threadIdx.x / kScTY;
+        const bool in = cx0 + cx_l < cxr && cy0 + cy_l < cyr;
+        float v[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+            v[tap] = (tap < ntap && in) ? sc[((int64_t)tap * cxr + cx0 + cx_l) * Cy + cy0 + cy_l] : 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+            if (tap < ntap) {
+                if (in) sc[((int64_t)tap * cxr + cx0 + cx_l) * Cy + cy0 + cy_l] = 0.f;
+                tile[cy_l][cx_l * ntap + tap] = v[tap];
+            }
+        __syncthreads();
+        float* dp[9];
+        float old[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int e = i * 256 + (int)threadIdx.x;
+            const int cy2 = e / run, j = e - cy2 * run;
+            const int cx2 = j / ntap, tap = j - cx2 * ntap;
+            const bool ok = i < ntap && e < kScTY * run && cx0 + cx2 < cxr && cy0 + cy2 < cyr;
+            dp[i] = ok ? dw + ((int64_t)tap * ts + (int64_t)(cx0 + cx2) * xs + (int64_t)(cy0 + cy2) * ys) : nullptr;
+            old[i] = ok ? *dp[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int e = i * 256 + (int)threadIdx.x;
+            const int cy2 = e / run, j = e - cy2 * run;
+            if (dp[i]) *dp[i] = old[i] + tile[cy2][j];
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -298,7 +374,8 @@ static inline int wg_floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2);
 /* d describes the FORWARD gather conv (up == 1, flip == 0): `x` = gathered operand, dense 16-bit NHWC [B,Hin,Win,Cin];
  * `dy` = pointwise operand, dense 16-bit NHWC [B,Hout,Wout,Cout]; dw fp32 (+=) addressed by d->w_ts / w_cis (X channel) / w_cos (DY channel).
  * cx_real / cx_off / cy_real: zero-padded operands (3- and 6-channel images padded to 16). */
-int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real, spaa_stream_t stream) {
+static int wgrad_tc_impl(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real, bool scratch_layout,
+                         spaa_stream_t stream) {
     SPAA_CHECK_ARG(d && x && dy && dw, "spaa_conv_wgrad_tc: null argument");
     SPAA_CHECK_ARG(spaa_conv_wgrad_tc_supported(d), "spaa_conv_wgrad_tc: unsupported shape / layout (see spaa_conv_wgrad_tc_supported)");
     SPAA_CHECK_ARG(cx_real > 0 && cx_off >= 0 && cx_off + cx_real <= d->Cin && cy_real > 0 && cy_real <= d->Cout, "spaa_conv_wgrad_tc: bad channel ranges");
@@ -315,7 +392,12 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
     P.atom_rows = Cx >= 128 ? 64 : P.cxb;
     P.cx_real = cx_real; P.cx_off = cx_off; P.cy_real = cy_real;
     P.x_f16 = d->in_dtype == 2; P.y_f16 = d->out_dtype == 2;
+    { static const int nf = [] { const char* e = getenv("SPAA_WGRAD_NOFLUSH"); return e ? atoi(e) : 0; }(); P.debug_noflush = nf; }
     P.w_ts = d->w_ts; P.w_xs = d->w_cis; P.w_ys = d->w_cos; P.dw = dw;
+    if (scratch_layout) {           // [tap][real X channel][Cy]: the DY channel is the contiguous index
+        P.w_ts = (int64_t)cx_real * Cy; P.w_xs = Cy; P.w_ys = 1; P.vec4 = 1;
+        SPAA_CHECK_ARG(((uintptr_t)dw & 15) == 0, "spaa_conv_wgrad_tc_scratch: scratch must be 16-byte aligned");
+    }
     // ---- taps: (plane, shift) ----
     struct TapPos { int plane, qy, qx; };
     TapPos tp[9];
@@ -407,6 +489,7 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
     }
     int max_per_set = 512 / Cy;
     if (max_per_set > 8) max_per_set = 8;
+    { static const int ms = [] { const char* e = getenv("SPAA_WGRAD_MAXSET"); return e ? atoi(e) : 0; }(); if (ms > 0 && ms < max_per_set) max_per_set = ms; }
     SPAA_CHECK_ARG(nacc <= kMaxGroups, "spaa_conv_wgrad_tc: too many accumulators");
     for (int i = 0; i < nacc; ++i) P.g[i] = accs[i].g;
     P.nsets = 0; P.max_groups = 0;
@@ -470,6 +553,40 @@ int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, f
     if ((int64_t)P.total_tiles * P.nsets < grid) grid = P.total_tiles * P.nsets;
     conv_wgrad_tc_kernel<<<grid, kThreads, smem_bytes, (cudaStream_t)stream>>>(mx, my, P);
     SPAA_CHECK_LAUNCH("spaa_conv_wgrad_tc");
+    return SPAA_OK;
+}
+
+int spaa_conv_wgrad_tc(const spaa_conv_desc* d, const void* x, const void* dy, float* dw, int cx_real, int cx_off, int cy_real, spaa_stream_t stream) {
+    return wgrad_tc_impl(d, x, dy, dw, cx_real, cx_off, cy_real, false, stream);
+}
+
+int64_t spaa_conv_wgrad_tc_scratch_elems(const spaa_conv_desc* d, int cx_real) {
+    if (!d || cx_real <= 0) return 0;
+    return (int64_t)d->KH * d->KW * cx_real * d->Cout;
+}
+
+int spaa_conv_wgrad_tc_scratch(const spaa_conv_desc* d, const void* x, const void* dy, float* scratch, int cx_real, int cx_off, int cy_real, spaa_stream_t stream) {
+    return wgrad_tc_impl(d, x, dy, scratch, cx_real, cx_off, cy_real, true, stream);
+}
+
+int spaa_wgrad_scatter_multi(const float* const* scratch, float* const* dw, const int32_t* ntap, const int32_t* cx_real, const int32_t* Cy, const int32_t* cy_real,
+                             const int64_t* w_ts, const int64_t* w_xs, const int64_t* w_ys, int n, spaa_stream_t stream) {
+    SPAA_CHECK_ARG(scratch && dw && ntap && cx_real && Cy && cy_real && w_ts && w_xs && w_ys && n >= 1 && n <= kMaxScatterJobs, "spaa_wgrad_scatter_multi: bad arguments");
+    ScatterJobs J;
+    memset(&J, 0, sizeof(J));
+    int64_t most = 1;
+    for (int i = 0; i < n; ++i) {
+        SPAA_CHECK_ARG(scratch[i] && dw[i] && ntap[i] >= 1 && cx_real[i] >= 1 && Cy[i] >= 1 && cy_real[i] >= 1 && cy_real[i] <= Cy[i], "spaa_wgrad_scatter_multi: bad job %d", i);
+        SPAA_CHECK_ARG(ntap[i] <= 9, "spaa_wgrad_scatter_multi: at most 9 taps (job %d)", i);
+        J.scratch[i] = const_cast<float*>(scratch[i]); J.dw[i] = dw[i];
+        J.ntap[i] = ntap[i]; J.cx_real[i] = cx_real[i]; J.Cy[i] = Cy[i]; J.cy_real[i] = cy_real[i]; J.w_ts[i] = w_ts[i]; J.w_xs[i] = w_xs[i]; J.w_ys[i] = w_ys[i];
+        J.tiles[i] = ((cx_real[i] + kScTX - 1) / kScTX) * ((cy_real[i] + kScTY - 1) / kScTY);
+        if (J.tiles[i] > most) most = J.tiles[i];
+    }
+    int64_t blocks = most;
+    if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+    wgrad_scatter_multi_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(J);
+    SPAA_CHECK_LAUNCH("spaa_wgrad_scatter_multi");
     return SPAA_OK;
 }
 

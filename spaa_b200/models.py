@@ -161,6 +161,7 @@ class _Stack:
         bf16_of = S.get("bf16_of") if S.get("bf16_of") is not None else {}
 
         bias_jobs: list = []                           # (cotangent, bias gradient) of every tensor-core layer: summed in ONE launch at the end
+        wg_scratch = ops.wgrad_scratch(S["out"].device) if (pg is not None and ops.WGRAD_SCRATCH and S["out"].is_cuda) else None
 
         def wgrad(name, inp, dy, x_offset=0):
             if pg is not None and (name + ".weight") in pg:
@@ -173,7 +174,7 @@ class _Stack:
                         bf16_of[key] = ops.half_to_bf16(inp)
                     inp = bf16_of[key]
                 ops.conv_backward_weight(sp[name], inp, dy, pg[name + ".weight"], pg.get(name + ".bias"), x_offset=x_offset, split=s3 and inp.dtype != torch.float32,
-                                         defer_bias=bias_jobs)
+                                         defer_bias=bias_jobs, scratch=wg_scratch)
 
         def packed_input():
             """[x | surf | 0] as one zero-padded 16-channel NHWC tensor in the gradient dtype: the X operand of the tensor-core
@@ -261,6 +262,8 @@ class _Stack:
             wgrad("skipConv1.0", S["skip_in"], dt1)
         if bias_jobs:
             ops.channel_sum_multi(bias_jobs)
+        if wg_scratch is not None:
+            wg_scratch.flush()
         return dx, dsurf, dskip
 
 
@@ -482,13 +485,16 @@ class _RefineFn(torch.autograd.Function):
         plist = [p for m in w for p in (m.weight, m.bias)]
         direct = [_flat_grad_view(p) for p in plist]
         grads = [p.grad if dflag else torch.zeros_like(p) for p, dflag in zip(plist, direct)]
-        ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7])
+        sc = ops.wgrad_scratch(g.device) if (ops.WGRAD_SCRATCH and g.is_cuda) else None      # one scatter launch for the four layers
+        ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7], scratch=sc)
         d3 = ops.conv_backward_data(_REFINE_SPECS[3], d4, w[3].weight, a3.shape[2:], mask=a3, mask_mode=MASK_POS, out_dtype=a3.dtype)
-        ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5])
+        ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5], scratch=sc)
         d2 = ops.conv_backward_data(_REFINE_SPECS[2], d3, w[2].weight, a2.shape[2:], mask=a2, mask_mode=MASK_POS)
-        ops.conv_backward_weight(_REFINE_SPECS[1], a1, d2, grads[2], grads[3])
+        ops.conv_backward_weight(_REFINE_SPECS[1], a1, d2, grads[2], grads[3], scratch=sc)
         d1 = ops.conv_backward_data(_REFINE_SPECS[1], d2, w[1].weight, a1.shape[2:], mask=a1, mask_mode=MASK_POS)
-        ops.conv_backward_weight(_REFINE_SPECS[0], gp if gp is not None else g, d1, grads[0], grads[1])
+        ops.conv_backward_weight(_REFINE_SPECS[0], gp if gp is not None else g, d1, grads[0], grads[1], scratch=sc)
+        if sc is not None:
+            sc.flush()
         dg = ops.conv_backward_data(_REFINE_SPECS[0], d1, w[0].weight, g.shape[2:], add=ds, out_dtype=torch.float32)      # + identity path
         ctx.saved = None
         return (None, dg[0]) + tuple(None if dflag else gr for gr, dflag in zip(grads, direct))

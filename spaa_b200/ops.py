@@ -556,6 +556,7 @@ def release_graph_pools() -> None:
 
 _packed_cache: Dict[tuple, Tensor] = {}
 TC_ENABLED = True          # tests flip this to compare the tensor-core path against the CUDA-core path
+WGRAD_SCRATCH = os.environ.get("SPAA_WGRAD_SCRATCH", "1") != "0"      # backward-weight flush through the scratch gradient (vector reductions)
 
 
 _weights_epoch = 0
@@ -788,8 +789,61 @@ def _dense_nhwc16(t: Tensor, np_: int = 1) -> bool:
 _SPLIT_WGRAD_PARTS = ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0))        # (x part, dy part) of the six part products, smallest first
 
 
+class WgradScratch:
+    """Scratch gradients of the tensor-core backward-weight kernel (spaa_conv_wgrad_tc_scratch: layout [tap][X channel][DY channel], so that the
+    kernel's flush is 16-byte vector reductions) for the layers of one backward pass, and the ONE launch that adds them into the parameter gradients
+    (spaa_wgrad_scatter_multi, which also zeroes the scratch again).  One persistent zero-filled buffer per device, bump-allocated per pass."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.buf: Optional[Tensor] = None
+        self.old: list = []                 # outgrown buffers with pending jobs
+        self.off = 0
+        self.jobs: list = []
+
+    def take(self, n: int) -> Tensor:
+        n_al = (n + 63) // 64 * 64
+        if self.buf is None or self.off + n_al > self.buf.numel():
+            if self.buf is not None:
+                self.old.append(self.buf)
+            self.buf = torch.zeros(max(4 << 20, 2 * n_al, 2 * (self.buf.numel() if self.buf is not None else 0)), dtype=torch.float32, device=self.device)
+            self.off = 0
+        sl = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return sl
+
+    def add(self, scratch: Tensor, dw: Tensor, ntap: int, cx_real: int, cy: int, cy_real: int, w_ts: int, w_xs: int, w_ys: int) -> None:
+        self.jobs.append((scratch, dw, ntap, cx_real, cy, cy_real, w_ts, w_xs, w_ys))
+
+    def flush(self) -> None:
+        jobs, self.jobs = self.jobs, []
+        for i in range(0, len(jobs), 24):
+            part = jobs[i:i + 24]
+            n = len(part)
+            arr = lambda ct, k: (ct * n)(*[j[k] for j in part])
+            sc = (ctypes.c_void_p * n)(*[j[0].data_ptr() for j in part])
+            dws = (ctypes.c_void_p * n)(*[j[1].data_ptr() for j in part])
+            with torch.cuda.device(self.device):
+                lib().spaa_wgrad_scatter_multi(sc, dws, arr(ctypes.c_int32, 2), arr(ctypes.c_int32, 3), arr(ctypes.c_int32, 4), arr(ctypes.c_int32, 5),
+                                               arr(ctypes.c_int64, 6), arr(ctypes.c_int64, 7), arr(ctypes.c_int64, 8), n, _stream())
+            _count()
+        self.off = 0
+        self.old.clear()
+
+
+_wgrad_scratch: Dict[int, WgradScratch] = {}
+
+
+def wgrad_scratch(device) -> WgradScratch:
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _wgrad_scratch:
+        _wgrad_scratch[idx] = WgradScratch(torch.device("cuda", idx))
+    return _wgrad_scratch[idx]
+
+
 def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: Optional[Tensor], *, x_offset: int = 0, split: bool = False,
-                         defer_bias: Optional[list] = None) -> None:
+                         defer_bias: Optional[list] = None, scratch: Optional[WgradScratch] = None) -> None:
     """dw += d(loss)/d(weight), db += d(loss)/d(bias); dw/db are fp32 accumulators in the parameter's own layout.
     16-bit dense NHWC operands go to the tcgen05 backward-weight kernel; `x` / `dy` may then be zero-padded to 16 channels
     (the layer's real input channels sit at [x_offset, x_offset + spec.cin) of `x`, the real output channels at [0, spec.cout) of `dy`).
@@ -821,16 +875,31 @@ def conv_backward_weight(spec: ConvSpec, x: Tensor, dy: Tensor, dw: Tensor, db: 
         _fill_desc(d, dy, x, None, None, split)
         gathered, pointwise, g_real, g_off, p_real = dy, x, spec.cout, 0, spec.cin
     if use_tc and L.spaa_conv_wgrad_tc_supported(ctypes.byref(d)) == 1:
+        # the kernel's final flush: into the parameter gradient with scalar atomics, or -- the training loops pass `scratch` -- into a scratch gradient
+        # with the DY channel contiguous (vector reductions), added to `dw` by scratch.flush() once per backward pass; WGRAD_SCRATCH = False: always direct
+        own = None
+        if scratch is None and WGRAD_SCRATCH:
+            scratch = own = wgrad_scratch(dw.device)
+        if not WGRAD_SCRATCH:
+            scratch = None
+        sc = None
+        if scratch is not None:
+            sc = scratch.take(spec.k * spec.k * g_real * d.Cout)
+            scratch.add(sc, dw, spec.k * spec.k, g_real, d.Cout, p_real, d.w_ts, d.w_cis, d.w_cos)
+        fn = L.spaa_conv_wgrad_tc if sc is None else L.spaa_conv_wgrad_tc_scratch
+        dst = _p(dw) if sc is None else _p(sc)
         with _Probe("bwd_weight_tc", spec):
             if split:
                 cg, cp = gathered.shape[1] // 3, pointwise.shape[1] // 3
                 for pg_, pp_ in _SPLIT_WGRAD_PARTS:
-                    L.spaa_conv_wgrad_tc(ctypes.byref(d), ctypes.c_void_p(gathered.data_ptr() + pg_ * cg * 2), ctypes.c_void_p(pointwise.data_ptr() + pp_ * cp * 2),
-                                         _p(dw), g_real, g_off, p_real, _stream())
+                    fn(ctypes.byref(d), ctypes.c_void_p(gathered.data_ptr() + pg_ * cg * 2), ctypes.c_void_p(pointwise.data_ptr() + pp_ * cp * 2),
+                       dst, g_real, g_off, p_real, _stream())
                     _count()
             else:
-                L.spaa_conv_wgrad_tc(ctypes.byref(d), _p(gathered), _p(pointwise), _p(dw), g_real, g_off, p_real, _stream())
+                fn(ctypes.byref(d), _p(gathered), _p(pointwise), dst, g_real, g_off, p_real, _stream())
                 _count()
+        if own is not None:
+            own.flush()                      # stand-alone call: add it into dw right away
         if db is not None:
             if split:
                 # bias gradient = sum over pixels of dy = of its three parts (real channels at [0, spec.cout) of each part)
