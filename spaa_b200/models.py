@@ -486,13 +486,20 @@ class _RefineFn(torch.autograd.Function):
         direct = [_flat_grad_view(p) for p in plist]
         grads = [p.grad if dflag else torch.zeros_like(p) for p, dflag in zip(plist, direct)]
         sc = ops.wgrad_scratch(g.device) if (ops.WGRAD_SCRATCH and g.is_cuda) else None      # one scatter launch for the four layers
-        ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7], scratch=sc)
+        bias_jobs: list = []
+        if gp is not None and a3.dtype == torch.bfloat16:
+            # tensor-core training: the last layer's 2-channel cotangent goes to the tcgen05 kernels too, zero-padded to 16 bf16 NHWC channels like the
+            # gradients of the three inner layers (on CUDA cores its backward-weight alone was 71 us of a 3.0 ms step)
+            d4 = ops.pack_nhwc16(d4, None, torch.bfloat16)
+        ops.conv_backward_weight(_REFINE_SPECS[3], a3, d4, grads[6], grads[7], scratch=sc, defer_bias=bias_jobs)
         d3 = ops.conv_backward_data(_REFINE_SPECS[3], d4, w[3].weight, a3.shape[2:], mask=a3, mask_mode=MASK_POS, out_dtype=a3.dtype)
-        ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5], scratch=sc)
+        ops.conv_backward_weight(_REFINE_SPECS[2], a2, d3, grads[4], grads[5], scratch=sc, defer_bias=bias_jobs)
         d2 = ops.conv_backward_data(_REFINE_SPECS[2], d3, w[2].weight, a2.shape[2:], mask=a2, mask_mode=MASK_POS)
-        ops.conv_backward_weight(_REFINE_SPECS[1], a1, d2, grads[2], grads[3], scratch=sc)
+        ops.conv_backward_weight(_REFINE_SPECS[1], a1, d2, grads[2], grads[3], scratch=sc, defer_bias=bias_jobs)
         d1 = ops.conv_backward_data(_REFINE_SPECS[1], d2, w[1].weight, a1.shape[2:], mask=a1, mask_mode=MASK_POS)
-        ops.conv_backward_weight(_REFINE_SPECS[0], gp if gp is not None else g, d1, grads[0], grads[1], scratch=sc)
+        ops.conv_backward_weight(_REFINE_SPECS[0], gp if gp is not None else g, d1, grads[0], grads[1], scratch=sc, defer_bias=bias_jobs)
+        if bias_jobs:
+            ops.channel_sum_multi(bias_jobs)
         if sc is not None:
             sc.flush()
         dg = ops.conv_backward_data(_REFINE_SPECS[0], d1, w[0].weight, g.shape[2:], add=ds, out_dtype=torch.float32)      # + identity path
