@@ -1,20 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2_final6_tests.log 2>&1
-tail -3 gpurun_out/r2_final6_tests.log | cut -c1-300
-python __graft_entry__.py smoke > gpurun_out/r2_final6_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/r2_final6_smoke.log | cut -c1-300
-( time python bench.py --steps 20 --warmup 5 > gpurun_out/r2_final6_bench.json 2> gpurun_out/r2_final6_bench.err ) 2> gpurun_out/r2_final6_bench.time; echo "bench rc=$?"
-tail -2 gpurun_out/r2_final6_bench.err | cut -c1-300
-( time python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_final6_ref.json 2> gpurun_out/r2_final6_ref.err ) 2> gpurun_out/r2_final6_ref.time; echo "ref rc=$?"
-python tools/train_probe.py fp16 > gpurun_out/train_probe_final.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/r2_final6_multi.log 2>&1
+tail -2 gpurun_out/r2_final6_multi.log | cut -c1-300
+python bench.py --steps 20 --warmup 5 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-cold > gpurun_out/r2_final6_1gpu.json 2> gpurun_out/r2_final6_1gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_final6_2gpu.json 2> gpurun_out/r2_final6_2gpu.err; echo "bench2 rc=$?"
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2_final6_bench.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches','dtype') if k in d}); print('e2e',d['e2e']['value']); print('roofline',d['roofline']['achieved'], d['roofline']['frac'], d['roofline'].get('frac_of_sustained_peak')); print('train',d['train']['value'],d['train'].get('phases'), d['train'].get('bf16_mode'), d['train'].get('bf16x3_mode'), d['train'].get('fp32_mode'))
-print('clocks',d.get('clocks'))
-for k in ('bf16x3_mode','fp32_mode','stock_classifier','e2e_cold','torch_cuda_reference','sweep'):
-    if k in d: print(k, str(d[k])[:200])
-print('percal', d['percal']['vgg16']['value'], d['percal']['vgg16']['torch_cuda_reference']['value'], d['percal']['inception_v3']['value'], d['percal']['inception_v3']['torch_cuda_reference']['value'])
-print('train ref', str(d['train'].get('torch_cuda_reference'))[:120], 'exact', d['torch_cuda_reference'].get('exact_fp32',{}).get('value'))
-r=json.loads(open('gpurun_out/r2_final6_ref.json').read().strip().splitlines()[-1]); print('ref', r['value'])
+a=json.loads(open('gpurun_out/r2_final6_1gpu.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/r2_final6_2gpu.json').read().strip().splitlines()[-1])
+print('1gpu', a['value'], a['train']['value'], a['train']['phases'])
+print('2gpu', d['value'], d['e2e']['value'], d['train']['value'], d['train']['phases'], d['train'].get('strong'))
+print('eff attack', d['value']/2/a['value'], 'train', d['train']['value']/2/a['train']['value'])
+print('sweep', str(d.get('sweep'))[:200])
 PY
