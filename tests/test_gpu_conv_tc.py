@@ -486,3 +486,41 @@ def test_tc_forward_bf16_copy_of_fp16_output(case):
     d = (c.float() - got.float()).abs()
     assert (d <= got.float().abs() * (2.0 ** -8) + 1e-7).all(), d.max().item()
     assert torch.equal(c == 0, got == 0) or ((c == 0) != (got == 0)).sum().item() <= 2      # (values below the fp16 subnormal range)
+
+
+def test_tc_backward_weight_scratch_flush_matches_direct_flush(monkeypatch):
+    """The two flushes of the backward-weight kernel -- scalar atomics straight into the parameter gradient, or vector reductions into the
+    [tap][X channel][DY channel] scratch + ONE scatter launch for several layers (ops.WgradScratch) -- accumulate the same sums: a conv, a transposed
+    conv and a zero-padded layer share one scratch and one flush here; the scratch is zero again afterwards."""
+    from spaa_b200 import ops
+    B = 2
+    layers = [(ops.ConvSpec("conv", 64, 128, 3, 1, 1), 64, 128, 12, 20, 0, None), (ops.ConvSpec("convT", 64, 32, 2, 2, 0), 64, 32, 9, 11, 0, None),
+              (ops.ConvSpec("conv", 6, 32, 3, 2, 1), 16, 32, 14, 18, 3, 6)]
+    tensors = []
+    for n, (spec, cx, cy, H, W, xoff, real) in enumerate(layers):
+        x = torch.zeros(B, cx, H, W)
+        x[:, xoff:xoff + (real or cx)] = synth.randn(60 + n, "sf.x", (B, real or cx, H, W))
+        Ho, Wo = spec.out_hw(H, W)
+        dy = synth.randn(70 + n, "sf.dy", (B, cy, Ho, Wo))
+        tensors.append((cl(x), cl(dy)))
+    monkeypatch.setattr(ops, "WGRAD_SCRATCH", False)
+    direct = []
+    for (spec, *_r, xoff, real), (x, dy) in zip(layers, tensors):
+        dw = torch.full(spec.weight_shape(), 0.25, device="cuda:0")
+        ops.conv_backward_weight(spec, x, dy, dw, None, x_offset=xoff)
+        direct.append(dw)
+    monkeypatch.setattr(ops, "WGRAD_SCRATCH", True)
+    sc = ops.wgrad_scratch("cuda:0")
+    got = []
+    n0 = ops.launch_count()
+    for (spec, *_r, xoff, real), (x, dy) in zip(layers, tensors):
+        dw = torch.full(spec.weight_shape(), 0.25, device="cuda:0")
+        ops.conv_backward_weight(spec, x, dy, dw, None, x_offset=xoff, scratch=sc)
+        got.append(dw)
+    assert all((g == 0.25).all() for g in got), "nothing reaches the parameter gradients before the flush"
+    sc.flush()
+    assert ops.launch_count() == n0 + len(layers) + 1, "one kernel per layer + ONE scatter launch"
+    for a, b in zip(direct, got):
+        tol = 1e-5 * max(1.0, a.abs().max().item())                 # same products, different summation order of the fp32 reductions
+        assert (a - b).abs().max().item() <= tol, (a - b).abs().max().item()
+    assert sc.buf is not None and not sc.buf.any().item(), "the scatter launch leaves the scratch zero-filled for the next pass"

@@ -1,15 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/r2_final6_multi.log 2>&1
-tail -2 gpurun_out/r2_final6_multi.log | cut -c1-300
-python bench.py --steps 20 --warmup 5 --skip-sweep --skip-cpu-baseline --skip-side-legs --skip-cold > gpurun_out/r2_final6_1gpu.json 2> gpurun_out/r2_final6_1gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_final6_2gpu.json 2> gpurun_out/r2_final6_2gpu.err; echo "bench2 rc=$?"
-python - <<'PY'
-import json
-a=json.loads(open('gpurun_out/r2_final6_1gpu.json').read().strip().splitlines()[-1])
-d=json.loads(open('gpurun_out/r2_final6_2gpu.json').read().strip().splitlines()[-1])
-print('1gpu', a['value'], a['train']['value'], a['train']['phases'])
-print('2gpu', d['value'], d['e2e']['value'], d['train']['value'], d['train']['phases'], d['train'].get('strong'))
-print('eff attack', d['value']/2/a['value'], 'train', d['train']['value']/2/a['train']['value'])
-print('sweep', str(d.get('sweep'))[:200])
-PY
+timeout 900 python -m pytest tests/test_gpu_conv_tc.py -x -q -m gpu -k "scratch or backward_weight" > gpurun_out/r2_sf_t1.log 2>&1
+tail -8 gpurun_out/r2_sf_t1.log | cut -c1-300
