@@ -17,7 +17,8 @@ struct GridParams {
 
 // Backward: every thread owns pixels, accumulates the 6 + 2(T+2) parameter gradients privately in a
 // round-robin over shared-memory reductions, block partials go to the workspace and the last block sums them.
-__global__ void __launch_bounds__(kThreads) coarse_grid_bwd_kernel(const float* __restrict__ aff, GridParams gp, const float* __restrict__ theta, const float* __restrict__ ctrl,
+template <int TT>       // accumulator capacity: control points <= TT (36 = the reference's 6 x 6 grid: ~110 registers, two blocks per SM; kMaxT otherwise)
+__global__ void __launch_bounds__(kThreads, TT <= 36 ? 2 : 1) coarse_grid_bwd_kernel(const float* __restrict__ aff, GridParams gp, const float* __restrict__ theta, const float* __restrict__ ctrl,
                                                                     const float* __restrict__ dgrid, float* __restrict__ daff,
                                                                     float* __restrict__ dtheta, float* __restrict__ partial,
                                                                     unsigned* __restrict__ counter) {
@@ -39,9 +40,9 @@ __global__ void __launch_bounds__(kThreads) coarse_grid_bwd_kernel(const float* 
     // version reduced every quantity across the warp for every 32 pixels -- 82 shuffle trees and as many shared-memory atomics per iteration: 68 us for
     // 76 800 pixels, latency bound, 2 % of a training step.)
     float da_acc[6] = {0, 0, 0, 0, 0, 0};
-    float ax[kMaxT + 2], ay[kMaxT + 2];            // theta gradient: rows 0..T-2 = TPS weights, rows T-1..T+1 = its affine part [1, x, y]
+    float ax[TT + 2], ay[TT + 2];            // theta gradient: rows 0..T-2 = TPS weights, rows T-1..T+1 = its affine part [1, x, y]
 #pragma unroll
-    for (int t = 0; t < kMaxT + 2; ++t) { ax[t] = 0.f; ay[t] = 0.f; }
+    for (int t = 0; t < TT + 2; ++t) { ax[t] = 0.f; ay[t] = 0.f; }
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
         float da[6] = {0, 0, 0, 0, 0, 0}, dzx = 0.f, dzy = 0.f;
         const int y = p / gp.W, x = p - y * gp.W;
@@ -57,13 +58,13 @@ __global__ void __launch_bounds__(kThreads) coarse_grid_bwd_kernel(const float* 
         }
         const float u0 = warp::tps_u<float>(px - s_ctrl[0], py - s_ctrl[1]);
 #pragma unroll
-        for (int t = 1; t < kMaxT; ++t) {
+        for (int t = 1; t < TT; ++t) {
             if (t < gp.T) {
                 const float u = warp::tps_u<float>(px - s_ctrl[2 * t], py - s_ctrl[2 * t + 1]) - u0;
                 ax[t - 1] += u * dzx; ay[t - 1] += u * dzy;
             }
         }
-        ax[kMaxT - 1] += dzx; ay[kMaxT - 1] += dzy; ax[kMaxT] += dzx * px; ay[kMaxT] += dzy * px; ax[kMaxT + 1] += dzx * py; ay[kMaxT + 1] += dzy * py;
+        ax[TT - 1] += dzx; ay[TT - 1] += dzy; ax[TT] += dzx * px; ay[TT] += dzy * px; ax[TT + 1] += dzx * py; ay[TT + 1] += dzy * py;
     }
     if (has_aff) {
 #pragma unroll
@@ -74,10 +75,10 @@ __global__ void __launch_bounds__(kThreads) coarse_grid_bwd_kernel(const float* 
     }
     float* acc_t = s_acc + 6;
 #pragma unroll
-    for (int t = 0; t < kMaxT + 2; ++t) {
-        // register slot t -> row of theta: TPS weights 0..T-2 stay, the affine slots kMaxT-1 .. kMaxT+1 are rows T-1 .. T+1
-        const int row = t < kMaxT - 1 ? t : gp.T - 1 + (t - (kMaxT - 1));
-        if (t < kMaxT - 1 && t >= gp.T - 1) continue;
+    for (int t = 0; t < TT + 2; ++t) {
+        // register slot t -> row of theta: TPS weights 0..T-2 stay, the affine slots TT-1 .. TT+1 are rows T-1 .. T+1
+        const int row = t < TT - 1 ? t : gp.T - 1 + (t - (TT - 1));
+        if (t < TT - 1 && t >= gp.T - 1) continue;
         const float vx = warp_sum(ax[t]), vy = warp_sum(ay[t]);
         if (lane == 0) { atomicAdd(acc_t + 2 * row, vx); atomicAdd(acc_t + 2 * row + 1, vy); }
     }
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kThreads) coarse_grid_bwd_kernel(const float* 
     }
 }
 
-constexpr int kGridBwdBlocks = 148;
+constexpr int kGridBwdBlocks = 296;        // two blocks per SM (coarse_grid_bwd_kernel<36>)
 
 __global__ void __launch_bounds__(kThreads) grid_finish_fwd_kernel(const float* __restrict__ coarse, const float* __restrict__ refine,
                                                                     float* __restrict__ fine, int64_t n) {
@@ -484,7 +485,8 @@ int spaa_coarse_grid_bwd(const float* affine, const float* theta, const float* c
     GridParams gp{T, Hin, Win, H, W};
     float* partial = (float*)ws;
     unsigned* counter = (unsigned*)(partial + (int64_t)kGridBwdBlocks * (6 + (T + 2) * 2));
-    coarse_grid_bwd_kernel<<<kGridBwdBlocks, kThreads, 0, (cudaStream_t)stream>>>(affine, gp, theta, ctrl, dgrid, daffine, dtheta, partial, counter);
+    if (T <= 36) coarse_grid_bwd_kernel<36><<<kGridBwdBlocks, kThreads, 0, (cudaStream_t)stream>>>(affine, gp, theta, ctrl, dgrid, daffine, dtheta, partial, counter);
+    else coarse_grid_bwd_kernel<kMaxT><<<kGridBwdBlocks, kThreads, 0, (cudaStream_t)stream>>>(affine, gp, theta, ctrl, dgrid, daffine, dtheta, partial, counter);
     SPAA_CHECK_LAUNCH("spaa_coarse_grid_bwd");
     return SPAA_OK;
 }
