@@ -522,12 +522,14 @@ _graph_pools: Dict[int, object] = {}
 
 
 def graph_pool(device) -> Optional[object]:
-    """One CUDA-graph memory pool per device, shared by the attack engines' captures (`CUDAGraph.capture_begin(pool=...)`).  A capture with a pool of
-    its own takes every per-iteration activation (~2 GB at B = 32) from fresh cudaMalloc segments -- measured 120 ms .. 1.7 s per capture, more than
-    the 50 iterations of the attack it serves; with the shared pool the second and later captures reuse the blocks earlier captures released.
-    The usual rule for shared pools applies: graphs are replayed on one stream, never concurrently, and a tensor PRODUCED by a replay is read before
-    another engine replays (the engines copy their results into persistent buffers inside the graph).  $SPAA_GRAPH_POOL=0: private pools."""
-    if os.environ.get("SPAA_GRAPH_POOL", "1") == "0":
+    """OPT-IN ($SPAA_GRAPH_POOL=1; default: every graph has its own pool): one CUDA-graph memory pool per device, shared by the captures of the attack
+    engines (`CUDAGraph.capture_begin(pool=...)`).  Measured both ways on B200: the FIRST spaa() call of a process took 0.66-0.67 s with it and
+    1.1-3.6 s without (a capture with a pool of its own takes its ~1.4 GB of per-iteration activations from fresh cudaMalloc segments), but the blocks of
+    a destroyed graph are not handed to the next capture either way (tools/capture_probe.py: +1.4 GB reserved per engine), so with the pool kept alive
+    they pile up until release_graph_pools(), and PerC-AL -- one short-lived graph per call -- ran at HALF speed with it (inception_v3: 26.7 vs 54.3
+    it/s).  Hence off by default.  The usual rule for shared pools applies: graphs are replayed on one stream, never concurrently, and a tensor PRODUCED
+    by a replay is read before another engine replays."""
+    if os.environ.get("SPAA_GRAPH_POOL", "0") == "0":
         return None
     idx = torch.device(device).index
     idx = torch.cuda.current_device() if idx is None else idx
