@@ -180,7 +180,8 @@ class _Stack:
         # optimiser), while the backward-data chain is strictly sequential: forked, the tail of every persistent kernel (CTAs that ran out of tiles, the
         # accumulator flush of the backward-weight kernel) overlaps with the other chain's kernels -- measured 8 750 -> 8 965 img/s at batch 24, same
         # job.  Joined before this function returns (the data-parallel gradient exchange starts there); works inside the captured step (fork / join).
-        side = _side_stream(S["out"].device) if (pg is not None and S["out"].is_cuda and os.environ.get("SPAA_WGRAD_STREAM", "1") != "0") else None
+        # (not in the split-precision mode: both chains are MMA-bound there and only slow each other down -- 1 483 img/s on one stream, 1 400 on two)
+        side = _side_stream(S["out"].device) if (pg is not None and S["out"].is_cuda and not s3 and os.environ.get("SPAA_WGRAD_STREAM", "1") != "0") else None
 
         def wgrad(name, inp, dy, x_offset=0):
             if side is not None:
