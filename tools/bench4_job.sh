@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 20 --warmup 5 --skip-cpu-baseline --skip-side-legs --skip-cold > gpurun_out/r2_final9_4gpu.json 2> gpurun_out/r2_final9_4gpu.err; echo "bench4 rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_final9_4gpu.json').read().strip().splitlines()[-1])
+print('4gpu', d['value'], d['e2e']['value'], d['train']['value'], d['train']['phases'], d['train'].get('strong',{}).get('img_per_s'), str(d.get('sweep'))[:200])
+PY
