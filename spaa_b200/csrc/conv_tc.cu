@@ -17,6 +17,11 @@
 // quadrant -> bias / residual add / ReLU / ReLU-mask of the backward pass -> bf16 -> global).  smem ring of NSTAGES
 // {A,B} stages with full/empty mbarriers; TWO accumulators in TMEM (2 x Cout columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.
+//
+// That paragraph describes conv_tc_kernel, the first version (one TMA box per tap), kept as the fallback.  The product path is
+// conv_halo_kernel further down: ONE halo box per tile whose taps are row-shifted descriptor views; weights resident in shared memory or
+// streamed through their own ring; 1-4 accumulator buffers and 1-4 epilogue groups per CTA; two epilogues (the round-1 one for the wide layers
+// and the split-precision mode, epilogue_nhwc16 with TMA tile stores for the narrow ones); halo_plan() picks the shape of every launch.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "../../include/spaa_b200.h"
