@@ -8,15 +8,17 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _plans():
+def _plans(batch=None, hw=None, variant="shading"):
     spec = importlib.util.spec_from_file_location("plan_table", os.path.join(ROOT, "tools", "plan_table.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    return m.layer_plans()
+    return m.layer_plans(batch, hw, variant)
 
 
-def test_every_layer_has_a_plan_within_the_sm_limits():
-    rows, names = _plans()
+@pytest.mark.parametrize("batch,hw,variant", [(32, (240, 320), "shading"), (24, (240, 320), "shading"), (1, (240, 320), "shading"), (100, (240, 320), "shading"),
+                                              (32, (256, 256), "compen"), (8, (64, 96), "shading")])
+def test_every_layer_has_a_plan_within_the_sm_limits(batch, hw, variant):
+    rows, names = _plans(batch, hw, variant)
     assert len(rows) == 27
     for layer, p in rows:
         assert p is not None, f"{layer}: not covered by the halo kernel"

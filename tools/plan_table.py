@@ -56,37 +56,43 @@ def bwd(spec, cout_t, hin, win, add=False, mask=False, mask2=False, planar=False
     return plan(d, add, mask, mask2)
 
 
-def layer_plans():
-    """[(layer, plan or None)] for the 27 tensor-core launches of one ShadingNetSPAA forward + backward-data pass."""
-    sp = _stack_specs("shading", 6)
+def layer_plans(batch=None, hw=None, variant="shading"):
+    """[(layer, plan or None)] for the 27 tensor-core launches of one ShadingNetSPAA (variant 'shading') / CompenNet ('compen') forward +
+    backward-data pass at `batch` images of `hw` pixels (default: the BASELINE attack shapes, 32 x 240 x 320)."""
+    global B, H, W
+    if batch is not None:
+        B = batch
+    if hw is not None:
+        H, W = hw
+    sp = _stack_specs(variant, 6)
     rows = []
     names = "ctas eg nbuf sa sb S dbuf pair smem tiles threads resident".split()
     r, _ = fwd(sp["conv1_s"], 16, H, W); rows.append(("conv1_s f", r))
-    r, _ = fwd(sp["conv2_s"], 32, 120, 160); rows.append(("conv2_s f", r))
-    r, _ = fwd(sp["conv3_s"], 64, 60, 80); rows.append(("conv3_s f", r))
-    r, _ = fwd(sp["conv4_s"], 128, 60, 80); rows.append(("conv4_s f", r))
+    r, _ = fwd(sp["conv2_s"], 32, H // 2, W // 2); rows.append(("conv2_s f", r))
+    r, _ = fwd(sp["conv3_s"], 64, H // 4, W // 4); rows.append(("conv3_s f", r))
+    r, _ = fwd(sp["conv4_s"], 128, H // 4, W // 4); rows.append(("conv4_s f", r))
     r, _ = fwd(sp["conv1"], 16, H, W, add=True); rows.append(("conv1 f", r))
-    r, _ = fwd(sp["skipConv2"], 32, 120, 160); rows.append(("skipConv2 f", r))
-    r, _ = fwd(sp["conv2"], 32, 120, 160, add=True); rows.append(("conv2 f", r))
-    r, _ = fwd(sp["skipConv3"], 64, 60, 80); rows.append(("skipConv3 f", r))
-    r, _ = fwd(sp["conv3"], 64, 60, 80, add=True); rows.append(("conv3 f", r))
-    r, _ = fwd(sp["conv4"], 128, 60, 80, add=True); rows.append(("conv4 f", r))
-    r, _ = fwd(sp["conv5"], 256, 60, 80, add=True); rows.append(("conv5 f", r))
-    r, _ = fwd(sp["transConv1"], 128, 60, 80, add=True); rows.append(("transConv1 f", r))
-    r, _ = fwd(sp["transConv2"], 64, 120, 160); rows.append(("transConv2 f", r))
+    r, _ = fwd(sp["skipConv2"], 32, H // 2, W // 2); rows.append(("skipConv2 f", r))
+    r, _ = fwd(sp["conv2"], 32, H // 2, W // 2, add=True); rows.append(("conv2 f", r))
+    r, _ = fwd(sp["skipConv3"], 64, H // 4, W // 4); rows.append(("skipConv3 f", r))
+    r, _ = fwd(sp["conv3"], 64, H // 4, W // 4, add=True); rows.append(("conv3 f", r))
+    r, _ = fwd(sp["conv4"], 128, H // 4, W // 4, add=True); rows.append(("conv4 f", r))
+    r, _ = fwd(sp["conv5"], 256, H // 4, W // 4, add=True); rows.append(("conv5 f", r))
+    r, _ = fwd(sp["transConv1"], 128, H // 4, W // 4, add=True); rows.append(("transConv1 f", r))
+    r, _ = fwd(sp["transConv2"], 64, H // 2, W // 2); rows.append(("transConv2 f", r))
     r, _ = fwd(sp["conv6"], 32, H, W, add=True, planar=True); rows.append(("conv6 f", r))
     rows.append(("conv6 b", bwd(sp["conv6"], 16, H, W, mask=True)))
-    rows.append(("transConv2 b", bwd(sp["transConv2"], 32, 120, 160, mask=True)))
-    rows.append(("transConv1 b", bwd(sp["transConv1"], 64, 60, 80, mask=True)))
-    rows.append(("conv5 b", bwd(sp["conv5"], 128, 60, 80, mask=True, mask2=True)))
-    rows.append(("conv4 b", bwd(sp["conv4"], 256, 60, 80, mask=True)))
-    rows.append(("conv3 b", bwd(sp["conv3"], 128, 60, 80)))
-    rows.append(("skipConv3 b", bwd(sp["skipConv3"], 128, 60, 80, add=True, mask=True)))
-    rows.append(("conv2 b", bwd(sp["conv2"], 64, 120, 160)))
-    rows.append(("skipConv2 b", bwd(sp["skipConv2"], 64, 120, 160, add=True, mask=True)))
+    rows.append(("transConv2 b", bwd(sp["transConv2"], 32, H // 2, W // 2, mask=True)))
+    rows.append(("transConv1 b", bwd(sp["transConv1"], 64, H // 4, W // 4, mask=True)))
+    rows.append(("conv5 b", bwd(sp["conv5"], 128, H // 4, W // 4, mask=True, mask2=True)))
+    rows.append(("conv4 b", bwd(sp["conv4"], 256, H // 4, W // 4, mask=True)))
+    rows.append(("conv3 b", bwd(sp["conv3"], 128, H // 4, W // 4)))
+    rows.append(("skipConv3 b", bwd(sp["skipConv3"], 128, H // 4, W // 4, add=True, mask=True)))
+    rows.append(("conv2 b", bwd(sp["conv2"], 64, H // 2, W // 2)))
+    rows.append(("skipConv2 b", bwd(sp["skipConv2"], 64, H // 2, W // 2, add=True, mask=True)))
     rows.append(("conv1 b", bwd(sp["conv1"], 32, H, W, planar=True, cin_out=3)))
-    rows.append(("conv3_s b", bwd(sp["conv3_s"], 128, 60, 80, add=True, mask=True)))
-    rows.append(("conv2_s b", bwd(sp["conv2_s"], 64, 120, 160, add=True, mask=True)))
+    rows.append(("conv3_s b", bwd(sp["conv3_s"], 128, H // 4, W // 4, add=True, mask=True)))
+    rows.append(("conv2_s b", bwd(sp["conv2_s"], 64, H // 2, W // 2, add=True, mask=True)))
     rows.append(("conv1_s b", bwd(sp["conv1_s"], 32, H, W, planar=True, cin_out=6)))
     return rows, names
 
